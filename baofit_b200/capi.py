@@ -1,0 +1,199 @@
+"""ctypes binding of the C ABI (include/baofit_b200.h) -- plumbing for tests and bench.py.
+
+Every call goes through libbaofit_b200.so; there is no Python or CPU implementation behind it.
+If the library is missing or no CUDA device is usable, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbaofit_b200.so")
+_LIB = None
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+EXPORTS = [
+    "bf_last_error", "bf_version", "bf_ctx_create", "bf_ctx_destroy", "bf_ctx_launch_count",
+    "bf_ctx_synchronize", "bf_ctx_stream", "bf_model_create", "bf_model_destroy", "bf_model_npar",
+    "bf_data_create", "bf_data_destroy", "bf_data_ndata", "bf_eval_batch", "bf_chi2_batch",
+    "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
+    "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
+]
+
+
+class BaofitError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("[%d] %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libbaofit_b200.so is not built: run python -c 'import __graft_entry__ as g; g.build()'")
+        L = C.CDLL(LIB_PATH)
+        L.bf_last_error.restype = C.c_char_p
+        L.bf_version.restype = C.c_char_p
+        L.bf_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.bf_ctx_destroy.argtypes = [C.c_void_p]
+        L.bf_ctx_launch_count.restype = C.c_longlong
+        L.bf_ctx_launch_count.argtypes = [C.c_void_p]
+        L.bf_ctx_synchronize.argtypes = [C.c_void_p]
+        L.bf_ctx_stream.restype = C.c_void_p
+        L.bf_ctx_stream.argtypes = [C.c_void_p]
+        L.bf_model_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bf_model_destroy.argtypes = [C.c_void_p]
+        L.bf_model_npar.argtypes = [C.c_void_p]
+        L.bf_data_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bf_data_destroy.argtypes = [C.c_void_p]
+        L.bf_data_ndata.argtypes = [C.c_void_p]
+        L.bf_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.bf_chi2_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bf_eval_batch_dev.argtypes = L.bf_eval_batch.argtypes
+        L.bf_chi2_batch_dev.argtypes = L.bf_chi2_batch.argtypes
+        L.bf_eval_undistorted_batch.argtypes = L.bf_eval_batch.argtypes
+        L.bf_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+        L.bf_model_transform_nr.argtypes = [C.c_void_p]
+        L.bf_model_transform_r0.restype = C.c_double
+        L.bf_model_transform_r0.argtypes = [C.c_void_p]
+        L.bf_model_transform_dr.restype = C.c_double
+        L.bf_model_transform_dr.argtypes = [C.c_void_p]
+        L.bf_sample_toys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int,
+                                     C.c_double, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise BaofitError(rc, lib().bf_last_error().decode())
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().bf_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bf_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def launches(self):
+        return lib().bf_ctx_launch_count(self.h)
+
+    def synchronize(self):
+        _check(lib().bf_ctx_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib().bf_ctx_stream(self.h)
+
+
+class Model:
+    def __init__(self, ctx, model):
+        """model: workloads.Model (descriptor + bookkeeping)"""
+        self.ctx, self.src = ctx, model
+        h = C.c_void_p()
+        _check(lib().bf_model_create(ctx.h, C.addressof(model.desc), C.byref(h)))
+        self.h = h
+        self.npar = lib().bf_model_npar(h)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            lib().bf_model_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def transform(self, params, z_trigger):
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, self.npar)
+        B = p.shape[0]
+        nr = lib().bf_model_transform_nr(self.h)
+        out = np.zeros((2, 3, nr, B))
+        _check(lib().bf_transform_batch(self.ctx.h, self.h, _ptr(p), B, float(z_trigger), _ptr(out), B))
+        r = lib().bf_model_transform_r0(self.h) + lib().bf_model_transform_dr(self.h) * np.arange(nr)
+        return r, out
+
+
+class Data:
+    def __init__(self, ctx, data):
+        """data: workloads.Data"""
+        self.ctx, self.src = ctx, data
+        h = C.c_void_p()
+        _check(lib().bf_data_create(ctx.h, C.addressof(data.desc), C.byref(h)))
+        self.h = h
+        self.n = lib().bf_data_ndata(h)
+        self.n_grid = data.desc.n_grid
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            lib().bf_data_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def sample_toys(self, truth, seed, first_toy, ntoy, scale=1.0):
+        t = np.ascontiguousarray(truth, dtype=np.float64)
+        out = np.zeros((ntoy, self.n))
+        _check(lib().bf_sample_toys(self.ctx.h, self.h, _ptr(t), seed, first_toy, ntoy, scale, _ptr(out)))
+        return out
+
+
+def eval_batch(ctx, model, data, params):
+    """pred[n_data, B], status[B] -- CorrelationFitter::getPrediction for B vectors."""
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, model.npar)
+    B = p.shape[0]
+    pred = np.zeros((data.n, B))
+    status = np.zeros(B, dtype=np.int32)
+    _check(lib().bf_eval_batch(ctx.h, model.h, data.h, _ptr(p), B, _ptr(pred), B, _ptr(status)))
+    return pred, status
+
+
+def eval_undistorted_batch(ctx, model, data, params):
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, model.npar)
+    B = p.shape[0]
+    xiu = np.zeros((data.n_grid, B))
+    status = np.zeros(B, dtype=np.int32)
+    _check(lib().bf_eval_undistorted_batch(ctx.h, model.h, data.h, _ptr(p), B, _ptr(xiu), B, _ptr(status)))
+    return xiu, status
+
+
+def chi2_batch(ctx, model, data, params, data_override=None):
+    """chi2[B], status[B] -- BinnedData::chiSquare(getPrediction(p_b))."""
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, model.npar)
+    B = p.shape[0]
+    ov = None
+    if data_override is not None:
+        ov = np.ascontiguousarray(data_override, dtype=np.float64)
+        assert ov.shape == (B, data.n)
+    chi2 = np.zeros(B)
+    status = np.zeros(B, dtype=np.int32)
+    _check(lib().bf_chi2_batch(ctx.h, model.h, data.h, _ptr(p), B, _ptr(ov), _ptr(chi2), _ptr(status)))
+    return chi2, status
+
+
+def chi2_batch_dev(ctx, model, data, d_params_ptr, B, d_chi2_ptr, d_status_ptr=None, d_override_ptr=None):
+    """Device-pointer variant (raw addresses as ints); asynchronous on the context's stream."""
+    _check(lib().bf_chi2_batch_dev(ctx.h, model.h, data.h, C.c_void_p(d_params_ptr), B,
+                                   C.c_void_p(d_override_ptr) if d_override_ptr else None,
+                                   C.c_void_p(d_chi2_ptr), C.c_void_p(d_status_ptr) if d_status_ptr else None))
+
+
+def chi2_batch_raw(ctx, model, data, params_ptr, B, chi2_ptr, status_ptr=None):
+    """Host-buffer entry point on raw addresses (e.g. pinned torch tensors)."""
+    _check(lib().bf_chi2_batch(ctx.h, model.h, data.h, C.c_void_p(params_ptr), B, None, C.c_void_p(chi2_ptr),
+                               C.c_void_p(status_ptr) if status_ptr else None))

@@ -1,0 +1,811 @@
+// C ABI of libbaofit_b200.so (include/baofit_b200.h): object lifetime, one-time setup, and the
+// per-batch kernel pipelines. No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "host_setup.h"
+#include "kernels.h"
+
+namespace bf {
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+}  // namespace bf
+
+using namespace bf;
+
+#define BF_FAIL(code, msg)  \
+    do {                    \
+        bf::set_error(msg); \
+        return (code);      \
+    } while (0)
+
+extern "C" const char *bf_last_error(void) { return bf::g_error.c_str(); }
+extern "C" const char *bf_version(void) { return "baofit_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int bf_ctx_create(int device, bf_ctx **out) {
+    if (!out) BF_FAIL(BF_ERR_OPTIONS, "bf_ctx_create: null output pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                                     "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) BF_FAIL(BF_ERR_OPTIONS, "bf_ctx_create: invalid device index");
+    BF_CUDA_OK(cudaSetDevice(device));
+    bf_ctx *c = new bf_ctx();
+    c->device = device;
+    BF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    BF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return BF_OK;
+}
+
+extern "C" int bf_ctx_destroy(bf_ctx *c) {
+    if (!c) return BF_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->ws) cudaFree(c->ws);
+    if (c->io) cudaFree(c->io);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return BF_OK;
+}
+
+extern "C" long long bf_ctx_launch_count(const bf_ctx *c) { return c ? c->launches : 0; }
+extern "C" void *bf_ctx_stream(bf_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int bf_ctx_synchronize(bf_ctx *c) {
+    if (!c) BF_FAIL(BF_ERR_OPTIONS, "null context");
+    BF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+static int ensure(void **p, size_t *have, size_t need) {
+    if (*have >= need) return BF_OK;
+    if (*p) BF_CUDA_OK(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    size_t want = need + need / 8;
+    BF_CUDA_OK(cudaMalloc(p, want));
+    *have = want;
+    return BF_OK;
+}
+
+template <class T> static int upload(std::vector<void *> &owner, const T *host, size_t count, T **dev) {
+    *dev = nullptr;
+    if (count == 0) return BF_OK;
+    BF_CUDA_OK(cudaMalloc((void **)dev, count * sizeof(T)));
+    owner.push_back(*dev);
+    BF_CUDA_OK(cudaMemcpy(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+static void copy_bb(const bf_broadband_spec &s, DevBB &d) {
+    d.enabled = s.enabled; d.idx_base = s.idx_base;
+    d.r_min = s.r_min; d.r_max = s.r_max; d.r_step = s.r_step; d.r_denom = s.r_denom;
+    d.mu_min = s.mu_min; d.mu_max = s.mu_max; d.mu_step = s.mu_step;
+    d.rp_min = s.rp_min; d.rp_max = s.rp_max; d.rp_step = s.rp_step;
+    d.rt_min = s.rt_min; d.rt_max = s.rt_max; d.rt_step = s.rt_step;
+    d.z_min = s.z_min; d.z_max = s.z_max; d.z_step = s.z_step;
+    d.inv_r0 = s.enabled ? 1.0 / s.r0 : 0.0;
+    d.z0 = s.z0;
+}
+
+static int bb_ncoef(const bf_broadband_spec &s) {
+    auto cnt = [](int lo, int hi, int st) { return st > 0 && hi >= lo ? (hi - lo) / st + 1 : 0; };
+    return cnt(s.z_min, s.z_max, s.z_step) * cnt(s.mu_min, s.mu_max, s.mu_step) * cnt(s.r_min, s.r_max, s.r_step) *
+           cnt(s.rp_min, s.rp_max, s.rp_step) * cnt(s.rt_min, s.rt_max, s.rt_step);
+}
+
+static int make_spline_set(bf_model *m, int n, const double *x, const double *y0, const double *y2,
+                           const double *y4, DevSplineSet &out) {
+    if (n < 3 || !x || !y0 || !y2 || !y4) BF_FAIL(BF_ERR_MODEL, "BaoCorrelationModel: error while reading model interpolation data.");
+    for (int j = 0; j + 1 < n; ++j)
+        if (!(x[j + 1] > x[j])) BF_FAIL(BF_ERR_MODEL, "BaoCorrelationModel: interpolation knots must increase");
+    std::vector<double> coef((size_t)3 * (n - 1) * 4);
+    const double *ys[3] = {y0, y2, y4};
+    for (int l = 0; l < 3; ++l) {
+        cspline_interval_coefs(n, x, ys[l], coef.data() + (size_t)l * (n - 1) * 4);
+        out.ylo[l] = ys[l][0];
+        out.yhi[l] = ys[l][n - 1];
+    }
+    out.n = n;
+    out.x0 = x[0];
+    out.xlast = x[n - 1];
+    double dx = (x[n - 1] - x[0]) / (n - 1);
+    out.inv_dx = 1.0 / dx;
+    out.uniform = 1;
+    for (int j = 0; j < n; ++j)
+        if (std::fabs(x[j] - (x[0] + j * dx)) > 1e-9 * dx) out.uniform = 0;
+    double *dxp = nullptr, *dcoef = nullptr;
+    int rc = upload(m->allocs, x, n, &dxp);
+    if (rc) return rc;
+    rc = upload(m->allocs, coef.data(), coef.size(), &dcoef);
+    if (rc) return rc;
+    out.x = dxp;
+    out.coef = dcoef;
+    return BF_OK;
+}
+
+extern "C" int bf_model_destroy(bf_model *m) {
+    if (!m) return BF_OK;
+    cudaSetDevice(m->ctx->device);
+    for (void *p : m->allocs) cudaFree(p);
+    delete m;
+    return BF_OK;
+}
+
+extern "C" int bf_model_npar(const bf_model *m) { return m ? m->dev.npar : 0; }
+
+extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **out) {
+    if (!ctx || !d || !out) BF_FAIL(BF_ERR_OPTIONS, "bf_model_create: null argument");
+    if (d->kind != BF_MODEL_RSPACE && d->kind != BF_MODEL_KSPACE)
+        BF_FAIL(BF_ERR_MODEL, "bf_model_create: model kind not built (the FFT k-space model is not implemented yet)");
+    if (d->npar <= 0 || d->npar > 256) BF_FAIL(BF_ERR_MODEL, "bf_model_create: bad parameter count");
+    auto chk = [&](int idx, int span) { return idx >= 0 && idx + span <= d->npar; };
+    if (!chk(d->idx_beta, 1) || !chk(d->idx_bb, 1) || !chk(d->idx_gamma_bias, 1) || !chk(d->idx_gamma_beta, 1) ||
+        !chk(d->idx_bao, 5))
+        BF_FAIL(BF_ERR_MODEL, "AbsCorrelationModel: no linear bias parameters defined.");
+    const bool cross = d->flags & BF_FLAG_CROSS_CORRELATION;
+    if (cross && (!chk(d->idx_delta_v, 1) || !chk(d->idx_bias2, 1) || !chk(d->idx_bb2, 1)))
+        BF_FAIL(BF_ERR_MODEL, "bf_model_create: cross-correlation needs delta-v, bias2, beta2*bias2");
+    if ((d->flags & BF_FLAG_COMBINED_BIAS) && !chk(d->idx_beta_bias, 1)) BF_FAIL(BF_ERR_MODEL, "bf_model_create: combined-bias needs beta*bias");
+    if ((d->flags & BF_FLAG_COMBINED_SCALE) && !chk(d->idx_comb_scale, 1)) BF_FAIL(BF_ERR_MODEL, "bf_model_create: combined-scale needs BAO aperp/apar");
+    if (d->zref < 0) BF_FAIL(BF_ERR_MODEL, "AbsCorrelationModel: expected zref >= 0.");
+    if (d->omega_matter < 0) BF_FAIL(BF_ERR_MODEL, "AbsCorrelationModel: expected OmegaMatter >= 0.");
+    for (int s = 0; s < 4; ++s)
+        if (d->bb[s].enabled) {
+            const bf_broadband_spec &b = d->bb[s];
+            if (b.r_max < b.r_min || b.r_step <= 0 || b.r_denom <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal r-parameter specification.");
+            if (b.mu_max < b.mu_min || b.mu_step <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal mu-parameter specification.");
+            if (b.mu_min < 0 || b.mu_max > 8) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: only multipoles 0-8 are allowed in mu-parameter specification.");
+            if (b.rp_max < b.rp_min || b.rp_step <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal rP-parameter specification.");
+            if (b.rt_max < b.rt_min || b.rt_step <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal rT-parameter specification.");
+            if (b.z_max < b.z_min || b.z_step <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal z-parameter specification.");
+            if (!chk(b.idx_base, bb_ncoef(b))) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: coefficients outside the parameter vector");
+            if (!(b.r0 > 0)) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: expected r0 > 0");
+        }
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    bf_model *m = new bf_model();
+    m->ctx = ctx;
+    DevModel &dm = m->dev;
+    std::memset(&dm, 0, sizeof(dm));
+    dm.kind = d->kind; dm.flags = d->flags; dm.npar = d->npar; dm.zref = d->zref; dm.omega_matter = d->omega_matter;
+    dm.idx_beta = d->idx_beta; dm.idx_bb = d->idx_bb; dm.idx_gamma_bias = d->idx_gamma_bias;
+    dm.idx_gamma_beta = d->idx_gamma_beta; dm.idx_delta_v = cross ? d->idx_delta_v : -1; dm.idx_bias2 = d->idx_bias2;
+    dm.idx_bb2 = d->idx_bb2; dm.idx_beta_bias = (d->flags & BF_FLAG_COMBINED_BIAS) ? d->idx_beta_bias : -1;
+    dm.idx_bao = d->idx_bao; dm.idx_comb_scale = d->idx_comb_scale; dm.idx_rad = d->idx_rad; dm.idx_nl = d->idx_nl;
+    dm.idx_cont = d->idx_cont; dm.idx_bs = d->idx_bs; dm.idx_hcd = d->idx_hcd; dm.idx_uv = d->idx_uv;
+    dm.idx_smgaus = d->idx_smgaus; dm.idx_smlor = d->idx_smlor; dm.idx_nlcorr = d->idx_nlcorr;
+    for (int s = 0; s < 4; ++s) copy_bb(d->bb[s], dm.bb[s]);
+    m->zref = d->zref;
+    int rc = BF_OK;
+    auto fail = [&](int code) { bf_model_destroy(m); return code; };
+
+    if (d->kind == BF_MODEL_RSPACE) {
+        if (d->idx_rad >= 0 && !chk(d->idx_rad, 4)) { bf::set_error("bf_model_create: bad radiation block"); return fail(BF_ERR_MODEL); }
+        if ((rc = make_spline_set(m, d->n_fid, d->fid_r, d->fid_xi0, d->fid_xi2, d->fid_xi4, dm.fid))) return fail(rc);
+        if ((rc = make_spline_set(m, d->n_nw, d->nw_r, d->nw_xi0, d->nw_xi2, d->nw_xi4, dm.nw))) return fail(rc);
+    } else {
+        if (!chk(d->idx_nl, 2)) { bf::set_error("bf_model_create: k-space model needs SigmaNL-perp, 1+f"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & BF_FLAG_RADIATION_MODEL) && !chk(d->idx_rad, 4)) { bf::set_error("bf_model_create: bad radiation block"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & (BF_FLAG_BIN_SMOOTH | BF_FLAG_BIN_SMOOTH_ALT)) && !chk(d->idx_bs, 2)) { bf::set_error("bf_model_create: bad bin-smooth block"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & (BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT)) && !chk(d->idx_hcd, 3)) { bf::set_error("bf_model_create: bad HCD block"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & BF_FLAG_UVFLUCTUATION) && !chk(d->idx_uv, 3)) { bf::set_error("bf_model_create: bad UV block"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & BF_FLAG_SMOOTH_GAUSS) && !chk(d->idx_smgaus, 1)) { bf::set_error("bf_model_create: bad smooth-gauss block"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & BF_FLAG_SMOOTH_LORENTZ) && !chk(d->idx_smlor, 1)) { bf::set_error("bf_model_create: bad smooth-lorentz block"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & BF_FLAG_FIT_NL_CORRECTION) && !chk(d->idx_nlcorr, 2)) { bf::set_error("bf_model_create: bad nlcorr block"); return fail(BF_ERR_MODEL); }
+        // baofit/BaoKSpaceCorrelationModel.cc:156-159
+        if (d->rmin >= d->rmax) { bf::set_error("BaoKSpaceCorrelationModel: expected rmin < rmax."); return fail(BF_ERR_MODEL); }
+        if (d->rmin <= 0) { bf::set_error("BaoKSpaceCorrelationModel: expected rmin > 0."); return fail(BF_ERR_MODEL); }
+        if (d->dilmin > d->dilmax) { bf::set_error("BaoKSpaceCorrelationModel: expected dilmin <= dilmax."); return fail(BF_ERR_MODEL); }
+        if (d->dilmin <= 0) { bf::set_error("BaoKSpaceCorrelationModel: expected dilmin > 0."); return fail(BF_ERR_MODEL); }
+        if (d->n_pk < 8 || !d->pk_k || !d->pk_fid || !d->pk_nw || d->samples_per_decade < 1) {
+            bf::set_error("BaoKSpaceCorrelationModel: error while reading model interpolation data.");
+            return fail(BF_ERR_MODEL);
+        }
+        if (d->ell_max != 0 && d->ell_max != 2 && d->ell_max != 4) { bf::set_error("bf_model_create: ell-max must be 0, 2 or 4"); return fail(BF_ERR_MODEL); }
+        HankelSetup hs;
+        build_hankel_weights(d->n_pk, d->pk_k, d->pk_fid, d->pk_nw, d->rmin, d->rmax, d->dilmin, d->dilmax,
+                             d->samples_per_decade, kFineSub, hs);
+        if (hs.nr < 4 || hs.nk < 8) { bf::set_error("bf_model_create: k-space grids too small"); return fail(BF_ERR_MODEL); }
+        dm.nk = hs.nk; dm.nk_pad = round_up(hs.nk, kGemmBK); dm.nr = hs.nr; dm.nr_pad = round_up(hs.nr, kGemmBM);
+        dm.ell_max = d->ell_max; dm.tr_r0 = hs.r0; dm.tr_dr = hs.dr; dm.tr_inv_dr = 1.0 / hs.dr; dm.rlo = hs.rlo; dm.rhi = hs.rhi;
+        dm.dilmin = d->dilmin; dm.dilmax = d->dilmax; dm.zeff = d->zeff; dm.sigma8 = d->sigma8;
+        std::vector<double> wpad((size_t)6 * dm.nr_pad * dm.nk_pad, 0.0);
+        for (int t = 0; t < 6; ++t)
+            for (int j = 0; j < hs.nr; ++j)
+                std::memcpy(&wpad[((size_t)t * dm.nr_pad + j) * dm.nk_pad], &hs.weights[((size_t)t * hs.nr + j) * hs.nk],
+                            sizeof(double) * hs.nk);
+        double *p = nullptr;
+        if ((rc = upload(m->allocs, wpad.data(), wpad.size(), &p))) return fail(rc);
+        dm.hankel = p;
+        if ((rc = upload(m->allocs, hs.kc.data(), hs.kc.size(), &p))) return fail(rc);
+        dm.kc = p;
+        if ((rc = upload(m->allocs, hs.pk_kc.data(), hs.pk_kc.size(), &p))) return fail(rc);
+        dm.pk_kc = p;
+        gauss_legendre_01(kMuNodes, dm.mu_x, dm.mu_w);
+        // constant (h, 4h, h) tridiagonal factors of the natural spline on the radial nodes
+        int msz = hs.nr - 2;
+        std::vector<double> thw(msz, 0.0), thd(msz, 0.0);
+        double h = hs.dr, diag = 4.0 * h;
+        thd[0] = 1.0 / diag;
+        for (int i = 1; i < msz; ++i) {
+            double w = h / diag;
+            thw[i] = w;
+            diag = 4.0 * h - w * h;
+            thd[i] = 1.0 / diag;
+        }
+        if ((rc = upload(m->allocs, thw.data(), thw.size(), &p))) return fail(rc);
+        dm.th_w = p;
+        if ((rc = upload(m->allocs, thd.data(), thd.size(), &p))) return fail(rc);
+        dm.th_inv_diag = p;
+    }
+    // metals
+    dm.metal_kind = d->metal_kind;
+    dm.idx_metal = d->idx_metal;
+    if (d->metal_kind == BF_METAL_TOY) {
+        if (!chk(d->idx_metal, 5)) { bf::set_error("MetalCorrelationModel: bad toy parameter block"); return fail(BF_ERR_MODEL); }
+        if (cross) { bf::set_error("MetalCorrelationModel: illegal option for cross-correlation."); return fail(BF_ERR_MODEL); }
+    } else if (d->metal_kind == BF_METAL_AUTO_TABLE || d->metal_kind == BF_METAL_CROSS_BICUBIC) {
+        const bool mcross = d->metal_kind == BF_METAL_CROSS_BICUBIC;
+        // baofit/MetalCorrelationModel.cc:35-37
+        if (mcross != cross) { bf::set_error("MetalCorrelationModel: illegal option for cross-correlation."); return fail(BF_ERR_MODEL); }
+        if (d->metal_ncomb < 1 || d->metal_ncomb > 8 || d->metal_nmet < 2 || d->metal_nmet > 6 || !d->metal_p1 || !d->metal_p2 ||
+            !d->metal_zgrid || d->metal_ngrid < 1 || !chk(d->idx_metal, 2 * (d->metal_nmet - 1))) {
+            bf::set_error("MetalCorrelationModel: bad metal description");
+            return fail(BF_ERR_MODEL);
+        }
+        dm.metal_ncomb = d->metal_ncomb; dm.metal_nmet = d->metal_nmet; dm.metal_ngrid = d->metal_ngrid;
+        for (int c = 0; c < d->metal_ncomb; ++c) {
+            dm.metal_p1[c] = d->metal_p1[c];
+            dm.metal_p2[c] = d->metal_p2[c];
+            if (d->metal_p1[c] < 0 || d->metal_p1[c] >= d->metal_nmet || d->metal_p2[c] < 0 || d->metal_p2[c] >= d->metal_nmet) {
+                bf::set_error("MetalCorrelationModel: bad combination index");
+                return fail(BF_ERR_MODEL);
+            }
+        }
+        m->metal_zgrid.assign(d->metal_zgrid, d->metal_zgrid + (size_t)d->metal_ncomb * d->metal_ngrid);
+        double *p = nullptr;
+        if (mcross) {
+            if (d->metal_nx < 2 || d->metal_ny < 2 || !d->metal_cross || !(d->metal_dx > 0) || !(d->metal_dy > 0)) {
+                bf::set_error("MetalCorrelationModel: error while reading metal model interpolation data.");
+                return fail(BF_ERR_MODEL);
+            }
+            int nt = d->metal_ncomb * 3, nx = d->metal_nx, ny = d->metal_ny;
+            std::vector<double> il((size_t)nt * nx * ny);
+            for (int t = 0; t < nt; ++t)
+                for (int iy = 0; iy < ny; ++iy)
+                    for (int ix = 0; ix < nx; ++ix)
+                        il[((size_t)iy * nx + ix) * nt + t] = d->metal_cross[((size_t)t * ny + iy) * nx + ix];
+            if ((rc = upload(m->allocs, il.data(), il.size(), &p))) return fail(rc);
+            dm.metal_cross = p;
+            dm.metal_nx = nx; dm.metal_ny = ny; dm.metal_x0 = d->metal_x0; dm.metal_y0 = d->metal_y0;
+            dm.metal_inv_dx = 1.0 / d->metal_dx; dm.metal_inv_dy = 1.0 / d->metal_dy;
+            dm.metal_xmax = d->metal_x0 + (nx - 1) * d->metal_dx;
+            dm.metal_ymax = d->metal_y0 + (ny - 1) * d->metal_dy;
+        } else {
+            if (!d->metal_auto) { bf::set_error("MetalCorrelationModel: missing templates"); return fail(BF_ERR_MODEL); }
+            if ((rc = upload(m->allocs, d->metal_auto, (size_t)d->metal_ncomb * 3 * d->metal_ngrid, &p))) return fail(rc);
+            dm.metal_auto = p;
+        }
+    } else if (d->metal_kind != BF_METAL_NONE) {
+        bf::set_error("MetalCorrelationModel: illegal option specification.");
+        return fail(BF_ERR_MODEL);
+    }
+    // distortion matrix (k-space model only, baofit/BaoKSpaceCorrelationModel.cc:188-200)
+    if (d->dist_matrix) {
+        if (d->kind != BF_MODEL_KSPACE) { bf::set_error("bf_model_create: the distortion matrix needs the k-space model"); return fail(BF_ERR_MODEL); }
+        if (d->dist_matrix_order <= 0) { bf::set_error("DistortionMatrix: expected distortion matrix order > 0."); return fail(BF_ERR_MODEL); }
+        dm.dm_order = d->dist_matrix_order;
+        m->dist_matrix.assign(d->dist_matrix, d->dist_matrix + (size_t)d->dist_matrix_order * d->dist_matrix_order);
+    }
+    *out = m;
+    return BF_OK;
+}
+
+extern "C" int bf_model_transform_nr(const bf_model *m) { return m ? m->dev.nr : 0; }
+extern "C" double bf_model_transform_r0(const bf_model *m) { return m ? m->dev.tr_r0 : 0; }
+extern "C" double bf_model_transform_dr(const bf_model *m) { return m ? m->dev.tr_dr : 0; }
+
+// ------------------------------------------------------------------------------------------
+// data
+// ------------------------------------------------------------------------------------------
+extern "C" int bf_data_destroy(bf_data *d) {
+    if (!d) return BF_OK;
+    cudaSetDevice(d->ctx->device);
+    for (void *p : d->allocs) cudaFree(p);
+    for (auto &kv : d->plans)
+        for (void *p : kv.second.allocs) cudaFree(p);
+    delete d;
+    return BF_OK;
+}
+
+extern "C" int bf_data_ndata(const bf_data *d) { return d ? d->n : 0; }
+
+template <class T> static int upload_padded(std::vector<void *> &owner, const T *host, int n, int n_pad, T **dev) {
+    std::vector<T> tmp(n_pad, T(0));
+    if (host) std::copy(host, host + n, tmp.begin());
+    return upload(owner, tmp.data(), (size_t)n_pad, dev);
+}
+
+extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out) {
+    if (!ctx || !d || !out) BF_FAIL(BF_ERR_OPTIONS, "bf_data_create: null argument");
+    if (d->n_data <= 0) BF_FAIL(BF_ERR_DATA, "CorrelationFitter: need some data to fit.");
+    if (!d->r || !d->mu || !d->z || !d->index || !d->data || !d->cov) BF_FAIL(BF_ERR_DATA, "bf_data_create: missing arrays");
+    if (d->n_grid < 0 || (d->n_grid > 0 && (!d->grid_r || !d->grid_mu || !d->grid_z)))
+        BF_FAIL(BF_ERR_DATA, "AbsCorrelationModel::setCoordinates: coordinate vectors not the same size.");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const int n = d->n_data, n_pad = round_up(n, kPadM);
+    // factor the covariance once (host): W lower triangular with W^T W = C^-1
+    std::vector<double> a((size_t)n * n), W((size_t)n * n), L;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = 0.5 * (d->cov[(size_t)i * n + j] + d->cov[(size_t)j * n + i]);
+    if (!d->cov_is_inverse) {
+        if (!cholesky_lower(n, a.data())) BF_FAIL(BF_ERR_DATA, "bf_data_create: covariance is not positive definite");
+        L = a;
+        invert_lower(n, L.data(), W.data());
+    } else {
+        // C^-1 = U U^T with U upper triangular, from the Cholesky factor of the index-reversed
+        // matrix; W = U^T
+        std::vector<double> f((size_t)n * n);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) f[(size_t)i * n + j] = a[(size_t)(n - 1 - i) * n + (n - 1 - j)];
+        if (!cholesky_lower(n, f.data())) BF_FAIL(BF_ERR_DATA, "bf_data_create: inverse covariance is not positive definite");
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) W[(size_t)i * n + j] = (i >= j) ? f[(size_t)(n - 1 - j) * n + (n - 1 - i)] : 0.0;
+    }
+    bf_data *o = new bf_data();
+    o->ctx = ctx;
+    o->n = n;
+    o->n_pad = n_pad;
+    o->n_grid = d->n_grid;
+    o->n_grid_pad = round_up(std::max(d->n_grid, 1), kPadM);
+    o->h_r.assign(d->r, d->r + n);
+    o->h_mu.assign(d->mu, d->mu + n);
+    o->h_z.assign(d->z, d->z + n);
+    o->h_index.assign(d->index, d->index + n);
+    if (d->n_grid > 0) {
+        o->h_grid_r.assign(d->grid_r, d->grid_r + d->n_grid);
+        o->h_grid_mu.assign(d->grid_mu, d->grid_mu + d->n_grid);
+        o->h_grid_z.assign(d->grid_z, d->grid_z + d->n_grid);
+    }
+    int rc;
+    auto fail = [&](int code) { bf_data_destroy(o); return code; };
+    if ((rc = upload_padded(o->allocs, d->r, n, n_pad, &o->d_r))) return fail(rc);
+    if ((rc = upload_padded(o->allocs, d->mu, n, n_pad, &o->d_mu))) return fail(rc);
+    if ((rc = upload_padded(o->allocs, d->z, n, n_pad, &o->d_z))) return fail(rc);
+    if ((rc = upload_padded(o->allocs, d->index, n, n_pad, &o->d_index))) return fail(rc);
+    if ((rc = upload_padded(o->allocs, d->data, n, n_pad, &o->d_data))) return fail(rc);
+    if (d->n_grid > 0) {
+        if ((rc = upload_padded(o->allocs, d->grid_r, d->n_grid, o->n_grid_pad, &o->d_grid_r))) return fail(rc);
+        if ((rc = upload_padded(o->allocs, d->grid_mu, d->n_grid, o->n_grid_pad, &o->d_grid_mu))) return fail(rc);
+        if ((rc = upload_padded(o->allocs, d->grid_z, d->n_grid, o->n_grid_pad, &o->d_grid_z))) return fail(rc);
+    }
+    auto pad_square = [&](const std::vector<double> &src, double **dev) {
+        std::vector<double> p((size_t)n_pad * n_pad, 0.0);
+        for (int i = 0; i < n; ++i) std::memcpy(&p[(size_t)i * n_pad], &src[(size_t)i * n], sizeof(double) * n);
+        return upload(o->allocs, p.data(), p.size(), dev);
+    };
+    if ((rc = pad_square(W, &o->d_W))) return fail(rc);
+    if (!L.empty() && (rc = pad_square(L, &o->d_L))) return fail(rc);
+    *out = o;
+    return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan = (model, data) binding: redshift classes, kept rows of the distortion matrix
+// ------------------------------------------------------------------------------------------
+static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **out) {
+    bf_data *d = const_cast<bf_data *>(dc);
+    auto it = d->plans.find(m);
+    if (it != d->plans.end()) { *out = &it->second; return BF_OK; }
+    const DevModel &dm = m->dev;
+    bf_data::Plan p;
+    std::map<double, int> cls;
+    auto classify = [&](double z) {
+        auto f = cls.find(z);
+        if (f != cls.end()) return f->second;
+        int id = (int)p.zvals.size();
+        cls[z] = id;
+        p.zvals.push_back(z);
+        return id;
+    };
+    const int n = d->n, n_pad = d->n_pad, ng = d->n_grid, ng_pad = d->n_grid_pad;
+    std::vector<int> zc_data(n_pad, 0), zc_grid(ng_pad, 0);
+    for (int i = 0; i < n; ++i) zc_data[i] = classify(d->h_z[i]);
+    p.zc_trigger = zc_data[0];  // the first kept bin triggers the transform
+    const bool use_dm = dm.dm_order > 0;
+    if (use_dm) {
+        // baofit/src/baofit.cc:591-594 order check
+        if (ng != dm.dm_order) BF_FAIL(BF_ERR_DATA, "distortion matrix order does not match the number of grid bins");
+        for (int g = 0; g < ng; ++g) zc_grid[g] = classify(d->h_grid_z[g]);
+        for (int i = 0; i < n; ++i)
+            if (d->h_index[i] < 0 || d->h_index[i] >= ng) BF_FAIL(BF_ERR_DATA, "DistortionMatrix::getDistortion: invalid indices.");
+    }
+    std::vector<int> zcm_data, zcm_grid;
+    if (dm.metal_kind == BF_METAL_AUTO_TABLE || dm.metal_kind == BF_METAL_CROSS_BICUBIC) {
+        zcm_data.assign((size_t)dm.metal_ncomb * n_pad, 0);
+        for (int c = 0; c < dm.metal_ncomb; ++c)
+            for (int i = 0; i < n; ++i) {
+                int idx = d->h_index[i];
+                if (idx < 0 || idx >= dm.metal_ngrid) BF_FAIL(BF_ERR_DATA, "MetalCorrelationModel::_evaluate: invalid index.");
+                zcm_data[(size_t)c * n_pad + i] = classify(m->metal_zgrid[(size_t)c * dm.metal_ngrid + idx]);
+            }
+        if (use_dm) {
+            if (dm.metal_ngrid < ng) BF_FAIL(BF_ERR_DATA, "MetalCorrelationModel: grid shorter than the distortion matrix order");
+            zcm_grid.assign((size_t)dm.metal_ncomb * ng_pad, 0);
+            for (int c = 0; c < dm.metal_ncomb; ++c)
+                for (int g = 0; g < ng; ++g) zcm_grid[(size_t)c * ng_pad + g] = classify(m->metal_zgrid[(size_t)c * dm.metal_ngrid + g]);
+        }
+    }
+    p.nz = (int)p.zvals.size();
+    std::vector<double> vfac(p.nz);
+    for (int c = 0; c < p.nz; ++c) {
+        double zp1 = 1.0 + p.zvals[c];
+        vfac[c] = (1.0 / 100.) * zp1 / std::sqrt(1.0 - dm.omega_matter + dm.omega_matter * zp1 * zp1 * zp1);
+    }
+    BF_CUDA_OK(cudaSetDevice(d->ctx->device));
+    int rc;
+    if ((rc = upload(p.allocs, p.zvals.data(), p.zvals.size(), &p.d_zvals))) return rc;
+    if ((rc = upload(p.allocs, vfac.data(), vfac.size(), &p.d_vfac))) return rc;
+    if ((rc = upload(p.allocs, zc_data.data(), zc_data.size(), &p.d_zc_data))) return rc;
+    if ((rc = upload(p.allocs, zc_grid.data(), zc_grid.size(), &p.d_zc_grid))) return rc;
+    if (!zcm_data.empty() && (rc = upload(p.allocs, zcm_data.data(), zcm_data.size(), &p.d_zc_metal_data))) return rc;
+    if (!zcm_grid.empty() && (rc = upload(p.allocs, zcm_grid.data(), zcm_grid.size(), &p.d_zc_metal_grid))) return rc;
+    if (use_dm) {
+        std::vector<double> dk((size_t)n_pad * ng_pad, 0.0);
+        for (int i = 0; i < n; ++i)
+            std::memcpy(&dk[(size_t)i * ng_pad], &m->dist_matrix[(size_t)d->h_index[i] * ng], sizeof(double) * ng);
+        if ((rc = upload(p.allocs, dk.data(), dk.size(), &p.d_Dkept))) return rc;
+    }
+    auto ins = d->plans.emplace(m, std::move(p));
+    *out = &ins.first->second;
+    return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pipelines
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Workspace {
+    double *pT, *S, *G, *T, *C2, *XiU, *Y, *Z;
+    int *status;
+};
+
+size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
+    size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + d->n_pad /*Z*/;
+    if (dm.kind == BF_MODEL_KSPACE) c += (size_t)6 * dm.nk_pad + (size_t)12 * dm.nr_pad;
+    if (dm.dm_order > 0) c += (size_t)d->n_grid_pad + d->n_pad;
+    return c;
+}
+
+void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Workspace &w) {
+    double *p = (double *)base;
+    auto take = [&](size_t rows) { double *q = p; p += rows * (size_t)ldb; return q; };
+    w.pT = take(dm.npar);
+    w.S = take((size_t)nz * 3);
+    w.status = (int *)take(1);
+    w.Z = take(d->n_pad);
+    w.G = w.T = w.C2 = w.XiU = w.Y = nullptr;
+    if (dm.kind == BF_MODEL_KSPACE) {
+        w.G = take((size_t)6 * dm.nk_pad);
+        w.T = take((size_t)6 * dm.nr_pad);
+        w.C2 = take((size_t)6 * dm.nr_pad);
+    }
+    if (dm.dm_order > 0) {
+        w.XiU = take(d->n_grid_pad);
+        w.Y = take(d->n_pad);
+    }
+}
+
+void nl_table(const DevModel &dm, double zeff, double out[5], double *pk_scale) {
+    // baofit/NonLinearCorrectionModel.cc:22-27, 55-64: linear interpolation in z, end-point clamp
+    static const double zA[] = {2.2, 2.4, 2.6, 2.8, 3.0};
+    static const double tab[5][5] = {{0.8670, 0.8510, 0.7810, 0.7730, 0.7920},
+                                     {1.1200, 1.1122, 1.2570, 1.2765, 1.2928},
+                                     {0.5140, 0.5480, 0.6110, 0.6080, 0.5780},
+                                     {1.6000, 1.6100, 1.6400, 1.6500, 1.6300},
+                                     {19.400, 19.500, 21.100, 19.200, 17.100}};
+    for (int q = 0; q < 5; ++q) {
+        const double *y = tab[q];
+        if (zeff <= zA[0]) out[q] = y[0];
+        else if (zeff >= zA[4]) out[q] = y[4];
+        else {
+            int i = 0;
+            while (i < 3 && zeff >= zA[i + 1]) ++i;
+            out[q] = y[i] + (y[i + 1] - y[i]) * (zeff - zA[i]) / (zA[i + 1] - zA[i]);
+        }
+    }
+    double s = 0.8338 / dm.sigma8;
+    *pk_scale = s * s * std::pow((1.0 + zeff) / (1.0 + dm.zref), -2.0);
+}
+
+enum Output { OUT_PRED, OUT_CHI2, OUT_XIU, OUT_TRANSFORM };
+
+// Runs one chunk (B <= chunk capacity) entirely on the context's stream.
+int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::Plan *plan, const double *d_params,
+              int B, Output what, double *d_out, int ldo, const double *d_override, int *d_status_out,
+              double z_trigger_override, bool use_ztrig_override) {
+    const DevModel &dm = m->dev;
+    cudaStream_t s = ctx->stream;
+    const int ldb = round_up(B, kPadN);
+    const int nz = plan ? plan->nz : 1;
+    // transform-only calls have no data: a single class holding the trigger redshift
+    Workspace w;
+    // fake data dims for transform-only
+    static bf_data empty_data;
+    const bf_data *dd = d ? d : &empty_data;
+    size_t need = ws_doubles_per_column(dm, dd, nz) * (size_t)ldb * sizeof(double);
+    int rc = ensure(&ctx->ws, &ctx->ws_bytes, need);
+    if (rc) return rc;
+    carve(ctx->ws, dm, dd, nz, ldb, w);
+
+    const double *d_zvals = plan ? plan->d_zvals : nullptr;
+    double *tmp_z = nullptr;
+    if (!plan) {
+        // OUT_TRANSFORM without data: one class = z_trigger
+        BF_CUDA_OK(cudaMallocAsync((void **)&tmp_z, sizeof(double), s));
+        BF_CUDA_OK(cudaMemcpyAsync(tmp_z, &z_trigger_override, sizeof(double), cudaMemcpyHostToDevice, s));
+        d_zvals = tmp_z;
+    }
+    launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, w.pT, w.S, w.status);
+    ctx->launches++;
+
+    if (dm.kind == BF_MODEL_KSPACE) {
+        ProjArgs pa;
+        pa.m = dm; pa.pT = w.pT; pa.S = w.S; pa.ldb = ldb; pa.B = B;
+        pa.zc_trigger = plan ? plan->zc_trigger : 0;
+        double ztrig = plan ? plan->zvals[plan->zc_trigger] : z_trigger_override;
+        (void)use_ztrig_override;
+        double zeff = dm.zeff > 0 ? dm.zeff : ztrig;
+        nl_table(dm, zeff, pa.nl_tab, &pa.nl_pk_scale);
+        pa.G = w.G;
+        launch_kspace_project(s, pa, ctx->sm_count);
+        GemmArgs g{};
+        g.A = dm.hankel; g.Bm = w.G; g.C = w.T;
+        g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
+        g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
+        g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
+        launch_gemm_store(s, g, 6);
+        ctx->launches += 2;
+        if (what == OUT_TRANSFORM) {
+            // out[((comp*3+l)*nr + j)*ldo + b]
+            for (int t = 0; t < 6; ++t)
+                BF_CUDA_OK(cudaMemcpy2DAsync(d_out + (size_t)t * dm.nr * ldo, (size_t)ldo * sizeof(double),
+                                             w.T + (size_t)t * dm.nr_pad * ldb, (size_t)ldb * sizeof(double),
+                                             (size_t)B * sizeof(double), dm.nr, cudaMemcpyDeviceToDevice, s));
+            if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
+            return BF_OK;
+        }
+        launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2);
+        ctx->launches++;
+    }
+
+    EvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.m = dm; a.pT = w.pT; a.S = w.S; a.ldb = ldb; a.B = B;
+    a.vfac = plan->d_vfac; a.T = w.T; a.C2 = w.C2; a.status = w.status;
+    const bool use_dm = dm.dm_order > 0;
+    const bool to_user = what == OUT_PRED;  // final rows go straight to the caller's buffer
+
+    bool finished = false;
+    if (use_dm) {
+        // undistorted xi on the full grid
+        a.npts = d->n_grid; a.npts_pad = d->n_grid_pad;
+        a.r = d->d_grid_r; a.mu = d->d_grid_mu; a.z = d->d_grid_z; a.zc = plan->d_zc_grid; a.gidx = nullptr;
+        a.zc_metal = plan->d_zc_metal_grid; a.zc_stride = d->n_grid_pad;
+        a.mode = 1;
+        a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
+        if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
+        launch_kspace_eval(s, a, ctx->sm_count);
+        ctx->launches++;
+        if (what == OUT_XIU) finished = true;
+        if (!finished) {
+            GemmArgs g{};
+            g.A = plan->d_Dkept; g.Bm = w.XiU; g.C = w.Y;
+            g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad;
+            g.lda = d->n_grid_pad; g.ldb = ldb; g.ldc = ldb;
+            launch_gemm_store(s, g, 1);
+            ctx->launches++;
+            // tail on the data bins: post-matrix broadband, dilation check, residual.
+            // Y (ld = ldb) -> Z (ld = ldb); predictions are copied out row by row afterwards.
+            a.npts = d->n; a.npts_pad = d->n_pad;
+            a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
+            a.in = w.Y; a.out = w.Z; a.ldo = ldb;
+            a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
+            launch_dist_post(s, a, ctx->sm_count);
+            ctx->launches++;
+            if (to_user)
+                BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
+                                             (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
+        }
+    } else {
+        if (what == OUT_XIU) BF_FAIL(BF_ERR_ANALYSIS, "bf_eval_undistorted_batch: the model has no distortion matrix");
+        a.npts = d->n; a.npts_pad = to_user ? d->n : d->n_pad;
+        a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
+        a.zc_metal = plan->d_zc_metal_data; a.zc_stride = d->n_pad;
+        a.mode = 0;
+        a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
+        a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
+        if (dm.kind == BF_MODEL_RSPACE) launch_rspace_eval(s, a, ctx->sm_count);
+        else launch_kspace_eval(s, a, ctx->sm_count);
+        ctx->launches++;
+    }
+    if (what == OUT_CHI2 && !finished) {
+        GemmArgs g{};
+        g.A = d->d_W; g.Bm = w.Z; g.C = nullptr;
+        g.M = d->n_pad; g.N = B; g.K = d->n_pad;
+        g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
+        g.lower_triangular = 1;
+        g.chi2 = d_out; g.status = w.status;
+        launch_gemm_chi2(s, g);
+        ctx->launches++;
+    }
+    if (d_status_out) BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+    BF_CUDA_OK(cudaGetLastError());
+    return BF_OK;
+}
+
+int chunk_capacity(const bf_model *m, const bf_data *d, int nz) {
+    static bf_data empty_data;
+    size_t per_col = ws_doubles_per_column(m->dev, d ? d : &empty_data, nz) * sizeof(double);
+    size_t budget = (size_t)3 << 30;  // 3 GiB of workspace at most
+    size_t cap = budget / per_col;
+    cap = std::min<size_t>(cap, 65536);
+    cap = std::max<size_t>(cap / kPadN * kPadN, kPadN);
+    return (int)cap;
+}
+
+int check_args(bf_ctx *ctx, const bf_model *m, const bf_data *d, const void *params, int B) {
+    if (!ctx || !m || !d || !params) BF_FAIL(BF_ERR_OPTIONS, "null argument");
+    if (B <= 0) BF_FAIL(BF_ERR_OPTIONS, "batch size must be positive");
+    if (m->ctx != ctx || d->ctx != ctx) BF_FAIL(BF_ERR_OPTIONS, "model/data belong to a different context");
+    return BF_OK;
+}
+}  // namespace
+
+static int run_device(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B, Output what,
+                      double *d_out, int ldo, const double *d_override, int *d_status) {
+    int rc = check_args(ctx, m, d, d_params, B);
+    if (rc) return rc;
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const bf_data::Plan *plan = nullptr;
+    if ((rc = get_plan(m, d, &plan))) return rc;
+    int cap = chunk_capacity(m, d, plan->nz);
+    for (int b0 = 0; b0 < B; b0 += cap) {
+        int bc = std::min(cap, B - b0);
+        double *o = what == OUT_CHI2 ? d_out + b0 : d_out + b0;  // chi2[b] or column offset in bin-major outputs
+        const double *ov = d_override ? d_override + (size_t)b0 * d->n : nullptr;
+        rc = run_chunk(ctx, m, d, plan, d_params + (size_t)b0 * m->dev.npar, bc, what, o, ldo, ov,
+                       d_status ? d_status + b0 : nullptr, 0.0, false);
+        if (rc) return rc;
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_eval_batch_dev(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B,
+                                 double *d_pred, int ldp, int *d_status) {
+    if (!d_pred || ldp < B) BF_FAIL(BF_ERR_OPTIONS, "bf_eval_batch_dev: bad output buffer");
+    return run_device(ctx, m, d, d_params, B, OUT_PRED, d_pred, ldp, nullptr, d_status);
+}
+
+extern "C" int bf_chi2_batch_dev(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B,
+                                 const double *d_override, double *d_chi2, int *d_status) {
+    if (!d_chi2) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_dev: null output");
+    return run_device(ctx, m, d, d_params, B, OUT_CHI2, d_chi2, 0, d_override, d_status);
+}
+
+// host-buffer entry points: stage through device memory owned by the context
+static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B, Output what,
+                    double *out, int ldo, int out_rows, const double *override_h, int *status) {
+    int rc = check_args(ctx, m, d, params, B);
+    if (rc) return rc;
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const int npar = m->dev.npar;
+    size_t nb_params = (size_t)B * npar * sizeof(double);
+    size_t nb_out = what == OUT_CHI2 ? (size_t)B * sizeof(double) : (size_t)out_rows * B * sizeof(double);
+    size_t nb_ov = override_h ? (size_t)B * d->n * sizeof(double) : 0;
+    size_t nb_st = (size_t)B * sizeof(int);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t total = al(nb_params) + al(nb_out) + al(nb_ov) + al(nb_st);
+    if ((rc = ensure(&ctx->io, &ctx->io_bytes, total))) return rc;
+    char *base = (char *)ctx->io;
+    double *d_params = (double *)base;
+    double *d_out = (double *)(base + al(nb_params));
+    double *d_ov = override_h ? (double *)(base + al(nb_params) + al(nb_out)) : nullptr;
+    int *d_st = (int *)(base + al(nb_params) + al(nb_out) + al(nb_ov));
+    cudaStream_t s = ctx->stream;
+    BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
+    if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
+    rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
+    if (rc) return rc;
+    if (what == OUT_CHI2)
+        BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, s));
+    else
+        BF_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(double), d_out, (size_t)B * sizeof(double),
+                                     (size_t)B * sizeof(double), out_rows, cudaMemcpyDeviceToHost, s));
+    std::vector<int> st_local;
+    int *st = status;
+    if (!st && what != OUT_CHI2) { st_local.resize(B); st = st_local.data(); }
+    if (st) BF_CUDA_OK(cudaMemcpyAsync(st, d_st, nb_st, cudaMemcpyDeviceToHost, s));
+    BF_CUDA_OK(cudaStreamSynchronize(s));
+    if (what != OUT_CHI2 && st)
+        for (int b = 0; b < B; ++b)
+            if (st[b])
+                for (int i = 0; i < out_rows; ++i) out[(size_t)i * ldo + b] = NAN;
+    return BF_OK;
+}
+
+extern "C" int bf_eval_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B,
+                             double *pred, int ldp, int *status) {
+    if (!pred || ldp < B) BF_FAIL(BF_ERR_OPTIONS, "bf_eval_batch: bad output buffer");
+    return run_host(ctx, m, d, params, B, OUT_PRED, pred, ldp, d ? d->n : 0, nullptr, status);
+}
+
+extern "C" int bf_chi2_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B,
+                             const double *data_override, double *chi2, int *status) {
+    if (!chi2) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch: null output");
+    return run_host(ctx, m, d, params, B, OUT_CHI2, chi2, 0, 0, data_override, status);
+}
+
+extern "C" int bf_eval_undistorted_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params,
+                                         int B, double *xiu, int ldp, int *status) {
+    if (!xiu || ldp < B) BF_FAIL(BF_ERR_OPTIONS, "bf_eval_undistorted_batch: bad output buffer");
+    if (!m || m->dev.dm_order <= 0) BF_FAIL(BF_ERR_ANALYSIS, "bf_eval_undistorted_batch: the model has no distortion matrix");
+    return run_host(ctx, m, d, params, B, OUT_XIU, xiu, ldp, d ? d->n_grid : 0, nullptr, status);
+}
+
+extern "C" int bf_transform_batch(bf_ctx *ctx, const bf_model *m, const double *params, int B, double z_trigger,
+                                  double *out, int ldb_out) {
+    if (!ctx || !m || !params || !out) BF_FAIL(BF_ERR_OPTIONS, "null argument");
+    if (m->dev.kind != BF_MODEL_KSPACE) BF_FAIL(BF_ERR_ANALYSIS, "bf_transform_batch: not a k-space model");
+    if (B <= 0 || ldb_out < B) BF_FAIL(BF_ERR_OPTIONS, "bf_transform_batch: bad batch size / leading dimension");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const int npar = m->dev.npar, nr = m->dev.nr;
+    int cap = chunk_capacity(m, nullptr, 1);
+    size_t nb_params = (size_t)std::min(B, cap) * npar * sizeof(double);
+    size_t nb_out = (size_t)6 * nr * std::min(B, cap) * sizeof(double);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    int rc = ensure(&ctx->io, &ctx->io_bytes, al(nb_params) + al(nb_out));
+    if (rc) return rc;
+    double *d_params = (double *)ctx->io;
+    double *d_out = (double *)((char *)ctx->io + al(nb_params));
+    for (int b0 = 0; b0 < B; b0 += cap) {
+        int bc = std::min(cap, B - b0);
+        BF_CUDA_OK(cudaMemcpyAsync(d_params, params + (size_t)b0 * npar, (size_t)bc * npar * sizeof(double),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        rc = run_chunk(ctx, m, nullptr, nullptr, d_params, bc, OUT_TRANSFORM, d_out, bc, nullptr, nullptr, z_trigger, true);
+        if (rc) return rc;
+        BF_CUDA_OK(cudaMemcpy2DAsync(out + b0, (size_t)ldb_out * sizeof(double), d_out, (size_t)bc * sizeof(double),
+                                     (size_t)bc * sizeof(double), (size_t)6 * nr, cudaMemcpyDeviceToHost, ctx->stream));
+        BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_sample_toys(bf_ctx *ctx, const bf_data *d, const double *truth, unsigned long long seed,
+                              long long first_toy, int ntoy, double scale, double *out) {
+    if (!ctx || !d || !truth || !out || ntoy <= 0) BF_FAIL(BF_ERR_OPTIONS, "bf_sample_toys: bad argument");
+    if (!d->d_L) BF_FAIL(BF_ERR_ANALYSIS, "bf_sample_toys: needs a covariance (not an inverse covariance)");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t nb_truth = (size_t)d->n * sizeof(double), nb_out = (size_t)ntoy * d->n * sizeof(double);
+    int rc = ensure(&ctx->io, &ctx->io_bytes, al(nb_truth) + al(nb_out));
+    if (rc) return rc;
+    double *d_truth = (double *)ctx->io, *d_out = (double *)((char *)ctx->io + al(nb_truth));
+    BF_CUDA_OK(cudaMemcpyAsync(d_truth, truth, nb_truth, cudaMemcpyHostToDevice, ctx->stream));
+    launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, d_out);
+    ctx->launches++;
+    BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, ctx->stream));
+    BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BF_OK;
+}

@@ -1,0 +1,141 @@
+// Internal structures of libbaofit_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/baofit_b200.h"
+
+namespace bf {
+
+void set_error(const std::string &msg);
+
+#define BF_CUDA_OK(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            bf::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+            return BF_ERR_ANALYSIS;                                                              \
+        }                                                                                        \
+    } while (0)
+
+// ---- tile geometry of the DMMA GEMM kernels (kernels_gemm.cu) ----
+constexpr int kGemmBM = 64;   // rows of C per CTA tile
+constexpr int kGemmBN = 64;   // columns (parameter vectors) per CTA tile
+constexpr int kGemmBK = 16;   // k depth of one pipeline stage
+constexpr int kPadN = 64;     // batch (b) leading dimensions are multiples of this
+constexpr int kPadM = 64;     // row counts of GEMM operands are padded to this
+constexpr int kMuNodes = 20;  // Gauss-Legendre nodes in mu for the multipoles of D(k,mu)
+constexpr int kFineSub = 4;   // fine k nodes per native P(k) interval
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct DevBB {
+    int enabled, idx_base;
+    int r_min, r_max, r_step, r_denom;
+    int mu_min, mu_max, mu_step;
+    int rp_min, rp_max, rp_step;
+    int rt_min, rt_max, rt_step;
+    int z_min, z_max, z_step;
+    double inv_r0, z0;
+};
+
+// One tabulated multipole family on shared knots: per-interval cubic coefficients
+// coef[(l*(n-1) + j)*4 + {0,1,2,3}] = y_j, b_j, c_j, d_j  (gsl cspline evaluation form)
+struct DevSplineSet {
+    int n;          // knots
+    int uniform;    // 1: x_j = x0 + j*dx
+    double x0, inv_dx, xlast;
+    const double *x;     // knots (device)
+    const double *coef;  // [3][n-1][4] (device)
+    double ylo[3], yhi[3];
+};
+
+// Immutable model description passed by value to kernels.
+struct DevModel {
+    int kind;
+    unsigned flags;
+    int npar;
+    double zref, omega_matter;
+    int idx_beta, idx_bb, idx_gamma_bias, idx_gamma_beta, idx_delta_v, idx_bias2, idx_bb2, idx_beta_bias;
+    int idx_bao, idx_comb_scale, idx_rad, idx_nl, idx_cont, idx_bs, idx_hcd, idx_uv, idx_smgaus, idx_smlor,
+        idx_nlcorr;
+    DevBB bb[4];
+    // r-space
+    DevSplineSet fid, nw;
+    // k-space
+    int nk, nk_pad, nr, nr_pad, ell_max;
+    double tr_r0, tr_dr, tr_inv_dr, rlo, rhi, dilmin, dilmax, zeff, sigma8;
+    const double *kc;      // [nk] coarse nodes
+    const double *pk_kc;   // [2][nk] P_comp at coarse nodes (argument of the non-linear correction)
+    const double *hankel;  // [2][3][nr_pad][nk_pad] Filon weights
+    const double *th_w, *th_inv_diag;  // [nr-2] factors of the constant (1,4,1) spline system
+    double mu_x[kMuNodes], mu_w[kMuNodes];
+    // metals
+    int metal_kind, idx_metal, metal_ncomb, metal_nmet, metal_ngrid;
+    int metal_p1[8], metal_p2[8];
+    const double *metal_auto;   // [ncomb*3][ngrid]
+    const double *metal_cross;  // interleaved [ny][nx][ncomb*3]
+    int metal_nx, metal_ny;
+    double metal_x0, metal_y0, metal_inv_dx, metal_inv_dy, metal_xmax, metal_ymax;
+    int dm_order;
+};
+
+struct bf_ctx_t;
+}  // namespace bf
+
+struct bf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    // growable workspaces (device)
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    void *io = nullptr;  // staging for host-buffer entry points
+    size_t io_bytes = 0;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int sm_count = 148;
+};
+
+struct bf_model {
+    bf_ctx *ctx = nullptr;
+    bf::DevModel dev;
+    std::vector<void *> allocs;  // device allocations owned by the model
+    // host copies needed at plan time
+    std::vector<double> metal_zgrid;  // [ncomb][ngrid]
+    std::vector<double> dist_matrix;  // [order][order]
+    double zref = 0;
+};
+
+struct bf_data {
+    bf_ctx *ctx = nullptr;
+    int n = 0, n_pad = 0, n_grid = 0, n_grid_pad = 0;
+    std::vector<double> h_r, h_mu, h_z, h_grid_r, h_grid_mu, h_grid_z;
+    std::vector<int> h_index;
+    std::vector<void *> allocs;
+    double *d_r = nullptr, *d_mu = nullptr, *d_z = nullptr;  // [n_pad]
+    int *d_index = nullptr;
+    double *d_grid_r = nullptr, *d_grid_mu = nullptr, *d_grid_z = nullptr;  // [n_grid_pad]
+    double *d_data = nullptr;  // [n_pad]
+    double *d_W = nullptr;     // [n_pad][n_pad] lower triangular, W^T W = C^-1
+    double *d_L = nullptr;     // [n_pad][n_pad] lower Cholesky factor of C (toy noise); may be null
+    // plans: per model, the z-class table and the gathered distortion matrix rows
+    struct Plan {
+        int nz = 0;
+        std::vector<double> zvals;
+        double *d_zvals = nullptr;   // [nz]
+        double *d_vfac = nullptr;    // [nz] (1/100)(1+z)/sqrt(1-Om+Om(1+z)^3)
+        int *d_zc_data = nullptr;    // [n_pad]
+        int *d_zc_grid = nullptr;    // [n_grid_pad]
+        int *d_zc_metal_data = nullptr;  // [ncomb][n_pad]    class of metal zgrid[c][index_i]
+        int *d_zc_metal_grid = nullptr;  // [ncomb][n_grid_pad]
+        int zc_trigger = 0;          // class of the z that triggers the k-space transform
+        double *d_Dkept = nullptr;   // [n_pad][n_grid_pad] rows of the distortion matrix of kept bins
+        std::vector<void *> allocs;
+    };
+    std::map<const bf_model *, Plan> plans;
+};

@@ -1,0 +1,226 @@
+// Device-side building blocks shared by the model kernels.
+#pragma once
+#include "bf_internal.h"
+
+namespace bf {
+
+__device__ __forceinline__ double ipow(double x, int n) {
+    // x^n for integer n by repeated squaring (the reference calls std::pow with an integral
+    // exponent, baofit/BroadbandModel.cc:205-213; results agree to ~1 ulp)
+    int m = n < 0 ? -n : n;
+    double r = 1.0, p = x;
+    while (m) {
+        if (m & 1) r *= p;
+        p *= p;
+        m >>= 1;
+    }
+    return n < 0 ? 1.0 / r : r;
+}
+
+__device__ __forceinline__ double legendre_p(int ell, double mu) {  // baofit/BroadbandModel.cc:171-195
+    double m2 = mu * mu;
+    switch (ell) {
+    case 0: return 1.0;
+    case 1: return mu;
+    case 2: return (-1.0 + 3.0 * m2) * 0.5;
+    case 3: return mu * (-3.0 + 5.0 * m2) * 0.5;
+    case 4: return (3.0 + m2 * (-30.0 + 35.0 * m2)) * 0.125;
+    case 5: return mu * (15.0 + m2 * (-70.0 + 63.0 * m2)) * 0.125;
+    case 6: return (-5.0 + m2 * (105.0 + m2 * (-315.0 + 231.0 * m2))) * 0.0625;
+    case 7: return mu * (-35.0 + m2 * (315.0 + m2 * (-693.0 + 429.0 * m2))) * 0.0625;
+    default: return (35.0 + m2 * (-1260.0 + m2 * (6930.0 + m2 * (-12012.0 + 6435.0 * m2)))) * 0.0078125;
+    }
+}
+
+// Broadband polynomial, baofit/BroadbandModel.cc:197-226. pT = transposed parameters
+// (pT[j*ldb + b]), already offset to column b.
+__device__ __forceinline__ double broadband_eval(const DevBB &s, const double *__restrict__ pT, int ldb, double r,
+                                                 double mu, double z) {
+    double rr = r * s.inv_r0, rrP = r * mu * s.inv_r0, rrT = r * sqrt(1.0 - mu * mu) * s.inv_r0;
+    double zz = (1.0 + z) / (1.0 + s.z0);
+    double xi = 0.0;
+    int off = s.idx_base;
+    for (int zi = s.z_min; zi <= s.z_max; zi += s.z_step) {
+        double zF = ipow(zz, zi);
+        for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step) {
+            double zmF = zF * legendre_p(mi, mu);
+            for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step) {
+                double base = ri > 0 ? rr - 1.0 : rr;
+                double rF = s.r_denom == 1 ? ipow(base, ri) : pow(base, (double)ri / s.r_denom);
+                for (int pi = s.rp_min; pi <= s.rp_max; pi += s.rp_step) {
+                    double rPF = ipow(pi > 0 ? rrP - 1.0 : rrP, pi);
+                    double acc = 0.0;
+                    for (int ti = s.rt_min; ti <= s.rt_max; ti += s.rt_step) {
+                        double rTF = ipow(ti > 0 ? rrT - 1.0 : rrT, ti);
+                        acc += pT[(size_t)off * ldb] * rTF;
+                        ++off;
+                    }
+                    xi += acc * rF * rPF * zmF;
+                }
+            }
+        }
+    }
+    return xi;
+}
+
+// natural cubic spline with end-point clamp on per-interval coefficients
+__device__ __forceinline__ int spline_interval(const DevSplineSet &t, double x) {
+    int j;
+    if (t.uniform) {
+        j = (int)((x - t.x0) * t.inv_dx);
+        j = max(0, min(j, t.n - 2));
+        // guard against rounding at knots
+        if (x < t.x[j] && j > 0) --j;
+        else if (x >= t.x[j + 1] && j < t.n - 2) ++j;
+    } else {
+        int lo = 0, hi = t.n - 1;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (t.x[mid] > x) hi = mid; else lo = mid;
+        }
+        j = lo;
+    }
+    return j;
+}
+
+__device__ __forceinline__ void spline3_eval(const DevSplineSet &t, const double *__restrict__ coef, double x,
+                                             double out[3]) {
+    if (x <= t.x0) { out[0] = t.ylo[0]; out[1] = t.ylo[1]; out[2] = t.ylo[2]; return; }
+    if (x >= t.xlast) { out[0] = t.yhi[0]; out[1] = t.yhi[1]; out[2] = t.yhi[2]; return; }
+    int j = spline_interval(t, x);
+    double dx = x - t.x[j];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const double4 c = *reinterpret_cast<const double4 *>(coef + ((size_t)l * (t.n - 1) + j) * 4);
+        out[l] = c.x + dx * (c.y + dx * (c.z + dx * c.w));
+    }
+}
+
+// Kaiser normalisation factors, baofit/AbsCorrelationModel.cc:196-204 / MetalCorrelationModel.cc:359-363
+__device__ __forceinline__ void norm_factors(double biasSq, double betaAvg, double betaProd, double &n0, double &n2,
+                                             double &n4) {
+    n0 = biasSq * (1.0 + (2.0 / 3.0) * betaAvg + (1.0 / 5.0) * betaProd);
+    n2 = biasSq * ((4.0 / 3.0) * betaAvg + (4.0 / 7.0) * betaProd);
+    n4 = biasSq * betaProd * (8.0 / 35.0);
+}
+
+// Velocity shift, baofit/AbsCorrelationModel.cc:146-157 with dpi = dv * vfac(z)
+__device__ __forceinline__ void velocity_shift(double dpi, double &r, double &mu) {
+    double rnew = sqrt(r * r + 2.0 * r * mu * dpi + dpi * dpi);
+    double munew = (r * mu + dpi) / rnew;
+    r = rnew;
+    mu = munew;
+}
+
+struct Internal {  // AbsCorrelationModel::_updateInternalParameters, AbsCorrelationModel.cc:132-144
+    double beta, bias, bias2, beta2, biasSq, betaAvg, betaProd;
+};
+
+__device__ __forceinline__ Internal load_internal(const DevModel &m, const double *__restrict__ pT, int ldb) {
+    Internal in;
+    in.beta = pT[(size_t)m.idx_beta * ldb];
+    in.bias = pT[(size_t)m.idx_bb * ldb] / (1.0 + in.beta);
+    if (m.idx_beta_bias >= 0) in.bias = pT[(size_t)m.idx_beta_bias * ldb] / in.beta;
+    in.bias2 = in.beta2 = 0.0;
+    if (m.flags & BF_FLAG_CROSS_CORRELATION) {
+        in.bias2 = pT[(size_t)m.idx_bias2 * ldb];
+        in.beta2 = pT[(size_t)m.idx_bb2 * ldb] / in.bias2;
+        in.betaAvg = (in.beta + in.beta2) / 2.0;
+        in.betaProd = in.beta * in.beta2;
+        in.biasSq = in.bias * in.bias2;
+    } else {
+        in.betaAvg = in.beta;
+        in.betaProd = in.beta * in.beta;
+        in.biasSq = in.bias * in.bias;
+    }
+    return in;
+}
+
+// Catmull-Rom weights (tensor-product form of the bicubic patch with centred differences)
+__device__ __forceinline__ void catmull_weights(double t, double w[4]) {
+    double t2 = t * t, t3 = t2 * t;
+    w[0] = 0.5 * (-t + 2.0 * t2 - t3);
+    w[1] = 0.5 * (2.0 - 5.0 * t2 + 3.0 * t3);
+    w[2] = 0.5 * (t + 4.0 * t2 - 3.0 * t3);
+    w[3] = 0.5 * (-t2 + t3);
+}
+__device__ __forceinline__ int wrap_index(int i, int n) {
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+// Metal correlations, baofit/MetalCorrelationModel.cc:235-351.
+// S = per-class evolution factors S[(c*3+k)*ldb] for column b; zc_metal[c*stride + bin] = class ids.
+__device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &in, const double *__restrict__ pT,
+                                             int ldb, const double *__restrict__ S, const int *__restrict__ zc_metal,
+                                             int zc_stride, int bin, int grid_index, double r, double mu) {
+    if (m.metal_kind == BF_METAL_TOY) {
+        const double rpar0[4] = {59.533, 111.344, 134.998, 174.525};
+        const double sigpar[4] = {0.0, 4.88626, 5.489, 8.48942};
+        const double sigperp[4] = {5.55309, 4.13032, 6.30484, 7.85636};
+        double rperp = r * sqrt(1.0 - mu * mu), rpar = fabs(r * mu), xi = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double sp = i == 0 ? pT[(size_t)(m.idx_metal + 4) * ldb] : sigpar[i];
+            double ep = (rpar - rpar0[i]) / sp, et = (rperp - 2.0) / sigperp[i];
+            if (fabs(ep) < 5.0 && fabs(et) < 10.0) xi += 1e-4 * pT[(size_t)(m.idx_metal + i) * ldb] * exp(-ep * ep - et);
+        }
+        return xi;
+    }
+    const bool cross = m.metal_kind == BF_METAL_CROSS_BICUBIC;
+    double betap[6], biasp[6];
+    betap[0] = cross ? in.beta2 : in.beta;
+    biasp[0] = cross ? in.bias2 : in.bias;
+    for (int i = 1; i < m.metal_nmet; ++i) {
+        betap[i] = pT[(size_t)(m.idx_metal + 2 * (i - 1)) * ldb];
+        biasp[i] = pT[(size_t)(m.idx_metal + 2 * (i - 1) + 1) * ldb];
+    }
+    double xi = 0.0;
+    double wx[4], wy[4];
+    int ix = 0, iy = 0;
+    if (cross) {
+        double rperp = r * sqrt(1.0 - mu * mu), rpar = r * mu;
+        rperp = fmin(fmax(rperp, m.metal_x0), m.metal_xmax);
+        rpar = fmin(fmax(rpar, m.metal_y0), m.metal_ymax);
+        double fx = (rperp - m.metal_x0) * m.metal_inv_dx, fy = (rpar - m.metal_y0) * m.metal_inv_dy;
+        double flx = floor(fx), fly = floor(fy);
+        ix = (int)flx;
+        iy = (int)fly;
+        catmull_weights(fx - flx, wx);
+        catmull_weights(fy - fly, wy);
+    }
+    const int nt = m.metal_ncomb * 3;
+    for (int c = 0; c < m.metal_ncomb; ++c) {
+        int a = m.metal_p1[c], b = m.metal_p2[c];
+        int zc = zc_metal[(size_t)c * zc_stride + bin];
+        double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb];
+        double n0, n2, n4;
+        norm_factors(biasp[a] * biasp[b] * eb, 0.5 * (betap[a] + betap[b]) * ebeta, betap[a] * betap[b] * ebeta * ebeta,
+                     n0, n2, n4);
+        if (cross) {
+            double t0 = 0.0, t2 = 0.0, t4 = 0.0;
+#pragma unroll
+            for (int jy = 0; jy < 4; ++jy) {
+                const double *row = m.metal_cross + (size_t)wrap_index(iy - 1 + jy, m.metal_ny) * m.metal_nx * nt;
+                double r0 = 0.0, r2 = 0.0, r4 = 0.0;
+#pragma unroll
+                for (int jx = 0; jx < 4; ++jx) {
+                    const double *cell = row + (size_t)wrap_index(ix - 1 + jx, m.metal_nx) * nt + 3 * c;
+                    r0 += wx[jx] * cell[0];
+                    r2 += wx[jx] * cell[1];
+                    r4 += wx[jx] * cell[2];
+                }
+                t0 += wy[jy] * r0;
+                t2 += wy[jy] * r2;
+                t4 += wy[jy] * r4;
+            }
+            xi += n0 * t0 + n2 * t2 + n4 * t4;
+        } else {
+            const double *t = m.metal_auto + (size_t)(3 * c) * m.metal_ngrid + grid_index;
+            xi += n0 * t[0] + n2 * t[m.metal_ngrid] + n4 * t[2 * (size_t)m.metal_ngrid];
+        }
+    }
+    return xi;
+}
+
+}  // namespace bf

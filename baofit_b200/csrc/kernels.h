@@ -1,0 +1,73 @@
+// Kernel argument blocks and launchers (implemented in kernels_model.cu / kernels_gemm.cu).
+#pragma once
+#include "bf_internal.h"
+
+namespace bf {
+
+struct EvalArgs {
+    DevModel m;
+    const double *pT;  // transposed parameters [npar][ldb]
+    const double *S;   // evolution factors [nz*3][ldb]
+    int ldb, B;
+    // evaluation points (data bins or grid bins)
+    int npts, npts_pad, pts_per_block;
+    const double *r, *mu, *z;
+    const int *zc;        // redshift class of each point
+    const int *gidx;      // global grid index of each point (null: the point index itself)
+    const int *zc_metal;  // [ncomb][zc_stride] class of the metal grid redshift at each point
+    int zc_stride;
+    const double *vfac;   // [nz] velocity-shift factor of each class
+    // k-space per-vector multipole tables and their spline second derivatives
+    const double *T, *C2;
+    int mode;
+    // output: out[i*ldo + b] = value - (dov ? dov[b*npts+i] : dsub ? dsub[i] : 0)
+    const double *in;
+    double *out;
+    int ldo;
+    const double *dsub;
+    const double *dov;
+    int *status;
+};
+
+struct ProjArgs {
+    DevModel m;
+    const double *pT, *S;
+    int ldb, B, zc_trigger, k_per_block;
+    double nl_tab[5];    // qnl, kv, av, bv, kp interpolated at z_eff (NonLinearCorrectionModel.cc:22-27)
+    double nl_pk_scale;  // (sigma8Sim/sigma8)^2 ((1+zeff)/(1+zref))^-2   (:62-64)
+    double *G;           // [2][3][nk_pad][ldb]
+};
+
+// C[M x N] = A[M x K] . B[K x N]; A row-major lda, B row-major ldb (N = parameter vectors),
+// batched over blockIdx.z with the given strides. Operands are padded: M, K multiples of the
+// tile sizes with zero fill in A.
+struct GemmArgs {
+    const double *A;
+    const double *Bm;
+    double *C;
+    int M, N, K;  // padded M and K; N = number of valid columns
+    int lda, ldb, ldc;
+    long long strideA, strideB, strideC;
+    int lower_triangular;  // A is lower triangular: skip k tiles above the diagonal
+    // chi-square epilogue: chi2[n] = sum_m C[m][n]^2 (C is not stored)
+    double *chi2;
+    const int *status;
+};
+
+void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
+                 const double *zvals, double *pT, double *S, int *status);
+void launch_rspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
+void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count);
+void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,
+                          const double *th_inv_diag, const double *T, double *C2);
+void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
+void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count);
+
+void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
+void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);
+
+// toy noise: out[t][i] = truth_i + scale * sum_j L[i][j] g_{t,j}
+void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth,
+                      unsigned long long seed, long long first_toy, int ntoy, double scale, double *out);
+
+}  // namespace bf

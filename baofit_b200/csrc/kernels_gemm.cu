@@ -1,0 +1,266 @@
+// FP64 tensor-pipe (DMMA, mma.sync.m8n8k4.f64) GEMM kernels.
+//
+// sm_100a has no tcgen05 kind for f64; the Blackwell FP64 tensor path is DMMA.8x8x4 (SASS), which
+// ptxas emits for mma.sync.aligned.m8n8k4.f64 (larger PTX shapes are split into the same SASS op).
+// Measured issue-bound rate on B200: 37.1 TFLOP/s (profiles/fp64_peaks_r01.json), cuBLAS DGEMM
+// 35.5 TFLOP/s.
+//
+// All three contractions of the hot path have the same shape: a small, L2-resident left matrix
+// (Hankel weights, kept rows of the distortion matrix, W = L^-1 of the covariance) times a wide
+// bin-major panel whose columns are the parameter vectors:
+//     C[M x N] = A[M x K] . B[K x N],   N = batch.
+// Tiles: CTA 64 x 64, k depth 16, three cp.async stages; 4 warps in a 2 x 2 grid, each warp a
+// 32 x 32 tile = 4 x 4 DMMA fragments. Shared-memory rows are padded by 4 doubles so that every
+// fragment load is bank-conflict free.
+#include "kernels.h"
+
+namespace bf {
+
+namespace {
+constexpr int BM = kGemmBM, BN = kGemmBN, BK = kGemmBK;
+constexpr int STAGES = 3;
+constexpr int LDA_S = BK + 4;  // 20 doubles
+constexpr int LDB_S = BN + 4;  // 68 doubles
+constexpr int A_STAGE = BM * LDA_S;
+constexpr int B_STAGE = BK * LDB_S;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// loads one (BM x BK) tile of A and one (BK x BN) tile of B into a pipeline stage
+__device__ __forceinline__ void load_stage(double *As, double *Bs, const double *__restrict__ A,
+                                           const double *__restrict__ Bm, int lda, int ldb, int m0, int n0, int k0,
+                                           int tid) {
+#pragma unroll
+    for (int c = tid; c < BM * (BK / 2); c += 128) {
+        int row = c / (BK / 2), ch = c % (BK / 2);
+        cp_async16(As + row * LDA_S + ch * 2, A + (size_t)(m0 + row) * lda + k0 + ch * 2);
+    }
+#pragma unroll
+    for (int c = tid; c < BK * (BN / 2); c += 128) {
+        int row = c / (BN / 2), ch = c % (BN / 2);
+        cp_async16(Bs + row * LDB_S + ch * 2, Bm + (size_t)(k0 + row) * ldb + n0 + ch * 2);
+    }
+}
+
+__device__ __forceinline__ void compute_stage(const double *As, const double *Bs, double (&acc)[4][4][2], int wm,
+                                              int wn, int lane) {
+    const int l4 = lane & 3, l8 = lane >> 2;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + l8) * LDA_S + kk + l4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(kk + l4) * LDB_S + wn * 32 + ni * 8 + l8];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+}  // namespace
+
+// ---- plain store epilogue: C = A.B --------------------------------------------------------
+__global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem, *Bs = smem + STAGES * A_STAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const double *A = g.A + (size_t)blockIdx.z * g.strideA;
+    const double *Bm = g.Bm + (size_t)blockIdx.z * g.strideB;
+    double *C = g.C + (size_t)blockIdx.z * g.strideC;
+    int kend = g.lower_triangular ? min(g.K, m0 + BM) : g.K;
+    const int T = kend / BK;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < T) load_stage(As + s * A_STAGE, Bs + s * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0, s * BK, tid);
+        cp_async_commit();
+    }
+    for (int t = 0; t < T; ++t) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        int tn = t + STAGES - 1;
+        if (tn < T)
+            load_stage(As + (tn % STAGES) * A_STAGE, Bs + (tn % STAGES) * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0,
+                       tn * BK, tid);
+        cp_async_commit();
+        compute_stage(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
+    }
+    cp_async_wait<0>();
+    const int l4 = lane & 3, l8 = lane >> 2;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        int row = m0 + wm * 32 + mi * 8 + l8;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int col = n0 + wn * 32 + ni * 8 + 2 * l4;
+            *reinterpret_cast<double2 *>(C + (size_t)row * g.ldc + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    }
+}
+
+// ---- chi-square epilogue: chi2[n] = sum_m (A.B)[m][n]^2 ----------------------------------------
+// One CTA owns a 64-column panel and walks all row tiles, so the row reduction never leaves the
+// CTA: registers -> warp shuffles -> one shared-memory exchange between the two row-warps.
+__global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem, *Bs = smem + STAGES * A_STAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
+    const int n0 = blockIdx.x * BN;
+    const int MT = g.M / BM;
+    // flattened (row tile, k tile) sequence so that the cp.async pipeline never drains
+    auto ktiles = [&](int mt) { return (g.lower_triangular ? min(g.K, (mt + 1) * BM) : g.K) / BK; };
+    int total = 0;
+    for (int mt = 0; mt < MT; ++mt) total += ktiles(mt);
+    int lmt = 0, lkt = 0;  // next tile to load
+    auto issue = [&](int slot) {
+        load_stage(As + slot * A_STAGE, Bs + slot * B_STAGE, g.A, g.Bm, g.lda, g.ldb, lmt * BM, n0, lkt * BK, tid);
+        if (++lkt == ktiles(lmt)) { lkt = 0; ++lmt; }
+    };
+    double colsum[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colsum[j][0] = colsum[j][1] = 0.0;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < total) issue(s);
+        cp_async_commit();
+    }
+    int cmt = 0, ckt = 0;
+    for (int t = 0; t < total; ++t) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (t + STAGES - 1 < total) issue((t + STAGES - 1) % STAGES);
+        cp_async_commit();
+        compute_stage(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
+        if (++ckt == ktiles(cmt)) {
+            // row tile finished: fold its squares into the column sums, restart accumulators
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    colsum[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], colsum[ni][0]);
+                    colsum[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], colsum[ni][1]);
+                    acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                }
+            ckt = 0;
+            ++cmt;
+        }
+    }
+    cp_async_wait<0>();
+    // reduce over the 8 row-lanes of each fragment column (lanes with equal lane%4)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double v = colsum[ni][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            colsum[ni][e] = v;
+        }
+    __syncthreads();
+    double *red = smem;  // [2 row-warps][64 columns]
+    if (lane < 4) {
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int col = wn * 32 + ni * 8 + 2 * lane;
+            red[wm * BN + col] = colsum[ni][0];
+            red[wm * BN + col + 1] = colsum[ni][1];
+        }
+    }
+    __syncthreads();
+    if (tid < BN) {
+        int n = n0 + tid;
+        if (n < g.N) {
+            double v = red[tid] + red[BN + tid];
+            if (g.status && g.status[n]) v = nan("");
+            g.chi2[n] = v;
+        }
+    }
+}
+
+// ---- toy-MC noise ------------------------------------------------------------------------------
+// Counter-based normal deviates keyed by (seed, toy id, element): realisations are independent of
+// how toys are sharded over GPUs (replaces likely::CovarianceMatrix::sample, call site
+// baofit/CorrelationAnalyzer.cc:271).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double counter_normal(unsigned long long seed, unsigned long long toy, unsigned j) {
+    unsigned long long k = splitmix64(seed ^ splitmix64(toy * 0x100000001B3ull + j));
+    unsigned long long k2 = splitmix64(k);
+    double u1 = ((k >> 11) + 1.0) * (1.0 / 9007199254740993.0);  // (0,1]
+    double u2 = (k2 >> 11) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__global__ void toy_noise_kernel(const double *__restrict__ L, int n, int n_pad, const double *__restrict__ truth,
+                                 unsigned long long seed, long long first_toy, int ntoy, double scale,
+                                 double *__restrict__ out) {
+    extern __shared__ double gsh[];  // [n] deviates of this toy
+    int t = blockIdx.x;
+    if (t >= ntoy) return;
+    for (int j = threadIdx.x; j < n; j += blockDim.x)
+        gsh[j] = counter_normal(seed, (unsigned long long)(first_toy + t), (unsigned)j);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double *row = L + (size_t)i * n_pad;
+        double s = 0.0;
+        for (int j = 0; j <= i; ++j) s = fma(row[j], gsh[j], s);
+        out[(size_t)t * n + i] = truth[i] + scale * s;
+    }
+}
+
+void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dgemm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        attr = true;
+    }
+    dim3 grid((g.N + BN - 1) / BN, g.M / BM, batch);
+    dgemm_store_kernel<<<grid, 128, SMEM_BYTES, s>>>(g);
+}
+
+void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dgemm_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        attr = true;
+    }
+    dim3 grid((g.N + BN - 1) / BN, 1, 1);
+    dgemm_chi2_kernel<<<grid, 128, SMEM_BYTES, s>>>(g);
+}
+
+void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth,
+                      unsigned long long seed, long long first_toy, int ntoy, double scale, double *out) {
+    toy_noise_kernel<<<ntoy, 256, n * sizeof(double), s>>>(L, n, n_pad, truth, seed, first_toy, ntoy, scale, out);
+}
+
+}  // namespace bf

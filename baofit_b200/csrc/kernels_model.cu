@@ -1,0 +1,472 @@
+// Model-evaluation kernels: xi(r, mu, z) of B parameter vectors over all bins.
+//
+// Thread mapping everywhere: consecutive lanes = consecutive parameter vectors b, so that the
+// bin-major outputs out[bin*ld + b] are written with coalesced, full-sector fp64 stores and the
+// transposed parameters pT[j*ld + b] are read coalesced. Bin coordinates are warp-uniform.
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace bf {
+
+// ------------------------------------------------------------------------------------------
+// prep: transpose parameters, per-(class, b) redshift-evolution factors, clear status
+// ------------------------------------------------------------------------------------------
+__global__ void prep_kernel(DevModel m, const double *__restrict__ params, int B, int ldb, int nz,
+                            const double *__restrict__ zvals, double *__restrict__ pT, double *__restrict__ S,
+                            int *__restrict__ status) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double *p = params + (size_t)b * m.npar;
+    for (int j = 0; j < m.npar; ++j) pT[(size_t)j * ldb + b] = p[j];
+    double gb = p[m.idx_gamma_bias], gbeta = p[m.idx_gamma_beta], gs = p[m.idx_bao + 4];
+    for (int c = 0; c < nz; ++c) {
+        // redshiftEvolution, baofit/AbsCorrelationModel.cc:159-161
+        double x = (1.0 + zvals[c]) / (1.0 + m.zref);
+        S[(size_t)(c * 3 + 0) * ldb + b] = gb == 0.0 ? 1.0 : pow(x, gb);
+        S[(size_t)(c * 3 + 1) * ldb + b] = gbeta == 0.0 ? 1.0 : pow(x, gbeta);
+        S[(size_t)(c * 3 + 2) * ldb + b] = gs == 0.0 ? 1.0 : pow(x, gs);
+    }
+    status[b] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared tail: dilation of (r,mu), radiation, broadband
+// ------------------------------------------------------------------------------------------
+struct Dilated {
+    double rBAO, muBAO, scalez;
+};
+
+__device__ __forceinline__ Dilated dilate(const DevModel &m, const double *__restrict__ pT, int ldb, double es,
+                                          double r, double mu) {
+    // baofit/BaoCorrelationModel.cc:104-127, baofit/BaoKSpaceCorrelationModel.cc:403-417
+    Dilated d;
+    if (m.flags & BF_FLAG_ANISOTROPIC) {
+        double apar = pT[(size_t)(m.idx_bao + 2) * ldb];
+        double aperp = (m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * apar
+                                                          : pT[(size_t)(m.idx_bao + 3) * ldb];
+        apar *= es;
+        aperp *= es;
+        double musq = mu * mu;
+        d.scalez = sqrt(apar * apar * musq + aperp * aperp * (1.0 - musq));
+        d.rBAO = r * d.scalez;
+        d.muBAO = apar * mu / d.scalez;
+    } else {
+        d.scalez = pT[(size_t)(m.idx_bao + 1) * ldb] * es;
+        d.rBAO = r * d.scalez;
+        d.muBAO = mu;
+    }
+    return d;
+}
+
+__device__ __forceinline__ double post_broadband(const DevModel &m, const double *__restrict__ pT, int ldb,
+                                                 double eb, double xi, double r, double mu, double z, int slot_add,
+                                                 int slot_mul) {
+    if (m.bb[slot_mul].enabled) xi *= 1.0 + broadband_eval(m.bb[slot_mul], pT, ldb, r, mu, z);
+    if (m.bb[slot_add].enabled) xi += broadband_eval(m.bb[slot_add], pT, ldb, r, mu, z) * eb;
+    return xi;
+}
+
+// ------------------------------------------------------------------------------------------
+// r-space model, baofit/BaoCorrelationModel.cc:90-179 (+ AbsCorrelationModel.cc:21-41)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rspace_eval_kernel(EvalArgs a) {
+    const DevModel &m = a.m;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const Internal in = load_internal(m, pT, ldb);
+    const double ampl = pT[(size_t)m.idx_bao * ldb];
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    double rad[4] = {0, 0, 0, 0};
+    if (m.idx_rad >= 0)
+        for (int k = 0; k < 4; ++k) rad[k] = pT[(size_t)(m.idx_rad + k) * ldb];
+    int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
+    for (int i = i0; i < i1; ++i) {
+        double val = 0.0;
+        if (i < a.npts) {
+            double r = a.r[i], mu = a.mu[i], z = a.z[i];
+            int zc = a.zc[i];
+            double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb],
+                   es = S[(size_t)(zc * 3 + 2) * ldb];
+            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            double n0, n2, n4;
+            norm_factors(in.biasSq * eb, in.betaAvg * ebeta, in.betaProd * ebeta * ebeta, n0, n2, n4);
+            double musq = d.muBAO * d.muBAO;
+            double L2 = (-1.0 + 3.0 * musq) * 0.5, L4 = (3.0 + musq * (-30.0 + 35.0 * musq)) * 0.125;
+            double f[3], w[3];
+            spline3_eval(m.fid, m.fid.coef, d.rBAO, f);
+            spline3_eval(m.nw, m.nw.coef, d.rBAO, w);
+            double fid = n0 * f[0] + n2 * L2 * f[1] + n4 * L4 * f[2];
+            double nw = n0 * w[0] + n2 * L2 * w[1] + n4 * L4 * w[2];
+            double peak = ampl * (fid - nw), smooth = nw;
+            if (m.flags & BF_FLAG_DECOUPLED) {
+                double m2 = mu * mu;
+                double L2a = (-1.0 + 3.0 * m2) * 0.5, L4a = (3.0 + m2 * (-30.0 + 35.0 * m2)) * 0.125;
+                spline3_eval(m.nw, m.nw.coef, r, w);
+                smooth = n0 * w[0] + n2 * L2a * w[1] + n4 * L4a * w[2];
+            }
+            double xi = peak + smooth;
+            if (m.metal_kind != BF_METAL_NONE)
+                xi += metal_eval(m, in, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx[i], r, mu);
+            xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DIST_ADD, BF_BB_DIST_MUL);
+            if (m.idx_rad >= 0 && rad[0] > 0.0 && r > 0.0) {  // :165-176
+                double rd = rad[0] / (r * r);
+                rd *= exp(-r / rad[2]);
+                rd *= (1.0 - rad[1] * (1.0 - mu * mu));
+                rd *= exp(-(r * (1.0 - mu) / (1.0 + z)) / rad[3]);
+                xi += rd;
+            }
+            val = xi;
+            if (a.dov) val -= a.dov[(size_t)b * a.npts + i];
+            else if (a.dsub) val -= a.dsub[i];
+        }
+        a.out[(size_t)i * a.ldo + b] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k-space: multipoles of D(k, mu_k), baofit/BaoKSpaceCorrelationModel.cc:215-283 and
+// baofit/NonLinearCorrectionModel.cc:49-86
+// ------------------------------------------------------------------------------------------
+struct KPar {
+    double betaz, beta2z, snl_par2, snl_perp2;
+    double uv[3], hcd[3], bs[2], sg, sl;
+    double qnl, kv, av, bv, kp;
+};
+
+__device__ __forceinline__ double nl_correction(const DevModel &m, const ProjArgs &a, const KPar &kp, double k,
+                                                double mu_k, double pk) {
+    if (m.flags & (BF_FLAG_NL_CORRECTION | BF_FLAG_FIT_NL_CORRECTION)) {
+        pk = pk * a.nl_pk_scale;
+        double deltaSq = k * k * k * pk / (2.0 * M_PI * M_PI);
+        double growth = kp.qnl * deltaSq;
+        double pec = pow(k / kp.kv, kp.av) * pow(fabs(mu_k), kp.bv);
+        double pressure = (k / kp.kp) * (k / kp.kp);
+        return exp(growth * (1.0 - pec) - pressure);
+    }
+    if (m.flags & BF_FLAG_NL_CORRECTION_ALT) {
+        const double knl = 6.4, pnl = 0.569, kpp = 15.3, pp = 2.01, kv0 = 1.22, pv = 1.5, kvi = 0.923, pvi = 0.451;
+        double kvel = kv0 * pow(1.0 + k / kvi, pvi);
+        double growth = pow(k / knl, pnl), pressure = pow(k / kpp, pp);
+        double pec = pow(fabs(k * mu_k) / kvel, pv);
+        return exp(growth - pressure - pec);
+    }
+    return 1.0;
+}
+
+__device__ __forceinline__ double kspace_distortion(const DevModel &m, const ProjArgs &a, const KPar &kp, double k,
+                                                    double mu_k, double pk) {
+    const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
+    double mu2 = mu_k * mu_k, kpar = fabs(k * mu_k);
+    double tracer1 = 1.0 + kp.betaz * mu2;
+    double tracer2 = cross ? 1.0 + kp.beta2z * mu2 : tracer1;
+    double linear = tracer1 * tracer2;
+    if (m.flags & BF_FLAG_UVFLUCTUATION) {
+        double s = kp.uv[2] * k, Ws = atan(s) / s;
+        double uvFunc = 1.0 + kp.uv[0] * Ws / (1.0 + kp.uv[1] * Ws);
+        tracer1 = uvFunc + kp.betaz * mu2;
+        tracer2 = cross ? 1.0 + kp.beta2z * mu2 : tracer1;
+        linear = tracer1 * tracer2;
+    }
+    if (m.flags & (BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT)) {
+        double x = kp.hcd[2] * kpar;
+        double hcdFunc = (m.flags & BF_FLAG_HCD_MODEL) ? sin(x) / x : exp(-x * x / 2.0);
+        double tracerHcd = kp.hcd[1] * (1.0 + kp.hcd[0] * mu2) * hcdFunc;
+        linear = cross ? tracer1 * tracer2 + tracer2 * tracerHcd
+                       : tracer1 * tracer1 + 2.0 * tracer1 * tracerHcd + tracerHcd * tracerHcd;
+    }
+    double smoothbin = 1.0;
+    if (m.flags & (BF_FLAG_BIN_SMOOTH | BF_FLAG_BIN_SMOOTH_ALT)) {
+        if (m.flags & BF_FLAG_BIN_SMOOTH) {
+            double kperp = k * sqrt(1.0 - mu2);
+            double xp = 0.5 * kp.bs[0] * kpar, xt = 0.5 * kp.bs[1] * kperp;
+            smoothbin = (sin(xp) / xp) * (sin(xt) / xt);
+        }
+        if (m.flags & BF_FLAG_BIN_SMOOTH_ALT) {
+            double bs2 = kp.bs[0] * kp.bs[0] * mu2 + kp.bs[1] * kp.bs[1] * (1.0 - mu2);
+            smoothbin = exp(-0.5 * bs2 * k * k);
+        }
+        smoothbin *= smoothbin;
+    }
+    double gaussmooth = (m.flags & BF_FLAG_SMOOTH_GAUSS) ? exp(-0.5 * kp.sg * kp.sg * kpar * kpar) : 1.0;
+    double lorsmooth = (m.flags & BF_FLAG_SMOOTH_LORENTZ) ? sqrt(1.0 / (1.0 + kp.sl * kp.sl * kpar * kpar)) : 1.0;
+    double snl2 = kp.snl_par2 * mu2 + kp.snl_perp2 * (1.0 - mu2);
+    double nonlinear = exp(-0.5 * snl2 * k * k);
+    double nlc = nl_correction(m, a, kp, k, mu_k, pk);
+    if (cross) nlc = sqrt(nlc);
+    return nonlinear * nlc * linear * smoothbin * gaussmooth * lorsmooth;
+}
+
+// G[((comp*3 + l)*nk_pad + i)*ldb + b] = (2l+1) Int_0^1 L_l(mu) D_comp(k_i, mu; p_b) dmu
+__global__ void __launch_bounds__(128) kspace_project_kernel(ProjArgs a) {
+    const DevModel &m = a.m;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const int comp = blockIdx.z;
+    KPar kp;
+    {
+        double ebeta = a.S[(size_t)(a.zc_trigger * 3 + 1) * ldb + b];
+        double beta = pT[(size_t)m.idx_beta * ldb];
+        kp.betaz = beta * ebeta;
+        kp.beta2z = 0.0;
+        if (m.flags & BF_FLAG_CROSS_CORRELATION)
+            kp.beta2z = pT[(size_t)m.idx_bb2 * ldb] / pT[(size_t)m.idx_bias2 * ldb] * ebeta;
+        double snlPerp = pT[(size_t)m.idx_nl * ldb], snlPar = snlPerp * pT[(size_t)(m.idx_nl + 1) * ldb];
+        kp.snl_perp2 = snlPerp * snlPerp;
+        kp.snl_par2 = snlPar * snlPar;
+        if (comp == 1 && !(m.flags & BF_FLAG_NL_BROADBAND)) kp.snl_perp2 = kp.snl_par2 = 0.0;  // :364-367
+        for (int k = 0; k < 3; ++k) {
+            kp.uv[k] = m.idx_uv >= 0 ? pT[(size_t)(m.idx_uv + k) * ldb] : 0.0;
+            kp.hcd[k] = m.idx_hcd >= 0 ? pT[(size_t)(m.idx_hcd + k) * ldb] : 0.0;
+        }
+        for (int k = 0; k < 2; ++k) kp.bs[k] = m.idx_bs >= 0 ? pT[(size_t)(m.idx_bs + k) * ldb] : 0.0;
+        kp.sg = m.idx_smgaus >= 0 ? pT[(size_t)m.idx_smgaus * ldb] : 0.0;
+        kp.sl = m.idx_smlor >= 0 ? pT[(size_t)m.idx_smlor * ldb] : 0.0;
+        kp.qnl = a.nl_tab[0]; kp.kv = a.nl_tab[1]; kp.av = a.nl_tab[2]; kp.bv = a.nl_tab[3]; kp.kp = a.nl_tab[4];
+        if (m.flags & BF_FLAG_FIT_NL_CORRECTION) {
+            kp.qnl = pT[(size_t)m.idx_nlcorr * ldb];
+            kp.kp = pT[(size_t)(m.idx_nlcorr + 1) * ldb];
+        }
+    }
+    const int lmax = m.ell_max / 2;
+    int i0 = blockIdx.y * a.k_per_block, i1 = min(i0 + a.k_per_block, m.nk_pad);
+    for (int i = i0; i < i1; ++i) {
+        double s0 = 0.0, s2 = 0.0, s4 = 0.0;
+        if (i < m.nk) {
+            double k = m.kc[i], pk = m.pk_kc[comp * m.nk + i];
+#pragma unroll 4
+            for (int q = 0; q < kMuNodes; ++q) {
+                double mu = m.mu_x[q], mu2 = mu * mu;
+                double wD = m.mu_w[q] * kspace_distortion(m, a, kp, k, mu, pk);
+                s0 += wD;
+                s2 += wD * ((-1.0 + 3.0 * mu2) * 0.5);
+                s4 += wD * ((3.0 + mu2 * (-30.0 + 35.0 * mu2)) * 0.125);
+            }
+        }
+        size_t o = ((size_t)(comp * 3) * m.nk_pad + i) * ldb + b;
+        size_t st = (size_t)m.nk_pad * ldb;
+        a.G[o] = s0;
+        a.G[o + st] = lmax >= 1 ? 5.0 * s2 : 0.0;
+        a.G[o + 2 * st] = lmax >= 2 ? 9.0 * s4 : 0.0;
+    }
+}
+
+// Natural-spline second derivatives (gsl "c" = y''/2) of the per-vector multipole tables on the
+// uniform radial grid: constant (1,4,1) tridiagonal system, factors precomputed on the host.
+// One thread per (b, table); consecutive lanes = consecutive b => coalesced column sweeps.
+__global__ void __launch_bounds__(128) kspace_thomas_kernel(int B, int ldb, int nr, int nr_pad, double h,
+                                                            const double *__restrict__ th_w,
+                                                            const double *__restrict__ th_inv_diag,
+                                                            const double *__restrict__ T, double *__restrict__ C2) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double *y = T + (size_t)blockIdx.y * nr_pad * ldb + b;
+    double *c = C2 + (size_t)blockIdx.y * nr_pad * ldb + b;
+    const int msz = nr - 2;
+    const double inv_h = 1.0 / h;
+    c[0] = 0.0;
+    double y0 = y[0], y1 = y[ldb], gprev = 0.0;
+    for (int i = 0; i < msz; ++i) {
+        double y2 = y[(size_t)(i + 2) * ldb];
+        double g = 3.0 * ((y2 - y1) * inv_h - (y1 - y0) * inv_h);
+        if (i > 0) g -= th_w[i] * gprev;
+        c[(size_t)(i + 1) * ldb] = g;
+        gprev = g;
+        y0 = y1;
+        y1 = y2;
+    }
+    c[(size_t)(nr - 1) * ldb] = 0.0;
+    double cnext = 0.0;
+    for (int i = msz - 1; i >= 0; --i) {
+        double ci = (c[(size_t)(i + 1) * ldb] - h * cnext) * th_inv_diag[i];
+        c[(size_t)(i + 1) * ldb] = ci;
+        cnext = ci;
+    }
+}
+
+// cosmo::DistortedPowerCorrelation::getCorrelation: sum_l L_l(mu) spline_l(r) for one component
+__device__ __forceinline__ double kspace_correlation(const EvalArgs &a, int comp, int b, double r, double mu) {
+    const DevModel &m = a.m;
+    const int nr = m.nr;
+    const size_t st = (size_t)m.nr_pad * a.ldb;
+    const double *T = a.T + (size_t)(comp * 3) * st + b;
+    const double *C = a.C2 + (size_t)(comp * 3) * st + b;
+    double musq = mu * mu;
+    double Lw[3] = {1.0, (-1.0 + 3.0 * musq) * 0.5, (3.0 + musq * (-30.0 + 35.0 * musq)) * 0.125};
+    double rlast = m.tr_r0 + (nr - 1) * m.tr_dr;
+    double out = 0.0;
+    if (r <= m.tr_r0 || r >= rlast) {
+        size_t row = r <= m.tr_r0 ? 0 : (size_t)(nr - 1) * a.ldb;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) out += Lw[l] * T[l * st + row];
+        return out;
+    }
+    int j = (int)((r - m.tr_r0) * m.tr_inv_dr);
+    j = max(0, min(j, nr - 2));
+    double xl = m.tr_r0 + j * m.tr_dr;
+    if (r < xl && j > 0) { --j; xl = m.tr_r0 + j * m.tr_dr; }
+    double xh = m.tr_r0 + (j + 1) * m.tr_dr;
+    if (r >= xh && j < nr - 2) { ++j; xl = xh; xh = m.tr_r0 + (j + 1) * m.tr_dr; }
+    double dx = xh - xl, t = r - xl;
+    size_t row = (size_t)j * a.ldb;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        double ylo = T[l * st + row], yhi = T[l * st + row + a.ldb];
+        double clo = C[l * st + row], chi = C[l * st + row + a.ldb];
+        double bb = (yhi - ylo) / dx - dx * (chi + 2.0 * clo) / 3.0;
+        double dd = (chi - clo) / (3.0 * dx);
+        out += Lw[l] * (ylo + t * (bb + t * (clo + t * dd)));
+    }
+    return out;
+}
+
+// k-space model at a set of points, baofit/BaoKSpaceCorrelationModel.cc:285-538.
+//   mode 0: data bins, no distortion matrix: full model incl. post broadband (:392-455,:529-535)
+//   mode 1: grid bins for the distortion matrix: undistorted xi_u with the range zeroing and the
+//           pre-matrix broadband (:460-521)
+__global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
+    const DevModel &m = a.m;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const Internal in = load_internal(m, pT, ldb);
+    const double ampl = pT[(size_t)m.idx_bao * ldb];
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    double rad[4] = {0, 0, 0, 0};
+    if (m.flags & BF_FLAG_RADIATION_MODEL)
+        for (int k = 0; k < 4; ++k) rad[k] = pT[(size_t)(m.idx_rad + k) * ldb];
+    int st_bits = 0;
+    int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
+    for (int i = i0; i < i1; ++i) {
+        double val = 0.0;
+        if (i < a.npts) {
+            double r = a.r[i], mu = a.mu[i], z = a.z[i];
+            int zc = a.zc[i];
+            double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
+            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            bool zero = false;
+            if (a.mode == 1) {
+                zero = (r < m.rlo || r > m.rhi) || (d.rBAO < m.rlo || d.rBAO > m.rhi);
+            } else {
+                if (d.scalez < m.dilmin) st_bits |= BF_STATUS_DILATION_MIN;
+                else if (d.scalez > m.dilmax) st_bits |= BF_STATUS_DILATION_MAX;
+            }
+            if (!zero) {
+                double peak = kspace_correlation(a, 0, b, d.rBAO, d.muBAO);
+                double smooth = (m.flags & BF_FLAG_DECOUPLED) ? kspace_correlation(a, 1, b, r, mu)
+                                                              : kspace_correlation(a, 1, b, d.rBAO, d.muBAO);
+                double xi = in.biasSq * eb * (ampl * peak + smooth);
+                if (m.metal_kind != BF_METAL_NONE)
+                    xi += metal_eval(m, in, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx ? a.gidx[i] : i, r, mu);
+                if ((m.flags & BF_FLAG_RADIATION_MODEL) && r > 0.0) {  // :441-455
+                    double rd = rad[0] / (r * r);
+                    if (rad[1] > 0.0) rd *= (1.0 - rad[1] * (1.0 - mu * mu));
+                    if (rad[2] > 0.0) rd *= exp(-r / rad[2]);
+                    if (rad[3] > 0.0) rd *= exp(-(r * (1.0 - mu) / (1.0 + z)) / rad[3]);
+                    xi += rd;
+                }
+                if (a.mode == 1) xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL);
+                else xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DIST_ADD, BF_BB_DIST_MUL);
+                val = xi;
+            }
+            if (a.mode == 0) {
+                if (st_bits) val = nan("");
+                if (a.dov) val -= a.dov[(size_t)b * a.npts + i];
+                else if (a.dsub) val -= a.dsub[i];
+            }
+        }
+        a.out[(size_t)i * a.ldo + b] = val;
+    }
+    if (st_bits) atomicOr(a.status + b, st_bits);
+}
+
+// Distortion-matrix tail for data bins: Z = Y (1 + dist mul) + dist add * evol - d, plus the
+// dilation-limit check of the data bin itself (baofit/BaoKSpaceCorrelationModel.cc:420-427,
+// :529-535). Y = D_kept . xi_u comes from the DMMA GEMM.
+__global__ void __launch_bounds__(128) dist_post_kernel(EvalArgs a) {
+    const DevModel &m = a.m;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    int st_bits = 0;
+    int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
+    for (int i = i0; i < i1; ++i) {
+        double val = 0.0;
+        if (i < a.npts) {
+            double r = a.r[i], mu = a.mu[i], z = a.z[i];
+            int zc = a.zc[i];
+            double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
+            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            if (d.scalez < m.dilmin) st_bits |= BF_STATUS_DILATION_MIN;
+            else if (d.scalez > m.dilmax) st_bits |= BF_STATUS_DILATION_MAX;
+            double xi = a.in[(size_t)i * a.ldo + b];
+            xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DIST_ADD, BF_BB_DIST_MUL);
+            val = st_bits ? nan("") : xi;
+            if (a.dov) val -= a.dov[(size_t)b * a.npts + i];
+            else if (a.dsub) val -= a.dsub[i];
+        }
+        a.out[(size_t)i * a.ldo + b] = val;
+    }
+    if (st_bits) atomicOr(a.status + b, st_bits);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static int pick_pts_per_block(int npts_pad, int B, int sm_count) {
+    // enough CTAs for >= 4 waves when B is small, long bin loops when B is large
+    int bx = (B + 127) / 128;
+    int want = sm_count * 8;
+    int by = max(1, min(npts_pad, (want + bx - 1) / bx));
+    int ppb = (npts_pad + by - 1) / by;
+    return max(1, ppb);
+}
+
+void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
+                 const double *zvals, double *pT, double *S, int *status) {
+    prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(m, params, B, ldb, nz, zvals, pT, S, status);
+}
+
+void launch_rspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
+    a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
+    dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
+    rspace_eval_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count) {
+    a.k_per_block = pick_pts_per_block(a.m.nk_pad, a.B, sm_count);
+    dim3 grid((a.B + 127) / 128, (a.m.nk_pad + a.k_per_block - 1) / a.k_per_block, 2);
+    kspace_project_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,
+                          const double *th_inv_diag, const double *T, double *C2) {
+    dim3 grid((B + 127) / 128, 6);
+    kspace_thomas_kernel<<<grid, 128, 0, s>>>(B, ldb, nr, nr_pad, h, th_w, th_inv_diag, T, C2);
+}
+
+void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
+    a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
+    dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
+    kspace_eval_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count) {
+    a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
+    dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
+    dist_post_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+}  // namespace bf
