@@ -58,6 +58,7 @@ def lib():
         L.orc_kspace_distortion.restype = C.c_double
         L.orc_kspace_distortion.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_int, C.c_double, C.c_double]
         L.orc_transform.argtypes = [C.c_void_p, c_double_p, C.c_double, c_double_p]
+        L.orc_transform_sub.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_int, c_double_p]
         L.orc_transform_nr.argtypes = [C.c_void_p]
         L.orc_transform_r0.restype = C.c_double
         L.orc_transform_r0.argtypes = [C.c_void_p]
@@ -97,11 +98,12 @@ class OracleModel:
         p = np.ascontiguousarray(params, dtype=np.float64)
         return lib().orc_evaluate_multipole(self.h, _dp(p), r, ell, z, nmu)
 
-    def transform(self, params, z_trigger):
+    def transform(self, params, z_trigger, jstep=1):
+        """xi_ell(r_j) tables [comp][ell][j]; with jstep > 1 only every jstep-th radius is filled."""
         p = np.ascontiguousarray(params, dtype=np.float64)
         nr = lib().orc_transform_nr(self.h)
-        out = np.zeros((2, 3, nr))
-        if lib().orc_transform(self.h, _dp(p), z_trigger, _dp(out)):
+        out = np.full((2, 3, nr), np.nan)
+        if lib().orc_transform_sub(self.h, _dp(p), z_trigger, jstep, _dp(out)):
             raise RuntimeError(lib().orc_last_error().decode())
         r = lib().orc_transform_r0(self.h) + lib().orc_transform_dr(self.h) * np.arange(nr)
         return r, out

@@ -761,28 +761,33 @@ static void sph_bessel_024(double x, double *j0, double *j2, double *j4) {
     *j4 = (105 * xi2 * xi2 - 45 * xi2 + 1) * s * xi - (105 * xi2 - 10) * c * xi2;
 }
 
-/* brute-force Int G(k) k^2 j_ell(k r) dk for G piecewise linear on the fine nodes, ell=0,2,4 */
-static void hankel_brute(int nf, const double *kf, const double *g, double r, double out[3]) {
+/* brute-force Int G_l(k) k^2 j_l(k r) dk, l = 0,2,4, for G_l piecewise linear on the fine nodes:
+ * every fine panel is cut into sub-panels of at most 1.5 rad of phase, 8-point Gauss-Legendre each */
+static void hankel_brute(int nf, const double *kf, const double *g0, const double *g2, const double *g4, double r,
+                         double out[3]) {
     static const double glx[8] = {-0.9602898564975363, -0.7966664774136267, -0.5255324099163290, -0.1834346424956498,
                                   0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
     static const double glw[8] = {0.1012285362903763, 0.2223810344533745, 0.3137066458778873, 0.3626837833783620,
                                   0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+    const double *g[3] = {g0, g2, g4};
     double acc[3] = {0, 0, 0}, comp[3] = {0, 0, 0};
     int f, s, q, l;
     for (f = 0; f + 1 < nf; ++f) {
-        double a = kf[f], b = kf[f + 1], ga = g[f], gb = g[f + 1];
-        if (ga == 0 && gb == 0) continue;
+        double a = kf[f], b = kf[f + 1];
+        int any = 0;
+        for (l = 0; l < 3; ++l) any |= (g[l][f] != 0 || g[l][f + 1] != 0);
+        if (!any) continue;
         int nsub = (int)ceil((b - a) * r / 1.5) + 1;
         double hs = (b - a) / nsub;
         for (s = 0; s < nsub; ++s) {
             double lo = a + s * hs, part[3] = {0, 0, 0};
             for (q = 0; q < 8; ++q) {
                 double k = lo + 0.5 * hs * (1 + glx[q]);
-                double G = ga + (gb - ga) * (k - a) / (b - a);
-                double j0, j2, j4;
-                sph_bessel_024(k * r, &j0, &j2, &j4);
-                double w = 0.5 * hs * glw[q] * k * k * G;
-                part[0] += w * j0; part[1] += w * j2; part[2] += w * j4;
+                double t = (k - a) / (b - a);
+                double j[3];
+                sph_bessel_024(k * r, &j[0], &j[1], &j[2]);
+                double w = 0.5 * hs * glw[q] * k * k;
+                for (l = 0; l < 3; ++l) part[l] += w * (g[l][f] + (g[l][f + 1] - g[l][f]) * t) * j[l];
             }
             for (l = 0; l < 3; ++l) { /* Kahan */
                 double y = part[l] - comp[l], t = acc[l] + y;
@@ -814,7 +819,7 @@ double orc_hankel_table(int n, const double *k, const double *pk, int ell, doubl
         }
     kf[nf - 1] = k[n - 1];
     pf[nf - 1] = pk[n - 1];
-    hankel_brute(nf, kf, pf, r, out);
+    hankel_brute(nf, kf, pf, pf, pf, r, out);
     spline_free(&sp);
     free(lnk); free(kf); free(pf);
     return out[ell / 2];
@@ -824,25 +829,34 @@ int orc_transform_nr(const orc_model *m) { return m->nr; }
 double orc_transform_r0(const orc_model *m) { return m->r0; }
 double orc_transform_dr(const orc_model *m) { return m->dr; }
 
-/* transform of one component at radial nodes j0, j0+jstep, ...; out[ell][j] (others untouched) */
+/* transform of one component at radial nodes 0, jstep, 2 jstep, ...; out[ell*nr + j] (others untouched) */
 static void transform_component(orc_model *m, const double *p, double z, int component, int jstep, double *out) {
     int lmaxi = m->d.ell_max / 2, l, i, f, j;
     double *dl = (double *)malloc(sizeof(double) * m->nk);
-    double *g = (double *)malloc(sizeof(double) * m->nfine);
+    double *g = (double *)calloc((size_t)3 * m->nfine, sizeof(double));
     const double *pf = component == 0 ? m->pf_pk : m->pf_nw;
     kspace_set_state(m, p, z, component);
-    for (l = 0; l < 3; ++l) {
-        if (l > lmaxi) { for (j = 0; j < m->nr; j += jstep) out[l * m->nr + j] = 0; continue; }
+    for (l = 0; l <= lmaxi; ++l) {
         for (i = 0; i < m->nk; ++i) dl[i] = d_multipole(m, p, component, i, 2 * l);
-        for (f = 0; f < m->nfine; ++f) g[f] = pf[f] * lagrange4(m, dl, log(m->kf[f]));
-        for (j = 0; j < m->nr; j += jstep) {
-            double o3[3];
-            hankel_brute(m->nfine, m->kf, g, m->tab_r[j], o3);
-            out[l * m->nr + j] = o3[l];
-        }
+        for (f = 0; f < m->nfine; ++f) g[(size_t)l * m->nfine + f] = pf[f] * lagrange4(m, dl, log(m->kf[f]));
+    }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) private(l)
+#endif
+    for (j = 0; j < m->nr; j += jstep) {
+        double o3[3];
+        hankel_brute(m->nfine, m->kf, g, g + m->nfine, g + 2 * (size_t)m->nfine, m->tab_r[j], o3);
+        for (l = 0; l < 3; ++l) out[l * m->nr + j] = o3[l];
     }
     free(dl);
     free(g);
+}
+
+int orc_transform_sub(orc_model *m, const double *params, double z_trigger, int jstep, double *out) {
+    if (m->d.kind != BF_MODEL_KSPACE) { set_err("orc_transform: not a k-space model"); return -1; }
+    transform_component(m, params, z_trigger, 0, jstep, out);
+    transform_component(m, params, z_trigger, 1, jstep, out + 3 * (size_t)m->nr);
+    return 0;
 }
 
 int orc_transform(orc_model *m, const double *params, double z_trigger, double *out) {
@@ -1101,8 +1115,12 @@ int orc_chi2_batch(orc_model *m, const orc_data *d, const double *params, int B,
                    double *chi2, int *status, double *pred, int ldp, int nthreads) {
     int n = d->d.n_data, npar = m->d.npar;
     if (nthreads < 1) nthreads = 1;
+    int outer = nthreads;
 #ifdef _OPENMP
-#pragma omp parallel num_threads(nthreads)
+    if (m->d.kind == BF_MODEL_KSPACE) { outer = 1; omp_set_num_threads(nthreads); }
+#endif
+#ifdef _OPENMP
+#pragma omp parallel num_threads(outer)
 #endif
     {
         orc_model *mc = model_thread_clone(m);

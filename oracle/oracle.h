@@ -71,6 +71,8 @@ double orc_kspace_distortion(orc_model *m, const double *params, double z, int c
 /* brute-force P(k) -> xi_ell(r) transform of component comp (0 peak, 1 no-wiggles) at the
  * model's r nodes; out[3][n_r]; also returns n_r, r0, dr via the getters below */
 int orc_transform(orc_model *m, const double *params, double z_trigger, double *out);
+/* same, only at radial nodes 0, jstep, 2 jstep, ... (other entries of out untouched) */
+int orc_transform_sub(orc_model *m, const double *params, double z_trigger, int jstep, double *out);
 int orc_transform_nr(const orc_model *m);
 double orc_transform_r0(const orc_model *m);
 double orc_transform_dr(const orc_model *m);

@@ -48,3 +48,73 @@ def test_rspace_qso_cross(ctx):
     e_pred, e_chi2 = _compare(ctx, m, d, 333, 12, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5),
                                                           "delta-v": (-300, 300)})
     assert e_pred < RTOL and e_chi2 < RTOL, (e_pred, e_chi2)
+
+
+def test_kspace_transform_tables(ctx):
+    """P(k) -> xi_ell(r) tables of the peak / no-wiggles components: Filon weights + device
+    projection + DMMA GEMM versus the oracle's brute-force quadrature of the same definition."""
+    m, d = W.qso_kspace(with_dist_matrix=False, with_metals=False)
+    rng = np.random.Generator(np.random.PCG64(5))
+    params = m.random_batch(3, rng)
+    gm = capi.Model(ctx, m)
+    r, tabs = gm.transform(params, 2.35717)
+    om = oracle.OracleModel(m)
+    for b in range(params.shape[0]):
+        ro, ref = om.transform(params[b], 2.35717, jstep=31)
+        sel = ~np.isnan(ref[0, 0])
+        assert np.allclose(r, ro, rtol=0, atol=1e-12)
+        for c in range(2):
+            for l in range(3):
+                got, want = tabs[c, l, sel, b], ref[c, l, sel]
+                err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+                assert err < RTOL, (b, c, l, err)
+    gm.close()
+
+
+def test_kspace_qso_cross_plain(ctx):
+    m, d = W.qso_kspace(with_dist_matrix=False, with_metals=False)
+    e_pred, e_chi2 = _compare(ctx, m, d, 4, 21, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.4)})
+    assert e_pred < RTOL and e_chi2 < RTOL, (e_pred, e_chi2)
+
+
+def test_kspace_qso_cross_distortion_matrix_metals(ctx):
+    """BASELINE config 4: cross-correlation k-space model + distortion matrix + bicubic metals."""
+    m, d = W.qso_kspace()
+    rng = np.random.Generator(np.random.PCG64(22))
+    params = m.random_batch(4, rng, sweep={"BAO alpha-parallel": (0.85, 1.2), "BAO alpha-perp": (0.7, 1.3),
+                                           "delta-v": (-200, 200)})
+    for j in range(m.desc.npar):
+        if m.names[j].startswith("bias Si"):
+            params[:, j] *= rng.uniform(0.5, 2.0, size=params.shape[0])
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    om, od = oracle.OracleModel(m), oracle.OracleData(d)
+    xiu, st = capi.eval_undistorted_batch(ctx, gm, gd, params)
+    for b in range(params.shape[0]):
+        ref, _ = oracle.undistorted(om, od, params[b], d.desc.n_grid)
+        assert rel_err_bins(xiu[:, b], ref) < RTOL
+    pred, status = capi.eval_batch(ctx, gm, gd, params)
+    chi2, _ = capi.chi2_batch(ctx, gm, gd, params)
+    ref_chi2, ref_status, ref_pred = oracle.chi2_batch(om, od, params, want_pred=True, nthreads=8)
+    assert np.array_equal(status, ref_status)
+    assert rel_err_bins(pred, ref_pred) < RTOL
+    assert rel_err(chi2, ref_chi2) < RTOL
+    gm.close(), gd.close()
+
+
+def test_kspace_dilation_limits_flag_not_abort(ctx):
+    """The reference throws on dilation limits (BaoKSpaceCorrelationModel.cc:420-427); a batch
+    flags the offending vectors instead and the others stay valid."""
+    m, d = W.qso_kspace(with_dist_matrix=False, with_metals=False)
+    params = np.tile(m.values, (3, 1))
+    params[1, m.index("BAO alpha-parallel")] = 1.7
+    params[1, m.index("BAO alpha-perp")] = 1.7
+    params[2, m.index("BAO alpha-parallel")] = 0.3
+    params[2, m.index("BAO alpha-perp")] = 0.3
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    chi2, status = capi.chi2_batch(ctx, gm, gd, params)
+    assert status[0] == 0 and np.isfinite(chi2[0])
+    assert status[1] == 2 and np.isnan(chi2[1])
+    assert status[2] == 1 and np.isnan(chi2[2])
+    pred, st = capi.eval_batch(ctx, gm, gd, params)
+    assert np.all(np.isnan(pred[:, 1])) and np.all(np.isnan(pred[:, 2])) and np.all(np.isfinite(pred[:, 0]))
+    gm.close(), gd.close()
