@@ -17,7 +17,7 @@ c_int_p = C.POINTER(C.c_int)
 
 EXPORTS = [
     "bf_last_error", "bf_version", "bf_ctx_create", "bf_ctx_destroy", "bf_ctx_launch_count",
-    "bf_ctx_synchronize", "bf_ctx_stream", "bf_model_create", "bf_model_destroy", "bf_model_npar",
+    "bf_ctx_synchronize", "bf_ctx_stream", "bf_ctx_set_profiling", "bf_ctx_get_profile", "bf_model_create", "bf_model_destroy", "bf_model_npar",
     "bf_data_create", "bf_data_destroy", "bf_data_ndata", "bf_eval_batch", "bf_chi2_batch",
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
@@ -45,6 +45,9 @@ def lib():
         L.bf_ctx_synchronize.argtypes = [C.c_void_p]
         L.bf_ctx_stream.restype = C.c_void_p
         L.bf_ctx_stream.argtypes = [C.c_void_p]
+        L.bf_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.bf_ctx_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p,
+                                         C.POINTER(C.c_longlong)]
         L.bf_model_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.bf_model_destroy.argtypes = [C.c_void_p]
         L.bf_model_npar.argtypes = [C.c_void_p]
@@ -101,6 +104,18 @@ class Context:
     @property
     def stream(self):
         return lib().bf_ctx_stream(self.h)
+
+    def set_profiling(self, enable):
+        _check(lib().bf_ctx_set_profiling(self.h, 1 if enable else 0))
+
+    def get_profile(self):
+        """{kernel name: (total ms, launches)} since profiling was enabled."""
+        n = 64
+        names = (C.c_char_p * n)()
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        k = lib().bf_ctx_get_profile(self.h, n, names, ms, cnt)
+        return {names[i].decode(): (ms[i], cnt[i]) for i in range(min(k, n))}
 
 
 class Model:

@@ -65,6 +65,72 @@ extern "C" int bf_ctx_synchronize(bf_ctx *c) {
     return BF_OK;
 }
 
+extern "C" int bf_ctx_set_profiling(bf_ctx *c, int enable) {
+    if (!c) BF_FAIL(BF_ERR_OPTIONS, "null context");
+    BF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    c->prof_pending.clear();
+    c->prof_acc.clear();
+    c->profiling = enable != 0;
+    return BF_OK;
+}
+
+static int prof_drain(bf_ctx *c) {
+    BF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_pending) {
+        float ms = 0;
+        BF_CUDA_OK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        auto &acc = c->prof_acc[r.name];
+        acc.first += ms;
+        acc.second += 1;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    c->prof_pending.clear();
+    return BF_OK;
+}
+
+extern "C" int bf_ctx_get_profile(bf_ctx *c, int max_entries, const char **names, double *ms_total,
+                                  long long *launches) {
+    if (!c) return 0;
+    if (prof_drain(c)) return 0;
+    int k = 0;
+    for (auto &kv : c->prof_acc) {
+        if (k < max_entries) {
+            if (names) names[k] = kv.first.c_str();
+            if (ms_total) ms_total[k] = kv.second.first;
+            if (launches) launches[k] = kv.second.second;
+        }
+        ++k;
+    }
+    return k;
+}
+
+namespace {
+struct ProfScope {
+    bf_ctx *c;
+    bf_ctx::ProfRec rec{};
+    ProfScope(bf_ctx *ctx, const char *name) : c(ctx) {
+        c->launches++;
+        if (!c->profiling) return;
+        rec.name = name;
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        cudaEventRecord(rec.e0, c->stream);
+    }
+    ~ProfScope() {
+        if (!c->profiling) return;
+        cudaEventRecord(rec.e1, c->stream);
+        c->prof_pending.push_back(rec);
+    }
+};
+}  // namespace
+#define BF_KERNEL(ctx, name, call) \
+    do {                           \
+        ProfScope _ps(ctx, name);  \
+        call;                      \
+    } while (0)
+
 static int ensure(void **p, size_t *have, size_t need) {
     if (*have >= need) return BF_OK;
     if (*p) BF_CUDA_OK(cudaFree(*p));
@@ -557,8 +623,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         BF_CUDA_OK(cudaMemcpyAsync(tmp_z, &z_trigger_override, sizeof(double), cudaMemcpyHostToDevice, s));
         d_zvals = tmp_z;
     }
-    launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, w.pT, w.S, w.status);
-    ctx->launches++;
+    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, w.pT, w.S, w.status));
 
     if (dm.kind == BF_MODEL_KSPACE) {
         ProjArgs pa;
@@ -569,14 +634,13 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         double zeff = dm.zeff > 0 ? dm.zeff : ztrig;
         nl_table(dm, zeff, pa.nl_tab, &pa.nl_pk_scale);
         pa.G = w.G;
-        launch_kspace_project(s, pa, ctx->sm_count);
+        BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));
         GemmArgs g{};
         g.A = dm.hankel; g.Bm = w.G; g.C = w.T;
         g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
         g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
         g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
-        launch_gemm_store(s, g, 6);
-        ctx->launches += 2;
+        BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6));
         if (what == OUT_TRANSFORM) {
             // out[((comp*3+l)*nr + j)*ldo + b]
             for (int t = 0; t < 6; ++t)
@@ -586,8 +650,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
             return BF_OK;
         }
-        launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2);
-        ctx->launches++;
+        BF_KERNEL(ctx, "kspace_thomas_kernel",
+                  launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2));
     }
 
     EvalArgs a;
@@ -606,24 +670,21 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.mode = 1;
         a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
         if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
-        launch_kspace_eval(s, a, ctx->sm_count);
-        ctx->launches++;
+        BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
         if (what == OUT_XIU) finished = true;
         if (!finished) {
             GemmArgs g{};
             g.A = plan->d_Dkept; g.Bm = w.XiU; g.C = w.Y;
             g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad;
             g.lda = d->n_grid_pad; g.ldb = ldb; g.ldc = ldb;
-            launch_gemm_store(s, g, 1);
-            ctx->launches++;
+            BF_KERNEL(ctx, "dgemm_store_kernel[distortion]", launch_gemm_store(s, g, 1));
             // tail on the data bins: post-matrix broadband, dilation check, residual.
             // Y (ld = ldb) -> Z (ld = ldb); predictions are copied out row by row afterwards.
             a.npts = d->n; a.npts_pad = d->n_pad;
             a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
             a.in = w.Y; a.out = w.Z; a.ldo = ldb;
             a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
-            launch_dist_post(s, a, ctx->sm_count);
-            ctx->launches++;
+            BF_KERNEL(ctx, "dist_post_kernel", launch_dist_post(s, a, ctx->sm_count));
             if (to_user)
                 BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
                                              (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
@@ -636,9 +697,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.mode = 0;
         a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
         a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
-        if (dm.kind == BF_MODEL_RSPACE) launch_rspace_eval(s, a, ctx->sm_count);
-        else launch_kspace_eval(s, a, ctx->sm_count);
-        ctx->launches++;
+        if (dm.kind == BF_MODEL_RSPACE) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
+        else BF_KERNEL(ctx, "kspace_eval_kernel[data]", launch_kspace_eval(s, a, ctx->sm_count));
     }
     if (what == OUT_CHI2 && !finished) {
         GemmArgs g{};
@@ -647,8 +707,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
         g.lower_triangular = 1;
         g.chi2 = d_out; g.status = w.status;
-        launch_gemm_chi2(s, g);
-        ctx->launches++;
+        BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
     }
     if (d_status_out) BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
     BF_CUDA_OK(cudaGetLastError());
@@ -803,8 +862,8 @@ extern "C" int bf_sample_toys(bf_ctx *ctx, const bf_data *d, const double *truth
     if (rc) return rc;
     double *d_truth = (double *)ctx->io, *d_out = (double *)((char *)ctx->io + al(nb_truth));
     BF_CUDA_OK(cudaMemcpyAsync(d_truth, truth, nb_truth, cudaMemcpyHostToDevice, ctx->stream));
-    launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, d_out);
-    ctx->launches++;
+    BF_KERNEL(ctx, "toy_noise_kernel",
+              launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, d_out));
     BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return BF_OK;

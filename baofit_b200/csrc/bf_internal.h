@@ -99,6 +99,11 @@ struct bf_ctx {
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     int sm_count = 148;
+    // optional per-kernel timing (bf_ctx_set_profiling): event pairs around every launch
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_pending;
+    std::map<std::string, std::pair<double, long long>> prof_acc;  // name -> (ms, launches)
 };
 
 struct bf_model {

@@ -192,6 +192,13 @@ long long bf_ctx_launch_count(const bf_ctx *ctx);
 int bf_ctx_synchronize(bf_ctx *ctx);
 /* Raw cudaStream_t of the context (as void*), so callers can record events on it. */
 void *bf_ctx_stream(bf_ctx *ctx);
+/* Per-kernel device timing for the roofline report: when enabled, a CUDA event pair brackets
+ * every kernel launch on the context's stream. bf_ctx_get_profile synchronises, then returns the
+ * number of distinct kernels and fills (up to max_entries) name / total milliseconds / launch
+ * count; names stay valid until the context is destroyed. Enabling resets the counters. */
+int bf_ctx_set_profiling(bf_ctx *ctx, int enable);
+int bf_ctx_get_profile(bf_ctx *ctx, int max_entries, const char **names, double *ms_total,
+                       long long *launches);
 
 /* Replaces the constructors of BaoCorrelationModel (BaoCorrelationModel.cc:18-86) and
  * BaoKSpaceCorrelationModel (BaoKSpaceCorrelationModel.cc:26-211): tables are copied, spline
