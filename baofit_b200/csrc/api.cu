@@ -42,6 +42,7 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
     cudaDeviceProp prop;
     BF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    BF_CUDA_OK(cudaMallocHost((void **)&c->pinned_flag, 64));
     *out = c;
     return BF_OK;
 }
@@ -52,6 +53,7 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
+    if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
     cudaStreamDestroy(c->stream);
     delete c;
     return BF_OK;
@@ -346,6 +348,7 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
                 bf::set_error("MetalCorrelationModel: error while reading metal model interpolation data.");
                 return fail(BF_ERR_MODEL);
             }
+            if (d->metal_ncomb > 5) { bf::set_error("MetalCorrelationModel: at most 5 cross combinations"); return fail(BF_ERR_MODEL); }
             int nt = d->metal_ncomb * 3, nx = d->metal_nx, ny = d->metal_ny;
             std::vector<double> il((size_t)nt * nx * ny);
             for (int t = 0; t < nt; ++t)
@@ -545,7 +548,16 @@ namespace {
 struct Workspace {
     double *pT, *S, *G, *T, *C2, *XiU, *Y, *Z;
     int *status;
+    // fixed-size region of the shared-transform path (independent of the batch size)
+    double *Gb, *Tb, *Cb;
+    double2 *tabs;
+    int *flag;
 };
+
+size_t ws_fixed_doubles(const DevModel &dm) {
+    if (dm.kind != BF_MODEL_KSPACE) return 16;
+    return (size_t)6 * dm.nk_pad * kPadN + (size_t)12 * dm.nr_pad * kPadN + (size_t)2 * dm.nr * 9 * 2 + 32;
+}
 
 size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
     size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + d->n_pad /*Z*/;
@@ -556,6 +568,20 @@ size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
 
 void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Workspace &w) {
     double *p = (double *)base;
+    w.flag = (int *)p;
+    p += 16;
+    w.Gb = w.Tb = w.Cb = nullptr;
+    w.tabs = nullptr;
+    if (dm.kind == BF_MODEL_KSPACE) {
+        w.tabs = (double2 *)p;
+        p += (size_t)2 * dm.nr * 9 * 2 + 16;
+        w.Gb = p;
+        p += (size_t)6 * dm.nk_pad * kPadN;
+        w.Tb = p;
+        p += (size_t)6 * dm.nr_pad * kPadN;
+        w.Cb = p;
+        p += (size_t)6 * dm.nr_pad * kPadN;
+    }
     auto take = [&](size_t rows) { double *q = p; p += rows * (size_t)ldb; return q; };
     w.pT = take(dm.npar);
     w.S = take((size_t)nz * 3);
@@ -610,7 +636,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     // fake data dims for transform-only
     static bf_data empty_data;
     const bf_data *dd = d ? d : &empty_data;
-    size_t need = ws_doubles_per_column(dm, dd, nz) * (size_t)ldb * sizeof(double);
+    size_t need = (ws_fixed_doubles(dm) + ws_doubles_per_column(dm, dd, nz) * (size_t)ldb) * sizeof(double);
     int rc = ensure(&ctx->ws, &ctx->ws_bytes, need);
     if (rc) return rc;
     carve(ctx->ws, dm, dd, nz, ldb, w);
@@ -625,6 +651,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     }
     BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, w.pT, w.S, w.status));
 
+    bool shared_tables = false;
     if (dm.kind == BF_MODEL_KSPACE) {
         ProjArgs pa;
         pa.m = dm; pa.pT = w.pT; pa.S = w.S; pa.ldb = ldb; pa.B = B;
@@ -633,31 +660,56 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         (void)use_ztrig_override;
         double zeff = dm.zeff > 0 ? dm.zeff : ztrig;
         nl_table(dm, zeff, pa.nl_tab, &pa.nl_pk_scale);
-        pa.G = w.G;
-        BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));
-        GemmArgs g{};
-        g.A = dm.hankel; g.Bm = w.G; g.C = w.T;
-        g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
-        g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
-        g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
-        BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6));
-        if (what == OUT_TRANSFORM) {
-            // out[((comp*3+l)*nr + j)*ldo + b]
-            for (int t = 0; t < 6; ++t)
-                BF_CUDA_OK(cudaMemcpy2DAsync(d_out + (size_t)t * dm.nr * ldo, (size_t)ldo * sizeof(double),
-                                             w.T + (size_t)t * dm.nr_pad * ldb, (size_t)ldb * sizeof(double),
-                                             (size_t)B * sizeof(double), dm.nr, cudaMemcpyDeviceToDevice, s));
-            if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
-            return BF_OK;
+        // Shared-transform fast path: possible when the tracer factor of D(k,mu) is polynomial
+        // (no UV / HCD terms) and every vector of the chunk has the same key parameters.
+        if (what != OUT_TRANSFORM && !(dm.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT))) {
+            BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(int), s));
+            if (B > 1) BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
+            BF_CUDA_OK(cudaMemcpyAsync(ctx->pinned_flag, w.flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+            BF_CUDA_OK(cudaStreamSynchronize(s));
+            shared_tables = (*ctx->pinned_flag == 0);
         }
-        BF_KERNEL(ctx, "kspace_thomas_kernel",
-                  launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2));
+        if (shared_tables) {
+            pa.G = w.Gb;
+            BF_CUDA_OK(cudaMemsetAsync(w.Gb, 0, (size_t)6 * dm.nk_pad * kPadN * sizeof(double), s));
+            BF_KERNEL(ctx, "kspace_basis_project_kernel", launch_kspace_basis_project(s, pa));
+            GemmArgs g{};
+            g.A = dm.hankel; g.Bm = w.Gb; g.C = w.Tb;
+            g.M = dm.nr_pad; g.N = 3; g.K = dm.nk_pad;
+            g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
+            g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
+            BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
+            BF_KERNEL(ctx, "kspace_thomas_kernel[basis]",
+                      launch_kspace_thomas(s, 3, kPadN, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.Tb, w.Cb));
+            BF_KERNEL(ctx, "kspace_basis_pack_kernel", launch_kspace_basis_pack(s, dm, w.Tb, w.Cb, w.tabs));
+        } else {
+            pa.G = w.G;
+            BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));
+            GemmArgs g{};
+            g.A = dm.hankel; g.Bm = w.G; g.C = w.T;
+            g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
+            g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
+            g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
+            BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6));
+            if (what == OUT_TRANSFORM) {
+                // out[((comp*3+l)*nr + j)*ldo + b]
+                for (int t = 0; t < 6; ++t)
+                    BF_CUDA_OK(cudaMemcpy2DAsync(d_out + (size_t)t * dm.nr * ldo, (size_t)ldo * sizeof(double),
+                                                 w.T + (size_t)t * dm.nr_pad * ldb, (size_t)ldb * sizeof(double),
+                                                 (size_t)B * sizeof(double), dm.nr, cudaMemcpyDeviceToDevice, s));
+                if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
+                return BF_OK;
+            }
+            BF_KERNEL(ctx, "kspace_thomas_kernel",
+                      launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2));
+        }
     }
 
     EvalArgs a;
     std::memset(&a, 0, sizeof(a));
     a.m = dm; a.pT = w.pT; a.S = w.S; a.ldb = ldb; a.B = B;
     a.vfac = plan->d_vfac; a.T = w.T; a.C2 = w.C2; a.status = w.status;
+    a.tabs = w.tabs; a.zc_trigger = plan->zc_trigger;
     const bool use_dm = dm.dm_order > 0;
     const bool to_user = what == OUT_PRED;  // final rows go straight to the caller's buffer
 
@@ -670,7 +722,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.mode = 1;
         a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
         if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
-        BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
+        if (shared_tables) BF_KERNEL(ctx, "kspace_eval_shared_kernel[grid]", launch_kspace_eval_shared(s, a, ctx->sm_count));
+        else BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
         if (what == OUT_XIU) finished = true;
         if (!finished) {
             GemmArgs g{};
@@ -698,6 +751,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
         a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
         if (dm.kind == BF_MODEL_RSPACE) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
+        else if (shared_tables) BF_KERNEL(ctx, "kspace_eval_shared_kernel[data]", launch_kspace_eval_shared(s, a, ctx->sm_count));
         else BF_KERNEL(ctx, "kspace_eval_kernel[data]", launch_kspace_eval(s, a, ctx->sm_count));
     }
     if (what == OUT_CHI2 && !finished) {
@@ -717,7 +771,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
 int chunk_capacity(const bf_model *m, const bf_data *d, int nz) {
     static bf_data empty_data;
     size_t per_col = ws_doubles_per_column(m->dev, d ? d : &empty_data, nz) * sizeof(double);
-    size_t budget = (size_t)3 << 30;  // 3 GiB of workspace at most
+    size_t budget = ((size_t)3 << 30) - ws_fixed_doubles(m->dev) * sizeof(double);  // 3 GiB of workspace at most
     size_t cap = budget / per_col;
     cap = std::min<size_t>(cap, 65536);
     cap = std::max<size_t>(cap / kPadN * kPadN, kPadN);

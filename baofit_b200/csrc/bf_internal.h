@@ -96,8 +96,7 @@ struct bf_ctx {
     size_t ws_bytes = 0;
     void *io = nullptr;  // staging for host-buffer entry points
     size_t io_bytes = 0;
-    void *pinned = nullptr;
-    size_t pinned_bytes = 0;
+    int *pinned_flag = nullptr;  // 1 pinned int for tiny device->host answers
     int sm_count = 148;
     // optional per-kernel timing (bf_ctx_set_profiling): event pairs around every launch
     bool profiling = false;

@@ -32,6 +32,28 @@ __device__ __forceinline__ double legendre_p(int ell, double mu) {  // baofit/Br
     }
 }
 
+// Power sequence of one broadband axis: exponents lo, lo+step, ... with the reference's rule
+// "use (x-1) instead of x when the exponent is positive" (baofit/BroadbandModel.cc:209-213).
+// Powers are advanced by one multiplication per term instead of one pow() per term.
+struct AxisPowers {
+    double neg, pos, neg_step, pos_step;
+    int first_pos;
+    __device__ __forceinline__ void init(double x, int lo, int step) {
+        neg = ipow(x, lo);
+        neg_step = ipow(x, step);
+        first_pos = lo > 0 ? lo : lo + ((0 - lo) / step + 1) * step;  // smallest exponent > 0
+        pos = ipow(x - 1.0, first_pos);
+        pos_step = ipow(x - 1.0, step);
+    }
+    // value for exponent e (called with e = lo, lo+step, ... in order), then advance
+    __device__ __forceinline__ double next(int e) {
+        double v;
+        if (e > 0) { v = pos; pos *= pos_step; }
+        else { v = neg; neg *= neg_step; }
+        return v;
+    }
+};
+
 // Broadband polynomial, baofit/BroadbandModel.cc:197-226. pT = transposed parameters
 // (pT[j*ldb + b]), already offset to column b.
 __device__ __forceinline__ double broadband_eval(const DevBB &s, const double *__restrict__ pT, int ldb, double r,
@@ -44,19 +66,25 @@ __device__ __forceinline__ double broadband_eval(const DevBB &s, const double *_
         double zF = ipow(zz, zi);
         for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step) {
             double zmF = zF * legendre_p(mi, mu);
+            AxisPowers pr;
+            if (s.r_denom == 1) pr.init(rr, s.r_min, s.r_step);
             for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step) {
-                double base = ri > 0 ? rr - 1.0 : rr;
-                double rF = s.r_denom == 1 ? ipow(base, ri) : pow(base, (double)ri / s.r_denom);
+                double rF = s.r_denom == 1 ? pr.next(ri) : pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom);
+                AxisPowers pp;
+                pp.init(rrP, s.rp_min, s.rp_step);
+                double accP = 0.0;
                 for (int pi = s.rp_min; pi <= s.rp_max; pi += s.rp_step) {
-                    double rPF = ipow(pi > 0 ? rrP - 1.0 : rrP, pi);
+                    double rPF = pp.next(pi);
+                    AxisPowers pt;
+                    pt.init(rrT, s.rt_min, s.rt_step);
                     double acc = 0.0;
                     for (int ti = s.rt_min; ti <= s.rt_max; ti += s.rt_step) {
-                        double rTF = ipow(ti > 0 ? rrT - 1.0 : rrT, ti);
-                        acc += pT[(size_t)off * ldb] * rTF;
+                        acc = fma(pT[(size_t)off * ldb], pt.next(ti), acc);
                         ++off;
                     }
-                    xi += acc * rF * rPF * zmF;
+                    accP = fma(acc, rPF, accP);
                 }
+                xi = fma(accP, rF * zmF, xi);
             }
         }
     }
@@ -151,6 +179,20 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 
 // Metal correlations, baofit/MetalCorrelationModel.cc:235-351.
 // S = per-class evolution factors S[(c*3+k)*ldb] for column b; zc_metal[c*stride + bin] = class ids.
+// Written without dynamically indexed local arrays (those would live in local memory).
+__device__ __forceinline__ void metal_pair(const DevModel &m, const Internal &in, bool cross,
+                                           const double *__restrict__ pT, int ldb, int a, double &beta, double &bias) {
+    if (a == 0) {  // :247-248, :282-283
+        beta = cross ? in.beta2 : in.beta;
+        bias = cross ? in.bias2 : in.bias;
+    } else {
+        beta = pT[(size_t)(m.idx_metal + 2 * (a - 1)) * ldb];
+        bias = pT[(size_t)(m.idx_metal + 2 * (a - 1) + 1) * ldb];
+    }
+}
+
+constexpr int kMaxCrossTemplates = 15;  // (4 + CIV) combinations x 3 multipoles
+
 __device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &in, const double *__restrict__ pT,
                                              int ldb, const double *__restrict__ S, const int *__restrict__ zc_metal,
                                              int zc_stride, int bin, int grid_index, double r, double mu) {
@@ -168,57 +210,59 @@ __device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &
         return xi;
     }
     const bool cross = m.metal_kind == BF_METAL_CROSS_BICUBIC;
-    double betap[6], biasp[6];
-    betap[0] = cross ? in.beta2 : in.beta;
-    biasp[0] = cross ? in.bias2 : in.bias;
-    for (int i = 1; i < m.metal_nmet; ++i) {
-        betap[i] = pT[(size_t)(m.idx_metal + 2 * (i - 1)) * ldb];
-        biasp[i] = pT[(size_t)(m.idx_metal + 2 * (i - 1) + 1) * ldb];
-    }
     double xi = 0.0;
-    double wx[4], wy[4];
-    int ix = 0, iy = 0;
     if (cross) {
+        // bicubic templates: the 16 patch weights are shared by all templates
         double rperp = r * sqrt(1.0 - mu * mu), rpar = r * mu;
         rperp = fmin(fmax(rperp, m.metal_x0), m.metal_xmax);
         rpar = fmin(fmax(rpar, m.metal_y0), m.metal_ymax);
         double fx = (rperp - m.metal_x0) * m.metal_inv_dx, fy = (rpar - m.metal_y0) * m.metal_inv_dy;
         double flx = floor(fx), fly = floor(fy);
-        ix = (int)flx;
-        iy = (int)fly;
+        int ix = (int)flx, iy = (int)fly;
+        double wx[4], wy[4];
         catmull_weights(fx - flx, wx);
         catmull_weights(fy - fly, wy);
+        const int nt = m.metal_ncomb * 3;
+        double acc[kMaxCrossTemplates];
+#pragma unroll
+        for (int t = 0; t < kMaxCrossTemplates; ++t) acc[t] = 0.0;
+#pragma unroll
+        for (int jy = 0; jy < 4; ++jy) {
+            const double *row = m.metal_cross + (size_t)wrap_index(iy - 1 + jy, m.metal_ny) * m.metal_nx * nt;
+#pragma unroll
+            for (int jx = 0; jx < 4; ++jx) {
+                const double *cell = row + (size_t)wrap_index(ix - 1 + jx, m.metal_nx) * nt;
+                double w = wx[jx] * wy[jy];
+#pragma unroll
+                for (int t = 0; t < kMaxCrossTemplates; ++t)
+                    if (t < nt) acc[t] = fma(w, __ldg(cell + t), acc[t]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxCrossTemplates / 3; ++c) {
+            if (c < m.metal_ncomb) {
+                double ba, bia, bb, bib;
+                metal_pair(m, in, true, pT, ldb, m.metal_p1[c], ba, bia);
+                metal_pair(m, in, true, pT, ldb, m.metal_p2[c], bb, bib);
+                int zc = zc_metal[(size_t)c * zc_stride + bin];
+                double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb];
+                double n0, n2, n4;
+                norm_factors(bia * bib * eb, 0.5 * (ba + bb) * ebeta, ba * bb * ebeta * ebeta, n0, n2, n4);
+                xi += n0 * acc[3 * c] + n2 * acc[3 * c + 1] + n4 * acc[3 * c + 2];
+            }
+        }
+        return xi;
     }
-    const int nt = m.metal_ncomb * 3;
     for (int c = 0; c < m.metal_ncomb; ++c) {
-        int a = m.metal_p1[c], b = m.metal_p2[c];
+        double ba, bia, bb, bib;
+        metal_pair(m, in, false, pT, ldb, m.metal_p1[c], ba, bia);
+        metal_pair(m, in, false, pT, ldb, m.metal_p2[c], bb, bib);
         int zc = zc_metal[(size_t)c * zc_stride + bin];
         double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb];
         double n0, n2, n4;
-        norm_factors(biasp[a] * biasp[b] * eb, 0.5 * (betap[a] + betap[b]) * ebeta, betap[a] * betap[b] * ebeta * ebeta,
-                     n0, n2, n4);
-        if (cross) {
-            double t0 = 0.0, t2 = 0.0, t4 = 0.0;
-#pragma unroll
-            for (int jy = 0; jy < 4; ++jy) {
-                const double *row = m.metal_cross + (size_t)wrap_index(iy - 1 + jy, m.metal_ny) * m.metal_nx * nt;
-                double r0 = 0.0, r2 = 0.0, r4 = 0.0;
-#pragma unroll
-                for (int jx = 0; jx < 4; ++jx) {
-                    const double *cell = row + (size_t)wrap_index(ix - 1 + jx, m.metal_nx) * nt + 3 * c;
-                    r0 += wx[jx] * cell[0];
-                    r2 += wx[jx] * cell[1];
-                    r4 += wx[jx] * cell[2];
-                }
-                t0 += wy[jy] * r0;
-                t2 += wy[jy] * r2;
-                t4 += wy[jy] * r4;
-            }
-            xi += n0 * t0 + n2 * t2 + n4 * t4;
-        } else {
-            const double *t = m.metal_auto + (size_t)(3 * c) * m.metal_ngrid + grid_index;
-            xi += n0 * t[0] + n2 * t[m.metal_ngrid] + n4 * t[2 * (size_t)m.metal_ngrid];
-        }
+        norm_factors(bia * bib * eb, 0.5 * (ba + bb) * ebeta, ba * bb * ebeta * ebeta, n0, n2, n4);
+        const double *t = m.metal_auto + (size_t)(3 * c) * m.metal_ngrid + grid_index;
+        xi += n0 * t[0] + n2 * t[m.metal_ngrid] + n4 * t[2 * (size_t)m.metal_ngrid];
     }
     return xi;
 }

@@ -19,6 +19,9 @@ struct EvalArgs {
     const double *vfac;   // [nz] velocity-shift factor of each class
     // k-space per-vector multipole tables and their spline second derivatives
     const double *T, *C2;
+    // shared-transform path: basis tables {y, y''/2} [2 comps][nr][9 = 3 ell x 3 powers of mu^2]
+    const double2 *tabs;
+    int zc_trigger;
     int mode;
     // output: out[i*ldo + b] = value - (dov ? dov[b*npts+i] : dsub ? dsub[i] : 0)
     const double *in;
@@ -61,6 +64,11 @@ void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count);
 void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,
                           const double *th_inv_diag, const double *T, double *C2);
 void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
+// shared-transform fast path (all vectors of the batch share the non-polynomial part of D(k,mu))
+void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, int *flag);
+void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a);  // a.G: [6][nk_pad][kPadN], columns 0..2
+void launch_kspace_basis_pack(cudaStream_t s, const DevModel &m, const double *T, const double *C2, double2 *tabs);
+void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count);
 
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);

@@ -157,27 +157,12 @@ __device__ __forceinline__ double nl_correction(const DevModel &m, const ProjArg
     return 1.0;
 }
 
-__device__ __forceinline__ double kspace_distortion(const DevModel &m, const ProjArgs &a, const KPar &kp, double k,
-                                                    double mu_k, double pk) {
+// Everything in D(k, mu_k) except the linear tracer factor (bin smoothing, Gaussian / Lorentzian
+// smoothing, non-linear broadening, non-linear correction); :246-282
+__device__ __forceinline__ double kspace_nonpoly(const DevModel &m, const ProjArgs &a, const KPar &kp, double k,
+                                                 double mu_k, double pk) {
     const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
     double mu2 = mu_k * mu_k, kpar = fabs(k * mu_k);
-    double tracer1 = 1.0 + kp.betaz * mu2;
-    double tracer2 = cross ? 1.0 + kp.beta2z * mu2 : tracer1;
-    double linear = tracer1 * tracer2;
-    if (m.flags & BF_FLAG_UVFLUCTUATION) {
-        double s = kp.uv[2] * k, Ws = atan(s) / s;
-        double uvFunc = 1.0 + kp.uv[0] * Ws / (1.0 + kp.uv[1] * Ws);
-        tracer1 = uvFunc + kp.betaz * mu2;
-        tracer2 = cross ? 1.0 + kp.beta2z * mu2 : tracer1;
-        linear = tracer1 * tracer2;
-    }
-    if (m.flags & (BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT)) {
-        double x = kp.hcd[2] * kpar;
-        double hcdFunc = (m.flags & BF_FLAG_HCD_MODEL) ? sin(x) / x : exp(-x * x / 2.0);
-        double tracerHcd = kp.hcd[1] * (1.0 + kp.hcd[0] * mu2) * hcdFunc;
-        linear = cross ? tracer1 * tracer2 + tracer2 * tracerHcd
-                       : tracer1 * tracer1 + 2.0 * tracer1 * tracerHcd + tracerHcd * tracerHcd;
-    }
     double smoothbin = 1.0;
     if (m.flags & (BF_FLAG_BIN_SMOOTH | BF_FLAG_BIN_SMOOTH_ALT)) {
         if (m.flags & BF_FLAG_BIN_SMOOTH) {
@@ -197,7 +182,62 @@ __device__ __forceinline__ double kspace_distortion(const DevModel &m, const Pro
     double nonlinear = exp(-0.5 * snl2 * k * k);
     double nlc = nl_correction(m, a, kp, k, mu_k, pk);
     if (cross) nlc = sqrt(nlc);
-    return nonlinear * nlc * linear * smoothbin * gaussmooth * lorsmooth;
+    return nonlinear * nlc * smoothbin * gaussmooth * lorsmooth;
+}
+
+// Linear tracer factor incl. the UV and HCD corrections; :216-245
+__device__ __forceinline__ double kspace_linear(const DevModel &m, const KPar &kp, double k, double mu_k) {
+    const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
+    double mu2 = mu_k * mu_k, kpar = fabs(k * mu_k);
+    double tracer1 = 1.0 + kp.betaz * mu2;
+    double tracer2 = cross ? 1.0 + kp.beta2z * mu2 : tracer1;
+    double linear = tracer1 * tracer2;
+    if (m.flags & BF_FLAG_UVFLUCTUATION) {
+        double s = kp.uv[2] * k, Ws = atan(s) / s;
+        double uvFunc = 1.0 + kp.uv[0] * Ws / (1.0 + kp.uv[1] * Ws);
+        tracer1 = uvFunc + kp.betaz * mu2;
+        tracer2 = cross ? 1.0 + kp.beta2z * mu2 : tracer1;
+        linear = tracer1 * tracer2;
+    }
+    if (m.flags & (BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT)) {
+        double x = kp.hcd[2] * kpar;
+        double hcdFunc = (m.flags & BF_FLAG_HCD_MODEL) ? sin(x) / x : exp(-x * x / 2.0);
+        double tracerHcd = kp.hcd[1] * (1.0 + kp.hcd[0] * mu2) * hcdFunc;
+        linear = cross ? tracer1 * tracer2 + tracer2 * tracerHcd
+                       : tracer1 * tracer1 + 2.0 * tracer1 * tracerHcd + tracerHcd * tracerHcd;
+    }
+    return linear;
+}
+
+__device__ __forceinline__ double kspace_distortion(const DevModel &m, const ProjArgs &a, const KPar &kp, double k,
+                                                    double mu_k, double pk) {
+    return kspace_nonpoly(m, a, kp, k, mu_k, pk) * kspace_linear(m, kp, k, mu_k);
+}
+
+__device__ __forceinline__ void load_kpar(const DevModel &m, const ProjArgs &a, const double *__restrict__ pT, int ldb,
+                                          int b, int comp, KPar &kp) {
+    double ebeta = a.S[(size_t)(a.zc_trigger * 3 + 1) * ldb + b];
+    double beta = pT[(size_t)m.idx_beta * ldb];
+    kp.betaz = beta * ebeta;
+    kp.beta2z = 0.0;
+    if (m.flags & BF_FLAG_CROSS_CORRELATION)
+        kp.beta2z = pT[(size_t)m.idx_bb2 * ldb] / pT[(size_t)m.idx_bias2 * ldb] * ebeta;
+    double snlPerp = pT[(size_t)m.idx_nl * ldb], snlPar = snlPerp * pT[(size_t)(m.idx_nl + 1) * ldb];
+    kp.snl_perp2 = snlPerp * snlPerp;
+    kp.snl_par2 = snlPar * snlPar;
+    if (comp == 1 && !(m.flags & BF_FLAG_NL_BROADBAND)) kp.snl_perp2 = kp.snl_par2 = 0.0;  // :364-367
+    for (int k = 0; k < 3; ++k) {
+        kp.uv[k] = m.idx_uv >= 0 ? pT[(size_t)(m.idx_uv + k) * ldb] : 0.0;
+        kp.hcd[k] = m.idx_hcd >= 0 ? pT[(size_t)(m.idx_hcd + k) * ldb] : 0.0;
+    }
+    for (int k = 0; k < 2; ++k) kp.bs[k] = m.idx_bs >= 0 ? pT[(size_t)(m.idx_bs + k) * ldb] : 0.0;
+    kp.sg = m.idx_smgaus >= 0 ? pT[(size_t)m.idx_smgaus * ldb] : 0.0;
+    kp.sl = m.idx_smlor >= 0 ? pT[(size_t)m.idx_smlor * ldb] : 0.0;
+    kp.qnl = a.nl_tab[0]; kp.kv = a.nl_tab[1]; kp.av = a.nl_tab[2]; kp.bv = a.nl_tab[3]; kp.kp = a.nl_tab[4];
+    if (m.flags & BF_FLAG_FIT_NL_CORRECTION) {
+        kp.qnl = pT[(size_t)m.idx_nlcorr * ldb];
+        kp.kp = pT[(size_t)(m.idx_nlcorr + 1) * ldb];
+    }
 }
 
 // G[((comp*3 + l)*nk_pad + i)*ldb + b] = (2l+1) Int_0^1 L_l(mu) D_comp(k_i, mu; p_b) dmu
@@ -209,30 +249,7 @@ __global__ void __launch_bounds__(128) kspace_project_kernel(ProjArgs a) {
     const double *pT = a.pT + b;
     const int comp = blockIdx.z;
     KPar kp;
-    {
-        double ebeta = a.S[(size_t)(a.zc_trigger * 3 + 1) * ldb + b];
-        double beta = pT[(size_t)m.idx_beta * ldb];
-        kp.betaz = beta * ebeta;
-        kp.beta2z = 0.0;
-        if (m.flags & BF_FLAG_CROSS_CORRELATION)
-            kp.beta2z = pT[(size_t)m.idx_bb2 * ldb] / pT[(size_t)m.idx_bias2 * ldb] * ebeta;
-        double snlPerp = pT[(size_t)m.idx_nl * ldb], snlPar = snlPerp * pT[(size_t)(m.idx_nl + 1) * ldb];
-        kp.snl_perp2 = snlPerp * snlPerp;
-        kp.snl_par2 = snlPar * snlPar;
-        if (comp == 1 && !(m.flags & BF_FLAG_NL_BROADBAND)) kp.snl_perp2 = kp.snl_par2 = 0.0;  // :364-367
-        for (int k = 0; k < 3; ++k) {
-            kp.uv[k] = m.idx_uv >= 0 ? pT[(size_t)(m.idx_uv + k) * ldb] : 0.0;
-            kp.hcd[k] = m.idx_hcd >= 0 ? pT[(size_t)(m.idx_hcd + k) * ldb] : 0.0;
-        }
-        for (int k = 0; k < 2; ++k) kp.bs[k] = m.idx_bs >= 0 ? pT[(size_t)(m.idx_bs + k) * ldb] : 0.0;
-        kp.sg = m.idx_smgaus >= 0 ? pT[(size_t)m.idx_smgaus * ldb] : 0.0;
-        kp.sl = m.idx_smlor >= 0 ? pT[(size_t)m.idx_smlor * ldb] : 0.0;
-        kp.qnl = a.nl_tab[0]; kp.kv = a.nl_tab[1]; kp.av = a.nl_tab[2]; kp.bv = a.nl_tab[3]; kp.kp = a.nl_tab[4];
-        if (m.flags & BF_FLAG_FIT_NL_CORRECTION) {
-            kp.qnl = pT[(size_t)m.idx_nlcorr * ldb];
-            kp.kp = pT[(size_t)(m.idx_nlcorr + 1) * ldb];
-        }
-    }
+    load_kpar(m, a, pT, ldb, b, comp, kp);
     const int lmax = m.ell_max / 2;
     int i0 = blockIdx.y * a.k_per_block, i1 = min(i0 + a.k_per_block, m.nk_pad);
     for (int i = i0; i < i1; ++i) {
@@ -388,6 +405,233 @@ __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
     if (st_bits) atomicOr(a.status + b, st_bits);
 }
 
+// ------------------------------------------------------------------------------------------
+// Shared-transform fast path.
+//
+// Without the UV / HCD corrections the tracer factor of D(k,mu) is the polynomial
+//     (1 + beta mu^2)(1 + beta2 mu^2) = 1 + c1 mu^2 + c2 mu^4
+// and everything else, K(k,mu), depends only on "key" parameters (SigmaNL-perp, 1+f, bin / Gauss /
+// Lorentz smoothing scales, nlcorr) that fits normally keep fixed. The whole chain projection ->
+// Hankel transform -> natural spline is linear in the multipoles of D, so when every vector of a
+// batch has the same key
+//     xi_l^comp(r; b) = X_{l,0}(r) + c1(b) X_{l,1}(r) + c2(b) X_{l,2}(r)
+// with 18 basis tables X computed once per batch. The per-vector transform disappears and the
+// tables become small and static: they are staged in shared memory with one TMA bulk copy.
+// ------------------------------------------------------------------------------------------
+__global__ void kspace_key_check_kernel(DevModel m, const double *__restrict__ pT, int ldb, int B, int *flag) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    bool diff = false;
+    auto cmp = [&](int idx) { diff |= (pT[(size_t)idx * ldb + b] != pT[(size_t)idx * ldb]); };
+    cmp(m.idx_nl);
+    cmp(m.idx_nl + 1);
+    if (m.flags & (BF_FLAG_BIN_SMOOTH | BF_FLAG_BIN_SMOOTH_ALT)) { cmp(m.idx_bs); cmp(m.idx_bs + 1); }
+    if (m.flags & BF_FLAG_SMOOTH_GAUSS) cmp(m.idx_smgaus);
+    if (m.flags & BF_FLAG_SMOOTH_LORENTZ) cmp(m.idx_smlor);
+    if (m.flags & BF_FLAG_FIT_NL_CORRECTION) { cmp(m.idx_nlcorr); cmp(m.idx_nlcorr + 1); }
+    if (diff) *flag = 1;
+}
+
+// G[((comp*3 + l)*nk_pad + i)*kPadN + n] = (2l+1) Int_0^1 L_l(mu) mu^(2n) K_comp(k_i, mu) dmu
+__global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
+    const DevModel &m = a.m;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, comp = blockIdx.y;
+    if (i >= m.nk_pad) return;
+    KPar kp;
+    load_kpar(m, a, a.pT, a.ldb, 0, comp, kp);
+    double s[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    if (i < m.nk) {
+        double k = m.kc[i], pk = m.pk_kc[comp * m.nk + i];
+        for (int q = 0; q < kMuNodes; ++q) {
+            double mu = m.mu_x[q], mu2 = mu * mu;
+            double w = m.mu_w[q] * kspace_nonpoly(m, a, kp, k, mu, pk);
+            double L[3] = {1.0, (-1.0 + 3.0 * mu2) * 0.5, (3.0 + mu2 * (-30.0 + 35.0 * mu2)) * 0.125};
+            double pw = w;
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+#pragma unroll
+                for (int l = 0; l < 3; ++l) s[l][n] += pw * L[l];
+                pw *= mu2;
+            }
+        }
+    }
+    const int lmax = m.ell_max / 2;
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+            a.G[((size_t)(comp * 3 + l) * m.nk_pad + i) * kPadN + n] = l <= lmax ? (2 * l * 2 + 1) * s[l][n] : 0.0;
+}
+
+// tabs[(comp*nr + j)*9 + l*3 + n] = { X_{l,n}(r_j), X''_{l,n}(r_j)/2 }
+__global__ void kspace_basis_pack_kernel(DevModel m, const double *__restrict__ T, const double *__restrict__ C2,
+                                         double2 *__restrict__ tabs) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = 2 * m.nr * 9;
+    if (idx >= total) return;
+    int q = idx % 9, j = (idx / 9) % m.nr, comp = idx / (9 * m.nr);
+    int l = q / 3, n = q % 3;
+    size_t src = ((size_t)(comp * 3 + l) * m.nr_pad + j) * kPadN + n;
+    tabs[idx] = make_double2(T[src], C2[src]);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                 "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar), ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// sum_l L_l(mu) sum_n coef_n X_{l,n}(r) for one component from the shared-memory basis tables
+__device__ __forceinline__ double shared_correlation(const DevModel &m, const double2 *__restrict__ tab, double r,
+                                                     double mu, double c1, double c2) {
+    const int nr = m.nr;
+    const double rlast = m.tr_r0 + (nr - 1) * m.tr_dr;
+    double w0, w1, w2, w3;
+    int j;
+    if (r <= m.tr_r0) { j = 0; w0 = 1.0; w1 = w2 = w3 = 0.0; }
+    else if (r >= rlast) { j = nr - 2; w1 = 1.0; w0 = w2 = w3 = 0.0; }
+    else {
+        j = (int)((r - m.tr_r0) * m.tr_inv_dr);
+        j = max(0, min(j, nr - 2));
+        double xl = m.tr_r0 + j * m.tr_dr;
+        if (r < xl && j > 0) { --j; xl = m.tr_r0 + j * m.tr_dr; }
+        else if (r >= xl + m.tr_dr && j < nr - 2) { ++j; xl = m.tr_r0 + j * m.tr_dr; }
+        const double dx = m.tr_dr, t = r - xl, u = t * m.tr_inv_dr, t3 = t * t * t * m.tr_inv_dr * (1.0 / 3.0);
+        // gsl cspline evaluation rearranged as weights of (y_lo, y_hi, c_lo, c_hi)
+        w0 = 1.0 - u;
+        w1 = u;
+        w2 = t * t - (2.0 / 3.0) * t * dx - t3;
+        w3 = t3 - (1.0 / 3.0) * t * dx;
+    }
+    const double musq = mu * mu;
+    const double L2 = (-1.0 + 3.0 * musq) * 0.5, L4 = (3.0 + musq * (-30.0 + 35.0 * musq)) * 0.125;
+    const double g[9] = {1.0, c1, c2, L2, L2 * c1, L2 * c2, L4, L4 * c1, L4 * c2};
+    const double2 *lo = tab + (size_t)j * 9, *hi = lo + 9;
+    double ylo = 0.0, yhi = 0.0, clo = 0.0, chi = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        double2 a = lo[q], b = hi[q];
+        ylo = fma(g[q], a.x, ylo);
+        clo = fma(g[q], a.y, clo);
+        yhi = fma(g[q], b.x, yhi);
+        chi = fma(g[q], b.y, chi);
+    }
+    return w0 * ylo + w1 * yhi + w2 * clo + w3 * chi;
+}
+
+// Same contract as kspace_eval_kernel, basis tables in shared memory (TMA bulk copy + mbarrier).
+__global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tab = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ __align__(8) unsigned long long bar;
+    const DevModel &m = a.m;
+    const unsigned tab_bytes = 2u * m.nr * 9u * (unsigned)sizeof(double2);
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, tab_bytes);
+        const unsigned chunk = 32768;
+        for (unsigned off = 0; off < tab_bytes; off += chunk)
+            tma_bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char *>(a.tabs) + off,
+                         min(chunk, tab_bytes - off), &bar);
+    }
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = b < a.B;
+    if (!active) b = a.B - 1;  // keep the whole CTA alive for the barrier; results are not stored
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const Internal in = load_internal(m, pT, ldb);
+    const double ampl = pT[(size_t)m.idx_bao * ldb];
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    double c1, c2;
+    {
+        double ebt = a.S[(size_t)(a.zc_trigger * 3 + 1) * ldb + b];
+        double betaz = in.beta * ebt;
+        if (m.flags & BF_FLAG_CROSS_CORRELATION) {
+            double beta2z = in.beta2 * ebt;
+            c1 = betaz + beta2z;
+            c2 = betaz * beta2z;
+        } else {
+            c1 = 2.0 * betaz;
+            c2 = betaz * betaz;
+        }
+    }
+    double rad[4] = {0, 0, 0, 0};
+    if (m.flags & BF_FLAG_RADIATION_MODEL)
+        for (int k = 0; k < 4; ++k) rad[k] = pT[(size_t)(m.idx_rad + k) * ldb];
+    mbar_wait(&bar, 0);
+    const double2 *tab_pk = tab, *tab_nw = tab + (size_t)m.nr * 9;
+    int st_bits = 0;
+    int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
+    for (int i = i0; i < i1; ++i) {
+        double val = 0.0;
+        if (i < a.npts) {
+            double r = a.r[i], mu = a.mu[i], z = a.z[i];
+            int zc = a.zc[i];
+            double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
+            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            bool zero = false;
+            if (a.mode == 1) {
+                zero = (r < m.rlo || r > m.rhi) || (d.rBAO < m.rlo || d.rBAO > m.rhi);
+            } else {
+                if (d.scalez < m.dilmin) st_bits |= BF_STATUS_DILATION_MIN;
+                else if (d.scalez > m.dilmax) st_bits |= BF_STATUS_DILATION_MAX;
+            }
+            if (!zero) {
+                double peak = shared_correlation(m, tab_pk, d.rBAO, d.muBAO, c1, c2);
+                double smooth = (m.flags & BF_FLAG_DECOUPLED) ? shared_correlation(m, tab_nw, r, mu, c1, c2)
+                                                              : shared_correlation(m, tab_nw, d.rBAO, d.muBAO, c1, c2);
+                double xi = in.biasSq * eb * (ampl * peak + smooth);
+                if (m.metal_kind != BF_METAL_NONE)
+                    xi += metal_eval(m, in, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx ? a.gidx[i] : i, r, mu);
+                if ((m.flags & BF_FLAG_RADIATION_MODEL) && r > 0.0) {
+                    double rd = rad[0] / (r * r);
+                    if (rad[1] > 0.0) rd *= (1.0 - rad[1] * (1.0 - mu * mu));
+                    if (rad[2] > 0.0) rd *= exp(-r / rad[2]);
+                    if (rad[3] > 0.0) rd *= exp(-(r * (1.0 - mu) / (1.0 + z)) / rad[3]);
+                    xi += rd;
+                }
+                if (a.mode == 1) xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL);
+                else xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DIST_ADD, BF_BB_DIST_MUL);
+                val = xi;
+            }
+            if (a.mode == 0) {
+                if (st_bits) val = nan("");
+                if (a.dov) val -= a.dov[(size_t)b * a.npts + i];
+                else if (a.dsub) val -= a.dsub[i];
+            }
+        }
+        if (active) a.out[(size_t)i * a.ldo + b] = val;
+    }
+    if (active && st_bits) atomicOr(a.status + b, st_bits);
+}
+
 // Distortion-matrix tail for data bins: Z = Y (1 + dist mul) + dist add * evol - d, plus the
 // dilation-limit check of the data bin itself (baofit/BaoKSpaceCorrelationModel.cc:420-427,
 // :529-535). Y = D_kept . xi_u comes from the DMMA GEMM.
@@ -461,6 +705,35 @@ void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
     a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
     dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
     kspace_eval_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, int *flag) {
+    kspace_key_check_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, pT, ldb, B, flag);
+}
+
+void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a) {
+    dim3 grid((a.m.nk_pad + 127) / 128, 2);
+    kspace_basis_project_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+void launch_kspace_basis_pack(cudaStream_t s, const DevModel &m, const double *T, const double *C2, double2 *tabs) {
+    int total = 2 * m.nr * 9;
+    kspace_basis_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m, T, C2, tabs);
+}
+
+void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count) {
+    size_t smem = (size_t)2 * a.m.nr * 9 * sizeof(double2);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(kspace_eval_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    int bx = (a.B + 255) / 256;
+    int want = sm_count * 6;
+    int by = max(1, min(a.npts_pad, (want + bx - 1) / bx));
+    a.pts_per_block = (a.npts_pad + by - 1) / by;
+    dim3 grid(bx, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
+    kspace_eval_shared_kernel<<<grid, 256, smem, s>>>(a);
 }
 
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count) {
