@@ -239,6 +239,10 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
             if (b.rt_max < b.rt_min || b.rt_step <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal rT-parameter specification.");
             if (b.z_max < b.z_min || b.z_step <= 0) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: illegal z-parameter specification.");
             if (!chk(b.idx_base, bb_ncoef(b))) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: coefficients outside the parameter vector");
+            auto big = [](int lo, int hi) { return lo < -31 || hi > 31; };
+            if (big(b.r_min, b.r_max) || big(b.rp_min, b.rp_max) || big(b.rt_min, b.rt_max) || big(b.z_min, b.z_max) ||
+                b.r_step > 31 || b.rp_step > 31 || b.rt_step > 31)
+                BF_FAIL(BF_ERR_MODEL, "BroadbandModel: exponents beyond +-31 are not supported");
             if (!(b.r0 > 0)) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: expected r0 > 0");
         }
     BF_CUDA_OK(cudaSetDevice(ctx->device));
@@ -327,7 +331,7 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         const bool mcross = d->metal_kind == BF_METAL_CROSS_BICUBIC;
         // baofit/MetalCorrelationModel.cc:35-37
         if (mcross != cross) { bf::set_error("MetalCorrelationModel: illegal option for cross-correlation."); return fail(BF_ERR_MODEL); }
-        if (d->metal_ncomb < 1 || d->metal_ncomb > 8 || d->metal_nmet < 2 || d->metal_nmet > 6 || !d->metal_p1 || !d->metal_p2 ||
+        if (d->metal_ncomb < 1 || d->metal_ncomb > 20 || d->metal_nmet < 2 || d->metal_nmet > 6 || !d->metal_p1 || !d->metal_p2 ||
             !d->metal_zgrid || d->metal_ngrid < 1 || !chk(d->idx_metal, 2 * (d->metal_nmet - 1))) {
             bf::set_error("MetalCorrelationModel: bad metal description");
             return fail(BF_ERR_MODEL);
@@ -679,9 +683,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
             g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
             BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
-            BF_KERNEL(ctx, "kspace_thomas_kernel[basis]",
-                      launch_kspace_thomas(s, 3, kPadN, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.Tb, w.Cb));
-            BF_KERNEL(ctx, "kspace_basis_pack_kernel", launch_kspace_basis_pack(s, dm, w.Tb, w.Cb, w.tabs));
+            BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, w.tabs));
         } else {
             pa.G = w.G;
             BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));

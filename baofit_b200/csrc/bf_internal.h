@@ -76,7 +76,7 @@ struct DevModel {
     double mu_x[kMuNodes], mu_w[kMuNodes];
     // metals
     int metal_kind, idx_metal, metal_ncomb, metal_nmet, metal_ngrid;
-    int metal_p1[8], metal_p2[8];
+    int metal_p1[20], metal_p2[20];
     const double *metal_auto;   // [ncomb*3][ngrid]
     const double *metal_cross;  // interleaved [ny][nx][ncomb*3]
     int metal_nx, metal_ny;

@@ -5,15 +5,20 @@
 namespace bf {
 
 __device__ __forceinline__ double ipow(double x, int n) {
-    // x^n for integer n by repeated squaring (the reference calls std::pow with an integral
-    // exponent, baofit/BroadbandModel.cc:205-213; results agree to ~1 ulp)
+    // x^n for integer |n| <= 31 (checked when the model is created) by binary powering, written
+    // without a data-dependent loop so that it stays a dozen instructions when inlined.
+    // The reference calls std::pow with an integral exponent (baofit/BroadbandModel.cc:205-213);
+    // results agree to ~1 ulp.
     int m = n < 0 ? -n : n;
-    double r = 1.0, p = x;
-    while (m) {
-        if (m & 1) r *= p;
-        p *= p;
-        m >>= 1;
-    }
+    double r = (m & 1) ? x : 1.0;
+    double p = x * x;
+    if (m & 2) r *= p;
+    p *= p;
+    if (m & 4) r *= p;
+    p *= p;
+    if (m & 8) r *= p;
+    p *= p;
+    if (m & 16) r *= p;
     return n < 0 ? 1.0 / r : r;
 }
 
@@ -34,22 +39,26 @@ __device__ __forceinline__ double legendre_p(int ell, double mu) {  // baofit/Br
 
 // Power sequence of one broadband axis: exponents lo, lo+step, ... with the reference's rule
 // "use (x-1) instead of x when the exponent is positive" (baofit/BroadbandModel.cc:209-213).
-// Powers are advanced by one multiplication per term instead of one pow() per term.
-struct AxisPowers {
-    double neg, pos, neg_step, pos_step;
-    int first_pos;
+// The four starting values are computed once per evaluation point (AxisBase); inside the nested
+// loops each term then costs one multiplication instead of one pow().
+struct AxisBase {
+    double neg0, neg_step, pos0, pos_step;
     __device__ __forceinline__ void init(double x, int lo, int step) {
-        neg = ipow(x, lo);
+        neg0 = ipow(x, lo);
         neg_step = ipow(x, step);
-        first_pos = lo > 0 ? lo : lo + ((0 - lo) / step + 1) * step;  // smallest exponent > 0
-        pos = ipow(x - 1.0, first_pos);
+        int first_pos = lo > 0 ? lo : lo + ((0 - lo) / step + 1) * step;  // smallest exponent > 0
+        pos0 = ipow(x - 1.0, first_pos);
         pos_step = ipow(x - 1.0, step);
     }
+};
+struct AxisIter {
+    double neg, pos;
+    __device__ __forceinline__ explicit AxisIter(const AxisBase &b) : neg(b.neg0), pos(b.pos0) {}
     // value for exponent e (called with e = lo, lo+step, ... in order), then advance
-    __device__ __forceinline__ double next(int e) {
+    __device__ __forceinline__ double next(const AxisBase &b, int e) {
         double v;
-        if (e > 0) { v = pos; pos *= pos_step; }
-        else { v = neg; neg *= neg_step; }
+        if (e > 0) { v = pos; pos *= b.pos_step; }
+        else { v = neg; neg *= b.neg_step; }
         return v;
     }
 };
@@ -60,27 +69,33 @@ __device__ __forceinline__ double broadband_eval(const DevBB &s, const double *_
                                                  double mu, double z) {
     double rr = r * s.inv_r0, rrP = r * mu * s.inv_r0, rrT = r * sqrt(1.0 - mu * mu) * s.inv_r0;
     double zz = (1.0 + z) / (1.0 + s.z0);
+    AxisBase br, bp, bt;
+    if (s.r_denom == 1) br.init(rr, s.r_min, s.r_step);
+    bp.init(rrP, s.rp_min, s.rp_step);
+    bt.init(rrT, s.rt_min, s.rt_step);
     double xi = 0.0;
-    int off = s.idx_base;
+    const double *pc = pT + (size_t)s.idx_base * ldb;  // walks the coefficients, rT fastest
+#pragma unroll 1
     for (int zi = s.z_min; zi <= s.z_max; zi += s.z_step) {
         double zF = ipow(zz, zi);
+#pragma unroll 1
         for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step) {
             double zmF = zF * legendre_p(mi, mu);
-            AxisPowers pr;
-            if (s.r_denom == 1) pr.init(rr, s.r_min, s.r_step);
+            AxisIter ir(br);
+#pragma unroll 1
             for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step) {
-                double rF = s.r_denom == 1 ? pr.next(ri) : pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom);
-                AxisPowers pp;
-                pp.init(rrP, s.rp_min, s.rp_step);
+                double rF = s.r_denom == 1 ? ir.next(br, ri) : pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom);
+                AxisIter ip(bp);
                 double accP = 0.0;
+#pragma unroll 1
                 for (int pi = s.rp_min; pi <= s.rp_max; pi += s.rp_step) {
-                    double rPF = pp.next(pi);
-                    AxisPowers pt;
-                    pt.init(rrT, s.rt_min, s.rt_step);
+                    double rPF = ip.next(bp, pi);
+                    AxisIter it(bt);
                     double acc = 0.0;
+#pragma unroll 2
                     for (int ti = s.rt_min; ti <= s.rt_max; ti += s.rt_step) {
-                        acc = fma(pT[(size_t)off * ldb], pt.next(ti), acc);
-                        ++off;
+                        acc = fma(__ldg(pc), it.next(bt, ti), acc);
+                        pc += ldb;
                     }
                     accP = fma(acc, rPF, accP);
                 }
@@ -178,8 +193,18 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 }
 
 // Metal correlations, baofit/MetalCorrelationModel.cc:235-351.
-// S = per-class evolution factors S[(c*3+k)*ldb] for column b; zc_metal[c*stride + bin] = class ids.
-// Written without dynamically indexed local arrays (those would live in local memory).
+// Everything that depends only on the parameter vector (bias products, beta averages of each line
+// combination) is gathered once per thread into MetalVec; the per-bin part is the redshift
+// evolution, the normalisation factors and the template look-up. No dynamically indexed local
+// arrays (those would live in local memory).
+constexpr int kMaxCombos = 5;            // bicubic cross templates: 4 lines + CIV
+constexpr int kMaxCrossTemplates = 15;   // x 3 multipoles
+
+struct MetalVec {
+    double biasSq[kMaxCombos], betaAvg[kMaxCombos], betaProd[kMaxCombos];
+    double toy_ampl[4], toy_width0;
+};
+
 __device__ __forceinline__ void metal_pair(const DevModel &m, const Internal &in, bool cross,
                                            const double *__restrict__ pT, int ldb, int a, double &beta, double &bias) {
     if (a == 0) {  // :247-248, :282-283
@@ -191,11 +216,62 @@ __device__ __forceinline__ void metal_pair(const DevModel &m, const Internal &in
     }
 }
 
-constexpr int kMaxCrossTemplates = 15;  // (4 + CIV) combinations x 3 multipoles
+__device__ __forceinline__ void metal_load(const DevModel &m, const Internal &in, const double *__restrict__ pT, int ldb,
+                                           MetalVec &mv) {
+    if (m.metal_kind == BF_METAL_TOY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mv.toy_ampl[i] = pT[(size_t)(m.idx_metal + i) * ldb];
+        mv.toy_width0 = pT[(size_t)(m.idx_metal + 4) * ldb];
+    } else if (m.metal_kind == BF_METAL_CROSS_BICUBIC) {
+#pragma unroll
+        for (int c = 0; c < kMaxCombos; ++c) {
+            mv.biasSq[c] = mv.betaAvg[c] = mv.betaProd[c] = 0.0;
+            if (c < m.metal_ncomb) {
+                double ba, bia, bb, bib;
+                metal_pair(m, in, true, pT, ldb, m.metal_p1[c], ba, bia);
+                metal_pair(m, in, true, pT, ldb, m.metal_p2[c], bb, bib);
+                mv.biasSq[c] = bia * bib;
+                mv.betaAvg[c] = 0.5 * (ba + bb);
+                mv.betaProd[c] = ba * bb;
+            }
+        }
+    }
+}
 
-__device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &in, const double *__restrict__ pT,
-                                             int ldb, const double *__restrict__ S, const int *__restrict__ zc_metal,
-                                             int zc_stride, int bin, int grid_index, double r, double mu) {
+template <int NT>
+__device__ __forceinline__ void bicubic_accumulate(const double *__restrict__ grid, int nx, int ny, int ix, int iy,
+                                                   const double (&wx)[4], const double (&wy)[4], double (&acc)[NT]) {
+    int cx[4], cy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cx[j] = wrap_index(ix - 1 + j, nx) * NT;
+        cy[j] = wrap_index(iy - 1 + j, ny) * nx * NT;
+    }
+#pragma unroll
+    for (int jy = 0; jy < 4; ++jy)
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) {
+            const double *cell = grid + cy[jy] + cx[jx];
+            const double w = wx[jx] * wy[jy];
+            if (NT % 2 == 0) {
+#pragma unroll
+                for (int t = 0; t < NT; t += 2) {
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(cell + t));
+                    acc[t] = fma(w, v.x, acc[t]);
+                    acc[t + 1] = fma(w, v.y, acc[t + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) acc[t] = fma(w, __ldg(cell + t), acc[t]);
+            }
+        }
+}
+
+// S = per-class evolution factors S[(c*3+k)*ldb] for column b; zc_metal[c*stride + bin] = class ids.
+__device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &in, const MetalVec &mv,
+                                             const double *__restrict__ pT, int ldb, const double *__restrict__ S,
+                                             const int *__restrict__ zc_metal, int zc_stride, int bin, int grid_index,
+                                             double r, double mu) {
     if (m.metal_kind == BF_METAL_TOY) {
         const double rpar0[4] = {59.533, 111.344, 134.998, 174.525};
         const double sigpar[4] = {0.0, 4.88626, 5.489, 8.48942};
@@ -203,15 +279,14 @@ __device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &
         double rperp = r * sqrt(1.0 - mu * mu), rpar = fabs(r * mu), xi = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            double sp = i == 0 ? pT[(size_t)(m.idx_metal + 4) * ldb] : sigpar[i];
+            double sp = i == 0 ? mv.toy_width0 : sigpar[i];
             double ep = (rpar - rpar0[i]) / sp, et = (rperp - 2.0) / sigperp[i];
-            if (fabs(ep) < 5.0 && fabs(et) < 10.0) xi += 1e-4 * pT[(size_t)(m.idx_metal + i) * ldb] * exp(-ep * ep - et);
+            if (fabs(ep) < 5.0 && fabs(et) < 10.0) xi += 1e-4 * mv.toy_ampl[i] * exp(-ep * ep - et);
         }
         return xi;
     }
-    const bool cross = m.metal_kind == BF_METAL_CROSS_BICUBIC;
     double xi = 0.0;
-    if (cross) {
+    if (m.metal_kind == BF_METAL_CROSS_BICUBIC) {
         // bicubic templates: the 16 patch weights are shared by all templates
         double rperp = r * sqrt(1.0 - mu * mu), rpar = r * mu;
         rperp = fmin(fmax(rperp, m.metal_x0), m.metal_xmax);
@@ -222,42 +297,45 @@ __device__ __forceinline__ double metal_eval(const DevModel &m, const Internal &
         double wx[4], wy[4];
         catmull_weights(fx - flx, wx);
         catmull_weights(fy - fly, wy);
-        const int nt = m.metal_ncomb * 3;
         double acc[kMaxCrossTemplates];
 #pragma unroll
         for (int t = 0; t < kMaxCrossTemplates; ++t) acc[t] = 0.0;
+        if (m.metal_ncomb == 4) {
+            double (&a12)[12] = reinterpret_cast<double (&)[12]>(acc);
+            bicubic_accumulate<12>(m.metal_cross, m.metal_nx, m.metal_ny, ix, iy, wx, wy, a12);
+        } else if (m.metal_ncomb == 5) {
+            bicubic_accumulate<15>(m.metal_cross, m.metal_nx, m.metal_ny, ix, iy, wx, wy, acc);
+        } else {
+            const int nt = m.metal_ncomb * 3;
+            for (int jy = 0; jy < 4; ++jy) {
+                const double *row = m.metal_cross + (size_t)wrap_index(iy - 1 + jy, m.metal_ny) * m.metal_nx * nt;
+                for (int jx = 0; jx < 4; ++jx) {
+                    const double *cell = row + (size_t)wrap_index(ix - 1 + jx, m.metal_nx) * nt;
+                    double w = wx[jx] * wy[jy];
 #pragma unroll
-        for (int jy = 0; jy < 4; ++jy) {
-            const double *row = m.metal_cross + (size_t)wrap_index(iy - 1 + jy, m.metal_ny) * m.metal_nx * nt;
-#pragma unroll
-            for (int jx = 0; jx < 4; ++jx) {
-                const double *cell = row + (size_t)wrap_index(ix - 1 + jx, m.metal_nx) * nt;
-                double w = wx[jx] * wy[jy];
-#pragma unroll
-                for (int t = 0; t < kMaxCrossTemplates; ++t)
-                    if (t < nt) acc[t] = fma(w, __ldg(cell + t), acc[t]);
+                    for (int t = 0; t < kMaxCrossTemplates; ++t)
+                        if (t < nt) acc[t] = fma(w, __ldg(cell + t), acc[t]);
+                }
             }
         }
 #pragma unroll
-        for (int c = 0; c < kMaxCrossTemplates / 3; ++c) {
+        for (int c = 0; c < kMaxCombos; ++c) {
             if (c < m.metal_ncomb) {
-                double ba, bia, bb, bib;
-                metal_pair(m, in, true, pT, ldb, m.metal_p1[c], ba, bia);
-                metal_pair(m, in, true, pT, ldb, m.metal_p2[c], bb, bib);
-                int zc = zc_metal[(size_t)c * zc_stride + bin];
+                int zc = zc_metal[c * zc_stride + bin];
                 double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb];
                 double n0, n2, n4;
-                norm_factors(bia * bib * eb, 0.5 * (ba + bb) * ebeta, ba * bb * ebeta * ebeta, n0, n2, n4);
+                norm_factors(mv.biasSq[c] * eb, mv.betaAvg[c] * ebeta, mv.betaProd[c] * ebeta * ebeta, n0, n2, n4);
                 xi += n0 * acc[3 * c] + n2 * acc[3 * c + 1] + n4 * acc[3 * c + 2];
             }
         }
         return xi;
     }
+    // auto-correlation templates tabulated per grid bin (up to 20 combinations)
     for (int c = 0; c < m.metal_ncomb; ++c) {
         double ba, bia, bb, bib;
         metal_pair(m, in, false, pT, ldb, m.metal_p1[c], ba, bia);
         metal_pair(m, in, false, pT, ldb, m.metal_p2[c], bb, bib);
-        int zc = zc_metal[(size_t)c * zc_stride + bin];
+        int zc = zc_metal[c * zc_stride + bin];
         double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb];
         double n0, n2, n4;
         norm_factors(bia * bib * eb, 0.5 * (ba + bb) * ebeta, ba * bb * ebeta * ebeta, n0, n2, n4);

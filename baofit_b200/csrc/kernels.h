@@ -67,7 +67,7 @@ void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
 // shared-transform fast path (all vectors of the batch share the non-polynomial part of D(k,mu))
 void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, int *flag);
 void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a);  // a.G: [6][nk_pad][kPadN], columns 0..2
-void launch_kspace_basis_pack(cudaStream_t s, const DevModel &m, const double *T, const double *C2, double2 *tabs);
+void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs);
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count);
 

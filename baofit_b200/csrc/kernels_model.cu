@@ -36,22 +36,38 @@ struct Dilated {
     double rBAO, muBAO, scalez;
 };
 
-__device__ __forceinline__ Dilated dilate(const DevModel &m, const double *__restrict__ pT, int ldb, double es,
-                                          double r, double mu) {
+// Everything a thread needs about its parameter vector, loaded once before the bin loop.
+struct VecCtx {
+    Internal in;
+    double ampl, dv, apar, aperp, iso, rad[4];
+    MetalVec mv;
+};
+
+__device__ __forceinline__ void load_vec(const DevModel &m, const double *__restrict__ pT, int ldb, bool want_rad,
+                                         VecCtx &v) {
+    v.in = load_internal(m, pT, ldb);
+    v.ampl = pT[(size_t)m.idx_bao * ldb];
+    v.iso = pT[(size_t)(m.idx_bao + 1) * ldb];
+    v.apar = pT[(size_t)(m.idx_bao + 2) * ldb];
+    v.aperp = (m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * v.apar
+                                                 : pT[(size_t)(m.idx_bao + 3) * ldb];
+    v.dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v.rad[k] = want_rad ? pT[(size_t)(m.idx_rad + k) * ldb] : 0.0;
+    if (m.metal_kind != BF_METAL_NONE) metal_load(m, v.in, pT, ldb, v.mv);
+}
+
+__device__ __forceinline__ Dilated dilate(const DevModel &m, const VecCtx &v, double es, double r, double mu) {
     // baofit/BaoCorrelationModel.cc:104-127, baofit/BaoKSpaceCorrelationModel.cc:403-417
     Dilated d;
     if (m.flags & BF_FLAG_ANISOTROPIC) {
-        double apar = pT[(size_t)(m.idx_bao + 2) * ldb];
-        double aperp = (m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * apar
-                                                          : pT[(size_t)(m.idx_bao + 3) * ldb];
-        apar *= es;
-        aperp *= es;
+        double apar = v.apar * es, aperp = v.aperp * es;
         double musq = mu * mu;
         d.scalez = sqrt(apar * apar * musq + aperp * aperp * (1.0 - musq));
         d.rBAO = r * d.scalez;
         d.muBAO = apar * mu / d.scalez;
     } else {
-        d.scalez = pT[(size_t)(m.idx_bao + 1) * ldb] * es;
+        d.scalez = v.iso * es;
         d.rBAO = r * d.scalez;
         d.muBAO = mu;
     }
@@ -76,12 +92,11 @@ __global__ void __launch_bounds__(128) rspace_eval_kernel(EvalArgs a) {
     const int ldb = a.ldb;
     const double *pT = a.pT + b;
     const double *S = a.S + b;
-    const Internal in = load_internal(m, pT, ldb);
-    const double ampl = pT[(size_t)m.idx_bao * ldb];
-    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
-    double rad[4] = {0, 0, 0, 0};
-    if (m.idx_rad >= 0)
-        for (int k = 0; k < 4; ++k) rad[k] = pT[(size_t)(m.idx_rad + k) * ldb];
+    VecCtx v;
+    load_vec(m, pT, ldb, m.idx_rad >= 0, v);
+    const Internal &in = v.in;
+    const double ampl = v.ampl;
+    const double *rad = v.rad;
     int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
     for (int i = i0; i < i1; ++i) {
         double val = 0.0;
@@ -90,8 +105,8 @@ __global__ void __launch_bounds__(128) rspace_eval_kernel(EvalArgs a) {
             int zc = a.zc[i];
             double eb = S[(size_t)(zc * 3 + 0) * ldb], ebeta = S[(size_t)(zc * 3 + 1) * ldb],
                    es = S[(size_t)(zc * 3 + 2) * ldb];
-            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
-            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            if (m.idx_delta_v >= 0) velocity_shift(v.dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, v, es, r, mu);
             double n0, n2, n4;
             norm_factors(in.biasSq * eb, in.betaAvg * ebeta, in.betaProd * ebeta * ebeta, n0, n2, n4);
             double musq = d.muBAO * d.muBAO;
@@ -110,7 +125,7 @@ __global__ void __launch_bounds__(128) rspace_eval_kernel(EvalArgs a) {
             }
             double xi = peak + smooth;
             if (m.metal_kind != BF_METAL_NONE)
-                xi += metal_eval(m, in, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx[i], r, mu);
+                xi += metal_eval(m, in, v.mv, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx[i], r, mu);
             xi = post_broadband(m, pT, ldb, eb, xi, r, mu, z, BF_BB_DIST_ADD, BF_BB_DIST_MUL);
             if (m.idx_rad >= 0 && rad[0] > 0.0 && r > 0.0) {  // :165-176
                 double rd = rad[0] / (r * r);
@@ -353,12 +368,11 @@ __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
     const int ldb = a.ldb;
     const double *pT = a.pT + b;
     const double *S = a.S + b;
-    const Internal in = load_internal(m, pT, ldb);
-    const double ampl = pT[(size_t)m.idx_bao * ldb];
-    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
-    double rad[4] = {0, 0, 0, 0};
-    if (m.flags & BF_FLAG_RADIATION_MODEL)
-        for (int k = 0; k < 4; ++k) rad[k] = pT[(size_t)(m.idx_rad + k) * ldb];
+    VecCtx v;
+    load_vec(m, pT, ldb, (m.flags & BF_FLAG_RADIATION_MODEL) != 0, v);
+    const Internal &in = v.in;
+    const double ampl = v.ampl;
+    const double *rad = v.rad;
     int st_bits = 0;
     int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
     for (int i = i0; i < i1; ++i) {
@@ -367,8 +381,8 @@ __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
             double r = a.r[i], mu = a.mu[i], z = a.z[i];
             int zc = a.zc[i];
             double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
-            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
-            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            if (m.idx_delta_v >= 0) velocity_shift(v.dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, v, es, r, mu);
             bool zero = false;
             if (a.mode == 1) {
                 zero = (r < m.rlo || r > m.rhi) || (d.rBAO < m.rlo || d.rBAO > m.rhi);
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
                                                               : kspace_correlation(a, 1, b, d.rBAO, d.muBAO);
                 double xi = in.biasSq * eb * (ampl * peak + smooth);
                 if (m.metal_kind != BF_METAL_NONE)
-                    xi += metal_eval(m, in, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx ? a.gidx[i] : i, r, mu);
+                    xi += metal_eval(m, in, v.mv, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx ? a.gidx[i] : i, r, mu);
                 if ((m.flags & BF_FLAG_RADIATION_MODEL) && r > 0.0) {  // :441-455
                     double rd = rad[0] / (r * r);
                     if (rad[1] > 0.0) rd *= (1.0 - rad[1] * (1.0 - mu * mu));
@@ -463,16 +477,46 @@ __global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
             a.G[((size_t)(comp * 3 + l) * m.nk_pad + i) * kPadN + n] = l <= lmax ? (2 * l * 2 + 1) * s[l][n] : 0.0;
 }
 
-// tabs[(comp*nr + j)*9 + l*3 + n] = { X_{l,n}(r_j), X''_{l,n}(r_j)/2 }
-__global__ void kspace_basis_pack_kernel(DevModel m, const double *__restrict__ T, const double *__restrict__ C2,
-                                         double2 *__restrict__ tabs) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = 2 * m.nr * 9;
-    if (idx >= total) return;
-    int q = idx % 9, j = (idx / 9) % m.nr, comp = idx / (9 * m.nr);
-    int l = q / 3, n = q % 3;
-    size_t src = ((size_t)(comp * 3 + l) * m.nr_pad + j) * kPadN + n;
-    tabs[idx] = make_double2(T[src], C2[src]);
+// Natural-spline second derivatives of the 18 basis tables and packing for the evaluation
+// kernel: tabs[(comp*nr + j)*9 + l*3 + n] = { X_{l,n}(r_j), X''_{l,n}(r_j)/2 }.
+// One CTA; the 18 serial (1,4,1) sweeps run in shared memory instead of global memory.
+__global__ void __launch_bounds__(256) kspace_basis_finish_kernel(DevModel m, const double *__restrict__ T,
+                                                                  double2 *__restrict__ tabs) {
+    extern __shared__ double sh[];  // y[18][nr], c[18][nr]
+    const int nr = m.nr;
+    double *y = sh, *c = sh + 18 * nr;
+    for (int idx = threadIdx.x; idx < 18 * nr; idx += blockDim.x) {
+        int t = idx / nr, j = idx % nr;  // t = comp*9 + l*3 + n
+        int comp = t / 9, l = (t % 9) / 3, n = t % 3;
+        y[idx] = T[((size_t)(comp * 3 + l) * m.nr_pad + j) * kPadN + n];
+    }
+    __syncthreads();
+    if (threadIdx.x < 18) {
+        double *yy = y + threadIdx.x * nr, *cc = c + threadIdx.x * nr;
+        const int msz = nr - 2;
+        const double h = m.tr_dr, inv_h = 1.0 / h;
+        cc[0] = 0.0;
+        cc[nr - 1] = 0.0;
+        double gprev = 0.0;
+        for (int i = 0; i < msz; ++i) {
+            double g = 3.0 * ((yy[i + 2] - yy[i + 1]) * inv_h - (yy[i + 1] - yy[i]) * inv_h);
+            if (i > 0) g -= m.th_w[i] * gprev;
+            cc[i + 1] = g;
+            gprev = g;
+        }
+        double cnext = 0.0;
+        for (int i = msz - 1; i >= 0; --i) {
+            double ci = (cc[i + 1] - h * cnext) * m.th_inv_diag[i];
+            cc[i + 1] = ci;
+            cnext = ci;
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 18 * nr; idx += blockDim.x) {
+        int t = idx / nr, j = idx % nr;
+        int comp = t / 9, q = t % 9;
+        tabs[((size_t)comp * nr + j) * 9 + q] = make_double2(y[idx], c[idx]);
+    }
 }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -544,7 +588,7 @@ __device__ __forceinline__ double shared_correlation(const DevModel &m, const do
 }
 
 // Same contract as kspace_eval_kernel, basis tables in shared memory (TMA bulk copy + mbarrier).
-__global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(256, 2) kspace_eval_shared_kernel(EvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
     __shared__ __align__(8) unsigned long long bar;
@@ -565,9 +609,11 @@ __global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
     const int ldb = a.ldb;
     const double *pT = a.pT + b;
     const double *S = a.S + b;
-    const Internal in = load_internal(m, pT, ldb);
-    const double ampl = pT[(size_t)m.idx_bao * ldb];
-    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    VecCtx v;
+    load_vec(m, pT, ldb, (m.flags & BF_FLAG_RADIATION_MODEL) != 0, v);
+    const Internal &in = v.in;
+    const double ampl = v.ampl;
+    const double *rad = v.rad;
     double c1, c2;
     {
         double ebt = a.S[(size_t)(a.zc_trigger * 3 + 1) * ldb + b];
@@ -581,9 +627,6 @@ __global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
             c2 = betaz * betaz;
         }
     }
-    double rad[4] = {0, 0, 0, 0};
-    if (m.flags & BF_FLAG_RADIATION_MODEL)
-        for (int k = 0; k < 4; ++k) rad[k] = pT[(size_t)(m.idx_rad + k) * ldb];
     mbar_wait(&bar, 0);
     const double2 *tab_pk = tab, *tab_nw = tab + (size_t)m.nr * 9;
     int st_bits = 0;
@@ -594,8 +637,8 @@ __global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
             double r = a.r[i], mu = a.mu[i], z = a.z[i];
             int zc = a.zc[i];
             double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
-            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
-            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            if (m.idx_delta_v >= 0) velocity_shift(v.dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, v, es, r, mu);
             bool zero = false;
             if (a.mode == 1) {
                 zero = (r < m.rlo || r > m.rhi) || (d.rBAO < m.rlo || d.rBAO > m.rhi);
@@ -609,7 +652,7 @@ __global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
                                                               : shared_correlation(m, tab_nw, d.rBAO, d.muBAO, c1, c2);
                 double xi = in.biasSq * eb * (ampl * peak + smooth);
                 if (m.metal_kind != BF_METAL_NONE)
-                    xi += metal_eval(m, in, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx ? a.gidx[i] : i, r, mu);
+                    xi += metal_eval(m, in, v.mv, pT, ldb, S, a.zc_metal, a.zc_stride, i, a.gidx ? a.gidx[i] : i, r, mu);
                 if ((m.flags & BF_FLAG_RADIATION_MODEL) && r > 0.0) {
                     double rd = rad[0] / (r * r);
                     if (rad[1] > 0.0) rd *= (1.0 - rad[1] * (1.0 - mu * mu));
@@ -635,14 +678,20 @@ __global__ void __launch_bounds__(256) kspace_eval_shared_kernel(EvalArgs a) {
 // Distortion-matrix tail for data bins: Z = Y (1 + dist mul) + dist add * evol - d, plus the
 // dilation-limit check of the data bin itself (baofit/BaoKSpaceCorrelationModel.cc:420-427,
 // :529-535). Y = D_kept . xi_u comes from the DMMA GEMM.
-__global__ void __launch_bounds__(128) dist_post_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(128, 4) dist_post_kernel(EvalArgs a) {
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const int ldb = a.ldb;
     const double *pT = a.pT + b;
     const double *S = a.S + b;
-    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    VecCtx v;
+    v.in = Internal();
+    v.iso = pT[(size_t)(m.idx_bao + 1) * ldb];
+    v.apar = pT[(size_t)(m.idx_bao + 2) * ldb];
+    v.aperp = (m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * v.apar
+                                                 : pT[(size_t)(m.idx_bao + 3) * ldb];
+    v.dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
     int st_bits = 0;
     int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, a.npts_pad);
     for (int i = i0; i < i1; ++i) {
@@ -651,8 +700,8 @@ __global__ void __launch_bounds__(128) dist_post_kernel(EvalArgs a) {
             double r = a.r[i], mu = a.mu[i], z = a.z[i];
             int zc = a.zc[i];
             double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
-            if (m.idx_delta_v >= 0) velocity_shift(dv * a.vfac[zc], r, mu);
-            Dilated d = dilate(m, pT, ldb, es, r, mu);
+            if (m.idx_delta_v >= 0) velocity_shift(v.dv * a.vfac[zc], r, mu);
+            Dilated d = dilate(m, v, es, r, mu);
             if (d.scalez < m.dilmin) st_bits |= BF_STATUS_DILATION_MIN;
             else if (d.scalez > m.dilmax) st_bits |= BF_STATUS_DILATION_MAX;
             double xi = a.in[(size_t)i * a.ldo + b];
@@ -716,9 +765,14 @@ void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a) {
     kspace_basis_project_kernel<<<grid, 128, 0, s>>>(a);
 }
 
-void launch_kspace_basis_pack(cudaStream_t s, const DevModel &m, const double *T, const double *C2, double2 *tabs) {
-    int total = 2 * m.nr * 9;
-    kspace_basis_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m, T, C2, tabs);
+void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs) {
+    size_t smem = (size_t)36 * m.nr * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(kspace_basis_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    kspace_basis_finish_kernel<<<1, 256, smem, s>>>(m, T, tabs);
 }
 
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count) {

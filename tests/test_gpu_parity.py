@@ -146,14 +146,14 @@ def test_kspace_shared_and_per_vector_paths_agree(ctx):
     rng = np.random.Generator(np.random.PCG64(32))
     params = m.random_batch(65, rng, sweep={"BAO alpha-parallel": (0.85, 1.2), "BAO alpha-perp": (0.7, 1.3)})
     gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
-    l0 = ctx.launches
+    ctx.set_profiling(True)
     shared, _ = capi.chi2_batch(ctx, gm, gd, params[1:])
-    n_shared = ctx.launches - l0
+    assert any(k.startswith("kspace_eval_shared_kernel") for k in ctx.get_profile())
     mixed = params.copy()
     mixed[0, m.index("SigmaNL-perp")] *= 1.1
-    l0 = ctx.launches
+    ctx.set_profiling(True)
     generic, _ = capi.chi2_batch(ctx, gm, gd, mixed)
-    n_generic = ctx.launches - l0
-    assert n_shared != n_generic
+    assert any(k.startswith("kspace_project_kernel") for k in ctx.get_profile())
+    ctx.set_profiling(False)
     assert rel_err(shared, generic[1:]) < RTOL
     gm.close(), gd.close()
