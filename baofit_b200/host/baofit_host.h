@@ -1,0 +1,335 @@
+// Host-side C++ mirror of the reference's hot-path interfaces (namespace baofit).
+//
+// Class names, constructor argument order, parameter names / order and error messages follow
+// the reference so that these remain drop-in plugins configured by the same .ini files:
+//   AbsCorrelationModel        baofit/AbsCorrelationModel.{h,cc}
+//   BaoCorrelationModel        baofit/BaoCorrelationModel.{h,cc}
+//   BaoKSpaceCorrelationModel  baofit/BaoKSpaceCorrelationModel.{h,cc}
+//   BroadbandModel             baofit/BroadbandModel.{h,cc}
+//   MetalCorrelationModel      baofit/MetalCorrelationModel.{h,cc}
+//   NonLinearCorrectionModel   baofit/NonLinearCorrectionModel.{h,cc}
+//   DistortionMatrix           baofit/DistortionMatrix.{h,cc}
+//   AbsCorrelationData, ComovingCorrelationData, loadCorrelationData   baofit/*Data.{h,cc}
+//   CorrelationFitter          baofit/CorrelationFitter.{h,cc}
+//   CorrelationAnalyzer        baofit/CorrelationAnalyzer.{h,cc} (fitSample, parameterScan, toy MC)
+// What differs: the models do not evaluate anything themselves. Their constructors lay out the
+// parameters and describe the model in a bf_model_desc; every number is computed by the CUDA
+// library through the C ABI (include/baofit_b200.h), batched over parameter vectors.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/baofit_b200.h"
+#include "likely_lite.h"
+
+namespace baofit {
+
+// ---- device binding ---------------------------------------------------------------------------
+// One CUDA context per process (one process per GPU); created on first use.
+bf_ctx *deviceContext();
+void setDevice(int device);  // call before the first use to pick a GPU (default 0)
+void releaseDeviceContext();
+
+// ---- models -----------------------------------------------------------------------------------
+class AbsCorrelationModel {
+public:
+    explicit AbsCorrelationModel(std::string const &name);
+    virtual ~AbsCorrelationModel();
+    // likely::FitModel interface (subset)
+    int defineParameter(std::string const &name, double value, double error);
+    int getNParameters() const { return (int)_parameters.size(); }
+    void configureFitParameters(std::string const &script);
+    likely::FitParameters const &getFitParameters() const { return _parameters; }
+    int findParameter(std::string const &name) const;  // -1 if absent
+    std::string const &getName() const { return _name; }
+    // Sets the grid coordinates to use for the distortion matrix (AbsCorrelationModel.cc:51-63).
+    void setCoordinates(std::vector<double> rbin, std::vector<double> mubin, std::vector<double> zbin);
+    std::vector<double> const &gridR() const { return _rbin; }
+    std::vector<double> const &gridMu() const { return _mubin; }
+    std::vector<double> const &gridZ() const { return _zbin; }
+    // Single-point evaluation kept for interface parity (AbsCorrelationModel.cc:21-41). It runs
+    // a batch of one through the CUDA path; use CorrelationFitter for anything hot.
+    double evaluate(double r, double mu, double z, likely::Parameters const &params, int index);
+    // The device-resident model (created on first use, after all parameters are defined).
+    bf_model *deviceModel();
+    bf_model_desc const &description() { finalizeDescription(); return _desc; }
+    virtual void printToStream(std::ostream &out) const;
+
+protected:
+    friend class BroadbandModel;
+    friend class MetalCorrelationModel;
+    friend class NonLinearCorrectionModel;
+    friend class DistortionMatrix;
+    // Defines the standard linear bias parameters (AbsCorrelationModel.cc:91-130); returns the
+    // index of the last parameter defined.
+    int _defineLinearBiasParameters(double zref, bool crossCorrelation = false, bool combinedBias = false);
+    void _setZRef(double zref);
+    void _setOmegaMatter(double OmegaMatter);
+    virtual void finalizeDescription() {}
+    bf_model_desc _desc;
+    // owned copies of every array the descriptor points at
+    std::vector<std::vector<double>> _arrays;
+    std::vector<std::vector<int>> _iarrays;
+    const double *_keep(std::vector<double> const &v);
+    const int *_keep(std::vector<int> const &v);
+
+private:
+    std::string _name;
+    likely::FitParameters _parameters;
+    std::vector<double> _rbin, _mubin, _zbin;
+    bf_model *_device = nullptr;
+};
+typedef std::shared_ptr<AbsCorrelationModel> AbsCorrelationModelPtr;
+
+// Parses the broadband specification (grammar of BroadbandModel.cc:21-90) and registers the
+// coefficients on the parent model (BroadbandModel.cc:141-166).
+class BroadbandModel {
+public:
+    BroadbandModel(std::string const &name, std::string const &tag, std::string const &paramSpec, double r0,
+                   double z0, AbsCorrelationModel *base);
+    bf_broadband_spec const &spec() const { return _spec; }
+    int _getIndexBase() const { return _spec.idx_base; }
+
+private:
+    bf_broadband_spec _spec;
+};
+
+// Reads the dense matrix from "<name>.dmat" lines "i j value" (DistortionMatrix.cc:22-73).
+class DistortionMatrix {
+public:
+    DistortionMatrix(std::string const &distMatrixName, int distMatrixOrder, bool verbose = false);
+    DistortionMatrix(std::vector<double> const &dense, int order);  // in-memory variant
+    double getDistortion(int index1, int index2) const;             // DistortionMatrix.cc:77-83
+    int order() const { return _nbins; }
+    std::vector<double> const &dense() const { return _dist; }
+
+private:
+    int _nbins;
+    std::vector<double> _dist;
+};
+
+// Registers the metal-line parameters on the parent and loads the templates
+// (MetalCorrelationModel.cc:27-161).
+class MetalCorrelationModel {
+public:
+    MetalCorrelationModel(std::string const &metalModelName, bool metalModel, bool metalModelInterpolate,
+                          bool metalCIV, bool toyMetal, bool crossCorrelation, AbsCorrelationModel *base);
+    void fill(bf_model_desc &d, AbsCorrelationModel &owner) const;
+
+private:
+    int _kind, _indexBase, _ncomb = 0, _nmet = 0, _ngrid = 0, _nx = 0, _ny = 0;
+    double _x0 = 0, _y0 = 0, _dx = 0, _dy = 0;
+    std::vector<int> _p1, _p2;
+    std::vector<double> _zgrid, _auto, _cross;
+    friend class AbsCorrelationModel;
+};
+
+class BaoCorrelationModel : public AbsCorrelationModel {
+public:
+    // Same argument list as baofit/BaoCorrelationModel.h (BaoCorrelationModel.cc:18-23)
+    BaoCorrelationModel(std::string const &modelrootName, std::string const &fiducialName,
+                        std::string const &nowigglesName, std::string const &metalModelName,
+                        std::string const &distAdd, std::string const &distMul, double distR0, double zref,
+                        double OmegaMatter, bool anisotropic = false, bool decoupled = false,
+                        bool metalModel = false, bool metalModelInterpolate = false, bool metalCIV = false,
+                        bool toyMetal = false, bool combinedBias = false, bool combinedScale = false,
+                        bool crossCorrelation = false);
+
+private:
+    std::shared_ptr<MetalCorrelationModel> _metalCorr;
+    std::shared_ptr<BroadbandModel> _distortAdd, _distortMul;
+};
+
+class BaoKSpaceCorrelationModel : public AbsCorrelationModel {
+public:
+    // Same argument list as baofit/BaoKSpaceCorrelationModel.h (BaoKSpaceCorrelationModel.cc:26-39)
+    BaoKSpaceCorrelationModel(std::string const &modelrootName, std::string const &fiducialName,
+                              std::string const &nowigglesName, std::string const &distMatrixName,
+                              std::string const &metalModelName, double zref, double OmegaMatter, double rmin,
+                              double rmax, double dilmin, double dilmax, double relerr, double abserr, int ellMax,
+                              int samplesPerDecade, std::string const &distAdd, std::string const &distMul,
+                              double distR0, double zeff, double sigma8, double dzmin, int distMatrixOrder,
+                              std::string const &distMatrixDistAdd, std::string const &distMatrixDistMul,
+                              bool anisotropic = false, bool decoupled = false, bool nlBroadband = false,
+                              bool nlCorrection = false, bool fitNLCorrection = false, bool nlCorrectionAlt = false,
+                              bool binSmooth = false, bool binSmoothAlt = false, bool hcdModel = false,
+                              bool hcdModelAlt = false, bool uvfluctuation = false, bool radiationModel = false,
+                              bool smoothGauss = false, bool smoothLorentz = false, bool distMatrix = false,
+                              bool metalModel = false, bool metalModelInterpolate = false, bool metalCIV = false,
+                              bool toyMetal = false, bool combinedBias = false, bool combinedScale = false,
+                              bool crossCorrelation = false, bool verbose = false);
+    // in-memory distortion matrix (synthetic workloads, tests)
+    void setDistortionMatrix(std::shared_ptr<DistortionMatrix> dm);
+
+private:
+    std::shared_ptr<MetalCorrelationModel> _metalCorr;
+    std::shared_ptr<DistortionMatrix> _distMat;
+    std::shared_ptr<BroadbandModel> _distortAdd, _distortMul, _distMatDistortAdd, _distMatDistortMul;
+};
+
+// ---- data -------------------------------------------------------------------------------------
+class BinnedGrid {
+public:
+    BinnedGrid() {}
+    BinnedGrid(std::vector<double> a1, std::vector<double> a2, std::vector<double> a3);
+    int getNBinsTotal() const { return (int)(_axis[0].size() * _axis[1].size() * _axis[2].size()); }
+    // bin centres of global index (axis 1 slowest, axis 3 fastest)
+    void getBinCenters(int index, double centers[3]) const;
+
+private:
+    std::vector<double> _axis[3];
+};
+BinnedGrid createCorrelationGrid(std::string const &axis1Bins, std::string const &axis2Bins,
+                                 std::string const &axis3Bins);  // AbsCorrelationData.cc:96-150
+
+class AbsCorrelationData {
+public:
+    enum TransverseBinningType { Coordinate, Multipole };
+    AbsCorrelationData(BinnedGrid grid, TransverseBinningType type);
+    virtual ~AbsCorrelationData();
+    virtual double getRadius(int index) const = 0;
+    virtual double getCosAngle(int index) const { return 0; }
+    virtual double getRedshift(int index) const = 0;
+    // BinnedData subset
+    void setData(int index, double value);
+    bool hasData(int index) const { return _values.count(index) > 0; }
+    void setCovariance(int i, int j, double value);
+    void setInverseCovariance(int i, int j, double value);
+    int getNBinsWithData() const { return (int)_values.size(); }
+    BinnedGrid const &getGrid() const { return _grid; }
+    std::vector<int> const &keptIndices() const { return _kept; }
+    double getData(int index) const;
+    // AbsCorrelationData.cc:34-54
+    void setFinalCuts(double rMin, double rMax, double rVetoMin, double rVetoMax, double muMin, double muMax,
+                      double rperpMin, double rperpMax, double rparMin, double rparMax, int lMin, int lMax,
+                      double zMin, double zMax);
+    // applies the final cuts (AbsCorrelationData.cc:67-94), prunes, and freezes the data set
+    virtual void finalize();
+    bool isFinalized() const { return _finalized; }
+    // coordinates of every grid bin, for AbsCorrelationModel::setCoordinates
+    void gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const;
+    // device-resident data (kept bins, d, Cholesky factors); gridFor: model whose distortion
+    // matrix needs the full grid (may be null)
+    bf_data *deviceData(bool withGrid);
+    std::vector<double> dataVector() const;           // kept bins, iteration order
+    std::vector<double> covarianceMatrix() const;     // dense kept x kept (cov or icov as loaded)
+    bool isInverse() const { return _isInverse; }
+
+protected:
+    BinnedGrid _grid;
+    TransverseBinningType _type;
+
+private:
+    std::map<int, double> _values;
+    std::map<std::pair<int, int>, double> _cov;
+    bool _isInverse = false, _haveCov = false, _haveFinalCuts = false, _finalized = false;
+    double _rMin, _rMax, _rVetoMin, _rVetoMax, _muMin, _muMax, _rperpMin, _rperpMax, _rparMin, _rparMax, _zMin, _zMax;
+    int _lMin, _lMax;
+    std::vector<int> _kept;
+    bf_data *_device = nullptr;
+    bool _deviceHasGrid = false;
+};
+typedef std::shared_ptr<AbsCorrelationData> AbsCorrelationDataPtr;
+
+class ComovingCorrelationData : public AbsCorrelationData {
+public:
+    enum CoordinateSystem { PolarCoordinates, CartesianCoordinates, MultipoleCoordinates };
+    ComovingCorrelationData(BinnedGrid grid, CoordinateSystem coordinateSystem);
+    double getRadius(int index) const override;    // ComovingCorrelationData.cc:46-55
+    double getCosAngle(int index) const override;  // ComovingCorrelationData.cc:57-69
+    double getRedshift(int index) const override;  // ComovingCorrelationData.cc:81-84
+
+private:
+    CoordinateSystem _coordinateSystem;
+};
+
+// "<name>.data" / ".cov" / ".icov" text loaders (AbsCorrelationData.cc:156-277); ".cov.gz" is not
+// handled here (tests decompress fixtures first).
+void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov = false);
+
+// ---- fitter -----------------------------------------------------------------------------------
+class CorrelationFitter {
+public:
+    // CorrelationFitter.cc:20-42
+    CorrelationFitter(AbsCorrelationDataPtr data, AbsCorrelationModelPtr model, int covSampleSize = 0);
+    void setErrorScale(double scale);
+    // CorrelationFitter.cc:53-72
+    void getPrediction(likely::Parameters const &params, std::vector<double> &prediction) const;
+    // CorrelationFitter.cc:74-86: (0.5*icovScale*chi2 + priors)/errorScale
+    double operator()(likely::Parameters const &params) const;
+    // The batched entry point: fval[b] for B parameter vectors in one CUDA pass; dataOverride is
+    // empty or B alternative data vectors (toy MC).
+    void evaluateBatch(std::vector<likely::Parameters> const &params, std::vector<double> &fval,
+                       std::vector<std::vector<double>> const *dataOverride = nullptr) const;
+    void predictBatch(std::vector<likely::Parameters> const &params, std::vector<double> &pred /*[n][B]*/) const;
+    // CorrelationFitter.cc:88-92; method is accepted for interface parity ("mn2::vmetric")
+    likely::FunctionMinimumPtr fit(std::string const &methodName = "mn2::vmetric", std::string const &config = "") const;
+    AbsCorrelationModelPtr model() const { return _model; }
+    AbsCorrelationDataPtr data() const { return _data; }
+    double icovScale() const { return _icovScale; }
+
+private:
+    AbsCorrelationDataPtr _data;
+    AbsCorrelationModelPtr _model;
+    double _errorScale, _icovScale;
+};
+
+// ---- analyzer (the callers either side of the hot path) ----------------------------------------
+struct ScanResult {
+    likely::FunctionMinimumPtr best;          // unconstrained fit
+    std::vector<std::string> axisNames;       // scanned parameters, in parameter order
+    std::vector<std::vector<double>> points;  // [npoints][npar] best-fit parameters at each grid point
+    std::vector<double> chi2;                 // 2 * fval at each grid point (0 for failed fits)
+    std::vector<int> status;
+};
+
+class CorrelationAnalyzer {
+public:
+    CorrelationAnalyzer(std::string const &method = "mn2::vmetric", double rmin = 0, double rmax = 200,
+                        int covSampleSize = 0, bool verbose = false);
+    void addData(AbsCorrelationDataPtr data) { _data = data; }
+    void setModel(AbsCorrelationModelPtr model) { _model = model; }
+    // CorrelationAnalyzer.cc:169-190
+    likely::FunctionMinimumPtr fitSample(AbsCorrelationDataPtr sample, std::string const &config = "") const;
+    // CorrelationAnalyzer.cc:573-605: refits at every point of the parameter binning grid, last
+    // axis fastest; grid points [first, first+count) only (count < 0: all) so that ranks can
+    // shard the grid. All fits of the shard run in lock step on the GPU.
+    ScanResult parameterScan(AbsCorrelationDataPtr sample, long first = 0, long count = -1) const;
+    long scanSize() const;
+    // writes the reference's scan.dat layout (CorrelationAnalyzer.cc:379-443)
+    static void writeScan(std::string const &path, ScanResult const &scan);
+    // CorrelationAnalyzer.cc:337-373 + 452-532: toy MC samples [first, first+count) drawn on the GPU
+    // from the truth prediction + L g, each refitted; returns best-fit vectors and 2*fval
+    void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
+                         std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "") const;
+
+private:
+    std::string _method;
+    int _covSampleSize;
+    bool _verbose;
+    AbsCorrelationDataPtr _data;
+    AbsCorrelationModelPtr _model;
+};
+
+// ---- .ini driven construction -----------------------------------------------------------------
+struct Options {
+    std::map<std::string, std::string> values;       // last value wins
+    std::vector<std::string> modelConfig;             // composing, in order
+    std::set<std::string> flags;                      // bool switches that are on
+    bool has(std::string const &k) const { return values.count(k) > 0; }
+    std::string str(std::string const &k, std::string const &def = "") const;
+    double num(std::string const &k, double def) const;
+    bool flag(std::string const &k) const { return flags.count(k) > 0; }
+};
+// Parses an INI text (key = value, '#' comments; "yes/true/1" switches; model-config composes).
+Options parseIni(std::string const &text);
+// src/baofit.cc:415-464: builds the model the options describe (r-space or --kspace).
+AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDir);
+// src/baofit.cc:475-628 (comoving formats): builds, loads, cuts and finalizes the data set.
+AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir);
+
+}  // namespace baofit

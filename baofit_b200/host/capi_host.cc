@@ -1,0 +1,210 @@
+// C entry points over the host-side classes (include/baofit_b200_host.h).
+#include <cstring>
+#include <string>
+
+#include "../../include/baofit_b200_host.h"
+#include "baofit_host.h"
+
+using namespace baofit;
+
+struct bfh_session {
+    Options options;
+    AbsCorrelationModelPtr model;
+    AbsCorrelationDataPtr data;
+    std::shared_ptr<CorrelationFitter> fitter;
+    std::shared_ptr<CorrelationAnalyzer> analyzer;
+};
+
+static thread_local std::string g_herr;
+extern "C" const char *bfh_last_error(void) { return g_herr.c_str(); }
+
+#define BFH_TRY try {
+#define BFH_CATCH                          \
+    }                                      \
+    catch (std::exception const &e) {      \
+        g_herr = e.what();                 \
+        return -4;                         \
+    }                                      \
+    return 0;
+
+extern "C" int bfh_set_device(int device) {
+    BFH_TRY
+    setDevice(device);
+    BFH_CATCH
+}
+
+extern "C" int bfh_session_create(const char *ini_text, const char *base_dir, const char *extra_config, bfh_session **out) {
+    if (!ini_text || !out) { g_herr = "null argument"; return -1; }
+    bfh_session *s = new bfh_session();
+    try {
+        s->options = parseIni(ini_text);
+        if (extra_config && *extra_config) s->options.modelConfig.push_back(extra_config);
+    } catch (std::exception const &e) { g_herr = e.what(); delete s; return -1; }
+    try {
+        s->model = createModel(s->options, base_dir ? base_dir : "");
+    } catch (std::exception const &e) { g_herr = e.what(); delete s; return -2; }
+    try {
+        s->data = createData(s->options, base_dir ? base_dir : "");
+        if (s->options.flag("dist-matrix")) {
+            std::vector<double> r, mu, z;
+            s->data->gridCoordinates(r, mu, z);
+            s->model->setCoordinates(r, mu, z);
+        }
+    } catch (std::exception const &e) { g_herr = e.what(); delete s; return -3; }
+    try {
+        int covSampleSize = (int)s->options.num("cov-sample-size", 0);
+        s->fitter.reset(new CorrelationFitter(s->data, s->model, covSampleSize));
+        s->analyzer.reset(new CorrelationAnalyzer(s->options.str("min-method", "mn2::vmetric"), s->options.num("rmin", 0),
+                                                  s->options.num("rmax", 200), covSampleSize, false));
+        s->analyzer->addData(s->data);
+        s->analyzer->setModel(s->model);
+    } catch (std::exception const &e) { g_herr = e.what(); delete s; return -4; }
+    *out = s;
+    return 0;
+}
+
+extern "C" int bfh_session_destroy(bfh_session *s) {
+    delete s;
+    return 0;
+}
+
+extern "C" int bfh_npar(const bfh_session *s) { return s ? s->model->getNParameters() : 0; }
+extern "C" int bfh_ndata(const bfh_session *s) { return s ? (int)s->data->keptIndices().size() : 0; }
+extern "C" const char *bfh_param_name(const bfh_session *s, int i) {
+    if (!s || i < 0 || i >= s->model->getNParameters()) return "";
+    return s->model->getFitParameters()[i].name.c_str();
+}
+extern "C" int bfh_param_info(const bfh_session *s, double *values, double *errors, int *floating) {
+    BFH_TRY
+    auto const &p = s->model->getFitParameters();
+    for (size_t i = 0; i < p.size(); ++i) {
+        if (values) values[i] = p[i].value;
+        if (errors) errors[i] = p[i].error;
+        if (floating) floating[i] = p[i].floating ? 1 : 0;
+    }
+    BFH_CATCH
+}
+extern "C" int bfh_kept_indices(const bfh_session *s, int *indices) {
+    BFH_TRY
+    auto const &k = s->data->keptIndices();
+    std::copy(k.begin(), k.end(), indices);
+    BFH_CATCH
+}
+
+extern "C" int bfh_set_distortion_matrix(bfh_session *s, const double *dense, int order) {
+    BFH_TRY
+    auto *km = dynamic_cast<BaoKSpaceCorrelationModel *>(s->model.get());
+    if (!km) throw RuntimeError("the distortion matrix needs the k-space model");
+    if (order != s->data->getGrid().getNBinsTotal()) throw RuntimeError("Distortion matrix order does not match grid size.");
+    std::vector<double> d(dense, dense + (size_t)order * order);
+    km->setDistortionMatrix(std::make_shared<DistortionMatrix>(d, order));
+    std::vector<double> r, mu, z;
+    s->data->gridCoordinates(r, mu, z);
+    s->model->setCoordinates(r, mu, z);
+    BFH_CATCH
+}
+
+static std::vector<likely::Parameters> unflatten(const double *params, int B, int npar) {
+    std::vector<likely::Parameters> v(B);
+    for (int b = 0; b < B; ++b) v[b].assign(params + (size_t)b * npar, params + (size_t)(b + 1) * npar);
+    return v;
+}
+
+extern "C" int bfh_evaluate_batch(bfh_session *s, const double *params, int B, double *fval) {
+    BFH_TRY
+    std::vector<double> f;
+    s->fitter->evaluateBatch(unflatten(params, B, s->model->getNParameters()), f);
+    std::copy(f.begin(), f.end(), fval);
+    BFH_CATCH
+}
+
+extern "C" int bfh_predict_batch(bfh_session *s, const double *params, int B, double *pred) {
+    BFH_TRY
+    std::vector<double> p;
+    s->fitter->predictBatch(unflatten(params, B, s->model->getNParameters()), p);
+    std::copy(p.begin(), p.end(), pred);
+    BFH_CATCH
+}
+
+extern "C" int bfh_fit(bfh_session *s, const char *config, double *values, double *errors, double *fval, int *status,
+                       int *nevaluations, double *covariance) {
+    BFH_TRY
+    likely::FunctionMinimumPtr fm = s->fitter->fit("mn2::vmetric", config ? config : "");
+    for (size_t i = 0; i < fm->parameters.size(); ++i) {
+        if (values) values[i] = fm->parameters[i].value;
+        if (errors) errors[i] = fm->parameters[i].floating ? fm->parameters[i].error : 0.0;
+    }
+    if (fval) *fval = fm->minValue;
+    if (status) *status = (int)fm->status;
+    if (nevaluations) *nevaluations = fm->nEvaluations;
+    if (covariance) std::copy(fm->covariance.begin(), fm->covariance.end(), covariance);
+    BFH_CATCH
+}
+
+extern "C" int bfh_scan_size(const bfh_session *s, long *total) {
+    BFH_TRY
+    *total = s->analyzer->scanSize();
+    BFH_CATCH
+}
+
+extern "C" int bfh_parameter_scan(bfh_session *s, long first, long count, double *chi2, double *points, int *status,
+                                  double *best) {
+    BFH_TRY
+    ScanResult r = s->analyzer->parameterScan(s->data, first, count);
+    int npar = s->model->getNParameters();
+    for (size_t k = 0; k < r.chi2.size(); ++k) {
+        if (chi2) chi2[k] = r.chi2[k];
+        if (status) status[k] = r.status[k];
+        if (points) std::copy(r.points[k].begin(), r.points[k].end(), points + k * npar);
+    }
+    if (best) {
+        likely::Parameters v = r.best->values();
+        std::copy(v.begin(), v.end(), best);
+        best[npar] = 2 * r.best->minValue;
+    }
+    BFH_CATCH
+}
+
+extern "C" int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
+                         int *status) {
+    BFH_TRY
+    std::vector<std::vector<double>> fit;
+    std::vector<double> c;
+    std::vector<int> st;
+    s->analyzer->doToyMCSampling(first, count, seed, fit, c, st);
+    int npar = s->model->getNParameters();
+    for (long t = 0; t < count; ++t) {
+        if (fitted) std::copy(fit[t].begin(), fit[t].end(), fitted + (size_t)t * npar);
+        if (chi2) chi2[t] = c[t];
+        if (status) status[t] = st[t];
+    }
+    BFH_CATCH
+}
+
+extern "C" int bfh_minimize(int npar, const double *values, const double *errors, const int *floating, bfh_batch_fn fn,
+                            void *user, double *out_values, double *out_errors, double *fval, int *status,
+                            int *nevaluations) {
+    BFH_TRY
+    likely::FitParameters params(npar);
+    for (int i = 0; i < npar; ++i) {
+        params[i].name = "p" + std::to_string(i);
+        params[i].value = values[i];
+        params[i].error = errors[i];
+        params[i].floating = floating[i] != 0;
+    }
+    std::vector<likely::NewtonFit> fits(1, likely::NewtonFit(params));
+    likely::runLockStep(fits, [&](std::vector<likely::Parameters> const &pts, std::vector<double> &f) {
+        std::vector<double> flat(pts.size() * (size_t)npar);
+        for (size_t b = 0; b < pts.size(); ++b) std::copy(pts[b].begin(), pts[b].end(), flat.begin() + b * npar);
+        fn(flat.data(), (int)pts.size(), f.data(), user);
+    });
+    likely::FunctionMinimumPtr fm = fits[0].result();
+    for (int i = 0; i < npar; ++i) {
+        if (out_values) out_values[i] = fm->parameters[i].value;
+        if (out_errors) out_errors[i] = fm->parameters[i].floating ? fm->parameters[i].error : 0.0;
+    }
+    if (fval) *fval = fm->minValue;
+    if (status) *status = (int)fm->status;
+    if (nevaluations) *nevaluations = fm->nEvaluations;
+    BFH_CATCH
+}

@@ -1,0 +1,235 @@
+// Host-side binned data: grid, loaders, final cuts (bit-exact restatement of the reference's
+// comparisons), device upload.
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "baofit_host.h"
+
+namespace baofit {
+
+namespace {
+void check(int rc, const char *what) {
+    if (rc != BF_OK) throw RuntimeError(std::string(what) + ": " + bf_last_error());
+}
+}  // namespace
+
+BinnedGrid::BinnedGrid(std::vector<double> a1, std::vector<double> a2, std::vector<double> a3) {
+    _axis[0] = a1;
+    _axis[1] = a2;
+    _axis[2] = a3;
+}
+
+void BinnedGrid::getBinCenters(int index, double centers[3]) const {
+    if (index < 0 || index >= getNBinsTotal()) throw RuntimeError("BinnedGrid: invalid bin index.");
+    int n2 = (int)_axis[1].size(), n3 = (int)_axis[2].size();
+    int i3 = index % n3, i2 = (index / n3) % n2, i1 = index / (n3 * n2);  // last axis fastest
+    centers[0] = _axis[0][i1];
+    centers[1] = _axis[1][i2];
+    centers[2] = _axis[2][i3];
+}
+
+BinnedGrid createCorrelationGrid(std::string const &axis1Bins, std::string const &axis2Bins, std::string const &axis3Bins) {
+    std::vector<double> a[3];
+    const std::string *spec[3] = {&axis1Bins, &axis2Bins, &axis3Bins};
+    for (int i = 0; i < 3; ++i) {
+        try {
+            a[i] = likely::createBinning(*spec[i]);
+        } catch (likely::RuntimeError const &) {
+            throw RuntimeError("createCorrelationGrid: error in axis " + std::to_string(i + 1) + " binning.");
+        }
+    }
+    return BinnedGrid(a[0], a[1], a[2]);
+}
+
+AbsCorrelationData::AbsCorrelationData(BinnedGrid grid, TransverseBinningType type) : _grid(grid), _type(type) {}
+
+AbsCorrelationData::~AbsCorrelationData() {
+    if (_device) bf_data_destroy(_device);
+}
+
+void AbsCorrelationData::setData(int index, double value) {
+    if (_finalized) throw RuntimeError("AbsCorrelationData: data is finalized.");
+    if (index < 0 || index >= _grid.getNBinsTotal()) throw RuntimeError("AbsCorrelationData::setData: invalid bin index.");
+    _values[index] = value;
+}
+
+double AbsCorrelationData::getData(int index) const {
+    auto it = _values.find(index);
+    if (it == _values.end()) throw RuntimeError("AbsCorrelationData::getData: bin has no data.");
+    return it->second;
+}
+
+void AbsCorrelationData::setCovariance(int i, int j, double value) {
+    if (_haveCov && _isInverse) throw RuntimeError("AbsCorrelationData: cannot mix covariance and inverse covariance.");
+    _haveCov = true;
+    _isInverse = false;
+    _cov[std::make_pair(std::min(i, j), std::max(i, j))] = value;
+}
+
+void AbsCorrelationData::setInverseCovariance(int i, int j, double value) {
+    if (_haveCov && !_isInverse) throw RuntimeError("AbsCorrelationData: cannot mix covariance and inverse covariance.");
+    _haveCov = true;
+    _isInverse = true;
+    _cov[std::make_pair(std::min(i, j), std::max(i, j))] = value;
+}
+
+void AbsCorrelationData::setFinalCuts(double rMin, double rMax, double rVetoMin, double rVetoMax, double muMin,
+                                      double muMax, double rperpMin, double rperpMax, double rparMin, double rparMax,
+                                      int lMin, int lMax, double zMin, double zMax) {
+    if (rMin > rMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected r-min <= r-max.");
+    if (rVetoMin > rVetoMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected rveto-min <= rveto-max.");
+    if (muMin > muMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected mu-min <= mu-max.");
+    if (rperpMin > rperpMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected rperp-min <= rperp-max.");
+    if (rparMin > rparMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected rpar-min <= rpar-max.");
+    if (lMin > lMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected lmin <= lmax.");
+    if (zMin > zMax) throw RuntimeError("AbsCorrelationData::setFinalCuts: expected z-min <= z-max.");
+    _rMin = rMin; _rMax = rMax; _rVetoMin = rVetoMin; _rVetoMax = rVetoMax; _muMin = muMin; _muMax = muMax;
+    _rperpMin = rperpMin; _rperpMax = rperpMax; _rparMin = rparMin; _rparMax = rparMax; _lMin = lMin; _lMax = lMax;
+    _zMin = zMin; _zMax = zMax;
+    _haveFinalCuts = true;
+}
+
+void AbsCorrelationData::finalize() {
+    if (_finalized) return;
+    if (!_haveFinalCuts) throw RuntimeError("AbsCorrelationData: no final cuts specified yet.");
+    if (_type != Coordinate) throw RuntimeError("AbsCorrelationData: multipole data is not supported by the CUDA path yet.");
+    // same comparisons in the same order as AbsCorrelationData.cc:71-93 (std::map iterates in
+    // ascending index order, like the reference's IndexIterator)
+    for (auto const &kv : _values) {
+        int index = kv.first;
+        double r = getRadius(index), z = getRedshift(index);
+        if (r < _rMin || r > _rMax) continue;
+        if (r > _rVetoMin && r < _rVetoMax) continue;
+        if (z < _zMin || z > _zMax) continue;
+        double mu = getCosAngle(index);
+        if (mu < _muMin || mu > _muMax) continue;
+        double rpar = r * mu;
+        if (rpar < _rparMin || rpar > _rparMax) continue;
+        double rperp = r * std::sqrt(1 - mu * mu);
+        if (rperp < _rperpMin || rperp > _rperpMax) continue;
+        _kept.push_back(index);
+    }
+    if (_kept.empty()) throw RuntimeError("CorrelationFitter: need some data to fit.");
+    if (!_haveCov) throw RuntimeError("AbsCorrelationData: no covariance loaded.");
+    _finalized = true;
+}
+
+void AbsCorrelationData::gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const {
+    int n = _grid.getNBinsTotal();
+    r.resize(n); mu.resize(n); z.resize(n);
+    for (int i = 0; i < n; ++i) { r[i] = getRadius(i); mu[i] = getCosAngle(i); z[i] = getRedshift(i); }
+}
+
+std::vector<double> AbsCorrelationData::dataVector() const {
+    std::vector<double> d;
+    for (int idx : _kept) d.push_back(_values.at(idx));
+    return d;
+}
+
+std::vector<double> AbsCorrelationData::covarianceMatrix() const {
+    int n = (int)_kept.size();
+    std::map<int, int> pos;
+    for (int i = 0; i < n; ++i) pos[_kept[i]] = i;
+    std::vector<double> c((size_t)n * n, 0.0);
+    for (auto const &kv : _cov) {
+        auto a = pos.find(kv.first.first), b = pos.find(kv.first.second);
+        if (a == pos.end() || b == pos.end()) continue;
+        c[(size_t)a->second * n + b->second] = kv.second;
+        c[(size_t)b->second * n + a->second] = kv.second;
+    }
+    return c;
+}
+
+bf_data *AbsCorrelationData::deviceData(bool withGrid) {
+    if (!_finalized) finalize();
+    if (_device && _deviceHasGrid == withGrid) return _device;
+    if (_device) { bf_data_destroy(_device); _device = nullptr; }
+    int n = (int)_kept.size();
+    std::vector<double> r(n), mu(n), z(n), d = dataVector(), cov = covarianceMatrix(), gr, gmu, gz;
+    for (int i = 0; i < n; ++i) { r[i] = getRadius(_kept[i]); mu[i] = getCosAngle(_kept[i]); z[i] = getRedshift(_kept[i]); }
+    bf_data_desc dd;
+    std::memset(&dd, 0, sizeof(dd));
+    dd.n_data = n;
+    dd.r = r.data(); dd.mu = mu.data(); dd.z = z.data(); dd.index = _kept.data(); dd.data = d.data();
+    dd.cov = cov.data();
+    dd.cov_is_inverse = _isInverse ? 1 : 0;
+    if (withGrid) {
+        gridCoordinates(gr, gmu, gz);
+        dd.n_grid = (int)gr.size();
+        dd.grid_r = gr.data(); dd.grid_mu = gmu.data(); dd.grid_z = gz.data();
+    }
+    check(bf_data_create(deviceContext(), &dd, &_device), "bf_data_create");
+    _deviceHasGrid = withGrid;
+    return _device;
+}
+
+ComovingCorrelationData::ComovingCorrelationData(BinnedGrid grid, CoordinateSystem coordinateSystem)
+    : AbsCorrelationData(grid, coordinateSystem == MultipoleCoordinates ? Multipole : Coordinate),
+      _coordinateSystem(coordinateSystem) {}
+
+double ComovingCorrelationData::getRadius(int index) const {
+    double c[3];
+    _grid.getBinCenters(index, c);
+    if (_coordinateSystem == CartesianCoordinates) {
+        double rpar = c[0], rperp = c[1];
+        return std::sqrt(rpar * rpar + rperp * rperp);
+    }
+    return c[0];
+}
+
+double ComovingCorrelationData::getCosAngle(int index) const {
+    double c[3];
+    _grid.getBinCenters(index, c);
+    if (_coordinateSystem == PolarCoordinates) return c[1];
+    if (_coordinateSystem == CartesianCoordinates) {
+        double rpar = c[0], rperp = c[1];
+        return rpar / std::sqrt(rpar * rpar + rperp * rperp);
+    }
+    throw RuntimeError("ComovingCorrelationData::getMultipole: invalid coordinate system.");
+}
+
+double ComovingCorrelationData::getRedshift(int index) const {
+    double c[3];
+    _grid.getBinCenters(index, c);
+    return c[2];
+}
+
+void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov) {
+    std::string paramsName = dataName + ".data";
+    std::ifstream in(paramsName.c_str());
+    if (!in.good()) throw RuntimeError("loadCorrelationData: Unable to open " + paramsName);
+    std::string line;
+    int lines = 0;
+    while (std::getline(in, line)) {
+        lines++;
+        std::istringstream ss(line);
+        int index;
+        double value;
+        // first two tokens only: trailing junk is accepted like the reference's phrase_parse
+        if (!(ss >> index >> value))
+            throw RuntimeError("loadCorrelationData: error reading line " + std::to_string(lines) + " of " + paramsName);
+        data.setData(index, value);
+    }
+    in.close();
+    int nbins = data.getGrid().getNBinsTotal();
+    std::string covName = dataName + (icov ? ".icov" : ".cov");
+    std::ifstream cin(covName.c_str());
+    if (!cin.good()) throw RuntimeError("loadCorrelationData: Unable to open " + covName);
+    lines = 0;
+    while (std::getline(cin, line)) {
+        lines++;
+        std::istringstream ss(line);
+        int i1, i2;
+        double value;
+        if (!(ss >> i1 >> i2 >> value))
+            throw RuntimeError("loadCorrelationData: error reading line " + std::to_string(lines) + " of " + covName);
+        if (i1 < 0 || i2 < 0 || i1 >= nbins || i2 >= nbins || !data.hasData(i1) || !data.hasData(i2))
+            throw RuntimeError("loadCorrelationData: invalid covariance indices on line " + std::to_string(lines) + " of " + covName);
+        if (icov) data.setInverseCovariance(i1, i2, value);
+        else data.setCovariance(i1, i2, value);
+    }
+}
+
+}  // namespace baofit

@@ -1,0 +1,364 @@
+// CorrelationFitter (the objective, batched) and CorrelationAnalyzer (fit, scan, toy MC drivers).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <sstream>
+
+#include "baofit_host.h"
+
+namespace baofit {
+
+namespace {
+void check(int rc, const char *what) {
+    if (rc != BF_OK) throw RuntimeError(std::string(what) + ": " + bf_last_error());
+}
+}  // namespace
+
+CorrelationFitter::CorrelationFitter(AbsCorrelationDataPtr data, AbsCorrelationModelPtr model, int covSampleSize)
+    : _data(data), _model(model), _errorScale(1) {
+    if (!data || 0 == data->getNBinsWithData()) throw RuntimeError("CorrelationFitter: need some data to fit.");
+    if (!model) throw RuntimeError("CorrelationFitter: need a model to fit.");
+    if (!data->isFinalized()) data->finalize();
+    int n = (int)data->keptIndices().size();
+    if (0 < covSampleSize) {
+        if (covSampleSize <= n + 2) throw RuntimeError("CorrelationFitter: cannot fit with covSampleSize <= nbins+2");
+        // eqn (25) of http://arxiv.org/abs/1212.4359, CorrelationFitter.cc:31-37
+        _icovScale = (covSampleSize - n - 2.) / (covSampleSize - 1.);
+    } else
+        _icovScale = 1;
+}
+
+void CorrelationFitter::setErrorScale(double scale) {
+    if (scale <= 0) throw RuntimeError("CorrelationFitter::setErrorScale: expected scale > 0.");
+    _errorScale = scale;
+}
+
+static bool needsGrid(AbsCorrelationModelPtr const &model) { return model->description().dist_matrix != nullptr; }
+
+void CorrelationFitter::predictBatch(std::vector<likely::Parameters> const &params, std::vector<double> &pred) const {
+    int B = (int)params.size(), npar = _model->getNParameters(), n = (int)_data->keptIndices().size();
+    std::vector<double> flat((size_t)B * npar);
+    for (int b = 0; b < B; ++b) {
+        if ((int)params[b].size() != npar) throw RuntimeError("CorrelationFitter: got unexpected number of parameters.");
+        std::copy(params[b].begin(), params[b].end(), flat.begin() + (size_t)b * npar);
+    }
+    pred.assign((size_t)n * B, 0.0);
+    std::vector<int> status(B);
+    check(bf_eval_batch(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), flat.data(), B,
+                        pred.data(), B, status.data()),
+          "bf_eval_batch");
+}
+
+void CorrelationFitter::getPrediction(likely::Parameters const &params, std::vector<double> &prediction) const {
+    std::vector<likely::Parameters> one(1, params);
+    predictBatch(one, prediction);
+}
+
+void CorrelationFitter::evaluateBatch(std::vector<likely::Parameters> const &params, std::vector<double> &fval,
+                                      std::vector<std::vector<double>> const *dataOverride) const {
+    int B = (int)params.size(), npar = _model->getNParameters(), n = (int)_data->keptIndices().size();
+    fval.assign(B, 0.0);
+    if (B == 0) return;
+    std::vector<double> flat((size_t)B * npar), ov;
+    for (int b = 0; b < B; ++b) {
+        if ((int)params[b].size() != npar) throw RuntimeError("CorrelationFitter: got unexpected number of parameters.");
+        std::copy(params[b].begin(), params[b].end(), flat.begin() + (size_t)b * npar);
+    }
+    if (dataOverride) {
+        if ((int)dataOverride->size() != B) throw RuntimeError("CorrelationFitter: one data vector per parameter vector expected.");
+        ov.resize((size_t)B * n);
+        for (int b = 0; b < B; ++b) {
+            if ((int)(*dataOverride)[b].size() != n) throw RuntimeError("CorrelationFitter: data override has the wrong length.");
+            std::copy((*dataOverride)[b].begin(), (*dataOverride)[b].end(), ov.begin() + (size_t)b * n);
+        }
+    }
+    std::vector<double> chi2(B);
+    std::vector<int> status(B);
+    check(bf_chi2_batch(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), flat.data(), B,
+                        dataOverride ? ov.data() : nullptr, chi2.data(), status.data()),
+          "bf_chi2_batch");
+    likely::FitParameters const &fp = _model->getFitParameters();
+    for (int b = 0; b < B; ++b) {
+        // CorrelationFitter.cc:85; a vector the reference would have thrown on evaluates to NaN
+        fval[b] = status[b] ? std::numeric_limits<double>::quiet_NaN()
+                            : (0.5 * _icovScale * chi2[b] + likely::evaluatePriors(fp, params[b])) / _errorScale;
+    }
+}
+
+double CorrelationFitter::operator()(likely::Parameters const &params) const {
+    if ((int)params.size() != _model->getNParameters()) throw RuntimeError("CorrelationFitter: got unexpected number of parameters.");
+    std::vector<likely::Parameters> one(1, params);
+    std::vector<double> f;
+    evaluateBatch(one, f);
+    if (!std::isfinite(f[0])) throw RuntimeError("BaoKSpaceCorrelationModel: hit dilation limit.");
+    return f[0];
+}
+
+likely::FunctionMinimumPtr CorrelationFitter::fit(std::string const &methodName, std::string const &config) const {
+    (void)methodName;
+    likely::FitParameters params = _model->getFitParameters();
+    if (!config.empty()) likely::modifyFitParameters(params, config);
+    std::vector<likely::NewtonFit> fits(1, likely::NewtonFit(params));
+    likely::runLockStep(fits, [this](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { evaluateBatch(pts, f); });
+    return fits[0].result();
+}
+
+// ------------------------------------------------------------------------------------------
+// CorrelationAnalyzer
+// ------------------------------------------------------------------------------------------
+CorrelationAnalyzer::CorrelationAnalyzer(std::string const &method, double rmin, double rmax, int covSampleSize, bool verbose)
+    : _method(method), _covSampleSize(covSampleSize), _verbose(verbose) {
+    (void)rmin;
+    (void)rmax;
+}
+
+likely::FunctionMinimumPtr CorrelationAnalyzer::fitSample(AbsCorrelationDataPtr sample, std::string const &config) const {
+    CorrelationFitter fitter(sample, _model, _covSampleSize);
+    return fitter.fit(_method, config);
+}
+
+long CorrelationAnalyzer::scanSize() const {
+    long n = 1;
+    bool any = false;
+    for (auto const &p : _model->getFitParameters())
+        if (!p.binning.empty()) { n *= (long)p.binning.size(); any = true; }
+    return any ? n : 0;
+}
+
+ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long first, long count) const {
+    ScanResult out;
+    CorrelationFitter fitter(sample, _model, _covSampleSize);
+    likely::FitParameters base = _model->getFitParameters();
+    // one axis per parameter with a binning, in parameter order; last axis fastest
+    // (likely::getFitParametersGrid, CorrelationAnalyzer.cc:578-584)
+    std::vector<int> axes;
+    for (size_t i = 0; i < base.size(); ++i)
+        if (!base[i].binning.empty()) { axes.push_back((int)i); out.axisNames.push_back(base[i].name); }
+    if (axes.empty()) throw RuntimeError("CorrelationAnalyzer::parameterScan: no parameter has a binning.");
+    long total = scanSize();
+    if (count < 0) count = total - first;
+    if (first < 0 || first + count > total) throw RuntimeError("CorrelationAnalyzer::parameterScan: bad grid range.");
+    std::vector<likely::NewtonFit> fits;
+    fits.reserve(count + 1);
+    // the unconstrained best fit runs in the same lock-step batch
+    fits.push_back(likely::NewtonFit(base));
+    for (long g = first; g < first + count; ++g) {
+        likely::FitParameters p = base;
+        long rem = g;
+        for (int a = (int)axes.size() - 1; a >= 0; --a) {
+            int nb = (int)base[axes[a]].binning.size();
+            int ib = (int)(rem % nb);
+            rem /= nb;
+            p[axes[a]].value = base[axes[a]].binning[ib];
+            p[axes[a]].floating = false;  // "fix[name]=value"
+        }
+        // each grid fit starts from the model's initial configuration, not from the best fit
+        // (CorrelationAnalyzer.cc:591)
+        fits.push_back(likely::NewtonFit(p));
+    }
+    likely::runLockStep(fits, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
+    out.best = fits[0].result();
+    for (long k = 0; k < count; ++k) {
+        likely::FunctionMinimumPtr fm = fits[k + 1].result();
+        bool ok = fm->status != likely::FunctionMinimum::ERROR;
+        out.points.push_back(fm->values());
+        out.chi2.push_back(ok ? 2 * fm->minValue : 0.0);  // failed fits are saved with fval = 0 (:595-602)
+        out.status.push_back((int)fm->status);
+    }
+    return out;
+}
+
+void CorrelationAnalyzer::writeScan(std::string const &path, ScanResult const &scan) {
+    // three header lines (npar ndump nfit / errors / best fit) then one line per sample: all
+    // parameter values followed by 2*fval (CorrelationAnalyzer.cc:379-443); ndump = 0, nfit = 1
+    std::ofstream out(path.c_str());
+    if (!out.good()) throw RuntimeError("CorrelationAnalyzer: unable to open " + path);
+    char buf[64];
+    auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.10g", v); return std::string(buf); };
+    int npar = (int)scan.best->parameters.size();
+    out << npar << " 0 1" << std::endl;
+    for (int i = 0; i < npar; ++i) out << (i ? " " : "") << num(scan.best->parameters[i].floating ? scan.best->parameters[i].error : 0.0);
+    out << std::endl;
+    for (int i = 0; i < npar; ++i) out << num(scan.best->parameters[i].value) << " ";
+    out << num(2 * scan.best->minValue) << std::endl;
+    for (size_t k = 0; k < scan.points.size(); ++k) {
+        for (int i = 0; i < npar; ++i) out << num(scan.points[k][i]) << " ";
+        out << num(scan.chi2[k]) << std::endl;
+    }
+}
+
+void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long long seed,
+                                          std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
+                                          std::vector<int> &status, std::string const &toymcConfig) const {
+    if (!_data || !_model) throw RuntimeError("CorrelationAnalyzer::doToyMCSampling: need data and a model.");
+    CorrelationFitter fitter(_data, _model, _covSampleSize);
+    // truth = model prediction at the (optionally reconfigured) initial parameters (:362-369)
+    likely::FitParameters truthParams = _model->getFitParameters();
+    if (!toymcConfig.empty()) likely::modifyFitParameters(truthParams, toymcConfig);
+    likely::Parameters tp;
+    for (auto const &p : truthParams) tp.push_back(p.value);
+    std::vector<double> truth;
+    fitter.getPrediction(tp, truth);
+    int n = (int)_data->keptIndices().size();
+    std::vector<double> toys((size_t)count * n);
+    bool grid = _model->description().dist_matrix != nullptr;
+    check(bf_sample_toys(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, toys.data()),
+          "bf_sample_toys");
+    // every toy is refitted from the model's initial configuration; all fits in lock step, each
+    // evaluation batch carries the data vector of the toy its point belongs to
+    std::vector<likely::NewtonFit> fits((size_t)count, likely::NewtonFit(_model->getFitParameters()));
+    std::vector<likely::Parameters> points;
+    std::vector<std::vector<double>> ov;
+    std::vector<double> values;
+    for (;;) {
+        points.clear();
+        ov.clear();
+        bool any = false;
+        for (long t = 0; t < count; ++t) {
+            if (fits[t].done()) continue;
+            size_t before = points.size();
+            fits[t].request(points);
+            std::vector<double> d(toys.begin() + (size_t)t * n, toys.begin() + (size_t)(t + 1) * n);
+            for (size_t k = before; k < points.size(); ++k) ov.push_back(d);
+            any = true;
+        }
+        if (!any) break;
+        fitter.evaluateBatch(points, values, &ov);
+        size_t off = 0;
+        for (long t = 0; t < count; ++t) {
+            if (fits[t].done()) continue;
+            int np = fits[t].pending();
+            fits[t].consume(values.data() + off);
+            off += np;
+        }
+    }
+    fitted.clear(); chi2.clear(); status.clear();
+    for (long t = 0; t < count; ++t) {
+        likely::FunctionMinimumPtr fm = fits[t].result();
+        fitted.push_back(fm->values());
+        chi2.push_back(2 * fm->minValue);
+        status.push_back((int)fm->status);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// options
+// ------------------------------------------------------------------------------------------
+std::string Options::str(std::string const &k, std::string const &def) const {
+    auto it = values.find(k);
+    return it == values.end() ? def : it->second;
+}
+double Options::num(std::string const &k, double def) const {
+    auto it = values.find(k);
+    if (it == values.end()) return def;
+    char *end = nullptr;
+    double v = std::strtod(it->second.c_str(), &end);
+    if (end == it->second.c_str()) throw RuntimeError("option " + k + " expects a number, got '" + it->second + "'");
+    return v;
+}
+
+Options parseIni(std::string const &text) {
+    static const char *switches[] = {"kspace", "kspace-fft", "kspace-hybrid", "anisotropic", "decoupled", "nl-broadband",
+                                     "nl-correction", "fit-nl-correction", "nl-correction-alt", "distortion-alt",
+                                     "no-distortion", "bin-smooth", "bin-smooth-alt", "hcd-model", "hcd-model-alt",
+                                     "uvfluctuation", "radiation-model", "smooth-gauss", "smooth-lorentz", "dist-matrix",
+                                     "metal-model", "metal-model-interpolate", "metal-civ", "toy-metal", "combined-bias",
+                                     "combined-scale", "cross-correlation", "load-icov", "custom-grid", "parameter-scan",
+                                     "verbose", "quiet"};
+    Options o;
+    std::stringstream ss(text);
+    std::string line;
+    auto trim = [](std::string s) {
+        size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+        return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+    };
+    while (std::getline(ss, line)) {
+        size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        line = trim(line);
+        if (line.empty()) continue;
+        size_t eq = line.find('=');
+        std::string key = trim(eq == std::string::npos ? line : line.substr(0, eq));
+        std::string val = eq == std::string::npos ? "" : trim(line.substr(eq + 1));
+        bool isSwitch = false;
+        for (const char *s : switches) isSwitch |= key == s;
+        if (isSwitch) {
+            std::string v = val;
+            std::transform(v.begin(), v.end(), v.begin(), ::tolower);
+            if (v.empty() || v == "yes" || v == "true" || v == "1" || v == "on") o.flags.insert(key);
+            else if (v == "no" || v == "false" || v == "0" || v == "off") o.flags.erase(key);
+            else throw RuntimeError("option " + key + " expects yes/no, got '" + val + "'");
+        } else if (key == "model-config") {
+            o.modelConfig.push_back(val);  // composing, order preserved (src/baofit.cc:335-338)
+        } else {
+            o.values[key] = val;
+        }
+    }
+    return o;
+}
+
+static std::string resolve(std::string const &baseDir, std::string const &path) {
+    if (path.empty() || path[0] == '/' || baseDir.empty()) return path;
+    return baseDir + (baseDir.back() == '/' ? "" : "/") + path;
+}
+
+AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDir) {
+    // defaults of src/baofit.cc:58-178
+    double OmegaMatter = opt.num("omega-matter", 0.27), zref = opt.num("zref", 2.25), distR0 = opt.num("dist-r0", 100);
+    std::string modelroot = resolve(baseDir, opt.str("modelroot")), fid = opt.str("fiducial"), nw = opt.str("nowiggles");
+    std::string distAdd = opt.str("dist-add"), distMul = opt.str("dist-mul");
+    std::string metalName = opt.str("metal-model-name");
+    if (!metalName.empty()) metalName = resolve(baseDir, metalName);
+    AbsCorrelationModelPtr model;
+    if (opt.flag("kspace-fft") || opt.flag("kspace-hybrid"))
+        throw RuntimeError("the FFT / hybrid k-space models are not built in this round (DESIGN.md, out of scope so far)");
+    if (opt.flag("kspace")) {
+        std::string dmName = opt.str("dist-matrix-name");
+        if (dmName.empty() && opt.flag("dist-matrix")) dmName = opt.str("data");  // src/baofit.cc: data name by default
+        if (!dmName.empty()) dmName = resolve(baseDir, dmName);
+        model.reset(new BaoKSpaceCorrelationModel(
+            modelroot, fid, nw, dmName, metalName, zref, OmegaMatter, opt.num("rmin", 0), opt.num("rmax", 200),
+            opt.num("dilmin", 0.5), opt.num("dilmax", 1.5), opt.num("relerr", 1e-3), opt.num("abserr", 1e-5),
+            (int)opt.num("ell-max", 4), (int)opt.num("samples-per-decade", 50), distAdd, distMul, distR0, opt.num("zeff", 0),
+            opt.num("sigma8", 0.8338), opt.num("dzmin", 0.5), (int)opt.num("dist-matrix-order", 2500),
+            opt.str("dist-matrix-dist-add"), opt.str("dist-matrix-dist-mul"), opt.flag("anisotropic"), opt.flag("decoupled"),
+            opt.flag("nl-broadband"), opt.flag("nl-correction"), opt.flag("fit-nl-correction"), opt.flag("nl-correction-alt"),
+            opt.flag("bin-smooth"), opt.flag("bin-smooth-alt"), opt.flag("hcd-model"), opt.flag("hcd-model-alt"),
+            opt.flag("uvfluctuation"), opt.flag("radiation-model"), opt.flag("smooth-gauss"), opt.flag("smooth-lorentz"),
+            opt.flag("dist-matrix"), opt.flag("metal-model"), opt.flag("metal-model-interpolate"), opt.flag("metal-civ"),
+            opt.flag("toy-metal"), opt.flag("combined-bias"), opt.flag("combined-scale"), opt.flag("cross-correlation"),
+            opt.flag("verbose")));
+    } else {
+        model.reset(new BaoCorrelationModel(modelroot, fid, nw, metalName, distAdd, distMul, distR0, zref, OmegaMatter,
+                                            opt.flag("anisotropic"), opt.flag("decoupled"), opt.flag("metal-model"),
+                                            opt.flag("metal-model-interpolate"), opt.flag("metal-civ"), opt.flag("toy-metal"),
+                                            opt.flag("combined-bias"), opt.flag("combined-scale"), opt.flag("cross-correlation")));
+    }
+    for (auto const &script : opt.modelConfig) model->configureFitParameters(script);  // src/baofit.cc:462-464
+    return model;
+}
+
+AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir) {
+    std::string fmt = opt.str("data-format");
+    ComovingCorrelationData::CoordinateSystem cs;
+    if (fmt == "comoving-cartesian") cs = ComovingCorrelationData::CartesianCoordinates;
+    else if (fmt == "comoving-polar") cs = ComovingCorrelationData::PolarCoordinates;
+    else throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar)");
+    BinnedGrid grid = createCorrelationGrid(opt.str("axis1-bins"), opt.str("axis2-bins"), opt.str("axis3-bins"));
+    AbsCorrelationDataPtr data(new ComovingCorrelationData(grid, cs));
+    // src/baofit.cc:510 with the defaults of :216-247
+    double rVetoWidth = opt.num("rveto-width", 0), rVetoCenter = opt.num("rveto-center", 114);
+    data->setFinalCuts(opt.num("rmin", 0), opt.num("rmax", 200), rVetoCenter - 0.5 * rVetoWidth, rVetoCenter + 0.5 * rVetoWidth,
+                       opt.num("mu-min", -1), opt.num("mu-max", 1), opt.num("rperp-min", 0), opt.num("rperp-max", 200),
+                       opt.num("rpar-min", -200), opt.num("rpar-max", 200), (int)opt.num("lmin", 0), (int)opt.num("lmax", 2),
+                       opt.num("z-min", 0), opt.num("z-max", 10));
+    loadCorrelationData(resolve(baseDir, opt.str("data")), *data, opt.flag("load-icov"));
+    data->finalize();
+    return data;
+}
+
+}  // namespace baofit

@@ -1,0 +1,421 @@
+#include "likely_lite.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <sstream>
+
+namespace likely {
+
+namespace {
+std::string trim(std::string const &s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+
+bool globMatch(const char *pat, const char *str) {
+    if (!*pat) return !*str;
+    if (*pat == '*') {
+        for (const char *s = str;; ++s) {
+            if (globMatch(pat + 1, s)) return true;
+            if (!*s) return false;
+        }
+    }
+    return *str && *pat == *str && globMatch(pat + 1, str + 1);
+}
+
+double toDouble(std::string const &s, std::string const &context) {
+    std::string t = trim(s);
+    char *end = nullptr;
+    double v = std::strtod(t.c_str(), &end);
+    if (t.empty() || end == t.c_str() || *end) throw RuntimeError("cannot parse number '" + t + "' in " + context);
+    return v;
+}
+
+void parseRange(std::string const &arg, double &lo, double &hi, std::string const &stmt) {
+    // "@ (lo,hi)" possibly with ";scale" inside the parentheses
+    size_t a = arg.find('('), b = arg.find(')');
+    if (arg.find('@') == std::string::npos || a == std::string::npos || b == std::string::npos || b < a)
+        throw RuntimeError("badly formatted prior range in: " + stmt);
+    std::string in = arg.substr(a + 1, b - a - 1);
+    size_t c = in.find(',');
+    if (c == std::string::npos) throw RuntimeError("badly formatted prior range in: " + stmt);
+    lo = toDouble(in.substr(0, c), stmt);
+    hi = toDouble(in.substr(c + 1), stmt);
+    if (!(lo < hi)) throw RuntimeError("prior range must have lo < hi in: " + stmt);
+}
+}  // namespace
+
+std::vector<double> createBinning(std::string const &specIn) {
+    std::string s = trim(specIn);
+    if (s.size() < 2) throw RuntimeError("createBinning: cannot parse '" + specIn + "'");
+    char open = s[0];
+    size_t close = s.find(open == '[' ? ']' : '}');
+    if ((open != '[' && open != '{') || close == std::string::npos) throw RuntimeError("createBinning: cannot parse '" + specIn + "'");
+    std::string body = s.substr(1, close - 1), tail = trim(s.substr(close + 1));
+    std::vector<double> out;
+    size_t colon = body.find(':');
+    if (colon != std::string::npos) {
+        if (tail.empty() || tail[0] != '*') throw RuntimeError("createBinning: expected *n in '" + specIn + "'");
+        double lo = toDouble(body.substr(0, colon), specIn), hi = toDouble(body.substr(colon + 1), specIn);
+        int n = (int)toDouble(tail.substr(1), specIn);
+        if (n <= 0) throw RuntimeError("createBinning: expected n > 0 in '" + specIn + "'");
+        if (open == '[') {
+            double w = (hi - lo) / n;
+            for (int i = 0; i < n; ++i) out.push_back(lo + (i + 0.5) * w);
+        } else {
+            for (int i = 0; i < n; ++i) out.push_back(n > 1 ? lo + (hi - lo) * i / (n - 1) : lo);
+        }
+        return out;
+    }
+    if (open != '{' || !tail.empty()) throw RuntimeError("createBinning: cannot parse '" + specIn + "'");
+    std::stringstream ss(body);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) out.push_back(toDouble(tok, specIn));
+    if (out.empty()) throw RuntimeError("createBinning: no bins in '" + specIn + "'");
+    return out;
+}
+
+void modifyFitParameters(FitParameters &params, std::string const &script) {
+    std::stringstream ss(script);
+    std::string stmt;
+    while (std::getline(ss, stmt, ';')) {
+        stmt = trim(stmt);
+        if (stmt.empty()) continue;
+        size_t lb = stmt.find('['), rb = stmt.find(']');
+        if (lb == std::string::npos || rb == std::string::npos || rb < lb)
+            throw RuntimeError("badly formatted parameter script: " + stmt);
+        std::string op = trim(stmt.substr(0, lb)), pat = stmt.substr(lb + 1, rb - lb - 1), arg = trim(stmt.substr(rb + 1));
+        bool haveValue = false;
+        double value = 0;
+        std::vector<double> bins;
+        double lo = 0, hi = 0;
+        if (op == "value" || op == "fix" || op == "error" || op == "release") {
+            if (!arg.empty()) {
+                if (arg[0] != '=') throw RuntimeError("expected '=' in: " + stmt);
+                value = toDouble(arg.substr(1), stmt);
+                haveValue = true;
+            }
+            if ((op == "value" || op == "error") && !haveValue) throw RuntimeError("missing value in: " + stmt);
+        } else if (op == "binning") {
+            if (arg.empty() || arg[0] != '=') throw RuntimeError("expected '=' in: " + stmt);
+            bins = createBinning(arg.substr(1));
+        } else if (op == "gaussprior" || op == "boxprior") {
+            parseRange(arg, lo, hi, stmt);
+        } else if (op == "noprior") {
+        } else {
+            throw RuntimeError("unknown parameter script command: " + stmt);
+        }
+        int matched = 0;
+        for (auto &p : params) {
+            if (!globMatch(pat.c_str(), p.name.c_str())) continue;
+            ++matched;
+            if (op == "value") p.value = value;
+            else if (op == "fix") { p.floating = false; if (haveValue) p.value = value; }
+            else if (op == "release") { p.floating = true; if (haveValue) p.value = value; }
+            else if (op == "error") p.error = value;
+            else if (op == "binning") p.binning = bins;
+            else if (op == "gaussprior") { p.priorType = FitParameter::GaussPrior; p.priorMin = lo; p.priorMax = hi; }
+            else if (op == "boxprior") { p.priorType = FitParameter::BoxPrior; p.priorMin = lo; p.priorMax = hi; }
+            else if (op == "noprior") p.priorType = FitParameter::NoPrior;
+        }
+        if (!matched) throw RuntimeError("no parameter matches '" + pat + "' in: " + stmt);
+    }
+}
+
+double evaluatePriors(FitParameters const &params, Parameters const &values) {
+    double sum = 0;
+    for (size_t i = 0; i < params.size(); ++i) {
+        FitParameter const &p = params[i];
+        if (!p.floating || p.priorType == FitParameter::NoPrior) continue;
+        double c = 0.5 * (p.priorMin + p.priorMax), s = 0.5 * (p.priorMax - p.priorMin), x = values[i];
+        if (p.priorType == FitParameter::GaussPrior) {
+            double t = (x - c) / s;
+            sum += 0.5 * t * t;
+        } else {
+            double d = x < p.priorMin ? p.priorMin - x : (x > p.priorMax ? x - p.priorMax : 0.0);
+            if (d > 0) {
+                double t = d / (1e-3 * s);
+                sum += 0.5 * t * t;
+            }
+        }
+    }
+    return sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// damped Newton with finite-difference derivatives, request/consume form
+// ------------------------------------------------------------------------------------------
+namespace {
+// Cholesky solve of (A) x = b for symmetric positive definite A (n x n, row-major). Returns false
+// if A is not positive definite. If inv != nullptr also returns A^-1.
+bool cholSolve(int n, std::vector<double> const &A, std::vector<double> const &b, std::vector<double> &x,
+               std::vector<double> *inv = nullptr) {
+    std::vector<double> L(A);
+    for (int j = 0; j < n; ++j) {
+        double s = L[j * n + j];
+        for (int k = 0; k < j; ++k) s -= L[j * n + k] * L[j * n + k];
+        if (!(s > 0) || !std::isfinite(s)) return false;
+        double d = std::sqrt(s);
+        L[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double t = L[i * n + j];
+            for (int k = 0; k < j; ++k) t -= L[i * n + k] * L[j * n + k];
+            L[i * n + j] = t / d;
+        }
+    }
+    auto solve = [&](std::vector<double> const &rhs, std::vector<double> &out) {
+        out = rhs;
+        for (int i = 0; i < n; ++i) {
+            double t = out[i];
+            for (int k = 0; k < i; ++k) t -= L[i * n + k] * out[k];
+            out[i] = t / L[i * n + i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double t = out[i];
+            for (int k = i + 1; k < n; ++k) t -= L[k * n + i] * out[k];
+            out[i] = t / L[i * n + i];
+        }
+    };
+    solve(b, x);
+    if (inv) {
+        inv->assign((size_t)n * n, 0.0);
+        std::vector<double> e(n), col;
+        for (int j = 0; j < n; ++j) {
+            std::fill(e.begin(), e.end(), 0.0);
+            e[j] = 1.0;
+            solve(e, col);
+            for (int i = 0; i < n; ++i) (*inv)[i * n + j] = col[i];
+        }
+    }
+    return true;
+}
+}  // namespace
+
+NewtonFit::NewtonFit(FitParameters const &params, double errorDef) : _stage(Derivs), _params(params), _up(errorDef) {
+    for (size_t i = 0; i < params.size(); ++i) {
+        _x.push_back(params[i].value);
+        if (params[i].floating) {
+            _fidx.push_back((int)i);
+            double e = params[i].error > 0 ? params[i].error : std::max(1e-3, 0.1 * std::fabs(params[i].value));
+            _h.push_back(0.1 * e);
+        }
+    }
+    _n = (int)_fidx.size();
+    _g.assign(_n, 0.0);
+    _H.assign((size_t)_n * _n, 0.0);
+    _step.assign(_n, 0.0);
+    if (_n == 0) _stage = Hesse;  // nothing to minimise: just evaluate once
+}
+
+Parameters NewtonFit::shifted(std::vector<std::pair<int, double>> const &moves) const {
+    Parameters p(_x);
+    for (auto const &m : moves) p[_fidx[m.first]] += m.second;
+    return p;
+}
+
+void NewtonFit::request(std::vector<Parameters> &out) {
+    _npending = 0;
+    auto push = [&](Parameters const &p) { out.push_back(p); ++_npending; };
+    if (_stage == Derivs) {
+        push(_x);
+        for (int i = 0; i < _n; ++i) { push(shifted({{i, _h[i]}})); push(shifted({{i, -_h[i]}})); }
+        for (int i = 0; i < _n; ++i)
+            for (int j = i + 1; j < _n; ++j) push(shifted({{i, _h[i]}, {j, _h[j]}}));
+    } else if (_stage == LineSearch) {
+        for (double a : _alphas) {
+            Parameters p(_x);
+            for (int i = 0; i < _n; ++i) p[_fidx[i]] += a * _step[i];
+            push(p);
+        }
+    } else if (_stage == Hesse) {
+        push(_x);
+        for (int i = 0; i < _n; ++i) { push(shifted({{i, _h[i]}})); push(shifted({{i, -_h[i]}})); }
+        for (int i = 0; i < _n; ++i)
+            for (int j = i + 1; j < _n; ++j) {
+                push(shifted({{i, _h[i]}, {j, _h[j]}}));
+                push(shifted({{i, _h[i]}, {j, -_h[j]}}));
+                push(shifted({{i, -_h[i]}, {j, _h[j]}}));
+                push(shifted({{i, -_h[i]}, {j, -_h[j]}}));
+            }
+    }
+}
+
+void NewtonFit::solveStep() {
+    // (H + lambda D) step = -g with D = diag(|H_ii|); lambda grows until positive definite
+    std::vector<double> rhs(_n), A, inv;
+    for (int i = 0; i < _n; ++i) rhs[i] = -_g[i];
+    for (int attempt = 0; attempt < 40; ++attempt) {
+        A = _H;
+        for (int i = 0; i < _n; ++i) {
+            double d = std::fabs(_H[i * _n + i]);
+            if (!(d > 0)) d = 1.0 / (_h[i] * _h[i]);
+            A[i * _n + i] += _lambda * d;
+        }
+        if (cholSolve(_n, A, rhs, _step, &inv)) {
+            double edm = 0;
+            for (int i = 0; i < _n; ++i) edm -= 0.5 * _g[i] * _step[i];
+            _edm = edm;
+            return;
+        }
+        _lambda = _lambda > 0 ? _lambda * 10 : 1e-3;
+    }
+    // hopeless Hessian: steepest descent scaled by the probe steps
+    for (int i = 0; i < _n; ++i) _step[i] = -_g[i] * _h[i] * _h[i];
+    _edm = std::numeric_limits<double>::infinity();
+}
+
+void NewtonFit::consume(const double *f) {
+    _neval += _npending;
+    const double inf = std::numeric_limits<double>::infinity();
+    auto val = [&](int k) { return std::isfinite(f[k]) ? f[k] : inf; };
+    if (_stage == Derivs) {
+        int k = 0;
+        double f0 = val(k++);
+        bool bad = !std::isfinite(f0);
+        std::vector<double> fp(_n), fm(_n);
+        for (int i = 0; i < _n; ++i) { fp[i] = val(k++); fm[i] = val(k++); bad |= !std::isfinite(fp[i]) || !std::isfinite(fm[i]); }
+        std::vector<double> fpp((size_t)_n * _n, 0.0);
+        for (int i = 0; i < _n; ++i)
+            for (int j = i + 1; j < _n; ++j) { fpp[i * _n + j] = val(k++); bad |= !std::isfinite(fpp[i * _n + j]); }
+        if (bad) {
+            // a probe left the valid domain (e.g. dilation limits): shrink the probe steps and retry
+            if (!std::isfinite(f0) || ++_stall > 8) { _failed = true; _f0 = f0; _stage = Done; return; }
+            for (auto &h : _h) h *= 0.25;
+            return;
+        }
+        _f0 = f0;
+        _haveF0 = true;
+        for (int i = 0; i < _n; ++i) {
+            _g[i] = (fp[i] - fm[i]) / (2 * _h[i]);
+            _H[i * _n + i] = (fp[i] + fm[i] - 2 * f0) / (_h[i] * _h[i]);
+        }
+        for (int i = 0; i < _n; ++i)
+            for (int j = i + 1; j < _n; ++j) {
+                double hij = (fpp[i * _n + j] - fp[i] - fp[j] + f0) / (_h[i] * _h[j]);
+                _H[i * _n + j] = _H[j * _n + i] = hij;
+            }
+        solveStep();
+        ++_iter;
+        if ((_edm < tolerance && _lambda < 1e-6) || _iter >= maxIterations) {
+            _stage = Hesse;
+            return;
+        }
+        _alphas = {1.0, 0.5, 0.25, 0.1, 0.03, 2.0, 4.0};
+        _stage = LineSearch;
+    } else if (_stage == LineSearch) {
+        int best = -1;
+        double fbest = _f0;
+        for (size_t k = 0; k < _alphas.size(); ++k)
+            if (val((int)k) < fbest) { fbest = val((int)k); best = (int)k; }
+        if (best >= 0) {
+            double a = _alphas[best];
+            for (int i = 0; i < _n; ++i) _x[_fidx[i]] += a * _step[i];
+            double gain = _f0 - fbest;
+            _f0 = fbest;
+            _stall = 0;
+            // full steps that work relax the damping, short ones keep it
+            _lambda = a >= 1.0 ? _lambda * 0.1 : _lambda;
+            if (_lambda < 1e-9) _lambda = 0;
+            // probe steps from the curvature: delta f ~ 1e-3 * errorDef along each axis
+            for (int i = 0; i < _n; ++i) {
+                double hii = _H[i * _n + i];
+                if (hii > 0) {
+                    double h = std::sqrt(2 * 1e-3 * _up / hii);
+                    _h[i] = std::min(std::max(h, 1e-8 * std::max(1.0, std::fabs(_x[_fidx[i]]))), 10 * _h[i]);
+                }
+            }
+            if (gain < 0.1 * tolerance && _edm < 10 * tolerance) { _stage = Hesse; return; }
+            _stage = Derivs;
+        } else {
+            // no trial improved: more damping, same derivatives
+            if (++_stall > 12) { _stage = Hesse; return; }
+            _lambda = _lambda > 0 ? _lambda * 10 : 1e-2;
+            solveStep();
+            _alphas = {1.0, 0.5, 0.25, 0.1, 0.03, 0.01, 0.003};
+        }
+    } else if (_stage == Hesse) {
+        int k = 0;
+        double f0 = val(k++);
+        _f0 = f0;
+        if (_n == 0) { _hesseOk = std::isfinite(f0); _failed = !_hesseOk; _stage = Done; return; }
+        std::vector<double> fp(_n), fm(_n), H((size_t)_n * _n, 0.0), g(_n);
+        bool bad = !std::isfinite(f0);
+        for (int i = 0; i < _n; ++i) {
+            fp[i] = val(k++); fm[i] = val(k++);
+            bad |= !std::isfinite(fp[i]) || !std::isfinite(fm[i]);
+            g[i] = (fp[i] - fm[i]) / (2 * _h[i]);
+            H[i * _n + i] = (fp[i] + fm[i] - 2 * f0) / (_h[i] * _h[i]);
+        }
+        for (int i = 0; i < _n; ++i)
+            for (int j = i + 1; j < _n; ++j) {
+                double a = val(k++), b = val(k++), c = val(k++), d = val(k++);
+                bad |= !std::isfinite(a + b + c + d);
+                H[i * _n + j] = H[j * _n + i] = (a - b - c + d) / (4 * _h[i] * _h[j]);
+            }
+        if (!bad) {
+            std::vector<double> rhs(_n), step;
+            for (int i = 0; i < _n; ++i) rhs[i] = -g[i];
+            _hesseOk = cholSolve(_n, H, rhs, step, &_cov);
+            if (_hesseOk) {
+                double edm = 0;
+                for (int i = 0; i < _n; ++i) edm -= 0.5 * g[i] * step[i];
+                _edm = edm;
+                // one more Newton polish with the accurate derivatives if it is still worth it
+                if (edm > tolerance && _iter < maxIterations + 5) {
+                    _g = g; _H = H; _step = step; _lambda = 0;
+                    _alphas = {1.0, 0.5, 0.25, 0.1};
+                    ++_iter;
+                    _stage = LineSearch;
+                    return;
+                }
+            }
+        }
+        _stage = Done;
+    }
+}
+
+FunctionMinimumPtr NewtonFit::result() const {
+    FunctionMinimumPtr fm(new FunctionMinimum());
+    fm->parameters = _params;
+    for (size_t i = 0; i < _params.size(); ++i) fm->parameters[i].value = _x[i];
+    fm->minValue = _f0;
+    fm->nEvaluations = _neval;
+    fm->nIterations = _iter;
+    fm->edm = _edm;
+    if (_failed || !std::isfinite(_f0)) fm->status = FunctionMinimum::ERROR;
+    else if (_hesseOk && _edm < 100 * tolerance) fm->status = FunctionMinimum::OK;
+    else fm->status = FunctionMinimum::WARNING;
+    if (_hesseOk && _n > 0) {
+        fm->covariance = _cov;
+        for (int i = 0; i < _n; ++i) fm->parameters[_fidx[i]].error = std::sqrt(std::max(0.0, _cov[i * _n + i]));
+    }
+    return fm;
+}
+
+void runLockStep(std::vector<NewtonFit> &fits, BatchFunction const &f) {
+    std::vector<Parameters> points;
+    std::vector<double> values;
+    for (;;) {
+        points.clear();
+        bool any = false;
+        for (auto &fit : fits) {
+            if (fit.done()) continue;
+            fit.request(points);
+            any = true;
+        }
+        if (!any) break;
+        values.assign(points.size(), 0.0);
+        if (!points.empty()) f(points, values);
+        size_t off = 0;
+        for (auto &fit : fits) {
+            if (fit.done()) continue;
+            int n = fit.pending();
+            fit.consume(values.data() + off);
+            off += n;
+        }
+    }
+}
+
+}  // namespace likely

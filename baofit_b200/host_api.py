@@ -1,0 +1,152 @@
+"""ctypes binding of include/baofit_b200_host.h (sessions built from .ini text) -- plumbing."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+_BOUND = False
+BATCH_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)
+
+HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
+                "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
+                "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize"]
+
+
+def lib():
+    global _BOUND
+    L = capi.lib()
+    if not _BOUND:
+        L.bfh_last_error.restype = C.c_char_p
+        L.bfh_session_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.bfh_session_destroy.argtypes = [C.c_void_p]
+        L.bfh_npar.argtypes = [C.c_void_p]
+        L.bfh_ndata.argtypes = [C.c_void_p]
+        L.bfh_param_name.restype = C.c_char_p
+        L.bfh_param_name.argtypes = [C.c_void_p, C.c_int]
+        L.bfh_param_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bfh_kept_indices.argtypes = [C.c_void_p, C.c_void_p]
+        L.bfh_set_distortion_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.bfh_evaluate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.bfh_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.bfh_fit.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                              C.POINTER(C.c_int), C.c_void_p]
+        L.bfh_scan_size.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        L.bfh_parameter_scan.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bfh_toymc.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bfh_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, BATCH_FN, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _BOUND = True
+    return L
+
+
+class HostError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("[%d] %s" % (code, msg))
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        raise HostError(rc, lib().bfh_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def set_device(device):
+    _check(lib().bfh_set_device(device))
+
+
+class Session:
+    """Model + data + CorrelationFitter built from INI text, like src/baofit.cc does."""
+
+    def __init__(self, ini_text, base_dir="", extra_config=""):
+        h = C.c_void_p()
+        _check(lib().bfh_session_create(ini_text.encode(), base_dir.encode(), extra_config.encode(), C.byref(h)))
+        self.h = h
+        self.npar = lib().bfh_npar(h)
+        self.ndata = lib().bfh_ndata(h)
+        self.names = [lib().bfh_param_name(h, i).decode() for i in range(self.npar)]
+        self.values = np.zeros(self.npar)
+        self.errors = np.zeros(self.npar)
+        fl = np.zeros(self.npar, dtype=np.int32)
+        _check(lib().bfh_param_info(h, _p(self.values), _p(self.errors), _p(fl)))
+        self.floating = fl.astype(bool)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bfh_session_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def kept_indices(self):
+        k = np.zeros(self.ndata, dtype=np.int32)
+        _check(lib().bfh_kept_indices(self.h, _p(k)))
+        return k
+
+    def set_distortion_matrix(self, dense):
+        d = np.ascontiguousarray(dense, dtype=np.float64)
+        _check(lib().bfh_set_distortion_matrix(self.h, _p(d), d.shape[0]))
+
+    def evaluate(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, self.npar)
+        f = np.zeros(p.shape[0])
+        _check(lib().bfh_evaluate_batch(self.h, _p(p), p.shape[0], _p(f)))
+        return f
+
+    def predict(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, self.npar)
+        out = np.zeros((self.ndata, p.shape[0]))
+        _check(lib().bfh_predict_batch(self.h, _p(p), p.shape[0], _p(out)))
+        return out
+
+    def fit(self, config=""):
+        v, e = np.zeros(self.npar), np.zeros(self.npar)
+        nf = int(self.floating.sum())
+        cov = np.zeros((self.npar, self.npar))  # large enough for any config
+        fval, status, nev = C.c_double(), C.c_int(), C.c_int()
+        _check(lib().bfh_fit(self.h, config.encode(), _p(v), _p(e), C.byref(fval), C.byref(status), C.byref(nev), _p(cov)))
+        return dict(values=v, errors=e, fval=fval.value, status=status.value, nevaluations=nev.value,
+                    covariance=cov.ravel()[:nf * nf].reshape(nf, nf) if config == "" else None)
+
+    def scan_size(self):
+        n = C.c_long()
+        _check(lib().bfh_scan_size(self.h, C.byref(n)))
+        return n.value
+
+    def parameter_scan(self, first=0, count=-1):
+        total = self.scan_size()
+        n = total - first if count < 0 else count
+        chi2, pts = np.zeros(n), np.zeros((n, self.npar))
+        st, best = np.zeros(n, dtype=np.int32), np.zeros(self.npar + 1)
+        _check(lib().bfh_parameter_scan(self.h, first, count, _p(chi2), _p(pts), _p(st), _p(best)))
+        return dict(chi2=chi2, points=pts, status=st, best_values=best[:-1], best_chi2=best[-1])
+
+    def toymc(self, first, count, seed=1966):
+        fitted, chi2 = np.zeros((count, self.npar)), np.zeros(count)
+        st = np.zeros(count, dtype=np.int32)
+        _check(lib().bfh_toymc(self.h, first, count, seed, _p(fitted), _p(chi2), _p(st)))
+        return dict(fitted=fitted, chi2=chi2, status=st)
+
+
+def minimize(fn, values, errors, floating):
+    """Runs the library's minimiser over a Python batch objective fn(points[B, npar]) -> f[B]."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    errors = np.ascontiguousarray(errors, dtype=np.float64)
+    fl = np.ascontiguousarray(np.asarray(floating).astype(np.int32))
+    npar = len(values)
+
+    def cb(pts, B, f, user):
+        p = np.ctypeslib.as_array(pts, shape=(B, npar))
+        out = np.ctypeslib.as_array(f, shape=(B,))
+        out[:] = fn(p.copy())
+
+    cfn = BATCH_FN(cb)
+    ov, oe = np.zeros(npar), np.zeros(npar)
+    fval, status, nev = C.c_double(), C.c_int(), C.c_int()
+    _check(lib().bfh_minimize(npar, _p(values), _p(errors), _p(fl), cfn, None, _p(ov), _p(oe), C.byref(fval),
+                              C.byref(status), C.byref(nev)))
+    return dict(values=ov, errors=oe, fval=fval.value, status=status.value, nevaluations=nev.value)

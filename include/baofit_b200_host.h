@@ -1,0 +1,70 @@
+/*
+ * baofit_b200_host.h -- C entry points over the host-side C++ mirror of the reference
+ * interfaces (baofit_b200/host/: AbsCorrelationModel, BaoCorrelationModel,
+ * BaoKSpaceCorrelationModel, AbsCorrelationData, CorrelationFitter, CorrelationAnalyzer).
+ *
+ * A "session" is what src/baofit.cc builds from an .ini file: a model configured by its
+ * model-config scripts, a data set loaded, cut and finalized, and a CorrelationFitter over
+ * both. These functions let non-C++ callers (the pytest suite, bench.py) drive it; C++ callers
+ * use the classes directly. All compute goes through the CUDA library (include/baofit_b200.h).
+ */
+#ifndef BAOFIT_B200_HOST_H
+#define BAOFIT_B200_HOST_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bfh_session bfh_session;
+
+const char *bfh_last_error(void);
+/* selects the GPU of this process (one process per GPU); call before the first session */
+int bfh_set_device(int device);
+
+/* Builds model + data + fitter from INI text (same keys as the reference's .ini files,
+ * src/baofit.cc:46-300); relative paths are resolved against base_dir. extra_config is appended
+ * as a last model-config line (may be NULL). Model construction needs no GPU; the data and the
+ * fitter touch the device lazily on the first evaluation. */
+int bfh_session_create(const char *ini_text, const char *base_dir, const char *extra_config, bfh_session **out);
+int bfh_session_destroy(bfh_session *s);
+
+int bfh_npar(const bfh_session *s);
+int bfh_ndata(const bfh_session *s);
+const char *bfh_param_name(const bfh_session *s, int i);
+/* value, error, floating (0/1) of every parameter after the model-config scripts */
+int bfh_param_info(const bfh_session *s, double *values, double *errors, int *floating);
+/* kept global bin indices in iteration order (bit-exact mask check) */
+int bfh_kept_indices(const bfh_session *s, int *indices);
+/* replaces the model's distortion matrix by an in-memory dense one (order x order, row-major)
+ * and forwards the grid coordinates of the data (AbsCorrelationModel::setCoordinates) */
+int bfh_set_distortion_matrix(bfh_session *s, const double *dense, int order);
+
+/* CorrelationFitter::operator() for B vectors: fval[b] = (0.5*icovScale*chi2 + priors)/errScale */
+int bfh_evaluate_batch(bfh_session *s, const double *params, int B, double *fval);
+/* CorrelationFitter::getPrediction for B vectors: pred[i*B + b] */
+int bfh_predict_batch(bfh_session *s, const double *params, int B, double *pred);
+/* CorrelationFitter::fit: best-fit values / errors [npar], fval, status (0 OK, 1 WARNING, 2 ERROR),
+ * covariance of the floating parameters [nfloat*nfloat] (may be NULL) */
+int bfh_fit(bfh_session *s, const char *config, double *values, double *errors, double *fval, int *status,
+            int *nevaluations, double *covariance);
+/* CorrelationAnalyzer::parameterScan over grid points [first, first+count) (count<0: all):
+ * chi2[count] = 2*fval, points[count*npar], status[count]; best[npar+1] = unconstrained best fit
+ * values followed by its 2*fval. Returns the total grid size through *total. */
+int bfh_scan_size(const bfh_session *s, long *total);
+int bfh_parameter_scan(bfh_session *s, long first, long count, double *chi2, double *points, int *status,
+                       double *best);
+/* CorrelationAnalyzer::doToyMCSampling for toys [first, first+count): fitted[count*npar], chi2, status */
+int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
+              int *status);
+
+/* The minimiser on its own (likely::FitModel::findMinimum "mn2::vmetric" replacement) over a
+ * caller-supplied batched objective: fn(points[B*npar], B, f[B], user). Used to run the identical
+ * minimiser code over the CPU oracle in the parity tests, and for host-only tests. */
+typedef void (*bfh_batch_fn)(const double *points, int B, double *f, void *user);
+int bfh_minimize(int npar, const double *values, const double *errors, const int *floating, bfh_batch_fn fn,
+                 void *user, double *out_values, double *out_errors, double *fval, int *status, int *nevaluations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

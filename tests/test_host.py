@@ -1,0 +1,82 @@
+"""Host-side C++ mirror of the reference interfaces, driven from the reference's own .ini recipes.
+No GPU needed: sessions only touch the device when something is evaluated."""
+import os
+
+import numpy as np
+import pytest
+
+from baofit_b200 import host_api as H, workloads as W
+
+
+def ini(golden_tree, name):
+    return open(os.path.join(golden_tree, "config", name)).read(), os.path.join(golden_tree, "config")
+
+
+def test_qso_rspace_session_matches_reference_layout(built, golden_tree):
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF.ini")
+    s = H.Session(text, base)
+    m, d = W.qso_rspace()
+    assert s.names == m.names and s.npar == 31
+    assert np.array_equal(s.values, m.values) and np.array_equal(s.floating, m.floating)
+    assert s.ndata == 440 and np.array_equal(s.kept_indices(), d.keep.desc.n_data and np.asarray(
+        [d.keep.desc.index[i] for i in range(440)], dtype=np.int32))
+    assert s.scan_size() == 60 * 35
+    # floating set of config/BOSSDR11QSOLyaF.ini: beta, delta-v, bias2, both alphas, 15 broadband terms
+    assert s.floating.sum() == 20
+
+
+def test_qso_kspace_session_layout(built, golden_tree):
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF_k.ini")
+    s = H.Session(text, base)
+    m, _ = W.qso_kspace(with_dist_matrix=False, with_metals=False)
+    assert s.names == m.names and s.npar == 29 and s.floating.sum() == 20
+    assert np.array_equal(s.values, m.values)
+    assert s.names[11:13] == ["BAO alpha-parallel", "BAO alpha-perp"]
+
+
+def test_demo_rmu_session(built, golden_tree):
+    text, base = ini(golden_tree, "rmu_to_bao.ini")
+    s = H.Session(text, base)
+    assert s.ndata == 800 and [n for n, f in zip(s.names, s.floating) if f] == ["beta", "BAO alpha-parallel", "BAO alpha-perp"]
+
+
+def test_model_errors_mirror_reference_messages(built, golden_tree):
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF.ini")
+    with pytest.raises(H.HostError) as e:
+        H.Session(text.replace("fiducial = DR9LyaMocksNLeffPk", "fiducial = nosuchmodel"), base)
+    assert e.value.code == -2 and "BaoCorrelationModel: error while reading model interpolation data." in str(e.value)
+    with pytest.raises(H.HostError) as e:
+        H.Session(text.replace("dist-add = rP,rT=0:2,-3:1", "dist-add = rP,rT=0:2,x"), base)
+    assert e.value.code == -2 and "BroadbandModel: badly formatted parameter specification" in str(e.value)
+    with pytest.raises(H.HostError) as e:
+        H.Session(text.replace("data = ../data/BOSSDR11QSOLyaF", "data = ../data/missing"), base)
+    assert e.value.code == -3 and "loadCorrelationData: Unable to open" in str(e.value)
+    with pytest.raises(H.HostError) as e:
+        H.Session(text, base, extra_config="fix[no such parameter]=1")
+    assert e.value.code == -2
+
+
+def test_parameter_script_language(built, golden_tree):
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF.ini")
+    s = H.Session(text, base, extra_config="fix[dist*]=0; value[beta]=1.3; error[bias2]=0.5; release[gamma-bias]")
+    assert s.floating.sum() == 20 - 15 + 1
+    assert s.values[s.names.index("beta")] == 1.3 and s.errors[s.names.index("bias2")] == 0.5
+
+
+def test_minimiser_on_quadratic_and_rosenbrock(built):
+    A = np.array([[4.0, 1.0, 0.5], [1.0, 3.0, 0.2], [0.5, 0.2, 2.0]])
+    x0 = np.array([1.0, -2.0, 0.5])
+
+    def quad(p):
+        d = p[:, :3] - x0
+        return 0.5 * np.einsum("bi,ij,bj->b", d, A, d) + 7.0
+
+    r = H.minimize(quad, [0, 0, 0, 9.0], [1, 1, 1, 1], [1, 1, 1, 0])
+    assert r["status"] == 0 and np.allclose(r["values"][:3], x0, atol=1e-6) and r["values"][3] == 9.0
+    assert np.allclose(r["errors"][:3], np.sqrt(np.diag(np.linalg.inv(A))), rtol=1e-4)
+
+    def rosen(p):
+        return 100 * (p[:, 1] - p[:, 0] ** 2) ** 2 + (1 - p[:, 0]) ** 2
+
+    r = H.minimize(rosen, [-1.2, 1.0], [0.1, 0.1], [1, 1])
+    assert r["fval"] < 1e-5 and np.allclose(r["values"], [1, 1], atol=5e-3)
