@@ -538,3 +538,29 @@ def dr11_auto_kspace(root=None, golden=GOLDEN, seed=1966):
     r, mu, z = grid_coordinates(a1, a2, a3, "comoving-cartesian")
     keep = final_cuts(r, mu, z, np.ones(len(r), dtype=bool), rmin=40, rmax=180)
     return m, (r, mu, z, keep)
+
+
+def make_golden_tree(root):
+    """Lays out tests/golden like the reference checkout (config/ data/ demo/ models/) under
+    `root`, expanding the gzip-compressed covariance, so that the .ini recipes run unmodified."""
+    import shutil
+    os.makedirs(root, exist_ok=True)
+    for sub in ("models", "demo"):
+        dst = os.path.join(root, sub)
+        if not os.path.exists(dst):
+            os.symlink(os.path.join(GOLDEN, sub), dst)
+    if not os.path.exists(os.path.join(root, "config")):
+        shutil.copytree(os.path.join(GOLDEN, "config"), os.path.join(root, "config"))
+    os.makedirs(os.path.join(root, "data"), exist_ok=True)
+    for f in os.listdir(os.path.join(GOLDEN, "data")):
+        src = os.path.join(GOLDEN, "data", f)
+        if f.endswith(".gz"):
+            dst = os.path.join(root, "data", f[:-3])
+            if not os.path.exists(dst):
+                with gzip.open(src, "rb") as g, open(dst, "wb") as o:
+                    shutil.copyfileobj(g, o)
+        else:
+            dst = os.path.join(root, "data", f)
+            if not os.path.exists(dst):
+                os.symlink(src, dst)
+    return root

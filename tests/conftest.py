@@ -31,19 +31,5 @@ def ctx(built):
 def golden_tree(tmp_path_factory):
     """A directory laid out like the reference checkout (config/ data/ demo/ models/) with the
     gzip-compressed covariance expanded, so that the .ini recipes run unmodified."""
-    import gzip
-    import shutil
     from baofit_b200 import workloads as W
-    root = tmp_path_factory.mktemp("golden")
-    for sub in ("models", "demo"):
-        os.symlink(os.path.join(W.GOLDEN, sub), os.path.join(root, sub))
-    shutil.copytree(os.path.join(W.GOLDEN, "config"), os.path.join(root, "config"))
-    os.makedirs(os.path.join(root, "data"))
-    for f in os.listdir(os.path.join(W.GOLDEN, "data")):
-        src = os.path.join(W.GOLDEN, "data", f)
-        if f.endswith(".gz"):
-            with gzip.open(src, "rb") as g, open(os.path.join(root, "data", f[:-3]), "wb") as o:
-                shutil.copyfileobj(g, o)
-        else:
-            os.symlink(src, os.path.join(root, "data", f))
-    return str(root)
+    return W.make_golden_tree(str(tmp_path_factory.mktemp("golden")))
