@@ -308,7 +308,7 @@ def main_ours(args, rank, world, local_rank):
                 "traffic": None, "peak_source": hbm_src, "share_of_step": kernels[top]["share"],
                 "note": "arithmetic intensity is far above machine balance: this kernel is FP64-ALU bound, see DESIGN.md"}
     # whole-step contraction throughput against the FP64 tensor roofline (north_star target)
-    contraction_flops = sum(fl.values()) * B
+    contraction_flops = sum(v for k, v in fl.items() if k in prof) * B
     contraction_ms = sum(prof[k][0] / prof[k][1] for k in fl if k in prof)
     roof["contraction_tflops"] = contraction_flops / (contraction_ms * 1e-3) * 1e-12 if contraction_ms else None
     roof["contraction_frac"] = roof["contraction_tflops"] / fp64 if contraction_ms else None
