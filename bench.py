@@ -195,6 +195,8 @@ def main_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION would print a banner there)
+        os.environ["NCCL_DEBUG"] = os.environ.get("BAOFIT_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
