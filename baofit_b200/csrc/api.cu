@@ -361,6 +361,9 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
                         il[((size_t)iy * nx + ix) * nt + t] = d->metal_cross[((size_t)t * ny + iy) * nx + ix];
             if ((rc = upload(m->allocs, il.data(), il.size(), &p))) return fail(rc);
             dm.metal_cross = p;
+            m->metal_cross_h.assign(d->metal_cross, d->metal_cross + (size_t)nt * nx * ny);
+            m->metal_dx = d->metal_dx;
+            m->metal_dy = d->metal_dy;
             dm.metal_nx = nx; dm.metal_ny = ny; dm.metal_x0 = d->metal_x0; dm.metal_y0 = d->metal_y0;
             dm.metal_inv_dx = 1.0 / d->metal_dx; dm.metal_inv_dy = 1.0 / d->metal_dy;
             dm.metal_xmax = d->metal_x0 + (nx - 1) * d->metal_dx;
@@ -540,6 +543,66 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
             std::memcpy(&dk[(size_t)i * ng_pad], &m->dist_matrix[(size_t)d->h_index[i] * ng], sizeof(double) * ng);
         if ((rc = upload(p.allocs, dk.data(), dk.size(), &p.d_Dkept))) return rc;
     }
+    // bin-static tables of the cartesian-form kernels
+    auto build_tab = [&](const std::vector<double> &r, const std::vector<double> &mu, const std::vector<double> &z,
+                         int npts, int npts_pad, const int *slots, int nslots, bool want_mx,
+                         bf_data::Plan::PointTabDev &t) -> int {
+        std::vector<double> rpar(npts_pad, 0.0), rperp(npts_pad, 0.0);
+        for (int i = 0; i < npts; ++i) {
+            rpar[i] = r[i] * mu[i];
+            rperp[i] = r[i] * std::sqrt(1 - mu[i] * mu[i]);
+        }
+        int rc2;
+        if ((rc2 = upload(p.allocs, rpar.data(), rpar.size(), &t.rpar0))) return rc2;
+        if ((rc2 = upload(p.allocs, rperp.data(), rperp.size(), &t.rperp0))) return rc2;
+        for (int q = 0; q < nslots; ++q) {
+            int s = slots[q];
+            const DevBB &b = dm.bb[s];
+            if (!b.enabled) continue;
+            int n_rt = (b.rt_max - b.rt_min) / b.rt_step + 1, n_z = (b.z_max - b.z_min) / b.z_step + 1;
+            std::vector<double> rt((size_t)npts * n_rt), zp((size_t)npts * n_z);
+            for (int i = 0; i < npts; ++i) {
+                // BroadbandModel.cc:201-213: rrT = r*sqrt(1-mu^2)/r0, zz = (1+z)/(1+z0), "x-1 if exponent > 0"
+                double rrT = r[i] * std::sqrt(1 - mu[i] * mu[i]) * b.inv_r0, zz = (1 + z[i]) / (1 + b.z0);
+                int k = 0;
+                for (int ti = b.rt_min; ti <= b.rt_max; ti += b.rt_step) rt[(size_t)i * n_rt + k++] = std::pow(ti > 0 ? rrT - 1 : rrT, ti);
+                k = 0;
+                for (int zi = b.z_min; zi <= b.z_max; zi += b.z_step) zp[(size_t)i * n_z + k++] = std::pow(zz, zi);
+            }
+            t.n_rt[s] = n_rt;
+            t.n_z[s] = n_z;
+            if ((rc2 = upload(p.allocs, rt.data(), rt.size(), &t.bb_rt[s]))) return rc2;
+            if ((rc2 = upload(p.allocs, zp.data(), zp.size(), &t.bb_z[s]))) return rc2;
+        }
+        if (want_mx && dm.metal_kind == BF_METAL_CROSS_BICUBIC) {
+            // collapse the bicubic patch along r_perp, which the velocity shift leaves unchanged
+            const int nt = dm.metal_ncomb * 3, nx = dm.metal_nx, ny = dm.metal_ny;
+            std::vector<double> mx((size_t)npts * ny * nt);
+            auto wrap = [](int i, int n) { i %= n; return i < 0 ? i + n : i; };
+            for (int i = 0; i < npts; ++i) {
+                double x = std::min(std::max(rperp[i], dm.metal_x0), dm.metal_xmax);
+                double fx = (x - dm.metal_x0) * dm.metal_inv_dx, flx = std::floor(fx), tt = fx - flx;
+                int ix = (int)flx;
+                double t2 = tt * tt, t3 = t2 * tt;
+                double wx[4] = {0.5 * (-tt + 2.0 * t2 - t3), 0.5 * (2.0 - 5.0 * t2 + 3.0 * t3), 0.5 * (tt + 4.0 * t2 - 3.0 * t3),
+                                0.5 * (-t2 + t3)};
+                for (int row = 0; row < ny; ++row)
+                    for (int tpl = 0; tpl < nt; ++tpl) {
+                        const double *g = &m->metal_cross_h[((size_t)tpl * ny + row) * nx];
+                        double v = 0;
+                        for (int jx = 0; jx < 4; ++jx) v += wx[jx] * g[wrap(ix - 1 + jx, nx)];
+                        mx[((size_t)i * ny + row) * nt + tpl] = v;
+                    }
+            }
+            if ((rc2 = upload(p.allocs, mx.data(), mx.size(), &t.mx))) return rc2;
+        }
+        return BF_OK;
+    };
+    {
+        const int post_slots[2] = {BF_BB_DIST_ADD, BF_BB_DIST_MUL}, pre_slots[2] = {BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL};
+        if ((rc = build_tab(d->h_r, d->h_mu, d->h_z, n, n_pad, post_slots, 2, !use_dm, p.tab_data))) return rc;
+        if (use_dm && (rc = build_tab(d->h_grid_r, d->h_grid_mu, d->h_grid_z, ng, ng_pad, pre_slots, 2, true, p.tab_grid))) return rc;
+    }
     auto ins = d->plans.emplace(m, std::move(p));
     *out = &ins.first->second;
     return BF_OK;
@@ -715,6 +778,22 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     const bool use_dm = dm.dm_order > 0;
     const bool to_user = what == OUT_PRED;  // final rows go straight to the caller's buffer
 
+    auto fill_tab = [&](const bf_data::Plan::PointTabDev &t, bool grid, PointTab &pt) {
+        pt.npts = grid ? d->n_grid : d->n;
+        pt.npts_pad = grid ? d->n_grid_pad : d->n_pad;
+        pt.rpar0 = t.rpar0; pt.rperp0 = t.rperp0;
+        pt.z = grid ? d->d_grid_z : d->d_z;
+        pt.zc = grid ? plan->d_zc_grid : plan->d_zc_data;
+        pt.gidx = grid ? nullptr : d->d_index;
+        pt.zc_metal = grid ? plan->d_zc_metal_grid : plan->d_zc_metal_data;
+        pt.zc_stride = grid ? d->n_grid_pad : d->n_pad;
+        for (int q = 0; q < 4; ++q) { pt.bb_rt[q] = t.bb_rt[q]; pt.bb_z[q] = t.bb_z[q]; pt.n_rt[q] = t.n_rt[q]; pt.n_z[q] = t.n_z[q]; }
+        pt.mx = t.mx; pt.mx_ny = dm.metal_ny; pt.mx_nt = dm.metal_ncomb * 3;
+    };
+    FastArgs fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.m = dm; fa.pT = w.pT; fa.S = w.S; fa.vfac = plan->d_vfac; fa.tabs = w.tabs; fa.ldb = ldb; fa.B = B;
+    fa.nz = plan->nz; fa.zc_trigger = plan->zc_trigger; fa.status = w.status;
     bool finished = false;
     if (use_dm) {
         // undistorted xi on the full grid
@@ -724,8 +803,13 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.mode = 1;
         a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
         if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
-        if (shared_tables) BF_KERNEL(ctx, "kspace_eval_shared_kernel[grid]", launch_kspace_eval_shared(s, a, ctx->sm_count));
-        else BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
+        if (shared_tables) {
+            fill_tab(plan->tab_grid, true, fa.pt);
+            fa.mode = 1; fa.out = a.out; fa.ldo = a.ldo;
+            if (what == OUT_XIU) fa.pt.npts_pad = fa.pt.npts;
+            BF_KERNEL(ctx, "kspace_fast_eval_kernel[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count));
+        } else
+            BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
         if (what == OUT_XIU) finished = true;
         if (!finished) {
             GemmArgs g{};
@@ -739,7 +823,9 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
             a.in = w.Y; a.out = w.Z; a.ldo = ldb;
             a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
-            BF_KERNEL(ctx, "dist_post_kernel", launch_dist_post(s, a, ctx->sm_count));
+            fill_tab(plan->tab_data, false, fa.pt);
+            fa.mode = 0; fa.in = w.Y; fa.out = w.Z; fa.ldo = ldb; fa.dsub = a.dsub; fa.dov = a.dov;
+            BF_KERNEL(ctx, "fast_post_kernel", launch_fast_post(s, fa, ctx->sm_count));
             if (to_user)
                 BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
                                              (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
@@ -753,7 +839,12 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
         a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
         if (dm.kind == BF_MODEL_RSPACE) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
-        else if (shared_tables) BF_KERNEL(ctx, "kspace_eval_shared_kernel[data]", launch_kspace_eval_shared(s, a, ctx->sm_count));
+        else if (shared_tables) {
+            fill_tab(plan->tab_data, false, fa.pt);
+            fa.pt.npts_pad = a.npts_pad;
+            fa.mode = 0; fa.out = a.out; fa.ldo = a.ldo; fa.dsub = a.dsub; fa.dov = a.dov;
+            BF_KERNEL(ctx, "kspace_fast_eval_kernel[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count));
+        }
         else BF_KERNEL(ctx, "kspace_eval_kernel[data]", launch_kspace_eval(s, a, ctx->sm_count));
     }
     if (what == OUT_CHI2 && !finished) {

@@ -112,6 +112,8 @@ struct bf_model {
     // host copies needed at plan time
     std::vector<double> metal_zgrid;  // [ncomb][ngrid]
     std::vector<double> dist_matrix;  // [order][order]
+    std::vector<double> metal_cross_h;  // [ncomb*3][ny][nx] as given (for the plan tables)
+    double metal_dx = 0, metal_dy = 0;
     double zref = 0;
 };
 
@@ -139,6 +141,13 @@ struct bf_data {
         int *d_zc_metal_grid = nullptr;  // [ncomb][n_grid_pad]
         int zc_trigger = 0;          // class of the z that triggers the k-space transform
         double *d_Dkept = nullptr;   // [n_pad][n_grid_pad] rows of the distortion matrix of kept bins
+        // bin-static tables of the cartesian-form kernels (kernels_fast.cu)
+        struct PointTabDev {
+            double *rpar0 = nullptr, *rperp0 = nullptr;
+            double *bb_rt[4] = {nullptr, nullptr, nullptr, nullptr}, *bb_z[4] = {nullptr, nullptr, nullptr, nullptr};
+            int n_rt[4] = {0, 0, 0, 0}, n_z[4] = {0, 0, 0, 0};
+            double *mx = nullptr;
+        } tab_data, tab_grid;
         std::vector<void *> allocs;
     };
     std::map<const bf_model *, Plan> plans;

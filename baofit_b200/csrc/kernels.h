@@ -32,6 +32,35 @@ struct EvalArgs {
     int *status;
 };
 
+// Bin-static tables of one point set (data bins or grid bins), built once per (model, data) plan.
+struct PointTab {
+    int npts, npts_pad;
+    const double *rpar0, *rperp0, *z;  // [npts_pad] r*mu, r*sqrt(1-mu^2), redshift
+    const int *zc;                     // redshift class
+    const int *gidx;                   // global grid index (null: the point index itself)
+    const int *zc_metal;               // [ncomb][zc_stride]
+    int zc_stride;
+    // r_T- and z-axis factors of the broadband polynomials, [npts][n_rt] / [npts][n_z] per slot
+    const double *bb_rt[4], *bb_z[4];
+    int n_rt[4], n_z[4];
+    // cross metal templates collapsed along r_perp: mx[(i*mx_ny + row)*mx_nt + t]
+    const double *mx;
+    int mx_ny, mx_nt;
+};
+
+struct FastArgs {
+    DevModel m;
+    PointTab pt;
+    const double *pT, *S, *vfac;
+    const double2 *tabs;
+    int ldb, B, nz, zc_trigger, mode, pts_per_block;
+    const double *in;
+    double *out;
+    int ldo;
+    const double *dsub, *dov;
+    int *status;
+};
+
 struct ProjArgs {
     DevModel m;
     const double *pT, *S;
@@ -70,6 +99,8 @@ void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a);  // a.G: [6][nk_p
 void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs);
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count);
+void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count);
+void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count);
 
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);

@@ -1,0 +1,441 @@
+// Hot kernels of the shared-transform path, written in "cartesian" form.
+//
+// Everything that depends only on the bin is tabulated once per (model, data) plan on the host
+// (PointTab): r_par, r_perp, the r_T- and z-axis factors of every broadband polynomial, and the
+// metal templates already collapsed along r_perp. What is left per (vector b, bin) is what really
+// depends on b: the velocity shift is an addition on r_par (r_perp is invariant under it), the
+// anisotropic dilation needs one rsqrt, two spline look-ups in the shared-memory basis tables,
+// a 4-row x 12-template metal patch, and the r_P powers of the broadband polynomial.
+// Lanes = consecutive b (coalesced bin-major stores); bin quantities are warp-uniform loads.
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace bf {
+
+namespace {
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                 "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar), ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// per-vector state, loaded once (kept small: it lives in registers across the bin loop)
+struct FastVec {
+    double biasSq, ampl, dv, apar, aperp, iso, c1, c2;
+};
+
+__device__ __forceinline__ void load_fast_vec(const DevModel &m, const double *__restrict__ pT, int ldb, double ebeta_trigger,
+                                              FastVec &v) {
+    const Internal in = load_internal(m, pT, ldb);
+    v.biasSq = in.biasSq;
+    v.ampl = pT[(size_t)m.idx_bao * ldb];
+    v.iso = pT[(size_t)(m.idx_bao + 1) * ldb];
+    v.apar = pT[(size_t)(m.idx_bao + 2) * ldb];
+    v.aperp = (m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * v.apar
+                                                 : pT[(size_t)(m.idx_bao + 3) * ldb];
+    v.dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    double betaz = in.beta * ebeta_trigger;
+    if (m.flags & BF_FLAG_CROSS_CORRELATION) {
+        double beta2z = in.beta2 * ebeta_trigger;
+        v.c1 = betaz + beta2z;
+        v.c2 = betaz * beta2z;
+    } else {
+        v.c1 = 2.0 * betaz;
+        v.c2 = betaz * betaz;
+    }
+}
+
+// normalisation factors of the cross metal templates for redshift-evolution factors (eb, ebeta)
+__device__ __forceinline__ void cross_metal_norms(const DevModel &m, const double *__restrict__ pT, int ldb, int c,
+                                                  double eb, double ebeta, double &n0, double &n2, double &n4) {
+    const Internal in = load_internal(m, pT, ldb);
+    double ba, bia, bb, bib;
+    metal_pair(m, in, true, pT, ldb, m.metal_p1[c], ba, bia);
+    metal_pair(m, in, true, pT, ldb, m.metal_p2[c], bb, bib);
+    norm_factors(bia * bib * eb, 0.5 * (ba + bb) * ebeta, ba * bb * ebeta * ebeta, n0, n2, n4);
+}
+
+// sum_l L_l(mu) sum_n coef_n X_{l,n}(r) from the shared-memory basis tables; musq = mu^2
+__device__ __forceinline__ double basis_correlation(const DevModel &m, const double2 *__restrict__ tab, double r, double musq,
+                                                    double c1, double c2) {
+    const int nr = m.nr;
+    const double rlast = m.tr_r0 + (nr - 1) * m.tr_dr;
+    double w0, w1, w2, w3;
+    int j;
+    if (r <= m.tr_r0) { j = 0; w0 = 1.0; w1 = w2 = w3 = 0.0; }
+    else if (r >= rlast) { j = nr - 2; w1 = 1.0; w0 = w2 = w3 = 0.0; }
+    else {
+        j = (int)((r - m.tr_r0) * m.tr_inv_dr);
+        j = max(0, min(j, nr - 2));
+        double xl = m.tr_r0 + j * m.tr_dr;
+        if (r < xl && j > 0) { --j; xl = m.tr_r0 + j * m.tr_dr; }
+        else if (r >= xl + m.tr_dr && j < nr - 2) { ++j; xl = m.tr_r0 + j * m.tr_dr; }
+        const double dx = m.tr_dr, t = r - xl, u = t * m.tr_inv_dr, t3 = t * t * t * m.tr_inv_dr * (1.0 / 3.0);
+        // gsl cspline evaluation rearranged as weights of (y_lo, y_hi, c_lo, c_hi)
+        w0 = 1.0 - u;
+        w1 = u;
+        w2 = t * t - (2.0 / 3.0) * t * dx - t3;
+        w3 = t3 - (1.0 / 3.0) * t * dx;
+    }
+    const double L2 = (-1.0 + 3.0 * musq) * 0.5, L4 = (3.0 + musq * (-30.0 + 35.0 * musq)) * 0.125;
+    const double g[9] = {1.0, c1, c2, L2, L2 * c1, L2 * c2, L4, L4 * c1, L4 * c2};
+    const double2 *lo = tab + (size_t)j * 9, *hi = lo + 9;
+    double ylo = 0.0, yhi = 0.0, clo = 0.0, chi = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        double2 a = lo[q], b = hi[q];
+        ylo = fma(g[q], a.x, ylo);
+        clo = fma(g[q], a.y, clo);
+        yhi = fma(g[q], b.x, yhi);
+        chi = fma(g[q], b.y, chi);
+    }
+    return w0 * ylo + w1 * yhi + w2 * clo + w3 * chi;
+}
+
+// Broadband polynomial with the bin-static r_T and z factors read from the plan tables.
+// rrP = r_par/r0 of this (b, bin); rr and mu are only touched if their axes are non-trivial.
+__device__ __forceinline__ double broadband_fast(const DevBB &s, const double *__restrict__ pT, int ldb,
+                                                 const double *__restrict__ rt_pow, int n_rt,
+                                                 const double *__restrict__ z_pow, double rr, double mu, double rrP) {
+    const bool r_axis = !(s.r_min == 0 && s.r_max == 0), p_axis = !(s.rp_min == 0 && s.rp_max == 0);
+    AxisBase br, bp;
+    if (r_axis && s.r_denom == 1) br.init(rr, s.r_min, s.r_step);
+    if (p_axis) bp.init(rrP, s.rp_min, s.rp_step);
+    double xi = 0.0;
+    const double *pc = pT + (size_t)s.idx_base * ldb;  // walks the coefficients, rT fastest
+    int kz = 0;
+#pragma unroll 1
+    for (int zi = s.z_min; zi <= s.z_max; zi += s.z_step, ++kz) {
+        const double zF = z_pow[kz];
+#pragma unroll 1
+        for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step) {
+            const double zmF = mi == 0 ? zF : zF * legendre_p(mi, mu);
+            AxisIter ir(br);
+#pragma unroll 1
+            for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step) {
+                double rF = 1.0;
+                if (r_axis) rF = s.r_denom == 1 ? ir.next(br, ri) : pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom);
+                AxisIter ip(bp);
+                double accP = 0.0;
+#pragma unroll 1
+                for (int pi = s.rp_min; pi <= s.rp_max; pi += s.rp_step) {
+                    const double rPF = p_axis ? ip.next(bp, pi) : 1.0;
+                    double acc = 0.0;
+#pragma unroll 5
+                    for (int kt = 0; kt < n_rt; ++kt) {
+                        acc = fma(__ldg(pc), rt_pow[kt], acc);
+                        pc += ldb;
+                    }
+                    accP = fma(acc, rPF, accP);
+                }
+                xi = fma(accP, rF * zmF, xi);
+            }
+        }
+    }
+    return xi;
+}
+
+__device__ __forceinline__ double broadband_pair(const DevModel &m, const PointTab &pt, int slot_add, int slot_mul, int i,
+                                                 const double *__restrict__ pT, int ldb, double eb, double xi, double rprime,
+                                                 double muprime, double rpar) {
+    if (m.bb[slot_mul].enabled) {
+        const DevBB &s = m.bb[slot_mul];
+        xi *= 1.0 + broadband_fast(s, pT, ldb, pt.bb_rt[slot_mul] + (size_t)i * pt.n_rt[slot_mul], pt.n_rt[slot_mul],
+                                   pt.bb_z[slot_mul] + (size_t)i * pt.n_z[slot_mul], rprime * s.inv_r0, muprime, rpar * s.inv_r0);
+    }
+    if (m.bb[slot_add].enabled) {
+        const DevBB &s = m.bb[slot_add];
+        xi += eb * broadband_fast(s, pT, ldb, pt.bb_rt[slot_add] + (size_t)i * pt.n_rt[slot_add], pt.n_rt[slot_add],
+                                  pt.bb_z[slot_add] + (size_t)i * pt.n_z[slot_add], rprime * s.inv_r0, muprime, rpar * s.inv_r0);
+    }
+    return xi;
+}
+
+// Cross metals from the x-collapsed templates MX[i][row][t]: 4 rows x NT templates, then the
+// normalisation factors n[t] of this vector. Returns sum_t n[t] * T_t(r_perp, r_par).
+template <int NT>
+__device__ __forceinline__ double metal_rows_apply(const double *__restrict__ mx_point, int ny, int iy, const double (&wy)[4],
+                                                   const double (&n)[kMaxCrossTemplates]) {
+    double acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+#pragma unroll
+    for (int jy = 0; jy < 4; ++jy) {
+        const double *row = mx_point + (size_t)wrap_index(iy - 1 + jy, ny) * NT;
+        if (NT % 2 == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; t += 2) {
+                const double2 v = __ldg(reinterpret_cast<const double2 *>(row + t));
+                acc[t] = fma(wy[jy], v.x, acc[t]);
+                acc[t + 1] = fma(wy[jy], v.y, acc[t + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t] = fma(wy[jy], __ldg(row + t), acc[t]);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) s = fma(n[t], acc[t], s);
+    return s;
+}
+
+}  // namespace
+
+// mode 0: data bins without distortion matrix (full model incl. post broadband, residual)
+// mode 1: grid bins for the distortion matrix (undistorted xi_u, range zeroing, pre-matrix broadband)
+// kLean: no radiation term, metals none or bicubic cross templates (the BASELINE configurations);
+// the full variant also carries the toy / auto-table metals and the radiation model.
+template <bool kLean>
+__global__ void __launch_bounds__(256, 2) kspace_fast_eval_kernel(FastArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tab = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ __align__(8) unsigned long long bar;
+    const DevModel &m = a.m;
+    const PointTab &pt = a.pt;
+    const unsigned tab_bytes = 2u * m.nr * 9u * (unsigned)sizeof(double2);
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, tab_bytes);
+        const unsigned chunk = 32768;
+        for (unsigned off = 0; off < tab_bytes; off += chunk)
+            tma_bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char *>(a.tabs) + off, min(chunk, tab_bytes - off), &bar);
+    }
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = b < a.B;
+    if (!active) b = a.B - 1;  // keep the whole CTA alive for the barrier; results are not stored
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    FastVec v;
+    load_fast_vec(m, pT, ldb, S[(size_t)(a.zc_trigger * 3 + 1) * ldb], v);
+    const bool aniso = m.flags & BF_FLAG_ANISOTROPIC, decoupled = m.flags & BF_FLAG_DECOUPLED;
+    const bool cross_metal = m.metal_kind == BF_METAL_CROSS_BICUBIC;
+    const double dmin2 = m.dilmin * m.dilmin, dmax2 = m.dilmax * m.dilmax;
+    // with a single redshift class the evolution factors and metal norms are per-vector constants
+    double eb1 = 1.0, es1 = 1.0, dpi1 = 0.0;
+    double mn[kMaxCrossTemplates];
+#pragma unroll
+    for (int t = 0; t < kMaxCrossTemplates; ++t) mn[t] = 0.0;
+    if (a.nz == 1) {
+        eb1 = S[0];
+        es1 = S[(size_t)2 * ldb];
+        dpi1 = v.dv * a.vfac[0];
+        double ebeta = S[(size_t)ldb];
+#pragma unroll
+        for (int c = 0; c < kMaxCombos; ++c)
+            if (cross_metal && c < m.metal_ncomb) cross_metal_norms(m, pT, ldb, c, eb1, ebeta, mn[3 * c], mn[3 * c + 1], mn[3 * c + 2]);
+    }
+    mbar_wait(&bar, 0);
+    const double2 *tab_pk = tab, *tab_nw = tab + (size_t)m.nr * 9;
+    int st_bits = 0;
+    const int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, pt.npts_pad);
+    for (int i = i0; i < i1; ++i) {
+        double val = 0.0;
+        if (i < pt.npts) {
+            double eb = eb1, es = es1, dpi = dpi1;
+            if (a.nz != 1) {
+                int zc = pt.zc[i];
+                eb = S[(size_t)(zc * 3 + 0) * ldb];
+                es = S[(size_t)(zc * 3 + 2) * ldb];
+                dpi = v.dv * a.vfac[zc];
+            }
+            const double rperp = pt.rperp0[i];
+            const double rpar = pt.rpar0[i] + dpi;  // the velocity shift only moves r_parallel
+            const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
+            const double rs = rsqrt(r2);
+            const double rprime = r2 * rs, muprime = rpar * rs, mu2 = muprime * muprime;
+            double rBAO, muBAO2, rBAO2;
+            if (aniso) {
+                const double apar = v.apar * es, aperp = v.aperp * es;
+                const double ap2 = apar * apar * rp2;
+                rBAO2 = ap2 + aperp * aperp * rt2;
+                const double rsb = rsqrt(rBAO2);
+                rBAO = rBAO2 * rsb;
+                muBAO2 = ap2 * rsb * rsb;
+            } else {
+                const double sc = v.iso * es;
+                rBAO = rprime * sc;
+                rBAO2 = rBAO * rBAO;
+                muBAO2 = mu2;
+            }
+            bool zero = false;
+            if (a.mode == 1) {
+                zero = (rprime < m.rlo || rprime > m.rhi) || (rBAO < m.rlo || rBAO > m.rhi);
+            } else {
+                if (rBAO2 < dmin2 * r2) st_bits |= BF_STATUS_DILATION_MIN;
+                else if (rBAO2 > dmax2 * r2) st_bits |= BF_STATUS_DILATION_MAX;
+            }
+            if (!zero) {
+                const double peak = basis_correlation(m, tab_pk, rBAO, muBAO2, v.c1, v.c2);
+                const double smooth = decoupled ? basis_correlation(m, tab_nw, rprime, mu2, v.c1, v.c2)
+                                                : basis_correlation(m, tab_nw, rBAO, muBAO2, v.c1, v.c2);
+                double xi = v.biasSq * eb * (v.ampl * peak + smooth);
+                if (cross_metal) {
+                    // r_perp (hence the x stencil) is bin-static and already folded into pt.mx
+                    double y = fmin(fmax(rpar, m.metal_y0), m.metal_ymax);
+                    double fy = (y - m.metal_y0) * m.metal_inv_dy, fly = floor(fy);
+                    double wy[4];
+                    catmull_weights(fy - fly, wy);
+                    const double *mxp = pt.mx + (size_t)i * pt.mx_ny * pt.mx_nt;
+                    if (a.nz != 1) {
+                        // several redshift classes: the normalisation factors depend on the bin
+#pragma unroll
+                        for (int c = 0; c < kMaxCombos; ++c)
+                            if (c < m.metal_ncomb) {
+                                int zcm = pt.zc_metal[c * pt.zc_stride + i];
+                                cross_metal_norms(m, pT, ldb, c, S[(size_t)(zcm * 3 + 0) * ldb], S[(size_t)(zcm * 3 + 1) * ldb],
+                                                  mn[3 * c], mn[3 * c + 1], mn[3 * c + 2]);
+                            }
+                    }
+                    if (pt.mx_nt == 12) xi += metal_rows_apply<12>(mxp, pt.mx_ny, (int)fly, wy, mn);
+                    else xi += metal_rows_apply<15>(mxp, pt.mx_ny, (int)fly, wy, mn);
+                } else if (!kLean && m.metal_kind != BF_METAL_NONE) {
+                    const Internal in = load_internal(m, pT, ldb);
+                    MetalVec mv;
+                    metal_load(m, in, pT, ldb, mv);
+                    xi += metal_eval(m, in, mv, pT, ldb, S, pt.zc_metal, pt.zc_stride, i, pt.gidx ? pt.gidx[i] : i, rprime, muprime);
+                }
+                if (!kLean && (m.flags & BF_FLAG_RADIATION_MODEL) && rprime > 0.0) {  // BaoKSpaceCorrelationModel.cc:441-455
+                    const double rad0 = pT[(size_t)m.idx_rad * ldb], rad1 = pT[(size_t)(m.idx_rad + 1) * ldb];
+                    const double rad2 = pT[(size_t)(m.idx_rad + 2) * ldb], rad3 = pT[(size_t)(m.idx_rad + 3) * ldb];
+                    double rd = rad0 / r2;
+                    if (rad1 > 0.0) rd *= (1.0 - rad1 * (1.0 - mu2));
+                    if (rad2 > 0.0) rd *= exp(-rprime / rad2);
+                    if (rad3 > 0.0) rd *= exp(-(rprime * (1.0 - muprime) / (1.0 + pt.z[i])) / rad3);
+                    xi += rd;
+                }
+                if (a.mode == 1) xi = broadband_pair(m, pt, BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL, i, pT, ldb, eb, xi, rprime, muprime, rpar);
+                else xi = broadband_pair(m, pt, BF_BB_DIST_ADD, BF_BB_DIST_MUL, i, pT, ldb, eb, xi, rprime, muprime, rpar);
+                val = xi;
+            }
+            if (a.mode == 0) {
+                if (st_bits) val = nan("");
+                if (a.dov) val -= a.dov[(size_t)b * pt.npts + i];
+                else if (a.dsub) val -= a.dsub[i];
+            }
+        }
+        if (active) a.out[(size_t)i * a.ldo + b] = val;
+    }
+    if (active && st_bits) atomicOr(a.status + b, st_bits);
+}
+
+// Distortion-matrix tail on the data bins: Z = Y (1 + dist mul) + dist add * evol - d and the
+// dilation-limit check of the data bin itself (BaoKSpaceCorrelationModel.cc:420-427, :529-535).
+__global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
+    const DevModel &m = a.m;
+    const PointTab &pt = a.pt;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const double iso = pT[(size_t)(m.idx_bao + 1) * ldb];
+    const double apar0 = pT[(size_t)(m.idx_bao + 2) * ldb];
+    const double aperp0 = (m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * apar0
+                                                             : pT[(size_t)(m.idx_bao + 3) * ldb];
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    const bool aniso = m.flags & BF_FLAG_ANISOTROPIC;
+    const double dmin2 = m.dilmin * m.dilmin, dmax2 = m.dilmax * m.dilmax;
+    const bool need_r = [&] {
+        bool n = false;
+        for (int s = 0; s < 2; ++s) {
+            const DevBB &q = m.bb[s];
+            if (q.enabled) n |= !(q.r_min == 0 && q.r_max == 0) || !(q.mu_min == 0 && q.mu_max == 0);
+        }
+        return n;
+    }();
+    int st_bits = 0;
+    const int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, pt.npts_pad);
+    for (int i = i0; i < i1; ++i) {
+        double val = 0.0;
+        if (i < pt.npts) {
+            int zc = a.nz == 1 ? 0 : pt.zc[i];
+            const double eb = S[(size_t)(zc * 3 + 0) * ldb], es = S[(size_t)(zc * 3 + 2) * ldb];
+            const double rperp = pt.rperp0[i], rpar = pt.rpar0[i] + dv * a.vfac[zc];
+            const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
+            double scale2;  // (r_BAO / r)^2
+            if (aniso) {
+                const double apar = apar0 * es, aperp = aperp0 * es;
+                scale2 = apar * apar * rp2 + aperp * aperp * rt2;
+            } else {
+                const double sc = iso * es;
+                scale2 = sc * sc * r2;
+            }
+            if (scale2 < dmin2 * r2) st_bits |= BF_STATUS_DILATION_MIN;
+            else if (scale2 > dmax2 * r2) st_bits |= BF_STATUS_DILATION_MAX;
+            double rprime = 0.0, muprime = 0.0;
+            if (need_r) {
+                const double rs = rsqrt(r2);
+                rprime = r2 * rs;
+                muprime = rpar * rs;
+            }
+            double xi = a.in[(size_t)i * a.ldo + b];
+            xi = broadband_pair(m, pt, BF_BB_DIST_ADD, BF_BB_DIST_MUL, i, pT, ldb, eb, xi, rprime, muprime, rpar);
+            val = st_bits ? nan("") : xi;
+            if (a.dov) val -= a.dov[(size_t)b * pt.npts + i];
+            else if (a.dsub) val -= a.dsub[i];
+        }
+        a.out[(size_t)i * a.ldo + b] = val;
+    }
+    if (st_bits) atomicOr(a.status + b, st_bits);
+}
+
+static void pick_grid(FastArgs &a, int sm_count, dim3 &grid) {
+    int bx = (a.B + 255) / 256;
+    int want = sm_count * 6;
+    int by = max(1, min(a.pt.npts_pad, (want + bx - 1) / bx));
+    a.pts_per_block = (a.pt.npts_pad + by - 1) / by;
+    grid = dim3(bx, (a.pt.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
+}
+
+void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count) {
+    size_t smem = (size_t)2 * a.m.nr * 9 * sizeof(double2);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(kspace_fast_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kspace_fast_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid;
+    pick_grid(a, sm_count, grid);
+    const bool lean = !(a.m.flags & BF_FLAG_RADIATION_MODEL) &&
+                      (a.m.metal_kind == BF_METAL_NONE || a.m.metal_kind == BF_METAL_CROSS_BICUBIC);
+    if (lean) kspace_fast_eval_kernel<true><<<grid, 256, smem, s>>>(a);
+    else kspace_fast_eval_kernel<false><<<grid, 256, smem, s>>>(a);
+}
+
+void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count) {
+    dim3 grid;
+    pick_grid(a, sm_count, grid);
+    fast_post_kernel<<<grid, 256, 0, s>>>(a);
+}
+
+}  // namespace bf

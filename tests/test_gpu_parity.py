@@ -148,7 +148,7 @@ def test_kspace_shared_and_per_vector_paths_agree(ctx):
     gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
     ctx.set_profiling(True)
     shared, _ = capi.chi2_batch(ctx, gm, gd, params[1:])
-    assert any(k.startswith("kspace_eval_shared_kernel") for k in ctx.get_profile())
+    assert any(k.startswith("kspace_fast_eval_kernel") for k in ctx.get_profile())
     mixed = params.copy()
     mixed[0, m.index("SigmaNL-perp")] *= 1.1
     ctx.set_profiling(True)
