@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "host_setup.h"
 #include "kernels.h"
@@ -471,6 +472,8 @@ extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out)
         for (int i = 0; i < n; ++i) std::memcpy(&p[(size_t)i * n_pad], &src[(size_t)i * n], sizeof(double) * n);
         return upload(o->allocs, p.data(), p.size(), dev);
     };
+    o->h_W = W;
+    o->h_data.assign(d->data, d->data + n);
     if ((rc = pad_square(W, &o->d_W))) return fail(rc);
     if (!L.empty() && (rc = pad_square(L, &o->d_L))) return fail(rc);
     *out = o;
@@ -603,6 +606,104 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
         if ((rc = build_tab(d->h_r, d->h_mu, d->h_z, n, n_pad, post_slots, 2, !use_dm, p.tab_data))) return rc;
         if (use_dm && (rc = build_tab(d->h_grid_r, d->h_grid_mu, d->h_grid_z, ng, ng_pad, pre_slots, 2, true, p.tab_grid))) return rc;
     }
+    // ---- fused tail of the distortion-matrix path ----
+    if (use_dm) {
+        const DevBB &ba = dm.bb[BF_BB_DIST_ADD];
+        bool single_class = true;
+        for (int i = 1; i < n; ++i) single_class &= zc_data[i] == zc_data[0];
+        const bool shift = dm.idx_delta_v >= 0;
+        int fcase = -1;
+        if (!dm.bb[BF_BB_DIST_MUL].enabled && single_class) {
+            if (!ba.enabled) fcase = 0;
+            else if (!shift) fcase = 1;
+            else if (ba.r_min == 0 && ba.r_max == 0 && ba.mu_min == 0 && ba.mu_max == 0 && ba.rp_min >= 0 && ba.rp_max <= 8) fcase = 2;
+        }
+        if (fcase >= 0) {
+            auto cnt = [](int lo, int hi, int st) { return (hi - lo) / st + 1; };
+            // (the coefficient rows must fit the 64 spare rows below the xi_u panel; checked below)
+            int n_rt = ba.enabled ? cnt(ba.rt_min, ba.rt_max, ba.rt_step) : 0, n_z = ba.enabled ? cnt(ba.z_min, ba.z_max, ba.z_step) : 0;
+            int nb = 0;
+            if (fcase == 1)
+                nb = n_z * cnt(ba.mu_min, ba.mu_max, ba.mu_step) * cnt(ba.r_min, ba.r_max, ba.r_step) * cnt(ba.rp_min, ba.rp_max, ba.rp_step) * n_rt;
+            else if (fcase == 2) nb = n_z * (ba.rp_max + 1) * n_rt;
+            const int kext = round_up(nb + 1, kGemmBK), ktot = ng_pad + kext;
+            if (kext <= 64) {
+            auto legendre = [](int ell, double mu) {
+                double m2 = mu * mu;
+                switch (ell) {
+                case 0: return 1.0;
+                case 1: return mu;
+                case 2: return (-1 + 3 * m2) / 2.;
+                case 3: return mu * (-3 + 5 * m2) / 2.;
+                case 4: return (3 + m2 * (-30 + 35 * m2)) / 8.;
+                case 5: return mu * (15 + m2 * (-70 + 63 * m2)) / 8.;
+                case 6: return (-5 + m2 * (105 + m2 * (-315 + 231 * m2))) / 16.;
+                case 7: return mu * (-35 + m2 * (315 + m2 * (-693 + 429 * m2))) / 16.;
+                default: return (35 + m2 * (-1260 + m2 * (6930 + m2 * (-12012 + 6435 * m2)))) / 128.;
+                }
+            };
+            std::vector<double> aext((size_t)n_pad * ktot, 0.0);
+            for (int i = 0; i < n; ++i) {
+                double *row = &aext[(size_t)i * ktot];
+                std::memcpy(row, &m->dist_matrix[(size_t)d->h_index[i] * ng], sizeof(double) * ng);
+                double *bs = row + ng_pad;
+                if (ba.enabled) {
+                    const double r = d->h_r[i], mu = d->h_mu[i], z = d->h_z[i];
+                    const double rr = r * ba.inv_r0, rrP = r * mu * ba.inv_r0, rrT = r * std::sqrt(1 - mu * mu) * ba.inv_r0;
+                    const double zz = (1 + z) / (1 + ba.z0);
+                    int k = 0;
+                    if (fcase == 1) {  // BroadbandModel.cc:204-213, one basis value per coefficient
+                        for (int zi = ba.z_min; zi <= ba.z_max; zi += ba.z_step)
+                            for (int mi = ba.mu_min; mi <= ba.mu_max; mi += ba.mu_step)
+                                for (int ri = ba.r_min; ri <= ba.r_max; ri += ba.r_step)
+                                    for (int pi = ba.rp_min; pi <= ba.rp_max; pi += ba.rp_step)
+                                        for (int ti = ba.rt_min; ti <= ba.rt_max; ti += ba.rt_step)
+                                            bs[k++] = std::pow(zz, zi) * legendre(mi, mu) *
+                                                      std::pow(ri > 0 ? rr - 1 : rr, (double)ri / ba.r_denom) *
+                                                      std::pow(pi > 0 ? rrP - 1 : rrP, pi) * std::pow(ti > 0 ? rrT - 1 : rrT, ti);
+                    } else {
+                        const double u = rrP - 1;
+                        for (int zi = ba.z_min; zi <= ba.z_max; zi += ba.z_step)
+                            for (int mm = 0; mm <= ba.rp_max; ++mm)
+                                for (int ti = ba.rt_min; ti <= ba.rt_max; ti += ba.rt_step)
+                                    bs[k++] = std::pow(zz, zi) * std::pow(u, mm) * std::pow(ti > 0 ? rrT - 1 : rrT, ti);
+                    }
+                }
+                bs[nb] = -d->h_data[i];
+            }
+            // WA = W . A_ext (W lower triangular), accumulated in long double
+            std::vector<double> wa((size_t)n_pad * ktot, 0.0);
+            {
+                unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < nt; ++t)
+                    pool.emplace_back([&, t] {
+                        std::vector<long double> acc(ktot);
+                        for (int i = (int)t; i < n; i += (int)nt) {
+                            std::fill(acc.begin(), acc.end(), 0.0L);
+                            for (int j = 0; j <= i; ++j) {
+                                const long double wij = d->h_W[(size_t)i * n + j];
+                                if (wij == 0) continue;
+                                const double *arow = &aext[(size_t)j * ktot];
+                                for (int k = 0; k < ktot; ++k) acc[k] += wij * arow[k];
+                            }
+                            for (int k = 0; k < ktot; ++k) wa[(size_t)i * ktot + k] = (double)acc[k];
+                        }
+                    });
+                for (auto &th : pool) th.join();
+            }
+            if ((rc = upload(p.allocs, aext.data(), aext.size(), &p.d_Aext))) return rc;
+            if ((rc = upload(p.allocs, wa.data(), wa.size(), &p.d_WA))) return rc;
+            p.fold_ok = true;
+            p.fold_case = fcase;
+            p.fold_nb = nb;
+            p.fold_kext = kext;
+            p.fold_pmax = ba.enabled ? ba.rp_max : 0;
+            p.fold_nrt = n_rt;
+            p.fold_nz = n_z;
+            }
+        }
+    }
     auto ins = d->plans.emplace(m, std::move(p));
     *out = &ins.first->second;
     return BF_OK;
@@ -629,7 +730,7 @@ size_t ws_fixed_doubles(const DevModel &dm) {
 size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
     size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + d->n_pad /*Z*/;
     if (dm.kind == BF_MODEL_KSPACE) c += (size_t)6 * dm.nk_pad + (size_t)12 * dm.nr_pad;
-    if (dm.dm_order > 0) c += (size_t)d->n_grid_pad + d->n_pad;
+    if (dm.dm_order > 0) c += (size_t)d->n_grid_pad + 64 + d->n_pad;  // xi_u panel (+ fused-tail rows) and Y
     return c;
 }
 
@@ -661,7 +762,7 @@ void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Wo
         w.C2 = take((size_t)6 * dm.nr_pad);
     }
     if (dm.dm_order > 0) {
-        w.XiU = take(d->n_grid_pad);
+        w.XiU = take((size_t)d->n_grid_pad + 64);
         w.Y = take(d->n_pad);
     }
 }
@@ -807,10 +908,44 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             fill_tab(plan->tab_grid, true, fa.pt);
             fa.mode = 1; fa.out = a.out; fa.ldo = a.ldo;
             if (what == OUT_XIU) fa.pt.npts_pad = fa.pt.npts;
-            BF_KERNEL(ctx, "kspace_fast_eval_kernel[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count));
+            if (fast_eval_is_lean(fa)) {
+                BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
+                if (fast_eval_has_extras(fa))
+                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<extras>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 2));
+            } else
+                BF_KERNEL(ctx, "kspace_fast_eval_kernel<all>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 0));
         } else
             BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
         if (what == OUT_XIU) finished = true;
+        if (!finished && plan->fold_ok && !d_override) {
+            // fused tail: the post-matrix broadband and "- d" are extra K rows of the panel, and for
+            // chi2 the whitening W is folded into the left matrix: one GEMM, squares in the epilogue
+            FoldArgs fo;
+            std::memset(&fo, 0, sizeof(fo));
+            fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
+            fo.zc_data = plan->zc_trigger;  // single class of the data bins (= class of the first kept bin)
+            fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
+            fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz;
+            fo.minus_d_row_value = what == OUT_CHI2 ? 1 : 0;
+            fo.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
+            fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
+            BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
+            GemmArgs g{};
+            g.Bm = w.XiU;
+            g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad + plan->fold_kext;
+            g.lda = g.K; g.ldb = ldb;
+            if (what == OUT_CHI2) {
+                g.A = plan->d_WA; g.C = nullptr; g.ldc = 0;
+                g.chi2 = d_out; g.status = w.status;
+                BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g));
+            } else {
+                g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
+                BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));
+                BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
+                                             (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
+            }
+            finished = true;
+        }
         if (!finished) {
             GemmArgs g{};
             g.A = plan->d_Dkept; g.Bm = w.XiU; g.C = w.Y;
@@ -843,7 +978,12 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             fill_tab(plan->tab_data, false, fa.pt);
             fa.pt.npts_pad = a.npts_pad;
             fa.mode = 0; fa.out = a.out; fa.ldo = a.ldo; fa.dsub = a.dsub; fa.dov = a.dov;
-            BF_KERNEL(ctx, "kspace_fast_eval_kernel[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count));
+            if (fast_eval_is_lean(fa)) {
+                BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
+                if (fast_eval_has_extras(fa))
+                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<extras>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 2));
+            } else
+                BF_KERNEL(ctx, "kspace_fast_eval_kernel<all>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 0));
         }
         else BF_KERNEL(ctx, "kspace_eval_kernel[data]", launch_kspace_eval(s, a, ctx->sm_count));
     }

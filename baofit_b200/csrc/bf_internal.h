@@ -129,6 +129,8 @@ struct bf_data {
     double *d_data = nullptr;  // [n_pad]
     double *d_W = nullptr;     // [n_pad][n_pad] lower triangular, W^T W = C^-1
     double *d_L = nullptr;     // [n_pad][n_pad] lower Cholesky factor of C (toy noise); may be null
+    std::vector<double> h_W;   // host copy [n][n] (folded into the fused tail matrices at plan time)
+    std::vector<double> h_data;
     // plans: per model, the z-class table and the gathered distortion matrix rows
     struct Plan {
         int nz = 0;
@@ -148,6 +150,14 @@ struct bf_data {
             int n_rt[4] = {0, 0, 0, 0}, n_z[4] = {0, 0, 0, 0};
             double *mx = nullptr;
         } tab_data, tab_grid;
+        // Fused tail of the distortion-matrix path: chi2 = || WA . [xi_u ; coef(b) ; 1] ||^2 with
+        // WA = W . [D_kept | broadband basis | -d]  (see DESIGN.md "fused tail")
+        bool fold_ok = false;
+        int fold_case = 0;            // 0: no post broadband, 1: static basis (no velocity shift), 2: binomial in dpi
+        int fold_nb = 0, fold_kext = 0;  // number of basis columns; extra K rows (multiple of 16)
+        int fold_pmax = 0, fold_nrt = 0, fold_nz = 0;
+        double *d_Aext = nullptr;     // [n_pad][n_grid_pad + fold_kext]
+        double *d_WA = nullptr;       // [n_pad][n_grid_pad + fold_kext]
         std::vector<void *> allocs;
     };
     std::map<const bf_model *, Plan> plans;

@@ -61,6 +61,20 @@ struct FastArgs {
     int *status;
 };
 
+// Coefficient rows of the fused tail + dilation-limit check of the data bins.
+struct FoldArgs {
+    DevModel m;
+    const double *pT, *S, *vfac;
+    int ldb, B, zc_data;         // single redshift class of the data bins
+    int fold_case, nb, kext, pmax, nrt, nz;
+    int minus_d_row_value;       // 1: chi2 mode (row multiplies the -d column), 0: prediction mode
+    double *rows;                // [kext][ldb] appended below the xi_u panel
+    // data bins for the dilation check
+    int npts;
+    const double *rpar0, *rperp0;
+    int *status;
+};
+
 struct ProjArgs {
     DevModel m;
     const double *pT, *S;
@@ -99,8 +113,11 @@ void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a);  // a.G: [6][nk_p
 void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs);
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count);
-void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count);
+void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part);  // part 0 all, 1 cosmology, 2 extras
+bool fast_eval_is_lean(const FastArgs &a);
+bool fast_eval_has_extras(const FastArgs &a);
 void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count);
+void launch_fold_coef(cudaStream_t s, const FoldArgs &a);
 
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);

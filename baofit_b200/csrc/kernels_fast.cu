@@ -212,17 +212,21 @@ __device__ __forceinline__ double metal_rows_apply(const double *__restrict__ mx
 // mode 1: grid bins for the distortion matrix (undistorted xi_u, range zeroing, pre-matrix broadband)
 // kLean: no radiation term, metals none or bicubic cross templates (the BASELINE configurations);
 // the full variant also carries the toy / auto-table metals and the radiation model.
-template <bool kLean>
-__global__ void __launch_bounds__(256, 2) kspace_fast_eval_kernel(FastArgs a) {
+// kPart: 0 = everything in one pass; 1 = cosmological part only (peak + smooth, status);
+// 2 = the rest (metals, radiation, broadband, residual) added to what part 1 stored. Splitting
+// halves the live registers of each kernel, which is what bounds the occupancy of this
+// latency-bound code.
+template <bool kLean, int kPart>
+__global__ void __launch_bounds__(256, kPart == 1 ? 3 : 2) kspace_fast_eval_kernel(FastArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
     __shared__ __align__(8) unsigned long long bar;
     const DevModel &m = a.m;
     const PointTab &pt = a.pt;
     const unsigned tab_bytes = 2u * m.nr * 9u * (unsigned)sizeof(double2);
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (kPart != 2 && threadIdx.x == 0) mbar_init(&bar, 1);
+    if (kPart != 2) __syncthreads();
+    if (kPart != 2 && threadIdx.x == 0) {
         mbar_expect_tx(&bar, tab_bytes);
         const unsigned chunk = 32768;
         for (unsigned off = 0; off < tab_bytes; off += chunk)
@@ -249,16 +253,33 @@ __global__ void __launch_bounds__(256, 2) kspace_fast_eval_kernel(FastArgs a) {
         es1 = S[(size_t)2 * ldb];
         dpi1 = v.dv * a.vfac[0];
         double ebeta = S[(size_t)ldb];
+        if (kPart != 1) {
 #pragma unroll
-        for (int c = 0; c < kMaxCombos; ++c)
-            if (cross_metal && c < m.metal_ncomb) cross_metal_norms(m, pT, ldb, c, eb1, ebeta, mn[3 * c], mn[3 * c + 1], mn[3 * c + 2]);
+            for (int c = 0; c < kMaxCombos; ++c)
+                if (cross_metal && c < m.metal_ncomb) cross_metal_norms(m, pT, ldb, c, eb1, ebeta, mn[3 * c], mn[3 * c + 1], mn[3 * c + 2]);
+        }
     }
-    mbar_wait(&bar, 0);
+    if (kPart != 2) mbar_wait(&bar, 0);
     const double2 *tab_pk = tab, *tab_nw = tab + (size_t)m.nr * 9;
     int st_bits = 0;
     const int i0 = blockIdx.y * a.pts_per_block, i1 = min(i0 + a.pts_per_block, pt.npts_pad);
+    // software pipelining of the bin-static loads: the coordinates of bin i+1 are fetched, and the
+    // metal rows it will need are prefetched into L1, while bin i is being computed
+    double nx_rperp = pt.rperp0[i0], nx_rpar0 = pt.rpar0[i0];
     for (int i = i0; i < i1; ++i) {
         double val = 0.0;
+        const double rperp = nx_rperp, rpar0 = nx_rpar0;
+        if (i + 1 < i1) {
+            nx_rperp = pt.rperp0[i + 1];
+            nx_rpar0 = pt.rpar0[i + 1];
+            if (kPart != 1 && cross_metal && a.nz == 1 && i + 1 < pt.npts) {
+                double y = fmin(fmax(nx_rpar0 + dpi1, m.metal_y0), m.metal_ymax);
+                int iy = (int)floor((y - m.metal_y0) * m.metal_inv_dy);
+                const double *row = pt.mx + ((size_t)(i + 1) * pt.mx_ny + max(iy - 1, 0)) * pt.mx_nt;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + q * 16));
+            }
+        }
         if (i < pt.npts) {
             double eb = eb1, es = es1, dpi = dpi1;
             if (a.nz != 1) {
@@ -267,8 +288,7 @@ __global__ void __launch_bounds__(256, 2) kspace_fast_eval_kernel(FastArgs a) {
                 es = S[(size_t)(zc * 3 + 2) * ldb];
                 dpi = v.dv * a.vfac[zc];
             }
-            const double rperp = pt.rperp0[i];
-            const double rpar = pt.rpar0[i] + dpi;  // the velocity shift only moves r_parallel
+            const double rpar = rpar0 + dpi;  // the velocity shift only moves r_parallel
             const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
             const double rs = rsqrt(r2);
             const double rprime = r2 * rs, muprime = rpar * rs, mu2 = muprime * muprime;
@@ -294,10 +314,18 @@ __global__ void __launch_bounds__(256, 2) kspace_fast_eval_kernel(FastArgs a) {
                 else if (rBAO2 > dmax2 * r2) st_bits |= BF_STATUS_DILATION_MAX;
             }
             if (!zero) {
-                const double peak = basis_correlation(m, tab_pk, rBAO, muBAO2, v.c1, v.c2);
-                const double smooth = decoupled ? basis_correlation(m, tab_nw, rprime, mu2, v.c1, v.c2)
-                                                : basis_correlation(m, tab_nw, rBAO, muBAO2, v.c1, v.c2);
-                double xi = v.biasSq * eb * (v.ampl * peak + smooth);
+                double xi;
+                if (kPart != 2) {
+                    const double peak = basis_correlation(m, tab_pk, rBAO, muBAO2, v.c1, v.c2);
+                    const double smooth = decoupled ? basis_correlation(m, tab_nw, rprime, mu2, v.c1, v.c2)
+                                                    : basis_correlation(m, tab_nw, rBAO, muBAO2, v.c1, v.c2);
+                    xi = v.biasSq * eb * (v.ampl * peak + smooth);
+                } else {
+                    xi = a.out[(size_t)i * a.ldo + b];
+                }
+                if (kPart == 1) {
+                    val = xi;
+                } else {
                 if (cross_metal) {
                     // r_perp (hence the x stencil) is bin-static and already folded into pt.mx
                     double y = fmin(fmax(rpar, m.metal_y0), m.metal_ymax);
@@ -335,16 +363,18 @@ __global__ void __launch_bounds__(256, 2) kspace_fast_eval_kernel(FastArgs a) {
                 if (a.mode == 1) xi = broadband_pair(m, pt, BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL, i, pT, ldb, eb, xi, rprime, muprime, rpar);
                 else xi = broadband_pair(m, pt, BF_BB_DIST_ADD, BF_BB_DIST_MUL, i, pT, ldb, eb, xi, rprime, muprime, rpar);
                 val = xi;
+                }
             }
-            if (a.mode == 0) {
+            if (a.mode == 0 && kPart != 1) {
                 if (st_bits) val = nan("");
                 if (a.dov) val -= a.dov[(size_t)b * pt.npts + i];
                 else if (a.dsub) val -= a.dsub[i];
             }
+            if (a.mode == 0 && kPart == 1 && st_bits) val = nan("");
         }
         if (active) a.out[(size_t)i * a.ldo + b] = val;
     }
-    if (active && st_bits) atomicOr(a.status + b, st_bits);
+    if (kPart != 2 && active && st_bits) atomicOr(a.status + b, st_bits);
 }
 
 // Distortion-matrix tail on the data bins: Z = Y (1 + dist mul) + dist add * evol - d and the
@@ -408,6 +438,72 @@ __global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
     if (st_bits) atomicOr(a.status + b, st_bits);
 }
 
+// Fused tail: per-vector coefficient rows appended below the xi_u panel, so that the post-matrix
+// additive broadband and the "- d" become extra K columns of the distortion GEMM. Also performs
+// the dilation-limit check of every data bin (BaoKSpaceCorrelationModel.cc:420-427).
+//   case 1 (no velocity shift): row k = eb * c_k                      (basis fully bin-static)
+//   case 2 (velocity shift):    rP factors are (u_i + v_b)^p with v_b = dpi_b / r0, expanded
+//           binomially: row (z, m, t) = eb * sum_{p >= m} C(p,m) c_{z,p,t} v_b^(p-m)
+__global__ void __launch_bounds__(128) fold_coef_kernel(FoldArgs a) {
+    const DevModel &m = a.m;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const double eb = S[(size_t)(a.zc_data * 3 + 0) * ldb], es = S[(size_t)(a.zc_data * 3 + 2) * ldb];
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    const double dpi = dv * a.vfac[a.zc_data];
+    double *rows = a.rows + b;
+    const DevBB &s = m.bb[BF_BB_DIST_ADD];
+    if (a.fold_case == 1) {
+        for (int k = 0; k < a.nb; ++k) rows[(size_t)k * ldb] = eb * pT[(size_t)(s.idx_base + k) * ldb];
+    } else if (a.fold_case == 2) {
+        const double v = dpi * s.inv_r0;
+        const int n_rp = (s.rp_max - s.rp_min) / s.rp_step + 1;
+        for (int zi = 0; zi < a.nz; ++zi)
+            for (int mm = 0; mm <= a.pmax; ++mm)
+                for (int t = 0; t < a.nrt; ++t) {
+                    double acc = 0.0;
+                    for (int ip = 0; ip < n_rp; ++ip) {
+                        int p = s.rp_min + ip * s.rp_step;
+                        if (p < mm) continue;
+                        // C(p, mm) v^(p-mm); exponent 0 terms use x, positive ones x-1: p = 0 only feeds mm = 0
+                        double binom = 1.0;
+                        for (int q = 0; q < mm; ++q) binom = binom * (p - q) / (q + 1);
+                        acc += binom * ipow(v, p - mm) * pT[(size_t)(s.idx_base + (zi * n_rp + ip) * a.nrt + t) * ldb];
+                    }
+                    rows[(size_t)((zi * (a.pmax + 1) + mm) * a.nrt + t) * ldb] = eb * acc;
+                }
+    }
+    rows[(size_t)a.nb * ldb] = a.minus_d_row_value ? 1.0 : 0.0;
+    for (int k = a.nb + 1; k < a.kext; ++k) rows[(size_t)k * ldb] = 0.0;
+    // dilation limits: scalez^2 = apar^2 mu^2 + aperp^2 (1 - mu^2) lies between the two squares, so
+    // bins only need checking when one of the two scales is outside the limits
+    const bool aniso = m.flags & BF_FLAG_ANISOTROPIC;
+    const double iso = pT[(size_t)(m.idx_bao + 1) * ldb] * es;
+    const double apar = pT[(size_t)(m.idx_bao + 2) * ldb] * es;
+    const double aperp = ((m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * pT[(size_t)(m.idx_bao + 2) * ldb]
+                                                              : pT[(size_t)(m.idx_bao + 3) * ldb]) * es;
+    int st = 0;
+    if (!aniso) {
+        if (iso < m.dilmin) st = BF_STATUS_DILATION_MIN;
+        else if (iso > m.dilmax) st = BF_STATUS_DILATION_MAX;
+    } else if (fmin(apar, aperp) < m.dilmin || fmax(apar, aperp) > m.dilmax) {
+        const double dmin2 = m.dilmin * m.dilmin, dmax2 = m.dilmax * m.dilmax;
+        for (int i = 0; i < a.npts; ++i) {
+            const double rpar = a.rpar0[i] + dpi, rperp = a.rperp0[i];
+            const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
+            const double sc2 = apar * apar * rp2 + aperp * aperp * rt2;
+            if (sc2 < dmin2 * r2) st |= BF_STATUS_DILATION_MIN;
+            else if (sc2 > dmax2 * r2) st |= BF_STATUS_DILATION_MAX;
+        }
+    }
+    if (st) atomicOr(a.status + b, st);
+}
+
+void launch_fold_coef(cudaStream_t s, const FoldArgs &a) { fold_coef_kernel<<<(a.B + 127) / 128, 128, 0, s>>>(a); }
+
 static void pick_grid(FastArgs &a, int sm_count, dim3 &grid) {
     int bx = (a.B + 255) / 256;
     int want = sm_count * 6;
@@ -416,20 +512,19 @@ static void pick_grid(FastArgs &a, int sm_count, dim3 &grid) {
     grid = dim3(bx, (a.pt.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
 }
 
-void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count) {
+void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part) {
     size_t smem = (size_t)2 * a.m.nr * 9 * sizeof(double2);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(kspace_fast_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(kspace_fast_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kspace_fast_eval_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kspace_fast_eval_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     dim3 grid;
     pick_grid(a, sm_count, grid);
-    const bool lean = !(a.m.flags & BF_FLAG_RADIATION_MODEL) &&
-                      (a.m.metal_kind == BF_METAL_NONE || a.m.metal_kind == BF_METAL_CROSS_BICUBIC);
-    if (lean) kspace_fast_eval_kernel<true><<<grid, 256, smem, s>>>(a);
-    else kspace_fast_eval_kernel<false><<<grid, 256, smem, s>>>(a);
+    if (part == 1) kspace_fast_eval_kernel<true, 1><<<grid, 256, smem, s>>>(a);
+    else if (part == 2) kspace_fast_eval_kernel<true, 2><<<grid, 256, 0, s>>>(a);
+    else kspace_fast_eval_kernel<false, 0><<<grid, 256, smem, s>>>(a);
 }
 
 void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count) {
@@ -438,4 +533,17 @@ void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count) {
     fast_post_kernel<<<grid, 256, 0, s>>>(a);
 }
 
+}  // namespace bf
+
+namespace bf {
+// Lean models (no radiation, metals none or bicubic cross) run as two passes with small register
+// footprints: the cosmological part, then everything else (if there is anything else).
+bool fast_eval_is_lean(const FastArgs &a) {
+    return !(a.m.flags & BF_FLAG_RADIATION_MODEL) &&
+           (a.m.metal_kind == BF_METAL_NONE || a.m.metal_kind == BF_METAL_CROSS_BICUBIC);
+}
+bool fast_eval_has_extras(const FastArgs &a) {
+    const int sa = a.mode == 1 ? BF_BB_DM_DIST_ADD : BF_BB_DIST_ADD, sm = a.mode == 1 ? BF_BB_DM_DIST_MUL : BF_BB_DIST_MUL;
+    return a.m.metal_kind != BF_METAL_NONE || a.m.bb[sa].enabled || a.m.bb[sm].enabled || (a.mode == 0 && (a.dsub || a.dov));
+}
 }  // namespace bf
