@@ -43,7 +43,7 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
     cudaDeviceProp prop;
     BF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    BF_CUDA_OK(cudaMallocHost((void **)&c->pinned_flag, 64));
+    BF_CUDA_OK(cudaMallocHost((void **)&c->pinned_flag, 256));
     *out = c;
     return BF_OK;
 }
@@ -719,7 +719,7 @@ struct Workspace {
     // fixed-size region of the shared-transform path (independent of the batch size)
     double *Gb, *Tb, *Cb;
     double2 *tabs;
-    int *flag;
+    double *flag;  // [kKeyMax] key-check answer
 };
 
 size_t ws_fixed_doubles(const DevModel &dm) {
@@ -736,7 +736,7 @@ size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
 
 void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Workspace &w) {
     double *p = (double *)base;
-    w.flag = (int *)p;
+    w.flag = p;
     p += 16;
     w.Gb = w.Tb = w.Cb = nullptr;
     w.tabs = nullptr;
@@ -830,14 +830,30 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         nl_table(dm, zeff, pa.nl_tab, &pa.nl_pk_scale);
         // Shared-transform fast path: possible when the tracer factor of D(k,mu) is polynomial
         // (no UV / HCD terms) and every vector of the chunk has the same key parameters.
+        bool cache_hit = false;
         if (what != OUT_TRANSFORM && !(dm.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT))) {
-            BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(int), s));
-            if (B > 1) BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
-            BF_CUDA_OK(cudaMemcpyAsync(ctx->pinned_flag, w.flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+            BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
+            BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
+            BF_CUDA_OK(cudaMemcpyAsync(ctx->pinned_flag, w.flag, sizeof(double) * kKeyMax, cudaMemcpyDeviceToHost, s));
             BF_CUDA_OK(cudaStreamSynchronize(s));
-            shared_tables = (*ctx->pinned_flag == 0);
+            shared_tables = (ctx->pinned_flag[0] == 0.0);
+            if (shared_tables) {
+                // key of this chunk: the key parameters of vector 0 plus everything else K(k,mu) sees
+                std::vector<double> key(ctx->pinned_flag + 1, ctx->pinned_flag + kKeyMax);
+                key.push_back(zeff);
+                key.push_back(pa.nl_pk_scale);
+                for (int q = 0; q < 5; ++q) key.push_back(pa.nl_tab[q]);
+                cache_hit = m->cache_valid && key == m->cached_key;
+                if (!cache_hit) { m->cached_key = key; m->cache_valid = false; }
+            }
         }
-        if (shared_tables) {
+        if (shared_tables && !m->d_tabs_cache) {
+            BF_CUDA_OK(cudaMalloc((void **)&m->d_tabs_cache, (size_t)2 * dm.nr * 9 * sizeof(double2)));
+            const_cast<bf_model *>(m)->allocs.push_back(m->d_tabs_cache);
+        }
+        if (shared_tables && cache_hit) {
+            // basis tables of an earlier call are still valid: nothing to recompute
+        } else if (shared_tables) {
             pa.G = w.Gb;
             BF_CUDA_OK(cudaMemsetAsync(w.Gb, 0, (size_t)6 * dm.nk_pad * kPadN * sizeof(double), s));
             BF_KERNEL(ctx, "kspace_basis_project_kernel", launch_kspace_basis_project(s, pa));
@@ -847,7 +863,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
             g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
             BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
-            BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, w.tabs));
+            BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, m->d_tabs_cache));
+            m->cache_valid = true;
         } else {
             pa.G = w.G;
             BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));
@@ -875,7 +892,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     std::memset(&a, 0, sizeof(a));
     a.m = dm; a.pT = w.pT; a.S = w.S; a.ldb = ldb; a.B = B;
     a.vfac = plan->d_vfac; a.T = w.T; a.C2 = w.C2; a.status = w.status;
-    a.tabs = w.tabs; a.zc_trigger = plan->zc_trigger;
+    a.tabs = m->d_tabs_cache; a.zc_trigger = plan->zc_trigger;
     const bool use_dm = dm.dm_order > 0;
     const bool to_user = what == OUT_PRED;  // final rows go straight to the caller's buffer
 
@@ -893,7 +910,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     };
     FastArgs fa;
     std::memset(&fa, 0, sizeof(fa));
-    fa.m = dm; fa.pT = w.pT; fa.S = w.S; fa.vfac = plan->d_vfac; fa.tabs = w.tabs; fa.ldb = ldb; fa.B = B;
+    fa.m = dm; fa.pT = w.pT; fa.S = w.S; fa.vfac = plan->d_vfac; fa.tabs = m->d_tabs_cache; fa.ldb = ldb; fa.B = B;
     fa.nz = plan->nz; fa.zc_trigger = plan->zc_trigger; fa.status = w.status;
     bool finished = false;
     if (use_dm) {

@@ -96,7 +96,7 @@ struct bf_ctx {
     size_t ws_bytes = 0;
     void *io = nullptr;  // staging for host-buffer entry points
     size_t io_bytes = 0;
-    int *pinned_flag = nullptr;  // 1 pinned int for tiny device->host answers
+    double *pinned_flag = nullptr;  // small pinned buffer for tiny device->host answers (flag + key values)
     int sm_count = 148;
     // optional per-kernel timing (bf_ctx_set_profiling): event pairs around every launch
     bool profiling = false;
@@ -113,6 +113,12 @@ struct bf_model {
     std::vector<double> metal_zgrid;  // [ncomb][ngrid]
     std::vector<double> dist_matrix;  // [order][order]
     std::vector<double> metal_cross_h;  // [ncomb*3][ny][nx] as given (for the plan tables)
+    // shared-transform basis tables, kept across calls while the "key" parameters are unchanged
+    // (the reference likewise re-transforms only when those parameters change,
+    // baofit/BaoKSpaceCorrelationModel.cc:333-380)
+    mutable double2 *d_tabs_cache = nullptr;
+    mutable std::vector<double> cached_key;
+    mutable bool cache_valid = false;
     double metal_dx = 0, metal_dy = 0;
     double zref = 0;
 };

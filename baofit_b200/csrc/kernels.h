@@ -108,7 +108,9 @@ void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, do
                           const double *th_inv_diag, const double *T, double *C2);
 void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
 // shared-transform fast path (all vectors of the batch share the non-polynomial part of D(k,mu))
-void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, int *flag);
+// keyout[0] = 1 if any vector's key differs from vector 0's, keyout[1..] = key values of vector 0
+void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, double *keyout);
+constexpr int kKeyMax = 12;
 void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a);  // a.G: [6][nk_pad][kPadN], columns 0..2
 void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs);
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count);

@@ -377,6 +377,92 @@ __global__ void __launch_bounds__(256, kPart == 1 ? 3 : 2) kspace_fast_eval_kern
     if (kPart != 2 && active && st_bits) atomicOr(a.status + b, st_bits);
 }
 
+// Specialised second pass for the common case "bicubic cross metals, one redshift class, no
+// broadband in this pass": out[i][b] += sum_row wy_row(b,i) * dot(n(b), MX[i][row][:]).
+// The normalisation factors n(b) are per-vector constants, so each row is a 12-term dot product;
+// two bins are processed per iteration to double the loads in flight (this pass is latency bound).
+template <int NT>
+__global__ void __launch_bounds__(256, 2) metal_add_kernel(FastArgs a) {
+    const DevModel &m = a.m;
+    const PointTab &pt = a.pt;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const double *S = a.S + b;
+    const double eb = S[0], ebeta = S[(size_t)ldb], es = S[(size_t)2 * ldb];
+    const double dv = m.idx_delta_v >= 0 ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    const double dpi = dv * a.vfac[0];
+    const bool aniso = m.flags & BF_FLAG_ANISOTROPIC;
+    const double iso = pT[(size_t)(m.idx_bao + 1) * ldb] * es;
+    const double apar = pT[(size_t)(m.idx_bao + 2) * ldb] * es;
+    const double aperp = ((m.flags & BF_FLAG_COMBINED_SCALE) ? pT[(size_t)m.idx_comb_scale * ldb] * pT[(size_t)(m.idx_bao + 2) * ldb]
+                                                              : pT[(size_t)(m.idx_bao + 3) * ldb]) * es;
+    double n[NT];
+#pragma unroll
+    for (int c = 0; c < NT / 3; ++c) cross_metal_norms(m, pT, ldb, c, eb, ebeta, n[3 * c], n[3 * c + 1], n[3 * c + 2]);
+    const int ny = pt.mx_ny;
+    const int i0 = blockIdx.y * a.pts_per_block, i1 = min(min(i0 + a.pts_per_block, pt.npts_pad), pt.npts);
+    auto one = [&](int i, double &wsum, bool &zero) {
+        const double rperp = pt.rperp0[i], rpar = pt.rpar0[i] + dpi;
+        zero = false;
+        if (a.mode == 1) {  // same range zeroing as the cosmological pass (BaoKSpaceCorrelationModel.cc:466-469,485-488)
+            const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
+            const double rprime = r2 * rsqrt(r2);
+            double rBAO;
+            if (aniso) {
+                const double q = apar * apar * rp2 + aperp * aperp * rt2;
+                rBAO = q * rsqrt(q);
+            } else
+                rBAO = rprime * iso;
+            zero = (rprime < m.rlo || rprime > m.rhi) || (rBAO < m.rlo || rBAO > m.rhi);
+        }
+        const double y = fmin(fmax(rpar, m.metal_y0), m.metal_ymax);
+        const double fy = (y - m.metal_y0) * m.metal_inv_dy, fly = floor(fy);
+        double wy[4];
+        catmull_weights(fy - fly, wy);
+        const int iy = (int)fly;
+        const double *mxp = pt.mx + (size_t)i * ny * NT;
+        wsum = 0.0;
+#pragma unroll
+        for (int jy = 0; jy < 4; ++jy) {
+            const double *row = mxp + (size_t)wrap_index(iy - 1 + jy, ny) * NT;
+            double d0 = 0.0, d1 = 0.0;
+            if (NT % 2 == 0) {
+#pragma unroll
+                for (int t = 0; t < NT; t += 2) {
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(row + t));
+                    d0 = fma(n[t], v.x, d0);
+                    d1 = fma(n[t + 1], v.y, d1);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) d0 = fma(n[t], __ldg(row + t), d0);
+            }
+            wsum = fma(wy[jy], d0 + d1, wsum);
+        }
+    };
+    int i = i0;
+    for (; i + 1 < i1; i += 2) {
+        double *o0 = a.out + (size_t)i * a.ldo + b, *o1 = o0 + a.ldo;
+        const double x0 = *o0, x1 = *o1;
+        double w0, w1;
+        bool z0, z1;
+        one(i, w0, z0);
+        one(i + 1, w1, z1);
+        if (!z0) *o0 = x0 + w0;
+        if (!z1) *o1 = x1 + w1;
+    }
+    if (i < i1) {
+        double *o0 = a.out + (size_t)i * a.ldo + b;
+        const double x0 = *o0;
+        double w0;
+        bool z0;
+        one(i, w0, z0);
+        if (!z0) *o0 = x0 + w0;
+    }
+}
+
 // Distortion-matrix tail on the data bins: Z = Y (1 + dist mul) + dist add * evol - d and the
 // dilation-limit check of the data bin itself (BaoKSpaceCorrelationModel.cc:420-427, :529-535).
 __global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
@@ -523,7 +609,15 @@ void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part
     dim3 grid;
     pick_grid(a, sm_count, grid);
     if (part == 1) kspace_fast_eval_kernel<true, 1><<<grid, 256, smem, s>>>(a);
-    else if (part == 2) kspace_fast_eval_kernel<true, 2><<<grid, 256, 0, s>>>(a);
+    else if (part == 2) {
+        const int sa = a.mode == 1 ? BF_BB_DM_DIST_ADD : BF_BB_DIST_ADD, sm = a.mode == 1 ? BF_BB_DM_DIST_MUL : BF_BB_DIST_MUL;
+        const bool metals_only = a.m.metal_kind == BF_METAL_CROSS_BICUBIC && a.nz == 1 && !a.m.bb[sa].enabled &&
+                                 !a.m.bb[sm].enabled && !(a.mode == 0 && (a.dsub || a.dov)) &&
+                                 (a.pt.mx_nt == 12 || a.pt.mx_nt == 15);
+        if (metals_only && a.pt.mx_nt == 12) metal_add_kernel<12><<<grid, 256, 0, s>>>(a);
+        else if (metals_only) metal_add_kernel<15><<<grid, 256, 0, s>>>(a);
+        else kspace_fast_eval_kernel<true, 2><<<grid, 256, 0, s>>>(a);
+    }
     else kspace_fast_eval_kernel<false, 0><<<grid, 256, smem, s>>>(a);
 }
 

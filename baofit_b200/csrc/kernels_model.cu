@@ -432,18 +432,26 @@ __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
 // with 18 basis tables X computed once per batch. The per-vector transform disappears and the
 // tables become small and static: they are staged in shared memory with one TMA bulk copy.
 // ------------------------------------------------------------------------------------------
-__global__ void kspace_key_check_kernel(DevModel m, const double *__restrict__ pT, int ldb, int B, int *flag) {
+__global__ void kspace_key_check_kernel(DevModel m, const double *__restrict__ pT, int ldb, int B, double *keyout) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     bool diff = false;
-    auto cmp = [&](int idx) { diff |= (pT[(size_t)idx * ldb + b] != pT[(size_t)idx * ldb]); };
+    int nkey = 0;
+    auto cmp = [&](int idx) {
+        double v0 = pT[(size_t)idx * ldb];
+        diff |= (pT[(size_t)idx * ldb + b] != v0);
+        if (b == 0) keyout[1 + nkey] = v0;
+        ++nkey;
+    };
     cmp(m.idx_nl);
     cmp(m.idx_nl + 1);
     if (m.flags & (BF_FLAG_BIN_SMOOTH | BF_FLAG_BIN_SMOOTH_ALT)) { cmp(m.idx_bs); cmp(m.idx_bs + 1); }
     if (m.flags & BF_FLAG_SMOOTH_GAUSS) cmp(m.idx_smgaus);
     if (m.flags & BF_FLAG_SMOOTH_LORENTZ) cmp(m.idx_smlor);
     if (m.flags & BF_FLAG_FIT_NL_CORRECTION) { cmp(m.idx_nlcorr); cmp(m.idx_nlcorr + 1); }
-    if (diff) *flag = 1;
+    if (b == 0)
+        for (int k = nkey; k < kKeyMax - 1; ++k) keyout[1 + k] = 0.0;
+    if (diff) keyout[0] = 1.0;
 }
 
 // G[((comp*3 + l)*nk_pad + i)*kPadN + n] = (2l+1) Int_0^1 L_l(mu) mu^(2n) K_comp(k_i, mu) dmu
@@ -756,8 +764,8 @@ void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
     kspace_eval_kernel<<<grid, 128, 0, s>>>(a);
 }
 
-void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, int *flag) {
-    kspace_key_check_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, pT, ldb, B, flag);
+void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, double *keyout) {
+    kspace_key_check_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, pT, ldb, B, keyout);
 }
 
 void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a) {

@@ -157,3 +157,20 @@ def test_kspace_shared_and_per_vector_paths_agree(ctx):
     ctx.set_profiling(False)
     assert rel_err(shared, generic[1:]) < RTOL
     gm.close(), gd.close()
+
+
+def test_kspace_basis_table_cache_follows_key_parameters(ctx):
+    """The shared basis tables are kept across calls while SigmaNL etc. are unchanged and must be
+    rebuilt when they change (the reference re-transforms only then, BaoKSpaceCorrelationModel.cc:333-380)."""
+    m, d = W.qso_kspace(with_dist_matrix=False, with_metals=False)
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    om, od = oracle.OracleModel(m), oracle.OracleData(d)
+    base = m.values.copy()
+    for snl in (3.26, 3.26, 4.5, 3.26):
+        p = np.tile(base, (3, 1))
+        p[:, m.index("SigmaNL-perp")] = snl
+        p[:, m.index("beta")] += [0.0, 0.05, -0.05]
+        chi2, _ = capi.chi2_batch(ctx, gm, gd, p)
+        ref, _ = oracle.chi2_batch(om, od, p, nthreads=8)
+        assert rel_err(chi2, ref) < RTOL, snl
+    gm.close(), gd.close()
