@@ -720,15 +720,18 @@ struct Workspace {
     double *Gb, *Tb, *Cb;
     double2 *tabs;
     double *flag;  // [kKeyMax] key-check answer
+    int *sort_hist, *sort_base, *rank;  // coherence sort
+    double *chi2_sorted;
 };
 
 size_t ws_fixed_doubles(const DevModel &dm) {
-    if (dm.kind != BF_MODEL_KSPACE) return 16;
-    return (size_t)6 * dm.nk_pad * kPadN + (size_t)12 * dm.nr_pad * kPadN + (size_t)2 * dm.nr * 9 * 2 + 32;
+    size_t sort = kSortTableInts;  // two int tables of 2048 = 2048 doubles
+    if (dm.kind != BF_MODEL_KSPACE) return 16 + sort;
+    return (size_t)6 * dm.nk_pad * kPadN + (size_t)12 * dm.nr_pad * kPadN + (size_t)2 * dm.nr * 9 * 2 + 32 + sort;
 }
 
 size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
-    size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + d->n_pad /*Z*/;
+    size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + 2 /*rank, sorted chi2*/ + d->n_pad /*Z*/;
     if (dm.kind == BF_MODEL_KSPACE) c += (size_t)6 * dm.nk_pad + (size_t)12 * dm.nr_pad;
     if (dm.dm_order > 0) c += (size_t)d->n_grid_pad + 64 + d->n_pad;  // xi_u panel (+ fused-tail rows) and Y
     return c;
@@ -738,6 +741,9 @@ void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Wo
     double *p = (double *)base;
     w.flag = p;
     p += 16;
+    w.sort_hist = (int *)p;
+    w.sort_base = w.sort_hist + kSortTableInts;
+    p += kSortTableInts;
     w.Gb = w.Tb = w.Cb = nullptr;
     w.tabs = nullptr;
     if (dm.kind == BF_MODEL_KSPACE) {
@@ -754,6 +760,8 @@ void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Wo
     w.pT = take(dm.npar);
     w.S = take((size_t)nz * 3);
     w.status = (int *)take(1);
+    w.rank = (int *)take(1);
+    w.chi2_sorted = take(1);
     w.Z = take(d->n_pad);
     w.G = w.T = w.C2 = w.XiU = w.Y = nullptr;
     if (dm.kind == BF_MODEL_KSPACE) {
@@ -817,7 +825,11 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         BF_CUDA_OK(cudaMemcpyAsync(tmp_z, &z_trigger_override, sizeof(double), cudaMemcpyHostToDevice, s));
         d_zvals = tmp_z;
     }
-    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, w.pT, w.S, w.status));
+    // coherence sort (chi2 only; outputs that are indexed by the original column stay unsorted)
+    const bool sorted = what == OUT_CHI2 && !d_override && B >= 2048;
+    if (sorted) BF_KERNEL(ctx, "coherence_sort_kernels", launch_coherence_sort(s, dm, d_params, B, w.sort_hist, w.sort_base, w.rank));
+    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status));
+    double *chi2_dst = sorted ? w.chi2_sorted : d_out;
 
     bool shared_tables = false;
     if (dm.kind == BF_MODEL_KSPACE) {
@@ -953,7 +965,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             g.lda = g.K; g.ldb = ldb;
             if (what == OUT_CHI2) {
                 g.A = plan->d_WA; g.C = nullptr; g.ldc = 0;
-                g.chi2 = d_out; g.status = w.status;
+                g.chi2 = chi2_dst; g.status = w.status;
                 BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g));
             } else {
                 g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
@@ -1010,10 +1022,13 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         g.M = d->n_pad; g.N = B; g.K = d->n_pad;
         g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
         g.lower_triangular = 1;
-        g.chi2 = d_out; g.status = w.status;
+        g.chi2 = chi2_dst; g.status = w.status;
         BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
     }
-    if (d_status_out) BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+    if (sorted) {
+        BF_KERNEL(ctx, "unpermute_kernel", launch_unpermute(s, B, w.rank, w.chi2_sorted, w.status, d_out, d_status_out));
+    } else if (d_status_out)
+        BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
     BF_CUDA_OK(cudaGetLastError());
     return BF_OK;
 }
@@ -1021,7 +1036,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
 int chunk_capacity(const bf_model *m, const bf_data *d, int nz) {
     static bf_data empty_data;
     size_t per_col = ws_doubles_per_column(m->dev, d ? d : &empty_data, nz) * sizeof(double);
-    size_t budget = ((size_t)3 << 30) - ws_fixed_doubles(m->dev) * sizeof(double);  // 3 GiB of workspace at most
+    size_t budget = ((size_t)8 << 30) - ws_fixed_doubles(m->dev) * sizeof(double);  // 8 GiB of workspace at most
     size_t cap = budget / per_col;
     cap = std::min<size_t>(cap, 65536);
     cap = std::max<size_t>(cap / kPadN * kPadN, kPadN);
@@ -1044,9 +1059,12 @@ static int run_device(bf_ctx *ctx, const bf_model *m, const bf_data *d, const do
     const bf_data::Plan *plan = nullptr;
     if ((rc = get_plan(m, d, &plan))) return rc;
     int cap = chunk_capacity(m, d, plan->nz);
+    // equal-sized chunks (a small trailing chunk would under-fill the GPU)
+    int nchunks = (B + cap - 1) / cap;
+    cap = round_up((B + nchunks - 1) / nchunks, kPadN);
     for (int b0 = 0; b0 < B; b0 += cap) {
         int bc = std::min(cap, B - b0);
-        double *o = what == OUT_CHI2 ? d_out + b0 : d_out + b0;  // chi2[b] or column offset in bin-major outputs
+        double *o = d_out + b0;  // chi2[b] or column offset in bin-major outputs
         const double *ov = d_override ? d_override + (size_t)b0 * d->n : nullptr;
         rc = run_chunk(ctx, m, d, plan, d_params + (size_t)b0 * m->dev.npar, bc, what, o, ldo, ov,
                        d_status ? d_status + b0 : nullptr, 0.0, false);

@@ -101,7 +101,12 @@ struct GemmArgs {
 };
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
-                 const double *zvals, double *pT, double *S, int *status);
+                 const double *zvals, const int *rank, double *pT, double *S, int *status);
+// counting sort of the vectors on their quantised dilation parameters; hist/base: 2048 ints each
+void launch_coherence_sort(cudaStream_t s, const DevModel &m, const double *params, int B, int *hist, int *base, int *rank);
+void launch_unpermute(cudaStream_t s, int B, const int *rank, const double *chi2_sorted, const int *status_sorted,
+                      double *chi2, int *status);
+constexpr int kSortTableInts = 2048;
 void launch_rspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count);
 void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,

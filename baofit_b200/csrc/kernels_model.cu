@@ -12,21 +12,87 @@ namespace bf {
 // prep: transpose parameters, per-(class, b) redshift-evolution factors, clear status
 // ------------------------------------------------------------------------------------------
 __global__ void prep_kernel(DevModel m, const double *__restrict__ params, int B, int ldb, int nz,
-                            const double *__restrict__ zvals, double *__restrict__ pT, double *__restrict__ S,
-                            int *__restrict__ status) {
+                            const double *__restrict__ zvals, const int *__restrict__ rank, double *__restrict__ pT,
+                            double *__restrict__ S, int *__restrict__ status) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double *p = params + (size_t)b * m.npar;
-    for (int j = 0; j < m.npar; ++j) pT[(size_t)j * ldb + b] = p[j];
+    const int col = rank ? rank[b] : b;  // column of this vector in the (possibly sorted) panels
+    for (int j = 0; j < m.npar; ++j) pT[(size_t)j * ldb + col] = p[j];
     double gb = p[m.idx_gamma_bias], gbeta = p[m.idx_gamma_beta], gs = p[m.idx_bao + 4];
     for (int c = 0; c < nz; ++c) {
         // redshiftEvolution, baofit/AbsCorrelationModel.cc:159-161
         double x = (1.0 + zvals[c]) / (1.0 + m.zref);
-        S[(size_t)(c * 3 + 0) * ldb + b] = gb == 0.0 ? 1.0 : pow(x, gb);
-        S[(size_t)(c * 3 + 1) * ldb + b] = gbeta == 0.0 ? 1.0 : pow(x, gbeta);
-        S[(size_t)(c * 3 + 2) * ldb + b] = gs == 0.0 ? 1.0 : pow(x, gs);
+        S[(size_t)(c * 3 + 0) * ldb + col] = gb == 0.0 ? 1.0 : pow(x, gb);
+        S[(size_t)(c * 3 + 1) * ldb + col] = gbeta == 0.0 ? 1.0 : pow(x, gbeta);
+        S[(size_t)(c * 3 + 2) * ldb + col] = gs == 0.0 ? 1.0 : pow(x, gs);
     }
-    status[b] = 0;
+    status[col] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Coherence sort. Lanes of a warp are consecutive parameter vectors; their table look-ups hit the
+// same shared-memory rows only if their dilation parameters are close. A counting sort on the
+// quantised (alpha_parallel, alpha_perp) makes warps coherent for arbitrary batches (scans and
+// lock-step fits already are). Results do not depend on the order: every column is independent.
+// ------------------------------------------------------------------------------------------
+constexpr int kSortQA = 32, kSortQP = 64, kSortBuckets = kSortQA * kSortQP;
+
+__device__ __forceinline__ int sort_bucket(const DevModel &m, const double *__restrict__ p) {
+    double a, t;
+    if (m.flags & BF_FLAG_ANISOTROPIC) {
+        a = p[m.idx_bao + 2];
+        t = (m.flags & BF_FLAG_COMBINED_SCALE) ? p[m.idx_comb_scale] * a : p[m.idx_bao + 3];
+    } else
+        a = t = p[m.idx_bao + 1];
+    int qa = (int)((a - 0.5) * kSortQA), qt = (int)((t - 0.5) * kSortQP);
+    qa = max(0, min(kSortQA - 1, qa));
+    qt = max(0, min(kSortQP - 1, qt));
+    return qa * kSortQP + qt;
+}
+
+__global__ void sort_hist_kernel(DevModel m, const double *__restrict__ params, int B, int *__restrict__ hist) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    atomicAdd(hist + sort_bucket(m, params + (size_t)b * m.npar), 1);
+}
+
+__global__ void sort_scan_kernel(int *__restrict__ hist, int *__restrict__ base) {
+    // exclusive prefix sum over kSortBuckets (= 2 per thread of a 1024-thread block)
+    __shared__ int sh[kSortBuckets];
+    int t = threadIdx.x;
+    sh[2 * t] = hist[2 * t];
+    sh[2 * t + 1] = hist[2 * t + 1];
+    __syncthreads();
+    for (int off = 1; off < kSortBuckets; off <<= 1) {
+        int v0 = 2 * t >= off ? sh[2 * t - off] : 0, v1 = 2 * t + 1 >= off ? sh[2 * t + 1 - off] : 0;
+        __syncthreads();
+        sh[2 * t] += v0;
+        sh[2 * t + 1] += v1;
+        __syncthreads();
+    }
+    base[2 * t] = sh[2 * t] - hist[2 * t];
+    base[2 * t + 1] = sh[2 * t + 1] - hist[2 * t + 1];
+    __syncthreads();
+    hist[2 * t] = 0;  // reused as the per-bucket cursor
+    hist[2 * t + 1] = 0;
+}
+
+__global__ void sort_rank_kernel(DevModel m, const double *__restrict__ params, int B, const int *__restrict__ base,
+                                 int *__restrict__ cursor, int *__restrict__ rank) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int k = sort_bucket(m, params + (size_t)b * m.npar);
+    rank[b] = base[k] + atomicAdd(cursor + k, 1);
+}
+
+__global__ void unpermute_kernel(int B, const int *__restrict__ rank, const double *__restrict__ chi2_sorted,
+                                 const int *__restrict__ status_sorted, double *__restrict__ chi2, int *__restrict__ status) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int c = rank[b];
+    chi2[b] = chi2_sorted[c];
+    if (status) status[b] = status_sorted[c];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -736,8 +802,20 @@ static int pick_pts_per_block(int npts_pad, int B, int sm_count) {
 }
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
-                 const double *zvals, double *pT, double *S, int *status) {
-    prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(m, params, B, ldb, nz, zvals, pT, S, status);
+                 const double *zvals, const int *rank, double *pT, double *S, int *status) {
+    prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(m, params, B, ldb, nz, zvals, rank, pT, S, status);
+}
+
+void launch_coherence_sort(cudaStream_t s, const DevModel &m, const double *params, int B, int *hist, int *base, int *rank) {
+    cudaMemsetAsync(hist, 0, sizeof(int) * kSortBuckets, s);
+    sort_hist_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, params, B, hist);
+    sort_scan_kernel<<<1, kSortBuckets / 2, 0, s>>>(hist, base);
+    sort_rank_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, params, B, base, hist, rank);
+}
+
+void launch_unpermute(cudaStream_t s, int B, const int *rank, const double *chi2_sorted, const int *status_sorted,
+                      double *chi2, int *status) {
+    unpermute_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, rank, chi2_sorted, status_sorted, chi2, status);
 }
 
 void launch_rspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {

@@ -174,3 +174,28 @@ def test_kspace_basis_table_cache_follows_key_parameters(ctx):
         ref, _ = oracle.chi2_batch(om, od, p, nthreads=8)
         assert rel_err(chi2, ref) < RTOL, snl
     gm.close(), gd.close()
+
+
+def test_coherence_sort_does_not_change_results(ctx):
+    """Batches of >= 2048 vectors are internally sorted on their dilation parameters; every column is
+    independent, so chi2 must be identical to the unsorted evaluation of the same vectors."""
+    m, d = W.qso_kspace()
+    rng = np.random.Generator(np.random.PCG64(41))
+    params = m.random_batch(4096, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5),
+                                              "delta-v": (-300, 300)})
+    params[7, m.index("BAO alpha-perp")] = 1.9  # one vector beyond the dilation limit
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    big, st_big = capi.chi2_batch(ctx, gm, gd, params)
+    parts = [capi.chi2_batch(ctx, gm, gd, params[k:k + 1024]) for k in range(0, 4096, 1024)]
+    small = np.concatenate([p[0] for p in parts])
+    st_small = np.concatenate([p[1] for p in parts])
+    assert np.array_equal(st_big, st_small) and st_big[7] == 2 and st_big.sum() == 2
+    ok = st_big == 0
+    assert np.array_equal(big[ok], small[ok]) and np.isnan(big[7])
+    gm.close(), gd.close()
+
+
+def test_rspace_large_batch_sorted_path(ctx):
+    m, d = W.qso_rspace()
+    e_pred, e_chi2 = _compare(ctx, m, d, 2500, 43, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)})
+    assert e_pred < RTOL and e_chi2 < RTOL, (e_pred, e_chi2)
