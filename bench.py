@@ -55,6 +55,20 @@ def parse():
     return ap.parse_args()
 
 
+def load_traffic(kernel, B):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic_r01.json), valid only for the batch size it was captured at."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+            t = json.load(f)
+        if t["batch"] != B or kernel not in t["kernels"]:
+            return None
+        k = t["kernels"][kernel]
+        return k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     hbm, src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -319,6 +333,8 @@ def main_ours(args, rank, world, local_rank):
     contraction_ms = sum(prof[k][0] / prof[k][1] for k in fl if k in prof)
     roof["contraction_tflops"] = contraction_flops / (contraction_ms * 1e-3) * 1e-12 if contraction_ms else None
     roof["contraction_frac"] = roof["contraction_tflops"] / fp64 if contraction_ms else None
+    roof["traffic"] = load_traffic(top, B)
+    roof["traffic_unit"] = "bytes of DRAM read+write per launch (ncu --set full, profiles/ncu_traffic_r01.json)"
 
     cpu = None
     if not args.no_cpu_baseline:
