@@ -21,6 +21,7 @@ EXPORTS = [
     "bf_data_create", "bf_data_destroy", "bf_data_ndata", "bf_eval_batch", "bf_chi2_batch",
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
+    "bf_fft_planes_batch", "bf_model_fft_plane_dims",
 ]
 
 
@@ -67,6 +68,8 @@ def lib():
         L.bf_model_transform_dr.argtypes = [C.c_void_p]
         L.bf_sample_toys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int,
                                      C.c_double, C.c_void_p]
+        L.bf_fft_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.bf_model_fft_plane_dims.argtypes = [C.c_void_p, c_int_p, c_int_p]
         _LIB = L
     return _LIB
 
@@ -142,6 +145,17 @@ class Model:
         _check(lib().bf_transform_batch(self.ctx.h, self.h, _ptr(p), B, float(z_trigger), _ptr(out), B))
         r = lib().bf_model_transform_r0(self.h) + lib().bf_model_transform_dr(self.h) * np.arange(nr)
         return r, out
+
+
+    def fft_planes(self, params, z_trigger):
+        """FFT model: xi_comp on the z = 0 plane of the box for every vector, [B][comp][iy][ix]."""
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, self.npar)
+        B = p.shape[0]
+        npx, npy = C.c_int(0), C.c_int(0)
+        _check(lib().bf_model_fft_plane_dims(self.h, C.byref(npx), C.byref(npy)))
+        out = np.zeros((B, 2, npy.value, npx.value))
+        _check(lib().bf_fft_planes_batch(self.ctx.h, self.h, _ptr(p), B, float(z_trigger), _ptr(out)))
+        return out
 
 
 class Data:

@@ -216,8 +216,8 @@ extern "C" int bf_model_npar(const bf_model *m) { return m ? m->dev.npar : 0; }
 
 extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **out) {
     if (!ctx || !d || !out) BF_FAIL(BF_ERR_OPTIONS, "bf_model_create: null argument");
-    if (d->kind != BF_MODEL_RSPACE && d->kind != BF_MODEL_KSPACE)
-        BF_FAIL(BF_ERR_MODEL, "bf_model_create: model kind not built (the FFT k-space model is not implemented yet)");
+    if (d->kind != BF_MODEL_RSPACE && d->kind != BF_MODEL_KSPACE && d->kind != BF_MODEL_KSPACE_FFT)
+        BF_FAIL(BF_ERR_MODEL, "bf_model_create: unknown model kind");
     if (d->npar <= 0 || d->npar > 256) BF_FAIL(BF_ERR_MODEL, "bf_model_create: bad parameter count");
     auto chk = [&](int idx, int span) { return idx >= 0 && idx + span <= d->npar; };
     if (!chk(d->idx_beta, 1) || !chk(d->idx_bb, 1) || !chk(d->idx_gamma_bias, 1) || !chk(d->idx_gamma_beta, 1) ||
@@ -267,6 +267,66 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         if (d->idx_rad >= 0 && !chk(d->idx_rad, 4)) { bf::set_error("bf_model_create: bad radiation block"); return fail(BF_ERR_MODEL); }
         if ((rc = make_spline_set(m, d->n_fid, d->fid_r, d->fid_xi0, d->fid_xi2, d->fid_xi4, dm.fid))) return fail(rc);
         if ((rc = make_spline_set(m, d->n_nw, d->nw_r, d->nw_xi0, d->nw_xi2, d->nw_xi4, dm.nw))) return fail(rc);
+    } else if (d->kind == BF_MODEL_KSPACE_FFT) {
+        // baofit/BaoKSpaceFftCorrelationModel.cc:36-113
+        if (!chk(d->idx_nl, 2) || !chk(d->idx_cont, 2)) { bf::set_error("bf_model_create: FFT model needs SigmaNL-perp, 1+f, cont-kc, cont-pc"); return fail(BF_ERR_MODEL); }
+        if ((d->flags & BF_FLAG_FIT_NL_CORRECTION) && !chk(d->idx_nlcorr, 2)) { bf::set_error("bf_model_create: bad nlcorr block"); return fail(BF_ERR_MODEL); }
+        if (d->n_pk < 8 || !d->pk_k || !d->pk_fid || !d->pk_nw) {
+            bf::set_error("BaoKSpaceFftCorrelationModel: error while reading tabulated P(k) data.");
+            return fail(BF_ERR_MODEL);
+        }
+        if (!(d->fft_spacing > 0) || d->fft_nx < 8 || d->fft_ny < 8 || d->fft_nz < 8 || d->fft_nx > 4096 || d->fft_ny > 4096 || d->fft_nz > 4096) {
+            bf::set_error("BaoKSpaceFftCorrelationModel: bad 3D FFT grid (gridspacing > 0, 8 <= ngrid <= 4096)");
+            return fail(BF_ERR_MODEL);
+        }
+        if (d->metal_kind != BF_METAL_NONE || d->dist_matrix) { bf::set_error("BaoKSpaceFftCorrelationModel has no metal model / distortion matrix"); return fail(BF_ERR_MODEL); }
+        DevFft &f = dm.fft;
+        f.nx = d->fft_nx; f.ny = d->fft_ny; f.nz = d->fft_nz;
+        f.mx = f.nx / 2 + 1; f.my = f.ny / 2 + 1; f.mz = f.nz / 2 + 1;
+        f.my_pad = round_up(f.my, 16);
+        f.delta = d->fft_spacing; f.inv_delta = 1.0 / d->fft_spacing;
+        f.norm = 1.0 / ((double)f.nx * f.ny * f.nz * f.delta * f.delta * f.delta);
+        f.zcorr0 = d->zcorr0; f.zcorr1 = d->zcorr1; f.zcorr2 = d->zcorr2;
+        const double plane_rmax = d->fft_rmax > 0 ? d->fft_rmax : d->rmax * d->dilmax;
+        if (!(plane_rmax > 0)) { bf::set_error("BaoKSpaceFftCorrelationModel: need fft_rmax > 0 or rmax * dilmax > 0"); return fail(BF_ERR_MODEL); }
+        const int np = (int)std::floor(plane_rmax / f.delta) + 3;
+        f.npx = std::min(np, f.mx); f.npy = std::min(np, f.my);
+        f.npx_pad = round_up(f.npx, 8); f.npy_pad = round_up(f.npy, 8);
+        dm.sigma8 = d->sigma8;
+        // P(k): natural cubic splines in ln k, power-law continuation through the end points
+        const int n = d->n_pk;
+        for (int j = 0; j + 1 < n; ++j)
+            if (!(d->pk_k[j + 1] > d->pk_k[j]) || !(d->pk_k[j] > 0)) { bf::set_error("BaoKSpaceFftCorrelationModel: P(k) nodes must be positive and increasing"); return fail(BF_ERR_MODEL); }
+        std::vector<double> lnk(n), coef((size_t)2 * (n - 1) * 4);
+        for (int j = 0; j < n; ++j) lnk[j] = std::log(d->pk_k[j]);
+        const double *tabs[2] = {d->pk_fid, d->pk_nw};
+        auto slope = [](double k0, double p0, double k1, double p1) { return p0 * p1 <= 0 ? 0.0 : std::log(p1 / p0) / std::log(k1 / k0); };
+        for (int w = 0; w < 2; ++w) {
+            cspline_interval_coefs(n, lnk.data(), tabs[w], coef.data() + (size_t)w * (n - 1) * 4);
+            f.pk_end[w][0] = tabs[w][0]; f.pk_end[w][1] = tabs[w][n - 1];
+            f.pk_slope[w][0] = slope(d->pk_k[0], tabs[w][0], d->pk_k[1], tabs[w][1]);
+            f.pk_slope[w][1] = slope(d->pk_k[n - 2], tabs[w][n - 2], d->pk_k[n - 1], tabs[w][n - 1]);
+        }
+        f.n_pk = n; f.pk_k0 = d->pk_k[0]; f.pk_k1 = d->pk_k[n - 1];
+        double *p = nullptr;
+        if ((rc = upload(m->allocs, lnk.data(), lnk.size(), &p))) return fail(rc);
+        f.lnk = p;
+        if ((rc = upload(m->allocs, coef.data(), coef.size(), &p))) return fail(rc);
+        f.pk_coef = p;
+        // cosine tables with exact argument reduction
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        std::vector<double> cosx(f.nx), cy((size_t)f.npy_pad * f.my_pad, 0.0);
+        for (int t = 0; t < f.nx; ++t) cosx[t] = (double)cosl(two_pi * t / f.nx);
+        for (int iy = 0; iy < f.npy; ++iy)
+            for (int my = 0; my < f.my; ++my) cy[(size_t)iy * f.my_pad + my] = (double)cosl(two_pi * (((long long)my * iy) % f.ny) / f.ny);
+        if ((rc = upload(m->allocs, cosx.data(), cosx.size(), &p))) return fail(rc);
+        f.cosx = p;
+        if ((rc = upload(m->allocs, cy.data(), cy.size(), &p))) return fail(rc);
+        f.Cy = p;
+        BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_T, (size_t)6 * f.my_pad * f.npx_pad * sizeof(double)));
+        m->allocs.push_back(m->d_fft_T);
+        BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_H, (size_t)6 * f.my * f.mx * sizeof(double)));
+        m->allocs.push_back(m->d_fft_H);
     } else {
         if (!chk(d->idx_nl, 2)) { bf::set_error("bf_model_create: k-space model needs SigmaNL-perp, 1+f"); return fail(BF_ERR_MODEL); }
         if ((d->flags & BF_FLAG_RADIATION_MODEL) && !chk(d->idx_rad, 4)) { bf::set_error("bf_model_create: bad radiation block"); return fail(BF_ERR_MODEL); }
@@ -722,6 +782,8 @@ struct Workspace {
     double *flag;  // [kKeyMax] key-check answer
     int *sort_hist, *sort_base, *rank;  // coherence sort
     double *chi2_sorted;
+    double *fft_c12, *fft_cont, *fft_planes;  // FFT model: [2][ldb], [my_pad][ldb], [ldb][2][npy_pad][npx_pad]
+    double *fft_keys;                         // [kFftKeyMax-1][ldb]
 };
 
 size_t ws_fixed_doubles(const DevModel &dm) {
@@ -734,6 +796,7 @@ size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
     size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + 2 /*rank, sorted chi2*/ + d->n_pad /*Z*/;
     if (dm.kind == BF_MODEL_KSPACE) c += (size_t)6 * dm.nk_pad + (size_t)12 * dm.nr_pad;
     if (dm.dm_order > 0) c += (size_t)d->n_grid_pad + 64 + d->n_pad;  // xi_u panel (+ fused-tail rows) and Y
+    if (dm.kind == BF_MODEL_KSPACE_FFT) c += 2 + kFftKeyMax + (size_t)dm.fft.my_pad + (size_t)2 * dm.fft.npy_pad * dm.fft.npx_pad;
     return c;
 }
 
@@ -772,6 +835,13 @@ void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Wo
     if (dm.dm_order > 0) {
         w.XiU = take((size_t)d->n_grid_pad + 64);
         w.Y = take(d->n_pad);
+    }
+    w.fft_c12 = w.fft_cont = w.fft_planes = nullptr;
+    if (dm.kind == BF_MODEL_KSPACE_FFT) {
+        w.fft_c12 = take(2);
+        w.fft_keys = take(kFftKeyMax);
+        w.fft_cont = take(dm.fft.my_pad);
+        w.fft_planes = take((size_t)2 * dm.fft.npy_pad * dm.fft.npx_pad);
     }
 }
 
@@ -826,7 +896,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         d_zvals = tmp_z;
     }
     // coherence sort (chi2 only; outputs that are indexed by the original column stay unsorted)
-    const bool sorted = what == OUT_CHI2 && !d_override && B >= 2048;
+    const bool sorted = what == OUT_CHI2 && !d_override && B >= 2048 && dm.kind != BF_MODEL_KSPACE_FFT;
     if (sorted) BF_KERNEL(ctx, "coherence_sort_kernels", launch_coherence_sort(s, dm, d_params, B, w.sort_hist, w.sort_base, w.rank));
     BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status));
     double *chi2_dst = sorted ? w.chi2_sorted : d_out;
@@ -898,6 +968,100 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             BF_KERNEL(ctx, "kspace_thomas_kernel",
                       launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2));
         }
+    }
+
+    if (dm.kind == BF_MODEL_KSPACE_FFT) {
+        const DevFft &f = dm.fft;
+        FftVecArgs va;
+        std::memset(&va, 0, sizeof(va));
+        va.m = dm; va.pT = w.pT; va.ldb = ldb; va.B = B;
+        if (d) { va.r0 = d->h_r[0]; va.mu0 = d->h_mu[0]; va.z0 = d->h_z[0]; }
+        va.use_ztrig = d ? 0 : 1;
+        va.ztrig = z_trigger_override;
+        va.keyflag = w.flag; va.keys = w.fft_keys; va.c12 = w.fft_c12; va.cont = w.fft_cont; va.status = w.status;
+        BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
+        BF_KERNEL(ctx, "fft_vec_kernel", launch_fft_vec(s, va));
+        BF_CUDA_OK(cudaMemcpyAsync(ctx->pinned_flag, w.flag, sizeof(double) * kFftKeyMax, cudaMemcpyDeviceToHost, s));
+        BF_CUDA_OK(cudaStreamSynchronize(s));
+        // key = SigmaNL-perp, 1+f, nlcorr qnl, nlcorr kp, z of the triggering bin: what the per-key
+        // tables read. The reference re-runs its 3-D FFTs when one of these changes (:191-214); here
+        // the tables are rebuilt, once per distinct key of the chunk.
+        constexpr int NK = 5;
+        auto tables_for = [&](const std::vector<double> &key) {
+            if (m->cache_valid && key == m->cached_key) return;
+            FftKeyState ks;
+            const double snl_perp = key[0], snl_par = key[0] * key[1], zeff = key[4];
+            ks.snl_perp2 = snl_perp * snl_perp;
+            ks.snl_par2 = snl_par * snl_par;
+            nl_table(dm, zeff, ks.nl_tab, &ks.nl_pk_scale);
+            if (dm.flags & BF_FLAG_FIT_NL_CORRECTION) { ks.nl_tab[0] = key[2]; ks.nl_tab[4] = key[3]; }
+            ProfScope ps1(ctx, "fft_hsum_kernel+fft_xtrans_kernel");
+            ctx->launches++;  // two kernels
+            launch_fft_tables(s, dm, ks, m->d_fft_H, m->d_fft_T);
+            m->cached_key = key;
+            m->cache_valid = true;
+        };
+        if (ctx->pinned_flag[0] == 0.0) {
+            tables_for(std::vector<double>(ctx->pinned_flag + 1, ctx->pinned_flag + 1 + NK));
+            BF_KERNEL(ctx, "fft_plane_kernel",
+                      launch_fft_planes(s, dm, m->d_fft_T, w.fft_c12, w.fft_cont, ldb, nullptr, B, w.fft_planes));
+        } else {
+            // several keys in one chunk (e.g. the finite-difference probes of a fit that floats
+            // SigmaNL): group the columns by key, one table build + one plane launch per group
+            std::vector<double> hk((size_t)NK * ldb);
+            BF_CUDA_OK(cudaMemcpyAsync(hk.data(), w.fft_keys, hk.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            BF_CUDA_OK(cudaStreamSynchronize(s));
+            std::map<std::vector<double>, std::vector<int>> groups;
+            std::vector<double> key(NK);
+            for (int b = 0; b < B; ++b) {
+                for (int q = 0; q < NK; ++q) key[q] = hk[(size_t)q * ldb + b];
+                groups[key].push_back(b);
+            }
+            std::vector<int> order;
+            order.reserve(B);
+            for (auto &kv : groups) order.insert(order.end(), kv.second.begin(), kv.second.end());
+            BF_CUDA_OK(cudaMemcpyAsync(w.rank, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+            BF_CUDA_OK(cudaStreamSynchronize(s));  // `order` is pageable host memory
+            int first = 0;
+            for (auto &kv : groups) {
+                tables_for(kv.first);
+                BF_KERNEL(ctx, "fft_plane_kernel", launch_fft_planes(s, dm, m->d_fft_T, w.fft_c12, w.fft_cont, ldb, w.rank + first,
+                                                                     (int)kv.second.size(), w.fft_planes));
+                first += (int)kv.second.size();
+            }
+        }
+        if (what == OUT_TRANSFORM) {
+            // out[((b*2 + comp)*npy + iy)*npx + ix]
+            BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)f.npx * sizeof(double), w.fft_planes, (size_t)f.npx_pad * sizeof(double),
+                                         (size_t)f.npx * sizeof(double), (size_t)B * 2 * f.npy_pad, cudaMemcpyDeviceToDevice, s));
+            if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
+            BF_CUDA_OK(cudaGetLastError());
+            return BF_OK;
+        }
+        if (what == OUT_XIU) BF_FAIL(BF_ERR_ANALYSIS, "bf_eval_undistorted_batch: the model has no distortion matrix");
+        const bool to_user = what == OUT_PRED;
+        FftEvalArgs ea;
+        std::memset(&ea, 0, sizeof(ea));
+        ea.m = dm; ea.pT = w.pT; ea.ldb = ldb; ea.B = B; ea.npts = d->n;
+        ea.r = d->d_r; ea.mu = d->d_mu; ea.z = d->d_z; ea.planes = w.fft_planes;
+        ea.out = to_user ? d_out : w.Z; ea.ldo = to_user ? ldo : ldb;
+        ea.dsub = to_user ? nullptr : d->d_data; ea.dov = to_user ? nullptr : d_override;
+        ea.status = w.status;
+        if (!to_user && d->n_pad > d->n)
+            BF_CUDA_OK(cudaMemsetAsync(w.Z + (size_t)d->n * ldb, 0, (size_t)(d->n_pad - d->n) * ldb * sizeof(double), s));
+        BF_KERNEL(ctx, "fft_eval_kernel", launch_fft_eval(s, ea));
+        if (what == OUT_CHI2) {
+            GemmArgs g{};
+            g.A = d->d_W; g.Bm = w.Z; g.C = nullptr;
+            g.M = d->n_pad; g.N = B; g.K = d->n_pad;
+            g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
+            g.lower_triangular = 1;
+            g.chi2 = d_out; g.status = w.status;
+            BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+        }
+        if (d_status_out) BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+        BF_CUDA_OK(cudaGetLastError());
+        return BF_OK;
     }
 
     EvalArgs a;
@@ -1168,6 +1332,45 @@ extern "C" int bf_transform_batch(bf_ctx *ctx, const bf_model *m, const double *
         if (rc) return rc;
         BF_CUDA_OK(cudaMemcpy2DAsync(out + b0, (size_t)ldb_out * sizeof(double), d_out, (size_t)bc * sizeof(double),
                                      (size_t)bc * sizeof(double), (size_t)6 * nr, cudaMemcpyDeviceToHost, ctx->stream));
+        BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_model_fft_plane_dims(const bf_model *m, int *npx, int *npy) {
+    if (!m || m->dev.kind != BF_MODEL_KSPACE_FFT) BF_FAIL(BF_ERR_OPTIONS, "bf_model_fft_plane_dims: not an FFT model");
+    if (npx) *npx = m->dev.fft.npx;
+    if (npy) *npy = m->dev.fft.npy;
+    return BF_OK;
+}
+
+extern "C" int bf_fft_planes_batch(bf_ctx *ctx, const bf_model *m, const double *params, int B, double z_trigger,
+                                   double *out) {
+    if (!ctx || !m || !params || !out) BF_FAIL(BF_ERR_OPTIONS, "null argument");
+    if (m->dev.kind != BF_MODEL_KSPACE_FFT) BF_FAIL(BF_ERR_ANALYSIS, "bf_fft_planes_batch: not an FFT model");
+    if (B <= 0) BF_FAIL(BF_ERR_OPTIONS, "bf_fft_planes_batch: bad batch size");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const DevFft &f = m->dev.fft;
+    const int npar = m->dev.npar;
+    const size_t per_b = (size_t)2 * f.npy_pad * f.npx;  // rows are compacted to npx, all npy_pad rows copied
+    int cap = std::min(chunk_capacity(m, nullptr, 1), 4096);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t nb_params = (size_t)std::min(B, cap) * npar * sizeof(double);
+    size_t nb_out = per_b * std::min(B, cap) * sizeof(double);
+    int rc = ensure(&ctx->io, &ctx->io_bytes, al(nb_params) + al(nb_out));
+    if (rc) return rc;
+    double *d_params = (double *)ctx->io;
+    double *d_out = (double *)((char *)ctx->io + al(nb_params));
+    for (int b0 = 0; b0 < B; b0 += cap) {
+        int bc = std::min(cap, B - b0);
+        BF_CUDA_OK(cudaMemcpyAsync(d_params, params + (size_t)b0 * npar, (size_t)bc * npar * sizeof(double),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        rc = run_chunk(ctx, m, nullptr, nullptr, d_params, bc, OUT_TRANSFORM, d_out, 0, nullptr, nullptr, z_trigger, true);
+        if (rc) return rc;
+        // drop the padded rows: out[((b*2+comp)*npy + iy)*npx + ix]
+        BF_CUDA_OK(cudaMemcpy2DAsync(out + (size_t)b0 * 2 * f.npy * f.npx, (size_t)f.npy * f.npx * sizeof(double), d_out,
+                                     (size_t)f.npy_pad * f.npx * sizeof(double), (size_t)f.npy * f.npx * sizeof(double),
+                                     (size_t)bc * 2, cudaMemcpyDeviceToHost, ctx->stream));
         BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
     return BF_OK;

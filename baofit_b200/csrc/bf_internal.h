@@ -54,6 +54,24 @@ struct DevSplineSet {
     double ylo[3], yhi[3];
 };
 
+// 3-D FFT k-space model (BaoKSpaceFftCorrelationModel.cc): grid geometry and static tables
+struct DevFft {
+    int nx, ny, nz;        // cells per axis (y = line of sight)
+    int mx, my, mz;        // non-negative frequencies per axis, n/2 + 1
+    int my_pad;            // K of the plane GEMM (multiple of 16)
+    int npx, npy;          // extent of the kept (r_perp, r_par) plane
+    int npx_pad, npy_pad;  // multiples of 8 (DMMA fragment)
+    double delta, inv_delta, norm;  // cell size, 1/(nx ny nz delta^3)
+    double zcorr0, zcorr1, zcorr2;
+    int n_pk;
+    const double *lnk;      // [n_pk] ln k knots of the tabulated P(k)
+    const double *pk_coef;  // [2][n_pk-1][4] cubic coefficients in ln k (fiducial, no-wiggles)
+    double pk_k0, pk_k1;    // table range; power-law continuation outside
+    double pk_end[2][2], pk_slope[2][2];
+    const double *cosx;     // [nx] cos(2 pi t / nx)
+    const double *Cy;       // [npy_pad][my_pad] cos(2 pi (my iy mod ny) / ny), zero padded
+};
+
 // Immutable model description passed by value to kernels.
 struct DevModel {
     int kind;
@@ -82,6 +100,7 @@ struct DevModel {
     int metal_nx, metal_ny;
     double metal_x0, metal_y0, metal_inv_dx, metal_inv_dy, metal_xmax, metal_ymax;
     int dm_order;
+    DevFft fft;
 };
 
 struct bf_ctx_t;
@@ -121,6 +140,9 @@ struct bf_model {
     mutable bool cache_valid = false;
     double metal_dx = 0, metal_dy = 0;
     double zref = 0;
+    // FFT model: per-key tables T[2 comps][3 powers of mu^2][my_pad][npx_pad] (x-transformed,
+    // weights folded in) and the scratch H[2][3][my][mx] they are built from
+    mutable double *d_fft_T = nullptr, *d_fft_H = nullptr;
 };
 
 struct bf_data {

@@ -126,6 +126,45 @@ bool fast_eval_has_extras(const FastArgs &a);
 void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count);
 void launch_fold_coef(cudaStream_t s, const FoldArgs &a);
 
+// ---- 3-D FFT k-space model (kernels_fft.cu) ----
+constexpr int kFftKeyMax = 8;
+struct FftKeyState {        // what the per-key tables depend on (values of vector 0 of the chunk)
+    double snl_perp2, snl_par2;  // SigmaNL^2 of the peak component (no-wiggles: 0 unless nl-broadband)
+    double nl_tab[5];            // qnl, kv, av, bv, kp at z_eff (NonLinearCorrectionModel.cc:55-61)
+    double nl_pk_scale;
+};
+struct FftVecArgs {
+    DevModel m;
+    const double *pT;
+    int ldb, B;
+    // bin that triggers the transform (first kept bin); use_ztrig: take ztrig as given instead
+    double r0, mu0, z0, ztrig;
+    int use_ztrig;
+    double *keyflag;  // [0] = 1 if a vector's key differs from vector 0's; [1..] key of vector 0
+    double *keys;     // [kFftKeyMax-1][ldb] key of every vector (read back only when they differ)
+    double *c12;      // [2][ldb]  c1 = beta_z + beta2_z, c2 = beta_z beta2_z
+    double *cont;     // [my_pad][ldb] continuum-fitting distortion at k_par = 2 pi my / (ny delta)
+    int *status;
+};
+void launch_fft_vec(cudaStream_t s, const FftVecArgs &a);
+void launch_fft_tables(cudaStream_t s, const DevModel &m, const FftKeyState &k, double *H, double *T);
+// planes[((b*2 + comp)*npy_pad + iy)*npx_pad + ix] for the `count` columns b = cols[i] (cols null: b = i)
+void launch_fft_planes(cudaStream_t s, const DevModel &m, const double *T, const double *c12, const double *cont,
+                       int ldb, const int *cols, int count, double *planes);
+struct FftEvalArgs {
+    DevModel m;
+    const double *pT;
+    int ldb, B;
+    int npts;
+    const double *r, *mu, *z;  // [npts] data bins
+    const double *planes;
+    double *out;               // out[i*ldo + b] = xi - (dov ? dov[b*npts+i] : dsub ? dsub[i] : 0)
+    int ldo;
+    const double *dsub, *dov;
+    int *status;
+};
+void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a);
+
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);
 

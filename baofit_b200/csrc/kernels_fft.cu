@@ -1,0 +1,484 @@
+// 3-D FFT k-space model (baofit/BaoKSpaceFftCorrelationModel.cc) without a 3-D FFT.
+//
+// The reference fills an nx x ny x nz grid with D(k, mu_k) P(k) (y = line of sight), runs an
+// inverse FFT (cosmo::DistortedPowerCorrelationFft::transform, call sites :204,:212) and reads xi
+// off the (r_perp, r_par) plane through the origin (:241-243). Only that plane is ever used, and
+// D P is even in every k component, so
+//
+//   xi(ix, iy) = norm  sum_my w_my cos(2 pi my iy / ny)  sum_mx w_mx cos(2 pi mx ix / nx)  G(mx, my),
+//   G(mx, my)  = sum_mz w_mz  D P (k = |(kx,ky,kz)|, mu = ky / k)
+//
+// with w = 1 at m = 0 and at the Nyquist index, 2 in between: the z transform degenerates to a sum
+// and the other two are small dense cosine transforms. D factorises (:120-153) as
+//
+//   D = (1 + c1 mu^2 + c2 mu^4) . cont(|k_y|; kc, pc) . K(k, mu)
+//
+// where c1, c2 depend only on beta (and beta2), cont only on k_y, and K (non-linear broadening,
+// non-linear correction, P itself) only on parameters that a fit keeps fixed. Hence
+//   * per key (SigmaNL, 1+f, nlcorr, z_eff):  H_j(mx,my) = sum_mz w K P mu^2j  and its x transform
+//     T_j[my][ix]  (fft_hsum_kernel, fft_xtrans_kernel; cached across calls),
+//   * per parameter vector: one (npy x my) . (my x npx) product per component,
+//       plane_b[iy][ix] = sum_my Cy[iy][my] . cont_b[my] (T_0 + c1_b T_1 + c2_b T_2)[my][ix],
+//     on the FP64 tensor pipe (fft_plane_kernel, DMMA m8n8k4), the right operand built on the fly
+//     in shared memory,
+//   * per (bin, vector): two bicubic look-ups on the planes (fft_eval_kernel).
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace bf {
+
+namespace {
+
+// ---- tabulated P(k): cubic spline in ln k inside the table, power law outside ---------------
+__device__ __forceinline__ double fft_table_power(const DevFft &f, int which, double k) {
+    if (k < f.pk_k0) return f.pk_end[which][0] * pow(k / f.pk_k0, f.pk_slope[which][0]);
+    if (k > f.pk_k1) return f.pk_end[which][1] * pow(k / f.pk_k1, f.pk_slope[which][1]);
+    const double lk = log(k);
+    int lo = 0, hi = f.n_pk - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (f.lnk[mid] > lk) hi = mid; else lo = mid;
+    }
+    const double dx = lk - f.lnk[lo];
+    const double4 c = *reinterpret_cast<const double4 *>(f.pk_coef + ((size_t)which * (f.n_pk - 1) + lo) * 4);
+    return c.x + dx * (c.y + dx * (c.z + dx * c.w));
+}
+
+// NonLinearCorrectionModel::_evaluateKSpace, baofit/NonLinearCorrectionModel.cc:49-86
+__device__ __forceinline__ double fft_nl_correction(unsigned flags, const FftKeyState &ks, double k, double mu_k,
+                                                    double pk) {
+    if (flags & (BF_FLAG_NL_CORRECTION | BF_FLAG_FIT_NL_CORRECTION)) {
+        pk = pk * ks.nl_pk_scale;
+        double deltaSq = k * k * k * pk / (2.0 * M_PI * M_PI);
+        double growth = ks.nl_tab[0] * deltaSq;
+        double pec = pow(k / ks.nl_tab[1], ks.nl_tab[2]) * pow(fabs(mu_k), ks.nl_tab[3]);
+        double pressure = (k / ks.nl_tab[4]) * (k / ks.nl_tab[4]);
+        return exp(growth * (1.0 - pec) - pressure);
+    }
+    if (flags & BF_FLAG_NL_CORRECTION_ALT) {
+        const double knl = 6.4, pnl = 0.569, kpp = 15.3, pp = 2.01, kv0 = 1.22, pv = 1.5, kvi = 0.923, pvi = 0.451;
+        double kvel = kv0 * pow(1.0 + k / kvi, pvi);
+        double growth = pow(k / knl, pnl), pressure = pow(k / kpp, pp);
+        double pec = pow(fabs(k * mu_k) / kvel, pv);
+        return exp(growth - pressure - pec);
+    }
+    return 1.0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// per key: H[comp][j][my][mx] = sum_mz w_mz K(k,mu) P_comp(k) mu^2j
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fft_hsum_kernel(DevModel m, FftKeyState ks, double *__restrict__ H) {
+    const DevFft &f = m.fft;
+    const int mx = blockIdx.x * blockDim.x + threadIdx.x, my = blockIdx.y, comp = blockIdx.z;
+    if (mx >= f.mx) return;
+    const double two_pi = 2.0 * M_PI;
+    const double kx = mx * (two_pi / (f.nx * f.delta)), ky = my * (two_pi / (f.ny * f.delta));
+    const double dkz = two_pi / (f.nz * f.delta);
+    const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
+    // :207-210 the no-wiggles component is broadened only with nl-broadband
+    const bool broaden = comp == 0 || (m.flags & BF_FLAG_NL_BROADBAND);
+    const double sperp2 = broaden ? ks.snl_perp2 : 0.0, spar2 = broaden ? ks.snl_par2 : 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int mz = 0; mz < f.mz; ++mz) {
+        const double kz = mz * dkz;
+        const double k = sqrt(kx * kx + ky * ky + kz * kz);
+        if (k == 0.0) continue;
+        const double mu = ky / k, mu2 = mu * mu;
+        const double pn = fft_table_power(f, 1, k);
+        const double pk = comp == 0 ? fft_table_power(f, 0, k) - pn : pn;
+        const double snl2 = spar2 * mu2 + sperp2 * (1.0 - mu2);
+        const double nonlinear = exp(-0.5 * snl2 * k * k);
+        double nlc = fft_nl_correction(m.flags, ks, k, mu, pk);
+        if (cross) nlc = sqrt(nlc);
+        const double w = (mz == 0 || 2 * mz == f.nz) ? 1.0 : 2.0;
+        const double v = w * nonlinear * nlc * pk;
+        a0 += v;
+        a1 = fma(v, mu2, a1);
+        a2 = fma(v, mu2 * mu2, a2);
+    }
+    const size_t plane = (size_t)f.my * f.mx, o = (size_t)my * f.mx + mx;
+    H[(size_t)(comp * 3 + 0) * plane + o] = a0;
+    H[(size_t)(comp * 3 + 1) * plane + o] = a1;
+    H[(size_t)(comp * 3 + 2) * plane + o] = a2;
+}
+
+// T[comp*3+j][my][ix] = norm w_my sum_mx w_mx cos(2 pi mx ix / nx) H[comp*3+j][my][mx]; rows my >= My are zero
+__global__ void __launch_bounds__(128) fft_xtrans_kernel(DevModel m, const double *__restrict__ H, double *__restrict__ T) {
+    const DevFft &f = m.fft;
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, my = blockIdx.y, t = blockIdx.z;
+    if (ix >= f.npx_pad) return;
+    double s = 0.0;
+    if (my < f.my && ix < f.npx) {
+        const double *h = H + ((size_t)t * f.my + my) * f.mx;
+        for (int mx = 0; mx < f.mx; ++mx) {
+            const double w = (mx == 0 || 2 * mx == f.nx) ? 1.0 : 2.0;
+            s = fma(w * f.cosx[(int)(((long long)mx * ix) % f.nx)], h[mx], s);
+        }
+        s *= f.norm * ((my == 0 || 2 * my == f.ny) ? 1.0 : 2.0);
+    }
+    T[((size_t)t * f.my_pad + my) * f.npx_pad + ix] = s;
+}
+
+void launch_fft_tables(cudaStream_t s, const DevModel &m, const FftKeyState &k, double *H, double *T) {
+    const DevFft &f = m.fft;
+    fft_hsum_kernel<<<dim3((f.mx + 127) / 128, f.my, 2), 128, 0, s>>>(m, k, H);
+    fft_xtrans_kernel<<<dim3((f.npx_pad + 127) / 128, f.my_pad, 6), 128, 0, s>>>(m, H, T);
+}
+
+// ------------------------------------------------------------------------------------------
+// per vector: key check, tracer coefficients, continuum-fitting distortion along k_par
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fft_zcorr(const DevFft &f, double r, double mu, double z) {
+    // BaoKSpaceFftCorrelationModel.cc:165-168
+    if (f.zcorr0 > 0.0) {
+        double rpar = fabs(r * mu) / 100.;
+        z = f.zcorr0 + f.zcorr1 * rpar + f.zcorr2 * rpar * rpar;
+    }
+    return z;
+}
+
+__device__ __forceinline__ double fft_dpi(const DevModel &m, double dv, double z) {
+    // AbsCorrelationModel.cc:146-149
+    double zp1 = 1.0 + z;
+    return (dv / 100.) * zp1 / sqrt(1.0 - m.omega_matter + m.omega_matter * zp1 * zp1 * zp1);
+}
+
+__device__ __forceinline__ double fft_trigger_z(const FftVecArgs &a, const double *__restrict__ pT) {
+    if (a.use_ztrig) return a.ztrig;
+    double r = a.r0, mu = a.mu0;
+    if (a.m.idx_delta_v >= 0) velocity_shift(fft_dpi(a.m, pT[(size_t)a.m.idx_delta_v * a.ldb], a.z0), r, mu);
+    return fft_zcorr(a.m.fft, r, mu, a.z0);
+}
+
+constexpr int kFftVecRows = 16;  // k_par rows per thread of fft_vec_kernel
+
+__global__ void __launch_bounds__(128) fft_vec_kernel(FftVecArgs a) {
+    const DevModel &m = a.m;
+    const DevFft &f = m.fft;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const double *pT = a.pT + b;
+    const int ldb = a.ldb;
+    const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
+    if (blockIdx.y == 0) {
+        const double ztrig = fft_trigger_z(a, pT);
+        // key: everything the per-key tables read
+        double key[kFftKeyMax - 1], key0[kFftKeyMax - 1];
+        int n = 0;
+        const double *p0 = a.pT;
+        key[n] = pT[(size_t)m.idx_nl * ldb]; key0[n++] = p0[(size_t)m.idx_nl * ldb];
+        key[n] = pT[(size_t)(m.idx_nl + 1) * ldb]; key0[n++] = p0[(size_t)(m.idx_nl + 1) * ldb];
+        if (m.flags & BF_FLAG_FIT_NL_CORRECTION) {
+            key[n] = pT[(size_t)m.idx_nlcorr * ldb]; key0[n++] = p0[(size_t)m.idx_nlcorr * ldb];
+            key[n] = pT[(size_t)(m.idx_nlcorr + 1) * ldb]; key0[n++] = p0[(size_t)(m.idx_nlcorr + 1) * ldb];
+        } else {
+            key[n] = 0.0; key0[n++] = 0.0;
+            key[n] = 0.0; key0[n++] = 0.0;
+        }
+        key[n] = ztrig; key0[n++] = fft_trigger_z(a, p0);
+        bool differs = false;
+        for (int q = 0; q < n; ++q) differs |= key[q] != key0[q];
+        if (differs) a.keyflag[0] = 1.0;
+        if (b == 0)
+            for (int q = 0; q < n; ++q) a.keyflag[1 + q] = key0[q];
+        for (int q = 0; q < n; ++q) a.keys[(size_t)q * ldb + b] = key[q];
+        // tracer factor (1 + beta_z mu^2)(1 + beta2_z mu^2), :122-125 with :171-173
+        const double gbeta = pT[(size_t)m.idx_gamma_beta * ldb];
+        const double zf = (1.0 + ztrig) / (1.0 + m.zref);
+        const double ev = gbeta == 0.0 ? 1.0 : pow(zf, gbeta);
+        const double betaz = pT[(size_t)m.idx_beta * ldb] * ev;
+        double c1, c2;
+        if (cross) {
+            const double beta2z = pT[(size_t)m.idx_bb2 * ldb] / pT[(size_t)m.idx_bias2 * ldb] * ev;
+            c1 = betaz + beta2z;
+            c2 = betaz * beta2z;
+        } else {
+            c1 = 2.0 * betaz;
+            c2 = betaz * betaz;
+        }
+        a.c12[b] = c1;
+        a.c12[(size_t)ldb + b] = c2;
+    }
+    // continuum-fitting distortion, :128-143 (a function of k_par = |k mu_k| = |k_y| only)
+    const double kc = pT[(size_t)m.idx_cont * ldb], pc = pT[(size_t)(m.idx_cont + 1) * ldb];
+    const double dky = 2.0 * M_PI / (f.ny * f.delta);
+    const int r0 = blockIdx.y * kFftVecRows;
+    for (int my = r0; my < r0 + kFftVecRows && my < f.my_pad; ++my) {
+        double c = 0.0;
+        if (my < f.my) {
+            const double kpar = my * dky;
+            if (m.flags & BF_FLAG_NO_DISTORTION) c = 1.0;
+            else if (m.flags & BF_FLAG_DISTORTION_ALT) c = tanh(pow(kpar / kc, pc));
+            else {
+                const double k1 = pow(kpar / kc + 1.0, 0.75);
+                c = pow((k1 - 1.0 / k1) / (k1 + 1.0 / k1), pc);
+            }
+            if (cross) c = sqrt(c);
+        }
+        a.cont[(size_t)my * ldb + b] = c;
+    }
+}
+
+void launch_fft_vec(cudaStream_t s, const FftVecArgs &a) {
+    dim3 grid((a.B + 127) / 128, (a.m.fft.my_pad + kFftVecRows - 1) / kFftVecRows);
+    fft_vec_kernel<<<grid, 128, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// per vector: the y transform as a DMMA product, right operand built in shared memory
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int PV = 4;        // parameter vectors per CTA
+constexpr int PKC = 16;      // k depth (k_par rows) per pipeline stage
+constexpr int PMAXF = 9;     // at most 9 row fragments (warps) and 9 column fragments per CTA
+constexpr int PLDA = PKC + 4;
+constexpr int PLDT = PMAXF * 8;
+constexpr int PLDS = PMAXF * 8 + 4;
+constexpr int P_A = PMAXF * 8 * PLDA;  // doubles per stage
+constexpr int P_T = 3 * PKC * PLDT;
+constexpr int P_S = PV * PKC * PLDS;
+
+__device__ __forceinline__ void p_cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void p_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+}  // namespace
+
+struct FftPlaneArgs {
+    DevFft f;
+    const double *T, *c12, *cont;
+    int ldb;
+    const int *cols;  // columns of the vectors to transform (null: 0..count-1)
+    int count;
+    int wr, ncf;  // row fragments and column fragments per CTA tile (each at most 9)
+    double *planes;
+};
+
+// CTA = PV vectors x one component x one (<= 72 x 72) tile of the plane. Warp w works on vector
+// w & 3 and the three 8-row fragments (w >> 2)*3 + {0,1,2}: 3 x 9 accumulator fragments per warp,
+// 3 A and 9 B fragment loads per 27 DMMAs.
+__global__ void __launch_bounds__(PV * 3 * 32, 1) fft_plane_kernel(FftPlaneArgs a) {
+    extern __shared__ __align__(16) double psm[];
+    const DevFft &f = a.f;
+    double *As = psm;                 // [2][wr*8][PLDA]
+    double *Ts = As + 2 * P_A;        // [2][3][PKC][PLDT]
+    double *Ss = Ts + 2 * P_T;        // [2][PV][PKC][PLDS]
+    double *conts = Ss + 2 * P_S;     // [PV][my_pad]
+    __shared__ double c12s[2][PV];
+    __shared__ int colv[PV];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int l4 = lane & 3, l8 = lane >> 2;
+    const int wv = warp & (PV - 1), rf0 = (warp >> 2) * 3;
+    const int b0 = (blockIdx.x >> 1) * PV, comp = blockIdx.x & 1;
+    const int row0 = blockIdx.y * a.wr * 8, col0 = blockIdx.z * a.ncf * 8;
+    const int ncols = min(a.ncf * 8, f.npx_pad - col0);   // multiple of 8
+    const int ncf = ncols >> 3;
+    const int nrows = min(a.wr * 8, f.npy_pad - row0);
+    const int nchunks = f.my_pad / PKC;
+
+    if (tid < PV) {
+        const int i = min(b0 + tid, a.count - 1);  // slots beyond the list repeat its last vector; not stored
+        colv[tid] = a.cols ? a.cols[i] : i;
+    }
+    __syncthreads();
+    for (int i = tid; i < PV * f.my_pad; i += nthr) {
+        int v = i / f.my_pad, my = i - v * f.my_pad;
+        conts[i] = a.cont[(size_t)my * a.ldb + colv[v]];
+    }
+    if (tid < 2 * PV) c12s[tid / PV][tid % PV] = a.c12[(size_t)(tid / PV) * a.ldb + colv[tid % PV]];
+
+    auto load_stage = [&](int slot, int chunk) {
+        const int k0 = chunk * PKC;
+        double *as = As + slot * P_A, *ts = Ts + slot * P_T;
+        // Cy rows of this tile: [nrows][PKC]
+        for (int c = tid; c < nrows * (PKC / 2); c += nthr) {
+            int row = c / (PKC / 2), ch = c % (PKC / 2);
+            p_cp_async16(as + row * PLDA + ch * 2, f.Cy + (size_t)(row0 + row) * f.my_pad + k0 + ch * 2);
+        }
+        // T_j rows: [3][PKC][ncols]
+        const int per_row = ncols / 2;
+        for (int c = tid; c < 3 * PKC * per_row; c += nthr) {
+            int j = c / (PKC * per_row), rem = c - j * PKC * per_row, kr = rem / per_row, ch = rem - kr * per_row;
+            p_cp_async16(ts + (j * PKC + kr) * PLDT + ch * 2,
+                         a.T + ((size_t)(comp * 3 + j) * f.my_pad + k0 + kr) * f.npx_pad + col0 + ch * 2);
+        }
+    };
+
+    double acc[3][PMAXF][2];
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < PMAXF; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    // rows beyond the tile read row 0 of the stage (finite values), their results are dropped
+    int arow[3];
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi) arow[mi] = (rf0 + mi) * 8 < nrows ? (rf0 + mi) * 8 + l8 : 0;
+    const bool active = rf0 * 8 < nrows;
+
+    load_stage(0, 0);
+    asm volatile("cp.async.commit_group;\n" ::);
+    for (int t = 0; t < nchunks; ++t) {
+        const int slot = t & 1;
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();  // stage t landed; everyone is done with the buffers of chunk t-1
+        if (t + 1 < nchunks) load_stage(slot ^ 1, t + 1);
+        asm volatile("cp.async.commit_group;\n" ::);
+        // right operand of this chunk: S_v[kr][ix] = cont_v[k0+kr] (T0 + c1_v T1 + c2_v T2)[kr][ix]
+        {
+            const double *ts = Ts + slot * P_T;
+            double *ss = Ss + slot * P_S;
+            const int k0 = t * PKC;
+            for (int e = tid; e < PKC * ncols; e += nthr) {
+                int kr = e / ncols, ix = e - kr * ncols;
+                double t0 = ts[kr * PLDT + ix], t1 = ts[(PKC + kr) * PLDT + ix], t2 = ts[(2 * PKC + kr) * PLDT + ix];
+#pragma unroll
+                for (int v = 0; v < PV; ++v)
+                    ss[(v * PKC + kr) * PLDS + ix] = conts[v * f.my_pad + k0 + kr] * fma(c12s[1][v], t2, fma(c12s[0][v], t1, t0));
+            }
+        }
+        __syncthreads();
+        if (active) {
+            const double *as = As + slot * P_A + l4;
+            const double *ss = Ss + slot * P_S + (wv * PKC + l4) * PLDS + l8;
+#pragma unroll
+            for (int kk = 0; kk < PKC; kk += 4) {
+                double af[3];
+#pragma unroll
+                for (int mi = 0; mi < 3; ++mi) af[mi] = as[arow[mi] * PLDA + kk];
+#pragma unroll
+                for (int ni = 0; ni < PMAXF; ++ni)
+                    if (ni < ncf) {
+                        const double bf = ss[kk * PLDS + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < 3; ++mi) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
+                    }
+            }
+        }
+    }
+    if (active && b0 + wv < a.count) {
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi) {
+            if ((rf0 + mi) * 8 >= nrows) continue;
+            const int row = row0 + (rf0 + mi) * 8 + l8;
+            double *dst = a.planes + (((size_t)colv[wv] * 2 + comp) * f.npy_pad + row) * f.npx_pad + col0 + 2 * l4;
+#pragma unroll
+            for (int ni = 0; ni < PMAXF; ++ni)
+                if (ni < ncf) *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    }
+}
+
+void launch_fft_planes(cudaStream_t s, const DevModel &m, const double *T, const double *c12, const double *cont,
+                       int ldb, const int *cols, int count, double *planes) {
+    const DevFft &f = m.fft;
+    FftPlaneArgs a;
+    a.f = f; a.T = T; a.c12 = c12; a.cont = cont; a.ldb = ldb; a.cols = cols; a.count = count; a.planes = planes;
+    const int nrf = f.npy_pad / 8, ncfr = f.npx_pad / 8;
+    const int rtiles = (nrf + PMAXF - 1) / PMAXF, ctiles = (ncfr + PMAXF - 1) / PMAXF;
+    a.wr = (nrf + rtiles - 1) / rtiles;
+    a.ncf = (ncfr + ctiles - 1) / ctiles;
+    const size_t smem = (size_t)(2 * P_A + 2 * P_T + 2 * P_S + PV * f.my_pad) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fft_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr = true;
+    }
+    dim3 grid(2 * ((count + PV - 1) / PV), rtiles, ctiles);
+    const int row_groups = (a.wr + 2) / 3;
+    fft_plane_kernel<<<grid, PV * row_groups * 32, smem, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// per (bin, vector): BaoKSpaceFftCorrelationModel::_evaluate, :155-250
+// ------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ double catmull(double pm1, double p0, double p1, double p2, double t) {
+    return p0 + 0.5 * t * (p1 - pm1 + t * (2.0 * pm1 - 5.0 * p0 + 4.0 * p1 - p2 + t * (3.0 * (p0 - p1) + p2 - pm1)));
+}
+
+// bicubic (Catmull-Rom) interpolation on an even plane; false if the stencil leaves the plane
+__device__ __forceinline__ bool plane_lookup(const DevFft &f, const double *__restrict__ pl, double r, double mu,
+                                             double &out) {
+    const double x = r * sqrt(1.0 - mu * mu) * f.inv_delta, y = fabs(r * mu) * f.inv_delta;
+    const int ix = (int)floor(x), iy = (int)floor(y);
+    if (ix + 2 > f.npx - 1 || iy + 2 > f.npy - 1 || !(x >= 0.0)) { out = nan(""); return false; }
+    const double tx = x - ix, ty = y - iy;
+    double col[4];
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq) {
+        const double *row = pl + (size_t)abs(iy - 1 + bq) * f.npx_pad;
+        col[bq] = catmull(__ldg(row + abs(ix - 1)), __ldg(row + ix), __ldg(row + ix + 1), __ldg(row + ix + 2), tx);
+    }
+    out = catmull(col[0], col[1], col[2], col[3], ty);
+    return true;
+}
+constexpr int kEvalBinsPerBlock = 512;  // 64 bin lanes x 8 iterations
+}  // namespace
+
+__global__ void __launch_bounds__(256) fft_eval_kernel(FftEvalArgs a) {
+    const DevModel &m = a.m;
+    const DevFft &f = m.fft;
+    // 4 consecutive vectors x 64 bins per pass: the 4 lanes of a bin write one 32-byte sector
+    const int b = blockIdx.x * 4 + (threadIdx.x & 3);
+    const int bin_lane = threadIdx.x >> 2;
+    if (b >= a.B) return;
+    const int ldb = a.ldb;
+    const double *pT = a.pT + b;
+    const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
+    const double beta = pT[(size_t)m.idx_beta * ldb];
+    const double bias = pT[(size_t)m.idx_bb * ldb] / (1.0 + beta);
+    const double biasSq = cross ? bias * pT[(size_t)m.idx_bias2 * ldb] : bias * bias;
+    const double gammaBias = pT[(size_t)m.idx_gamma_bias * ldb];
+    const double dv = cross ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    const double ampl = pT[(size_t)m.idx_bao * ldb], s_iso = pT[(size_t)(m.idx_bao + 1) * ldb];
+    const double s_par = pT[(size_t)(m.idx_bao + 2) * ldb], s_perp = pT[(size_t)(m.idx_bao + 3) * ldb];
+    const double gamma_scale = pT[(size_t)(m.idx_bao + 4) * ldb];
+    const double *pl_peak = a.planes + (size_t)b * 2 * f.npy_pad * f.npx_pad;
+    const double *pl_smooth = pl_peak + (size_t)f.npy_pad * f.npx_pad;
+    int st = 0;
+    const int i0 = blockIdx.y * kEvalBinsPerBlock;
+    for (int i = i0 + bin_lane; i < min(i0 + kEvalBinsPerBlock, a.npts); i += 64) {
+        double r = a.r[i], mu = a.mu[i], z = a.z[i];
+        if (cross) velocity_shift(fft_dpi(m, dv, z), r, mu);  // AbsCorrelationModel.cc:25
+        z = fft_zcorr(f, r, mu, z);
+        const double zf = (1.0 + z) / (1.0 + m.zref);
+        const double evb = gammaBias == 0.0 ? 1.0 : pow(zf, gammaBias);
+        const double evs = gamma_scale == 0.0 ? 1.0 : pow(zf, gamma_scale);
+        double rBAO, muBAO;
+        if (m.flags & BF_FLAG_ANISOTROPIC) {
+            const double apar = s_par * evs, aperp = s_perp * evs, musq = mu * mu;
+            const double scale = sqrt(apar * apar * musq + aperp * aperp * (1.0 - musq));
+            rBAO = r * scale;
+            muBAO = apar * mu / scale;
+        } else {
+            rBAO = r * (s_iso * evs);
+            muBAO = mu;
+        }
+        double peak, smooth;
+        bool ok = plane_lookup(f, pl_peak, rBAO, muBAO, peak);
+        if (m.flags & BF_FLAG_DECOUPLED) ok &= plane_lookup(f, pl_smooth, r, mu, smooth);
+        else ok &= plane_lookup(f, pl_smooth, rBAO, muBAO, smooth);
+        if (!ok) st |= BF_STATUS_FFT_RANGE;
+        double xi = (biasSq * evb) * (ampl * peak + smooth);
+        if (m.bb[BF_BB_DIST_MUL].enabled) xi *= 1.0 + broadband_eval(m.bb[BF_BB_DIST_MUL], pT, ldb, r, mu, z);
+        if (m.bb[BF_BB_DIST_ADD].enabled) xi += broadband_eval(m.bb[BF_BB_DIST_ADD], pT, ldb, r, mu, z) * evb;
+        const double sub = a.dov ? a.dov[(size_t)b * a.npts + i] : (a.dsub ? a.dsub[i] : 0.0);
+        a.out[(size_t)i * a.ldo + b] = xi - sub;
+    }
+    if (st) atomicOr(a.status + b, st);
+}
+
+void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a) {
+    dim3 grid((a.B + 3) / 4, (a.npts + kEvalBinsPerBlock - 1) / kEvalBinsPerBlock);
+    fft_eval_kernel<<<grid, 256, 0, s>>>(a);
+}
+
+}  // namespace bf

@@ -25,7 +25,7 @@ FLAGS = {
 }
 BF_METAL_NONE, BF_METAL_AUTO_TABLE, BF_METAL_CROSS_BICUBIC, BF_METAL_TOY = 0, 1, 2, 3
 BF_BB_DIST_ADD, BF_BB_DIST_MUL, BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL = 0, 1, 2, 3
-BF_STATUS_DILATION_MIN, BF_STATUS_DILATION_MAX = 1, 2
+BF_STATUS_DILATION_MIN, BF_STATUS_DILATION_MAX, BF_STATUS_FFT_RANGE = 1, 2, 4
 
 
 class BroadbandSpec(C.Structure):
@@ -79,6 +79,10 @@ class ModelDesc(C.Structure):
         ("metal_dy", C.c_double),
         ("metal_cross", c_double_p),
         ("dist_matrix_order", C.c_int), ("dist_matrix", c_double_p),
+        ("fft_spacing", C.c_double),
+        ("fft_nx", C.c_int), ("fft_ny", C.c_int), ("fft_nz", C.c_int),
+        ("fft_rmax", C.c_double),
+        ("zcorr0", C.c_double), ("zcorr1", C.c_double), ("zcorr2", C.c_double),
     ]
 
 

@@ -388,6 +388,51 @@ def kspace_model(pk_fid, pk_nw, rmin, rmax, zref=2.25, omega_matter=0.27, dilmin
     return m
 
 
+def fft_model(pk_fid, pk_nw, spacing=4., nx=400, ny=0, nz=0, rmax=180., dilmax=1.5, fft_rmax=0.,
+              zref=2.25, omega_matter=0.27, zcorr=(0., 0., 0.), sigma8=0.8338, anisotropic=True,
+              decoupled=True, cross=False, nl_broadband=False, nl_correction=False,
+              fit_nl_correction=False, nl_correction_alt=False, distortion_alt=False,
+              no_distortion=False, dist_add="", dist_mul="", dist_r0=100.):
+    """BaoKSpaceFftCorrelationModel parameter layout (baofit/BaoKSpaceFftCorrelationModel.cc:36-113;
+    ngridy / ngridz default to ngridx, src/baofit.cc:398-399)."""
+    k = D.new_model_desc()
+    d = k.desc
+    d.kind, d.zref, d.omega_matter = D.BF_MODEL_KSPACE_FFT, zref, omega_matter
+    flags = 0
+    loc = locals()
+    for name in ("anisotropic", "decoupled", "nl_broadband", "nl_correction", "fit_nl_correction",
+                 "nl_correction_alt", "distortion_alt", "no_distortion"):
+        if loc[name]:
+            flags |= D.FLAGS[name]
+    if cross:
+        flags |= D.FLAGS["cross_correlation"]
+    d.flags = flags
+    d.fft_spacing, d.fft_nx, d.fft_ny, d.fft_nz = spacing, nx, ny or nx, nz or ny or nx
+    d.rmax, d.dilmax, d.fft_rmax, d.sigma8 = rmax, dilmax, fft_rmax, sigma8
+    d.zcorr0, d.zcorr1, d.zcorr2 = zcorr
+    names, values, errors = [], [], []
+
+    def add(n, v, e):
+        names.append(n); values.append(float(v)); errors.append(float(e))
+        return len(names) - 1
+
+    _linear_bias(d, names, values, errors, cross, False)
+    d.idx_nl = add("SigmaNL-perp", 3.26, 0.3); add("1+f", 2, 0.1)
+    d.idx_cont = add("cont-kc", 0.02, 0.002); add("cont-pc", 1, 0.1)
+    d.idx_bao = add("BAO amplitude", 1, 0.15); add("BAO alpha-iso", 1, 0.02)
+    add("BAO alpha-parallel", 1, 0.1); add("BAO alpha-perp", 1, 0.1); add("gamma-scale", 0, 0.5)
+    assert np.array_equal(pk_fid[0], pk_nw[0])
+    k.f64("pk_k", pk_fid[0]), k.f64("pk_fid", pk_fid[1]), k.f64("pk_nw", pk_nw[1])
+    d.n_pk = len(pk_fid[0])
+    if dist_add:
+        d.bb[D.BF_BB_DIST_ADD] = _add_broadband(names, values, errors, dist_add, "dist add", dist_r0, zref)
+    if dist_mul:
+        d.bb[D.BF_BB_DIST_MUL] = _add_broadband(names, values, errors, dist_mul, "dist mul", dist_r0, zref)
+    if fit_nl_correction:  # constructed last, :111-112
+        d.idx_nlcorr = add("nlcorr qnl", 0.867, 0.08); add("nlcorr kp", 19.4, 1)
+    return Model(k, names, values, errors)
+
+
 # --------------------------------------------------------------------------------------------
 # ready-made workloads
 # --------------------------------------------------------------------------------------------
@@ -538,6 +583,42 @@ def dr11_auto_kspace(root=None, golden=GOLDEN, seed=1966):
     r, mu, z = grid_coordinates(a1, a2, a3, "comoving-cartesian")
     keep = final_cuts(r, mu, z, np.ones(len(r), dtype=bool), rmin=40, rmax=180)
     return m, (r, mu, z, keep)
+
+
+def dr11_auto_fft(root=None, golden=GOLDEN, ngrid=400, spacing=4., seed=1966, nbins=50, **kw):
+    """config/BOSSDR11LyaF_fft.ini: BaoKSpaceFftCorrelationModel, Lya auto-correlation, 3-D grid of
+    ngrid^3 cells of 4 Mpc/h, effective-redshift correction and non-linear correction on; 50x50
+    cartesian data grid at z = 2.34, r in [40,180] (N_data = 1515). The covariance blob is missing
+    from the reference, so the data vector and covariance are synthetic."""
+    root = root or os.path.join(golden, "models")
+    pk_fid = load_table(os.path.join(root, "DR9LyaMocksLCDM_matterpower.dat"))
+    pk_nw = load_table(os.path.join(root, "DR9LyaMocksLCDMSB_matterpower.dat"))
+    args = dict(spacing=spacing, nx=ngrid, rmax=180., dilmax=1.5, zref=2.3,
+                zcorr=(2.32454, 5.1141e-3, 8.00906e-3), sigma8=0.788, nl_correction=True)
+    args.update(kw)
+    m = fft_model(pk_fid, pk_nw, **args)
+    m.configure("value[beta]=1.4; value[(1+beta)*bias]=-0.351; fix[BAO amplitude]=1; fix[BAO alpha-iso];"
+                "value[BAO alpha-p*]=1; fix[gamma-bias]=3.8; fix[gamma-beta]=0; fix[gamma-scale]=0;"
+                "fix[1+f]=1.966; fix[SigmaNL-perp]=3.26; value[cont-kc]=0.005; fix[cont-pc]=3")
+    a1 = parse_binning("[0:200]*%d" % nbins)
+    a2, a3 = a1.copy(), parse_binning("{2.34}")
+    r, mu, z = grid_coordinates(a1, a2, a3, "comoving-cartesian")
+    keep = final_cuts(r, mu, z, np.ones(len(r), dtype=bool), rmin=40, rmax=180)
+    return m, (r, mu, z, keep)
+
+
+def synthetic_dataset(model, coords, predict, seed=1966, cov_seed=1):
+    """d = model(p0) + L g with the synthetic covariance of SURVEY.md section 8d; ``predict`` maps
+    (Model, Data, params[1][npar]) to the prediction [n_data] (the oracle in tests, the CUDA
+    library in bench.py)."""
+    r, mu, z, keep = coords
+    n = len(keep)
+    probe = make_data(r, mu, z, keep, np.zeros(n), np.eye(n))
+    xi0 = np.asarray(predict(model, probe, model.values[None, :])).reshape(n)
+    cov = synthetic_cov(xi0, seed=cov_seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d = xi0 + np.linalg.cholesky(cov) @ rng.standard_normal(n)
+    return make_data(r, mu, z, keep, d, cov), xi0
 
 
 def make_golden_tree(root):

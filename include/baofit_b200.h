@@ -41,11 +41,12 @@ extern "C" {
 #define BF_STATUS_OK 0
 #define BF_STATUS_DILATION_MIN 1 /* "hit min dilation limit", BaoKSpaceCorrelationModel.cc:420 */
 #define BF_STATUS_DILATION_MAX 2 /* "hit max dilation limit", BaoKSpaceCorrelationModel.cc:424 */
+#define BF_STATUS_FFT_RANGE 4    /* FFT model: a dilated bin falls outside the tabulated (r_perp, r_par) plane (fft_rmax) */
 
 /* model kinds */
 #define BF_MODEL_RSPACE 0     /* baofit/BaoCorrelationModel.cc          */
 #define BF_MODEL_KSPACE 1     /* baofit/BaoKSpaceCorrelationModel.cc    */
-#define BF_MODEL_KSPACE_FFT 2 /* baofit/BaoKSpaceFftCorrelationModel.cc (not built yet) */
+#define BF_MODEL_KSPACE_FFT 2 /* baofit/BaoKSpaceFftCorrelationModel.cc       */
 
 /* option flags (names follow the reference's command-line options, src/baofit.cc:46-178) */
 #define BF_FLAG_CROSS_CORRELATION (1u << 0)
@@ -159,6 +160,17 @@ typedef struct bf_model_desc {
     /* distortion matrix (DistortionMatrix.cc:22-73): dense row-major order x order, or NULL */
     int dist_matrix_order;
     const double *dist_matrix;
+
+    /* 3-D FFT k-space model (BaoKSpaceFftCorrelationModel.cc:21-27,92-97; options gridspacing,
+     * ngridx/y/z, zcorr0/1/2 of src/baofit.cc:76-84,102-106). The y axis is the line of sight.
+     * xi is tabulated on the (r_perp, r_par) plane through the origin of the periodic box and
+     * interpolated bicubically (cosmo::DistortedPowerCorrelationFft::getCorrelation call sites
+     * :241-243); the plane is kept out to fft_rmax in both directions, a dilated bin beyond it
+     * flags BF_STATUS_FFT_RANGE. fft_rmax <= 0 selects rmax * dilmax.                        */
+    double fft_spacing;
+    int fft_nx, fft_ny, fft_nz;
+    double fft_rmax;
+    double zcorr0, zcorr1, zcorr2; /* effective redshift of a bin, :165-168 (zcorr0 <= 0: off) */
 } bf_model_desc;
 
 typedef struct bf_data_desc {
@@ -200,8 +212,9 @@ int bf_ctx_set_profiling(bf_ctx *ctx, int enable);
 int bf_ctx_get_profile(bf_ctx *ctx, int max_entries, const char **names, double *ms_total,
                        long long *launches);
 
-/* Replaces the constructors of BaoCorrelationModel (BaoCorrelationModel.cc:18-86) and
- * BaoKSpaceCorrelationModel (BaoKSpaceCorrelationModel.cc:26-211): tables are copied, spline
+/* Replaces the constructors of BaoCorrelationModel (BaoCorrelationModel.cc:18-86),
+ * BaoKSpaceCorrelationModel (BaoKSpaceCorrelationModel.cc:26-211) and
+ * BaoKSpaceFftCorrelationModel (BaoKSpaceFftCorrelationModel.cc:21-113): tables are copied, spline
  * coefficients / Hankel weights are computed once and uploaded. */
 int bf_model_create(bf_ctx *ctx, const bf_model_desc *desc, bf_model **out);
 int bf_model_destroy(bf_model *model);
@@ -249,6 +262,14 @@ int bf_eval_undistorted_batch(bf_ctx *ctx, const bf_model *model, const bf_data 
  * comp 0 = peak, 1 = no-wiggles; r_j = bf_model_transform_r0 + j*bf_model_transform_dr. */
 int bf_transform_batch(bf_ctx *ctx, const bf_model *model, const double *params, int B,
                        double z_trigger, double *out, int ldb);
+/* FFT k-space model: the two planes xi_comp(ix*spacing, iy*spacing) that the 3-D transform of
+ * parameter vector b leaves on the z = 0 plane of the box (cosmo::DistortedPowerCorrelationFft::
+ * transform call sites BaoKSpaceFftCorrelationModel.cc:204,212). out[((b*2 + comp)*npy + iy)*npx + ix],
+ * comp 0 = peak, 1 = no-wiggles; npx/npy from bf_model_fft_plane_dims. z_trigger is the redshift of
+ * the bin that triggers the transform (after the zcorr correction, if any). Host buffers. */
+int bf_fft_planes_batch(bf_ctx *ctx, const bf_model *model, const double *params, int B,
+                        double z_trigger, double *out);
+int bf_model_fft_plane_dims(const bf_model *model, int *npx, int *npy);
 int bf_model_transform_nr(const bf_model *model);
 double bf_model_transform_r0(const bf_model *model);
 double bf_model_transform_dr(const bf_model *model);

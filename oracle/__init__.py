@@ -66,6 +66,10 @@ def lib():
         L.orc_transform_dr.argtypes = [C.c_void_p]
         L.orc_hankel_table.restype = C.c_double
         L.orc_hankel_table.argtypes = [C.c_int, c_double_p, c_double_p, C.c_int, C.c_double]
+        L.orc_fft_distortion_power.restype = C.c_double
+        L.orc_fft_distortion_power.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_int, C.c_double, C.c_double]
+        L.orc_fft_plane_dims.argtypes = [C.c_void_p, c_int_p, c_int_p]
+        L.orc_fft_planes.argtypes = [C.c_void_p, c_double_p, C.c_double, c_double_p]
         _LIB = L
     return _LIB
 
@@ -107,6 +111,22 @@ class OracleModel:
             raise RuntimeError(lib().orc_last_error().decode())
         r = lib().orc_transform_r0(self.h) + lib().orc_transform_dr(self.h) * np.arange(nr)
         return r, out
+
+    def fft_distortion_power(self, params, z, component, k, muk):
+        """D(k, mu_k) P_comp(k) of the FFT model (BaoKSpaceFftCorrelationModel.cc:120-153)."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        return lib().orc_fft_distortion_power(self.h, _dp(p), z, component, k, muk)
+
+    def fft_planes(self, params, z_trigger):
+        """xi_comp on the z = 0 plane of the FFT box: array [comp][iy][ix]."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        npx, npy = C.c_int(0), C.c_int(0)
+        if lib().orc_fft_plane_dims(self.h, C.byref(npx), C.byref(npy)):
+            raise RuntimeError("not an FFT model")
+        out = np.zeros((2, npy.value, npx.value))
+        if lib().orc_fft_planes(self.h, _dp(p), z_trigger, _dp(out)):
+            raise RuntimeError(lib().orc_last_error().decode())
+        return out
 
     def kspace_distortion(self, params, z, component, k, muk):
         p = np.ascontiguousarray(params, dtype=np.float64)

@@ -159,6 +159,15 @@ struct orc_model {
     double *tab_y[2][3], *tab_c[2][3];
     double *last_params;
     double last_ztrig;
+    /* 3-D FFT model (BaoKSpaceFftCorrelationModel.cc) */
+    int fnx, fny, fnz;      /* grid sizes, y = line of sight */
+    int fmx, fmy, fmz;      /* number of non-negative frequencies per axis */
+    int fnpx, fnpy;         /* extent of the tabulated plane */
+    double fdelta;
+    double pk_slope[2][2];  /* power-law extrapolation exponents [fid,nw][below,above] */
+    double *fplane[2];      /* xi_comp(ix*delta, iy*delta), [iy*fnpx + ix] */
+    double fkey[16];
+    int fhave;
 };
 
 struct orc_data {
@@ -262,6 +271,45 @@ static int kspace_setup(orc_model *m) {
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* 3-D FFT model set-up (BaoKSpaceFftCorrelationModel.cc:64-97)                          */
+/* ------------------------------------------------------------------------------------ */
+
+static double extrap_slope(double k0, double p0, double k1, double p1) {
+    /* cosmo::createTabulatedPower(..., extrapolateBelow, extrapolateAbove, ...) continues the table as
+     * a power law through its last two points (UNVERIFIED dep); a sign change or a zero leaves a
+     * constant */
+    if (p0 * p1 <= 0) return 0;
+    return log(p1 / p0) / log(k1 / k0);
+}
+
+static int fft_setup(orc_model *m) {
+    const bf_model_desc *d = &m->d;
+    int n = d->n_pk, i, c;
+    if (n < 4 || !d->pk_k || !d->pk_fid || !d->pk_nw) { set_err("orc: FFT model needs P(k) tables"); return -1; }
+    if (!(d->fft_spacing > 0) || d->fft_nx < 4 || d->fft_ny < 4 || d->fft_nz < 4) { set_err("orc: bad FFT grid"); return -1; }
+    m->n_pk = n;
+    m->pk_lnk = (double *)malloc(sizeof(double) * n);
+    for (i = 0; i < n; ++i) m->pk_lnk[i] = log(d->pk_k[i]);
+    spline_make(&m->pk_fid, n, m->pk_lnk, d->pk_fid);
+    spline_make(&m->pk_nw, n, m->pk_lnk, d->pk_nw);
+    for (c = 0; c < 2; ++c) {
+        const double *pk = c == 0 ? d->pk_fid : d->pk_nw;
+        m->pk_slope[c][0] = extrap_slope(d->pk_k[0], pk[0], d->pk_k[1], pk[1]);
+        m->pk_slope[c][1] = extrap_slope(d->pk_k[n - 2], pk[n - 2], d->pk_k[n - 1], pk[n - 1]);
+    }
+    m->fnx = d->fft_nx; m->fny = d->fft_ny; m->fnz = d->fft_nz;
+    m->fmx = m->fnx / 2 + 1; m->fmy = m->fny / 2 + 1; m->fmz = m->fnz / 2 + 1;
+    m->fdelta = d->fft_spacing;
+    double rmax = d->fft_rmax > 0 ? d->fft_rmax : d->rmax * d->dilmax;
+    int np = (int)floor(rmax / m->fdelta) + 3;
+    m->fnpx = np < m->fmx ? np : m->fmx;
+    m->fnpy = np < m->fmy ? np : m->fmy;
+    for (c = 0; c < 2; ++c) m->fplane[c] = (double *)calloc((size_t)m->fnpx * m->fnpy, sizeof(double));
+    m->fhave = 0;
+    return 0;
+}
+
 orc_model *orc_model_create(const bf_model_desc *desc) {
     orc_model *m = (orc_model *)calloc(1, sizeof(orc_model));
     m->d = *desc;
@@ -276,6 +324,8 @@ orc_model *orc_model_create(const bf_model_desc *desc) {
         spline_make(&m->nw[2], d->n_nw, d->nw_r, d->nw_xi4);
     } else if (d->kind == BF_MODEL_KSPACE) {
         if (kspace_setup(m)) { free(m); return NULL; }
+    } else if (d->kind == BF_MODEL_KSPACE_FFT) {
+        if (fft_setup(m)) { free(m); return NULL; }
     } else {
         set_err("orc: model kind not restated");
         free(m);
@@ -305,6 +355,10 @@ void orc_model_destroy(orc_model *m) {
         free(m->kc); free(m->kf); free(m->pf_pk); free(m->pf_nw); free(m->tab_r);
         for (i = 0; i < 2; ++i) for (s = 0; s < 3; ++s) { free(m->tab_y[i][s]); free(m->tab_c[i][s]); }
         free(m->last_params);
+    }
+    if (m->d.kind == BF_MODEL_KSPACE_FFT) {
+        free(m->pk_lnk); spline_free(&m->pk_fid); spline_free(&m->pk_nw);
+        free(m->fplane[0]); free(m->fplane[1]);
     }
     free(m->metal_p1); free(m->metal_p2); free(m->metal_zgrid); free(m->metal_auto);
     free(m->metal_cross); free(m->dist_matrix);
@@ -952,6 +1006,235 @@ static double kspace_point(const orc_model *m, const double *p, const internal_t
     return xi;
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* BaoKSpaceFftCorrelationModel (baofit/BaoKSpaceFftCorrelationModel.cc)                 */
+/* ------------------------------------------------------------------------------------ */
+
+/* tabulated P(k) of one input table (0 fiducial, 1 no-wiggles): cubic spline in ln k inside the
+ * table, power law outside */
+static double fft_table_power(const orc_model *m, int which, double k) {
+    const bf_model_desc *d = &m->d;
+    const double *pk = which == 0 ? d->pk_fid : d->pk_nw;
+    int n = m->n_pk;
+    if (k < d->pk_k[0]) return pk[0] * pow(k / d->pk_k[0], m->pk_slope[which][0]);
+    if (k > d->pk_k[n - 1]) return pk[n - 1] * pow(k / d->pk_k[n - 1], m->pk_slope[which][1]);
+    return spline_eval(which == 0 ? &m->pk_fid : &m->pk_nw, log(k));
+}
+static double fft_power(const orc_model *m, int comp, double k) {
+    /* :81 peak = fid - nw (createDelta), smooth = nw */
+    double pn = fft_table_power(m, 1, k);
+    return comp == 0 ? fft_table_power(m, 0, k) - pn : pn;
+}
+
+static double fft_distortion(const orc_model *m, const double *p, double k, double mu_k, double pk) {
+    /* _evaluateKSpaceDistortion, BaoKSpaceFftCorrelationModel.cc:120-153 */
+    const bf_model_desc *d = &m->d;
+    int cross = (d->flags & BF_FLAG_CROSS_CORRELATION) != 0;
+    double mu2 = mu_k * mu_k;
+    double tracer1 = 1 + m->betaz * mu2;
+    double tracer2 = cross ? 1 + m->beta2z * mu2 : tracer1;
+    double linear = tracer1 * tracer2;
+    double snl2 = m->snl_par2 * mu2 + m->snl_perp2 * (1 - mu2);
+    double nonlinear = exp(-0.5 * snl2 * k * k);
+    double kpar = fabs(k * mu_k);
+    double kc = p[d->idx_cont], pc = p[d->idx_cont + 1];
+    double contdistortion;
+    if (d->flags & BF_FLAG_NO_DISTORTION) contdistortion = 1;
+    else if (d->flags & BF_FLAG_DISTORTION_ALT) contdistortion = tanh(pow(kpar / kc, pc));
+    else {
+        double k1 = pow(kpar / kc + 1, 0.75);
+        contdistortion = pow((k1 - 1 / k1) / (k1 + 1 / k1), pc);
+    }
+    double nonlinearcorr = nl_correction(m, p, k, mu_k, pk, m->zeff);
+    if (cross) {
+        contdistortion = sqrt(contdistortion);
+        nonlinearcorr = sqrt(nonlinearcorr);
+    }
+    return contdistortion * nonlinear * nonlinearcorr * linear;
+}
+
+/* the members _evaluate sets before a transform (:178-188,:200-211), for a transform triggered at z */
+static void fft_set_state(orc_model *m, const double *p, double z, int component) {
+    const bf_model_desc *d = &m->d;
+    double beta = p[d->idx_beta], gammaBeta = p[d->idx_gamma_beta];
+    m->zeff = z; /* :169, the FFT model has no zeff option */
+    m->betaz = orc_redshift_evolution(beta, gammaBeta, z, d->zref);
+    m->beta2z = 0;
+    if (d->flags & BF_FLAG_CROSS_CORRELATION)
+        m->beta2z = orc_redshift_evolution(p[d->idx_bb2] / p[d->idx_bias2], gammaBeta, z, d->zref);
+    double snlPerp = p[d->idx_nl], snlPar = snlPerp * p[d->idx_nl + 1];
+    m->snl_perp2 = snlPerp * snlPerp;
+    m->snl_par2 = snlPar * snlPar;
+    if (component == 1 && !(d->flags & BF_FLAG_NL_BROADBAND)) m->snl_perp2 = m->snl_par2 = 0; /* :207-210 */
+}
+
+double orc_fft_distortion_power(orc_model *m, const double *params, double z, int component, double k, double muk) {
+    if (k <= 0) return 0;
+    fft_set_state(m, params, z, component);
+    double pk = fft_power(m, component, k);
+    return fft_distortion(m, params, k, muk, pk) * pk;
+}
+
+/* cosmo::DistortedPowerCorrelationFft::transform restated (UNVERIFIED dep, see oracle.h): the box has
+ * nx x ny x nz cells of side delta, y is the line of sight, the k grid is the FFT grid of the box,
+ *   xi(x) = 1/(nx ny nz delta^3) sum_k D(k, k_y/k) P(k) exp(i k.x),     the k = 0 term dropped,
+ * and only the z = 0 plane is kept. D P is even in every k component, so the plane is the cosine
+ * series over the non-negative frequencies with weight 2 on the interior ones. */
+static void fft_transform_component(orc_model *m, const double *p, double z, int comp, double *plane) {
+    const int nx = m->fnx, ny = m->fny, nz = m->fnz, Mx = m->fmx, My = m->fmy, Mz = m->fmz;
+    const double dkx = 2 * M_PI / (nx * m->fdelta), dky = 2 * M_PI / (ny * m->fdelta), dkz = 2 * M_PI / (nz * m->fdelta);
+    double *G = (double *)calloc((size_t)My * Mx, sizeof(double));
+    double *X = (double *)calloc((size_t)My * m->fnpx, sizeof(double));
+    int my;
+    fft_set_state(m, p, z, comp);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (my = 0; my < My; ++my) {
+        int mx, mz, ix;
+        double ky = my * dky;
+        for (mx = 0; mx < Mx; ++mx) {
+            double kx = mx * dkx, s = 0;
+            for (mz = 0; mz < Mz; ++mz) {
+                double kz = mz * dkz, k = sqrt(kx * kx + ky * ky + kz * kz);
+                if (k == 0) continue;
+                double w = (mz == 0 || 2 * mz == nz) ? 1.0 : 2.0;
+                double pk = fft_power(m, comp, k);
+                s += w * fft_distortion(m, p, k, ky / k, pk) * pk;
+            }
+            G[(size_t)my * Mx + mx] = s;
+        }
+        for (ix = 0; ix < m->fnpx; ++ix) {
+            double s = 0;
+            for (mx = 0; mx < Mx; ++mx) {
+                double w = (mx == 0 || 2 * mx == nx) ? 1.0 : 2.0;
+                s += w * cos(2 * M_PI * (double)(((long long)mx * ix) % nx) / nx) * G[(size_t)my * Mx + mx];
+            }
+            X[(size_t)my * m->fnpx + ix] = s;
+        }
+    }
+    double norm = 1.0 / ((double)nx * ny * nz * m->fdelta * m->fdelta * m->fdelta);
+    int iy;
+    for (iy = 0; iy < m->fnpy; ++iy) {
+        int ix;
+        for (ix = 0; ix < m->fnpx; ++ix) {
+            double s = 0;
+            for (my = 0; my < My; ++my) {
+                double w = (my == 0 || 2 * my == ny) ? 1.0 : 2.0;
+                s += w * cos(2 * M_PI * (double)(((long long)my * iy) % ny) / ny) * X[(size_t)my * m->fnpx + ix];
+            }
+            plane[(size_t)iy * m->fnpx + ix] = norm * s;
+        }
+    }
+    free(G);
+    free(X);
+}
+
+int orc_fft_plane_dims(const orc_model *m, int *npx, int *npy) {
+    if (m->d.kind != BF_MODEL_KSPACE_FFT) return -1;
+    *npx = m->fnpx;
+    *npy = m->fnpy;
+    return 0;
+}
+
+int orc_fft_planes(orc_model *m, const double *params, double z_trigger, double *out) {
+    /* out[(comp*npy + iy)*npx + ix] */
+    if (m->d.kind != BF_MODEL_KSPACE_FFT) { set_err("orc_fft_planes: not an FFT model"); return -1; }
+    fft_transform_component(m, params, z_trigger, 0, out);
+    fft_transform_component(m, params, z_trigger, 1, out + (size_t)m->fnpx * m->fnpy);
+    return 0;
+}
+
+static void fft_update_tables(orc_model *m, const double *p, double z) {
+    /* :191-214: the reference re-transforms when the broadening, continuum, nlcorr parameters or
+     * beta changed; here: whenever anything D(k,mu) reads changed (same thing for every BASELINE
+     * config, see DESIGN.md "FFT model") */
+    const bf_model_desc *d = &m->d;
+    double key[16];
+    int n = 0, i;
+    memset(key, 0, sizeof(key));
+    key[n++] = z; key[n++] = p[d->idx_beta]; key[n++] = p[d->idx_gamma_beta];
+    key[n++] = p[d->idx_nl]; key[n++] = p[d->idx_nl + 1]; key[n++] = p[d->idx_cont]; key[n++] = p[d->idx_cont + 1];
+    if (d->flags & BF_FLAG_CROSS_CORRELATION) { key[n++] = p[d->idx_bias2]; key[n++] = p[d->idx_bb2]; }
+    if (d->flags & BF_FLAG_FIT_NL_CORRECTION) { key[n++] = p[d->idx_nlcorr]; key[n++] = p[d->idx_nlcorr + 1]; }
+    if (m->fhave && memcmp(key, m->fkey, sizeof(key)) == 0) return;
+    for (i = 0; i < 2; ++i) fft_transform_component(m, p, z, i, m->fplane[i]);
+    memcpy(m->fkey, key, sizeof(key));
+    m->fhave = 1;
+}
+
+/* cosmo::DistortedPowerCorrelationFft::getCorrelation(r,mu) restated: bicubic (Catmull-Rom)
+ * interpolation on the plane at (r_perp, |r_par|); the plane is even in both coordinates, which
+ * supplies the node at index -1 (UNVERIFIED dep). Returns NaN and flags outside the kept plane. */
+static double fft_correlation(const orc_model *m, int c, double r, double mu, int *status) {
+    double x = r * sqrt(1 - mu * mu) / m->fdelta, y = fabs(r * mu) / m->fdelta;
+    int ix = (int)floor(x), iy = (int)floor(y), a, b;
+    if (ix + 2 > m->fnpx - 1 || iy + 2 > m->fnpy - 1) { *status |= BF_STATUS_FFT_RANGE; return NAN; }
+    double tx = x - ix, ty = y - iy, col[4];
+    for (b = 0; b < 4; ++b) {
+        int jy = abs(iy - 1 + b);
+        const double *row = m->fplane[c] + (size_t)jy * m->fnpx;
+        double v[4];
+        for (a = 0; a < 4; ++a) v[a] = row[abs(ix - 1 + a)];
+        col[b] = catmull(v[0], v[1], v[2], v[3], tx);
+    }
+    return catmull(col[0], col[1], col[2], col[3], ty);
+}
+
+static double fft_zcorr(const orc_model *m, double r, double mu, double z) {
+    /* :165-168 */
+    const bf_model_desc *d = &m->d;
+    if (d->zcorr0 > 0) {
+        double rpar = fabs(r * mu) / 100.;
+        z = d->zcorr0 + d->zcorr1 * rpar + d->zcorr2 * rpar * rpar;
+    }
+    return z;
+}
+
+/* BaoKSpaceFftCorrelationModel::_evaluate, :155-250; z_trigger = corrected z of the bin whose
+ * evaluation triggers the transform */
+static double fft_evaluate(orc_model *m, const double *p, double r, double mu, double z, double z_trigger, int *status) {
+    const bf_model_desc *d = &m->d;
+    int cross = (d->flags & BF_FLAG_CROSS_CORRELATION) != 0;
+    double beta = p[d->idx_beta], bb = p[d->idx_bb];
+    double bias = bb / (1 + beta);
+    double biasSq = cross ? bias * p[d->idx_bias2] : bias * bias;
+    double gammaBias = p[d->idx_gamma_bias];
+    z = fft_zcorr(m, r, mu, z);
+    biasSq = orc_redshift_evolution(biasSq, gammaBias, z, d->zref);
+    fft_update_tables(m, p, z_trigger);
+    double ampl = p[d->idx_bao], scale = p[d->idx_bao + 1], scale_parallel = p[d->idx_bao + 2];
+    double scale_perp = p[d->idx_bao + 3], gamma_scale = p[d->idx_bao + 4];
+    double rBAO, muBAO;
+    if (d->flags & BF_FLAG_ANISOTROPIC) {
+        double apar = orc_redshift_evolution(scale_parallel, gamma_scale, z, d->zref);
+        double aperp = orc_redshift_evolution(scale_perp, gamma_scale, z, d->zref);
+        double musq = mu * mu;
+        scale = sqrt(apar * apar * musq + aperp * aperp * (1 - musq));
+        rBAO = r * scale;
+        muBAO = apar * mu / scale;
+    } else {
+        scale = orc_redshift_evolution(scale, gamma_scale, z, d->zref);
+        rBAO = r * scale;
+        muBAO = mu;
+    }
+    double peak = fft_correlation(m, 0, rBAO, muBAO, status);
+    double smooth = (d->flags & BF_FLAG_DECOUPLED) ? fft_correlation(m, 1, r, mu, status) : fft_correlation(m, 1, rBAO, muBAO, status);
+    double xi = biasSq * (ampl * peak + smooth);
+    if (d->bb[BF_BB_DIST_MUL].enabled) xi *= 1 + broadband_eval(&d->bb[BF_BB_DIST_MUL], p, r, mu, z);
+    if (d->bb[BF_BB_DIST_ADD].enabled)
+        xi += orc_redshift_evolution(broadband_eval(&d->bb[BF_BB_DIST_ADD], p, r, mu, z), gammaBias, z, d->zref);
+    return xi;
+}
+
+/* corrected redshift of the bin that triggers the transform: the first kept bin, after the
+ * velocity shift of AbsCorrelationModel::evaluate (AbsCorrelationModel.cc:25) */
+static double fft_trigger_z(const orc_model *m, const double *p, double r, double mu, double z) {
+    if (m->d.idx_delta_v >= 0) velocity_shift(m, p, &r, &mu, z);
+    return fft_zcorr(m, r, mu, z);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* AbsCorrelationModel::evaluate, AbsCorrelationModel.cc:21-41                           */
 /* ------------------------------------------------------------------------------------ */
@@ -963,6 +1246,7 @@ static double evaluate_with_ztrig(orc_model *m, const orc_data *data, const doub
     update_internal(m, p, &in);
     if (d->idx_delta_v >= 0) velocity_shift(m, p, &r, &mu, z);
     if (d->kind == BF_MODEL_RSPACE) return rspace_evaluate(m, p, &in, r, mu, z, index);
+    if (d->kind == BF_MODEL_KSPACE_FFT) return fft_evaluate(m, p, r, mu, z, z_trigger, status);
     /* k-space */
     kspace_update_tables(m, p, z_trigger);
     double xi = kspace_point(m, p, &in, r, mu, z, index, 0, status);
@@ -985,7 +1269,8 @@ static double evaluate_with_ztrig(orc_model *m, const orc_data *data, const doub
 double orc_evaluate(orc_model *m, const orc_data *data, const double *params, double r, double mu, double z,
                     int index, int *status) {
     int st = 0;
-    double v = evaluate_with_ztrig(m, data, params, r, mu, z, index, z, &st);
+    double ztrig = m->d.kind == BF_MODEL_KSPACE_FFT ? fft_trigger_z(m, params, r, mu, z) : z;
+    double v = evaluate_with_ztrig(m, data, params, r, mu, z, index, ztrig, &st);
     if (status) *status = st;
     return v;
 }
@@ -1000,6 +1285,7 @@ double orc_evaluate_multipole(orc_model *m, const double *params, double r, int 
     for (q = 0; q < nmu; ++q) {
         double mu = 2 * x[q] - 1, v;
         if (m->d.kind == BF_MODEL_RSPACE) v = rspace_evaluate(m, params, &in, r, mu, z, -1);
+        else if (m->d.kind == BF_MODEL_KSPACE_FFT) v = fft_evaluate(m, params, r, mu, z, fft_zcorr(m, r, 0, z), &st);
         else { kspace_update_tables(m, params, z); v = kspace_point(m, params, &in, r, mu, z, -1, 0, &st); }
         s += 2 * w[q] * orc_legendre(ell, mu) * v;
     }
@@ -1027,6 +1313,7 @@ int orc_predict(orc_model *m, const orc_data *d, const double *params, double *p
      * after a parameter change, i.e. with z of the first kept bin. */
     int i, st = 0;
     double ztrig = d->d.n_data > 0 ? d->z[0] : m->d.zref;
+    if (m->d.kind == BF_MODEL_KSPACE_FFT && d->d.n_data > 0) ztrig = fft_trigger_z(m, params, d->r[0], d->mu[0], d->z[0]);
     if (m->d.kind == BF_MODEL_KSPACE && m->dist_matrix) {
         /* evaluate the undistorted grid once, then one matrix row per data bin */
         int nb = m->d.dist_matrix_order;
@@ -1100,6 +1387,10 @@ static orc_model *model_thread_clone(const orc_model *m) {
         c->last_params = (double *)malloc(sizeof(double) * m->d.npar);
         c->have_tables = 0;
     }
+    if (m->d.kind == BF_MODEL_KSPACE_FFT) {
+        for (i = 0; i < 2; ++i) c->fplane[i] = (double *)calloc((size_t)m->fnpx * m->fnpy, sizeof(double));
+        c->fhave = 0;
+    }
     return c;
 }
 static void model_thread_free(orc_model *c) {
@@ -1108,6 +1399,7 @@ static void model_thread_free(orc_model *c) {
         for (i = 0; i < 2; ++i) for (s = 0; s < 3; ++s) { free(c->tab_y[i][s]); free(c->tab_c[i][s]); }
         free(c->last_params);
     }
+    if (c->d.kind == BF_MODEL_KSPACE_FFT) { free(c->fplane[0]); free(c->fplane[1]); }
     free(c);
 }
 
@@ -1117,7 +1409,7 @@ int orc_chi2_batch(orc_model *m, const orc_data *d, const double *params, int B,
     if (nthreads < 1) nthreads = 1;
     int outer = nthreads;
 #ifdef _OPENMP
-    if (m->d.kind == BF_MODEL_KSPACE) { outer = 1; omp_set_num_threads(nthreads); }
+    if (m->d.kind == BF_MODEL_KSPACE || m->d.kind == BF_MODEL_KSPACE_FFT) { outer = 1; omp_set_num_threads(nthreads); }
 #endif
 #ifdef _OPENMP
 #pragma omp parallel num_threads(outer)

@@ -17,7 +17,9 @@
  *            quadrature here is our own, anchored only on models/DR9LyaMocksLCDM.{0,2,4}.dat
  *            which cosmocalc produced from DR9LyaMocksLCDM_matterpower.dat), bicubic metal
  *            templates (likely::BiCubicInterpolator), distortion-matrix product and metals
- *            (no fixture ships a .dmat or metal template).
+ *            (no fixture ships a .dmat or metal template), the 3-D FFT transform and plane
+ *            interpolation of cosmo::DistortedPowerCorrelationFft (our definition is pinned
+ *            against numpy.fft.ifftn of the same filled box, tests/test_oracle_golden.py).
  *
  * The input descriptions are the PODs of include/baofit_b200.h (types only).
  */
@@ -79,6 +81,13 @@ double orc_transform_dr(const orc_model *m);
 /* plain Hankel transform xi_ell(r) = i^ell/(2 pi^2) Int k^2 j_ell(kr) P(k) dk of a tabulated
  * P(k) (cubic spline in ln k), used to anchor the quadrature on models/<name>.<ell>.dat */
 double orc_hankel_table(int n, const double *k, const double *pk, int ell, double r);
+
+/* 3-D FFT model (BaoKSpaceFftCorrelationModel.cc): D(k,mu_k) P_comp(k) of :120-153 for the current
+ * parameters, and the two planes xi_comp(ix*spacing, iy*spacing) of the z = 0 slice of the box,
+ * out[(comp*npy + iy)*npx + ix] */
+double orc_fft_distortion_power(orc_model *m, const double *params, double z, int component, double k, double muk);
+int orc_fft_plane_dims(const orc_model *m, int *npx, int *npy);
+int orc_fft_planes(orc_model *m, const double *params, double z_trigger, double *out);
 
 #ifdef __cplusplus
 }

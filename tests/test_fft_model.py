@@ -1,0 +1,163 @@
+"""BaoKSpaceFftCorrelationModel (baofit/BaoKSpaceFftCorrelationModel.cc): the oracle's cosine-series
+restatement of the 3-D transform pinned on numpy's FFT (CPU), and the CUDA path against the oracle
+(GPU). cosmo::DistortedPowerCorrelationFft itself is not in the tree: parity with the reference is
+unpinned for this model, the definition is ours and these tests pin both sides to it."""
+import numpy as np
+import pytest
+
+import oracle
+from baofit_b200 import workloads as W
+from util import RTOL, rel_err, rel_err_bins
+
+
+def _box_planes(om, params, z, n, dl):
+    """numpy.fft.ifftn of the completely filled box, z = 0 slice, as [comp][iy][ix]."""
+    f = np.fft.fftfreq(n, d=dl) * 2 * np.pi
+    KX, KY, KZ = np.meshgrid(f, f, f, indexing="ij")
+    K = np.sqrt(KX ** 2 + KY ** 2 + KZ ** 2)
+    out = []
+    for comp in (0, 1):
+        F = np.zeros_like(K)
+        it = np.nditer(K, flags=["multi_index"])
+        for kk in it:
+            i = it.multi_index
+            if kk > 0:
+                F[i] = om.fft_distortion_power(params, z, comp, float(kk), float(KY[i] / kk))
+        xi = np.fft.ifftn(F).real / dl ** 3
+        out.append(xi[:, :, 0].T)
+    return np.array(out)
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_oracle_planes_equal_full_3d_fft(cross):
+    """The oracle sums the non-negative frequencies with weights (collapsed z axis, two cosine
+    transforms); numpy transforms the whole 24^3 box. Same plane to rounding."""
+    n, dl = 24, 20.0
+    m, _ = W.dr11_auto_fft(ngrid=n, spacing=dl, nbins=10, fft_rmax=180., cross=cross, nl_broadband=cross)
+    p = m.values.copy()
+    p[m.index("cont-kc")] = 0.02
+    om = oracle.OracleModel(m)
+    got = om.fft_planes(p, 2.4)
+    ref = _box_planes(om, p, 2.4, n, dl)[:, :got.shape[1], :got.shape[2]]
+    for c in range(2):
+        assert np.max(np.abs(got[c] - ref[c])) < 1e-13 * np.max(np.abs(ref[c]))
+
+
+def test_oracle_fft_reduces_to_tabulated_multipoles():
+    """With D = 1 the plane is the monopole of the same P(k): the 400^3, 4 Mpc/h box reproduces
+    models/DR9LyaMocksLCDM.0.dat up to the ringing of the sharp Nyquist cut of the grid."""
+    m, _ = W.dr11_auto_fft(ngrid=400, spacing=4., nl_correction=False, no_distortion=True, zcorr=(0, 0, 0))
+    p = m.values.copy()
+    p[m.index("beta")] = 0.0
+    p[m.index("SigmaNL-perp")] = 0.0
+    pl = oracle.OracleModel(m).fft_planes(p, 2.3)
+    r, x0, _, _ = W.load_multipoles(W.GOLDEN + "/models", "DR9LyaMocksLCDM")
+    i = np.arange(10, 45)
+    got = pl[0][0, i] + pl[1][0, i]
+    want = np.interp(4.0 * i, r, x0)
+    assert np.max(np.abs(got - want)) < 3e-4
+    assert np.allclose(pl[0][0, i], pl[0][i, 0], rtol=0, atol=1e-18)  # isotropic when D = 1
+    assert abs(np.mean(got - want)) < 2e-5
+
+
+def test_oracle_zcorr_and_trigger():
+    """z of a bin follows zcorr0 + zcorr1 rpar/100 + zcorr2 (rpar/100)^2 (:165-168): with gamma-bias
+    the prediction scales by ((1+z)/(1+zref))^gamma, everything else equal."""
+    m, (r, mu, z, keep) = W.dr11_auto_fft(ngrid=32, spacing=16., nbins=10, fft_rmax=300.)
+    om = oracle.OracleModel(m)
+    p = m.values.copy()
+    p[m.index("gamma-bias")] = 0.0
+    i = keep[len(keep) // 2]
+    a, _ = om.evaluate(p, r[i], mu[i], z[i])
+    p[m.index("gamma-bias")] = 2.0
+    b, _ = om.evaluate(p, r[i], mu[i], z[i])
+    rpar = abs(r[i] * mu[i]) / 100.
+    zc = 2.32454 + 5.1141e-3 * rpar + 8.00906e-3 * rpar ** 2
+    assert abs(b / a - ((1 + zc) / (1 + 2.3)) ** 2.0) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU parity
+# ----------------------------------------------------------------------------------------------
+
+def _gpu_case(ngrid, spacing, nbins, **kw):
+    m, coords = W.dr11_auto_fft(ngrid=ngrid, spacing=spacing, nbins=nbins, **kw)
+    om = oracle.OracleModel(m)
+
+    def predict(model, data, params):
+        return oracle.predict(om, oracle.OracleData(data), params[0])[0]
+
+    d, _ = W.synthetic_dataset(m, coords, predict)
+    return m, d, om
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cross", [False, True])
+def test_gpu_fft_planes(ctx, cross):
+    from baofit_b200 import capi
+    m, _ = W.dr11_auto_fft(ngrid=96, spacing=6., nbins=25, cross=cross, fit_nl_correction=cross)
+    rng = np.random.Generator(np.random.PCG64(3))
+    params = m.random_batch(6, rng)
+    gm = capi.Model(ctx, m)
+    got = gm.fft_planes(params, 2.41)
+    om = oracle.OracleModel(m)
+    for b in range(params.shape[0]):
+        ref = om.fft_planes(params[b], 2.41)
+        assert got[b].shape == ref.shape
+        for c in range(2):
+            err = np.max(np.abs(got[b, c] - ref[c])) / np.max(np.abs(ref[c]))
+            assert err < RTOL, (b, c, err)
+    gm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["dr11", "cross_bb", "alt_iso"])
+def test_gpu_fft_model_against_oracle(ctx, variant):
+    from baofit_b200 import capi
+    kw = dict(ngrid=128, spacing=5., nbins=40)
+    sweep = {"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)}
+    if variant == "cross_bb":
+        kw.update(cross=True, dist_add="rP,rT=0:2,-3:1", nl_broadband=True, zcorr=(0, 0, 0), nl_correction=False,
+                  nl_correction_alt=True)
+        sweep["delta-v"] = (-300, 300)
+    elif variant == "alt_iso":
+        kw.update(anisotropic=False, decoupled=False, distortion_alt=True, dist_mul="0:1,0:2:2,0")
+        sweep = {"BAO alpha-iso": (0.7, 1.4)}
+    m, d, om = _gpu_case(**kw)
+    if variant == "alt_iso":
+        m.configure("release[BAO alpha-iso]; release[gamma-bias]; release[gamma-scale]")
+    rng = np.random.Generator(np.random.PCG64(17))
+    params = m.random_batch(9, rng, sweep=sweep)
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    pred, st = capi.eval_batch(ctx, gm, gd, params)
+    chi2, st2 = capi.chi2_batch(ctx, gm, gd, params)
+    od = oracle.OracleData(d)
+    ref_chi2, ref_st, ref_pred = oracle.chi2_batch(om, od, params, want_pred=True, nthreads=8)
+    assert np.array_equal(st, ref_st) and np.array_equal(st2, ref_st)
+    ok = ref_st == 0
+    assert ok.sum() >= 5
+    assert rel_err_bins(pred[:, ok], ref_pred[:, ok]) < RTOL
+    assert rel_err(chi2[ok], ref_chi2[ok]) < RTOL
+    assert np.all(np.isnan(chi2[~ok]))
+    gm.close(), gd.close()
+
+
+@pytest.mark.gpu
+def test_gpu_fft_full_size_dr11(ctx):
+    """config/BOSSDR11LyaF_fft.ini at its own size: 400^3 cells of 4 Mpc/h, 1515 bins."""
+    from baofit_b200 import capi
+    m, d, om = _gpu_case(ngrid=400, spacing=4., nbins=50)
+    assert d.n_data == 1515
+    rng = np.random.Generator(np.random.PCG64(5))
+    params = m.random_batch(3, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)})
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    chi2, st = capi.chi2_batch(ctx, gm, gd, params)
+    ref_chi2, ref_st = oracle.chi2_batch(om, oracle.OracleData(d), params, nthreads=16)
+    assert np.array_equal(st, ref_st) and np.all(ref_st == 0)
+    assert rel_err(chi2, ref_chi2) < RTOL
+    # toy data vectors through the same path
+    ov = d.keep._arrays[4][None, :] + 1e-6 * rng.standard_normal((3, d.n_data))
+    chi2b, _ = capi.chi2_batch(ctx, gm, gd, params, data_override=ov)
+    refb, _ = oracle.chi2_batch(om, oracle.OracleData(d), params, data_override=ov, nthreads=16)
+    assert rel_err(chi2b, refb) < RTOL
+    gm.close(), gd.close()
