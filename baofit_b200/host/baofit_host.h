@@ -5,6 +5,7 @@
 //   AbsCorrelationModel        baofit/AbsCorrelationModel.{h,cc}
 //   BaoCorrelationModel        baofit/BaoCorrelationModel.{h,cc}
 //   BaoKSpaceCorrelationModel  baofit/BaoKSpaceCorrelationModel.{h,cc}
+//   BaoKSpaceFftCorrelationModel  baofit/BaoKSpaceFftCorrelationModel.{h,cc}
 //   BroadbandModel             baofit/BroadbandModel.{h,cc}
 //   MetalCorrelationModel      baofit/MetalCorrelationModel.{h,cc}
 //   NonLinearCorrectionModel   baofit/NonLinearCorrectionModel.{h,cc}
@@ -169,6 +170,23 @@ private:
     std::shared_ptr<MetalCorrelationModel> _metalCorr;
     std::shared_ptr<DistortionMatrix> _distMat;
     std::shared_ptr<BroadbandModel> _distortAdd, _distortMul, _distMatDistortAdd, _distMatDistortMul;
+};
+
+class BaoKSpaceFftCorrelationModel : public AbsCorrelationModel {
+public:
+    // Same argument list as baofit/BaoKSpaceFftCorrelationModel.h (BaoKSpaceFftCorrelationModel.cc:21-28);
+    // planeRMax (extra, default rmax*dilmax of the k-space options) bounds the tabulated plane.
+    BaoKSpaceFftCorrelationModel(std::string const &modelrootName, std::string const &fiducialName,
+                                 std::string const &nowigglesName, double zref, double OmegaMatter, double spacing,
+                                 int nx, int ny, int nz, std::string const &distAdd, std::string const &distMul,
+                                 double distR0, double zcorr0, double zcorr1, double zcorr2, double sigma8,
+                                 bool anisotropic = false, bool decoupled = false, bool nlBroadband = false,
+                                 bool nlCorrection = false, bool fitNLCorrection = false, bool nlCorrectionAlt = false,
+                                 bool distortionAlt = false, bool noDistortion = false, bool crossCorrelation = false,
+                                 bool verbose = false, double planeRMax = 300.);
+
+private:
+    std::shared_ptr<BroadbandModel> _distortAdd, _distortMul;
 };
 
 // ---- data -------------------------------------------------------------------------------------

@@ -287,11 +287,10 @@ Options parseIni(std::string const &text) {
         bool isSwitch = false;
         for (const char *s : switches) isSwitch |= key == s;
         if (isSwitch) {
-            std::string v = val;
-            std::transform(v.begin(), v.end(), v.begin(), ::tolower);
-            if (v.empty() || v == "yes" || v == "true" || v == "1" || v == "on") o.flags.insert(key);
-            else if (v == "no" || v == "false" || v == "0" || v == "off") o.flags.erase(key);
-            else throw RuntimeError("option " + key + " expects yes/no, got '" + val + "'");
+            // The reference declares these without a value and tests vm.count(name)
+            // (src/baofit.cc:76,132-135,349-354): the mere presence of the key switches the option
+            // on, whatever follows the '=' ("yes", "true;", even "no").
+            o.flags.insert(key);
         } else if (key == "model-config") {
             o.modelConfig.push_back(val);  // composing, order preserved (src/baofit.cc:335-338)
         } else {
@@ -314,9 +313,20 @@ AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDi
     std::string metalName = opt.str("metal-model-name");
     if (!metalName.empty()) metalName = resolve(baseDir, metalName);
     AbsCorrelationModelPtr model;
-    if (opt.flag("kspace-fft") || opt.flag("kspace-hybrid"))
-        throw RuntimeError("the FFT / hybrid k-space models are not built in this round (DESIGN.md, out of scope so far)");
-    if (opt.flag("kspace")) {
+    if (opt.flag("kspace-hybrid"))
+        throw RuntimeError("the hybrid k-space model is not part of the accelerated path (DESIGN.md, out of scope)");
+    if (opt.flag("kspace-fft")) {
+        // src/baofit.cc:398-399,436-443
+        int ngridx = (int)opt.num("ngridx", 400), ngridy = (int)opt.num("ngridy", 0), ngridz = (int)opt.num("ngridz", 0);
+        if (ngridy == 0) ngridy = ngridx;
+        if (ngridz == 0) ngridz = ngridy;
+        model.reset(new BaoKSpaceFftCorrelationModel(
+            modelroot, fid, nw, zref, OmegaMatter, opt.num("gridspacing", 4), ngridx, ngridy, ngridz, distAdd, distMul, distR0,
+            opt.num("zcorr0", 0), opt.num("zcorr1", 0), opt.num("zcorr2", 0), opt.num("sigma8", 0.8338), opt.flag("anisotropic"),
+            opt.flag("decoupled"), opt.flag("nl-broadband"), opt.flag("nl-correction"), opt.flag("fit-nl-correction"),
+            opt.flag("nl-correction-alt"), opt.flag("distortion-alt"), opt.flag("no-distortion"), opt.flag("cross-correlation"),
+            opt.flag("verbose"), opt.num("rmax", 200) * opt.num("dilmax", 1.5)));
+    } else if (opt.flag("kspace")) {
         std::string dmName = opt.str("dist-matrix-name");
         if (dmName.empty() && opt.flag("dist-matrix")) dmName = opt.str("data");  // src/baofit.cc: data name by default
         if (!dmName.empty()) dmName = resolve(baseDir, dmName);

@@ -626,6 +626,71 @@ BaoKSpaceCorrelationModel::BaoKSpaceCorrelationModel(
     }
 }
 
+// baofit/BaoKSpaceFftCorrelationModel.cc:21-113
+BaoKSpaceFftCorrelationModel::BaoKSpaceFftCorrelationModel(
+    std::string const &modelrootName, std::string const &fiducialName, std::string const &nowigglesName, double zref,
+    double OmegaMatter, double spacing, int nx, int ny, int nz, std::string const &distAdd, std::string const &distMul,
+    double distR0, double zcorr0, double zcorr1, double zcorr2, double sigma8, bool anisotropic, bool decoupled,
+    bool nlBroadband, bool nlCorrection, bool fitNLCorrection, bool nlCorrectionAlt, bool distortionAlt,
+    bool noDistortion, bool crossCorrelation, bool verbose, double planeRMax)
+    : AbsCorrelationModel("BAO k-Space FFT Correlation Model") {
+    _desc.kind = BF_MODEL_KSPACE_FFT;
+    _setZRef(zref);
+    _setOmegaMatter(OmegaMatter);
+    auto on = [&](bool b, unsigned f) { if (b) _desc.flags |= f; };
+    on(anisotropic, BF_FLAG_ANISOTROPIC); on(decoupled, BF_FLAG_DECOUPLED); on(nlBroadband, BF_FLAG_NL_BROADBAND);
+    on(nlCorrection, BF_FLAG_NL_CORRECTION); on(fitNLCorrection, BF_FLAG_FIT_NL_CORRECTION);
+    on(nlCorrectionAlt, BF_FLAG_NL_CORRECTION_ALT); on(distortionAlt, BF_FLAG_DISTORTION_ALT);
+    on(noDistortion, BF_FLAG_NO_DISTORTION); on(crossCorrelation, BF_FLAG_CROSS_CORRELATION);
+    // :39-62
+    _desc.idx_beta = defineParameter("beta", 1.4, 0.1);
+    _desc.idx_bb = defineParameter("(1+beta)*bias", -0.336, 0.03);
+    _desc.idx_gamma_bias = defineParameter("gamma-bias", 3.8, 0.3);
+    _desc.idx_gamma_beta = defineParameter("gamma-beta", 0, 0.1);
+    if (crossCorrelation) {
+        _desc.idx_delta_v = defineParameter("delta-v", 0, 10);
+        _desc.idx_bias2 = defineParameter("bias2", 3.6, 0.1);
+        _desc.idx_bb2 = defineParameter("beta2*bias2", 1, 0.05);
+    }
+    _desc.idx_nl = defineParameter("SigmaNL-perp", 3.26, 0.3);
+    defineParameter("1+f", 2, 0.1);
+    _desc.idx_cont = defineParameter("cont-kc", 0.02, 0.002);
+    defineParameter("cont-pc", 1, 0.1);
+    _desc.idx_bao = defineParameter("BAO amplitude", 1, 0.15);
+    defineParameter("BAO alpha-iso", 1, 0.02);
+    defineParameter("BAO alpha-parallel", 1, 0.1);
+    defineParameter("BAO alpha-perp", 1, 0.1);
+    defineParameter("gamma-scale", 0, 0.5);
+    std::string root = withSlash(modelrootName);
+    try {
+        std::vector<double> k1, p1, k2, p2;
+        readTwoColumns(root + fiducialName + "_matterpower.dat", k1, p1);
+        readTwoColumns(root + nowigglesName + "_matterpower.dat", k2, p2);
+        if (k1 != k2) throw RuntimeError("P(k) tables must share k nodes");
+        _desc.n_pk = (int)k1.size();
+        _desc.pk_k = _keep(k1); _desc.pk_fid = _keep(p1); _desc.pk_nw = _keep(p2);
+    } catch (RuntimeError const &) {
+        throw RuntimeError("BaoKSpaceFftCorrelationModel: error while reading tabulated P(k) data.");
+    }
+    _desc.fft_spacing = spacing; _desc.fft_nx = nx; _desc.fft_ny = ny; _desc.fft_nz = nz; _desc.fft_rmax = planeRMax;
+    _desc.zcorr0 = zcorr0; _desc.zcorr1 = zcorr1; _desc.zcorr2 = zcorr2; _desc.sigma8 = sigma8;
+    if (verbose) {
+        // the reference prints the size of its 3-D grids here (:93-96); ours are never allocated
+        std::cout << "3D FFT memory size = " << (double)nx * ny * nz * 16 / 1048576. << " Mb (not allocated: the transform is"
+                  << " evaluated on the z = 0 plane only)" << std::endl;
+    }
+    if (!distAdd.empty()) {
+        _distortAdd.reset(new BroadbandModel("Additive broadband distortion", "dist add", distAdd, distR0, zref, this));
+        _desc.bb[BF_BB_DIST_ADD] = _distortAdd->spec();
+    }
+    if (!distMul.empty()) {
+        _distortMul.reset(new BroadbandModel("Multiplicative broadband distortion", "dist mul", distMul, distR0, zref, this));
+        _desc.bb[BF_BB_DIST_MUL] = _distortMul->spec();
+    }
+    // :110-112 the non-linear correction model is constructed last
+    if (fitNLCorrection) { _desc.idx_nlcorr = defineParameter("nlcorr qnl", 0.867, 0.08); defineParameter("nlcorr kp", 19.4, 1); }
+}
+
 void BaoKSpaceCorrelationModel::setDistortionMatrix(std::shared_ptr<DistortionMatrix> dm) {
     _distMat = dm;
     _desc.dist_matrix_order = dm->order();

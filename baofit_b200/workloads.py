@@ -621,6 +621,18 @@ def synthetic_dataset(model, coords, predict, seed=1966, cov_seed=1):
     return make_data(r, mu, z, keep, d, cov), xi0
 
 
+def write_dataset_files(path_prefix, nbins, keep, dvec, cov):
+    """Writes ``<prefix>.data`` / ``<prefix>.cov`` in the reference's text formats (SURVEY.md
+    appendix A) for a data set that lives on the kept bins only; the other grid bins get no data."""
+    keep = np.asarray(keep)
+    with open(path_prefix + ".data", "w") as f:
+        np.savetxt(f, np.column_stack([keep, dvec]), fmt="%d %.17g")
+    i, j = np.tril_indices(len(keep))
+    with open(path_prefix + ".cov", "w") as f:
+        np.savetxt(f, np.column_stack([keep[i], keep[j], cov[i, j]]), fmt="%d %d %.17g")
+    return path_prefix
+
+
 def make_golden_tree(root):
     """Lays out tests/golden like the reference checkout (config/ data/ demo/ models/) under
     `root`, expanding the gzip-compressed covariance, so that the .ini recipes run unmodified."""

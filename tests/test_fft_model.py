@@ -161,3 +161,55 @@ def test_gpu_fft_full_size_dr11(ctx):
     refb, _ = oracle.chi2_batch(om, oracle.OracleData(d), params, data_override=ov, nthreads=16)
     assert rel_err(chi2b, refb) < RTOL
     gm.close(), gd.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# config/BOSSDR11LyaF_fft.ini through the host-side classes (unmodified .ini, synthetic data + cov)
+# ----------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def fft_session(built, golden_tree):
+    import os
+    from baofit_b200 import host_api as H
+    m, d, om = _gpu_case(ngrid=400, spacing=4., nbins=50)
+    keep = d.keep._arrays[3]
+    W.write_dataset_files(os.path.join(golden_tree, "data", "BOSSDR11LyaF_synth"), 2500, keep, d.keep._arrays[4],
+                          d.keep._arrays[5])
+    text = open(os.path.join(golden_tree, "config", "BOSSDR11LyaF_fft.ini")).read()
+    text = text.replace("data = ../data/BOSSDR11LyaF", "data = ../data/BOSSDR11LyaF_synth")
+    s = H.Session(text, os.path.join(golden_tree, "config"))
+    yield s, m, d, om
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_fft_session_layout_and_evaluate(fft_session):
+    s, m, d, om = fft_session
+    assert s.names == m.names and s.npar == 13 and int(s.floating.sum()) == 5
+    assert np.array_equal(s.floating, m.floating) and np.allclose(s.values, m.values)
+    assert np.array_equal(s.kept_indices(), d.keep._arrays[3]) and s.ndata == 1515
+    rng = np.random.Generator(np.random.PCG64(8))
+    params = m.random_batch(4, rng)
+    f = s.evaluate(params)
+    ref, st = oracle.chi2_batch(om, oracle.OracleData(d), params, nthreads=16)
+    assert np.all(st == 0) and np.max(np.abs(2 * f - ref) / ref) < RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_fft_fit_and_toys(fft_session):
+    """A fit of the synthetic DR11 data set recovers the truth it was drawn from, and toy-MC
+    realisations refitted in lock step are unbiased and independent of how they are sharded."""
+    s, m, d, om = fft_session
+    r = s.fit()
+    assert r["status"] in (0, 1)
+    fl = np.nonzero(s.floating)[0]
+    pull = (r["values"][fl] - m.values[fl]) / r["errors"][fl]
+    assert np.all(np.abs(pull) < 4.5), pull
+    assert abs(2 * r["fval"] - (1515 - 5)) < 5 * np.sqrt(2 * 1510)
+    a = s.toymc(0, 24, seed=11)
+    b1, b2 = s.toymc(0, 10, seed=11), s.toymc(10, 14, seed=11)
+    assert np.array_equal(a["fitted"], np.vstack([b1["fitted"], b2["fitted"]]))
+    assert np.all(a["status"] != 2)
+    assert abs(a["chi2"].mean() - 1510) < 5 * np.sqrt(2 * 1510 / 24)
+    ia = s.names.index("BAO alpha-parallel")
+    assert abs(a["fitted"][:, ia].mean() - 1.0) < 5 * a["fitted"][:, ia].std() / np.sqrt(24) + 1e-3
