@@ -197,9 +197,11 @@ public:
     int getNBinsTotal() const { return (int)(_axis[0].size() * _axis[1].size() * _axis[2].size()); }
     // bin centres of global index (axis 1 slowest, axis 3 fastest)
     void getBinCenters(int index, double centers[3]) const;
+    void getBinWidths(int index, double widths[3]) const;
+    void setWidths(std::vector<double> w1, std::vector<double> w2, std::vector<double> w3);
 
 private:
-    std::vector<double> _axis[3];
+    std::vector<double> _axis[3], _width[3];
 };
 BinnedGrid createCorrelationGrid(std::string const &axis1Bins, std::string const &axis2Bins,
                                  std::string const &axis3Bins);  // AbsCorrelationData.cc:96-150
@@ -240,6 +242,9 @@ public:
 protected:
     BinnedGrid _grid;
     TransverseBinningType _type;
+    // format-specific cut applied to bins that passed the final cuts (true = drop the bin);
+    // QuasarCorrelationData::finalize, QuasarCorrelationData.cc:112-127
+    virtual bool extraCut(int index) const { (void)index; return false; }
 
 private:
     std::map<int, double> _values;
@@ -263,6 +268,49 @@ public:
 
 private:
     CoordinateSystem _coordinateSystem;
+};
+
+// Stand-in for cosmo::LambdaCdmRadiationUniverse (src/baofit.cc:413; the dependency is not in the
+// tree): flat or curved LCDM with photons + massless neutrinos,
+//   E(z)^2 = Or (1+z)^4 + Om (1+z)^3 + Ok (1+z)^2 + (1 - Om - Ok - Or),
+//   Or h^2 = 2.469e-5 (Tcmb/2.725)^4 (1 + 0.2271 Nnu)            UNVERIFIED (dep)
+// Distances in Mpc/h.
+class LambdaCdmRadiationUniverse {
+public:
+    LambdaCdmRadiationUniverse(double OmegaMatter, double OmegaK, double hubbleConstant, double Tcmb = 2.725,
+                               double Nnu = 3.04);
+    double getHubbleFunction(double z) const;                  // E(z)
+    double getLineOfSightComovingDistance(double z) const;     // Mpc/h
+    double getTransverseComovingScale(double z) const;         // Mpc/h per radian
+    double omegaRadiation() const { return _OmegaRadiation; }
+    void setOmegaRadiation(double v) { _OmegaRadiation = v; }
+
+private:
+    double _OmegaMatter, _OmegaK, _h, _OmegaRadiation;
+};
+typedef std::shared_ptr<LambdaCdmRadiationUniverse> AbsHomogeneousUniversePtr;
+
+// baofit/QuasarCorrelationData.{h,cc}: observing coordinates (log(lam2/lam1), angular separation in
+// arcmin, mean redshift) converted to (r, mu) through the cosmology (:139-152), with the extra
+// ll / separation cuts of finalize() (:102-137).
+class QuasarCorrelationData : public AbsCorrelationData {
+public:
+    QuasarCorrelationData(BinnedGrid grid, double llMin, double llMax, double sepMin, double sepMax, bool fixCov,
+                          AbsHomogeneousUniversePtr cosmology);
+    double getRadius(int index) const override;
+    double getCosAngle(int index) const override;
+    double getRedshift(int index) const override;
+    void transform(double ll, double sep, double dsep, double z, double &r, double &mu) const;
+
+protected:
+    bool extraCut(int index) const override;
+
+private:
+    double _llMin, _llMax, _sepMin, _sepMax, _arcminToRad;
+    AbsHomogeneousUniversePtr _cosmology;
+    mutable int _lastIndex = -1;
+    mutable double _rLast = 0, _muLast = 0, _zLast = 0;
+    void _setIndex(int index) const;
 };
 
 // "<name>.data" / ".cov" / ".icov" text loaders (AbsCorrelationData.cc:156-277); ".cov.gz" is not

@@ -91,6 +91,17 @@ extern "C" int bfh_kept_indices(const bfh_session *s, int *indices) {
     BFH_CATCH
 }
 
+extern "C" int bfh_kept_coordinates(const bfh_session *s, double *r, double *mu, double *z) {
+    BFH_TRY
+    auto const &k = s->data->keptIndices();
+    for (size_t i = 0; i < k.size(); ++i) {
+        if (r) r[i] = s->data->getRadius(k[i]);
+        if (mu) mu[i] = s->data->getCosAngle(k[i]);
+        if (z) z[i] = s->data->getRedshift(k[i]);
+    }
+    BFH_CATCH
+}
+
 extern "C" int bfh_set_distortion_matrix(bfh_session *s, const double *dense, int order) {
     BFH_TRY
     auto *km = dynamic_cast<BaoKSpaceCorrelationModel *>(s->model.get());

@@ -30,17 +30,35 @@ void BinnedGrid::getBinCenters(int index, double centers[3]) const {
     centers[2] = _axis[2][i3];
 }
 
+void BinnedGrid::setWidths(std::vector<double> w1, std::vector<double> w2, std::vector<double> w3) {
+    _width[0] = w1;
+    _width[1] = w2;
+    _width[2] = w3;
+}
+
+void BinnedGrid::getBinWidths(int index, double widths[3]) const {
+    if (index < 0 || index >= getNBinsTotal()) throw RuntimeError("BinnedGrid: invalid bin index.");
+    int n2 = (int)_axis[1].size(), n3 = (int)_axis[2].size();
+    int i3 = index % n3, i2 = (index / n3) % n2, i1 = index / (n3 * n2);
+    widths[0] = _width[0].empty() ? 0.0 : _width[0][i1];
+    widths[1] = _width[1].empty() ? 0.0 : _width[1][i2];
+    widths[2] = _width[2].empty() ? 0.0 : _width[2][i3];
+}
+
 BinnedGrid createCorrelationGrid(std::string const &axis1Bins, std::string const &axis2Bins, std::string const &axis3Bins) {
-    std::vector<double> a[3];
+    std::vector<double> a[3], w[3];
     const std::string *spec[3] = {&axis1Bins, &axis2Bins, &axis3Bins};
     for (int i = 0; i < 3; ++i) {
         try {
             a[i] = likely::createBinning(*spec[i]);
+            w[i] = likely::createBinningWidths(*spec[i]);
         } catch (likely::RuntimeError const &) {
             throw RuntimeError("createCorrelationGrid: error in axis " + std::to_string(i + 1) + " binning.");
         }
     }
-    return BinnedGrid(a[0], a[1], a[2]);
+    BinnedGrid g(a[0], a[1], a[2]);
+    g.setWidths(w[0], w[1], w[2]);
+    return g;
 }
 
 AbsCorrelationData::AbsCorrelationData(BinnedGrid grid, TransverseBinningType type) : _grid(grid), _type(type) {}
@@ -109,6 +127,7 @@ void AbsCorrelationData::finalize() {
         if (rpar < _rparMin || rpar > _rparMax) continue;
         double rperp = r * std::sqrt(1 - mu * mu);
         if (rperp < _rperpMin || rperp > _rperpMax) continue;
+        if (extraCut(index)) continue;
         _kept.push_back(index);
     }
     if (_kept.empty()) throw RuntimeError("CorrelationFitter: need some data to fit.");
@@ -230,6 +249,92 @@ void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, 
         if (icov) data.setInverseCovariance(i1, i2, value);
         else data.setCovariance(i1, i2, value);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// cosmology + quasar coordinates
+// ------------------------------------------------------------------------------------------
+LambdaCdmRadiationUniverse::LambdaCdmRadiationUniverse(double OmegaMatter, double OmegaK, double hubbleConstant,
+                                                       double Tcmb, double Nnu)
+    : _OmegaMatter(OmegaMatter), _OmegaK(OmegaK), _h(hubbleConstant) {
+    if (hubbleConstant <= 0) throw RuntimeError("LambdaCdmRadiationUniverse: expected hubbleConstant > 0.");
+    double t = Tcmb / 2.725;
+    _OmegaRadiation = 2.469e-5 * t * t * t * t * (1 + 0.2271 * Nnu) / (hubbleConstant * hubbleConstant);
+}
+
+double LambdaCdmRadiationUniverse::getHubbleFunction(double z) const {
+    double zp1 = 1 + z, ol = 1 - _OmegaMatter - _OmegaK - _OmegaRadiation;
+    return std::sqrt(ol + zp1 * zp1 * (_OmegaK + zp1 * (_OmegaMatter + zp1 * _OmegaRadiation)));
+}
+
+double LambdaCdmRadiationUniverse::getLineOfSightComovingDistance(double z) const {
+    // c/H0 Int_0^z dz'/E(z'), composite 8-point Gauss-Legendre on panels of 0.05 in z: the integrand
+    // is smooth, the result is converged to rounding
+    static const double x[4] = {0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
+    static const double w[4] = {0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+    if (z == 0) return 0;
+    int n = (int)std::ceil(std::fabs(z) / 0.05);
+    double h = z / n, sum = 0;
+    for (int i = 0; i < n; ++i) {
+        double mid = (i + 0.5) * h, part = 0;
+        for (int q = 0; q < 4; ++q) part += w[q] * (1 / getHubbleFunction(mid + 0.5 * h * x[q]) + 1 / getHubbleFunction(mid - 0.5 * h * x[q]));
+        sum += 0.5 * h * part;
+    }
+    const double hubbleLength = 299792.458 / 100.;  // c/(100 km/s/Mpc) in Mpc/h
+    return hubbleLength * sum;
+}
+
+double LambdaCdmRadiationUniverse::getTransverseComovingScale(double z) const {
+    const double hubbleLength = 299792.458 / 100.;
+    double dc = getLineOfSightComovingDistance(z);
+    if (_OmegaK == 0) return dc;
+    double sk = std::sqrt(std::fabs(_OmegaK)), x = sk * dc / hubbleLength;
+    return hubbleLength / sk * (_OmegaK > 0 ? std::sinh(x) : std::sin(x));
+}
+
+QuasarCorrelationData::QuasarCorrelationData(BinnedGrid grid, double llMin, double llMax, double sepMin, double sepMax,
+                                             bool fixCov, AbsHomogeneousUniversePtr cosmology)
+    : AbsCorrelationData(grid, Coordinate), _llMin(llMin), _llMax(llMax), _sepMin(sepMin), _sepMax(sepMax),
+      _cosmology(cosmology) {
+    // QuasarCorrelationData.cc:25-37
+    if (llMin > llMax) throw RuntimeError("QuasarCorrelationData: expected llMin <= llMax.");
+    if (sepMin > sepMax) throw RuntimeError("QuasarCorrelationData: expected sepMin <= sepMax.");
+    if (fixCov) throw RuntimeError("QuasarCorrelationData: fixCovariance is not part of the accelerated path (src/baofit.cc:496 never sets it).");
+    if (!cosmology) throw RuntimeError("QuasarCorrelationData: need a cosmology.");
+    _arcminToRad = 4 * std::atan(1) / (60. * 180.);
+}
+
+void QuasarCorrelationData::transform(double ll, double sep, double dsep, double z, double &r, double &mu) const {
+    // QuasarCorrelationData.cc:139-152
+    double ratio(std::exp(0.5 * ll)), zp1(z + 1);
+    double z1(zp1 / ratio - 1), z2(zp1 * ratio - 1);
+    double drLos = _cosmology->getLineOfSightComovingDistance(z2) - _cosmology->getLineOfSightComovingDistance(z1);
+    double swgt = sep + (dsep * dsep / 12) / sep;
+    double drPerp = _cosmology->getTransverseComovingScale(z) * (swgt * _arcminToRad);
+    double rsq = drLos * drLos + drPerp * drPerp;
+    r = std::sqrt(rsq);
+    mu = std::abs(drLos) / r;
+}
+
+void QuasarCorrelationData::_setIndex(int index) const {
+    if (index == _lastIndex) return;
+    double c[3], w[3];
+    _grid.getBinCenters(index, c);
+    _grid.getBinWidths(index, w);
+    _zLast = c[2];
+    transform(c[0], c[1], w[1], _zLast, _rLast, _muLast);
+    _lastIndex = index;
+}
+
+double QuasarCorrelationData::getRadius(int index) const { _setIndex(index); return _rLast; }
+double QuasarCorrelationData::getCosAngle(int index) const { _setIndex(index); return _muLast; }
+double QuasarCorrelationData::getRedshift(int index) const { _setIndex(index); return _zLast; }
+
+bool QuasarCorrelationData::extraCut(int index) const {
+    double c[3];
+    _grid.getBinCenters(index, c);
+    double ll(c[0]), sep(c[1]);
+    return ll < _llMin || ll > _llMax || sep < _sepMin || sep > _sepMax;
 }
 
 }  // namespace baofit

@@ -354,12 +354,18 @@ AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDi
 
 AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir) {
     std::string fmt = opt.str("data-format");
-    ComovingCorrelationData::CoordinateSystem cs;
-    if (fmt == "comoving-cartesian") cs = ComovingCorrelationData::CartesianCoordinates;
-    else if (fmt == "comoving-polar") cs = ComovingCorrelationData::PolarCoordinates;
-    else throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar)");
     BinnedGrid grid = createCorrelationGrid(opt.str("axis1-bins"), opt.str("axis2-bins"), opt.str("axis3-bins"));
-    AbsCorrelationDataPtr data(new ComovingCorrelationData(grid, cs));
+    AbsCorrelationDataPtr data;
+    if (fmt == "comoving-cartesian") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::CartesianCoordinates));
+    else if (fmt == "comoving-polar") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::PolarCoordinates));
+    else if (fmt == "quasar") {
+        // src/baofit.cc:409-414,495-500
+        AbsHomogeneousUniversePtr cosmology(new LambdaCdmRadiationUniverse(opt.num("omega-matter", 0.27), 0, opt.num("hubble-constant", 0.7)));
+        if (opt.has("omega-radiation")) cosmology->setOmegaRadiation(opt.num("omega-radiation", 0));  // not a reference option
+        data.reset(new QuasarCorrelationData(grid, opt.num("ll-min", 0), opt.num("ll-max", 1), opt.num("sep-min", 0),
+                                             opt.num("sep-max", 200), false, cosmology));
+    } else
+        throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar, quasar)");
     // src/baofit.cc:510 with the defaults of :216-247
     double rVetoWidth = opt.num("rveto-width", 0), rVetoCenter = opt.num("rveto-center", 114);
     data->setFinalCuts(opt.num("rmin", 0), opt.num("rmax", 200), rVetoCenter - 0.5 * rVetoWidth, rVetoCenter + 0.5 * rVetoWidth,

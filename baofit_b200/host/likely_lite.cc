@@ -77,6 +77,18 @@ std::vector<double> createBinning(std::string const &specIn) {
     return out;
 }
 
+std::vector<double> createBinningWidths(std::string const &specIn) {
+    std::vector<double> centres = createBinning(specIn);
+    std::string s = trim(specIn);
+    std::vector<double> w(centres.size(), 0.0);
+    size_t colon = s.find(':'), close = s.find(']');
+    if (s[0] == '[' && colon != std::string::npos && close != std::string::npos) {
+        double lo = toDouble(s.substr(1, colon - 1), specIn), hi = toDouble(s.substr(colon + 1, close - colon - 1), specIn);
+        for (auto &x : w) x = (hi - lo) / (double)centres.size();
+    }
+    return w;
+}
+
 void modifyFitParameters(FitParameters &params, std::string const &script) {
     std::stringstream ss(script);
     std::string stmt;

@@ -49,6 +49,9 @@ void modifyFitParameters(FitParameters &params, std::string const &script);
 // including both ends), {a,b,c} (explicit centres). Conventions pinned by demo/rmu.theory and
 // demo/multi.theory.
 std::vector<double> createBinning(std::string const &spec);
+// same strings -> bin widths: (hi-lo)/n for "[lo:hi]*n" bins, 0 for samplings ({..} forms, which
+// describe points rather than intervals; likely::AbsBinning::getBinWidth UNVERIFIED (dep))
+std::vector<double> createBinningWidths(std::string const &spec);
 
 // Gaussian prior: centre (lo+hi)/2, sigma (hi-lo)/2 ("range is -/+ 1 sigma",
 // config/BOSSDR9LyaF.ini:81). Box prior: flat inside, quadratic wall outside (exact form of the

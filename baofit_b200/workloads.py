@@ -78,6 +78,51 @@ def grid_coordinates(axis1, axis2, axis3, fmt):
     return r, mu, c3.copy()
 
 
+class LambdaCdmRadiationUniverse:
+    """Stand-in for cosmo::LambdaCdmRadiationUniverse(OmegaMatter, OmegaK = 0, h) (src/baofit.cc:413,
+    dependency not in the tree): flat LCDM with photons and massless neutrinos, distances in Mpc/h.
+    Omega_r h^2 = 2.469e-5 (1 + 0.2271 * 3.04) -- UNVERIFIED (dep); pinned end to end by
+    data/BOSSDR9LyaF.scan (tests/test_quasar_data.py)."""
+
+    def __init__(self, omega_matter=0.27, hubble_constant=0.7, omega_radiation=None):
+        self.om = omega_matter
+        self.orad = 2.469e-5 * (1 + 0.2271 * 3.04) / hubble_constant ** 2 if omega_radiation is None else omega_radiation
+
+    def efunc(self, z):
+        zp1 = 1 + z
+        return np.sqrt(1 - self.om - self.orad + zp1 ** 3 * (self.om + zp1 * self.orad))
+
+    def los_distance(self, z):
+        from scipy.integrate import quad
+        return 2997.92458 * quad(lambda x: 1.0 / self.efunc(x), 0, z, epsabs=0, epsrel=1e-13)[0]
+
+
+def quasar_grid_coordinates(axis1, axis2, axis2_width, axis3, cosmology):
+    """(r, mu, z) of every bin of an observing-coordinate grid (log(lam2/lam1), separation in
+    arcmin, z): QuasarCorrelationData::transform (baofit/QuasarCorrelationData.cc:139-152).
+    Also returns the (ll, sep) centres for the ll-min / sep cuts of finalize (:123)."""
+    c1, c2, c3 = np.meshgrid(axis1, axis2, axis3, indexing="ij")
+    ll, sep, z = c1.ravel(), c2.ravel(), c3.ravel()
+    arcmin = 4 * np.arctan(1) / (60. * 180.)
+    r, mu = np.zeros(len(ll)), np.zeros(len(ll))
+    cache = {}
+
+    def dist(x):
+        if x not in cache:
+            cache[x] = cosmology.los_distance(x)
+        return cache[x]
+
+    for i in range(len(ll)):
+        ratio, zp1 = np.exp(0.5 * ll[i]), z[i] + 1
+        z1, z2 = zp1 / ratio - 1, zp1 * ratio - 1
+        dr_los = dist(z2) - dist(z1)
+        swgt = sep[i] + (axis2_width * axis2_width / 12) / sep[i]
+        dr_perp = dist(z[i]) * (swgt * arcmin)
+        r[i] = np.sqrt(dr_los * dr_los + dr_perp * dr_perp)
+        mu[i] = abs(dr_los) / r[i]
+    return r, mu, z.copy(), ll, sep
+
+
 def final_cuts(r, mu, z, has_data, rmin=0., rmax=200., rveto=(0., 0.), mumin=-1., mumax=1.,
                rperpmin=0., rperpmax=200., rparmin=-200., rparmax=200., zmin=0., zmax=10.):
     """Same comparisons, in the same order, as AbsCorrelationData::_applyFinalCuts
@@ -549,6 +594,48 @@ def qso_kspace(root=None, golden=GOLDEN, with_dist_matrix=True, with_metals=True
         cov = synthetic_cov(val[keep])
     data = make_data(r, mu, z, keep, val[keep], cov, with_grid=with_dist_matrix)
     return m, data
+
+
+DR9_AXIS1 = ("{0.,0.001,0.003,0.005,0.007,0.009,0.011,0.013,0.015,0.017,0.019,0.021,0.023,0.025,0.027,0.029,0.031,"
+             "0.033,0.035,0.037,0.039,0.041,0.043,0.045,0.047,0.049,0.0591608,0.0828251}")
+
+
+def dr9_data(golden=GOLDEN, cosmology=None):
+    """data/BOSSDR9LyaF.{data,cov} on the 28 x 18 x 3 observing grid of config/BOSSDR9LyaF.ini
+    (data-format = quasar), cuts r in [50,190], ll >= 0.003."""
+    cosmology = cosmology or LambdaCdmRadiationUniverse()
+    a1, a2, a3 = parse_binning(DR9_AXIS1), parse_binning("[0:180]*18"), parse_binning("{2.0,2.5,3.0}")
+    r, mu, z, ll, sep = quasar_grid_coordinates(a1, a2, 10.0, a3, cosmology)
+    n = len(r)
+    val, has = load_data_vector(os.path.join(golden, "data", "BOSSDR9LyaF.data"), n)
+    cov = load_cov(os.path.join(golden, "data", "BOSSDR9LyaF.cov.gz"), n)
+    keep = final_cuts(r, mu, z, has, rmin=50, rmax=190)
+    keep = np.array([i for i in keep if not (ll[i] < 0.003 or ll[i] > 1 or sep[i] < 0 or sep[i] > 200)], dtype=np.int32)
+    return make_data(r, mu, z, keep, val[keep], cov[np.ix_(keep, keep)])
+
+
+def dr9_rspace(root=None, golden=GOLDEN, cosmology=None):
+    """config/BOSSDR9LyaF.ini: BaoCorrelationModel, Lya auto-correlation, quasar coordinates, real
+    data and covariance (the golden BOSSDR9LyaF.scan case). Priors live in the host fitter."""
+    root = root or os.path.join(golden, "models")
+    fid = load_multipoles(root, "DR9LyaMocksNLeffPk")
+    nw = load_multipoles(root, "DR9LyaMocksSB")
+    m = rspace_model(fid, nw, zref=2.25, dist_add="-2:0,0:4:2,0")
+    m.configure("value[beta]=1.4; value[(1+beta)*bias]=-0.336; value[gamma-bias]=3.8; fix[gamma-beta]=0;"
+                "fix[BAO amplitude]=1; fix[BAO alpha-iso]; value[BAO alpha-p*]=1; fix[gamma-scale]=0")
+    return m, dr9_data(golden, cosmology)
+
+
+def dr9_kspace(root=None, golden=GOLDEN, cosmology=None):
+    """config/BOSSDR9LyaF_k.ini: BaoKSpaceCorrelationModel on the same data (BASELINE config 2)."""
+    root = root or os.path.join(golden, "models")
+    pk_fid = load_table(os.path.join(root, "DR9LyaMocksLCDM_matterpower.dat"))
+    pk_nw = load_table(os.path.join(root, "DR9LyaMocksLCDMSB_matterpower.dat"))
+    m = kspace_model(pk_fid, pk_nw, rmin=50, rmax=190, zref=2.25, dist_add="-2:0,0:4:2,0")
+    m.configure("value[beta]=1.4; value[(1+beta)*bias]=-0.336; value[gamma-bias]=3.8; fix[gamma-beta]=0;"
+                "fix[BAO amplitude]=1; fix[BAO alpha-iso]; value[BAO alpha-p*]=1; fix[gamma-scale]=0;"
+                "fix[1+f]=1.966; fix[SigmaNL-perp]=3.26")
+    return m, dr9_data(golden, cosmology)
 
 
 def demo_rmu(root=None, golden=GOLDEN):

@@ -35,6 +35,9 @@ const char *bfh_param_name(const bfh_session *s, int i);
 int bfh_param_info(const bfh_session *s, double *values, double *errors, int *floating);
 /* kept global bin indices in iteration order (bit-exact mask check) */
 int bfh_kept_indices(const bfh_session *s, int *indices);
+/* (r, mu, z) of the kept bins in iteration order: AbsCorrelationData::getRadius / getCosAngle /
+ * getRedshift (ComovingCorrelationData.cc:46-84, QuasarCorrelationData.cc:139-185) */
+int bfh_kept_coordinates(const bfh_session *s, double *r, double *mu, double *z);
 /* replaces the model's distortion matrix by an in-memory dense one (order x order, row-major)
  * and forwards the grid coordinates of the data (AbsCorrelationModel::setCoordinates) */
 int bfh_set_distortion_matrix(bfh_session *s, const double *dense, int order);
