@@ -315,15 +315,22 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         f.pk_coef = p;
         // cosine tables with exact argument reduction
         const long double two_pi = 6.283185307179586476925286766559005768L;
-        std::vector<double> cosx(f.nx), cy((size_t)f.npy_pad * f.my_pad, 0.0);
+        const int nrf = f.npy_pad / 8, ncfr = f.npx_pad / 8;
+        f.rtiles = (nrf + 8) / 9; f.ctiles = (ncfr + 8) / 9;
+        f.wr = (nrf + f.rtiles - 1) / f.rtiles; f.ncf = (ncfr + f.ctiles - 1) / f.ctiles;
+        const int nchunks = f.my_pad / kFftKC;
+        std::vector<double> cosx(f.nx), cy((size_t)f.rtiles * nchunks * kFftStageA, 0.0);
         for (int t = 0; t < f.nx; ++t) cosx[t] = (double)cosl(two_pi * t / f.nx);
         for (int iy = 0; iy < f.npy; ++iy)
-            for (int my = 0; my < f.my; ++my) cy[(size_t)iy * f.my_pad + my] = (double)cosl(two_pi * (((long long)my * iy) % f.ny) / f.ny);
+            for (int my = 0; my < f.my; ++my) {
+                const int rt = iy / (f.wr * 8), row = iy - rt * f.wr * 8, ch = my / kFftKC, k = my - ch * kFftKC;
+                cy[((size_t)(rt * nchunks + ch) * 72 + row) * kFftLdA + k] = (double)cosl(two_pi * (((long long)my * iy) % f.ny) / f.ny);
+            }
         if ((rc = upload(m->allocs, cosx.data(), cosx.size(), &p))) return fail(rc);
         f.cosx = p;
         if ((rc = upload(m->allocs, cy.data(), cy.size(), &p))) return fail(rc);
         f.Cy = p;
-        BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_T, (size_t)6 * f.my_pad * f.npx_pad * sizeof(double)));
+        BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_T, (size_t)2 * f.ctiles * nchunks * kFftStageT * sizeof(double)));
         m->allocs.push_back(m->d_fft_T);
         BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_H, (size_t)6 * f.my * f.mx * sizeof(double)));
         m->allocs.push_back(m->d_fft_H);

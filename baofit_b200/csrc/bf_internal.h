@@ -69,8 +69,17 @@ struct DevFft {
     double pk_k0, pk_k1;    // table range; power-law continuation outside
     double pk_end[2][2], pk_slope[2][2];
     const double *cosx;     // [nx] cos(2 pi t / nx)
-    const double *Cy;       // [npy_pad][my_pad] cos(2 pi (my iy mod ny) / ny), zero padded
+    // tiling of the plane for fft_plane_kernel: rtiles x ctiles tiles of wr x ncf 8x8 fragments
+    int rtiles, ctiles, wr, ncf;
+    // Cy = cos(2 pi (my iy mod ny) / ny), stored in the kernel's shared-memory stage layout
+    // [rtile][chunk of 16 my][72 rows][20] (zero padded) so that a stage is one contiguous bulk copy
+    const double *Cy;
 };
+constexpr int kFftKC = 16;                 // k_par rows per pipeline stage of fft_plane_kernel
+constexpr int kFftLdA = kFftKC + 4;        // row stride of a Cy stage
+constexpr int kFftLdT = 9 * 8 + 4;         // row stride of a T stage (4 mod 8 doubles: conflict-free)
+constexpr int kFftStageA = 9 * 8 * kFftLdA;        // doubles
+constexpr int kFftStageT = 3 * kFftKC * kFftLdT;   // doubles
 
 // Immutable model description passed by value to kernels.
 struct DevModel {
@@ -140,8 +149,9 @@ struct bf_model {
     mutable bool cache_valid = false;
     double metal_dx = 0, metal_dy = 0;
     double zref = 0;
-    // FFT model: per-key tables T[2 comps][3 powers of mu^2][my_pad][npx_pad] (x-transformed,
-    // weights folded in) and the scratch H[2][3][my][mx] they are built from
+    // FFT model: per-key tables T (x-transformed, weights folded in), stored in the plane kernel's
+    // stage layout [2 comps][ctiles][chunks][3 powers of mu^2][16][76], and the scratch
+    // H[2][3][my][mx] they are built from
     mutable double *d_fft_T = nullptr, *d_fft_H = nullptr;
 };
 

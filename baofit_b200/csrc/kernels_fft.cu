@@ -22,6 +22,8 @@
 //     on the FP64 tensor pipe (fft_plane_kernel, DMMA m8n8k4), the right operand built on the fly
 //     in shared memory,
 //   * per (bin, vector): two bicubic look-ups on the planes (fft_eval_kernel).
+#include <cstdlib>
+
 #include "device_math.cuh"
 #include "kernels.h"
 
@@ -105,13 +107,15 @@ __global__ void __launch_bounds__(128) fft_hsum_kernel(DevModel m, FftKeyState k
     H[(size_t)(comp * 3 + 2) * plane + o] = a2;
 }
 
-// T[comp*3+j][my][ix] = norm w_my sum_mx w_mx cos(2 pi mx ix / nx) H[comp*3+j][my][mx]; rows my >= My are zero
+// T[comp*3+j][my][ix] = norm w_my sum_mx w_mx cos(2 pi mx ix / nx) H[comp*3+j][my][mx], stored in the stage
+// layout of fft_plane_kernel: [comp][ctile][chunk][j][kr][kFftLdT]; rows my >= My and columns >= npx are zero
 __global__ void __launch_bounds__(128) fft_xtrans_kernel(DevModel m, const double *__restrict__ H, double *__restrict__ T) {
     const DevFft &f = m.fft;
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x, my = blockIdx.y, t = blockIdx.z;
-    if (ix >= f.npx_pad) return;
+    const int ixl = threadIdx.x, ctile = blockIdx.x, my = blockIdx.y, t = blockIdx.z;
+    if (ixl >= kFftLdT) return;
+    const int ix = ctile * f.ncf * 8 + ixl;
     double s = 0.0;
-    if (my < f.my && ix < f.npx) {
+    if (my < f.my && ix < f.npx && ixl < f.ncf * 8) {
         const double *h = H + ((size_t)t * f.my + my) * f.mx;
         for (int mx = 0; mx < f.mx; ++mx) {
             const double w = (mx == 0 || 2 * mx == f.nx) ? 1.0 : 2.0;
@@ -119,13 +123,14 @@ __global__ void __launch_bounds__(128) fft_xtrans_kernel(DevModel m, const doubl
         }
         s *= f.norm * ((my == 0 || 2 * my == f.ny) ? 1.0 : 2.0);
     }
-    T[((size_t)t * f.my_pad + my) * f.npx_pad + ix] = s;
+    const int comp = t / 3, j = t - comp * 3, chunk = my / kFftKC, kr = my - chunk * kFftKC, nchunks = f.my_pad / kFftKC;
+    T[((((size_t)(comp * f.ctiles + ctile) * nchunks + chunk) * 3 + j) * kFftKC + kr) * kFftLdT + ixl] = s;
 }
 
 void launch_fft_tables(cudaStream_t s, const DevModel &m, const FftKeyState &k, double *H, double *T) {
     const DevFft &f = m.fft;
     fft_hsum_kernel<<<dim3((f.mx + 127) / 128, f.my, 2), 128, 0, s>>>(m, k, H);
-    fft_xtrans_kernel<<<dim3((f.npx_pad + 127) / 128, f.my_pad, 6), 128, 0, s>>>(m, H, T);
+    fft_xtrans_kernel<<<dim3(f.ctiles, f.my_pad, 6), 128, 0, s>>>(m, H, T);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -232,23 +237,47 @@ void launch_fft_vec(cudaStream_t s, const FftVecArgs &a) {
 // ------------------------------------------------------------------------------------------
 namespace {
 constexpr int PV = 4;        // parameter vectors per CTA
-constexpr int PKC = 16;      // k depth (k_par rows) per pipeline stage
-constexpr int PMAXF = 9;     // at most 9 row fragments (warps) and 9 column fragments per CTA
-constexpr int PLDA = PKC + 4;
-constexpr int PLDT = PMAXF * 8;
-constexpr int PLDS = PMAXF * 8 + 4;
-constexpr int P_A = PMAXF * 8 * PLDA;  // doubles per stage
-constexpr int P_T = 3 * PKC * PLDT;
-constexpr int P_S = PV * PKC * PLDS;
+constexpr int PKC = kFftKC;  // k depth (k_par rows) per pipeline stage
+constexpr int PSTAGES = 5;   // TMA stages of the Cy / T_j tiles
+constexpr int PLDA = kFftLdA, PLDT = kFftLdT, P_A = kFftStageA, P_T = kFftStageT;
 
-__device__ __forceinline__ void p_cp_async16(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
 __device__ __forceinline__ void p_dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void p_mbar_init(unsigned long long *bar, int count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void p_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void p_mbar_arrive(unsigned long long *bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void p_mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar), ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void p_tma_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                 "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
 }
 }  // namespace
 
@@ -258,122 +287,158 @@ struct FftPlaneArgs {
     int ldb;
     const int *cols;  // columns of the vectors to transform (null: 0..count-1)
     int count;
-    int wr, ncf;  // row fragments and column fragments per CTA tile (each at most 9)
     double *planes;
 };
 
-// CTA = PV vectors x one component x one (<= 72 x 72) tile of the plane. Warp w works on vector
-// w & 3 and the three 8-row fragments (w >> 2)*3 + {0,1,2}: 3 x 9 accumulator fragments per warp,
-// 3 A and 9 B fragment loads per 27 DMMAs.
+// CTA = PV vectors x one component x one (<= 72 x 72) tile of the plane; warp w works on vector
+// w & 3 and the column group w >> 2 (three 8-column fragments) over all row fragments of the tile:
+// 9 x 3 accumulator fragments, 9 A + 9 T fragment loads per 27 DMMAs.
+//   * The per-vector operands are never materialised: the continuum-fitting factor cont_v[my] scales
+//     the A fragments (a column scaling of Cy) and each B fragment T0 + c1_v T1 + c2_v T2 is combined
+//     in registers from the three static tiles (2 DFMA per B fragment feeding 9 DMMAs).
+//   * Cy and T_j are stored in global memory in exactly the padded stage layout, so one stage is
+//     two contiguous TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by one thread; "full"
+//     mbarriers carry the byte counts, "empty" mbarriers count the consumer warps. No CTA-wide
+//     barrier inside the k loop: warps drift apart by up to PSTAGES-1 chunks, so the FP64 tensor
+//     pipe never drains at chunk boundaries.
+// NCF (column fragments per tile) is a template parameter: all tile index arithmetic is constant.
+template <int NCF>
 __global__ void __launch_bounds__(PV * 3 * 32, 1) fft_plane_kernel(FftPlaneArgs a) {
-    extern __shared__ __align__(16) double psm[];
+    extern __shared__ __align__(128) double psm[];
     const DevFft &f = a.f;
-    double *As = psm;                 // [2][wr*8][PLDA]
-    double *Ts = As + 2 * P_A;        // [2][3][PKC][PLDT]
-    double *Ss = Ts + 2 * P_T;        // [2][PV][PKC][PLDS]
-    double *conts = Ss + 2 * P_S;     // [PV][my_pad]
+    constexpr int NCOLS = NCF * 8, NRF = 9;
+    double *As = psm;                    // [PSTAGES][72][PLDA]
+    double *Ts = As + PSTAGES * P_A;     // [PSTAGES][3][PKC][PLDT]
+    double *conts = Ts + PSTAGES * P_T;  // [PV][my_pad]
     __shared__ double c12s[2][PV];
     __shared__ int colv[PV];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(8) unsigned long long full_bar[PSTAGES], empty_bar[PSTAGES];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int l4 = lane & 3, l8 = lane >> 2;
-    const int wv = warp & (PV - 1), rf0 = (warp >> 2) * 3;
+    const int wv = warp & (PV - 1), cf0 = (warp >> 2) * 3;  // vector, first column fragment
+    const int ncf = min(3, NCF - cf0);                       // column fragments of this warp
     const int b0 = (blockIdx.x >> 1) * PV, comp = blockIdx.x & 1;
-    const int row0 = blockIdx.y * a.wr * 8, col0 = blockIdx.z * a.ncf * 8;
-    const int ncols = min(a.ncf * 8, f.npx_pad - col0);   // multiple of 8
-    const int ncf = ncols >> 3;
-    const int nrows = min(a.wr * 8, f.npy_pad - row0);
+    const int rtile = blockIdx.y, ctile = blockIdx.z;
+    const int row0 = rtile * f.wr * 8, col0 = ctile * NCOLS;
+    const int nrows = min(f.wr * 8, f.npy_pad - row0);
+    const int nrf = nrows >> 3;
+    const int ncols_valid = min(NCOLS, f.npx_pad - col0);
     const int nchunks = f.my_pad / PKC;
+    const double *gA = f.Cy + (size_t)rtile * nchunks * P_A;
+    const double *gT = a.T + (size_t)(comp * f.ctiles + ctile) * nchunks * P_T;
+    constexpr unsigned kStageBytes = (unsigned)((P_A + P_T) * sizeof(double));
 
+    auto issue = [&](int chunk) {  // one thread
+        const int slot = chunk % PSTAGES;
+        p_mbar_expect_tx(&full_bar[slot], kStageBytes);
+        p_tma_g2s(As + slot * P_A, gA + (size_t)chunk * P_A, (unsigned)(P_A * sizeof(double)), &full_bar[slot]);
+        p_tma_g2s(Ts + slot * P_T, gT + (size_t)chunk * P_T, (unsigned)(P_T * sizeof(double)), &full_bar[slot]);
+    };
+
+    if (tid == 0) {
+        for (int st = 0; st < PSTAGES; ++st) { p_mbar_init(&full_bar[st], 1); p_mbar_init(&empty_bar[st], nwarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
     if (tid < PV) {
         const int i = min(b0 + tid, a.count - 1);  // slots beyond the list repeat its last vector; not stored
         colv[tid] = a.cols ? a.cols[i] : i;
     }
     __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < PSTAGES && c < nchunks; ++c) issue(c);
     for (int i = tid; i < PV * f.my_pad; i += nthr) {
         int v = i / f.my_pad, my = i - v * f.my_pad;
         conts[i] = a.cont[(size_t)my * a.ldb + colv[v]];
     }
     if (tid < 2 * PV) c12s[tid / PV][tid % PV] = a.c12[(size_t)(tid / PV) * a.ldb + colv[tid % PV]];
+    __syncthreads();
+    const double c1 = c12s[0][wv], c2 = c12s[1][wv];
 
-    auto load_stage = [&](int slot, int chunk) {
-        const int k0 = chunk * PKC;
-        double *as = As + slot * P_A, *ts = Ts + slot * P_T;
-        // Cy rows of this tile: [nrows][PKC]
-        for (int c = tid; c < nrows * (PKC / 2); c += nthr) {
-            int row = c / (PKC / 2), ch = c % (PKC / 2);
-            p_cp_async16(as + row * PLDA + ch * 2, f.Cy + (size_t)(row0 + row) * f.my_pad + k0 + ch * 2);
-        }
-        // T_j rows: [3][PKC][ncols]
-        const int per_row = ncols / 2;
-        for (int c = tid; c < 3 * PKC * per_row; c += nthr) {
-            int j = c / (PKC * per_row), rem = c - j * PKC * per_row, kr = rem / per_row, ch = rem - kr * per_row;
-            p_cp_async16(ts + (j * PKC + kr) * PLDT + ch * 2,
-                         a.T + ((size_t)(comp * 3 + j) * f.my_pad + k0 + kr) * f.npx_pad + col0 + ch * 2);
-        }
-    };
+    double acc[NRF][3][2];
+#pragma unroll
+    for (int mi = 0; mi < NRF; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const bool full_tile = nrf == NRF && ncf == 3;  // warp-uniform: the common case runs unpredicated
 
-    double acc[3][PMAXF][2];
-#pragma unroll
-    for (int mi = 0; mi < 3; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < PMAXF; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    // rows beyond the tile read row 0 of the stage (finite values), their results are dropped
-    int arow[3];
-#pragma unroll
-    for (int mi = 0; mi < 3; ++mi) arow[mi] = (rf0 + mi) * 8 < nrows ? (rf0 + mi) * 8 + l8 : 0;
-    const bool active = rf0 * 8 < nrows;
-
-    load_stage(0, 0);
-    asm volatile("cp.async.commit_group;\n" ::);
     for (int t = 0; t < nchunks; ++t) {
-        const int slot = t & 1;
-        asm volatile("cp.async.wait_group 0;\n" ::);
-        __syncthreads();  // stage t landed; everyone is done with the buffers of chunk t-1
-        if (t + 1 < nchunks) load_stage(slot ^ 1, t + 1);
-        asm volatile("cp.async.commit_group;\n" ::);
-        // right operand of this chunk: S_v[kr][ix] = cont_v[k0+kr] (T0 + c1_v T1 + c2_v T2)[kr][ix]
-        {
-            const double *ts = Ts + slot * P_T;
-            double *ss = Ss + slot * P_S;
-            const int k0 = t * PKC;
-            for (int e = tid; e < PKC * ncols; e += nthr) {
-                int kr = e / ncols, ix = e - kr * ncols;
-                double t0 = ts[kr * PLDT + ix], t1 = ts[(PKC + kr) * PLDT + ix], t2 = ts[(2 * PKC + kr) * PLDT + ix];
-#pragma unroll
-                for (int v = 0; v < PV; ++v)
-                    ss[(v * PKC + kr) * PLDS + ix] = conts[v * f.my_pad + k0 + kr] * fma(c12s[1][v], t2, fma(c12s[0][v], t1, t0));
-            }
+        const int slot = t % PSTAGES;
+        if (tid == 0 && t >= 1 && t - 1 + PSTAGES < nchunks) {
+            // refill the stage of chunk t-1 once every warp has released it
+            p_mbar_wait(&empty_bar[(t - 1) % PSTAGES], ((t - 1) / PSTAGES) & 1);
+            issue(t - 1 + PSTAGES);
         }
-        __syncthreads();
-        if (active) {
-            const double *as = As + slot * P_A + l4;
-            const double *ss = Ss + slot * P_S + (wv * PKC + l4) * PLDS + l8;
+        __syncwarp();
+        p_mbar_wait(&full_bar[slot], (t / PSTAGES) & 1);
+        if (ncf > 0) {
+            const double *as = As + slot * P_A + l8 * PLDA + l4;
+            const double *ts = Ts + slot * P_T + l4 * PLDT + cf0 * 8 + l8;
+            const double *cs = conts + wv * f.my_pad + t * PKC + l4;
+            if (full_tile) {
 #pragma unroll
-            for (int kk = 0; kk < PKC; kk += 4) {
-                double af[3];
+                for (int kk = 0; kk < PKC; kk += 4) {
+                    const double cv = cs[kk];
+                    double bf[3];
 #pragma unroll
-                for (int mi = 0; mi < 3; ++mi) af[mi] = as[arow[mi] * PLDA + kk];
-#pragma unroll
-                for (int ni = 0; ni < PMAXF; ++ni)
-                    if (ni < ncf) {
-                        const double bf = ss[kk * PLDS + ni * 8];
-#pragma unroll
-                        for (int mi = 0; mi < 3; ++mi) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
+                    for (int ni = 0; ni < 3; ++ni) {
+                        const double *tp = ts + kk * PLDT + ni * 8;
+                        bf[ni] = fma(c2, tp[2 * PKC * PLDT], fma(c1, tp[PKC * PLDT], tp[0]));
                     }
+#pragma unroll
+                    for (int mi = 0; mi < NRF; ++mi) {
+                        const double af = as[mi * 8 * PLDA + kk] * cv;
+#pragma unroll
+                        for (int ni = 0; ni < 3; ++ni) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < PKC; kk += 4) {
+                    const double cv = cs[kk];
+                    double bf[3];
+#pragma unroll
+                    for (int ni = 0; ni < 3; ++ni) {
+                        const double *tp = ts + kk * PLDT + (ni < ncf ? ni * 8 : 0);
+                        bf[ni] = fma(c2, tp[2 * PKC * PLDT], fma(c1, tp[PKC * PLDT], tp[0]));
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < NRF; ++mi) {
+                        if (mi < nrf) {
+                            const double af = as[mi * 8 * PLDA + kk] * cv;
+#pragma unroll
+                            for (int ni = 0; ni < 3; ++ni)
+                                if (ni < ncf) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
+                        }
+                    }
+                }
             }
         }
+        __syncwarp();
+        if (lane == 0) p_mbar_arrive(&empty_bar[slot]);
     }
-    if (active && b0 + wv < a.count) {
+    if (ncf > 0 && b0 + wv < a.count) {
 #pragma unroll
-        for (int mi = 0; mi < 3; ++mi) {
-            if ((rf0 + mi) * 8 >= nrows) continue;
-            const int row = row0 + (rf0 + mi) * 8 + l8;
-            double *dst = a.planes + (((size_t)colv[wv] * 2 + comp) * f.npy_pad + row) * f.npx_pad + col0 + 2 * l4;
+        for (int mi = 0; mi < NRF; ++mi) {
+            if (mi >= nrf) continue;
+            const int row = row0 + mi * 8 + l8;
+            double *dst = a.planes + (((size_t)colv[wv] * 2 + comp) * f.npy_pad + row) * f.npx_pad + col0 + cf0 * 8 + 2 * l4;
 #pragma unroll
-            for (int ni = 0; ni < PMAXF; ++ni)
-                if (ni < ncf) *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            for (int ni = 0; ni < 3; ++ni)
+                if (ni < ncf && (cf0 + ni) * 8 < ncols_valid)
+                    *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
     }
+}
+
+template <int NCF>
+static void launch_fft_planes_t(cudaStream_t s, const FftPlaneArgs &a, dim3 grid, int threads, size_t smem) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fft_plane_kernel<NCF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        attr = true;
+    }
+    fft_plane_kernel<NCF><<<grid, threads, smem, s>>>(a);
 }
 
 void launch_fft_planes(cudaStream_t s, const DevModel &m, const double *T, const double *c12, const double *cont,
@@ -381,19 +446,20 @@ void launch_fft_planes(cudaStream_t s, const DevModel &m, const double *T, const
     const DevFft &f = m.fft;
     FftPlaneArgs a;
     a.f = f; a.T = T; a.c12 = c12; a.cont = cont; a.ldb = ldb; a.cols = cols; a.count = count; a.planes = planes;
-    const int nrf = f.npy_pad / 8, ncfr = f.npx_pad / 8;
-    const int rtiles = (nrf + PMAXF - 1) / PMAXF, ctiles = (ncfr + PMAXF - 1) / PMAXF;
-    a.wr = (nrf + rtiles - 1) / rtiles;
-    a.ncf = (ncfr + ctiles - 1) / ctiles;
-    const size_t smem = (size_t)(2 * P_A + 2 * P_T + 2 * P_S + PV * f.my_pad) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(fft_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr = true;
+    const size_t smem = (size_t)(PSTAGES * (P_A + P_T) + PV * f.my_pad) * sizeof(double);
+    dim3 grid(2 * ((count + PV - 1) / PV), f.rtiles, f.ctiles);
+    const int threads = PV * ((f.ncf + 2) / 3) * 32;  // (vector, column group of three fragments)
+    switch (f.ncf) {
+    case 1: launch_fft_planes_t<1>(s, a, grid, threads, smem); break;
+    case 2: launch_fft_planes_t<2>(s, a, grid, threads, smem); break;
+    case 3: launch_fft_planes_t<3>(s, a, grid, threads, smem); break;
+    case 4: launch_fft_planes_t<4>(s, a, grid, threads, smem); break;
+    case 5: launch_fft_planes_t<5>(s, a, grid, threads, smem); break;
+    case 6: launch_fft_planes_t<6>(s, a, grid, threads, smem); break;
+    case 7: launch_fft_planes_t<7>(s, a, grid, threads, smem); break;
+    case 8: launch_fft_planes_t<8>(s, a, grid, threads, smem); break;
+    default: launch_fft_planes_t<9>(s, a, grid, threads, smem); break;
     }
-    dim3 grid(2 * ((count + PV - 1) / PV), rtiles, ctiles);
-    const int row_groups = (a.wr + 2) / 3;
-    fft_plane_kernel<<<grid, PV * row_groups * 32, smem, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="vectors per step of the CPU arms (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan", action="store_true", help="skip the 2-D scan measurement")
+    ap.add_argument("--no-fft", action="store_true", help="skip the FFT-model (BASELINE configs[4]) measurements")
+    ap.add_argument("--fft-batch", type=int, default=18944, help="parameter vectors per step per GPU of the FFT-model leg")
+    ap.add_argument("--toys", type=int, default=512, help="toy-MC realisations per GPU refitted in the FFT-model leg")
     return ap.parse_args()
 
 
@@ -182,6 +185,104 @@ def run_scan(rank, world, dev):
             "reference_seconds_per_fit": 1.7, "reference_source": "config/BOSSDR11QSOLyaF_k.ini:11-12 (hardware unspecified)"}
 
 
+def run_fft(args, rank, world, dev, ctx):
+    """BASELINE configs[4], config/BOSSDR11LyaF_fft.ini: BaoKSpaceFftCorrelationModel on a 400^3 grid of
+    4 Mpc/h cells, 1515 data bins, synthetic data vector and covariance (the reference ships neither).
+    (1) batched chi2 evaluations per second with device-resident parameters, per-kernel shares and
+    the FP64-tensor roofline of the per-vector transform; (2) toy-MC realisations refitted per second
+    through the host-side CorrelationAnalyzer (5 floating parameters each), toys sharded over ranks,
+    one all-gather."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from baofit_b200 import capi, host_api, shard, workloads as W
+    m, coords = W.dr11_auto_fft()
+
+    def predict(model, data, params):
+        gm, gd = capi.Model(ctx, model), capi.Data(ctx, data)
+        pred, _ = capi.eval_batch(ctx, gm, gd, params)
+        gm.close(), gd.close()
+        return pred[:, 0]
+
+    d, _ = W.synthetic_dataset(m, coords, predict)
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    B, K, Wm = args.fft_batch, max(3, min(args.steps, 10)), 3
+    sweep = {"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)}
+    rng = np.random.Generator(np.random.PCG64(500 + rank))
+    nb = 4
+    d_params = [torch.from_numpy(m.random_batch(B, rng, sweep=sweep)).to(dev) for _ in range(nb)]
+    d_chi2 = torch.empty(B, dtype=torch.float64, device=dev)
+    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    for i in range(Wm):
+        capi.chi2_batch_dev(ctx, gm, gd, d_params[i % nb].data_ptr(), B, d_chi2.data_ptr(), d_status.data_ptr())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record()
+    for i in range(K):
+        capi.chi2_batch_dev(ctx, gm, gd, d_params[(Wm + i) % nb].data_ptr(), B, d_chi2.data_ptr(), d_status.data_ptr())
+    with torch.cuda.stream(ext):
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    bad = int((d_status != 0).sum().item())
+    ctx.set_profiling(True)
+    for i in range(K):
+        capi.chi2_batch_dev(ctx, gm, gd, d_params[(Wm + i) % nb].data_ptr(), B, d_chi2.data_ptr(), d_status.data_ptr())
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    total = sum(v[0] for v in prof.values())
+    _, _, fp64, _ = load_peaks()
+    npx = npy = int(np.floor(180. * 1.5 / 4.)) + 3
+    fl = {"fft_plane_kernel": 2 * 2.0 * npy * 201 * npx, "dgemm_chi2_kernel": 1.0 * d.n_data ** 2 + 3.0 * d.n_data}
+    kernels = {}
+    for name, (msk, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ent = {"ms_per_launch": msk / cnt, "launches": int(cnt), "share": msk / total}
+        if name in fl:
+            ent["tflops"] = fl[name] * B / (msk / cnt * 1e-3) * 1e-12
+            ent["frac_of_fp64_peak"] = ent["tflops"] / fp64
+        kernels[name] = ent
+    out = {"workload": "BOSSDR11LyaF_fft: BaoKSpaceFftCorrelationModel, 400^3 cells of 4 Mpc/h, N_data=1515, nl-correction, zcorr; synthetic data+cov",
+           "evals_per_s": world * B * K / (ms * 1e-3), "ms_per_step": ms / K, "batch_per_gpu_per_step": B, "steps": K,
+           "vectors_outside_plane": bad, "kernels": kernels,
+           "flops_per_eval": {"plane_transform": fl["fft_plane_kernel"], "chi2": fl["dgemm_chi2_kernel"]}}
+    gm.close(), gd.close()
+    # ---- toy-MC study through the host classes (files in the reference's formats) ----
+    if args.toys > 0:
+        tree = W.make_golden_tree(os.path.join(tempfile.gettempdir(), "baofit_b200_fft_%d" % os.getpid()))
+        W.write_dataset_files(os.path.join(tree, "data", "BOSSDR11LyaF_synth"), 2500, coords[3], d.keep._arrays[4], d.keep._arrays[5])
+        text = open(os.path.join(tree, "config", "BOSSDR11LyaF_fft.ini")).read().replace("data = ../data/BOSSDR11LyaF", "data = ../data/BOSSDR11LyaF_synth")
+        s = host_api.Session(text, os.path.join(tree, "config"))
+        s.toymc(0, 4, seed=1)  # warm-up
+        ntoys = args.toys * world
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = shard.toymc_sharded(s, ntoys, seed=1966, device=dev if world > 1 else None)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        ia, ip = s.names.index("BAO alpha-parallel"), s.names.index("BAO alpha-perp")
+        good = res["status"] != 2
+        out["toymc"] = {"toys": int(ntoys), "seconds": dt, "toys_per_s": ntoys / dt, "floating_parameters": int(s.floating.sum()),
+                        "failed_fits": int((~good).sum()), "mean_chi2": float(res["chi2"][good].mean()), "ndof": int(s.ndata - s.floating.sum()),
+                        "alpha_parallel_mean_std": [float(res["fitted"][good, ia].mean()), float(res["fitted"][good, ia].std())],
+                        "alpha_perp_mean_std": [float(res["fitted"][good, ip].mean()), float(res["fitted"][good, ip].std())]}
+        s.close()
+    return out
+
+
 def main_reference(args, rank, world):
     if rank != 0:
         return
@@ -299,6 +400,7 @@ def main_ours(args, rank, world, local_rank):
     prof = ctx.get_profile()
     ctx.set_profiling(False)
     scan = None if args.no_scan else run_scan(rank, world, dev)
+    fft = None if args.no_fft else run_fft(args, rank, world, dev, ctx)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,7 +458,7 @@ def main_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * npar * 8, "d2h_bytes_per_step": B * 12,
                     "api": "bf_chi2_batch (host buffers, pinned)"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "scan": scan, "kernels": kernels,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "scan": scan, "fft": fft, "kernels": kernels,
             "chi2_checksum": chi2_check}
     print(json.dumps(line))
     if world > 1:

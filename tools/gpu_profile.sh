@@ -12,7 +12,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; e
 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"; cat $OUT/bench_$TAG.json
 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref exit $?"; cat $OUT/bench_ref_$TAG.json
 kill $SMI
-CMD="python bench.py --steps 3 --warmup 3 --no-scan --no-cpu-baseline"
+CMD="python bench.py --steps 3 --warmup 3 --no-scan --no-cpu-baseline --no-fft"
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
