@@ -284,6 +284,11 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         f.nx = d->fft_nx; f.ny = d->fft_ny; f.nz = d->fft_nz;
         f.mx = f.nx / 2 + 1; f.my = f.ny / 2 + 1; f.mz = f.nz / 2 + 1;
         f.my_pad = round_up(f.my, 16);
+        // fft_plane_kernel keeps two sets of k_par tables (4 vectors each) next to >= 2 pipeline stages in shared memory
+        if ((size_t)2 * 4 * f.my_pad * sizeof(double) + 2 * (size_t)(kFftStageA + kFftStageT) * sizeof(double) > (size_t)226 * 1024) {
+            bf::set_error("BaoKSpaceFftCorrelationModel: ngridy too large for the shared-memory pipeline (ngridy <= 4600)");
+            return fail(BF_ERR_MODEL);
+        }
         f.delta = d->fft_spacing; f.inv_delta = 1.0 / d->fft_spacing;
         f.norm = 1.0 / ((double)f.nx * f.ny * f.nz * f.delta * f.delta * f.delta);
         f.zcorr0 = d->zcorr0; f.zcorr1 = d->zcorr1; f.zcorr2 = d->zcorr2;

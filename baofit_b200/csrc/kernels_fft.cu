@@ -22,6 +22,7 @@
 //     on the FP64 tensor pipe (fft_plane_kernel, DMMA m8n8k4), the right operand built on the fly
 //     in shared memory,
 //   * per (bin, vector): two bicubic look-ups on the planes (fft_eval_kernel).
+#include <algorithm>
 #include <cstdlib>
 
 #include "device_math.cuh"
@@ -238,7 +239,7 @@ void launch_fft_vec(cudaStream_t s, const FftVecArgs &a) {
 namespace {
 constexpr int PV = 4;        // parameter vectors per CTA
 constexpr int PKC = kFftKC;  // k depth (k_par rows) per pipeline stage
-constexpr int PSTAGES = 5;   // TMA stages of the Cy / T_j tiles
+constexpr int PSTAGES = 5;   // at most 5 TMA stages of the Cy / T_j tiles (fewer if k_par tables crowd shared memory)
 constexpr int PLDA = kFftLdA, PLDT = kFftLdT, P_A = kFftStageA, P_T = kFftStageT;
 
 __device__ __forceinline__ void p_dmma(double &c0, double &c1, double a, double b) {
@@ -287,6 +288,7 @@ struct FftPlaneArgs {
     int ldb;
     const int *cols;  // columns of the vectors to transform (null: 0..count-1)
     int count;
+    int nstages;  // pipeline depth actually used, 2..PSTAGES
     double *planes;
 };
 
@@ -307,17 +309,16 @@ __global__ void __launch_bounds__(PV * 3 * 32, 1) fft_plane_kernel(FftPlaneArgs 
     extern __shared__ __align__(128) double psm[];
     const DevFft &f = a.f;
     constexpr int NCOLS = NCF * 8, NRF = 9;
-    double *As = psm;                    // [PSTAGES][72][PLDA]
-    double *Ts = As + PSTAGES * P_A;     // [PSTAGES][3][PKC][PLDT]
-    double *conts = Ts + PSTAGES * P_T;  // [PV][my_pad]
-    __shared__ double c12s[2][PV];
-    __shared__ int colv[PV];
+    const int NS = a.nstages;
+    double *As = psm;               // [NS][72][PLDA]
+    double *Ts = As + NS * P_A;     // [NS][3][PKC][PLDT]
+    double *conts = Ts + NS * P_T;  // [2 item parities][PV][my_pad]
+    __shared__ double c12s[2][2][PV];
     __shared__ __align__(8) unsigned long long full_bar[PSTAGES], empty_bar[PSTAGES];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int l4 = lane & 3, l8 = lane >> 2;
     const int wv = warp & (PV - 1), cf0 = (warp >> 2) * 3;  // vector, first column fragment
     const int ncf = min(3, NCF - cf0);                       // column fragments of this warp
-    const int b0 = (blockIdx.x >> 1) * PV, comp = blockIdx.x & 1;
     const int rtile = blockIdx.y, ctile = blockIdx.z;
     const int row0 = rtile * f.wr * 8, col0 = ctile * NCOLS;
     const int nrows = min(f.wr * 8, f.npy_pad - row0);
@@ -325,108 +326,155 @@ __global__ void __launch_bounds__(PV * 3 * 32, 1) fft_plane_kernel(FftPlaneArgs 
     const int ncols_valid = min(NCOLS, f.npx_pad - col0);
     const int nchunks = f.my_pad / PKC;
     const double *gA = f.Cy + (size_t)rtile * nchunks * P_A;
-    const double *gT = a.T + (size_t)(comp * f.ctiles + ctile) * nchunks * P_T;
     constexpr unsigned kStageBytes = (unsigned)((P_A + P_T) * sizeof(double));
 
-    auto issue = [&](int chunk) {  // one thread
-        const int slot = chunk % PSTAGES;
+    // Persistent CTA: work items (vector group, component) i = blockIdx.x, blockIdx.x + gridDim.x, ...
+    // The stage pipeline runs across item boundaries (global chunk counter gc), so the prologue,
+    // the epilogue stores and the TMA latency of one item hide behind its neighbours.
+    const bool full_tile = nrf == NRF && ncf == 3;  // warp-uniform: the common case runs unpredicated
+    const int ngroups = (a.count + PV - 1) / PV, nitems = 2 * ngroups;
+    const int my_items = blockIdx.x < nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int total_chunks = my_items * nchunks;
+    auto issue = [&](int gc) {  // one thread
+        const int slot = gc % NS, it = gc / nchunks, chunk = gc - it * nchunks;
+        const int comp = (blockIdx.x + it * gridDim.x) & 1;
+        const double *gT = a.T + (size_t)(comp * f.ctiles + ctile) * nchunks * P_T;
         p_mbar_expect_tx(&full_bar[slot], kStageBytes);
         p_tma_g2s(As + slot * P_A, gA + (size_t)chunk * P_A, (unsigned)(P_A * sizeof(double)), &full_bar[slot]);
         p_tma_g2s(Ts + slot * P_T, gT + (size_t)chunk * P_T, (unsigned)(P_T * sizeof(double)), &full_bar[slot]);
     };
+    auto item_col = [&](int it, int v) {  // column of vector slot v of item it (clamped; extra slots are not stored)
+        const int i = min(((blockIdx.x + it * gridDim.x) >> 1) * PV + v, a.count - 1);
+        return a.cols ? a.cols[i] : i;
+    };
 
     if (tid == 0) {
-        for (int st = 0; st < PSTAGES; ++st) { p_mbar_init(&full_bar[st], 1); p_mbar_init(&empty_bar[st], nwarps); }
+        for (int st = 0; st < NS; ++st) { p_mbar_init(&full_bar[st], 1); p_mbar_init(&empty_bar[st], nwarps); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
-    if (tid < PV) {
-        const int i = min(b0 + tid, a.count - 1);  // slots beyond the list repeat its last vector; not stored
-        colv[tid] = a.cols ? a.cols[i] : i;
-    }
     __syncthreads();
+    if (my_items == 0) return;
     if (tid == 0)
-        for (int c = 0; c < PSTAGES && c < nchunks; ++c) issue(c);
+        for (int c = 0; c < NS && c < total_chunks; ++c) issue(c);
+    // per-vector scalars of the first item; later items are prefetched one item ahead
+    constexpr int kContRegs = 3;  // registers per thread for that prefetch; larger k_par tables are copied in place
+    const bool pre_ok = PV * f.my_pad <= kContRegs * nthr;
     for (int i = tid; i < PV * f.my_pad; i += nthr) {
         int v = i / f.my_pad, my = i - v * f.my_pad;
-        conts[i] = a.cont[(size_t)my * a.ldb + colv[v]];
+        conts[i] = a.cont[(size_t)my * a.ldb + item_col(0, v)];
     }
-    if (tid < 2 * PV) c12s[tid / PV][tid % PV] = a.c12[(size_t)(tid / PV) * a.ldb + colv[tid % PV]];
-    __syncthreads();
-    const double c1 = c12s[0][wv], c2 = c12s[1][wv];
+    if (tid < 2 * PV) c12s[0][tid / PV][tid % PV] = a.c12[(size_t)(tid / PV) * a.ldb + item_col(0, tid % PV)];
 
-    double acc[NRF][3][2];
+    for (int it = 0; it < my_items; ++it) {
+        const int par = it & 1;
+        __syncthreads();  // scalars of this item are in place; everyone has left item it-1
+        const int item = blockIdx.x + it * gridDim.x, b0 = (item >> 1) * PV, comp = item & 1;
+        const double c1 = c12s[par][0][wv], c2 = c12s[par][1][wv];
+        const int mycol = item_col(it, wv);
+        // prefetch the scalars of the next item into registers; stored after this item's k loop
+        double cpre[kContRegs], c12pre = 0.0;
+        const bool have_next = it + 1 < my_items;
+        if (have_next && pre_ok) {
 #pragma unroll
-    for (int mi = 0; mi < NRF; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    const bool full_tile = nrf == NRF && ncf == 3;  // warp-uniform: the common case runs unpredicated
-
-    for (int t = 0; t < nchunks; ++t) {
-        const int slot = t % PSTAGES;
-        if (tid == 0 && t >= 1 && t - 1 + PSTAGES < nchunks) {
-            // refill the stage of chunk t-1 once every warp has released it
-            p_mbar_wait(&empty_bar[(t - 1) % PSTAGES], ((t - 1) / PSTAGES) & 1);
-            issue(t - 1 + PSTAGES);
-        }
-        __syncwarp();
-        p_mbar_wait(&full_bar[slot], (t / PSTAGES) & 1);
-        if (ncf > 0) {
-            const double *as = As + slot * P_A + l8 * PLDA + l4;
-            const double *ts = Ts + slot * P_T + l4 * PLDT + cf0 * 8 + l8;
-            const double *cs = conts + wv * f.my_pad + t * PKC + l4;
-            if (full_tile) {
-#pragma unroll
-                for (int kk = 0; kk < PKC; kk += 4) {
-                    const double cv = cs[kk];
-                    double bf[3];
-#pragma unroll
-                    for (int ni = 0; ni < 3; ++ni) {
-                        const double *tp = ts + kk * PLDT + ni * 8;
-                        bf[ni] = fma(c2, tp[2 * PKC * PLDT], fma(c1, tp[PKC * PLDT], tp[0]));
-                    }
-#pragma unroll
-                    for (int mi = 0; mi < NRF; ++mi) {
-                        const double af = as[mi * 8 * PLDA + kk] * cv;
-#pragma unroll
-                        for (int ni = 0; ni < 3; ++ni) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
-                    }
+            for (int q = 0; q < kContRegs; ++q) {
+                const int i = tid + q * nthr;
+                if (i < PV * f.my_pad) {
+                    int v = i / f.my_pad, my = i - v * f.my_pad;
+                    cpre[q] = a.cont[(size_t)my * a.ldb + item_col(it + 1, v)];
                 }
-            } else {
+            }
+            if (tid < 2 * PV) c12pre = a.c12[(size_t)(tid / PV) * a.ldb + item_col(it + 1, tid % PV)];
+        } else if (have_next && tid < 2 * PV)
+            c12pre = a.c12[(size_t)(tid / PV) * a.ldb + item_col(it + 1, tid % PV)];
+
+        double acc[NRF][3][2];
 #pragma unroll
-                for (int kk = 0; kk < PKC; kk += 4) {
-                    const double cv = cs[kk];
-                    double bf[3];
+        for (int mi = 0; mi < NRF; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 3; ++ni) {
-                        const double *tp = ts + kk * PLDT + (ni < ncf ? ni * 8 : 0);
-                        bf[ni] = fma(c2, tp[2 * PKC * PLDT], fma(c1, tp[PKC * PLDT], tp[0]));
-                    }
+            for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+        for (int t = 0; t < nchunks; ++t) {
+            const int gc = it * nchunks + t, slot = gc % NS;
+            if (tid == 0 && gc >= 1 && gc - 1 + NS < total_chunks) {
+                // refill the stage of chunk gc-1 once every warp has released it
+                p_mbar_wait(&empty_bar[(gc - 1) % NS], ((gc - 1) / NS) & 1);
+                issue(gc - 1 + NS);
+            }
+            __syncwarp();
+            p_mbar_wait(&full_bar[slot], (gc / NS) & 1);
+            if (ncf > 0) {
+                const double *as = As + slot * P_A + l8 * PLDA + l4;
+                const double *ts = Ts + slot * P_T + l4 * PLDT + cf0 * 8 + l8;
+                const double *cs = conts + (par * PV + wv) * f.my_pad + t * PKC + l4;
+                if (full_tile) {
 #pragma unroll
-                    for (int mi = 0; mi < NRF; ++mi) {
-                        if (mi < nrf) {
+                    for (int kk = 0; kk < PKC; kk += 4) {
+                        const double cv = cs[kk];
+                        double bf[3];
+#pragma unroll
+                        for (int ni = 0; ni < 3; ++ni) {
+                            const double *tp = ts + kk * PLDT + ni * 8;
+                            bf[ni] = fma(c2, tp[2 * PKC * PLDT], fma(c1, tp[PKC * PLDT], tp[0]));
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < NRF; ++mi) {
                             const double af = as[mi * 8 * PLDA + kk] * cv;
 #pragma unroll
-                            for (int ni = 0; ni < 3; ++ni)
-                                if (ni < ncf) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
+                            for (int ni = 0; ni < 3; ++ni) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < PKC; kk += 4) {
+                        const double cv = cs[kk];
+                        double bf[3];
+#pragma unroll
+                        for (int ni = 0; ni < 3; ++ni) {
+                            const double *tp = ts + kk * PLDT + (ni < ncf ? ni * 8 : 0);
+                            bf[ni] = fma(c2, tp[2 * PKC * PLDT], fma(c1, tp[PKC * PLDT], tp[0]));
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < NRF; ++mi) {
+                            if (mi < nrf) {
+                                const double af = as[mi * 8 * PLDA + kk] * cv;
+#pragma unroll
+                                for (int ni = 0; ni < 3; ++ni)
+                                    if (ni < ncf) p_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
+                            }
                         }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) p_mbar_arrive(&empty_bar[slot]);
         }
-        __syncwarp();
-        if (lane == 0) p_mbar_arrive(&empty_bar[slot]);
-    }
-    if (ncf > 0 && b0 + wv < a.count) {
+        if (have_next) {
+            if (pre_ok) {
 #pragma unroll
-        for (int mi = 0; mi < NRF; ++mi) {
-            if (mi >= nrf) continue;
-            const int row = row0 + mi * 8 + l8;
-            double *dst = a.planes + (((size_t)colv[wv] * 2 + comp) * f.npy_pad + row) * f.npx_pad + col0 + cf0 * 8 + 2 * l4;
+                for (int q = 0; q < kContRegs; ++q) {
+                    const int i = tid + q * nthr;
+                    if (i < PV * f.my_pad) conts[(par ^ 1) * PV * f.my_pad + i] = cpre[q];
+                }
+            } else {
+                for (int i = tid; i < PV * f.my_pad; i += nthr) {
+                    int v = i / f.my_pad, my = i - v * f.my_pad;
+                    conts[(par ^ 1) * PV * f.my_pad + i] = a.cont[(size_t)my * a.ldb + item_col(it + 1, v)];
+                }
+            }
+            if (tid < 2 * PV) c12s[par ^ 1][tid / PV][tid % PV] = c12pre;
+        }
+        if (ncf > 0 && b0 + wv < a.count) {
 #pragma unroll
-            for (int ni = 0; ni < 3; ++ni)
-                if (ni < ncf && (cf0 + ni) * 8 < ncols_valid)
-                    *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            for (int mi = 0; mi < NRF; ++mi) {
+                if (mi >= nrf) continue;
+                const int row = row0 + mi * 8 + l8;
+                double *dst = a.planes + (((size_t)mycol * 2 + comp) * f.npy_pad + row) * f.npx_pad + col0 + cf0 * 8 + 2 * l4;
+#pragma unroll
+                for (int ni = 0; ni < 3; ++ni)
+                    if (ni < ncf && (cf0 + ni) * 8 < ncols_valid)
+                        *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
         }
     }
 }
@@ -446,8 +494,15 @@ void launch_fft_planes(cudaStream_t s, const DevModel &m, const double *T, const
     const DevFft &f = m.fft;
     FftPlaneArgs a;
     a.f = f; a.T = T; a.c12 = c12; a.cont = cont; a.ldb = ldb; a.cols = cols; a.count = count; a.planes = planes;
-    const size_t smem = (size_t)(PSTAGES * (P_A + P_T) + PV * f.my_pad) * sizeof(double);
-    dim3 grid(2 * ((count + PV - 1) / PV), f.rtiles, f.ctiles);
+    const size_t smem_max = 226 * 1024, conts_bytes = (size_t)2 * PV * f.my_pad * sizeof(double), stage_bytes = (size_t)(P_A + P_T) * sizeof(double);
+    a.nstages = (int)std::min<size_t>(PSTAGES, conts_bytes < smem_max ? (smem_max - conts_bytes) / stage_bytes : 0);
+    const size_t smem = a.nstages * stage_bytes + conts_bytes;
+    // persistent CTAs: one per SM (the kernel needs most of an SM's registers and shared memory)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = f.rtiles * f.ctiles;
+    dim3 grid(std::max(1, std::min(2 * ((count + PV - 1) / PV), sms / tiles)), f.rtiles, f.ctiles);
     const int threads = PV * ((f.ncf + 2) / 3) * 32;  // (vector, column group of three fragments)
     switch (f.ncf) {
     case 1: launch_fft_planes_t<1>(s, a, grid, threads, smem); break;
