@@ -54,6 +54,7 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
+    if (c->mp) cudaFree(c->mp);
     if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -471,6 +472,7 @@ extern "C" double bf_model_transform_dr(const bf_model *m) { return m ? m->dev.t
 extern "C" int bf_data_destroy(bf_data *d) {
     if (!d) return BF_OK;
     cudaSetDevice(d->ctx->device);
+    if (d->expanded) bf_data_destroy(d->expanded);
     for (void *p : d->allocs) cudaFree(p);
     for (auto &kv : d->plans)
         for (void *p : kv.second.allocs) cudaFree(p);
@@ -548,6 +550,47 @@ extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out)
     o->h_data.assign(d->data, d->data + n);
     if ((rc = pad_square(W, &o->d_W))) return fail(rc);
     if (!L.empty() && (rc = pad_square(L, &o->d_L))) return fail(rc);
+    if (d->binning_type == BF_BINNING_MULTIPOLE) {
+        // CorrelationFitter.cc:66-69: every bin becomes nmu points (r_i, mu_q, z_i) of a Gauss-Legendre rule
+        // on [-1,1]; the prediction is sum_q (2 ell_i + 1)/2 w_q L_ell_i(mu_q) xi(r_i, mu_q, z_i)
+        if (d->n_grid > 0) return fail((bf::set_error("bf_data_create: multipole data cannot carry a distortion-matrix grid"), BF_ERR_DATA));
+        const int nmu = d->nmu_project > 0 ? d->nmu_project : 16;
+        if (nmu > 64) return fail((bf::set_error("bf_data_create: nmu_project <= 64"), BF_ERR_DATA));
+        std::vector<double> x(nmu), w(nmu), proj((size_t)n * nmu), er((size_t)n * nmu), emu((size_t)n * nmu), ez((size_t)n * nmu);
+        std::vector<int> eidx((size_t)n * nmu);
+        gauss_legendre_01(nmu, x.data(), w.data());
+        auto legendre = [](int ell, double mu) {
+            double m2 = mu * mu;
+            return ell == 0 ? 1.0 : ell == 2 ? (-1 + 3 * m2) / 2. : (3 + m2 * (-30 + 35 * m2)) / 8.;
+        };
+        for (int i = 0; i < n; ++i) {
+            const int ell = (int)std::floor(d->mu[i] + 0.5);  // ComovingCorrelationData.cc:73-75
+            if (ell != 0 && ell != 2 && ell != 4) return fail((bf::set_error("bf_data_create: multipole bins must have ell = 0, 2 or 4"), BF_ERR_DATA));
+            for (int q = 0; q < nmu; ++q) {
+                const double mu = 2 * x[q] - 1;
+                const size_t k = (size_t)i * nmu + q;
+                er[k] = d->r[i]; emu[k] = mu; ez[k] = d->z[i]; eidx[k] = d->index[i];
+                proj[k] = 0.5 * (2 * ell + 1) * 2 * w[q] * legendre(ell, mu);
+            }
+        }
+        bf_data *e = new bf_data();
+        e->ctx = ctx;
+        e->points_only = true;
+        e->trigger_mu_zero = true;
+        e->n = n * nmu;
+        e->n_pad = round_up(e->n, kPadM);
+        e->n_grid = 0;
+        e->n_grid_pad = kPadM;
+        e->h_r = er; e->h_mu = emu; e->h_z = ez; e->h_index = eidx;
+        o->expanded = e;
+        o->binning_type = BF_BINNING_MULTIPOLE;
+        o->nmu = nmu;
+        if ((rc = upload_padded(e->allocs, er.data(), e->n, e->n_pad, &e->d_r))) return fail(rc);
+        if ((rc = upload_padded(e->allocs, emu.data(), e->n, e->n_pad, &e->d_mu))) return fail(rc);
+        if ((rc = upload_padded(e->allocs, ez.data(), e->n, e->n_pad, &e->d_z))) return fail(rc);
+        if ((rc = upload_padded(e->allocs, eidx.data(), e->n, e->n_pad, &e->d_index))) return fail(rc);
+        if ((rc = upload(o->allocs, proj.data(), proj.size(), &o->d_proj))) return fail(rc);
+    }
     *out = o;
     return BF_OK;
 }
@@ -987,7 +1030,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         FftVecArgs va;
         std::memset(&va, 0, sizeof(va));
         va.m = dm; va.pT = w.pT; va.ldb = ldb; va.B = B;
-        if (d) { va.r0 = d->h_r[0]; va.mu0 = d->h_mu[0]; va.z0 = d->h_z[0]; }
+        if (d) { va.r0 = d->h_r[0]; va.mu0 = d->trigger_mu_zero ? 0.0 : d->h_mu[0]; va.z0 = d->h_z[0]; }
         va.use_ztrig = d ? 0 : 1;
         va.ztrig = z_trigger_override;
         va.keyflag = w.flag; va.keys = w.fft_keys; va.c12 = w.fft_c12; va.cont = w.fft_cont; va.status = w.status;
@@ -1228,10 +1271,56 @@ int check_args(bf_ctx *ctx, const bf_model *m, const bf_data *d, const void *par
 }  // namespace
 
 static int run_device(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B, Output what,
+                      double *d_out, int ldo, const double *d_override, int *d_status);
+
+// Multipole-binned data: evaluate the model at the expanded (r, mu_q, z) points, project, then the
+// usual chi-square GEMM on the residual panel.
+static int run_device_multipole(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B, Output what,
+                                double *d_out, int ldo, const double *d_override, int *d_status) {
+    if (what != OUT_PRED && what != OUT_CHI2) BF_FAIL(BF_ERR_ANALYSIS, "multipole data: only predictions and chi-square are defined");
+    if (m->dev.dm_order > 0) BF_FAIL(BF_ERR_DATA, "multipole data cannot be combined with a distortion matrix");
+    if (m->dev.idx_delta_v >= 0)
+        BF_FAIL(BF_ERR_DATA, "multipole data with a cross-correlation model is not supported (the reference's multipole overload "
+                             "applies no velocity shift, AbsCorrelationModel.cc:43-49)");
+    const bf_data *e = d->expanded;
+    const int cap = 8192;  // columns per pass: bounds the panel of expanded predictions
+    cudaStream_t s = ctx->stream;
+    for (int b0 = 0; b0 < B; b0 += cap) {
+        const int bc = std::min(cap, B - b0), ldb = round_up(bc, kPadN);
+        const size_t need = ((size_t)e->n + d->n_pad) * ldb * sizeof(double);
+        int rc = ensure(&ctx->mp, &ctx->mp_bytes, need);
+        if (rc) return rc;
+        double *X = (double *)ctx->mp, *Z = X + (size_t)e->n * ldb;
+        rc = run_device(ctx, m, e, d_params + (size_t)b0 * m->dev.npar, bc, OUT_PRED, X, ldb, nullptr, d_status ? d_status + b0 : nullptr);
+        if (rc) return rc;
+        if (what == OUT_PRED) {
+            BF_KERNEL(ctx, "multipole_project_kernel",
+                      launch_multipole_project(s, X, ldb, d->d_proj, d->n, d->nmu, bc, d_out + b0, ldo, nullptr, nullptr));
+        } else {
+            if (d->n_pad > d->n) BF_CUDA_OK(cudaMemsetAsync(Z + (size_t)d->n * ldb, 0, (size_t)(d->n_pad - d->n) * ldb * sizeof(double), s));
+            BF_KERNEL(ctx, "multipole_project_kernel",
+                      launch_multipole_project(s, X, ldb, d->d_proj, d->n, d->nmu, bc, Z, ldb, d->d_data,
+                                               d_override ? d_override + (size_t)b0 * d->n : nullptr));
+            GemmArgs g{};
+            g.A = d->d_W; g.Bm = Z; g.C = nullptr;
+            g.M = d->n_pad; g.N = bc; g.K = d->n_pad;
+            g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
+            g.lower_triangular = 1;
+            g.chi2 = d_out + b0; g.status = d_status ? d_status + b0 : nullptr;
+            BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+        }
+    }
+    BF_CUDA_OK(cudaGetLastError());
+    return BF_OK;
+}
+
+static int run_device(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B, Output what,
                       double *d_out, int ldo, const double *d_override, int *d_status) {
     int rc = check_args(ctx, m, d, d_params, B);
     if (rc) return rc;
     BF_CUDA_OK(cudaSetDevice(ctx->device));
+    if (d->binning_type == BF_BINNING_MULTIPOLE)
+        return run_device_multipole(ctx, m, d, d_params, B, what, d_out, ldo, d_override, d_status);
     const bf_data::Plan *plan = nullptr;
     if ((rc = get_plan(m, d, &plan))) return rc;
     int cap = chunk_capacity(m, d, plan->nz);

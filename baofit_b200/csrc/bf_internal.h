@@ -124,6 +124,8 @@ struct bf_ctx {
     size_t ws_bytes = 0;
     void *io = nullptr;  // staging for host-buffer entry points
     size_t io_bytes = 0;
+    void *mp = nullptr;  // multipole-binned data: predictions at the expanded points + residual panel
+    size_t mp_bytes = 0;
     double *pinned_flag = nullptr;  // small pinned buffer for tiny device->host answers (flag + key values)
     int sm_count = 148;
     // optional per-kernel timing (bf_ctx_set_profiling): event pairs around every launch
@@ -167,6 +169,13 @@ struct bf_data {
     double *d_data = nullptr;  // [n_pad]
     double *d_W = nullptr;     // [n_pad][n_pad] lower triangular, W^T W = C^-1
     double *d_L = nullptr;     // [n_pad][n_pad] lower Cholesky factor of C (toy noise); may be null
+    // multipole-binned data (BF_BINNING_MULTIPOLE): every bin is expanded into nmu Gauss-Legendre points
+    // in mu, held by `expanded` (a points-only data object); the prediction is the weighted sum
+    int binning_type = 0, nmu = 0;
+    bf_data *expanded = nullptr;
+    double *d_proj = nullptr;  // [n][nmu] weights (2 ell + 1)/2 w_q L_ell(mu_q)
+    bool points_only = false;  // internal object without data vector / covariance
+    bool trigger_mu_zero = false;  // the multipole overload triggers transforms with mu = 0 (AbsCorrelationModel.cc:73)
     std::vector<double> h_W;   // host copy [n][n] (folded into the fused tail matrices at plan time)
     std::vector<double> h_data;
     // plans: per model, the z-class table and the gathered distortion matrix rows

@@ -165,6 +165,10 @@ struct FftEvalArgs {
 };
 void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a);
 
+// multipole projection: out[i*ldo + b] = sum_q proj[i*nmu + q] X[(i*nmu + q)*ldx + b] - (dov ? dov[b*n + i] : dsub ? dsub[i] : 0)
+void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const double *proj, int n, int nmu, int B,
+                              double *out, int ldo, const double *dsub, const double *dov);
+
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);
 

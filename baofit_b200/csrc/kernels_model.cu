@@ -882,4 +882,24 @@ void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count) {
     dist_post_kernel<<<grid, 128, 0, s>>>(a);
 }
 
+// ------------------------------------------------------------------------------------------
+// multipole-binned data: AbsCorrelationModel::evaluate(r, multipole, z, ...) = Gauss-Legendre
+// projection of the (r, mu) model (AbsCorrelationModel.cc:65-79)
+// ------------------------------------------------------------------------------------------
+__global__ void multipole_project_kernel(const double *__restrict__ X, int ldx, const double *__restrict__ proj, int n, int nmu,
+                                         int B, double *__restrict__ out, int ldo, const double *__restrict__ dsub,
+                                         const double *__restrict__ dov) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int q = 0; q < nmu; ++q) s = fma(proj[i * nmu + q], X[(size_t)(i * nmu + q) * ldx + b], s);
+    const double sub = dov ? dov[(size_t)b * n + i] : (dsub ? dsub[i] : 0.0);
+    out[(size_t)i * ldo + b] = s - sub;
+}
+
+void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const double *proj, int n, int nmu, int B,
+                              double *out, int ldo, const double *dsub, const double *dov) {
+    multipole_project_kernel<<<dim3((B + 127) / 128, n), 128, 0, s>>>(X, ldx, proj, n, nmu, B, out, ldo, dsub, dov);
+}
+
 }  // namespace bf

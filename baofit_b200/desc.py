@@ -94,6 +94,7 @@ class DataDesc(C.Structure):
         ("cov", c_double_p), ("cov_is_inverse", C.c_int),
         ("n_grid", C.c_int),
         ("grid_r", c_double_p), ("grid_mu", c_double_p), ("grid_z", c_double_p),
+        ("binning_type", C.c_int), ("nmu_project", C.c_int),
     ]
 
 
@@ -184,7 +185,7 @@ def new_model_desc():
     return k
 
 
-def new_data_desc(r, mu, z, index, data, cov, cov_is_inverse=False, grid=None):
+def new_data_desc(r, mu, z, index, data, cov, cov_is_inverse=False, grid=None, multipole=False, nmu=0):
     k = Keep(DataDesc())
     d = k.desc
     d.n_data = len(r)
@@ -193,6 +194,7 @@ def new_data_desc(r, mu, z, index, data, cov, cov_is_inverse=False, grid=None):
     assert cov.shape == (len(r), len(r))
     k.f64("cov", cov)
     d.cov_is_inverse = 1 if cov_is_inverse else 0
+    d.binning_type, d.nmu_project = (1 if multipole else 0), nmu
     if grid is not None:
         gr, gmu, gz = grid
         d.n_grid = len(gr)

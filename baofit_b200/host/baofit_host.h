@@ -213,6 +213,8 @@ public:
     virtual ~AbsCorrelationData();
     virtual double getRadius(int index) const = 0;
     virtual double getCosAngle(int index) const { return 0; }
+    virtual int getMultipole(int index) const { (void)index; return 0; }
+    TransverseBinningType getTransverseBinningType() const { return _type; }
     virtual double getRedshift(int index) const = 0;
     // BinnedData subset
     void setData(int index, double value);
@@ -264,6 +266,7 @@ public:
     ComovingCorrelationData(BinnedGrid grid, CoordinateSystem coordinateSystem);
     double getRadius(int index) const override;    // ComovingCorrelationData.cc:46-55
     double getCosAngle(int index) const override;  // ComovingCorrelationData.cc:57-69
+    int getMultipole(int index) const override;    // ComovingCorrelationData.cc:71-79
     double getRedshift(int index) const override;  // ComovingCorrelationData.cc:81-84
 
 private:

@@ -96,7 +96,7 @@ extern "C" int bfh_kept_coordinates(const bfh_session *s, double *r, double *mu,
     auto const &k = s->data->keptIndices();
     for (size_t i = 0; i < k.size(); ++i) {
         if (r) r[i] = s->data->getRadius(k[i]);
-        if (mu) mu[i] = s->data->getCosAngle(k[i]);
+        if (mu) mu[i] = s->data->getTransverseBinningType() == AbsCorrelationData::Coordinate ? s->data->getCosAngle(k[i]) : (double)s->data->getMultipole(k[i]);
         if (z) z[i] = s->data->getRedshift(k[i]);
     }
     BFH_CATCH

@@ -112,7 +112,6 @@ void AbsCorrelationData::setFinalCuts(double rMin, double rMax, double rVetoMin,
 void AbsCorrelationData::finalize() {
     if (_finalized) return;
     if (!_haveFinalCuts) throw RuntimeError("AbsCorrelationData: no final cuts specified yet.");
-    if (_type != Coordinate) throw RuntimeError("AbsCorrelationData: multipole data is not supported by the CUDA path yet.");
     // same comparisons in the same order as AbsCorrelationData.cc:71-93 (std::map iterates in
     // ascending index order, like the reference's IndexIterator)
     for (auto const &kv : _values) {
@@ -121,12 +120,17 @@ void AbsCorrelationData::finalize() {
         if (r < _rMin || r > _rMax) continue;
         if (r > _rVetoMin && r < _rVetoMax) continue;
         if (z < _zMin || z > _zMax) continue;
-        double mu = getCosAngle(index);
-        if (mu < _muMin || mu > _muMax) continue;
-        double rpar = r * mu;
-        if (rpar < _rparMin || rpar > _rparMax) continue;
-        double rperp = r * std::sqrt(1 - mu * mu);
-        if (rperp < _rperpMin || rperp > _rperpMax) continue;
+        if (_type == Coordinate) {
+            double mu = getCosAngle(index);
+            if (mu < _muMin || mu > _muMax) continue;
+            double rpar = r * mu;
+            if (rpar < _rparMin || rpar > _rparMax) continue;
+            double rperp = r * std::sqrt(1 - mu * mu);
+            if (rperp < _rperpMin || rperp > _rperpMax) continue;
+        } else {  // _type == Multipole, AbsCorrelationData.cc:86-89
+            int ell = getMultipole(index);
+            if (ell < _lMin || ell > _lMax) continue;
+        }
         if (extraCut(index)) continue;
         _kept.push_back(index);
     }
@@ -138,7 +142,7 @@ void AbsCorrelationData::finalize() {
 void AbsCorrelationData::gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const {
     int n = _grid.getNBinsTotal();
     r.resize(n); mu.resize(n); z.resize(n);
-    for (int i = 0; i < n; ++i) { r[i] = getRadius(i); mu[i] = getCosAngle(i); z[i] = getRedshift(i); }
+    for (int i = 0; i < n; ++i) { r[i] = getRadius(i); mu[i] = _type == Coordinate ? getCosAngle(i) : (double)getMultipole(i); z[i] = getRedshift(i); }
 }
 
 std::vector<double> AbsCorrelationData::dataVector() const {
@@ -167,9 +171,14 @@ bf_data *AbsCorrelationData::deviceData(bool withGrid) {
     if (_device) { bf_data_destroy(_device); _device = nullptr; }
     int n = (int)_kept.size();
     std::vector<double> r(n), mu(n), z(n), d = dataVector(), cov = covarianceMatrix(), gr, gmu, gz;
-    for (int i = 0; i < n; ++i) { r[i] = getRadius(_kept[i]); mu[i] = getCosAngle(_kept[i]); z[i] = getRedshift(_kept[i]); }
+    for (int i = 0; i < n; ++i) {
+        r[i] = getRadius(_kept[i]);
+        mu[i] = _type == Coordinate ? getCosAngle(_kept[i]) : (double)getMultipole(_kept[i]);  // multipole bins carry ell
+        z[i] = getRedshift(_kept[i]);
+    }
     bf_data_desc dd;
     std::memset(&dd, 0, sizeof(dd));
+    dd.binning_type = _type == Coordinate ? BF_BINNING_COORDINATE : BF_BINNING_MULTIPOLE;
     dd.n_data = n;
     dd.r = r.data(); dd.mu = mu.data(); dd.z = z.data(); dd.index = _kept.data(); dd.data = d.data();
     dd.cov = cov.data();
@@ -206,6 +215,13 @@ double ComovingCorrelationData::getCosAngle(int index) const {
         double rpar = c[0], rperp = c[1];
         return rpar / std::sqrt(rpar * rpar + rperp * rperp);
     }
+    throw RuntimeError("ComovingCorrelationData::getMultipole: invalid coordinate system.");
+}
+
+int ComovingCorrelationData::getMultipole(int index) const {
+    double c[3];
+    _grid.getBinCenters(index, c);
+    if (_coordinateSystem == MultipoleCoordinates) return (int)std::floor(c[1] + 0.5);
     throw RuntimeError("ComovingCorrelationData::getMultipole: invalid coordinate system.");
 }
 

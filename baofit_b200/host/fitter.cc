@@ -358,6 +358,7 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir)
     AbsCorrelationDataPtr data;
     if (fmt == "comoving-cartesian") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::CartesianCoordinates));
     else if (fmt == "comoving-polar") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::PolarCoordinates));
+    else if (fmt == "comoving-multipole") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::MultipoleCoordinates));
     else if (fmt == "quasar") {
         // src/baofit.cc:409-414,495-500
         AbsHomogeneousUniversePtr cosmology(new LambdaCdmRadiationUniverse(opt.num("omega-matter", 0.27), 0, opt.num("hubble-constant", 0.7)));
@@ -365,7 +366,7 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir)
         data.reset(new QuasarCorrelationData(grid, opt.num("ll-min", 0), opt.num("ll-max", 1), opt.num("sep-min", 0),
                                              opt.num("sep-max", 200), false, cosmology));
     } else
-        throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar, quasar)");
+        throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar, comoving-multipole, quasar)");
     // src/baofit.cc:510 with the defaults of :216-247
     double rVetoWidth = opt.num("rveto-width", 0), rVetoCenter = opt.num("rveto-center", 114);
     data->setFinalCuts(opt.num("rmin", 0), opt.num("rmax", 200), rVetoCenter - 0.5 * rVetoWidth, rVetoCenter + 0.5 * rVetoWidth,

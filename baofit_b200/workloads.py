@@ -498,10 +498,11 @@ class Data:
         self.n_data = keep.desc.n_data
 
 
-def make_data(r, mu, z, keep_idx, dvec, cov, cov_is_inverse=False, with_grid=False):
+def make_data(r, mu, z, keep_idx, dvec, cov, cov_is_inverse=False, with_grid=False, multipole=False, nmu=0):
+    """multipole=True: ``mu`` holds the multipole ell of every bin (data-format comoving-multipole)."""
     grid = (r, mu, z)
     k = D.new_data_desc(r[keep_idx], mu[keep_idx], z[keep_idx], keep_idx, dvec, cov, cov_is_inverse,
-                        grid if with_grid else None)
+                        grid if with_grid else None, multipole=multipole, nmu=nmu)
     return Data(k, grid)
 
 
@@ -654,6 +655,27 @@ def demo_rmu(root=None, golden=GOLDEN):
     keep = final_cuts(r, mu, z, has, rmin=40, rmax=200)
     data = make_data(r, mu, z, keep, val[keep], icov[np.ix_(keep, keep)], cov_is_inverse=True)
     return m, data
+
+
+def demo_multi(root=None, golden=GOLDEN, which=0, lmax=2):
+    """demo/multi_to_bao.ini: 29 radii x ell = 0,2,4 multipole bins at z = 2.25 (data-format
+    comoving-multipole), one of the three demo realisations demo/multi_<which>.{data,cov}."""
+    root = root or os.path.join(golden, "models")
+    fid = load_multipoles(root, "DR9LyaMocks")
+    nw = load_multipoles(root, "DR9LyaMocksSB")
+    m = rspace_model(fid, nw, zref=2.25)
+    m.configure("fix[(1+beta)*bias]=-0.336; fix[gamma-bias]=3.8; fix[gamma-beta]=0; fix[gamma-scale]=0;"
+                "fix[BAO amplitude]=1; fix[BAO alpha-iso]=1; value[beta]=1.4; value[BAO alpha-p*]=1.0")
+    a1, a2, a3 = parse_binning("{40:180}*29"), parse_binning("{0,2,4}"), parse_binning("{2.25}")
+    c1, c2, c3 = np.meshgrid(a1, a2, a3, indexing="ij")
+    r, ell, z = c1.ravel(), c2.ravel(), c3.ravel()
+    n = len(r)
+    val, has = load_data_vector(os.path.join(golden, "demo", "multi_%d.data" % which), n)
+    cov = load_cov(os.path.join(golden, "demo", "multi_%d.cov" % which), n)
+    # final cuts of the Multipole type: r, z and lmin <= ell <= lmax (AbsCorrelationData.cc:75-90; the lmax
+    # option defaults to 2, src/baofit.cc:247, so the hexadecapole bins are dropped unless lmax = 4 is given)
+    keep = np.array([i for i in np.nonzero(has)[0] if 40 <= r[i] <= 200 and 0 <= ell[i] <= lmax], dtype=np.int32)
+    return m, make_data(r, ell, z, keep, val[keep], cov[np.ix_(keep, keep)], multipole=True)
 
 
 def dr11_auto_kspace(root=None, golden=GOLDEN, seed=1966):

@@ -187,7 +187,18 @@ typedef struct bf_data_desc {
      * n_grid may be 0 when the model has no distortion matrix                               */
     int n_grid;
     const double *grid_r, *grid_mu, *grid_z;
+    /* transverse binning type (AbsCorrelationData.h:19, CorrelationFitter.cc:62-69):
+     * 0 = Coordinate: bins are points (r, mu, z);
+     * 1 = Multipole (data-format comoving-multipole): mu[i] holds the multipole ell = 0, 2, 4 of bin i
+     *     and the prediction is AbsCorrelationModel::evaluate(r, multipole, z, ...), i.e. the projection
+     *     (2 ell + 1)/2 Int_-1^1 L_ell(mu) xi(r, mu, z) dmu (AbsCorrelationModel.cc:65-79), evaluated
+     *     with an nmu_project-point Gauss-Legendre rule (0 selects 16).                            */
+    int binning_type;
+    int nmu_project;
 } bf_data_desc;
+
+#define BF_BINNING_COORDINATE 0
+#define BF_BINNING_MULTIPOLE 1
 
 typedef struct bf_ctx bf_ctx;     /* one CUDA device + stream + workspaces; one per host thread */
 typedef struct bf_model bf_model; /* immutable after creation: tables, weights, layout          */

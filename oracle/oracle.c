@@ -1342,6 +1342,30 @@ int orc_predict(orc_model *m, const orc_data *d, const double *params, double *p
         free(xiu);
         return st;
     }
+    if (d->d.binning_type == BF_BINNING_MULTIPOLE) {
+        /* CorrelationFitter.cc:66-69 -> AbsCorrelationModel::evaluate(r, multipole, z, ...), :43-49,65-79 */
+        int nmu = d->d.nmu_project > 0 ? d->d.nmu_project : 16, q;
+        double *x = (double *)malloc(sizeof(double) * nmu), *w = (double *)malloc(sizeof(double) * nmu);
+        if (m->dist_matrix || m->d.idx_delta_v >= 0) { /* the multipole overload applies no velocity shift (:43-49) */
+            set_err("orc_predict: multipole data with a distortion matrix / cross-correlation is not restated");
+            free(x); free(w);
+            return -1;
+        }
+        if (m->d.kind == BF_MODEL_KSPACE_FFT) ztrig = fft_trigger_z(m, params, d->r[0], 0.0, d->z[0]); /* :73, mu = 0 */
+        gauss_legendre_01(nmu, x, w);
+        for (i = 0; i < d->d.n_data; ++i) {
+            int ell = (int)floor(d->mu[i] + 0.5);
+            double s = 0;
+            for (q = 0; q < nmu; ++q) {
+                double mu = 2 * x[q] - 1;
+                s += 2 * w[q] * orc_legendre(ell, mu) * evaluate_with_ztrig(m, d, params, d->r[i], mu, d->z[i], d->index[i], ztrig, &st);
+            }
+            pred[i] = 0.5 * (2 * ell + 1) * s;
+        }
+        free(x);
+        free(w);
+        return st;
+    }
     for (i = 0; i < d->d.n_data; ++i)
         pred[i] = evaluate_with_ztrig(m, d, params, d->r[i], d->mu[i], d->z[i], d->index[i], ztrig, &st);
     return st;

@@ -1,0 +1,76 @@
+"""data-format = comoving-multipole (demo/multi_to_bao.ini): bins are (r, ell, z), predictions are
+AbsCorrelationModel::evaluate(r, multipole, z, ...) (baofit/AbsCorrelationModel.cc:43-49,65-79,
+baofit/CorrelationFitter.cc:62-69). The oracle is pinned on demo/multi.theory; the CUDA path expands
+every bin into Gauss-Legendre points in mu and projects."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from baofit_b200 import host_api as H, workloads as W
+from util import RTOL, rel_err, rel_err_bins
+
+
+def test_oracle_multipole_prediction_is_demo_theory():
+    m, d = W.demo_multi(lmax=4)
+    pred, st = oracle.predict(oracle.OracleModel(m), oracle.OracleData(d), m.values)
+    mt = np.loadtxt(os.path.join(W.GOLDEN, "demo", "multi.theory"))[:, 1]
+    assert st == 0 and d.n_data == 87
+    assert np.max(np.abs(pred - mt[d.keep._arrays[3]])) < 1e-15
+
+
+def test_host_multipole_final_cuts(built, golden_tree):
+    """lmax defaults to 2 (src/baofit.cc:247): the hexadecapole bins are cut, bit-exact mask."""
+    base = os.path.join(golden_tree, "config")
+    text = open(os.path.join(base, "multi_to_bao.ini")).read() + "\ndata = ../demo/multi_0\n"
+    s = H.Session(text, base)
+    m, d = W.demo_multi()
+    assert s.ndata == 58 == d.n_data and np.array_equal(s.kept_indices(), d.keep._arrays[3])
+    r, ell, z = s.kept_coordinates()
+    assert np.array_equal(ell, d.keep._arrays[1]) and np.allclose(r, d.keep._arrays[0], rtol=0, atol=1e-13)
+    s4 = H.Session(text + "lmax = 4\n", base)
+    assert s4.ndata == 87
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["rspace", "kspace", "fft"])
+def test_gpu_multipole_data_against_oracle(ctx, model):
+    from baofit_b200 import capi
+    m, d = W.demo_multi(lmax=4)
+    sweep = {"BAO alpha-parallel": (0.8, 1.25), "BAO alpha-perp": (0.8, 1.25)}
+    B = 40
+    if model == "kspace":
+        pk_fid = W.load_table(os.path.join(W.GOLDEN, "models", "DR9LyaMocksLCDM_matterpower.dat"))
+        pk_nw = W.load_table(os.path.join(W.GOLDEN, "models", "DR9LyaMocksLCDMSB_matterpower.dat"))
+        m = W.kspace_model(pk_fid, pk_nw, rmin=40, rmax=180, dist_add="-2:0,0:4:2,0")
+        m.configure("fix[gamma-beta]=0; fix[gamma-scale]=0; fix[BAO alpha-iso]; fix[1+f]=1.966; fix[SigmaNL-perp]=3.26")
+        B = 4
+    elif model == "fft":
+        m, _ = W.dr11_auto_fft(ngrid=128, spacing=5., nbins=40)
+        B = 6
+    rng = np.random.Generator(np.random.PCG64(9))
+    params = m.random_batch(B, rng, sweep=sweep)
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    pred, st = capi.eval_batch(ctx, gm, gd, params)
+    chi2, st2 = capi.chi2_batch(ctx, gm, gd, params)
+    ref_chi2, ref_st, ref_pred = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), params, want_pred=True, nthreads=8)
+    assert np.array_equal(st, ref_st) and np.array_equal(st2, ref_st)
+    ok = ref_st == 0
+    assert ok.sum() >= B // 2
+    assert rel_err_bins(pred[:, ok], ref_pred[:, ok]) < RTOL
+    assert rel_err(chi2[ok], ref_chi2[ok]) < RTOL
+    gm.close(), gd.close()
+
+
+@pytest.mark.gpu
+def test_gpu_multipole_demo_fit(built, golden_tree):
+    """demo/multi_to_bao.ini on demo/multi_0: the fit recovers the generating values within errors."""
+    base = os.path.join(golden_tree, "config")
+    text = open(os.path.join(base, "multi_to_bao.ini")).read() + "\ndata = ../demo/multi_0\nlmax = 4\n"
+    s = H.Session(text, base)
+    r = s.fit()
+    assert r["status"] == 0
+    for name, v in {"beta": 1.4, "BAO alpha-parallel": 1.0, "BAO alpha-perp": 1.0}.items():
+        i = s.names.index(name)
+        assert abs(r["values"][i] - v) < 4 * r["errors"][i], (name, r["values"][i], r["errors"][i])
