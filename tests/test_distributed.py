@@ -75,3 +75,35 @@ def test_scan_sharded_over_two_gloo_ranks_equals_single_process(built, tmp_path)
     u0 = np.load(tmp_path / "uneven_0.npy")
     assert u0.shape == (11, 2) and np.array_equal(u0, np.load(tmp_path / "uneven_1.npy"))
     assert u0[0, 0] == 0 and u0[6, 0] == 100  # rank 0 owns 6 of 11 units, rank 1 the other 5
+
+
+class FakeToySession:
+    """Toy 'fits' keyed by the global toy index, as bf_sample_toys keys its noise: results must not
+    depend on how the realisations are split over ranks."""
+    npar = 2
+
+    def toymc(self, first, count, seed=1966):
+        idx = np.arange(first, first + count)
+        rng_vals = np.array([np.random.Generator(np.random.PCG64([seed, int(i)])).standard_normal(3) for i in idx]).reshape(-1, 3)
+        return dict(fitted=rng_vals[:, :2], chi2=100 + rng_vals[:, 2], status=(idx % 7 == 0).astype(np.int32))
+
+
+def _toy_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = shard.toymc_sharded(FakeToySession(), 37, seed=5)
+        np.save(os.path.join(out_dir, "toys_%d.npy" % rank), np.column_stack([res["chi2"], res["fitted"], res["status"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_toymc_sharded_over_two_gloo_ranks_equals_single_process(tmp_path):
+    single = FakeToySession().toymc(0, 37, seed=5)
+    port = _free_port()
+    mp.spawn(_toy_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "toys_0.npy"), np.load(tmp_path / "toys_1.npy")
+    assert np.array_equal(r0, r1) and r0.shape == (37, 4)
+    assert np.array_equal(r0[:, 0], single["chi2"]) and np.array_equal(r0[:, 1:3], single["fitted"])
+    assert np.array_equal(r0[:, 3].astype(np.int32), single["status"])
