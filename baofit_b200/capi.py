@@ -22,6 +22,7 @@ EXPORTS = [
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
     "bf_fft_planes_batch", "bf_model_fft_plane_dims",
+    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys",
 ]
 
 
@@ -68,6 +69,12 @@ def lib():
         L.bf_model_transform_dr.argtypes = [C.c_void_p]
         L.bf_sample_toys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int,
                                      C.c_double, C.c_void_p]
+        L.bf_toys_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int, C.c_double,
+                                     C.POINTER(C.c_void_p)]
+        L.bf_toys_destroy.argtypes = [C.c_void_p]
+        L.bf_toys_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bf_chi2_batch_toys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
         L.bf_fft_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.bf_model_fft_plane_dims.argtypes = [C.c_void_p, c_int_p, c_int_p]
         _LIB = L
@@ -180,6 +187,40 @@ class Data:
         out = np.zeros((ntoy, self.n))
         _check(lib().bf_sample_toys(self.ctx.h, self.h, _ptr(t), seed, first_toy, ntoy, scale, _ptr(out)))
         return out
+
+
+class Toys:
+    """Device-resident toy-MC realisations of one data set (bf_toys)."""
+
+    def __init__(self, ctx, data, truth, seed, first_toy, ntoy, scale=1.0):
+        self.ctx, self.data, self.ntoy = ctx, data, ntoy
+        t = np.ascontiguousarray(truth, dtype=np.float64)
+        h = C.c_void_p()
+        _check(lib().bf_toys_create(ctx.h, data.h, _ptr(t), seed, first_toy, ntoy, scale, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            lib().bf_toys_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def download(self):
+        out = np.zeros((self.ntoy, self.data.n))
+        _check(lib().bf_toys_download(self.ctx.h, self.h, _ptr(out)))
+        return out
+
+
+def chi2_batch_toys(ctx, model, data, params, toys, toy_index):
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, model.npar)
+    B = p.shape[0]
+    idx = np.ascontiguousarray(toy_index, dtype=np.int32)
+    assert idx.shape == (B,)
+    chi2 = np.zeros(B)
+    status = np.zeros(B, dtype=np.int32)
+    _check(lib().bf_chi2_batch_toys(ctx.h, model.h, data.h, _ptr(p), B, toys.h, _ptr(idx), _ptr(chi2), _ptr(status)))
+    return chi2, status
 
 
 def eval_batch(ctx, model, data, params):

@@ -1494,3 +1494,80 @@ extern "C" int bf_sample_toys(bf_ctx *ctx, const bf_data *d, const double *truth
     BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return BF_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// device-resident toy tables
+// ------------------------------------------------------------------------------------------
+extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth, unsigned long long seed,
+                              long long first_toy, int ntoy, double scale, bf_toys **out) {
+    if (!ctx || !d || !truth || !out || ntoy <= 0) BF_FAIL(BF_ERR_OPTIONS, "bf_toys_create: bad argument");
+    if (!d->d_L) BF_FAIL(BF_ERR_ANALYSIS, "bf_toys_create: needs a covariance (not an inverse covariance)");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    bf_toys *t = new bf_toys();
+    t->ctx = ctx; t->ntoy = ntoy; t->n = d->n;
+    double *d_truth = nullptr;
+    cudaError_t e = cudaMalloc((void **)&t->d_table, (size_t)ntoy * d->n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_truth, (size_t)d->n * sizeof(double));
+    if (e != cudaSuccess) { if (t->d_table) cudaFree(t->d_table); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_truth, truth, (size_t)d->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    BF_KERNEL(ctx, "toy_noise_kernel",
+              launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, t->d_table));
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_truth);
+    if (e != cudaSuccess) { cudaFree(t->d_table); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
+    *out = t;
+    return BF_OK;
+}
+
+extern "C" int bf_toys_destroy(bf_toys *t) {
+    if (!t) return BF_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaFree(t->d_table);
+    delete t;
+    return BF_OK;
+}
+
+extern "C" int bf_toys_download(bf_ctx *ctx, const bf_toys *t, double *out) {
+    if (!ctx || !t || !out) BF_FAIL(BF_ERR_OPTIONS, "bf_toys_download: null argument");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    BF_CUDA_OK(cudaMemcpyAsync(out, t->d_table, (size_t)t->ntoy * t->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BF_OK;
+}
+
+extern "C" int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B,
+                                  const bf_toys *toys, const int *toy_index, double *chi2, int *status) {
+    if (!chi2 || !toys || !toy_index) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_toys: null argument");
+    int rc = check_args(ctx, m, d, params, B);
+    if (rc) return rc;
+    if (toys->ctx != ctx || toys->n != d->n) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_toys: the toy table belongs to another context / data set");
+    for (int b = 0; b < B; ++b)
+        if (toy_index[b] < 0 || toy_index[b] >= toys->ntoy) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_toys: toy index out of range");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const int npar = m->dev.npar, n = d->n;
+    cudaStream_t s = ctx->stream;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    // passes of at most 16384 points bound the gathered override panel (B x n doubles)
+    const int cap = 16384;
+    const int pass = std::min(B, cap);
+    size_t nb_params = al((size_t)pass * npar * sizeof(double)), nb_idx = al((size_t)pass * sizeof(int)), nb_chi2 = al((size_t)pass * sizeof(double)),
+           nb_st = al((size_t)pass * sizeof(int)), nb_ov = al((size_t)pass * n * sizeof(double));
+    if ((rc = ensure(&ctx->io, &ctx->io_bytes, nb_params + nb_idx + nb_chi2 + nb_st + nb_ov))) return rc;
+    char *base = (char *)ctx->io;
+    double *d_params = (double *)base;
+    int *d_idx = (int *)(base + nb_params);
+    double *d_chi2 = (double *)(base + nb_params + nb_idx);
+    int *d_st = (int *)(base + nb_params + nb_idx + nb_chi2);
+    double *d_ov = (double *)(base + nb_params + nb_idx + nb_chi2 + nb_st);
+    for (int b0 = 0; b0 < B; b0 += cap) {
+        const int bc = std::min(cap, B - b0);
+        BF_CUDA_OK(cudaMemcpyAsync(d_params, params + (size_t)b0 * npar, (size_t)bc * npar * sizeof(double), cudaMemcpyHostToDevice, s));
+        BF_CUDA_OK(cudaMemcpyAsync(d_idx, toy_index + b0, (size_t)bc * sizeof(int), cudaMemcpyHostToDevice, s));
+        BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
+        if ((rc = run_device(ctx, m, d, d_params, bc, OUT_CHI2, d_chi2, 0, d_ov, d_st))) return rc;
+        BF_CUDA_OK(cudaMemcpyAsync(chi2 + b0, d_chi2, (size_t)bc * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (status) BF_CUDA_OK(cudaMemcpyAsync(status + b0, d_st, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, s));
+        BF_CUDA_OK(cudaStreamSynchronize(s));
+    }
+    return BF_OK;
+}

@@ -209,3 +209,9 @@ struct bf_data {
     };
     std::map<const bf_model *, Plan> plans;
 };
+
+struct bf_toys {
+    bf_ctx *ctx = nullptr;
+    int ntoy = 0, n = 0;
+    double *d_table = nullptr;  // [ntoy][n]
+};

@@ -169,6 +169,9 @@ void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a);
 void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const double *proj, int n, int nmu, int B,
                               double *out, int ldo, const double *dsub, const double *dov);
 
+// override panel of the toy path: out[b][i] = table[index[b]][i]
+void launch_gather_rows(cudaStream_t s, const double *table, const int *index, int B, int n, double *out);
+
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);
 

@@ -902,4 +902,15 @@ void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const do
     multipole_project_kernel<<<dim3((B + 127) / 128, n), 128, 0, s>>>(X, ldx, proj, n, nmu, B, out, ldo, dsub, dov);
 }
 
+__global__ void gather_rows_kernel(const double *__restrict__ table, const int *__restrict__ index, int B, int n,
+                                   double *__restrict__ out) {
+    const int b = blockIdx.y;
+    const double *src = table + (size_t)index[b] * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[(size_t)b * n + i] = src[i];
+}
+
+void launch_gather_rows(cudaStream_t s, const double *table, const int *index, int B, int n, double *out) {
+    gather_rows_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(table, index, B, n, out);
+}
+
 }  // namespace bf

@@ -334,6 +334,9 @@ public:
     // empty or B alternative data vectors (toy MC).
     void evaluateBatch(std::vector<likely::Parameters> const &params, std::vector<double> &fval,
                        std::vector<std::vector<double>> const *dataOverride = nullptr) const;
+    // Same against device-resident toy realisations (bf_toys): point b is compared with toy toyIndex[b].
+    void evaluateBatchToys(std::vector<likely::Parameters> const &params, std::vector<double> &fval, bf_toys const *toys,
+                           std::vector<int> const &toyIndex) const;
     void predictBatch(std::vector<likely::Parameters> const &params, std::vector<double> &pred /*[n][B]*/) const;
     // CorrelationFitter.cc:88-92; method is accepted for interface parity ("mn2::vmetric")
     likely::FunctionMinimumPtr fit(std::string const &methodName = "mn2::vmetric", std::string const &config = "") const;

@@ -89,6 +89,27 @@ void CorrelationFitter::evaluateBatch(std::vector<likely::Parameters> const &par
     }
 }
 
+void CorrelationFitter::evaluateBatchToys(std::vector<likely::Parameters> const &params, std::vector<double> &fval,
+                                          bf_toys const *toys, std::vector<int> const &toyIndex) const {
+    int B = (int)params.size(), npar = _model->getNParameters();
+    fval.assign(B, 0.0);
+    if (B == 0) return;
+    if ((int)toyIndex.size() != B) throw RuntimeError("CorrelationFitter: one toy index per parameter vector expected.");
+    std::vector<double> flat((size_t)B * npar), chi2(B);
+    std::vector<int> status(B);
+    for (int b = 0; b < B; ++b) {
+        if ((int)params[b].size() != npar) throw RuntimeError("CorrelationFitter: got unexpected number of parameters.");
+        std::copy(params[b].begin(), params[b].end(), flat.begin() + (size_t)b * npar);
+    }
+    check(bf_chi2_batch_toys(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), flat.data(), B, toys,
+                             toyIndex.data(), chi2.data(), status.data()),
+          "bf_chi2_batch_toys");
+    likely::FitParameters const &fp = _model->getFitParameters();
+    for (int b = 0; b < B; ++b)
+        fval[b] = status[b] ? std::numeric_limits<double>::quiet_NaN()
+                            : (0.5 * _icovScale * chi2[b] + likely::evaluatePriors(fp, params[b])) / _errorScale;
+}
+
 double CorrelationFitter::operator()(likely::Parameters const &params) const {
     if ((int)params.size() != _model->getNParameters()) throw RuntimeError("CorrelationFitter: got unexpected number of parameters.");
     std::vector<likely::Parameters> one(1, params);
@@ -203,31 +224,30 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
     for (auto const &p : truthParams) tp.push_back(p.value);
     std::vector<double> truth;
     fitter.getPrediction(tp, truth);
-    int n = (int)_data->keptIndices().size();
-    std::vector<double> toys((size_t)count * n);
     bool grid = _model->description().dist_matrix != nullptr;
-    check(bf_sample_toys(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, toys.data()),
-          "bf_sample_toys");
-    // every toy is refitted from the model's initial configuration; all fits in lock step, each
-    // evaluation batch carries the data vector of the toy its point belongs to
+    // the realisations are drawn on the GPU and stay there; every evaluation point carries the
+    // index of the toy it belongs to
+    bf_toys *toys = nullptr;
+    check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, &toys), "bf_toys_create");
+    std::shared_ptr<bf_toys> guard(toys, [](bf_toys *t) { bf_toys_destroy(t); });
+    // every toy is refitted from the model's initial configuration; all fits in lock step
     std::vector<likely::NewtonFit> fits((size_t)count, likely::NewtonFit(_model->getFitParameters()));
     std::vector<likely::Parameters> points;
-    std::vector<std::vector<double>> ov;
+    std::vector<int> toyIndex;
     std::vector<double> values;
     for (;;) {
         points.clear();
-        ov.clear();
+        toyIndex.clear();
         bool any = false;
         for (long t = 0; t < count; ++t) {
             if (fits[t].done()) continue;
             size_t before = points.size();
             fits[t].request(points);
-            std::vector<double> d(toys.begin() + (size_t)t * n, toys.begin() + (size_t)(t + 1) * n);
-            for (size_t k = before; k < points.size(); ++k) ov.push_back(d);
+            toyIndex.insert(toyIndex.end(), points.size() - before, (int)t);
             any = true;
         }
         if (!any) break;
-        fitter.evaluateBatch(points, values, &ov);
+        fitter.evaluateBatchToys(points, values, toys, toyIndex);
         size_t off = 0;
         for (long t = 0; t < count; ++t) {
             if (fits[t].done()) continue;

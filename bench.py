@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-scan", action="store_true", help="skip the 2-D scan measurement")
     ap.add_argument("--no-fft", action="store_true", help="skip the FFT-model (BASELINE configs[4]) measurements")
     ap.add_argument("--fft-batch", type=int, default=18944, help="parameter vectors per step per GPU of the FFT-model leg")
-    ap.add_argument("--toys", type=int, default=512, help="toy-MC realisations per GPU refitted in the FFT-model leg")
+    ap.add_argument("--toys", type=int, default=1250, help="toy-MC realisations per GPU refitted in the FFT-model leg (1250 x 8 GPUs = the 10^4-toy study of BASELINE configs[4])")
     return ap.parse_args()
 
 

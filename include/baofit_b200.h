@@ -292,6 +292,19 @@ double bf_model_transform_dr(const bf_model *model);
 int bf_sample_toys(bf_ctx *ctx, const bf_data *data, const double *truth, unsigned long long seed,
                    long long first_toy, int ntoy, double scale, double *out);
 
+/* Device-resident toy-MC realisations: the table [ntoy][n_data] of bf_sample_toys, drawn once on the
+ * GPU and kept there (the loop of CorrelationAnalyzer.cc:262-299,337-373 refits each realisation many
+ * times; only its index travels with every evaluation point). */
+typedef struct bf_toys bf_toys;
+int bf_toys_create(bf_ctx *ctx, const bf_data *data, const double *truth, unsigned long long seed,
+                   long long first_toy, int ntoy, double scale, bf_toys **out);
+int bf_toys_destroy(bf_toys *toys);
+int bf_toys_download(bf_ctx *ctx, const bf_toys *toys, double *out /* [ntoy][n_data] */);
+/* chi2[b] = BinnedData::chiSquare of prediction b against realisation toy_index[b] (host ints, each in
+ * [0, ntoy)) of the table. Host buffers for params / chi2 / status. */
+int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *params, int B,
+                       const bf_toys *toys, const int *toy_index, double *chi2, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,3 +199,24 @@ def test_rspace_large_batch_sorted_path(ctx):
     m, d = W.qso_rspace()
     e_pred, e_chi2 = _compare(ctx, m, d, 2500, 43, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)})
     assert e_pred < RTOL and e_chi2 < RTOL, (e_pred, e_chi2)
+
+
+def test_toy_table_on_device_matches_host_override_path(ctx):
+    """bf_toys_create / bf_chi2_batch_toys (realisations stay on the GPU, points carry a toy index)
+    against bf_sample_toys + bf_chi2_batch with explicit per-point data vectors, and the oracle."""
+    m, d = W.qso_rspace()
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    truth, _ = capi.eval_batch(ctx, gm, gd, m.values[None, :])
+    truth = np.ascontiguousarray(truth[:, 0])
+    toys = capi.Toys(ctx, gd, truth, seed=42, first_toy=100, ntoy=9)
+    table = toys.download()
+    assert np.array_equal(table, gd.sample_toys(truth, 42, 100, 9))
+    rng = np.random.Generator(np.random.PCG64(1))
+    params = m.random_batch(50, rng)
+    idx = rng.integers(0, 9, size=50)
+    a, sa = capi.chi2_batch_toys(ctx, gm, gd, params, toys, idx)
+    b, sb = capi.chi2_batch(ctx, gm, gd, params, data_override=table[idx])
+    assert np.array_equal(a, b) and np.array_equal(sa, sb)
+    ref, _ = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), params, data_override=table[idx], nthreads=8)
+    assert rel_err(a, ref) < RTOL
+    toys.close(), gm.close(), gd.close()
