@@ -22,7 +22,7 @@ EXPORTS = [
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
     "bf_fft_planes_batch", "bf_model_fft_plane_dims",
-    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys",
+    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch",
 ]
 
 
@@ -75,6 +75,8 @@ def lib():
         L.bf_toys_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bf_chi2_batch_toys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+        L.bf_gram_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
         L.bf_fft_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.bf_model_fft_plane_dims.argtypes = [C.c_void_p, c_int_p, c_int_p]
         _LIB = L
@@ -221,6 +223,19 @@ def chi2_batch_toys(ctx, model, data, params, toys, toy_index):
     status = np.zeros(B, dtype=np.int32)
     _check(lib().bf_chi2_batch_toys(ctx.h, model.h, data.h, _ptr(p), B, toys.h, _ptr(idx), _ptr(chi2), _ptr(status)))
     return chi2, status
+
+
+def gram_batch(ctx, model, data, params, G, toys=None, toy_index=None):
+    """Gauss-Newton normal equations of nfit = len(params)/G fits: gram[nfit, G, G], status[nfit, G]."""
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, model.npar)
+    nfit = p.shape[0] // G
+    assert nfit * G == p.shape[0]
+    gram = np.zeros((nfit, G, G))
+    status = np.zeros((nfit, G), dtype=np.int32)
+    idx = None if toy_index is None else np.ascontiguousarray(toy_index, dtype=np.int32)
+    _check(lib().bf_gram_batch(ctx.h, model.h, data.h, _ptr(p), nfit, G, toys.h if toys is not None else None,
+                               _ptr(idx), _ptr(gram), _ptr(status)))
+    return gram, status
 
 
 def eval_batch(ctx, model, data, params):

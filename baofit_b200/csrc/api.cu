@@ -922,7 +922,7 @@ void nl_table(const DevModel &dm, double zeff, double out[5], double *pk_scale) 
     *pk_scale = s * s * std::pow((1.0 + zeff) / (1.0 + dm.zref), -2.0);
 }
 
-enum Output { OUT_PRED, OUT_CHI2, OUT_XIU, OUT_TRANSFORM };
+enum Output { OUT_PRED, OUT_CHI2, OUT_XIU, OUT_TRANSFORM, OUT_WHITENED /* y = L^-1 (pred - d), [n_pad][ldo] */ };
 
 // Runs one chunk (B <= chunk capacity) entirely on the context's stream.
 int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::Plan *plan, const double *d_params,
@@ -1105,14 +1105,19 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         if (!to_user && d->n_pad > d->n)
             BF_CUDA_OK(cudaMemsetAsync(w.Z + (size_t)d->n * ldb, 0, (size_t)(d->n_pad - d->n) * ldb * sizeof(double), s));
         BF_KERNEL(ctx, "fft_eval_kernel", launch_fft_eval(s, ea));
-        if (what == OUT_CHI2) {
+        if (what == OUT_CHI2 || what == OUT_WHITENED) {
             GemmArgs g{};
             g.A = d->d_W; g.Bm = w.Z; g.C = nullptr;
             g.M = d->n_pad; g.N = B; g.K = d->n_pad;
             g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
             g.lower_triangular = 1;
-            g.chi2 = d_out; g.status = w.status;
-            BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+            if (what == OUT_CHI2) {
+                g.chi2 = d_out; g.status = w.status;
+                BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+            } else {
+                g.C = d_out; g.ldc = ldo;
+                BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+            }
         }
         if (d_status_out) BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
         BF_CUDA_OK(cudaGetLastError());
@@ -1165,7 +1170,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         } else
             BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
         if (what == OUT_XIU) finished = true;
-        if (!finished && plan->fold_ok && !d_override) {
+        if (!finished && plan->fold_ok && !d_override && what != OUT_WHITENED) {
             // fused tail: the post-matrix broadband and "- d" are extra K rows of the panel, and for
             // chi2 the whitening W is folded into the left matrix: one GEMM, squares in the epilogue
             FoldArgs fo;
@@ -1244,6 +1249,14 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         g.chi2 = chi2_dst; g.status = w.status;
         BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
     }
+    if (what == OUT_WHITENED) {
+        GemmArgs g{};
+        g.A = d->d_W; g.Bm = w.Z; g.C = d_out;
+        g.M = d->n_pad; g.N = B; g.K = d->n_pad;
+        g.lda = d->n_pad; g.ldb = ldb; g.ldc = ldo;
+        g.lower_triangular = 1;
+        BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+    }
     if (sorted) {
         BF_KERNEL(ctx, "unpermute_kernel", launch_unpermute(s, B, w.rank, w.chi2_sorted, w.status, d_out, d_status_out));
     } else if (d_status_out)
@@ -1277,7 +1290,7 @@ static int run_device(bf_ctx *ctx, const bf_model *m, const bf_data *d, const do
 // usual chi-square GEMM on the residual panel.
 static int run_device_multipole(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *d_params, int B, Output what,
                                 double *d_out, int ldo, const double *d_override, int *d_status) {
-    if (what != OUT_PRED && what != OUT_CHI2) BF_FAIL(BF_ERR_ANALYSIS, "multipole data: only predictions and chi-square are defined");
+    if (what != OUT_PRED && what != OUT_CHI2 && what != OUT_WHITENED) BF_FAIL(BF_ERR_ANALYSIS, "multipole data: only predictions and chi-square are defined");
     if (m->dev.dm_order > 0) BF_FAIL(BF_ERR_DATA, "multipole data cannot be combined with a distortion matrix");
     if (m->dev.idx_delta_v >= 0)
         BF_FAIL(BF_ERR_DATA, "multipole data with a cross-correlation model is not supported (the reference's multipole overload "
@@ -1306,8 +1319,13 @@ static int run_device_multipole(bf_ctx *ctx, const bf_model *m, const bf_data *d
             g.M = d->n_pad; g.N = bc; g.K = d->n_pad;
             g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
             g.lower_triangular = 1;
-            g.chi2 = d_out + b0; g.status = d_status ? d_status + b0 : nullptr;
-            BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+            if (what == OUT_CHI2) {
+                g.chi2 = d_out + b0; g.status = d_status ? d_status + b0 : nullptr;
+                BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+            } else {
+                g.C = d_out + b0; g.ldc = ldo;
+                BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+            }
         }
     }
     BF_CUDA_OK(cudaGetLastError());
@@ -1569,5 +1587,57 @@ extern "C" int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *m, const bf_data 
         if (status) BF_CUDA_OK(cudaMemcpyAsync(status + b0, d_st, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, s));
         BF_CUDA_OK(cudaStreamSynchronize(s));
     }
+    return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gauss-Newton normal equations
+// ------------------------------------------------------------------------------------------
+extern "C" int bf_gram_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int nfit, int G,
+                             const bf_toys *toys, const int *toy_index, double *gram, int *status) {
+    if (!gram || nfit <= 0 || G < 1 || G > 96) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: bad argument (1 <= G <= 96)");
+    int rc = check_args(ctx, m, d, params, nfit * G);
+    if (rc) return rc;
+    if ((toys == nullptr) != (toy_index == nullptr)) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: toys and toy_index go together");
+    if (toys) {
+        if (toys->ctx != ctx || toys->n != d->n) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: the toy table belongs to another context / data set");
+        for (int f = 0; f < nfit; ++f)
+            if (toy_index[f] < 0 || toy_index[f] >= toys->ntoy) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: toy index out of range");
+    }
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const int npar = m->dev.npar, n = d->n;
+    cudaStream_t s = ctx->stream;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    // passes of whole fits, at most ~16384 columns each
+    const int fits_per_pass = std::max(1, std::min(nfit, 16384 / G));
+    const int colcap = fits_per_pass * G, ldy = round_up(colcap, kPadN);
+    size_t nb_params = al((size_t)colcap * npar * sizeof(double)), nb_idx = al((size_t)colcap * sizeof(int)),
+           nb_st = al((size_t)colcap * sizeof(int)), nb_gram = al((size_t)fits_per_pass * G * G * sizeof(double)),
+           nb_ov = toys ? al((size_t)colcap * n * sizeof(double)) : 0, nb_y = al((size_t)d->n_pad * ldy * sizeof(double));
+    if ((rc = ensure(&ctx->io, &ctx->io_bytes, nb_params + nb_idx + nb_st + nb_gram + nb_ov + nb_y))) return rc;
+    char *base = (char *)ctx->io;
+    double *d_params = (double *)base;
+    int *d_idx = (int *)(base + nb_params);
+    int *d_st = (int *)(base + nb_params + nb_idx);
+    double *d_gram = (double *)(base + nb_params + nb_idx + nb_st);
+    double *d_ov = toys ? (double *)(base + nb_params + nb_idx + nb_st + nb_gram) : nullptr;
+    double *d_y = (double *)(base + nb_params + nb_idx + nb_st + nb_gram + nb_ov);
+    std::vector<int> colidx;
+    for (int f0 = 0; f0 < nfit; f0 += fits_per_pass) {
+        const int nf = std::min(fits_per_pass, nfit - f0), bc = nf * G;
+        BF_CUDA_OK(cudaMemcpyAsync(d_params, params + (size_t)f0 * G * npar, (size_t)bc * npar * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (toys) {
+            colidx.resize(bc);
+            for (int c = 0; c < bc; ++c) colidx[c] = toy_index[f0 + c / G];
+            BF_CUDA_OK(cudaMemcpyAsync(d_idx, colidx.data(), (size_t)bc * sizeof(int), cudaMemcpyHostToDevice, s));
+            BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
+        }
+        if ((rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st))) return rc;
+        BF_KERNEL(ctx, "gram_kernel", launch_gram(s, d_y, ldy, n, G, nf, d_gram));
+        BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * G * G, d_gram, (size_t)nf * G * G * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (status) BF_CUDA_OK(cudaMemcpyAsync(status + (size_t)f0 * G, d_st, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, s));
+        BF_CUDA_OK(cudaStreamSynchronize(s));  // colidx is reused by the next pass
+    }
+    BF_CUDA_OK(cudaGetLastError());
     return BF_OK;
 }

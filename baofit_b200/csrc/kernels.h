@@ -169,6 +169,8 @@ void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a);
 void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const double *proj, int n, int nmu, int B,
                               double *out, int ldo, const double *dsub, const double *dov);
 
+// per fit f: Gram matrix of [y0, y1-y0, ..., y_{G-1}-y0] over the columns f*G .. f*G+G-1 of Y (ld = ldy)
+void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out);
 // override panel of the toy path: out[b][i] = table[index[b]][i]
 void launch_gather_rows(cudaStream_t s, const double *table, const int *index, int B, int n, double *out);
 

@@ -913,4 +913,48 @@ void launch_gather_rows(cudaStream_t s, const double *table, const int *index, i
     gather_rows_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(table, index, B, n, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Gauss-Newton normal equations: one CTA per fit
+// ------------------------------------------------------------------------------------------
+constexpr int kGramRows = 32, kGramMaxG = 96;
+
+__global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y, int ldy, int nrows, int G, int nfit,
+                                                   double *__restrict__ out) {
+    extern __shared__ double gsm[];  // [kGramRows][G]
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int npairs = G * (G + 1) / 2;
+    // every thread owns the pairs tid, tid + 256, ... (i >= j), at most kGramMaxG*(kGramMaxG+1)/2/256 = 19
+    double acc[19];
+    int pi[19], pj[19], np = 0;
+    for (int p = tid; p < npairs && np < 19; p += blockDim.x) {
+        int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+        while (i * (i + 1) / 2 > p) --i;
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        pi[np] = i; pj[np] = p - i * (i + 1) / 2; acc[np] = 0.0; ++np;
+    }
+    const double *base = Y + (size_t)f * G;
+    for (int r0 = 0; r0 < nrows; r0 += kGramRows) {
+        const int nr = min(kGramRows, nrows - r0);
+        __syncthreads();
+        for (int e = tid; e < nr * G; e += blockDim.x) {
+            int r = e / G, c = e - r * G;
+            const double *row = base + (size_t)(r0 + r) * ldy;
+            gsm[r * G + c] = c == 0 ? row[0] : row[c] - row[0];
+        }
+        __syncthreads();
+        for (int q = 0; q < np; ++q) {
+            double s = acc[q];
+            const int i = pi[q], j = pj[q];
+            for (int r = 0; r < nr; ++r) s = fma(gsm[r * G + i], gsm[r * G + j], s);
+            acc[q] = s;
+        }
+    }
+    double *o = out + (size_t)f * G * G;
+    for (int q = 0; q < np; ++q) { o[pi[q] * G + pj[q]] = acc[q]; o[pj[q] * G + pi[q]] = acc[q]; }
+}
+
+void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out) {
+    gram_kernel<<<nfit, 256, (size_t)kGramRows * G * sizeof(double), s>>>(Y, ldy, nrows, G, nfit, out);
+}
+
 }  // namespace bf

@@ -337,6 +337,17 @@ public:
     // Same against device-resident toy realisations (bf_toys): point b is compared with toy toyIndex[b].
     void evaluateBatchToys(std::vector<likely::Parameters> const &params, std::vector<double> &fval, bf_toys const *toys,
                            std::vector<int> const &toyIndex) const;
+    // chi2 of B flat parameter vectors (params[B*npar]); NaN where the reference would have thrown.
+    // toys / toyIndex (per point) optional.
+    void chiSquareFlat(std::vector<double> const &params, int B, std::vector<double> &chi2, bf_toys const *toys = nullptr,
+                       const int *toyIndex = nullptr) const;
+    // Gauss-Newton normal equations of nfit probe groups of G points (bf_gram_batch); bad[f] = some point invalid
+    void gramFlat(std::vector<double> const &params, int nfit, int G, std::vector<double> &gram, std::vector<char> &bad,
+                  bf_toys const *toys = nullptr, const int *toyIndexPerFit = nullptr) const;
+    // Runs many LM fits in lock step (Jacobian rounds through gramFlat, trial rounds through chiSquareFlat);
+    // toyOfFit (optional) gives the realisation each fit is taken against.
+    void runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys = nullptr, std::vector<int> const *toyOfFit = nullptr) const;
+    double errorScale() const { return _errorScale; }
     void predictBatch(std::vector<likely::Parameters> const &params, std::vector<double> &pred /*[n][B]*/) const;
     // CorrelationFitter.cc:88-92; method is accepted for interface parity ("mn2::vmetric")
     likely::FunctionMinimumPtr fit(std::string const &methodName = "mn2::vmetric", std::string const &config = "") const;

@@ -1,4 +1,5 @@
 // C entry points over the host-side classes (include/baofit_b200_host.h).
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -217,5 +218,65 @@ extern "C" int bfh_minimize(int npar, const double *values, const double *errors
     if (fval) *fval = fm->minValue;
     if (status) *status = (int)fm->status;
     if (nevaluations) *nevaluations = fm->nEvaluations;
+    BFH_CATCH
+}
+
+extern "C" int bfh_lm_minimize(int npar, const double *values, const double *errors, const int *floating,
+                               const double *prior_centre, const double *prior_sigma, int nres, bfh_resid_fn fn, void *user,
+                               double *out_values, double *fval, int *status, int *nevaluations, int *niterations) {
+    BFH_TRY
+    likely::FitParameters params(npar);
+    for (int i = 0; i < npar; ++i) {
+        params[i].name = "p" + std::to_string(i);
+        params[i].value = values[i];
+        params[i].error = errors[i];
+        params[i].floating = floating[i] != 0;
+        if (prior_sigma && prior_sigma[i] > 0) {
+            params[i].priorType = likely::FitParameter::GaussPrior;
+            params[i].priorMin = prior_centre[i] - prior_sigma[i];
+            params[i].priorMax = prior_centre[i] + prior_sigma[i];
+        }
+    }
+    likely::LMFit fit(params);
+    std::vector<double> flat, resid, gram, chi2;
+    while (!fit.done()) {
+        flat.clear();
+        if (fit.wantsJacobian()) {
+            const int G = fit.groupSize();
+            fit.requestJacobian(flat);
+            resid.assign((size_t)G * nres, 0.0);
+            fn(flat.data(), G, resid.data(), user);
+            gram.assign((size_t)G * G, 0.0);
+            bool bad = false;
+            for (int i = 0; i < G; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    double s = 0;
+                    for (int r = 0; r < nres; ++r) {
+                        double a = i == 0 ? resid[r] : resid[(size_t)i * nres + r] - resid[r];
+                        double b = j == 0 ? resid[r] : resid[(size_t)j * nres + r] - resid[r];
+                        s += a * b;
+                    }
+                    gram[i * G + j] = gram[j * G + i] = s;
+                    bad |= !std::isfinite(s);
+                }
+            fit.consumeJacobian(gram.data(), bad);
+        } else {
+            fit.requestPoints(flat);
+            const int B = fit.pending();
+            resid.assign((size_t)B * nres, 0.0);
+            fn(flat.data(), B, resid.data(), user);
+            chi2.assign(B, 0.0);
+            for (int b = 0; b < B; ++b)
+                for (int r = 0; r < nres; ++r) chi2[b] += resid[(size_t)b * nres + r] * resid[(size_t)b * nres + r];
+            fit.consumePoints(chi2.data());
+        }
+    }
+    likely::FunctionMinimumPtr fm = fit.result();
+    for (int i = 0; i < npar; ++i)
+        if (out_values) out_values[i] = fm->parameters[i].value;
+    if (fval) *fval = fm->minValue;
+    if (status) *status = (int)fm->status;
+    if (nevaluations) *nevaluations = fm->nEvaluations;
+    if (niterations) *niterations = fm->nIterations;
     BFH_CATCH
 }

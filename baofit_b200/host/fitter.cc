@@ -110,6 +110,78 @@ void CorrelationFitter::evaluateBatchToys(std::vector<likely::Parameters> const 
                             : (0.5 * _icovScale * chi2[b] + likely::evaluatePriors(fp, params[b])) / _errorScale;
 }
 
+void CorrelationFitter::chiSquareFlat(std::vector<double> const &params, int B, std::vector<double> &chi2, bf_toys const *toys,
+                                      const int *toyIndex) const {
+    chi2.assign(B, 0.0);
+    if (B == 0) return;
+    std::vector<int> status(B);
+    bf_data *dd = _data->deviceData(needsGrid(_model));
+    if (toys)
+        check(bf_chi2_batch_toys(deviceContext(), _model->deviceModel(), dd, params.data(), B, toys, toyIndex, chi2.data(), status.data()),
+              "bf_chi2_batch_toys");
+    else
+        check(bf_chi2_batch(deviceContext(), _model->deviceModel(), dd, params.data(), B, nullptr, chi2.data(), status.data()), "bf_chi2_batch");
+    for (int b = 0; b < B; ++b)
+        if (status[b]) chi2[b] = std::numeric_limits<double>::quiet_NaN();
+}
+
+void CorrelationFitter::gramFlat(std::vector<double> const &params, int nfit, int G, std::vector<double> &gram, std::vector<char> &bad,
+                                 bf_toys const *toys, const int *toyIndexPerFit) const {
+    gram.assign((size_t)nfit * G * G, 0.0);
+    bad.assign(nfit, 0);
+    if (nfit == 0) return;
+    std::vector<int> status((size_t)nfit * G);
+    check(bf_gram_batch(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), params.data(), nfit, G, toys,
+                        toys ? toyIndexPerFit : nullptr, gram.data(), status.data()),
+          "bf_gram_batch");
+    for (int f = 0; f < nfit; ++f)
+        for (int g = 0; g < G; ++g) bad[f] |= status[(size_t)f * G + g] != 0;
+}
+
+void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys, std::vector<int> const *toyOfFit) const {
+    std::vector<double> flatJ, flatP, gram, chi2;
+    std::vector<char> bad;
+    std::vector<int> jfits, pfits, jtoy, ptoy;
+    for (;;) {
+        // fits are bucketed by group size so that one bf_gram_batch call serves all fits of a size
+        std::map<int, std::vector<int>> byG;
+        pfits.clear();
+        for (size_t k = 0; k < fits.size(); ++k) {
+            if (fits[k].done()) continue;
+            if (fits[k].wantsJacobian()) byG[fits[k].groupSize()].push_back((int)k);
+            else pfits.push_back((int)k);
+        }
+        if (byG.empty() && pfits.empty()) break;
+        for (auto const &kv : byG) {
+            const int G = kv.first;
+            flatJ.clear();
+            jtoy.clear();
+            for (int k : kv.second) {
+                fits[k].requestJacobian(flatJ);
+                if (toys) jtoy.push_back((*toyOfFit)[k]);
+            }
+            gramFlat(flatJ, (int)kv.second.size(), G, gram, bad, toys, toys ? jtoy.data() : nullptr);
+            for (size_t q = 0; q < kv.second.size(); ++q) fits[kv.second[q]].consumeJacobian(gram.data() + q * G * G, bad[q] != 0);
+        }
+        if (!pfits.empty()) {
+            flatP.clear();
+            ptoy.clear();
+            for (int k : pfits) {
+                fits[k].requestPoints(flatP);
+                if (toys) ptoy.insert(ptoy.end(), fits[k].pending(), (*toyOfFit)[k]);
+            }
+            const int npar = fits[pfits[0]].nPar();
+            chiSquareFlat(flatP, (int)(flatP.size() / npar), chi2, toys, toys ? ptoy.data() : nullptr);
+            size_t off = 0;
+            for (int k : pfits) {
+                int np = fits[k].pending();
+                fits[k].consumePoints(chi2.data() + off);
+                off += np;
+            }
+        }
+    }
+}
+
 double CorrelationFitter::operator()(likely::Parameters const &params) const {
     if ((int)params.size() != _model->getNParameters()) throw RuntimeError("CorrelationFitter: got unexpected number of parameters.");
     std::vector<likely::Parameters> one(1, params);
@@ -163,10 +235,15 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
     long total = scanSize();
     if (count < 0) count = total - first;
     if (first < 0 || first + count > total) throw RuntimeError("CorrelationAnalyzer::parameterScan: bad grid range.");
-    std::vector<likely::NewtonFit> fits;
-    fits.reserve(count + 1);
-    // the unconstrained best fit runs in the same lock-step batch
-    fits.push_back(likely::NewtonFit(base));
+    // the unconstrained best fit keeps the Newton driver (its HESSE errors go into the scan header);
+    // the grid fits, whose covariance nobody reads, run Levenberg-Marquardt on Gauss-Newton normal
+    // equations from the GPU
+    std::vector<likely::NewtonFit> bestFit(1, likely::NewtonFit(base));
+    likely::runLockStep(bestFit, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
+    const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
+    std::vector<likely::LMFit> fits;
+    std::vector<likely::Parameters> starts;
+    fits.reserve(count);
     for (long g = first; g < first + count; ++g) {
         likely::FitParameters p = base;
         long rem = g;
@@ -179,12 +256,38 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
         }
         // each grid fit starts from the model's initial configuration, not from the best fit
         // (CorrelationAnalyzer.cc:591)
-        fits.push_back(likely::NewtonFit(p));
+        fits.push_back(likely::LMFit(p, cs, ps));
+        likely::Parameters st;
+        for (auto const &q : p) st.push_back(q.value);
+        starts.push_back(st);
     }
-    likely::runLockStep(fits, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
-    out.best = fits[0].result();
+    fitter.runLockStepLM(fits);
+    // grid points where Levenberg-Marquardt did not converge cleanly (flat or saddle-like regions,
+    // where the Gauss-Newton curvature is a poor model) are refitted with the Newton driver
+    std::vector<likely::FunctionMinimumPtr> results(count);
+    std::vector<likely::NewtonFit> redo;
+    std::vector<long> redoIdx;
     for (long k = 0; k < count; ++k) {
-        likely::FunctionMinimumPtr fm = fits[k + 1].result();
+        results[k] = fits[k].result();
+        if (results[k]->status != likely::FunctionMinimum::OK) {
+            likely::FitParameters p = results[k]->parameters;
+            for (size_t i = 0; i < p.size(); ++i) { p[i].value = starts[k][i]; p[i].error = base[i].error; }
+            redo.push_back(likely::NewtonFit(p));
+            redoIdx.push_back(k);
+        }
+    }
+    if (!redo.empty()) {
+        likely::runLockStep(redo, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
+        for (size_t q = 0; q < redo.size(); ++q) {
+            likely::FunctionMinimumPtr fm = redo[q].result();
+            bool better = fm->status != likely::FunctionMinimum::ERROR &&
+                          (results[redoIdx[q]]->status == likely::FunctionMinimum::ERROR || fm->minValue <= results[redoIdx[q]]->minValue);
+            if (better) results[redoIdx[q]] = fm;
+        }
+    }
+    out.best = bestFit[0].result();
+    for (long k = 0; k < count; ++k) {
+        likely::FunctionMinimumPtr fm = results[k];
         bool ok = fm->status != likely::FunctionMinimum::ERROR;
         out.points.push_back(fm->values());
         out.chi2.push_back(ok ? 2 * fm->minValue : 0.0);  // failed fits are saved with fval = 0 (:595-602)
@@ -231,34 +334,54 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
     check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, &toys), "bf_toys_create");
     std::shared_ptr<bf_toys> guard(toys, [](bf_toys *t) { bf_toys_destroy(t); });
     // every toy is refitted from the model's initial configuration; all fits in lock step
-    std::vector<likely::NewtonFit> fits((size_t)count, likely::NewtonFit(_model->getFitParameters()));
-    std::vector<likely::Parameters> points;
-    std::vector<int> toyIndex;
-    std::vector<double> values;
-    for (;;) {
-        points.clear();
-        toyIndex.clear();
-        bool any = false;
+    const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
+    std::vector<likely::LMFit> fits((size_t)count, likely::LMFit(_model->getFitParameters(), cs, ps));
+    std::vector<int> toyOfFit(count);
+    for (long t = 0; t < count; ++t) toyOfFit[t] = (int)t;
+    fitter.runLockStepLM(fits, toys, &toyOfFit);
+    std::vector<likely::FunctionMinimumPtr> results(count);
+    {
+        // toys whose LM fit did not converge cleanly are refitted with the Newton driver
+        std::vector<likely::NewtonFit> redo;
+        std::vector<int> redoToy;
         for (long t = 0; t < count; ++t) {
-            if (fits[t].done()) continue;
-            size_t before = points.size();
-            fits[t].request(points);
-            toyIndex.insert(toyIndex.end(), points.size() - before, (int)t);
-            any = true;
+            results[t] = fits[t].result();
+            if (results[t]->status != likely::FunctionMinimum::OK) { redo.push_back(likely::NewtonFit(_model->getFitParameters())); redoToy.push_back((int)t); }
         }
-        if (!any) break;
-        fitter.evaluateBatchToys(points, values, toys, toyIndex);
-        size_t off = 0;
-        for (long t = 0; t < count; ++t) {
-            if (fits[t].done()) continue;
-            int np = fits[t].pending();
-            fits[t].consume(values.data() + off);
-            off += np;
+        std::vector<likely::Parameters> points;
+        std::vector<int> toyIndex;
+        std::vector<double> values;
+        while (!redo.empty()) {
+            points.clear();
+            toyIndex.clear();
+            bool any = false;
+            for (size_t q = 0; q < redo.size(); ++q) {
+                if (redo[q].done()) continue;
+                size_t before = points.size();
+                redo[q].request(points);
+                toyIndex.insert(toyIndex.end(), points.size() - before, redoToy[q]);
+                any = true;
+            }
+            if (!any) break;
+            fitter.evaluateBatchToys(points, values, toys, toyIndex);
+            size_t off = 0;
+            for (size_t q = 0; q < redo.size(); ++q) {
+                if (redo[q].done()) continue;
+                int np = redo[q].pending();
+                redo[q].consume(values.data() + off);
+                off += np;
+            }
+        }
+        for (size_t q = 0; q < redo.size(); ++q) {
+            likely::FunctionMinimumPtr fm = redo[q].result();
+            if (fm->status != likely::FunctionMinimum::ERROR &&
+                (results[redoToy[q]]->status == likely::FunctionMinimum::ERROR || fm->minValue <= results[redoToy[q]]->minValue))
+                results[redoToy[q]] = fm;
         }
     }
     fitted.clear(); chi2.clear(); status.clear();
     for (long t = 0; t < count; ++t) {
-        likely::FunctionMinimumPtr fm = fits[t].result();
+        likely::FunctionMinimumPtr fm = results[t];
         fitted.push_back(fm->values());
         chi2.push_back(2 * fm->minValue);
         status.push_back((int)fm->status);

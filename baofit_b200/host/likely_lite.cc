@@ -406,6 +406,169 @@ FunctionMinimumPtr NewtonFit::result() const {
     return fm;
 }
 
+// ------------------------------------------------------------------------------------------
+// Levenberg-Marquardt on Gauss-Newton normal equations
+// ------------------------------------------------------------------------------------------
+void priorDerivatives(FitParameter const &p, double x, double &value, double &grad, double &hess) {
+    value = grad = hess = 0;
+    if (!p.floating || p.priorType == FitParameter::NoPrior) return;
+    double c = 0.5 * (p.priorMin + p.priorMax), s = 0.5 * (p.priorMax - p.priorMin);
+    if (p.priorType == FitParameter::GaussPrior) {
+        double t = (x - c) / s;
+        value = 0.5 * t * t; grad = t / s; hess = 1 / (s * s);
+    } else {
+        double w = 1e-3 * s;
+        if (x < p.priorMin) { double d = p.priorMin - x; value = 0.5 * d * d / (w * w); grad = -d / (w * w); hess = 1 / (w * w); }
+        else if (x > p.priorMax) { double d = x - p.priorMax; value = 0.5 * d * d / (w * w); grad = d / (w * w); hess = 1 / (w * w); }
+    }
+}
+
+LMFit::LMFit(FitParameters const &params, double chi2Scale, double priorScale)
+    : _stage(Jacobian), _params(params), _cs(chi2Scale), _ps(priorScale) {
+    for (size_t i = 0; i < params.size(); ++i) {
+        _x.push_back(params[i].value);
+        if (params[i].floating) {
+            _fidx.push_back((int)i);
+            double e = params[i].error > 0 ? params[i].error : std::max(1e-3, 0.1 * std::fabs(params[i].value));
+            _h.push_back(1e-3 * e);
+            _scale.push_back(e);
+        }
+    }
+    _n = (int)_fidx.size();
+    _g.assign(_n, 0.0);
+    _A.assign((size_t)_n * _n, 0.0);
+    _step.assign(_n, 0.0);
+}
+
+double LMFit::priorValue(Parameters const &x) const { return _ps * evaluatePriors(_params, x); }
+
+void LMFit::requestJacobian(std::vector<double> &flat) const {
+    flat.insert(flat.end(), _x.begin(), _x.end());
+    for (int i = 0; i < _n; ++i) {
+        size_t at = flat.size();
+        flat.insert(flat.end(), _x.begin(), _x.end());
+        flat[at + _fidx[i]] += _h[i];
+    }
+}
+
+void LMFit::solveStep() {
+    std::vector<double> rhs(_n), M;
+    for (int i = 0; i < _n; ++i) rhs[i] = -_g[i];
+    for (int attempt = 0; attempt < 60; ++attempt) {
+        M = _A;
+        for (int i = 0; i < _n; ++i) {
+            // Marquardt scaling with a floor from the parameter's natural size: where the Gauss-Newton
+            // curvature vanishes (e.g. bias -> 0, the model is quadratic in it) the damping still bites
+            double d = std::max(_A[i * _n + i], 1e-2 / (_scale[i] * _scale[i]));
+            M[i * _n + i] += _lambda * d;
+        }
+        if (cholSolve(_n, M, rhs, _step)) break;
+        _lambda = _lambda > 0 ? _lambda * 10 : 1e-6;
+        if (attempt == 59)
+            for (int i = 0; i < _n; ++i) _step[i] = -_g[i] * _h[i] * _h[i];
+    }
+    // trust region in units of the parameters' natural sizes: no parameter moves by more than 5 of them
+    double worst = 0;
+    for (int i = 0; i < _n; ++i) worst = std::max(worst, std::fabs(_step[i]) / _scale[i]);
+    if (worst > 5.0)
+        for (int i = 0; i < _n; ++i) _step[i] *= 5.0 / worst;
+}
+
+void LMFit::consumeJacobian(const double *gram, bool bad) {
+    const int G = _n + 1;
+    _neval += G;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int k = 0; k < G * G && !bad; ++k) bad |= !std::isfinite(gram[k]);
+    if (bad) {
+        // a probe (or the centre) left the valid domain: shrink the probe steps; a bad centre is fatal
+        if (!std::isfinite(gram[0]) || ++_shrinks > 8) { _failed = true; _f0 = inf; _stage = Done; return; }
+        for (auto &h : _h) h *= 0.25;
+        return;
+    }
+    _f0 = _cs * 0.5 * gram[0] + priorValue(_x);
+    for (int i = 0; i < _n; ++i) {
+        double pv, pg, ph;
+        priorDerivatives(_params[_fidx[i]], _x[_fidx[i]], pv, pg, ph);
+        _g[i] = _cs * gram[(i + 1) * G] / _h[i] + _ps * pg;
+        for (int j = 0; j < _n; ++j) _A[i * _n + j] = _cs * gram[(i + 1) * G + (j + 1)] / (_h[i] * _h[j]);
+        _A[i * _n + i] += _ps * ph;
+    }
+    if (_n == 0) { _converged = true; _stage = Done; return; }
+    // estimated distance to the minimum with the undamped Gauss-Newton step
+    {
+        std::vector<double> rhs(_n), st;
+        for (int i = 0; i < _n; ++i) rhs[i] = -_g[i];
+        if (cholSolve(_n, _A, rhs, st)) {
+            double edm = 0;
+            for (int i = 0; i < _n; ++i) edm -= 0.5 * _g[i] * st[i];
+            _edm = edm;
+        } else
+            _edm = inf;
+    }
+    ++_iter;
+    if (_edm < tolerance) { _converged = true; _stage = Done; return; }
+    if (_iter > maxIterations) { _stage = Done; return; }
+    // probe steps from the curvature: forward differences with delta F ~ 1e-6 keep the truncation
+    // error of the Jacobian far below the tolerance, the residual differences stay ~1e-4 of |y|
+    for (int i = 0; i < _n; ++i) {
+        double a = _A[i * _n + i];
+        if (a > 0) _h[i] = std::max(std::sqrt(2e-6 / a), 1e-9 * std::max(1.0, std::fabs(_x[_fidx[i]])));
+    }
+    solveStep();
+    _alphas = {1.0, 0.3, 0.1};
+    _stage = Trial;
+}
+
+void LMFit::requestPoints(std::vector<double> &flat) {
+    _npending = 0;
+    for (double a : _alphas) {
+        size_t at = flat.size();
+        flat.insert(flat.end(), _x.begin(), _x.end());
+        for (int i = 0; i < _n; ++i) flat[at + _fidx[i]] += a * _step[i];
+        ++_npending;
+    }
+}
+
+void LMFit::consumePoints(const double *chi2) {
+    _neval += _npending;
+    int best = -1;
+    double fbest = _f0;
+    Parameters trial(_x);
+    for (size_t k = 0; k < _alphas.size(); ++k) {
+        if (!std::isfinite(chi2[k])) continue;
+        for (int i = 0; i < _n; ++i) trial[_fidx[i]] = _x[_fidx[i]] + _alphas[k] * _step[i];
+        double f = _cs * 0.5 * chi2[k] + priorValue(trial);
+        if (f < fbest) { fbest = f; best = (int)k; }
+    }
+    if (best >= 0) {
+        double a = _alphas[best];
+        for (int i = 0; i < _n; ++i) _x[_fidx[i]] += a * _step[i];
+        _f0 = fbest;
+        _stall = 0;
+        _lambda = a >= 1.0 ? std::max(_lambda * 0.1, 1e-12) : _lambda;
+        _stage = Jacobian;
+    } else {
+        // no trial improved: damp more, same normal equations
+        if (++_stall > 12) { _stage = Done; return; }
+        _lambda = std::max(_lambda, 1e-4) * (_stall > 3 ? 100 : 10);
+        solveStep();
+        _alphas = {1.0, 0.3, 0.1};
+    }
+}
+
+FunctionMinimumPtr LMFit::result() const {
+    FunctionMinimumPtr fm(new FunctionMinimum());
+    fm->parameters = _params;
+    for (size_t i = 0; i < _params.size(); ++i) fm->parameters[i].value = _x[i];
+    fm->minValue = _f0;
+    fm->nEvaluations = _neval;
+    fm->nIterations = _iter;
+    fm->edm = _edm;
+    if (_failed || !std::isfinite(_f0)) fm->status = FunctionMinimum::ERROR;
+    else fm->status = _converged ? FunctionMinimum::OK : FunctionMinimum::WARNING;
+    return fm;
+}
+
 void runLockStep(std::vector<NewtonFit> &fits, BatchFunction const &f) {
     std::vector<Parameters> points;
     std::vector<double> values;

@@ -113,4 +113,46 @@ private:
 // Runs a set of fits in lock step: gathers every unfinished fit's requests into one batch.
 void runLockStep(std::vector<NewtonFit> &fits, BatchFunction const &f);
 
+// -log(prior) of one parameter and its first / second derivative (same forms as evaluatePriors)
+void priorDerivatives(FitParameter const &p, double x, double &value, double &grad, double &hess);
+
+// Levenberg-Marquardt on the Gauss-Newton normal equations, request/consume form, for objectives
+//   F(x) = chi2Scale * 0.5 |y(x)|^2 + priorScale * priors(x)
+// whose residual Gram matrices come from the GPU (bf_gram_batch): one Jacobian round needs only the
+// centre + n forward probes (n+1 points instead of the 1 + 2n + n(n-1)/2 of NewtonFit), one trial
+// round three step lengths. Used for the many independent refits of scans and toy studies, where the
+// covariance of each fit is not needed; single fits keep NewtonFit (accurate HESSE errors).
+class LMFit {
+public:
+    LMFit(FitParameters const &params, double chi2Scale = 1.0, double priorScale = 1.0);
+    bool done() const { return _stage == Done; }
+    bool wantsJacobian() const { return _stage == Jacobian; }
+    int groupSize() const { return _n + 1; }
+    int nPar() const { return (int)_x.size(); }
+    // Jacobian round: appends groupSize() full-length vectors (centre first) to flat
+    void requestJacobian(std::vector<double> &flat) const;
+    // gram[G*G] as returned by bf_gram_batch; bad = some column had a non-zero status
+    void consumeJacobian(const double *gram, bool bad);
+    // trial round: appends pending() full-length vectors
+    void requestPoints(std::vector<double> &flat);
+    int pending() const { return _npending; }
+    // fval[k] = chi2 of point k (NaN if invalid); priors are added here
+    void consumePoints(const double *chi2);
+    FunctionMinimumPtr result() const;
+    double tolerance = 1e-6;
+    int maxIterations = 25;  // a fit that needs more is handed to NewtonFit by the callers
+
+private:
+    enum Stage { Jacobian, Trial, Done } _stage;
+    FitParameters _params;
+    std::vector<int> _fidx;
+    int _n, _npending = 0, _iter = 0, _neval = 0, _stall = 0, _shrinks = 0;
+    double _cs, _ps, _f0 = 0, _edm = 0, _lambda = 1e-3;
+    bool _failed = false, _converged = false;
+    Parameters _x;
+    std::vector<double> _h, _g, _A, _step, _alphas, _scale;  // _scale: natural size of each floating parameter (its error estimate)
+    double priorValue(Parameters const &x) const;
+    void solveStep();
+};
+
 }  // namespace likely

@@ -7,10 +7,12 @@ from . import capi
 
 _BOUND = False
 BATCH_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)
+RESID_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)
 
 HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
-                "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize"]
+                "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
+                "bfh_lm_minimize"]
 
 
 def lib():
@@ -37,6 +39,9 @@ def lib():
         L.bfh_toymc.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, BATCH_FN, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.bfh_lm_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, RESID_FN,
+                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]
         _BOUND = True
     return L
 
@@ -156,3 +161,26 @@ def minimize(fn, values, errors, floating):
     _check(lib().bfh_minimize(npar, _p(values), _p(errors), _p(fl), cfn, None, _p(ov), _p(oe), C.byref(fval),
                               C.byref(status), C.byref(nev)))
     return dict(values=ov, errors=oe, fval=fval.value, status=status.value, nevaluations=nev.value)
+
+
+def lm_minimize(resid_fn, nres, values, errors, floating, prior_centre=None, prior_sigma=None):
+    """Runs the library's Levenberg-Marquardt driver over a Python residual function
+    resid_fn(points[B, npar]) -> resid[B, nres]; objective 0.5 |resid|^2 + Gaussian priors."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    errors = np.ascontiguousarray(errors, dtype=np.float64)
+    fl = np.ascontiguousarray(np.asarray(floating).astype(np.int32))
+    npar = len(values)
+    pc = np.zeros(npar) if prior_centre is None else np.ascontiguousarray(prior_centre, dtype=np.float64)
+    ps = np.zeros(npar) if prior_sigma is None else np.ascontiguousarray(prior_sigma, dtype=np.float64)
+
+    def cb(pts, B, out, user):
+        p = np.ctypeslib.as_array(pts, shape=(B, npar))
+        o = np.ctypeslib.as_array(out, shape=(B, nres))
+        o[:] = resid_fn(p.copy())
+
+    cfn = RESID_FN(cb)
+    ov = np.zeros(npar)
+    fval, status, nev, nit = C.c_double(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib().bfh_lm_minimize(npar, _p(values), _p(errors), _p(fl), _p(pc), _p(ps), nres, cfn, None, _p(ov), C.byref(fval),
+                                 C.byref(status), C.byref(nev), C.byref(nit)))
+    return dict(values=ov, fval=fval.value, status=status.value, nevaluations=nev.value, niterations=nit.value)

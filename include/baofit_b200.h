@@ -305,6 +305,19 @@ int bf_toys_download(bf_ctx *ctx, const bf_toys *toys, double *out /* [ntoy][n_d
 int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *params, int B,
                        const bf_toys *toys, const int *toy_index, double *chi2, int *status);
 
+/* Gauss-Newton normal equations for many independent fits at once (the minimiser-side consumer of the
+ * hot path: CorrelationFitter::fit -> likely::FitModel::findMinimum, CorrelationFitter.cc:88-97, called
+ * per scan point / toy by CorrelationAnalyzer.cc:169-190). params holds nfit groups of G consecutive
+ * vectors: the centre x of a fit followed by its G-1 probe points. With y(p) = L^-1 (pred(p) - d) the
+ * whitened residual (chi2 = |y|^2) and d_i = y(probe i) - y(centre), the call returns per fit the
+ * symmetric G x G matrix
+ *     gram[0][0] = y0.y0 (= chi2 at the centre),  gram[i][0] = gram[0][i] = d_i.y0,  gram[i][j] = d_i.d_j,
+ * from which J^T J and J^T y follow by dividing by the probe steps. toys / toy_index (may be NULL)
+ * select, per fit, the device-resident realisation the residuals are taken against.
+ * status[nfit*G] as in bf_chi2_batch. Host buffers. */
+int bf_gram_batch(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *params, int nfit, int G,
+                  const bf_toys *toys, const int *toy_index, double *gram, int *status);
+
 #ifdef __cplusplus
 }
 #endif

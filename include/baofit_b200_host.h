@@ -67,6 +67,15 @@ typedef void (*bfh_batch_fn)(const double *points, int B, double *f, void *user)
 int bfh_minimize(int npar, const double *values, const double *errors, const int *floating, bfh_batch_fn fn,
                  void *user, double *out_values, double *out_errors, double *fval, int *status, int *nevaluations);
 
+/* The Levenberg-Marquardt driver (likely::LMFit, used for the refits of scans and toy studies) over a
+ * caller-supplied batched residual function: fn(points[B*npar], B, resid[B*nres], user), objective
+ * 0.5 |resid|^2 + Gaussian priors (prior_sigma[i] > 0: centre prior_centre[i]). The normal equations
+ * are formed on the host here (on the GPU in the product path). For host-only tests of the driver. */
+typedef void (*bfh_resid_fn)(const double *points, int B, double *resid, void *user);
+int bfh_lm_minimize(int npar, const double *values, const double *errors, const int *floating, const double *prior_centre,
+                    const double *prior_sigma, int nres, bfh_resid_fn fn, void *user, double *out_values, double *fval,
+                    int *status, int *nevaluations, int *niterations);
+
 #ifdef __cplusplus
 }
 #endif

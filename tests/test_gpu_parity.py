@@ -220,3 +220,44 @@ def test_toy_table_on_device_matches_host_override_path(ctx):
     ref, _ = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), params, data_override=table[idx], nthreads=8)
     assert rel_err(a, ref) < RTOL
     toys.close(), gm.close(), gd.close()
+
+
+@pytest.mark.parametrize("case", ["rspace", "kspace_dm", "fft"])
+def test_gram_batch_against_oracle_residuals(ctx, case):
+    """bf_gram_batch: Gram matrices of the whitened residuals y = L^-1 (pred - d) of probe groups,
+    against numpy on the oracle's predictions."""
+    import scipy.linalg
+    if case == "rspace":
+        m, d = W.qso_rspace()
+        nfit, G = 7, 19
+    elif case == "kspace_dm":
+        m, d = W.qso_kspace()
+        nfit, G = 2, 3
+    else:
+        import test_fft_model as T
+        m, d, _ = T._gpu_case(ngrid=128, spacing=5., nbins=40)
+        nfit, G = 3, 6
+    rng = np.random.Generator(np.random.PCG64(31))
+    centres = m.random_batch(nfit, rng)
+    params = np.repeat(centres, G, axis=0)
+    fl = np.nonzero(m.floating)[0]
+    for f in range(nfit):
+        for g in range(1, G):
+            j = fl[(g - 1) % len(fl)]
+            params[f * G + g, j] += 0.01 * m.errors[j]
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    gram, st = capi.gram_batch(ctx, gm, gd, params, G)
+    chi2, _ = capi.chi2_batch(ctx, gm, gd, params)
+    _, ref_st, pred = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), params, want_pred=True, nthreads=8)
+    assert np.all(st == 0) and np.all(ref_st == 0)
+    cov = d.keep._arrays[5]
+    L = np.linalg.cholesky(cov)
+    y = scipy.linalg.solve_triangular(L, pred - d.keep._arrays[4][:, None], lower=True)
+    for f in range(nfit):
+        yf = y[:, f * G:(f + 1) * G]
+        D = np.column_stack([yf[:, 0]] + [yf[:, g] - yf[:, 0] for g in range(1, G)])
+        ref = D.T @ D
+        scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+        assert np.max(np.abs(gram[f] - ref) / scale) < 1e-7  # differences of nearly equal residual vectors
+        assert abs(gram[f, 0, 0] - chi2[f * G]) < 1e-10 * chi2[f * G]
+    gm.close(), gd.close()
