@@ -8,6 +8,9 @@
 #include <limits>
 #include <sstream>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "baofit_host.h"
 
 namespace baofit {
@@ -257,6 +260,7 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
         // each grid fit starts from the model's initial configuration, not from the best fit
         // (CorrelationAnalyzer.cc:591)
         fits.push_back(likely::LMFit(p, cs, ps));
+        if (g == first && std::getenv("BAOFIT_VERBOSE_FITS") && std::atoi(std::getenv("BAOFIT_VERBOSE_FITS")) > 1) fits.back().debug = true;
         likely::Parameters st;
         for (auto const &q : p) st.push_back(q.value);
         starts.push_back(st);
@@ -275,6 +279,11 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
             redo.push_back(likely::NewtonFit(p));
             redoIdx.push_back(k);
         }
+    }
+    if (std::getenv("BAOFIT_VERBOSE_FITS")) {
+        long nev = 0;
+        for (auto const &r : results) nev += r->nEvaluations;
+        std::fprintf(stderr, "parameterScan: %ld grid fits, %zu handed to the Newton driver, %ld LM evaluations\n", count, redo.size(), nev);
     }
     if (!redo.empty()) {
         likely::runLockStep(redo, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });

@@ -1,5 +1,7 @@
 #include "likely_lite.h"
 
+#include <cstdio>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -443,12 +445,14 @@ LMFit::LMFit(FitParameters const &params, double chi2Scale, double priorScale)
 double LMFit::priorValue(Parameters const &x) const { return _ps * evaluatePriors(_params, x); }
 
 void LMFit::requestJacobian(std::vector<double> &flat) const {
+    // columns: x, x + h_1, x - h_1, x + h_2, x - h_2, ...
     flat.insert(flat.end(), _x.begin(), _x.end());
-    for (int i = 0; i < _n; ++i) {
-        size_t at = flat.size();
-        flat.insert(flat.end(), _x.begin(), _x.end());
-        flat[at + _fidx[i]] += _h[i];
-    }
+    for (int i = 0; i < _n; ++i)
+        for (int sgn = 1; sgn >= -1; sgn -= 2) {
+            size_t at = flat.size();
+            flat.insert(flat.end(), _x.begin(), _x.end());
+            flat[at + _fidx[i]] += sgn * _h[i];
+        }
 }
 
 void LMFit::solveStep() {
@@ -467,15 +471,18 @@ void LMFit::solveStep() {
         if (attempt == 59)
             for (int i = 0; i < _n; ++i) _step[i] = -_g[i] * _h[i] * _h[i];
     }
-    // trust region in units of the parameters' natural sizes: no parameter moves by more than 5 of them
+    // trust region in units of the parameters' natural sizes: no parameter moves by more than _radius
+    // of them; the radius grows while capped full steps keep succeeding (valleys that run to a prior
+    // wall, e.g. beta -> large with beta*bias fixed) and shrinks when a trial round fails
     double worst = 0;
     for (int i = 0; i < _n; ++i) worst = std::max(worst, std::fabs(_step[i]) / _scale[i]);
-    if (worst > 5.0)
-        for (int i = 0; i < _n; ++i) _step[i] *= 5.0 / worst;
+    _capped = worst > _radius;
+    if (_capped)
+        for (int i = 0; i < _n; ++i) _step[i] *= _radius / worst;
 }
 
 void LMFit::consumeJacobian(const double *gram, bool bad) {
-    const int G = _n + 1;
+    const int G = 2 * _n + 1;
     _neval += G;
     const double inf = std::numeric_limits<double>::infinity();
     for (int k = 0; k < G * G && !bad; ++k) bad |= !std::isfinite(gram[k]);
@@ -486,11 +493,21 @@ void LMFit::consumeJacobian(const double *gram, bool bad) {
         return;
     }
     _f0 = _cs * 0.5 * gram[0] + priorValue(_x);
+    // with d+_i = y(x + h_i) - y0 (column 2i+1) and d-_i = y(x - h_i) - y0 (column 2i+2):
+    //   J_i = (d+_i - d-_i)/(2 h_i),   y0.d2y/dx_i^2 = y0.(d+_i + d-_i)/h_i^2
+    auto gm = [&](int a, int b) { return gram[a * G + b]; };
     for (int i = 0; i < _n; ++i) {
+        const int ip = 2 * i + 1, im = 2 * i + 2;
         double pv, pg, ph;
         priorDerivatives(_params[_fidx[i]], _x[_fidx[i]], pv, pg, ph);
-        _g[i] = _cs * gram[(i + 1) * G] / _h[i] + _ps * pg;
-        for (int j = 0; j < _n; ++j) _A[i * _n + j] = _cs * gram[(i + 1) * G + (j + 1)] / (_h[i] * _h[j]);
+        _g[i] = _cs * (gm(ip, 0) - gm(im, 0)) / (2 * _h[i]) + _ps * pg;
+        for (int j = 0; j < _n; ++j) {
+            const int jp = 2 * j + 1, jm = 2 * j + 2;
+            _A[i * _n + j] = _cs * (gm(ip, jp) - gm(ip, jm) - gm(im, jp) + gm(im, jm)) / (4 * _h[i] * _h[j]);
+        }
+        // diagonal of the second-order term, kept only while the curvature stays positive
+        const double second = _cs * (gm(ip, 0) + gm(im, 0)) / (_h[i] * _h[i]);
+        if (_A[i * _n + i] + second > 0.1 * _A[i * _n + i]) _A[i * _n + i] += second;
         _A[i * _n + i] += _ps * ph;
     }
     if (_n == 0) { _converged = true; _stage = Done; return; }
@@ -506,13 +523,18 @@ void LMFit::consumeJacobian(const double *gram, bool bad) {
             _edm = inf;
     }
     ++_iter;
+    if (debug) {
+        std::fprintf(stderr, "LM it %d f0 %.6f edm %.3e lambda %.1e x", _iter, _f0, _edm, _lambda);
+        for (int i = 0; i < _n; ++i) std::fprintf(stderr, " %.5g", _x[_fidx[i]]);
+        std::fprintf(stderr, "\n");
+    }
     if (_edm < tolerance) { _converged = true; _stage = Done; return; }
     if (_iter > maxIterations) { _stage = Done; return; }
-    // probe steps from the curvature: forward differences with delta F ~ 1e-6 keep the truncation
-    // error of the Jacobian far below the tolerance, the residual differences stay ~1e-4 of |y|
+    // probe steps from the curvature: delta F ~ 1e-4 along each axis, never more than a tenth of the
+    // parameter's natural size
     for (int i = 0; i < _n; ++i) {
         double a = _A[i * _n + i];
-        if (a > 0) _h[i] = std::max(std::sqrt(2e-6 / a), 1e-9 * std::max(1.0, std::fabs(_x[_fidx[i]])));
+        if (a > 0) _h[i] = std::min(0.1 * _scale[i], std::max(std::sqrt(2e-4 / a), 1e-9 * std::max(1.0, std::fabs(_x[_fidx[i]]))));
     }
     solveStep();
     _alphas = {1.0, 0.3, 0.1};
@@ -540,16 +562,24 @@ void LMFit::consumePoints(const double *chi2) {
         double f = _cs * 0.5 * chi2[k] + priorValue(trial);
         if (f < fbest) { fbest = f; best = (int)k; }
     }
+    if (debug) std::fprintf(stderr, "   trial best %d f %.6f (f0 %.6f) stall %d lambda %.1e\n", best, fbest, _f0, _stall, _lambda);
     if (best >= 0) {
         double a = _alphas[best];
         for (int i = 0; i < _n; ++i) _x[_fidx[i]] += a * _step[i];
+        const double gain = _f0 - fbest;
         _f0 = fbest;
         _stall = 0;
         _lambda = a >= 1.0 ? std::max(_lambda * 0.1, 1e-12) : _lambda;
+        if (_capped && a >= 1.0) _radius *= 3.0;
+        // a minimum with a flat direction (bias = 0 makes beta irrelevant: singular normal matrix, no
+        // finite EDM) is recognised by accepted steps that no longer gain anything
+        _smallGains = gain < 0.01 * tolerance ? _smallGains + 1 : 0;
+        if (_smallGains >= 2) { _converged = true; _stage = Done; return; }
         _stage = Jacobian;
     } else {
         // no trial improved: damp more, same normal equations
-        if (++_stall > 12) { _stage = Done; return; }
+        if (++_stall > 12) { _converged = _smallGains >= 1; _stage = Done; return; }
+        _radius = std::max(_radius / 3.0, 1.0);
         _lambda = std::max(_lambda, 1e-4) * (_stall > 3 ? 100 : 10);
         solveStep();
         _alphas = {1.0, 0.3, 0.1};

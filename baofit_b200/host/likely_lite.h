@@ -118,16 +118,18 @@ void priorDerivatives(FitParameter const &p, double x, double &value, double &gr
 
 // Levenberg-Marquardt on the Gauss-Newton normal equations, request/consume form, for objectives
 //   F(x) = chi2Scale * 0.5 |y(x)|^2 + priorScale * priors(x)
-// whose residual Gram matrices come from the GPU (bf_gram_batch): one Jacobian round needs only the
-// centre + n forward probes (n+1 points instead of the 1 + 2n + n(n-1)/2 of NewtonFit), one trial
-// round three step lengths. Used for the many independent refits of scans and toy studies, where the
+// whose residual Gram matrices come from the GPU (bf_gram_batch): one Jacobian round needs the centre
+// and the 2n central probes x +- h_i (2n+1 points instead of the 1 + 2n + n(n-1)/2 of NewtonFit), one
+// trial round three step lengths. The central probes also give the diagonal of the second-order
+// term y.d2y/dx_i^2 that Gauss-Newton drops; it is added to the normal matrix, which matters where the
+// model is quadratic in a parameter (bias -> 0). Used for the many independent refits of scans and toy studies, where the
 // covariance of each fit is not needed; single fits keep NewtonFit (accurate HESSE errors).
 class LMFit {
 public:
     LMFit(FitParameters const &params, double chi2Scale = 1.0, double priorScale = 1.0);
     bool done() const { return _stage == Done; }
     bool wantsJacobian() const { return _stage == Jacobian; }
-    int groupSize() const { return _n + 1; }
+    int groupSize() const { return 2 * _n + 1; }
     int nPar() const { return (int)_x.size(); }
     // Jacobian round: appends groupSize() full-length vectors (centre first) to flat
     void requestJacobian(std::vector<double> &flat) const;
@@ -140,14 +142,17 @@ public:
     void consumePoints(const double *chi2);
     FunctionMinimumPtr result() const;
     double tolerance = 1e-6;
-    int maxIterations = 25;  // a fit that needs more is handed to NewtonFit by the callers
+    int maxIterations = 40;  // a fit that needs more is handed to NewtonFit by the callers
+    bool debug = false;      // trace iterations on stderr
 
 private:
     enum Stage { Jacobian, Trial, Done } _stage;
     FitParameters _params;
     std::vector<int> _fidx;
     int _n, _npending = 0, _iter = 0, _neval = 0, _stall = 0, _shrinks = 0;
-    double _cs, _ps, _f0 = 0, _edm = 0, _lambda = 1e-3;
+    double _cs, _ps, _f0 = 0, _edm = 0, _lambda = 1e-3, _radius = 5.0;
+    bool _capped = false;
+    int _smallGains = 0;
     bool _failed = false, _converged = false;
     Parameters _x;
     std::vector<double> _h, _g, _A, _step, _alphas, _scale;  // _scale: natural size of each floating parameter (its error estimate)

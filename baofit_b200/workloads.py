@@ -506,12 +506,13 @@ def make_data(r, mu, z, keep_idx, dvec, cov, cov_is_inverse=False, with_grid=Fal
     return Data(k, grid)
 
 
-def synthetic_cov(xi0, seed=1):
-    """C = A A^T / N + diag(sigma^2), sigma_i = 0.1 |xi_i| + 1e-6."""
+def synthetic_cov(xi0, seed=1, rel=0.1):
+    """C = A A^T / N + diag(sigma^2), sigma_i = rel |xi_i| + 1e-6 (SURVEY.md section 8d: rel = 0.1;
+    rel = 1 gives BOSS-like errors on the BAO scale parameters, a few per cent)."""
     n = len(xi0)
     rng = np.random.Generator(np.random.PCG64(seed))
     A = rng.standard_normal((n, n))
-    sig = 0.1 * np.abs(xi0) + 1e-6
+    sig = rel * np.abs(xi0) + 1e-6
     C = (A @ A.T) / n
     C = C * np.outer(sig, sig) * 0.2 + np.diag(sig * sig)
     return 0.5 * (C + C.T)
@@ -716,7 +717,7 @@ def dr11_auto_fft(root=None, golden=GOLDEN, ngrid=400, spacing=4., seed=1966, nb
     return m, (r, mu, z, keep)
 
 
-def synthetic_dataset(model, coords, predict, seed=1966, cov_seed=1):
+def synthetic_dataset(model, coords, predict, seed=1966, cov_seed=1, rel=0.1):
     """d = model(p0) + L g with the synthetic covariance of SURVEY.md section 8d; ``predict`` maps
     (Model, Data, params[1][npar]) to the prediction [n_data] (the oracle in tests, the CUDA
     library in bench.py)."""
@@ -724,7 +725,7 @@ def synthetic_dataset(model, coords, predict, seed=1966, cov_seed=1):
     n = len(keep)
     probe = make_data(r, mu, z, keep, np.zeros(n), np.eye(n))
     xi0 = np.asarray(predict(model, probe, model.values[None, :])).reshape(n)
-    cov = synthetic_cov(xi0, seed=cov_seed)
+    cov = synthetic_cov(xi0, seed=cov_seed, rel=rel)
     rng = np.random.Generator(np.random.PCG64(seed))
     d = xi0 + np.linalg.cholesky(cov) @ rng.standard_normal(n)
     return make_data(r, mu, z, keep, d, cov), xi0

@@ -185,6 +185,52 @@ def run_scan(rank, world, dev):
             "reference_seconds_per_fit": 1.7, "reference_source": "config/BOSSDR11QSOLyaF_k.ini:11-12 (hardware unspecified)"}
 
 
+def run_scan_k(args, rank, world, dev, ctx):
+    """BASELINE configs[2], config/BOSSDR11LyaF_k.ini: 60 x 35 (alpha_perp, alpha_parallel) scan of the
+    k-space auto-correlation model (N_data = 1515, 11 floating parameters per grid fit), synthetic data
+    vector and covariance (the reference's covariance blob is missing), grid sharded over ranks, one
+    all-gather of the surface."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from baofit_b200 import capi, host_api, shard, workloads as W
+    m, coords = W.dr11_auto_kspace()
+
+    def predict(model, data, params):
+        gm, gd = capi.Model(ctx, model), capi.Data(ctx, data)
+        pred, _ = capi.eval_batch(ctx, gm, gd, params)
+        gm.close(), gd.close()
+        return pred[:, 0]
+
+    d, _ = W.synthetic_dataset(m, coords, predict, rel=1.0)  # BOSS-like errors on the alphas (a few per cent)
+    tree = W.make_golden_tree(os.path.join(tempfile.gettempdir(), "baofit_b200_k_%d" % os.getpid()))
+    W.write_dataset_files(os.path.join(tree, "data", "BOSSDR11LyaF_synthk"), 2500, coords[3], d.keep._arrays[4], d.keep._arrays[5])
+    text = open(os.path.join(tree, "config", "BOSSDR11LyaF_k.ini")).read().replace("data = ../data/BOSSDR11LyaF", "data = ../data/BOSSDR11LyaF_synthk")
+    s = host_api.Session(text, os.path.join(tree, "config"))
+    s.parameter_scan(0, 2)  # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = shard.scan_sharded(s, dev if world > 1 else None)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    ia, ip = s.names.index("BAO alpha-parallel"), s.names.index("BAO alpha-perp")
+    k = int(np.argmin(res["chi2"]))
+    out = {"workload": "BOSSDR11LyaF_k.ini: BaoKSpaceCorrelationModel auto-correlation, N_data=1515, 60x35 grid, %d floating parameters per grid fit; synthetic data+cov" % (int(s.floating.sum()) - 2),
+           "points": int(len(res["chi2"])), "seconds": dt, "points_per_s": len(res["chi2"]) / dt,
+           "failed_fits": int((res["status"] == 2).sum()), "chi2_min": float(res["best_chi2"]), "ndof": int(s.ndata - s.floating.sum()),
+           "grid_minimum": {"alpha_parallel": float(res["points"][k, ia]), "alpha_perp": float(res["points"][k, ip]),
+                            "delta_chi2": float(res["chi2"][k] - res["best_chi2"])},
+           "reference_seconds_per_fit": "25-39 s per fit (config/BOSSDR11LyaF_k.ini header comments, hardware unspecified)"}
+    s.close()
+    return out
+
+
 def run_fft(args, rank, world, dev, ctx):
     """BASELINE configs[4], config/BOSSDR11LyaF_fft.ini: BaoKSpaceFftCorrelationModel on a 400^3 grid of
     4 Mpc/h cells, 1515 data bins, synthetic data vector and covariance (the reference ships neither).
@@ -400,6 +446,7 @@ def main_ours(args, rank, world, local_rank):
     prof = ctx.get_profile()
     ctx.set_profiling(False)
     scan = None if args.no_scan else run_scan(rank, world, dev)
+    scan_k = None if args.no_scan else run_scan_k(args, rank, world, dev, ctx)
     fft = None if args.no_fft else run_fft(args, rank, world, dev, ctx)
     if rank != 0:
         if world > 1:
@@ -458,7 +505,7 @@ def main_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * npar * 8, "d2h_bytes_per_step": B * 12,
                     "api": "bf_chi2_batch (host buffers, pinned)"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "scan": scan, "fft": fft, "kernels": kernels,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "scan": scan, "scan_kspace": scan_k, "fft": fft, "kernels": kernels,
             "chi2_checksum": chi2_check}
     print(json.dumps(line))
     if world > 1:
