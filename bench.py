@@ -44,7 +44,7 @@ WORKLOAD = ("BOSSDR11QSOLyaF_k: BaoKSpaceCorrelationModel cross-correlation, N_g
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=37888,
