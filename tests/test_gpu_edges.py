@@ -1,0 +1,74 @@
+"""Edge cases of the C ABI on the GPU: ragged batch sizes, single vectors, out-of-range bins,
+argument errors. Every call goes through libbaofit_b200.so."""
+import numpy as np
+import pytest
+
+import oracle
+from baofit_b200 import capi, workloads as W
+from baofit_b200.desc import BF_STATUS_FFT_RANGE
+from util import RTOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B", [1, 3, 65, 130])
+def test_ragged_batches_rspace_and_gram(ctx, B):
+    m, d = W.qso_rspace()
+    rng = np.random.Generator(np.random.PCG64(B))
+    params = m.random_batch(B, rng)
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    chi2, st = capi.chi2_batch(ctx, gm, gd, params)
+    ref, rst = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), params, nthreads=8)
+    assert np.array_equal(st, rst) and rel_err(chi2, ref) < RTOL
+    # one probe group per vector (G = 1): gram[f][0][0] is chi2
+    gram, gst = capi.gram_batch(ctx, gm, gd, params, 1)
+    assert np.all(gst == 0) and rel_err(gram[:, 0, 0], ref) < RTOL
+    gm.close(), gd.close()
+
+
+def test_fft_bins_outside_the_kept_plane_are_flagged(ctx):
+    """A dilation that carries bins beyond fft_rmax flags BF_STATUS_FFT_RANGE and yields NaN, like the
+    dilation limits of the k-space model; vectors inside are unaffected. Bit-exact status vs oracle."""
+    m, coords = W.dr11_auto_fft(ngrid=128, spacing=5., nbins=40, fft_rmax=200.)
+    om = oracle.OracleModel(m)
+    d, _ = W.synthetic_dataset(m, coords, lambda mm, dd, p: oracle.predict(om, oracle.OracleData(dd), p[0])[0])
+    params = np.tile(m.values, (5, 1))
+    params[:, m.index("BAO alpha-parallel")] = [1.0, 1.05, 1.3, 0.9, 1.5]
+    params[:, m.index("BAO alpha-perp")] = [1.0, 1.1, 1.0, 1.4, 0.7]
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    chi2, st = capi.chi2_batch(ctx, gm, gd, params)
+    pred, st2 = capi.eval_batch(ctx, gm, gd, params)
+    ref, rst = oracle.chi2_batch(om, oracle.OracleData(d), params, nthreads=8)
+    assert np.array_equal(st, rst) and np.array_equal(st2, rst)
+    assert set(np.unique(rst)) == {0, BF_STATUS_FFT_RANGE}
+    ok = rst == 0
+    assert rel_err(chi2[ok], ref[ok]) < RTOL and np.all(np.isnan(chi2[~ok])) and np.all(np.isnan(pred[:, ~ok]))
+    gm.close(), gd.close()
+
+
+def test_argument_errors_are_reported_not_crashed(ctx):
+    m, d = W.qso_rspace()
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    with pytest.raises(capi.BaofitError):
+        capi.gram_batch(ctx, gm, gd, np.tile(m.values, (200, 1)), 100)  # G > 96
+    truth = np.zeros(gd.n)
+    toys = capi.Toys(ctx, gd, truth, seed=1, first_toy=0, ntoy=3)
+    with pytest.raises(capi.BaofitError):
+        capi.chi2_batch_toys(ctx, gm, gd, m.values[None, :], toys, np.array([3]))  # toy index out of range
+    with pytest.raises(capi.BaofitError):
+        gm.fft_planes(m.values[None, :], 2.3)  # not an FFT model
+    # multipole data refuse cross-correlation models (the reference's multipole overload applies no velocity shift)
+    _, dm = W.demo_multi(lmax=4)
+    gdm = capi.Data(ctx, dm)
+    with pytest.raises(capi.BaofitError):
+        capi.chi2_batch(ctx, gm, gdm, m.values[None, :])
+    toys.close(), gm.close(), gd.close(), gdm.close()
+
+
+def test_fft_model_rejects_bad_grids(ctx):
+    m, _ = W.dr11_auto_fft(ngrid=4, spacing=4.)
+    with pytest.raises(capi.BaofitError):
+        capi.Model(ctx, m)
+    m, _ = W.dr11_auto_fft(ngrid=64, spacing=-1.)
+    with pytest.raises(capi.BaofitError):
+        capi.Model(ctx, m)
