@@ -237,6 +237,9 @@ public:
     // device-resident data (kept bins, d, Cholesky factors); gridFor: model whose distortion
     // matrix needs the full grid (may be null)
     bf_data *deviceData(bool withGrid);
+    // all bins with data (before final cuts), ascending index; dense covariance / inverse over them
+    std::vector<int> binsWithData() const;
+    std::vector<double> denseOverBinsWithData() const;
     std::vector<double> dataVector() const;           // kept bins, iteration order
     std::vector<double> covarianceMatrix() const;     // dense kept x kept (cov or icov as loaded)
     bool isInverse() const { return _isInverse; }
@@ -315,6 +318,11 @@ private:
     mutable double _rLast = 0, _muLast = 0, _zLast = 0;
     void _setIndex(int index) const;
 };
+
+// Inverse-covariance weighted combination of congruent observations, what likely::BinnedDataResampler::combined
+// returns for the plates added with CorrelationAnalyzer::addData (baofit/CorrelationAnalyzer.cc:42-75,
+// src/baofit.cc:526-583): C^-1 = sum_k C_k^-1,  C^-1 d = sum_k C_k^-1 d_k. `into` receives data + covariance.
+void combineCorrelationData(std::vector<AbsCorrelationDataPtr> const &observations, AbsCorrelationData &into);
 
 // "<name>.data" / ".cov" / ".icov" text loaders (AbsCorrelationData.cc:156-277); ".cov.gz" is not
 // handled here (tests decompress fixtures first).

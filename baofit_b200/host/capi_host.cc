@@ -103,6 +103,13 @@ extern "C" int bfh_kept_coordinates(const bfh_session *s, double *r, double *mu,
     BFH_CATCH
 }
 
+extern "C" int bfh_data_vector(const bfh_session *s, double *data, double *cov) {
+    BFH_TRY
+    if (data) { std::vector<double> d = s->data->dataVector(); std::copy(d.begin(), d.end(), data); }
+    if (cov) { std::vector<double> c = s->data->covarianceMatrix(); std::copy(c.begin(), c.end(), cov); }
+    BFH_CATCH
+}
+
 extern "C" int bfh_set_distortion_matrix(bfh_session *s, const double *dense, int order) {
     BFH_TRY
     auto *km = dynamic_cast<BaoKSpaceCorrelationModel *>(s->model.get());

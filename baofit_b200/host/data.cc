@@ -6,6 +6,7 @@
 #include <sstream>
 
 #include "baofit_host.h"
+#include "../csrc/host_setup.h"
 
 namespace baofit {
 
@@ -145,6 +146,25 @@ void AbsCorrelationData::gridCoordinates(std::vector<double> &r, std::vector<dou
     for (int i = 0; i < n; ++i) { r[i] = getRadius(i); mu[i] = _type == Coordinate ? getCosAngle(i) : (double)getMultipole(i); z[i] = getRedshift(i); }
 }
 
+std::vector<int> AbsCorrelationData::binsWithData() const {
+    std::vector<int> b;
+    for (auto const &kv : _values) b.push_back(kv.first);
+    return b;
+}
+
+std::vector<double> AbsCorrelationData::denseOverBinsWithData() const {
+    std::vector<int> bins = binsWithData();
+    int n = (int)bins.size();
+    std::map<int, int> pos;
+    for (int i = 0; i < n; ++i) pos[bins[i]] = i;
+    std::vector<double> c((size_t)n * n, 0.0);
+    for (auto const &kv : _cov) {
+        int a = pos.at(kv.first.first), b = pos.at(kv.first.second);
+        c[(size_t)a * n + b] = c[(size_t)b * n + a] = kv.second;
+    }
+    return c;
+}
+
 std::vector<double> AbsCorrelationData::dataVector() const {
     std::vector<double> d;
     for (int idx : _kept) d.push_back(_values.at(idx));
@@ -229,6 +249,48 @@ double ComovingCorrelationData::getRedshift(int index) const {
     double c[3];
     _grid.getBinCenters(index, c);
     return c[2];
+}
+
+namespace {
+// inverse of a dense symmetric positive definite matrix through its Cholesky factor
+std::vector<double> spdInverse(int n, std::vector<double> a, const char *what) {
+    if (!bf::cholesky_lower(n, a.data())) throw RuntimeError(std::string("combineCorrelationData: ") + what + " is not positive definite");
+    std::vector<double> li((size_t)n * n, 0.0), out((size_t)n * n, 0.0);
+    bf::invert_lower(n, a.data(), li.data());
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = 0;
+            for (int k = i; k < n; ++k) s += li[(size_t)k * n + i] * li[(size_t)k * n + j];  // (L^-T L^-1)_ij
+            out[(size_t)i * n + j] = out[(size_t)j * n + i] = s;
+        }
+    return out;
+}
+}  // namespace
+
+void combineCorrelationData(std::vector<AbsCorrelationDataPtr> const &observations, AbsCorrelationData &into) {
+    if (observations.empty()) throw RuntimeError("combineCorrelationData: no observations.");
+    std::vector<int> bins = observations[0]->binsWithData();
+    const int n = (int)bins.size();
+    std::vector<double> icovSum((size_t)n * n, 0.0), icovData(n, 0.0);
+    for (auto const &obs : observations) {
+        if (obs->binsWithData() != bins) throw RuntimeError("combineCorrelationData: observations are not congruent.");
+        std::vector<double> m = obs->denseOverBinsWithData();
+        std::vector<double> icov = obs->isInverse() ? m : spdInverse(n, m, "a covariance");
+        for (size_t k = 0; k < icov.size(); ++k) icovSum[k] += icov[k];
+        for (int i = 0; i < n; ++i) {
+            double s = 0;
+            for (int j = 0; j < n; ++j) s += icov[(size_t)i * n + j] * obs->getData(bins[j]);
+            icovData[i] += s;
+        }
+    }
+    std::vector<double> cov = spdInverse(n, icovSum, "the summed inverse covariance");
+    for (int i = 0; i < n; ++i) {
+        double s = 0;
+        for (int j = 0; j < n; ++j) s += cov[(size_t)i * n + j] * icovData[j];
+        into.setData(bins[i], s);
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) into.setCovariance(bins[i], bins[j], cov[(size_t)i * n + j]);
 }
 
 void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov) {

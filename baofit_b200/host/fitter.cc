@@ -507,25 +507,45 @@ AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDi
 AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir) {
     std::string fmt = opt.str("data-format");
     BinnedGrid grid = createCorrelationGrid(opt.str("axis1-bins"), opt.str("axis2-bins"), opt.str("axis3-bins"));
-    AbsCorrelationDataPtr data;
-    if (fmt == "comoving-cartesian") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::CartesianCoordinates));
-    else if (fmt == "comoving-polar") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::PolarCoordinates));
-    else if (fmt == "comoving-multipole") data.reset(new ComovingCorrelationData(grid, ComovingCorrelationData::MultipoleCoordinates));
-    else if (fmt == "quasar") {
-        // src/baofit.cc:409-414,495-500
-        AbsHomogeneousUniversePtr cosmology(new LambdaCdmRadiationUniverse(opt.num("omega-matter", 0.27), 0, opt.num("hubble-constant", 0.7)));
-        if (opt.has("omega-radiation")) cosmology->setOmegaRadiation(opt.num("omega-radiation", 0));  // not a reference option
-        data.reset(new QuasarCorrelationData(grid, opt.num("ll-min", 0), opt.num("ll-max", 1), opt.num("sep-min", 0),
-                                             opt.num("sep-max", 200), false, cosmology));
-    } else
+    auto prototype = [&]() -> AbsCorrelationDataPtr {
+        if (fmt == "comoving-cartesian") return AbsCorrelationDataPtr(new ComovingCorrelationData(grid, ComovingCorrelationData::CartesianCoordinates));
+        if (fmt == "comoving-polar") return AbsCorrelationDataPtr(new ComovingCorrelationData(grid, ComovingCorrelationData::PolarCoordinates));
+        if (fmt == "comoving-multipole") return AbsCorrelationDataPtr(new ComovingCorrelationData(grid, ComovingCorrelationData::MultipoleCoordinates));
+        if (fmt == "quasar") {
+            // src/baofit.cc:409-414,495-500
+            AbsHomogeneousUniversePtr cosmology(new LambdaCdmRadiationUniverse(opt.num("omega-matter", 0.27), 0, opt.num("hubble-constant", 0.7)));
+            if (opt.has("omega-radiation")) cosmology->setOmegaRadiation(opt.num("omega-radiation", 0));  // not a reference option
+            return AbsCorrelationDataPtr(new QuasarCorrelationData(grid, opt.num("ll-min", 0), opt.num("ll-max", 1), opt.num("sep-min", 0),
+                                                                   opt.num("sep-max", 200), false, cosmology));
+        }
         throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar, comoving-multipole, quasar)");
+    };
+    AbsCorrelationDataPtr data = prototype();
     // src/baofit.cc:510 with the defaults of :216-247
     double rVetoWidth = opt.num("rveto-width", 0), rVetoCenter = opt.num("rveto-center", 114);
     data->setFinalCuts(opt.num("rmin", 0), opt.num("rmax", 200), rVetoCenter - 0.5 * rVetoWidth, rVetoCenter + 0.5 * rVetoWidth,
                        opt.num("mu-min", -1), opt.num("mu-max", 1), opt.num("rperp-min", 0), opt.num("rperp-max", 200),
                        opt.num("rpar-min", -200), opt.num("rpar-max", 200), (int)opt.num("lmin", 0), (int)opt.num("lmax", 2),
                        opt.num("z-min", 0), opt.num("z-max", 10));
-    loadCorrelationData(resolve(baseDir, opt.str("data")), *data, opt.flag("load-icov"));
+    if (!opt.str("data").empty()) {
+        loadCorrelationData(resolve(baseDir, opt.str("data")), *data, opt.flag("load-icov"));
+    } else {
+        // individual observations named by plateroot + platelist (src/baofit.cc:531-583), combined with
+        // inverse-covariance weights like likely::BinnedDataResampler::combined
+        std::string root = resolve(baseDir, opt.str("plateroot")), listName = root + opt.str("platelist");
+        std::ifstream list(listName.c_str());
+        if (!list.good()) throw RuntimeError("Unable to open platelist file " + listName);
+        std::vector<AbsCorrelationDataPtr> plates;
+        std::string plateName;
+        int maxPlates = (int)opt.num("max-plates", 0);
+        while (list >> plateName) {
+            AbsCorrelationDataPtr plate = prototype();
+            loadCorrelationData(root + plateName, *plate, opt.flag("load-icov"));
+            plates.push_back(plate);
+            if (maxPlates > 0 && (int)plates.size() == maxPlates) break;
+        }
+        combineCorrelationData(plates, *data);
+    }
     data->finalize();
     return data;
 }

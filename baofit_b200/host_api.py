@@ -10,7 +10,7 @@ BATCH_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_doubl
 RESID_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)
 
 HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
-                "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
+                "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize"]
 
@@ -29,6 +29,7 @@ def lib():
         L.bfh_param_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_kept_indices.argtypes = [C.c_void_p, C.c_void_p]
         L.bfh_kept_coordinates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bfh_data_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_set_distortion_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.bfh_evaluate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.bfh_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -97,6 +98,16 @@ class Session:
         r, mu, z = np.zeros(self.ndata), np.zeros(self.ndata), np.zeros(self.ndata)
         _check(lib().bfh_kept_coordinates(self.h, _p(r), _p(mu), _p(z)))
         return r, mu, z
+
+    def data_vector(self):
+        d = np.zeros(self.ndata)
+        _check(lib().bfh_data_vector(self.h, _p(d), None))
+        return d
+
+    def covariance(self):
+        c = np.zeros((self.ndata, self.ndata))
+        _check(lib().bfh_data_vector(self.h, None, _p(c)))
+        return c
 
     def set_distortion_matrix(self, dense):
         d = np.ascontiguousarray(dense, dtype=np.float64)

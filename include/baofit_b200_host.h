@@ -38,6 +38,8 @@ int bfh_kept_indices(const bfh_session *s, int *indices);
 /* (r, mu, z) of the kept bins in iteration order: AbsCorrelationData::getRadius / getCosAngle /
  * getRedshift (ComovingCorrelationData.cc:46-84, QuasarCorrelationData.cc:139-185) */
 int bfh_kept_coordinates(const bfh_session *s, double *r, double *mu, double *z);
+/* data vector [ndata] and dense covariance (or inverse covariance, as loaded) [ndata*ndata] of the kept bins */
+int bfh_data_vector(const bfh_session *s, double *data, double *cov);
 /* replaces the model's distortion matrix by an in-memory dense one (order x order, row-major)
  * and forwards the grid coordinates of the data (AbsCorrelationModel::setCoordinates) */
 int bfh_set_distortion_matrix(bfh_session *s, const double *dense, int order);

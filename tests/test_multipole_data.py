@@ -74,3 +74,35 @@ def test_gpu_multipole_demo_fit(built, golden_tree):
     for name, v in {"beta": 1.4, "BAO alpha-parallel": 1.0, "BAO alpha-perp": 1.0}.items():
         i = s.names.index(name)
         assert abs(r["values"][i] - v) < 4 * r["errors"][i], (name, r["values"][i], r["errors"][i])
+
+
+def test_host_platelist_combination_is_inverse_covariance_weighted(built, golden_tree):
+    """plateroot + platelist (src/baofit.cc:531-583): congruent observations are combined like
+    likely::BinnedDataResampler::combined does, C^-1 = sum C_k^-1, C^-1 d = sum C_k^-1 d_k; observations
+    with different bins are refused."""
+    base = os.path.join(golden_tree, "config")
+    m, d0 = W.demo_multi(lmax=4)
+    keep, dv, cov = d0.keep._arrays[3], d0.keep._arrays[4], d0.keep._arrays[5]
+    rng = np.random.Generator(np.random.PCG64(12))
+    obs = []
+    for k in range(3):
+        ck = cov * (1.0 + 0.5 * k)
+        dk = dv + np.linalg.cholesky(ck) @ rng.standard_normal(len(dv))
+        W.write_dataset_files(os.path.join(golden_tree, "data", "obs_%d" % k), 87, keep, dk, ck)
+        obs.append((dk, ck))
+    with open(os.path.join(golden_tree, "data", "obs.list"), "w") as f:
+        f.write("obs_0\nobs_1\nobs_2\n")
+    text = open(os.path.join(base, "multi_to_bao.ini")).read() + "\nplateroot = ../data/\nplatelist = obs.list\nlmax = 4\n"
+    s = H.Session(text, base)
+    assert s.ndata == 87
+    icov = [np.linalg.inv(c) for _, c in obs]
+    csum = np.linalg.inv(sum(icov))
+    dcomb = csum @ sum(ic @ dk for ic, (dk, _) in zip(icov, obs))
+    assert np.max(np.abs(s.data_vector() - dcomb)) < 1e-11 * np.max(np.abs(dcomb))
+    assert np.max(np.abs(s.covariance() - csum)) < 1e-10 * np.max(np.abs(csum))
+    assert H.Session(text + "max-plates = 1\n", base).data_vector() == pytest.approx(obs[0][0], rel=1e-12)
+    # demo/multi_0, multi_1, multi_2 carry different multipole sets: not congruent
+    with open(os.path.join(golden_tree, "data", "bad.list"), "w") as f:
+        f.write("../demo/multi_0\n../demo/multi_1\n")
+    with pytest.raises(H.HostError):
+        H.Session(text.replace("obs.list", "bad.list"), base)
