@@ -225,6 +225,7 @@ public:
     BinnedGrid const &getGrid() const { return _grid; }
     std::vector<int> const &keptIndices() const { return _kept; }
     double getData(int index) const;
+    double getCovarianceElement(int i, int j) const;  // as loaded (covariance or inverse); 0 if absent
     // AbsCorrelationData.cc:34-54
     void setFinalCuts(double rMin, double rMax, double rVetoMin, double rVetoMax, double muMin, double muMax,
                       double rperpMin, double rperpMax, double rparMin, double rparMax, int lMin, int lMax,
@@ -395,11 +396,20 @@ public:
     static void writeScan(std::string const &path, ScanResult const &scan);
     // CorrelationAnalyzer.cc:337-373 + 452-532: toy MC samples [first, first+count) drawn on the GPU
     // from the truth prediction + L g, each refitted; returns best-fit vectors and 2*fval
+    // CorrelationAnalyzer.cc:607-676: one line per kept bin "index c1 c2 c3 r mu|ell z predicted data error
+    // [d pred / d p_j ...]"; the gradients are central differences over 0.1 * error_j, all 1 + 2 npar
+    // predictions in one batch on the GPU.
+    void dumpResiduals(std::ostream &out, likely::FunctionMinimumPtr fmin, std::string const &script = "", bool dumpGradients = false) const;
+    // CorrelationAnalyzer.cc:678-716: "r mono quad hexa" at ndump radii between rmin and rmax at redshift zdump
+    // (< 0: z of the first kept bin), from AbsCorrelationModel::evaluate(r, multipole, z, ...).
+    void dumpModel(std::ostream &out, likely::FitParameters parameters, int ndump, double zdump = -1, std::string const &script = "",
+                   bool oneLine = false) const;
     void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
                          std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "") const;
 
 private:
     std::string _method;
+    double _rmin, _rmax;
     int _covSampleSize;
     bool _verbose;
     AbsCorrelationDataPtr _data;

@@ -1,6 +1,8 @@
 // C entry points over the host-side classes (include/baofit_b200_host.h).
 #include <cmath>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 #include <string>
 
 #include "../../include/baofit_b200_host.h"
@@ -157,6 +159,32 @@ extern "C" int bfh_fit(bfh_session *s, const char *config, double *values, doubl
     if (status) *status = (int)fm->status;
     if (nevaluations) *nevaluations = fm->nEvaluations;
     if (covariance) std::copy(fm->covariance.begin(), fm->covariance.end(), covariance);
+    BFH_CATCH
+}
+
+extern "C" int bfh_dump_residuals(bfh_session *s, const double *values, const double *errors, const char *path, int gradients) {
+    BFH_TRY
+    likely::FunctionMinimumPtr fm(new likely::FunctionMinimum());
+    fm->parameters = s->model->getFitParameters();
+    for (size_t i = 0; i < fm->parameters.size(); ++i) {
+        fm->parameters[i].value = values[i];
+        if (errors) fm->parameters[i].error = errors[i];
+    }
+    std::ofstream out(path);
+    if (!out.good()) throw RuntimeError(std::string("unable to open ") + path);
+    s->analyzer->dumpResiduals(out, fm, "", gradients != 0);
+    BFH_CATCH
+}
+
+extern "C" int bfh_dump_model(bfh_session *s, const double *values, int ndump, double zdump, double *multipoles) {
+    BFH_TRY
+    likely::FitParameters p = s->model->getFitParameters();
+    for (size_t i = 0; i < p.size(); ++i) p[i].value = values[i];
+    std::ostringstream os;
+    s->analyzer->dumpModel(os, p, ndump, zdump, "", true);
+    std::istringstream is(os.str());
+    for (int k = 0; k < 3 * ndump; ++k)
+        if (!(is >> multipoles[k])) throw RuntimeError("dumpModel produced too few values");
     BFH_CATCH
 }
 

@@ -80,6 +80,11 @@ double AbsCorrelationData::getData(int index) const {
     return it->second;
 }
 
+double AbsCorrelationData::getCovarianceElement(int i, int j) const {
+    auto it = _cov.find(std::make_pair(std::min(i, j), std::max(i, j)));
+    return it == _cov.end() ? 0.0 : it->second;
+}
+
 void AbsCorrelationData::setCovariance(int i, int j, double value) {
     if (_haveCov && _isInverse) throw RuntimeError("AbsCorrelationData: cannot mix covariance and inverse covariance.");
     _haveCov = true;

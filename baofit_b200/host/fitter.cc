@@ -207,10 +207,7 @@ likely::FunctionMinimumPtr CorrelationFitter::fit(std::string const &methodName,
 // CorrelationAnalyzer
 // ------------------------------------------------------------------------------------------
 CorrelationAnalyzer::CorrelationAnalyzer(std::string const &method, double rmin, double rmax, int covSampleSize, bool verbose)
-    : _method(method), _covSampleSize(covSampleSize), _verbose(verbose) {
-    (void)rmin;
-    (void)rmax;
-}
+    : _method(method), _rmin(rmin), _rmax(rmax), _covSampleSize(covSampleSize), _verbose(verbose) {}
 
 likely::FunctionMinimumPtr CorrelationAnalyzer::fitSample(AbsCorrelationDataPtr sample, std::string const &config) const {
     CorrelationFitter fitter(sample, _model, _covSampleSize);
@@ -303,6 +300,94 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
         out.status.push_back((int)fm->status);
     }
     return out;
+}
+
+void CorrelationAnalyzer::dumpResiduals(std::ostream &out, likely::FunctionMinimumPtr fmin, std::string const &script,
+                                        bool dumpGradients) const {
+    if (!_data || !_model) throw RuntimeError("CorrelationAnalyzer::dumpResiduals: no observations have been added.");
+    CorrelationFitter fitter(_data, _model, _covSampleSize);
+    likely::FitParameters parameters(fmin->parameters);
+    if (!script.empty()) likely::modifyFitParameters(parameters, script);
+    const int npar = (int)parameters.size();
+    likely::Parameters values, errors;
+    for (auto const &p : parameters) { values.push_back(p.value); errors.push_back(p.floating ? p.error : 0.0); }
+    // one batch: the prediction itself, then +-0.5 dpar for every parameter with an error (:656-670)
+    std::vector<likely::Parameters> points(1, values);
+    std::vector<int> slot(npar, -1);
+    if (dumpGradients)
+        for (int j = 0; j < npar; ++j) {
+            double dpar = 0.1 * errors[j];
+            if (!(dpar > 0)) continue;
+            slot[j] = (int)points.size();
+            likely::Parameters hi(values), lo(values);
+            hi[j] = values[j] + 0.5 * dpar;
+            lo[j] = values[j] - 0.5 * dpar;
+            points.push_back(hi);
+            points.push_back(lo);
+        }
+    std::vector<double> pred;
+    fitter.predictBatch(points, pred);
+    const int B = (int)points.size();
+    std::vector<int> const &kept = _data->keptIndices();
+    const bool coord = _data->getTransverseBinningType() == AbsCorrelationData::Coordinate;
+    char buf[64];
+    auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.12g", v); return std::string(buf); };
+    for (size_t i = 0; i < kept.size(); ++i) {
+        const int index = kept[i];
+        double c[3];
+        _data->getGrid().getBinCenters(index, c);
+        out << index << ' ' << num(c[0]) << ' ' << num(c[1]) << ' ' << num(c[2]) << ' ' << num(_data->getRadius(index)) << ' ';
+        if (coord) out << num(_data->getCosAngle(index));
+        else out << _data->getMultipole(index);
+        double cii = _data->getCovarianceElement(index, index);
+        double error = _data->isInverse() ? 0.0 : std::sqrt(std::max(cii, 0.0));
+        out << ' ' << num(_data->getRedshift(index)) << ' ' << num(pred[i * B]) << ' ' << num(_data->getData(index)) << ' ' << num(error);
+        if (dumpGradients)
+            for (int j = 0; j < npar; ++j) {
+                double g = 0;
+                if (slot[j] >= 0) g = (pred[i * B + slot[j]] - pred[i * B + slot[j] + 1]) / (0.1 * errors[j]);
+                out << ' ' << num(g);
+            }
+        out << std::endl;
+    }
+}
+
+void CorrelationAnalyzer::dumpModel(std::ostream &out, likely::FitParameters parameters, int ndump, double zdump,
+                                    std::string const &script, bool oneLine) const {
+    if (ndump <= 1) throw RuntimeError("CorrelationAnalyzer::dump: expected ndump > 1.");
+    if (!_model) throw RuntimeError("CorrelationAnalyzer::dumpModel: no model.");
+    if (zdump < 0) {
+        if (!_data) throw RuntimeError("CorrelationAnalyzer::dumpModel: no data to take the redshift from.");
+        zdump = _data->getRedshift(_data->keptIndices().at(0));
+    }
+    if (!script.empty()) likely::modifyFitParameters(parameters, script);
+    likely::Parameters values;
+    for (auto const &p : parameters) values.push_back(p.value);
+    // a multipole-binned point set (r_k, ell = 0,2,4, zdump) evaluated in one batch through the C ABI
+    const int n = 3 * ndump;
+    const double dr = (_rmax - _rmin) / (ndump - 1);
+    std::vector<double> r(n), ell(n), z(n, zdump), zero(n, 0.0), eye((size_t)n * n, 0.0), pred(n);
+    std::vector<int> idx(n);
+    for (int k = 0; k < ndump; ++k)
+        for (int l = 0; l < 3; ++l) { r[3 * k + l] = _rmin + dr * k; ell[3 * k + l] = 2 * l; idx[3 * k + l] = -1; }
+    for (int i = 0; i < n; ++i) eye[(size_t)i * n + i] = 1.0;
+    bf_data_desc dd;
+    std::memset(&dd, 0, sizeof(dd));
+    dd.n_data = n; dd.r = r.data(); dd.mu = ell.data(); dd.z = z.data(); dd.index = idx.data(); dd.data = zero.data();
+    dd.cov = eye.data(); dd.binning_type = BF_BINNING_MULTIPOLE;
+    bf_data *pts = nullptr;
+    check(bf_data_create(deviceContext(), &dd, &pts), "bf_data_create");
+    int status = 0;
+    int rc = bf_eval_batch(deviceContext(), _model->deviceModel(), pts, values.data(), 1, pred.data(), 1, &status);
+    bf_data_destroy(pts);
+    check(rc, "bf_eval_batch");
+    char buf[64];
+    auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.17g", v); return std::string(buf); };
+    for (int k = 0; k < ndump; ++k) {
+        if (!oneLine) out << num(_rmin + dr * k);
+        out << ' ' << num(pred[3 * k]) << ' ' << num(pred[3 * k + 1]) << ' ' << num(pred[3 * k + 2]);
+        if (!oneLine) out << std::endl;
+    }
 }
 
 void CorrelationAnalyzer::writeScan(std::string const &path, ScanResult const &scan) {

@@ -12,7 +12,7 @@ RESID_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_doubl
 HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
-                "bfh_lm_minimize"]
+                "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model"]
 
 
 def lib():
@@ -40,6 +40,8 @@ def lib():
         L.bfh_toymc.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, BATCH_FN, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.bfh_dump_residuals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.bfh_dump_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.bfh_lm_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, RESID_FN,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]
@@ -123,6 +125,18 @@ class Session:
         p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, self.npar)
         out = np.zeros((self.ndata, p.shape[0]))
         _check(lib().bfh_predict_batch(self.h, _p(p), p.shape[0], _p(out)))
+        return out
+
+    def dump_residuals(self, values, errors, path, gradients=False):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        e = np.ascontiguousarray(errors, dtype=np.float64)
+        _check(lib().bfh_dump_residuals(self.h, _p(v), _p(e), path.encode(), 1 if gradients else 0))
+        return np.loadtxt(path, ndmin=2)
+
+    def dump_model(self, values, ndump, zdump=-1.0):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = np.zeros((ndump, 3))
+        _check(lib().bfh_dump_model(self.h, _p(v), ndump, float(zdump), _p(out)))
         return out
 
     def fit(self, config=""):

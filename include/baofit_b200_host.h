@@ -62,6 +62,12 @@ int bfh_parameter_scan(bfh_session *s, long first, long count, double *chi2, dou
 int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
               int *status);
 
+/* CorrelationAnalyzer::dumpResiduals (CorrelationAnalyzer.cc:607-676) at the given parameter values / errors
+ * into the text file `path`; CorrelationAnalyzer::dumpModel (:678-716): multipoles[ndump*3] = mono, quad, hexa
+ * at ndump radii between the rmin and rmax options, at redshift zdump (< 0: first kept bin). */
+int bfh_dump_residuals(bfh_session *s, const double *values, const double *errors, const char *path, int gradients);
+int bfh_dump_model(bfh_session *s, const double *values, int ndump, double zdump, double *multipoles);
+
 /* The minimiser on its own (likely::FitModel::findMinimum "mn2::vmetric" replacement) over a
  * caller-supplied batched objective: fn(points[B*npar], B, f[B], user). Used to run the identical
  * minimiser code over the CPU oracle in the parity tests, and for host-only tests. */

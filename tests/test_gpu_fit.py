@@ -99,3 +99,33 @@ def test_toymc_is_shard_independent_and_unbiased(built, golden_tree):
     ib = s.names.index("beta")
     assert abs(a["fitted"][:, ib].mean() - 1.4) < 0.05
     assert 600 < a["chi2"].mean() < 1000  # ~ N_data - n_float
+
+
+def test_dump_residuals_and_model_against_oracle(built, golden_tree, tmp_path):
+    """CorrelationAnalyzer::dumpResiduals (predictions + central-difference gradients, one GPU batch)
+    and dumpModel (monopole / quadrupole / hexadecapole of the model) against the oracle; the
+    multipoles of the demo model reproduce demo/multi.theory."""
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF.ini")
+    s = H.Session(text, base)
+    m, d = W.qso_rspace()
+    om, od = oracle.OracleModel(m), oracle.OracleData(d)
+    errors = np.where(s.floating, s.errors, 0.0)
+    tab = s.dump_residuals(s.values, errors, str(tmp_path / "resid.dat"), gradients=True)
+    assert tab.shape == (s.ndata, 10 + s.npar)
+    assert np.array_equal(tab[:, 0].astype(int), s.kept_indices())
+    pred, _ = oracle.predict(om, od, s.values)
+    assert np.max(np.abs(tab[:, 7] - pred)) < 2e-12 * np.max(np.abs(pred))  # 12 printed digits
+    assert np.allclose(tab[:, 8], d.keep._arrays[4], rtol=1e-11) and np.allclose(tab[:, 9], np.sqrt(np.diag(d.keep._arrays[5])), rtol=1e-11)
+    for j in np.nonzero(s.floating)[0][:6]:
+        hi, lo = s.values.copy(), s.values.copy()
+        hi[j] += 0.05 * errors[j]
+        lo[j] -= 0.05 * errors[j]
+        g = (oracle.predict(om, od, hi)[0] - oracle.predict(om, od, lo)[0]) / (0.1 * errors[j])
+        assert np.max(np.abs(tab[:, 10 + j] - g)) < 1e-6 * np.max(np.abs(g)) + 1e-14
+    assert np.all(tab[:, 10 + np.nonzero(~s.floating)[0]] == 0)
+    # dumpModel on the demo model: the 29 radii of demo/multi.theory are {40:180}*29 = rmin..rmax of the ini
+    text2, base2 = ini(golden_tree, "rmu_to_bao.ini")
+    s2 = H.Session(text2.replace("rmax = 200", "rmax = 180"), base2)
+    mp = s2.dump_model(s2.values, 29, 2.25)
+    mt = np.loadtxt(os.path.join(golden_tree, "demo", "multi.theory"))[:, 1].reshape(29, 3)
+    assert np.max(np.abs(mp - mt)) < 1e-14
