@@ -381,12 +381,31 @@ __global__ void __launch_bounds__(256, kPart == 1 ? 3 : 2) kspace_fast_eval_kern
 // broadband in this pass": out[i][b] += sum_row wy_row(b,i) * dot(n(b), MX[i][row][:]).
 // The normalisation factors n(b) are per-vector constants, so each row is a 12-term dot product;
 // two bins are processed per iteration to double the loads in flight (this pass is latency bound).
+// The four template rows a (vector, bin) pair needs depend on the vector only through its velocity
+// shift, which moves r_par by at most a cell or two: for every bin the rows of all 256 vectors of
+// the CTA lie in one window of kMetalWin consecutive rows of MX[i], 768 contiguous bytes. The
+// window of bin i + kMetalStages is fetched by one TMA bulk copy (cp.async.bulk + mbarrier) while
+// bin i is being computed, so the pass reads shared memory instead of waiting on L1/L2 (it was
+// long-scoreboard bound). Bins whose window would wrap or exceed kMetalWin rows take the global path.
+constexpr int kMetalWin = 8, kMetalStages = 8;
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256, 2) metal_add_kernel(FastArgs a) {
+    __shared__ __align__(128) double win[kMetalStages][kMetalWin * NT];
+    __shared__ __align__(8) unsigned long long full_bar[kMetalStages], empty_bar[kMetalStages];
+    __shared__ double red_min[8], red_max[8];
+    __shared__ int win_lo[kMetalStages];
     const DevModel &m = a.m;
     const PointTab &pt = a.pt;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    const bool active = b < a.B;
+    if (!active) b = a.B - 1;  // keep the whole CTA alive for the barriers; results are not stored
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ldb = a.ldb;
     const double *pT = a.pT + b;
     const double *S = a.S + b;
@@ -403,9 +422,62 @@ __global__ void __launch_bounds__(256, 2) metal_add_kernel(FastArgs a) {
     for (int c = 0; c < NT / 3; ++c) cross_metal_norms(m, pT, ldb, c, eb, ebeta, n[3 * c], n[3 * c + 1], n[3 * c + 2]);
     const int ny = pt.mx_ny;
     const int i0 = blockIdx.y * a.pts_per_block, i1 = min(min(i0 + a.pts_per_block, pt.npts_pad), pt.npts);
-    auto one = [&](int i, double &wsum, bool &zero) {
+
+    // range of the velocity shift over the CTA
+    double lo = dpi, hi = dpi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { red_min[warp] = lo; red_max[warp] = hi; }
+    if (tid == 0)
+        for (int st = 0; st < kMetalStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 8); }
+    __syncthreads();
+    double dpi_min = red_min[0], dpi_max = red_max[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { dpi_min = fmin(dpi_min, red_min[w]); dpi_max = fmax(dpi_max, red_max[w]); }
+
+    // first row of the window of bin i, or -1 if the bin cannot be staged
+    auto window = [&](int i) {
+        const double r0 = pt.rpar0[i];
+        const double ya = fmin(fmax(r0 + dpi_min, m.metal_y0), m.metal_ymax), yb = fmin(fmax(r0 + dpi_max, m.metal_y0), m.metal_ymax);
+        const int ia = (int)floor((ya - m.metal_y0) * m.metal_inv_dy), ib = (int)floor((yb - m.metal_y0) * m.metal_inv_dy);
+        const int first = ia - 1, last = ib + 2;
+        if (NT % 2 != 0 || first < 0 || last > ny - 1 || last - first + 1 > kMetalWin) return -1;  // odd NT: rows are not 16-byte aligned
+        return min(first, ny - kMetalWin);
+    };
+    auto issue = [&](int i) {  // thread 0
+        const int st = (i - i0) % kMetalStages, w = window(i);
+        win_lo[st] = w;
+        if (w >= 0) {
+            mbar_expect_tx(&full_bar[st], (unsigned)(kMetalWin * NT * sizeof(double)));
+            tma_bulk_g2s(&win[st][0], pt.mx + ((size_t)i * ny + w) * NT, (unsigned)(kMetalWin * NT * sizeof(double)), &full_bar[st]);
+        } else {
+            // nothing to copy: complete the phase right away so that consumers fall through
+            mbar_expect_tx(&full_bar[st], 0);
+        }
+    };
+    if (tid == 0)
+        for (int i = i0; i < i1 && i < i0 + kMetalStages; ++i) issue(i);
+    __syncthreads();  // win_lo of the first stages is visible
+
+    double x_next = (active && i0 < i1) ? a.out[(size_t)i0 * a.ldo + b] : 0.0;
+    for (int i = i0; i < i1; ++i) {
+        const int k = i - i0, st = k % kMetalStages;
+        // the read-modify-write of the xi panel: the value of the next bin is fetched a whole iteration ahead
+        const double x_cur = x_next;
+        if (active && i + 1 < i1) x_next = a.out[(size_t)(i + 1) * a.ldo + b];
+        if (tid == 0 && k >= 1 && i - 1 + kMetalStages < i1) {
+            // refill the stage of bin i-1 once all eight warps have released it
+            mbar_wait(&empty_bar[(k - 1) % kMetalStages], ((k - 1) / kMetalStages) & 1);
+            issue(i - 1 + kMetalStages);
+        }
+        __syncwarp();
+        mbar_wait(&full_bar[st], (k / kMetalStages) & 1);
+        const int wlo = win_lo[st];
         const double rperp = pt.rperp0[i], rpar = pt.rpar0[i] + dpi;
-        zero = false;
+        bool zero = false;
         if (a.mode == 1) {  // same range zeroing as the cosmological pass (BaoKSpaceCorrelationModel.cc:466-469,485-488)
             const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
             const double rprime = r2 * rsqrt(r2);
@@ -422,44 +494,42 @@ __global__ void __launch_bounds__(256, 2) metal_add_kernel(FastArgs a) {
         double wy[4];
         catmull_weights(fy - fly, wy);
         const int iy = (int)fly;
-        const double *mxp = pt.mx + (size_t)i * ny * NT;
-        wsum = 0.0;
+        double wsum = 0.0;
+        if (wlo >= 0) {
+            const double *base = &win[st][0] + (iy - 1 - wlo) * NT;
 #pragma unroll
-        for (int jy = 0; jy < 4; ++jy) {
-            const double *row = mxp + (size_t)wrap_index(iy - 1 + jy, ny) * NT;
-            double d0 = 0.0, d1 = 0.0;
-            if (NT % 2 == 0) {
+            for (int jy = 0; jy < 4; ++jy) {
+                const double *row = base + jy * NT;
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                if (NT % 4 == 0) {
 #pragma unroll
-                for (int t = 0; t < NT; t += 2) {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(row + t));
-                    d0 = fma(n[t], v.x, d0);
-                    d1 = fma(n[t + 1], v.y, d1);
+                    for (int t = 0; t < NT; t += 4) {
+                        const double2 u = *reinterpret_cast<const double2 *>(row + t), v = *reinterpret_cast<const double2 *>(row + t + 2);
+                        d0 = fma(n[t], u.x, d0);
+                        d1 = fma(n[t + 1], u.y, d1);
+                        d2 = fma(n[t + 2], v.x, d2);
+                        d3 = fma(n[t + 3], v.y, d3);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) d0 = fma(n[t], row[t], d0);
                 }
-            } else {
+                wsum = fma(wy[jy], (d0 + d1) + (d2 + d3), wsum);
+            }
+        } else {
+            const double *mxp = pt.mx + (size_t)i * ny * NT;
+#pragma unroll
+            for (int jy = 0; jy < 4; ++jy) {
+                const double *row = mxp + (size_t)wrap_index(iy - 1 + jy, ny) * NT;
+                double d0 = 0.0;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) d0 = fma(n[t], __ldg(row + t), d0);
+                wsum = fma(wy[jy], d0, wsum);
             }
-            wsum = fma(wy[jy], d0 + d1, wsum);
         }
-    };
-    int i = i0;
-    for (; i + 1 < i1; i += 2) {
-        double *o0 = a.out + (size_t)i * a.ldo + b, *o1 = o0 + a.ldo;
-        const double x0 = *o0, x1 = *o1;
-        double w0, w1;
-        bool z0, z1;
-        one(i, w0, z0);
-        one(i + 1, w1, z1);
-        if (!z0) *o0 = x0 + w0;
-        if (!z1) *o1 = x1 + w1;
-    }
-    if (i < i1) {
-        double *o0 = a.out + (size_t)i * a.ldo + b;
-        const double x0 = *o0;
-        double w0;
-        bool z0;
-        one(i, w0, z0);
-        if (!z0) *o0 = x0 + w0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if (active && !zero) a.out[(size_t)i * a.ldo + b] = x_cur + wsum;
     }
 }
 
