@@ -17,6 +17,6 @@ $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'dgemm_chi2_kernel|kspace_fast_eval_kernel' -s 9 -c 6 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'dgemm_chi2_kernel|kspace_fast_eval_kernel|metal_add_kernel' -s 9 -c 6 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT
