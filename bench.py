@@ -331,7 +331,7 @@ def run_fft(args, rank, world, dev, ctx):
 
 def main_reference(args, rank, world):
     if rank != 0:
-        return
+        return None
     model, data = build_workload()
     cores = os.cpu_count() or 1
     S = args.cpu_sample or max(4, min(32, cores))
@@ -351,7 +351,7 @@ def main_reference(args, rank, world):
                              "sample": "%d parameter vectors per step, oracle/oracle.c with OpenMP on all host threads" % S},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    return line
 
 
 def main_ours(args, rank, world, local_rank):
@@ -451,7 +451,7 @@ def main_ours(args, rank, world, local_rank):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
     total_ms = sum(v[0] for v in prof.values())
     nr = capi.lib().bf_model_transform_nr(gm.h)
     nk = int(np.ceil(np.log10(1152.5 / 1e-4) * 50))
@@ -507,9 +507,26 @@ def main_ours(args, rank, world, local_rank):
                     "api": "bf_chi2_batch (host buffers, pinned)"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "scan": scan, "scan_kspace": scan_k, "fft": fft, "kernels": kernels,
             "chi2_checksum": chi2_check}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
+
+
+class StdoutToStderr:
+    """Everything libraries print on fd 1 while the benchmark runs (NCCL's version banner, torchrun
+    notices) goes to stderr; stdout carries the one JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -518,12 +535,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        main_reference(args, rank, world)
+        with StdoutToStderr():
+            line = main_reference(args, rank, world)
     else:
         if world != args.gpus and world == 1 and args.gpus > 1:
             print(json.dumps({"error": "launch with torchrun for --gpus > 1"}))
             sys.exit(2)
-        main_ours(args, rank, world, local_rank)
+        with StdoutToStderr():
+            line = main_ours(args, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
