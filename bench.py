@@ -463,6 +463,13 @@ def main_ours(args, rank, world, local_rank):
         if name in fl:
             ent["tflops"] = fl[name] * B / (msk / cnt * 1e-3) * 1e-12
             ent["frac_of_fp64_peak"] = ent["tflops"] / fp64
+        elif "eval_kernel" in name:
+            # model-evaluation kernels: algorithmic bytes = 8*N_out store (+ 8*N_out read-modify-write for the
+            # second pass) + 8*npar load per evaluation; they are FP64-ALU bound
+            n_out = gd.n_grid if "grid" in name else gd.n
+            by = (8.0 * n_out * (2 if "extras" in name else 1) + 8.0 * npar) * B
+            ent["hbm_gbs"] = by / (msk / cnt * 1e-3) * 1e-9
+            ent["frac_of_hbm_peak"] = ent["hbm_gbs"] / hbm
         kernels[name] = ent
     top = max(prof.items(), key=lambda kv: kv[1][0])[0]
     if top in fl:
