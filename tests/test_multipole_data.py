@@ -60,6 +60,15 @@ def test_gpu_multipole_data_against_oracle(ctx, model):
     assert ok.sum() >= B // 2
     assert rel_err_bins(pred[:, ok], ref_pred[:, ok]) < RTOL
     assert rel_err(chi2[ok], ref_chi2[ok]) < RTOL
+    # the normal-equation path sees the same whitened residuals: gram[f][0][0] = chi2, and toy data vectors work
+    gram, gst = capi.gram_batch(ctx, gm, gd, params, 1)
+    assert np.array_equal(gst[:, 0], ref_st) and rel_err(gram[ok, 0, 0], ref_chi2[ok]) < RTOL
+    toys = capi.Toys(ctx, gd, pred[:, np.argmax(ok)], seed=3, first_toy=0, ntoy=4)
+    idx = np.arange(B) % 4
+    c_t, _ = capi.chi2_batch_toys(ctx, gm, gd, params, toys, idx)
+    ref_t, _ = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), params, data_override=toys.download()[idx], nthreads=8)
+    assert rel_err(c_t[ok], ref_t[ok]) < RTOL
+    toys.close()
     gm.close(), gd.close()
 
 
