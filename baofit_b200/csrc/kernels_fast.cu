@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256, 2) metal_add_kernel(FastArgs a) {
         const double ya = fmin(fmax(r0 + dpi_min, m.metal_y0), m.metal_ymax), yb = fmin(fmax(r0 + dpi_max, m.metal_y0), m.metal_ymax);
         const int ia = (int)floor((ya - m.metal_y0) * m.metal_inv_dy), ib = (int)floor((yb - m.metal_y0) * m.metal_inv_dy);
         const int first = ia - 1, last = ib + 2;
-        if (NT % 2 != 0 || first < 0 || last > ny - 1 || last - first + 1 > kMetalWin) return -1;  // odd NT: rows are not 16-byte aligned
+        if (NT % 2 != 0 || ny < kMetalWin || first < 0 || last > ny - 1 || last - first + 1 > kMetalWin) return -1;  // odd NT: rows are not 16-byte aligned
         return min(first, ny - kMetalWin);
     };
     auto issue = [&](int i) {  // thread 0
