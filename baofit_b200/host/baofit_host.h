@@ -360,6 +360,12 @@ public:
     void predictBatch(std::vector<likely::Parameters> const &params, std::vector<double> &pred /*[n][B]*/) const;
     // CorrelationFitter.cc:88-92; method is accepted for interface parity ("mn2::vmetric")
     likely::FunctionMinimumPtr fit(std::string const &methodName = "mn2::vmetric", std::string const &config = "") const;
+    // CorrelationFitter.cc:109-123 (likely::MarkovChainEngine "saunter" is one Metropolis chain; here nwalkers
+    // independent Metropolis chains advance in lock step, one chi-square batch per step): appends nchain
+    // samples of npar values + fval, one every `interval` steps of a walker, proposals drawn from the
+    // covariance of fminStart scaled by 2.38/sqrt(nfloat).
+    void mcmc(likely::FunctionMinimumPtr fminStart, int nchain, int interval, std::vector<double> &samples, int nwalkers = 256,
+              unsigned long long seed = 1966) const;
     AbsCorrelationModelPtr model() const { return _model; }
     AbsCorrelationDataPtr data() const { return _data; }
     double icovScale() const { return _icovScale; }

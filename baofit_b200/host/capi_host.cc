@@ -188,6 +188,15 @@ extern "C" int bfh_dump_model(bfh_session *s, const double *values, int ndump, d
     BFH_CATCH
 }
 
+extern "C" int bfh_mcmc(bfh_session *s, int nchain, int interval, int nwalkers, unsigned long long seed, double *samples) {
+    BFH_TRY
+    likely::FunctionMinimumPtr fm = s->fitter->fit("mn2::vmetric", "");
+    std::vector<double> out;
+    s->fitter->mcmc(fm, nchain, interval, out, nwalkers, seed);
+    std::copy(out.begin(), out.end(), samples);
+    BFH_CATCH
+}
+
 extern "C" int bfh_scan_size(const bfh_session *s, long *total) {
     BFH_TRY
     *total = s->analyzer->scanSize();

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <random>
 #include <iostream>
 #include <limits>
 #include <sstream>
@@ -182,6 +183,63 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
                 off += np;
             }
         }
+    }
+}
+
+void CorrelationFitter::mcmc(likely::FunctionMinimumPtr fminStart, int nchain, int interval, std::vector<double> &samples, int nwalkers,
+                             unsigned long long seed) const {
+    if (!fminStart || fminStart->covariance.empty()) throw RuntimeError("CorrelationFitter::mcmc: the starting minimum has no covariance.");
+    if (nchain <= 0 || interval <= 0 || nwalkers <= 0) throw RuntimeError("CorrelationFitter::mcmc: expected nchain, interval, nwalkers > 0.");
+    likely::FitParameters const &fp = fminStart->parameters;
+    const int npar = (int)fp.size();
+    std::vector<int> fidx;
+    for (int i = 0; i < npar; ++i)
+        if (fp[i].floating) fidx.push_back(i);
+    const int n = (int)fidx.size();
+    // Cholesky factor of the proposal covariance
+    std::vector<double> L(fminStart->covariance);
+    for (int j = 0; j < n; ++j) {
+        double d = L[j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
+        if (!(d > 0)) throw RuntimeError("CorrelationFitter::mcmc: covariance is not positive definite.");
+        L[j * n + j] = std::sqrt(d);
+        for (int i = j + 1; i < n; ++i) {
+            double t = L[i * n + j];
+            for (int k = 0; k < j; ++k) t -= L[i * n + k] * L[j * n + k];
+            L[i * n + j] = t / L[j * n + j];
+        }
+    }
+    const double scale = 2.38 / std::sqrt((double)std::max(n, 1));
+    nwalkers = std::min(nwalkers, nchain);
+    const int perWalker = (nchain + nwalkers - 1) / nwalkers;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> gauss(0.0, 1.0);
+    std::uniform_real_distribution<double> unif(0.0, 1.0);
+    std::vector<likely::Parameters> x(nwalkers, fminStart->values()), trial(nwalkers);
+    std::vector<double> fx, ft, g(n);
+    evaluateBatch(x, fx);
+    samples.clear();
+    samples.reserve((size_t)nchain * (npar + 1));
+    for (int step = 1; step <= perWalker * interval && (int)samples.size() < nchain * (npar + 1); ++step) {
+        for (int w = 0; w < nwalkers; ++w) {
+            for (int i = 0; i < n; ++i) g[i] = gauss(rng);
+            trial[w] = x[w];
+            for (int i = 0; i < n; ++i) {
+                double s = 0;
+                for (int k = 0; k <= i; ++k) s += L[i * n + k] * g[k];
+                trial[w][fidx[i]] += scale * s;
+            }
+        }
+        evaluateBatch(trial, ft);  // one batch on the GPU per Metropolis step
+        for (int w = 0; w < nwalkers; ++w) {
+            // fval = -log L; a vector outside the model's valid domain (NaN) is always rejected
+            if (std::isfinite(ft[w]) && std::log(unif(rng)) < fx[w] - ft[w]) { x[w] = trial[w]; fx[w] = ft[w]; }
+        }
+        if (step % interval == 0)
+            for (int w = 0; w < nwalkers && (int)samples.size() < nchain * (npar + 1); ++w) {
+                samples.insert(samples.end(), x[w].begin(), x[w].end());
+                samples.push_back(fx[w]);
+            }
     }
 }
 

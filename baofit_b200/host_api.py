@@ -12,7 +12,7 @@ RESID_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_doubl
 HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
-                "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model"]
+                "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc"]
 
 
 def lib():
@@ -42,6 +42,7 @@ def lib():
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.bfh_dump_residuals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.bfh_dump_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.bfh_mcmc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
         L.bfh_lm_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, RESID_FN,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]
@@ -137,6 +138,12 @@ class Session:
         v = np.ascontiguousarray(values, dtype=np.float64)
         out = np.zeros((ndump, 3))
         _check(lib().bfh_dump_model(self.h, _p(v), ndump, float(zdump), _p(out)))
+        return out
+
+    def mcmc(self, nchain, interval=10, nwalkers=256, seed=1966):
+        """Fit, then nchain Metropolis samples [npar values, fval] from lock-step walkers."""
+        out = np.zeros((nchain, self.npar + 1))
+        _check(lib().bfh_mcmc(self.h, nchain, interval, nwalkers, seed, _p(out)))
         return out
 
     def fit(self, config=""):

@@ -68,6 +68,10 @@ int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, d
 int bfh_dump_residuals(bfh_session *s, const double *values, const double *errors, const char *path, int gradients);
 int bfh_dump_model(bfh_session *s, const double *values, int ndump, double zdump, double *multipoles);
 
+/* CorrelationFitter::fit followed by CorrelationFitter::mcmc (CorrelationFitter.cc:109-123): nchain samples of
+ * [npar values, fval], one every `interval` Metropolis steps of nwalkers lock-step chains. */
+int bfh_mcmc(bfh_session *s, int nchain, int interval, int nwalkers, unsigned long long seed, double *samples);
+
 /* The minimiser on its own (likely::FitModel::findMinimum "mn2::vmetric" replacement) over a
  * caller-supplied batched objective: fn(points[B*npar], B, f[B], user). Used to run the identical
  * minimiser code over the CPU oracle in the parity tests, and for host-only tests. */

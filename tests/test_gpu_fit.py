@@ -129,3 +129,19 @@ def test_dump_residuals_and_model_against_oracle(built, golden_tree, tmp_path):
     mp = s2.dump_model(s2.values, 29, 2.25)
     mt = np.loadtxt(os.path.join(golden_tree, "demo", "multi.theory"))[:, 1].reshape(29, 3)
     assert np.max(np.abs(mp - mt)) < 1e-14
+
+
+def test_mcmc_walkers_sample_the_fit_posterior(built, golden_tree):
+    """CorrelationFitter::mcmc with lock-step walkers: the sample mean and covariance of the floating
+    parameters agree with the fit's best values and HESSE covariance (demo data, nearly Gaussian)."""
+    text, base = ini(golden_tree, "rmu_to_bao.ini")
+    s = H.Session(text, base)
+    fit = s.fit()
+    chain = s.mcmc(4096, interval=20, nwalkers=512, seed=3)
+    fl = np.nonzero(s.floating)[0]
+    mean, cov = chain[:, fl].mean(axis=0), np.cov(chain[:, fl].T)
+    sig = np.sqrt(np.diag(fit["covariance"]))
+    assert np.all(np.abs(mean - fit["values"][fl]) < 0.15 * sig)
+    assert np.all(np.abs(np.sqrt(np.diag(cov)) / sig - 1) < 0.15)
+    assert np.all(chain[:, -1] >= fit["fval"] - 1e-9)
+    assert np.all(chain[:, np.nonzero(~s.floating)[0]] == s.values[~s.floating])
