@@ -104,16 +104,24 @@ __device__ __forceinline__ double basis_correlation(const DevModel &m, const dou
         w3 = t3 - (1.0 / 3.0) * t * dx;
     }
     const double L2 = (-1.0 + 3.0 * musq) * 0.5, L4 = (3.0 + musq * (-30.0 + 35.0 * musq)) * 0.125;
-    const double g[9] = {1.0, c1, c2, L2, L2 * c1, L2 * c2, L4, L4 * c1, L4 * c2};
     const double2 *lo = tab + (size_t)j * 9, *hi = lo + 9;
-    double ylo = 0.0, yhi = 0.0, clo = 0.0, chi = 0.0;
+    // sum_l L_l (X_l0 + c1 X_l1 + c2 X_l2) for the four spline quantities: 32 FMAs, no products of weights
+    double ylo, yhi, clo, chi;
+    {
+        const double2 a0 = lo[0], a1 = lo[1], a2 = lo[2], b0 = hi[0], b1 = hi[1], b2 = hi[2];
+        ylo = fma(c2, a2.x, fma(c1, a1.x, a0.x));
+        clo = fma(c2, a2.y, fma(c1, a1.y, a0.y));
+        yhi = fma(c2, b2.x, fma(c1, b1.x, b0.x));
+        chi = fma(c2, b2.y, fma(c1, b1.y, b0.y));
+    }
 #pragma unroll
-    for (int q = 0; q < 9; ++q) {
-        double2 a = lo[q], b = hi[q];
-        ylo = fma(g[q], a.x, ylo);
-        clo = fma(g[q], a.y, clo);
-        yhi = fma(g[q], b.x, yhi);
-        chi = fma(g[q], b.y, chi);
+    for (int l = 1; l < 3; ++l) {
+        const double Ll = l == 1 ? L2 : L4;
+        const double2 a0 = lo[3 * l], a1 = lo[3 * l + 1], a2 = lo[3 * l + 2], b0 = hi[3 * l], b1 = hi[3 * l + 1], b2 = hi[3 * l + 2];
+        ylo = fma(Ll, fma(c2, a2.x, fma(c1, a1.x, a0.x)), ylo);
+        clo = fma(Ll, fma(c2, a2.y, fma(c1, a1.y, a0.y)), clo);
+        yhi = fma(Ll, fma(c2, b2.x, fma(c1, b1.x, b0.x)), yhi);
+        chi = fma(Ll, fma(c2, b2.y, fma(c1, b1.y, b0.y)), chi);
     }
     return w0 * ylo + w1 * yhi + w2 * clo + w3 * chi;
 }
