@@ -22,7 +22,7 @@ EXPORTS = [
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
     "bf_fft_planes_batch", "bf_model_fft_plane_dims",
-    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch",
+    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch", "bf_gram_probes",
 ]
 
 
@@ -77,6 +77,8 @@ def lib():
                                          C.c_void_p, C.c_void_p]
         L.bf_gram_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+        L.bf_gram_probes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
         L.bf_fft_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.bf_model_fft_plane_dims.argtypes = [C.c_void_p, c_int_p, c_int_p]
         _LIB = L
@@ -235,6 +237,20 @@ def gram_batch(ctx, model, data, params, G, toys=None, toy_index=None):
     idx = None if toy_index is None else np.ascontiguousarray(toy_index, dtype=np.int32)
     _check(lib().bf_gram_batch(ctx.h, model.h, data.h, _ptr(p), nfit, G, toys.h if toys is not None else None,
                                _ptr(idx), _ptr(gram), _ptr(status)))
+    return gram, status
+
+
+def gram_probes(ctx, model, data, centres, steps, toys=None, toy_index=None):
+    """bf_gram_probes: central-difference probe groups generated on the GPU; gram[nfit, G, G], status[nfit]."""
+    c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, model.npar)
+    h = np.ascontiguousarray(steps, dtype=np.float64).reshape(-1, model.npar)
+    nfit, nprobe = c.shape[0], int(np.count_nonzero(h[0]))
+    G = 2 * nprobe + 1
+    gram = np.zeros((nfit, G, G))
+    status = np.zeros(nfit, dtype=np.int32)
+    idx = None if toy_index is None else np.ascontiguousarray(toy_index, dtype=np.int32)
+    _check(lib().bf_gram_probes(ctx.h, model.h, data.h, _ptr(c), _ptr(h), nfit, nprobe, toys.h if toys is not None else None,
+                                _ptr(idx), _ptr(gram), _ptr(status)))
     return gram, status
 
 

@@ -1609,7 +1609,7 @@ extern "C" int bf_gram_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, c
     cudaStream_t s = ctx->stream;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     // passes of whole fits, at most ~16384 columns each
-    const int fits_per_pass = std::max(1, std::min(nfit, 16384 / G));
+    const int fits_per_pass = std::max(1, std::min(nfit, 65536 / G));
     const int colcap = fits_per_pass * G, ldy = round_up(colcap, kPadN);
     size_t nb_params = al((size_t)colcap * npar * sizeof(double)), nb_idx = al((size_t)colcap * sizeof(int)),
            nb_st = al((size_t)colcap * sizeof(int)), nb_gram = al((size_t)fits_per_pass * G * G * sizeof(double)),
@@ -1637,6 +1637,61 @@ extern "C" int bf_gram_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, c
         BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * G * G, d_gram, (size_t)nf * G * G * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (status) BF_CUDA_OK(cudaMemcpyAsync(status + (size_t)f0 * G, d_st, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, s));
         BF_CUDA_OK(cudaStreamSynchronize(s));  // colidx is reused by the next pass
+    }
+    BF_CUDA_OK(cudaGetLastError());
+    return BF_OK;
+}
+
+extern "C" int bf_gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *centres, const double *steps,
+                              int nfit, int nprobe, const bf_toys *toys, const int *toy_index, double *gram, int *status) {
+    const int G = 2 * nprobe + 1;
+    if (!gram || !steps || nfit <= 0 || nprobe < 0 || G > 96) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: bad argument (2 nprobe + 1 <= 96)");
+    int rc = check_args(ctx, m, d, centres, nfit);
+    if (rc) return rc;
+    if ((toys == nullptr) != (toy_index == nullptr)) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: toys and toy_index go together");
+    const int npar = m->dev.npar, n = d->n;
+    for (int f = 0; f < nfit; ++f) {
+        int cnt = 0;
+        for (int j = 0; j < npar; ++j) cnt += steps[(size_t)f * npar + j] != 0.0;
+        if (cnt != nprobe) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: every fit must probe exactly nprobe parameters");
+        if (toys && (toy_index[f] < 0 || toy_index[f] >= toys->ntoy)) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: toy index out of range");
+    }
+    if (toys && (toys->ctx != ctx || toys->n != n)) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: the toy table belongs to another context / data set");
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const int fits_per_pass = std::max(1, std::min(nfit, 65536 / G));
+    const int colcap = fits_per_pass * G, ldy = round_up(colcap, kPadN);
+    size_t nb_cs = al((size_t)fits_per_pass * npar * sizeof(double)), nb_params = al((size_t)colcap * npar * sizeof(double)),
+           nb_idx = al((size_t)colcap * sizeof(int)), nb_st = al((size_t)colcap * sizeof(int)), nb_sf = al((size_t)fits_per_pass * sizeof(int)),
+           nb_gram = al((size_t)fits_per_pass * G * G * sizeof(double)), nb_ov = toys ? al((size_t)colcap * n * sizeof(double)) : 0,
+           nb_y = al((size_t)d->n_pad * ldy * sizeof(double));
+    if ((rc = ensure(&ctx->io, &ctx->io_bytes, 2 * nb_cs + nb_params + nb_idx + nb_st + nb_sf + nb_gram + nb_ov + nb_y))) return rc;
+    char *p = (char *)ctx->io;
+    auto take = [&](size_t bytes) { char *q = p; p += bytes; return q; };
+    double *d_c = (double *)take(nb_cs), *d_h = (double *)take(nb_cs), *d_params = (double *)take(nb_params);
+    int *d_idx = (int *)take(nb_idx), *d_st = (int *)take(nb_st), *d_sf = (int *)take(nb_sf);
+    double *d_gram = (double *)take(nb_gram), *d_ov = toys ? (double *)take(nb_ov) : nullptr, *d_y = (double *)take(nb_y);
+    std::vector<int> colidx;
+    for (int f0 = 0; f0 < nfit; f0 += fits_per_pass) {
+        const int nf = std::min(fits_per_pass, nfit - f0), bc = nf * G;
+        BF_CUDA_OK(cudaMemcpyAsync(d_c, centres + (size_t)f0 * npar, (size_t)nf * npar * sizeof(double), cudaMemcpyHostToDevice, s));
+        BF_CUDA_OK(cudaMemcpyAsync(d_h, steps + (size_t)f0 * npar, (size_t)nf * npar * sizeof(double), cudaMemcpyHostToDevice, s));
+        BF_KERNEL(ctx, "expand_probes_kernel", launch_expand_probes(s, d_c, d_h, nf, npar, nprobe, d_params));
+        if (toys) {
+            colidx.resize(bc);
+            for (int c = 0; c < bc; ++c) colidx[c] = toy_index[f0 + c / G];
+            BF_CUDA_OK(cudaMemcpyAsync(d_idx, colidx.data(), (size_t)bc * sizeof(int), cudaMemcpyHostToDevice, s));
+            BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
+        }
+        if ((rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st))) return rc;
+        BF_KERNEL(ctx, "gram_kernel", launch_gram(s, d_y, ldy, n, G, nf, d_gram));
+        BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * G * G, d_gram, (size_t)nf * G * G * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (status) {
+            BF_KERNEL(ctx, "reduce_status_kernel", launch_reduce_status(s, d_st, nf, G, d_sf));
+            BF_CUDA_OK(cudaMemcpyAsync(status + f0, d_sf, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, s));
+        }
+        BF_CUDA_OK(cudaStreamSynchronize(s));
     }
     BF_CUDA_OK(cudaGetLastError());
     return BF_OK;

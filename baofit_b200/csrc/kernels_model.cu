@@ -957,4 +957,42 @@ void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int
     gram_kernel<<<nfit, 256, (size_t)kGramRows * G * sizeof(double), s>>>(Y, ldy, nrows, G, nfit, out);
 }
 
+__global__ void expand_probes_kernel(const double *__restrict__ centres, const double *__restrict__ steps, int nfit, int npar,
+                                     int nprobe, double *__restrict__ params) {
+    const int G = 2 * nprobe + 1;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= nfit * G) return;
+    const int f = col / G, g = col - f * G;
+    const double *c = centres + (size_t)f * npar, *h = steps + (size_t)f * npar;
+    double *out = params + (size_t)col * npar;
+    // the probed parameter of column g is the ((g-1)/2)-th parameter with a non-zero step
+    int want = g == 0 ? -1 : (g - 1) / 2, seen = 0;
+    const double sgn = (g & 1) ? 1.0 : -1.0;
+    for (int j = 0; j < npar; ++j) {
+        double v = c[j];
+        if (h[j] != 0.0) {
+            if (seen == want) v += sgn * h[j];
+            ++seen;
+        }
+        out[j] = v;
+    }
+}
+
+__global__ void reduce_status_kernel(const int *__restrict__ status, int nfit, int G, int *__restrict__ status_fit) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfit) return;
+    int s = 0;
+    for (int g = 0; g < G; ++g) s |= status[(size_t)f * G + g];
+    status_fit[f] = s;
+}
+
+void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params) {
+    const int total = nfit * (2 * nprobe + 1);
+    expand_probes_kernel<<<(total + 127) / 128, 128, 0, s>>>(centres, steps, nfit, npar, nprobe, params);
+}
+
+void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, int *status_fit) {
+    reduce_status_kernel<<<(nfit + 127) / 128, 128, 0, s>>>(status, nfit, G, status_fit);
+}
+
 }  // namespace bf

@@ -353,6 +353,9 @@ public:
     // Gauss-Newton normal equations of nfit probe groups of G points (bf_gram_batch); bad[f] = some point invalid
     void gramFlat(std::vector<double> const &params, int nfit, int G, std::vector<double> &gram, std::vector<char> &bad,
                   bf_toys const *toys = nullptr, const int *toyIndexPerFit = nullptr) const;
+    // the same with the probe columns generated on the GPU from centres / steps (bf_gram_probes)
+    void gramProbes(std::vector<double> const &centres, std::vector<double> const &steps, int nfit, int nprobe, std::vector<double> &gram,
+                    std::vector<char> &bad, bf_toys const *toys = nullptr, const int *toyIndexPerFit = nullptr) const;
     // Runs many LM fits in lock step (Jacobian rounds through gramFlat, trial rounds through chiSquareFlat);
     // toyOfFit (optional) gives the realisation each fit is taken against.
     void runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys = nullptr, std::vector<int> const *toyOfFit = nullptr) const;

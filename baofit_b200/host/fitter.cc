@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <random>
@@ -142,8 +143,28 @@ void CorrelationFitter::gramFlat(std::vector<double> const &params, int nfit, in
         for (int g = 0; g < G; ++g) bad[f] |= status[(size_t)f * G + g] != 0;
 }
 
+namespace {
+double nowSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+void CorrelationFitter::gramProbes(std::vector<double> const &centres, std::vector<double> const &steps, int nfit, int nprobe,
+                                   std::vector<double> &gram, std::vector<char> &bad, bf_toys const *toys, const int *toyIndexPerFit) const {
+    const int G = 2 * nprobe + 1;
+    gram.assign((size_t)nfit * G * G, 0.0);
+    bad.assign(nfit, 0);
+    if (nfit == 0) return;
+    std::vector<int> status(nfit);
+    check(bf_gram_probes(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), centres.data(), steps.data(), nfit,
+                         nprobe, toys, toys ? toyIndexPerFit : nullptr, gram.data(), status.data()),
+          "bf_gram_probes");
+    for (int f = 0; f < nfit; ++f) bad[f] = status[f] != 0;
+}
+
 void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys, std::vector<int> const *toyOfFit) const {
-    std::vector<double> flatJ, flatP, gram, chi2;
+    const bool verbose = std::getenv("BAOFIT_VERBOSE_FITS") != nullptr;
+    double tGram = 0, tChi2 = 0, t0 = nowSeconds();
+    long nGram = 0, nChi2 = 0, rounds = 0;
+    std::vector<double> flatJ, steps, flatP, gram, chi2;
     std::vector<char> bad;
     std::vector<int> jfits, pfits, jtoy, ptoy;
     for (;;) {
@@ -156,15 +177,20 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             else pfits.push_back((int)k);
         }
         if (byG.empty() && pfits.empty()) break;
+        ++rounds;
         for (auto const &kv : byG) {
             const int G = kv.first;
             flatJ.clear();
+            steps.clear();
             jtoy.clear();
             for (int k : kv.second) {
-                fits[k].requestJacobian(flatJ);
+                fits[k].requestProbes(flatJ, steps);
                 if (toys) jtoy.push_back((*toyOfFit)[k]);
             }
-            gramFlat(flatJ, (int)kv.second.size(), G, gram, bad, toys, toys ? jtoy.data() : nullptr);
+            double ta = nowSeconds();
+            gramProbes(flatJ, steps, (int)kv.second.size(), (G - 1) / 2, gram, bad, toys, toys ? jtoy.data() : nullptr);
+            tGram += nowSeconds() - ta;
+            nGram += (long)kv.second.size() * G;
             for (size_t q = 0; q < kv.second.size(); ++q) fits[kv.second[q]].consumeJacobian(gram.data() + q * G * G, bad[q] != 0);
         }
         if (!pfits.empty()) {
@@ -175,7 +201,10 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
                 if (toys) ptoy.insert(ptoy.end(), fits[k].pending(), (*toyOfFit)[k]);
             }
             const int npar = fits[pfits[0]].nPar();
+            double ta = nowSeconds();
             chiSquareFlat(flatP, (int)(flatP.size() / npar), chi2, toys, toys ? ptoy.data() : nullptr);
+            tChi2 += nowSeconds() - ta;
+            nChi2 += (long)(flatP.size() / npar);
             size_t off = 0;
             for (int k : pfits) {
                 int np = fits[k].pending();
@@ -184,6 +213,9 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             }
         }
     }
+    if (verbose)
+        std::fprintf(stderr, "runLockStepLM: %zu fits, %ld rounds, %.3f s total: bf_gram_batch %.3f s (%ld points), bf_chi2_batch %.3f s (%ld points)\n",
+                     fits.size(), rounds, nowSeconds() - t0, tGram, nGram, tChi2, nChi2);
 }
 
 void CorrelationFitter::mcmc(likely::FunctionMinimumPtr fminStart, int nchain, int interval, std::vector<double> &samples, int nwalkers,

@@ -455,6 +455,13 @@ void LMFit::requestJacobian(std::vector<double> &flat) const {
         }
 }
 
+void LMFit::requestProbes(std::vector<double> &centres, std::vector<double> &steps) const {
+    centres.insert(centres.end(), _x.begin(), _x.end());
+    size_t at = steps.size();
+    steps.resize(at + _x.size(), 0.0);
+    for (int i = 0; i < _n; ++i) steps[at + _fidx[i]] = _h[i];
+}
+
 void LMFit::solveStep() {
     std::vector<double> rhs(_n), M;
     for (int i = 0; i < _n; ++i) rhs[i] = -_g[i];

@@ -133,6 +133,10 @@ public:
     int nPar() const { return (int)_x.size(); }
     // Jacobian round: appends groupSize() full-length vectors (centre first) to flat
     void requestJacobian(std::vector<double> &flat) const;
+    // the same round described compactly: the centre and the probe step of every parameter (0 = not
+    // probed), npar numbers each; the probe columns are generated on the GPU (bf_gram_probes)
+    void requestProbes(std::vector<double> &centres, std::vector<double> &steps) const;
+    int nFloating() const { return _n; }
     // gram[G*G] as returned by bf_gram_batch; bad = some column had a non-zero status
     void consumeJacobian(const double *gram, bool bad);
     // trial round: appends pending() full-length vectors

@@ -318,6 +318,15 @@ int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *model, const bf_data *data, 
 int bf_gram_batch(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *params, int nfit, int G,
                   const bf_toys *toys, const int *toy_index, double *gram, int *status);
 
+/* Same normal equations with the probe points generated on the GPU: fit f is described by its centre
+ * centres[f*npar ..] and its probe steps steps[f*npar ..] (0 = parameter not probed; every fit probes
+ * the same number nprobe of parameters). The group of fit f is
+ *     x,  x + h_1 e_1,  x - h_1 e_1,  x + h_2 e_2,  x - h_2 e_2, ...      (G = 2 nprobe + 1 columns)
+ * with the probed parameters in index order, i.e. only (2 npar) instead of (G npar) numbers per fit
+ * cross the bus. gram[nfit][G][G] as in bf_gram_batch; status[nfit] is the OR over the group. */
+int bf_gram_probes(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *centres, const double *steps,
+                   int nfit, int nprobe, const bf_toys *toys, const int *toy_index, double *gram, int *status);
+
 #ifdef __cplusplus
 }
 #endif

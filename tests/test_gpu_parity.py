@@ -261,3 +261,31 @@ def test_gram_batch_against_oracle_residuals(ctx, case):
         assert np.max(np.abs(gram[f] - ref) / scale) < 1e-7  # differences of nearly equal residual vectors
         assert abs(gram[f, 0, 0] - chi2[f * G]) < 1e-10 * chi2[f * G]
     gm.close(), gd.close()
+
+
+def test_gram_probes_equal_explicit_probe_groups(ctx):
+    """bf_gram_probes (probe columns generated on the GPU from centre + steps) returns bit-identical
+    Gram matrices to bf_gram_batch fed with the same columns built on the host."""
+    m, d = W.qso_rspace()
+    rng = np.random.Generator(np.random.PCG64(8))
+    nfit = 40
+    centres = m.random_batch(nfit, rng)
+    steps = np.zeros_like(centres)
+    fl = np.nonzero(m.floating)[0]
+    steps[:, fl] = 0.01 * m.errors[fl] * rng.uniform(0.5, 1.5, size=(nfit, len(fl)))
+    G = 2 * len(fl) + 1
+    cols = np.repeat(centres, G, axis=0)
+    for f in range(nfit):
+        for k, j in enumerate(fl):
+            cols[f * G + 1 + 2 * k, j] += steps[f, j]
+            cols[f * G + 2 + 2 * k, j] -= steps[f, j]
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    a, sa = capi.gram_probes(ctx, gm, gd, centres, steps)
+    b, sb = capi.gram_batch(ctx, gm, gd, cols, G)
+    assert np.array_equal(a, b) and np.array_equal(sa, sb.max(axis=1))
+    toys = capi.Toys(ctx, gd, np.zeros(gd.n), seed=2, first_toy=0, ntoy=5)
+    idx = rng.integers(0, 5, size=nfit)
+    a, _ = capi.gram_probes(ctx, gm, gd, centres, steps, toys, idx)
+    b, _ = capi.gram_batch(ctx, gm, gd, cols, G, toys, idx)
+    assert np.array_equal(a, b)
+    toys.close(), gm.close(), gd.close()
