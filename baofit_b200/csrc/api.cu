@@ -2,6 +2,7 @@
 // per-batch kernel pipelines. No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -809,6 +810,11 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
             }
             if ((rc = upload(p.allocs, aext.data(), aext.size(), &p.d_Aext))) return rc;
             if ((rc = upload(p.allocs, wa.data(), wa.size(), &p.d_WA))) return rc;
+            if (n_pad <= kFullmMaxM && n_pad % 32 == 0 && ktot % kFullmKC == 0) {
+                std::vector<double> wat((size_t)(ktot / kFullmKC) * n_pad * kFullmLdA);
+                gemm_fullm_tile_A(wa.data(), n_pad, ktot, ktot, wat.data());
+                if ((rc = upload(p.allocs, wat.data(), wat.size(), &p.d_WAt))) return rc;
+            }
             p.fold_ok = true;
             p.fold_case = fcase;
             p.fold_nb = nb;
@@ -1190,7 +1196,14 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             if (what == OUT_CHI2) {
                 g.A = plan->d_WA; g.C = nullptr; g.ldc = 0;
                 g.chi2 = chi2_dst; g.status = w.status;
-                BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g));
+                // opt-in: reads the panel from HBM exactly once, but streams the left matrix from L2 twice as
+                // often (32-column panels) and measures slower on B200 (0.63 vs 0.56 ms)
+                static const bool use_fullm = std::getenv("BAOFIT_FULLM_GEMM") != nullptr;
+                if (plan->d_WAt && use_fullm) {
+                    g.A = plan->d_WAt;
+                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2_fullm(s, g, ctx->sm_count));
+                } else
+                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g));
             } else {
                 g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
                 BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));

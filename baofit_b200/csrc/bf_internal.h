@@ -205,6 +205,7 @@ struct bf_data {
         int fold_pmax = 0, fold_nrt = 0, fold_nz = 0;
         double *d_Aext = nullptr;     // [n_pad][n_grid_pad + fold_kext]
         double *d_WA = nullptr;       // [n_pad][n_grid_pad + fold_kext]
+        double *d_WAt = nullptr;      // the same matrix in the stage layout of dgemm_chi2_fullm_kernel (n_pad <= 512)
         std::vector<void *> allocs;
     };
     std::map<const bf_model *, Plan> plans;

@@ -177,6 +177,13 @@ void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, in
 // override panel of the toy path: out[b][i] = table[index[b]][i]
 void launch_gather_rows(cudaStream_t s, const double *table, const int *index, int B, int n, double *out);
 
+// Full-M chi-square GEMM (M <= 512): one CTA owns all rows of a 32-column panel, so the panel is read from
+// HBM exactly once; the left matrix streams from L2 in the pre-tiled stage layout At[K/8][M][12]
+// (see gemm_fullm_tile_A). chi2[n] = sum_m (A.B)[m][n]^2.
+constexpr int kFullmKC = 8, kFullmLdA = kFullmKC + 4, kFullmBN = 32, kFullmMaxM = 512;
+void gemm_fullm_tile_A(const double *A, int M, int K, int lda, double *At /* [K/8][M][12] */);
+void launch_gemm_chi2_fullm(cudaStream_t s, const GemmArgs &g /* g.A = At */, int sm_count);
+
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);
 

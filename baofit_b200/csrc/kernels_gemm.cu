@@ -12,6 +12,8 @@
 // Tiles: CTA 64 x 64, k depth 16, three cp.async stages; 4 warps in a 2 x 2 grid, each warp a
 // 32 x 32 tile = 4 x 4 DMMA fragments. Shared-memory rows are padded by 4 doubles so that every
 // fragment load is bank-conflict free.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace bf {
@@ -201,6 +203,172 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
             g.chi2[n] = v;
         }
     }
+}
+
+// ---- full-M chi-square GEMM ---------------------------------------------------------------------
+// dgemm_chi2_kernel above walks the row tiles of A one after the other and re-reads its 64-column panel of B
+// for each of them (7 times for the 448 x 528 fused tail of the DR11 QSO model: 525 MB of DRAM traffic for a
+// 175 MB panel). Here one CTA holds accumulators for ALL rows of a 32-column panel (M/32 warps, each a
+// 32 x 32 tile), so B is read exactly once and only the small, L2-resident left matrix is streamed per CTA.
+// A is stored pre-tiled as At[k chunk][M][12], i.e. one pipeline stage is ONE contiguous TMA bulk copy
+// (cp.async.bulk, SASS UBLKCP) plus 8 row copies of the panel; full/empty mbarriers, no CTA-wide barrier in
+// the k loop; persistent CTAs keep the pipeline running across panels.
+namespace {
+constexpr int FKC = kFullmKC, FLDA = kFullmLdA, FBN = kFullmBN, FLDB = FBN + 4, FSTAGES = 4;
+
+__device__ __forceinline__ void f_mbar_init(unsigned long long *bar, int count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void f_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_arrive(unsigned long long *bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar), ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void f_tma_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                 "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kFullmMaxM, 1) dgemm_chi2_fullm_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) double fsm[];
+    const int M = g.M, K = g.K;
+    const int a_stage = M * FLDA, b_stage = FKC * FLDB;
+    double *As = fsm;                       // [FSTAGES][M][FLDA]
+    double *Bs = As + FSTAGES * a_stage;    // [FSTAGES][FKC][FLDB]
+    double *red = Bs + FSTAGES * b_stage;   // [M/32][FBN]
+    __shared__ __align__(8) unsigned long long full_bar[FSTAGES], empty_bar[FSTAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int l4 = lane & 3, l8 = lane >> 2;
+    const int nchunks = K / FKC, ntiles = (g.N + FBN - 1) / FBN;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int total = my_tiles * nchunks;
+    const unsigned stage_bytes = (unsigned)((a_stage + FKC * FBN) * sizeof(double));
+
+    auto issue = [&](int gc) {  // one thread: chunk gc of this CTA's (tile, k chunk) sequence
+        const int slot = gc % FSTAGES, it = gc / nchunks, chunk = gc - it * nchunks;
+        const int n0 = (blockIdx.x + it * gridDim.x) * FBN;
+        f_mbar_expect_tx(&full_bar[slot], stage_bytes);
+        f_tma_g2s(As + slot * a_stage, g.A + (size_t)chunk * a_stage, (unsigned)(a_stage * sizeof(double)), &full_bar[slot]);
+#pragma unroll
+        for (int kr = 0; kr < FKC; ++kr)
+            f_tma_g2s(Bs + slot * b_stage + kr * FLDB, g.Bm + (size_t)(chunk * FKC + kr) * g.ldb + n0, (unsigned)(FBN * sizeof(double)),
+                      &full_bar[slot]);
+    };
+    if (tid == 0) {
+        for (int st = 0; st < FSTAGES; ++st) { f_mbar_init(&full_bar[st], 1); f_mbar_init(&empty_bar[st], nwarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (my_tiles == 0) return;
+    if (tid == 0)
+        for (int c = 0; c < FSTAGES && c < total; ++c) issue(c);
+
+    for (int it = 0; it < my_tiles; ++it) {
+        const int n0 = (blockIdx.x + it * gridDim.x) * FBN;
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int t = 0; t < nchunks; ++t) {
+            const int gc = it * nchunks + t, slot = gc % FSTAGES;
+            if (tid == 0 && gc >= 1 && gc - 1 + FSTAGES < total) {
+                f_mbar_wait(&empty_bar[(gc - 1) % FSTAGES], ((gc - 1) / FSTAGES) & 1);
+                issue(gc - 1 + FSTAGES);
+            }
+            __syncwarp();
+            f_mbar_wait(&full_bar[slot], (gc / FSTAGES) & 1);
+            const double *as = As + slot * a_stage + (warp * 32 + l8) * FLDA + l4;
+            const double *bs = Bs + slot * b_stage + l4 * FLDB + l8;
+#pragma unroll
+            for (int kk = 0; kk < FKC; kk += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * FLDA + kk];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = bs[kk * FLDB + ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) f_mbar_arrive(&empty_bar[slot]);
+        }
+        // column sums of squares over this warp's 32 rows, then over the warps
+        double cs[4][2];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double v = 0.0;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) v = fma(acc[mi][ni][e], acc[mi][ni][e], v);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                cs[ni][e] = v;
+            }
+        __syncthreads();  // the previous tile's reduction buffer has been consumed
+        if (lane < 4) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                red[warp * FBN + ni * 8 + 2 * lane] = cs[ni][0];
+                red[warp * FBN + ni * 8 + 2 * lane + 1] = cs[ni][1];
+            }
+        }
+        __syncthreads();
+        if (tid < FBN) {
+            const int n = n0 + tid;
+            if (n < g.N) {
+                double v = 0.0;
+                for (int w = 0; w < nwarps; ++w) v += red[w * FBN + tid];
+                if (g.status && g.status[n]) v = nan("");
+                g.chi2[n] = v;
+            }
+        }
+    }
+}
+
+void gemm_fullm_tile_A(const double *A, int M, int K, int lda, double *At) {
+    const int nch = K / kFullmKC;
+    for (int c = 0; c < nch; ++c)
+        for (int m = 0; m < M; ++m)
+            for (int k = 0; k < kFullmLdA; ++k)
+                At[((size_t)c * M + m) * kFullmLdA + k] = k < kFullmKC ? A[(size_t)m * lda + c * kFullmKC + k] : 0.0;
+}
+
+void launch_gemm_chi2_fullm(cudaStream_t s, const GemmArgs &g, int sm_count) {
+    const size_t smem = ((size_t)FSTAGES * (g.M * FLDA + FKC * FLDB) + (size_t)(g.M / 32) * FBN) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(dgemm_chi2_fullm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int ntiles = (g.N + FBN - 1) / FBN;
+    dgemm_chi2_fullm_kernel<<<std::min(ntiles, sm_count), g.M, smem, s>>>(g);
 }
 
 // ---- toy-MC noise ------------------------------------------------------------------------------

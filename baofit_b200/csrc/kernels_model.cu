@@ -916,7 +916,7 @@ void launch_gather_rows(cudaStream_t s, const double *table, const int *index, i
 // ------------------------------------------------------------------------------------------
 // Gauss-Newton normal equations: one CTA per fit
 // ------------------------------------------------------------------------------------------
-constexpr int kGramRows = 32, kGramMaxG = 96;
+constexpr int kGramRows = 32;  // G <= 96 (checked by the callers): at most 19 pairs per thread
 
 __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y, int ldy, int nrows, int G, int nfit,
                                                    double *__restrict__ out) {
