@@ -168,6 +168,10 @@ static void copy_bb(const bf_broadband_spec &s, DevBB &d) {
     d.z_min = s.z_min; d.z_max = s.z_max; d.z_step = s.z_step;
     d.inv_r0 = s.enabled ? 1.0 / s.r0 : 0.0;
     d.z0 = s.z0;
+    d.inv_1pz0 = 1.0 / (1.0 + s.z0);
+    d.plan_r = axis_plan(s.r_min, s.r_max, s.r_step);
+    d.plan_rp = axis_plan(s.rp_min, s.rp_max, s.rp_step);
+    d.plan_rt = axis_plan(s.rt_min, s.rt_max, s.rt_step);
 }
 
 static int bb_ncoef(const bf_broadband_spec &s) {

@@ -33,14 +33,32 @@ constexpr int kFineSub = 4;   // fine k nodes per native P(k) interval
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Exponent run lo, lo+step, ..., <= hi of one broadband axis, split for Horner evaluation: the first nneg
+// exponents are <= 0 (powers of x, the last of them is -elast), the remaining n - nneg are > 0 (powers of
+// x - 1, the first of them is efirst); baofit/BroadbandModel.cc:209-213.
+struct AxisPlan {
+    int n, nneg, elast, efirst, step;
+};
+inline AxisPlan axis_plan(int lo, int hi, int step) {
+    AxisPlan p{0, 0, 0, 0, step};
+    if (step <= 0 || hi < lo) return p;
+    p.n = (hi - lo) / step + 1;
+    for (int k = 0; k < p.n; ++k)
+        if (lo + k * step <= 0) p.nneg = k + 1;
+    if (p.nneg > 0) p.elast = -(lo + (p.nneg - 1) * step);
+    if (p.nneg < p.n) p.efirst = lo + p.nneg * step;
+    return p;
+}
+
 struct DevBB {
     int enabled, idx_base;
+    AxisPlan plan_r, plan_rp, plan_rt;
     int r_min, r_max, r_step, r_denom;
     int mu_min, mu_max, mu_step;
     int rp_min, rp_max, rp_step;
     int rt_min, rt_max, rt_step;
     int z_min, z_max, z_step;
-    double inv_r0, z0;
+    double inv_r0, z0, inv_1pz0;
 };
 
 // One tabulated multipole family on shared knots: per-interval cubic coefficients

@@ -37,70 +37,97 @@ __device__ __forceinline__ double legendre_p(int ell, double mu) {  // baofit/Br
     }
 }
 
-// Power sequence of one broadband axis: exponents lo, lo+step, ... with the reference's rule
-// "use (x-1) instead of x when the exponent is positive" (baofit/BroadbandModel.cc:209-213).
-// The four starting values are computed once per evaluation point (AxisBase); inside the nested
-// loops each term then costs one multiplication instead of one pow().
-struct AxisBase {
-    double neg0, neg_step, pos0, pos_step;
-    __device__ __forceinline__ void init(double x, int lo, int step) {
-        neg0 = ipow(x, lo);
-        neg_step = ipow(x, step);
-        int first_pos = lo > 0 ? lo : lo + ((0 - lo) / step + 1) * step;  // smallest exponent > 0
-        pos0 = ipow(x - 1.0, first_pos);
-        pos_step = ipow(x - 1.0, step);
+// One broadband axis in Horner form. The reference multiplies every coefficient by
+// pow(e > 0 ? x - 1 : x, e) (baofit/BroadbandModel.cc:209-213); summed over a run of exponents that is
+// a polynomial in 1/x^step for the non-positive exponents and one in (x-1)^step for the positive ones,
+// so an axis costs one fma per term and at most one division per evaluation point instead of a power
+// per term. AxisPlan (host-built, warp-uniform) holds the split of the run.
+__device__ __forceinline__ double small_pow(double x, int k) {  // k >= 0, almost always 0 or 1
+    return k == 0 ? 1.0 : k == 1 ? x : ipow(x, k);
+}
+
+struct AxisVal {
+    double us, tail, vs, head;
+    __device__ __forceinline__ void init(const AxisPlan &p, double x) {
+        us = tail = vs = head = 1.0;
+        if (p.nneg > 1 || p.elast > 0) {
+            const double u = 1.0 / x;
+            us = small_pow(u, p.step);
+            tail = small_pow(u, p.elast);
+        }
+        if (p.n > p.nneg) {
+            const double v = x - 1.0;
+            vs = small_pow(v, p.step);
+            head = small_pow(v, p.efirst);
+        }
     }
 };
-struct AxisIter {
-    double neg, pos;
-    __device__ __forceinline__ explicit AxisIter(const AxisBase &b) : neg(b.neg0), pos(b.pos0) {}
-    // value for exponent e (called with e = lo, lo+step, ... in order), then advance
-    __device__ __forceinline__ double next(const AxisBase &b, int e) {
-        double v;
-        if (e > 0) { v = pos; pos *= b.pos_step; }
-        else { v = neg; neg *= b.neg_step; }
-        return v;
+
+// sum_k term(base + k*stride) * pow(e_k > 0 ? x - 1 : x, e_k) over the exponent run of the plan; the coefficient
+// pointer is stepped (forwards over the first run, backwards over the second) so that a term costs no multiply
+template <class Term>
+__device__ __forceinline__ double axis_sum(const AxisPlan &p, const AxisVal &v, const double *base, size_t stride, Term term) {
+    double acc = 0.0;
+    if (p.nneg > 0) {
+        const double *q = base;
+        acc = term(q);
+#pragma unroll 1
+        for (int k = 1; k < p.nneg; ++k) {
+            q += stride;
+            acc = fma(acc, v.us, term(q));
+        }
+        if (p.elast > 0) acc *= v.tail;
     }
-};
+    if (p.n > p.nneg) {
+        const double *q = base + (size_t)(p.n - 1) * stride;
+        double pos = term(q);
+#pragma unroll 1
+        for (int k = p.n - 2; k >= p.nneg; --k) {
+            q -= stride;
+            pos = fma(pos, v.vs, term(q));
+        }
+        acc = fma(pos, v.head, acc);
+    }
+    return acc;
+}
 
 // Broadband polynomial, baofit/BroadbandModel.cc:197-226. pT = transposed parameters
 // (pT[j*ldb + b]), already offset to column b.
 __device__ __forceinline__ double broadband_eval(const DevBB &s, const double *__restrict__ pT, int ldb, double r,
                                                  double mu, double z) {
-    double rr = r * s.inv_r0, rrP = r * mu * s.inv_r0, rrT = r * sqrt(1.0 - mu * mu) * s.inv_r0;
-    double zz = (1.0 + z) / (1.0 + s.z0);
-    AxisBase br, bp, bt;
-    if (s.r_denom == 1) br.init(rr, s.r_min, s.r_step);
-    bp.init(rrP, s.rp_min, s.rp_step);
-    bt.init(rrT, s.rt_min, s.rt_step);
+    const double rr = r * s.inv_r0;
+    AxisVal vr, vp, vt;
+    if (s.r_denom == 1) vr.init(s.plan_r, rr);
+    vp.init(s.plan_rp, r * mu * s.inv_r0);
+    if (s.plan_rt.n > 1 || s.rt_min != 0) vt.init(s.plan_rt, r * sqrt(1.0 - mu * mu) * s.inv_r0);
+    else vt.us = vt.tail = vt.vs = vt.head = 1.0;
+    const bool z_axis = !(s.z_min == 0 && s.z_max == 0);
+    const double zz = z_axis ? (1.0 + z) * s.inv_1pz0 : 1.0;
     double xi = 0.0;
-    const double *pc = pT + (size_t)s.idx_base * ldb;  // walks the coefficients, rT fastest
+    const double *pc = pT + (size_t)s.idx_base * ldb;  // coefficient blocks, rT fastest
+    const size_t st_t = (size_t)ldb, st_p = st_t * s.plan_rt.n, st_r = st_p * s.plan_rp.n, st_m = st_r * s.plan_r.n;
 #pragma unroll 1
     for (int zi = s.z_min; zi <= s.z_max; zi += s.z_step) {
-        double zF = ipow(zz, zi);
+        const double zF = zi == 0 ? 1.0 : ipow(zz, zi);
 #pragma unroll 1
-        for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step) {
-            double zmF = zF * legendre_p(mi, mu);
-            AxisIter ir(br);
+        for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step, pc += st_m) {
+            const double zmF = mi == 0 ? zF : zF * legendre_p(mi, mu);
+            auto p_block = [&](const double *pr) {
+                return axis_sum(s.plan_rp, vp, pr, st_p, [&](const double *pp) {
+                    return axis_sum(s.plan_rt, vt, pp, st_t, [](const double *q) { return __ldg(q); });
+                });
+            };
+            double sum_r;
+            if (s.r_denom == 1) {
+                sum_r = axis_sum(s.plan_r, vr, pc, st_r, p_block);
+            } else {  // fractional r exponents (r-index denominator), one pow per term as in the reference
+                sum_r = 0.0;
+                int kr = 0;
 #pragma unroll 1
-            for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step) {
-                double rF = s.r_denom == 1 ? ir.next(br, ri) : pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom);
-                AxisIter ip(bp);
-                double accP = 0.0;
-#pragma unroll 1
-                for (int pi = s.rp_min; pi <= s.rp_max; pi += s.rp_step) {
-                    double rPF = ip.next(bp, pi);
-                    AxisIter it(bt);
-                    double acc = 0.0;
-#pragma unroll 2
-                    for (int ti = s.rt_min; ti <= s.rt_max; ti += s.rt_step) {
-                        acc = fma(__ldg(pc), it.next(bt, ti), acc);
-                        pc += ldb;
-                    }
-                    accP = fma(acc, rPF, accP);
-                }
-                xi = fma(accP, rF * zmF, xi);
+                for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step, ++kr)
+                    sum_r = fma(p_block(pc + kr * st_r), pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom), sum_r);
             }
+            xi = fma(sum_r, zmF, xi);
         }
     }
     return xi;

@@ -131,39 +131,40 @@ __device__ __forceinline__ double basis_correlation(const DevModel &m, const dou
 __device__ __forceinline__ double broadband_fast(const DevBB &s, const double *__restrict__ pT, int ldb,
                                                  const double *__restrict__ rt_pow, int n_rt,
                                                  const double *__restrict__ z_pow, double rr, double mu, double rrP) {
-    const bool r_axis = !(s.r_min == 0 && s.r_max == 0), p_axis = !(s.rp_min == 0 && s.rp_max == 0);
-    AxisBase br, bp;
-    if (r_axis && s.r_denom == 1) br.init(rr, s.r_min, s.r_step);
-    if (p_axis) bp.init(rrP, s.rp_min, s.rp_step);
+    const bool r_axis = !(s.r_min == 0 && s.r_max == 0);
+    AxisVal vr, vp;
+    vr.us = vr.tail = vr.vs = vr.head = 1.0;
+    if (r_axis && s.r_denom == 1) vr.init(s.plan_r, rr);
+    vp.init(s.plan_rp, rrP);
     double xi = 0.0;
-    const double *pc = pT + (size_t)s.idx_base * ldb;  // walks the coefficients, rT fastest
+    const double *pc = pT + (size_t)s.idx_base * ldb;  // coefficient blocks, rT fastest
+    const size_t st_p = (size_t)ldb * n_rt, st_r = st_p * s.plan_rp.n, st_m = st_r * s.plan_r.n;
     int kz = 0;
 #pragma unroll 1
     for (int zi = s.z_min; zi <= s.z_max; zi += s.z_step, ++kz) {
         const double zF = z_pow[kz];
 #pragma unroll 1
-        for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step) {
+        for (int mi = s.mu_min; mi <= s.mu_max; mi += s.mu_step, pc += st_m) {
             const double zmF = mi == 0 ? zF : zF * legendre_p(mi, mu);
-            AxisIter ir(br);
-#pragma unroll 1
-            for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step) {
-                double rF = 1.0;
-                if (r_axis) rF = s.r_denom == 1 ? ir.next(br, ri) : pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom);
-                AxisIter ip(bp);
-                double accP = 0.0;
-#pragma unroll 1
-                for (int pi = s.rp_min; pi <= s.rp_max; pi += s.rp_step) {
-                    const double rPF = p_axis ? ip.next(bp, pi) : 1.0;
+            auto p_block = [&](const double *pr) {
+                return axis_sum(s.plan_rp, vp, pr, st_p, [&](const double *pp) {
                     double acc = 0.0;
 #pragma unroll 5
-                    for (int kt = 0; kt < n_rt; ++kt) {
-                        acc = fma(__ldg(pc), rt_pow[kt], acc);
-                        pc += ldb;
-                    }
-                    accP = fma(acc, rPF, accP);
-                }
-                xi = fma(accP, rF * zmF, xi);
+                    for (int kt = 0; kt < n_rt; ++kt) acc = fma(__ldg(pp + (size_t)kt * ldb), rt_pow[kt], acc);
+                    return acc;
+                });
+            };
+            double sum_r;
+            if (s.r_denom == 1) {
+                sum_r = axis_sum(s.plan_r, vr, pc, st_r, p_block);
+            } else {
+                sum_r = 0.0;
+                int kr = 0;
+#pragma unroll 1
+                for (int ri = s.r_min; ri <= s.r_max; ri += s.r_step, ++kr)
+                    sum_r = fma(p_block(pc + kr * st_r), pow(ri > 0 ? rr - 1.0 : rr, (double)ri / s.r_denom), sum_r);
             }
+            xi = fma(sum_r, zmF, xi);
         }
     }
     return xi;
