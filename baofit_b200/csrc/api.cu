@@ -56,6 +56,7 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     if (c->mp) cudaFree(c->mp);
+    if (c->chi2_part) cudaFree(c->chi2_part);
     if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -932,6 +933,25 @@ void nl_table(const DevModel &dm, double zeff, double out[5], double *pk_scale) 
     *pk_scale = s * s * std::pow((1.0 + zeff) / (1.0 + dm.zref), -2.0);
 }
 
+// Small batches run the chi-square GEMM with the row tiles split over CTAs; this provides its scratch.
+static int gemm_chi2_scratch(bf_ctx *ctx, cudaStream_t s, GemmArgs &g) {
+    g.chi2_part = nullptr;
+    g.part_ld = 0;
+    if (g.N > gemm_chi2_split_columns(g.M, ctx->sm_count)) return BF_OK;
+    const int ld = round_up(g.N, 64);
+    const size_t need = (size_t)(g.M / 64) * ld * sizeof(double);
+    if (need > ctx->chi2_part_bytes) {
+        BF_CUDA_OK(cudaStreamSynchronize(s));
+        void *p = ctx->chi2_part;
+        if (int rc = ensure(&p, &ctx->chi2_part_bytes, need)) return rc;
+        ctx->chi2_part = (double *)p;
+    }
+    g.chi2_part = ctx->chi2_part;
+    g.part_ld = ld;
+    ctx->launches++;  // the kernel that sums the partials
+    return BF_OK;
+}
+
 enum Output { OUT_PRED, OUT_CHI2, OUT_XIU, OUT_TRANSFORM, OUT_WHITENED /* y = L^-1 (pred - d), [n_pad][ldo] */ };
 
 // Runs one chunk (B <= chunk capacity) entirely on the context's stream.
@@ -1123,7 +1143,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             g.lower_triangular = 1;
             if (what == OUT_CHI2) {
                 g.chi2 = d_out; g.status = w.status;
-                BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+                if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+                BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
             } else {
                 g.C = d_out; g.ldc = ldo;
                 BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
@@ -1206,8 +1227,10 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 if (plan->d_WAt && use_fullm) {
                     g.A = plan->d_WAt;
                     BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2_fullm(s, g, ctx->sm_count));
-                } else
-                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g));
+                } else {
+                    if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g, ctx->sm_count));
+                }
             } else {
                 g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
                 BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));
@@ -1264,7 +1287,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
         g.lower_triangular = 1;
         g.chi2 = chi2_dst; g.status = w.status;
-        BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+        if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+        BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
     }
     if (what == OUT_WHITENED) {
         GemmArgs g{};
@@ -1338,7 +1362,8 @@ static int run_device_multipole(bf_ctx *ctx, const bf_model *m, const bf_data *d
             g.lower_triangular = 1;
             if (what == OUT_CHI2) {
                 g.chi2 = d_out + b0; g.status = d_status ? d_status + b0 : nullptr;
-                BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g));
+                if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+                BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
             } else {
                 g.C = d_out + b0; g.ldc = ldo;
                 BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));

@@ -144,6 +144,8 @@ struct bf_ctx {
     size_t io_bytes = 0;
     void *mp = nullptr;  // multipole-binned data: predictions at the expanded points + residual panel
     size_t mp_bytes = 0;
+    double *chi2_part = nullptr;  // per-row-tile chi2 partial sums of small batches (launch_gemm_chi2)
+    size_t chi2_part_bytes = 0;
     double *pinned_flag = nullptr;  // small pinned buffer for tiny device->host answers (flag + key values)
     int sm_count = 148;
     // optional per-kernel timing (bf_ctx_set_profiling): event pairs around every launch

@@ -98,6 +98,10 @@ struct GemmArgs {
     // chi-square epilogue: chi2[n] = sum_m C[m][n]^2 (C is not stored)
     double *chi2;
     const int *status;
+    // small batches: one CTA per (column panel, row tile) writes chi2_part[row tile][part_ld], summed in fixed
+    // order by a second kernel (launch_gemm_chi2 decides; scratch of (M/64) * part_ld doubles or null)
+    double *chi2_part;
+    int part_ld;
 };
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
@@ -185,7 +189,9 @@ void gemm_fullm_tile_A(const double *A, int M, int K, int lda, double *At /* [K/
 void launch_gemm_chi2_fullm(cudaStream_t s, const GemmArgs &g /* g.A = At */, int sm_count);
 
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
-void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g);
+void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count = 0);
+// columns up to which launch_gemm_chi2 splits the row tiles over CTAs (scratch sizing)
+int gemm_chi2_split_columns(int M, int sm_count);
 
 // toy noise: out[t][i] = truth_i + scale * sum_j L[i][j] g_{t,j}
 void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth,

@@ -128,12 +128,14 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
     double *As = smem, *Bs = smem + STAGES * A_STAGE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
     const int n0 = blockIdx.x * BN;
-    const int MT = g.M / BM;
+    // gridDim.y == 1: this CTA walks all row tiles; otherwise (small batches) only row tile blockIdx.y
+    const bool split = gridDim.y > 1;
+    const int mt0 = split ? blockIdx.y : 0, mt1 = split ? blockIdx.y + 1 : g.M / BM;
     // flattened (row tile, k tile) sequence so that the cp.async pipeline never drains
     auto ktiles = [&](int mt) { return (g.lower_triangular ? min(g.K, (mt + 1) * BM) : g.K) / BK; };
     int total = 0;
-    for (int mt = 0; mt < MT; ++mt) total += ktiles(mt);
-    int lmt = 0, lkt = 0;  // next tile to load
+    for (int mt = mt0; mt < mt1; ++mt) total += ktiles(mt);
+    int lmt = mt0, lkt = 0;  // next tile to load
     auto issue = [&](int slot) {
         load_stage(As + slot * A_STAGE, Bs + slot * B_STAGE, g.A, g.Bm, g.lda, g.ldb, lmt * BM, n0, lkt * BK, tid);
         if (++lkt == ktiles(lmt)) { lkt = 0; ++lmt; }
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
         if (s < total) issue(s);
         cp_async_commit();
     }
-    int cmt = 0, ckt = 0;
+    int cmt = mt0, ckt = 0;
     for (int t = 0; t < total; ++t) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -197,12 +199,25 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
     __syncthreads();
     if (tid < BN) {
         int n = n0 + tid;
-        if (n < g.N) {
-            double v = red[tid] + red[BN + tid];
+        double v = red[tid] + red[BN + tid];
+        if (split) {
+            g.chi2_part[(size_t)blockIdx.y * g.part_ld + n] = v;  // part_ld covers whole panels
+        } else if (n < g.N) {
             if (g.status && g.status[n]) v = nan("");
             g.chi2[n] = v;
         }
     }
+}
+
+// chi2[n] = sum over row tiles of the partial sums, in tile order (deterministic)
+__global__ void chi2_part_sum_kernel(const double *__restrict__ part, int part_ld, int tiles, int N,
+                                     const int *__restrict__ status, double *__restrict__ chi2) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double v = 0.0;
+    for (int t = 0; t < tiles; ++t) v += part[(size_t)t * part_ld + n];
+    if (status && status[n]) v = nan("");
+    chi2[n] = v;
 }
 
 // ---- full-M chi-square GEMM ---------------------------------------------------------------------
@@ -416,14 +431,28 @@ void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch) {
     dgemm_store_kernel<<<grid, 128, SMEM_BYTES, s>>>(g);
 }
 
-void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g) {
+// Row tiles are split over CTAs while all (panel, row tile) CTAs fit in about two waves of 4 resident CTAs
+// per SM: a 64-column panel walked by one CTA is a serial chain of M/64 * K/16 pipeline steps (183 us for the
+// 448 x 528 fused tail), far longer than the rest of a small-batch call.
+int gemm_chi2_split_columns(int M, int sm_count) {
+    const int tiles = M / BM;
+    if (tiles < 2 || sm_count <= 0) return 0;
+    return (8 * sm_count / tiles) * BN;
+}
+
+void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count) {
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(dgemm_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         attr = true;
     }
-    dim3 grid((g.N + BN - 1) / BN, 1, 1);
-    dgemm_chi2_kernel<<<grid, 128, SMEM_BYTES, s>>>(g);
+    const int panels = (g.N + BN - 1) / BN, tiles = g.M / BM;
+    if (g.chi2_part && g.N <= gemm_chi2_split_columns(g.M, sm_count) && g.part_ld >= panels * BN) {
+        dgemm_chi2_kernel<<<dim3(panels, tiles, 1), 128, SMEM_BYTES, s>>>(g);
+        chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, tiles, g.N, g.status, g.chi2);
+        return;
+    }
+    dgemm_chi2_kernel<<<dim3(panels, 1, 1), 128, SMEM_BYTES, s>>>(g);
 }
 
 void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth,
