@@ -29,6 +29,10 @@ def test_config4_full_batch_properties(ctx):
     # a ragged sub-batch gives the same numbers as the full batch
     sub, _ = capi.chi2_batch(ctx, gm, gd, p[:1000 + 37])
     assert np.max(np.abs(sub - chi2[:1037]) / chi2[:1037]) < 1e-12
+    # ... also through the small-batch chi2 GEMM (row tiles split over CTAs, partial sums), down to B = 1
+    for nb in (1, 65, 9000, 11000):
+        sub, _ = capi.chi2_batch(ctx, gm, gd, p[:nb])
+        assert np.max(np.abs(sub - chi2[:nb]) / chi2[:nb]) < 1e-12
     # linear in the BAO amplitude: pred(a=2) - pred(a=1) = pred(a=1) - pred(a=0)
     q = np.repeat(p[:256], 3, axis=0)
     q[:, m.index("BAO amplitude")] = np.tile([0.0, 1.0, 2.0], 256)
