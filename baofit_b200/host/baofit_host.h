@@ -18,6 +18,8 @@
 // library through the C ABI (include/baofit_b200.h), batched over parameter vectors.
 #pragma once
 
+#include <array>
+#include <functional>
 #include <map>
 #include <memory>
 #include <set>
@@ -217,8 +219,19 @@ public:
     TransverseBinningType getTransverseBinningType() const { return _type; }
     virtual double getRedshift(int index) const = 0;
     // BinnedData subset
-    void setData(int index, double value);
+    // weighted = the value is an element of Cinv.d (".wdata" files); such data is un-weighted with the full
+    // covariance over the bins with data when the data set is finalized
+    void setData(int index, double value, bool weighted = false);
     bool hasData(int index) const { return _values.count(index) > 0; }
+    // custom bin centres (".grid" files, AbsCorrelationData.cc:243-274): replace the grid's centres once every
+    // bin of the grid has been given one
+    void setCustomBinCenters(int index, double c1, double c2, double c3);
+    int getNCustomBins() const { return (int)_custom.size(); }
+    bool useCustomGrid() const { return _useCustom; }
+    void enableCustomGrid();
+    void copyCustomGridFrom(AbsCorrelationData const &other);
+    bool isWeighted() const { return _weighted; }
+    void getBinCenters(int index, double centers[3]) const;
     void setCovariance(int i, int j, double value);
     void setInverseCovariance(int i, int j, double value);
     int getNBinsWithData() const { return (int)_values.size(); }
@@ -254,6 +267,8 @@ protected:
 
 private:
     std::map<int, double> _values;
+    std::map<int, std::array<double, 3>> _custom;
+    bool _useCustom = false, _weighted = false;
     std::map<std::pair<int, int>, double> _cov;
     bool _isInverse = false, _haveCov = false, _haveFinalCuts = false, _finalized = false;
     double _rMin, _rMax, _rVetoMin, _rVetoMax, _muMin, _muMax, _rperpMin, _rperpMax, _rparMin, _rparMax, _zMin, _zMax;
@@ -320,14 +335,43 @@ private:
     void _setIndex(int index) const;
 };
 
-// Inverse-covariance weighted combination of congruent observations, what likely::BinnedDataResampler::combined
-// returns for the plates added with CorrelationAnalyzer::addData (baofit/CorrelationAnalyzer.cc:42-75,
-// src/baofit.cc:526-583): C^-1 = sum_k C_k^-1,  C^-1 d = sum_k C_k^-1 d_k. `into` receives data + covariance.
-void combineCorrelationData(std::vector<AbsCorrelationDataPtr> const &observations, AbsCorrelationData &into);
-
 // "<name>.data" / ".cov" / ".icov" text loaders (AbsCorrelationData.cc:156-277); ".cov.gz" is not
 // handled here (tests decompress fixtures first).
-void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov = false);
+void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov = false, bool weighted = false,
+                         bool customGrid = false);
+
+// Stand-in for likely::BinnedDataResampler as baofit uses it (CorrelationAnalyzer.cc:42-75 addData/getCombined,
+// :213-260 the jackknife / bootstrap / each samplers): keeps the individual observations of a platelist and
+// builds inverse-covariance weighted combinations of subsets of them,
+//   Cinv = sum_k n_k Cinv_k,   Cinv.d = sum_k n_k Cinv_k.d_k     (n_k = how often observation k was drawn).
+// With fixCovariance the covariance of a bootstrap sample accounts for repeated observations,
+//   C_fixed = C (sum_k n_k^2 Cinv_k) C   (the variance of the weighted mean above)        UNVERIFIED (dep).
+// Every sample is a fresh data set from the prototype factory (grid, final cuts), not finalized.
+class BinnedDataResampler {
+public:
+    typedef std::function<AbsCorrelationDataPtr()> Factory;
+    explicit BinnedDataResampler(Factory prototype) : _prototype(prototype) {}
+    void addObservation(AbsCorrelationDataPtr observation);  // not finalized; congruent with the first one
+    int getNObservations() const { return (int)_icov.size(); }
+    AbsCorrelationDataPtr combined() const;
+    // observations left after dropping the seqno-th ndrop-subset (subsets in lexicographic order of the dropped
+    // indices); null once seqno is past the last subset
+    AbsCorrelationDataPtr jackknife(int ndrop, long seqno) const;
+    static long jackknifeSize(int nobs, int ndrop);
+    // size draws with replacement (0: as many as there are observations) from a counter-based generator keyed by
+    // (seed, trial), so that trials can be sharded over ranks
+    AbsCorrelationDataPtr bootstrap(int size, bool fixCovariance, unsigned long long seed, long trial) const;
+    std::vector<int> bootstrapCounts(int size, unsigned long long seed, long trial) const;
+    AbsCorrelationDataPtr getObservationCopy(int index) const;
+    AbsCorrelationDataPtr combine(std::vector<int> const &counts, bool fixCovariance) const;
+
+private:
+    Factory _prototype;
+    std::vector<int> _bins;
+    AbsCorrelationDataPtr _first;
+    std::vector<std::vector<double>> _icov, _icovData;  // per observation: dense Cinv over the bins with data, Cinv.d
+};
+typedef std::shared_ptr<BinnedDataResampler> BinnedDataResamplerPtr;
 
 // ---- fitter -----------------------------------------------------------------------------------
 class CorrelationFitter {
@@ -415,6 +459,17 @@ public:
                    bool oneLine = false) const;
     void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
                          std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "") const;
+    // CorrelationAnalyzer.cc:301-335 (doJackknifeAnalysis, doBootstrapAnalysis, fitEach) + the loop of
+    // doSamplingAnalysis :452-532: every sample is a new data vector AND covariance, refitted from the model's
+    // initial parameters. kind = "jackknife" (n = observations dropped per sample), "bootstrap" (n = trials,
+    // size = draws per trial, 0: number of observations), "each" (one sample per observation). Samples
+    // [first, first+count) of the sequence, count < 0: to its end. Returns the number of samples fitted.
+    void setResampler(BinnedDataResamplerPtr resampler) { _resampler = resampler; }
+    BinnedDataResamplerPtr resampler() const { return _resampler; }
+    long resamplingSize(std::string const &kind, int n) const;
+    AbsCorrelationDataPtr resample(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long seqno) const;
+    long doResampling(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long first, long count,
+                      std::vector<std::vector<double>> &fitted, std::vector<double> &chi2, std::vector<int> &status) const;
 
 private:
     std::string _method;
@@ -423,6 +478,7 @@ private:
     bool _verbose;
     AbsCorrelationDataPtr _data;
     AbsCorrelationModelPtr _model;
+    BinnedDataResamplerPtr _resampler;
 };
 
 // ---- .ini driven construction -----------------------------------------------------------------
@@ -440,6 +496,7 @@ Options parseIni(std::string const &text);
 // src/baofit.cc:415-464: builds the model the options describe (r-space or --kspace).
 AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDir);
 // src/baofit.cc:475-628 (comoving formats): builds, loads, cuts and finalizes the data set.
-AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir);
+// With plateroot/platelist the individual observations are also handed to *resampler (if given).
+AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir, BinnedDataResamplerPtr *resampler = nullptr);
 
 }  // namespace baofit

@@ -14,6 +14,7 @@ struct bfh_session {
     Options options;
     AbsCorrelationModelPtr model;
     AbsCorrelationDataPtr data;
+    BinnedDataResamplerPtr resampler;  // platelist sessions only
     std::shared_ptr<CorrelationFitter> fitter;
     std::shared_ptr<CorrelationAnalyzer> analyzer;
 };
@@ -47,7 +48,7 @@ extern "C" int bfh_session_create(const char *ini_text, const char *base_dir, co
         s->model = createModel(s->options, base_dir ? base_dir : "");
     } catch (std::exception const &e) { g_herr = e.what(); delete s; return -2; }
     try {
-        s->data = createData(s->options, base_dir ? base_dir : "");
+        s->data = createData(s->options, base_dir ? base_dir : "", &s->resampler);
         if (s->options.flag("dist-matrix")) {
             std::vector<double> r, mu, z;
             s->data->gridCoordinates(r, mu, z);
@@ -61,6 +62,7 @@ extern "C" int bfh_session_create(const char *ini_text, const char *base_dir, co
                                                   s->options.num("rmax", 200), covSampleSize, false));
         s->analyzer->addData(s->data);
         s->analyzer->setModel(s->model);
+        s->analyzer->setResampler(s->resampler);
     } catch (std::exception const &e) { g_herr = e.what(); delete s; return -4; }
     *out = s;
     return 0;
@@ -230,6 +232,48 @@ extern "C" int bfh_toymc(bfh_session *s, long first, long count, unsigned long l
     s->analyzer->doToyMCSampling(first, count, seed, fit, c, st);
     int npar = s->model->getNParameters();
     for (long t = 0; t < count; ++t) {
+        if (fitted) std::copy(fit[t].begin(), fit[t].end(), fitted + (size_t)t * npar);
+        if (chi2) chi2[t] = c[t];
+        if (status) status[t] = st[t];
+    }
+    BFH_CATCH
+}
+
+extern "C" int bfh_nobservations(const bfh_session *s) { return s && s->resampler ? s->resampler->getNObservations() : 0; }
+
+extern "C" int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size) {
+    BFH_TRY
+    *size = s->analyzer->resamplingSize(kind, n);
+    BFH_CATCH
+}
+
+extern "C" int bfh_bootstrap_counts(bfh_session *s, int size, unsigned long long seed, long trial, int *counts) {
+    BFH_TRY
+    if (!s->resampler) throw RuntimeError("bfh_bootstrap_counts: the session has no individual observations.");
+    std::vector<int> c = s->resampler->bootstrapCounts(size, seed, trial);
+    std::copy(c.begin(), c.end(), counts);
+    BFH_CATCH
+}
+
+extern "C" int bfh_resample_data(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
+                                 long seqno, double *data, double *cov) {
+    BFH_TRY
+    AbsCorrelationDataPtr sample = s->analyzer->resample(kind, n, size, fix_covariance != 0, seed, seqno);
+    if (sample->keptIndices() != s->data->keptIndices()) throw RuntimeError("bfh_resample_data: the sample keeps different bins.");
+    if (data) { std::vector<double> d = sample->dataVector(); std::copy(d.begin(), d.end(), data); }
+    if (cov) { std::vector<double> c = sample->covarianceMatrix(); std::copy(c.begin(), c.end(), cov); }
+    BFH_CATCH
+}
+
+extern "C" int bfh_resample_fit(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
+                                long first, long count, double *fitted, double *chi2, int *status) {
+    BFH_TRY
+    std::vector<std::vector<double>> fit;
+    std::vector<double> c;
+    std::vector<int> st;
+    long done = s->analyzer->doResampling(kind, n, size, fix_covariance != 0, seed, first, count, fit, c, st);
+    int npar = s->model->getNParameters();
+    for (long t = 0; t < done; ++t) {
         if (fitted) std::copy(fit[t].begin(), fit[t].end(), fitted + (size_t)t * npar);
         if (chi2) chi2[t] = c[t];
         if (status) status[t] = st[t];

@@ -68,10 +68,37 @@ AbsCorrelationData::~AbsCorrelationData() {
     if (_device) bf_data_destroy(_device);
 }
 
-void AbsCorrelationData::setData(int index, double value) {
+void AbsCorrelationData::setData(int index, double value, bool weighted) {
     if (_finalized) throw RuntimeError("AbsCorrelationData: data is finalized.");
     if (index < 0 || index >= _grid.getNBinsTotal()) throw RuntimeError("AbsCorrelationData::setData: invalid bin index.");
+    if (!_values.empty() && weighted != _weighted) throw RuntimeError("AbsCorrelationData::setData: cannot mix weighted and unweighted data.");
+    _weighted = weighted;
     _values[index] = value;
+}
+
+void AbsCorrelationData::setCustomBinCenters(int index, double c1, double c2, double c3) {
+    if (_finalized) throw RuntimeError("AbsCorrelationData: data is finalized.");
+    if (index < 0 || index >= _grid.getNBinsTotal()) throw RuntimeError("AbsCorrelationData::setCustomBinCenters: invalid bin index.");
+    _custom[index] = {{c1, c2, c3}};
+}
+
+void AbsCorrelationData::enableCustomGrid() {
+    if (getNCustomBins() != _grid.getNBinsTotal())
+        throw RuntimeError("loadCorrelationData: number of custom bins must match the number of default bins.");
+    _useCustom = true;
+}
+
+void AbsCorrelationData::copyCustomGridFrom(AbsCorrelationData const &other) {
+    _custom = other._custom;
+    _useCustom = other._useCustom;
+}
+
+void AbsCorrelationData::getBinCenters(int index, double centers[3]) const {
+    if (_useCustom) {
+        auto const &c = _custom.at(index);
+        centers[0] = c[0]; centers[1] = c[1]; centers[2] = c[2];
+    } else
+        _grid.getBinCenters(index, centers);
 }
 
 double AbsCorrelationData::getData(int index) const {
@@ -115,6 +142,22 @@ void AbsCorrelationData::setFinalCuts(double rMin, double rMax, double rVetoMin,
     _haveFinalCuts = true;
 }
 
+namespace {
+// inverse of a dense symmetric positive definite matrix through its Cholesky factor
+std::vector<double> spdInverse(int n, std::vector<double> a, const char *what) {
+    if (!bf::cholesky_lower(n, a.data())) throw RuntimeError(std::string("AbsCorrelationData: ") + what + " is not positive definite");
+    std::vector<double> li((size_t)n * n, 0.0), out((size_t)n * n, 0.0);
+    bf::invert_lower(n, a.data(), li.data());
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = 0;
+            for (int k = i; k < n; ++k) s += li[(size_t)k * n + i] * li[(size_t)k * n + j];  // (L^-T L^-1)_ij
+            out[(size_t)i * n + j] = out[(size_t)j * n + i] = s;
+        }
+    return out;
+}
+}  // namespace
+
 void AbsCorrelationData::finalize() {
     if (_finalized) return;
     if (!_haveFinalCuts) throw RuntimeError("AbsCorrelationData: no final cuts specified yet.");
@@ -142,6 +185,34 @@ void AbsCorrelationData::finalize() {
     }
     if (_kept.empty()) throw RuntimeError("CorrelationFitter: need some data to fit.");
     if (!_haveCov) throw RuntimeError("AbsCorrelationData: no covariance loaded.");
+    const bool pruned = _kept.size() < _values.size();
+    if (_weighted || (_isInverse && pruned)) {
+        // Both steps need the covariance over ALL bins with data. Weighted values are elements of Cinv.d, so
+        // d = C.(Cinv.d). Dropping bins from a data set whose matrix was given as an inverse means marginalising
+        // over them, i.e. taking the sub-block of the covariance, not of its inverse (likely::BinnedData::prune
+        // works on the covariance representation; UNVERIFIED (dep), but the only choice that keeps the
+        // likelihood of the kept bins unchanged).
+        std::vector<int> bins = binsWithData();
+        const int n = (int)bins.size();
+        std::vector<double> m = denseOverBinsWithData();
+        std::vector<double> cov = _isInverse ? spdInverse(n, m, "the inverse covariance") : m;
+        if (_weighted) {
+            std::vector<double> w(n);
+            for (int i = 0; i < n; ++i) w[i] = _values.at(bins[i]);
+            for (int i = 0; i < n; ++i) {
+                double sum = 0;
+                for (int j = 0; j < n; ++j) sum += cov[(size_t)i * n + j] * w[j];
+                _values[bins[i]] = sum;
+            }
+            _weighted = false;
+        }
+        if (_isInverse && pruned) {
+            _cov.clear();
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j <= i; ++j) _cov[std::make_pair(std::min(bins[i], bins[j]), std::max(bins[i], bins[j]))] = cov[(size_t)i * n + j];
+            _isInverse = false;
+        }
+    }
     _finalized = true;
 }
 
@@ -224,7 +295,7 @@ ComovingCorrelationData::ComovingCorrelationData(BinnedGrid grid, CoordinateSyst
 
 double ComovingCorrelationData::getRadius(int index) const {
     double c[3];
-    _grid.getBinCenters(index, c);
+    getBinCenters(index, c);
     if (_coordinateSystem == CartesianCoordinates) {
         double rpar = c[0], rperp = c[1];
         return std::sqrt(rpar * rpar + rperp * rperp);
@@ -234,7 +305,7 @@ double ComovingCorrelationData::getRadius(int index) const {
 
 double ComovingCorrelationData::getCosAngle(int index) const {
     double c[3];
-    _grid.getBinCenters(index, c);
+    getBinCenters(index, c);
     if (_coordinateSystem == PolarCoordinates) return c[1];
     if (_coordinateSystem == CartesianCoordinates) {
         double rpar = c[0], rperp = c[1];
@@ -245,61 +316,149 @@ double ComovingCorrelationData::getCosAngle(int index) const {
 
 int ComovingCorrelationData::getMultipole(int index) const {
     double c[3];
-    _grid.getBinCenters(index, c);
+    getBinCenters(index, c);
     if (_coordinateSystem == MultipoleCoordinates) return (int)std::floor(c[1] + 0.5);
     throw RuntimeError("ComovingCorrelationData::getMultipole: invalid coordinate system.");
 }
 
 double ComovingCorrelationData::getRedshift(int index) const {
     double c[3];
-    _grid.getBinCenters(index, c);
+    getBinCenters(index, c);
     return c[2];
 }
 
-namespace {
-// inverse of a dense symmetric positive definite matrix through its Cholesky factor
-std::vector<double> spdInverse(int n, std::vector<double> a, const char *what) {
-    if (!bf::cholesky_lower(n, a.data())) throw RuntimeError(std::string("combineCorrelationData: ") + what + " is not positive definite");
-    std::vector<double> li((size_t)n * n, 0.0), out((size_t)n * n, 0.0);
-    bf::invert_lower(n, a.data(), li.data());
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double s = 0;
-            for (int k = i; k < n; ++k) s += li[(size_t)k * n + i] * li[(size_t)k * n + j];  // (L^-T L^-1)_ij
-            out[(size_t)i * n + j] = out[(size_t)j * n + i] = s;
-        }
-    return out;
-}
-}  // namespace
 
-void combineCorrelationData(std::vector<AbsCorrelationDataPtr> const &observations, AbsCorrelationData &into) {
-    if (observations.empty()) throw RuntimeError("combineCorrelationData: no observations.");
-    std::vector<int> bins = observations[0]->binsWithData();
+// ------------------------------------------------------------------------------------------
+// BinnedDataResampler
+// ------------------------------------------------------------------------------------------
+void BinnedDataResampler::addObservation(AbsCorrelationDataPtr obs) {
+    if (!obs) throw RuntimeError("BinnedDataResampler: null observation.");
+    std::vector<int> bins = obs->binsWithData();
+    if (_icov.empty()) { _bins = bins; _first = obs; }
+    else if (bins != _bins) throw RuntimeError("combineCorrelationData: observations are not congruent.");
     const int n = (int)bins.size();
-    std::vector<double> icovSum((size_t)n * n, 0.0), icovData(n, 0.0);
-    for (auto const &obs : observations) {
-        if (obs->binsWithData() != bins) throw RuntimeError("combineCorrelationData: observations are not congruent.");
-        std::vector<double> m = obs->denseOverBinsWithData();
-        std::vector<double> icov = obs->isInverse() ? m : spdInverse(n, m, "a covariance");
-        for (size_t k = 0; k < icov.size(); ++k) icovSum[k] += icov[k];
-        for (int i = 0; i < n; ++i) {
-            double s = 0;
-            for (int j = 0; j < n; ++j) s += icov[(size_t)i * n + j] * obs->getData(bins[j]);
-            icovData[i] += s;
-        }
+    std::vector<double> m = obs->denseOverBinsWithData();
+    std::vector<double> icov = obs->isInverse() ? m : spdInverse(n, m, "a covariance");
+    std::vector<double> wd(n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        if (obs->isWeighted()) { wd[i] = obs->getData(bins[i]); continue; }  // ".wdata": already Cinv.d
+        double s = 0;
+        for (int j = 0; j < n; ++j) s += icov[(size_t)i * n + j] * obs->getData(bins[j]);
+        wd[i] = s;
+    }
+    _icov.push_back(std::move(icov));
+    _icovData.push_back(std::move(wd));
+}
+
+AbsCorrelationDataPtr BinnedDataResampler::combine(std::vector<int> const &counts, bool fixCovariance) const {
+    if ((int)counts.size() != getNObservations()) throw RuntimeError("BinnedDataResampler::combine: one count per observation expected.");
+    const int n = (int)_bins.size();
+    std::vector<double> icovSum((size_t)n * n, 0.0), icovSq, icovData(n, 0.0);
+    bool repeated = false, any = false;
+    for (int c : counts) { if (c < 0) throw RuntimeError("BinnedDataResampler::combine: negative count."); repeated |= c > 1; any |= c > 0; }
+    if (!any) throw RuntimeError("BinnedDataResampler::combine: no observations.");
+    const bool fix = fixCovariance && repeated;
+    if (fix) icovSq.assign((size_t)n * n, 0.0);
+    for (size_t k = 0; k < counts.size(); ++k) {
+        if (counts[k] == 0) continue;
+        const double w = counts[k];
+        for (size_t q = 0; q < icovSum.size(); ++q) icovSum[q] += w * _icov[k][q];
+        if (fix)
+            for (size_t q = 0; q < icovSq.size(); ++q) icovSq[q] += w * w * _icov[k][q];
+        for (int i = 0; i < n; ++i) icovData[i] += w * _icovData[k][i];
     }
     std::vector<double> cov = spdInverse(n, icovSum, "the summed inverse covariance");
+    AbsCorrelationDataPtr out = _prototype();
     for (int i = 0; i < n; ++i) {
         double s = 0;
         for (int j = 0; j < n; ++j) s += cov[(size_t)i * n + j] * icovData[j];
-        into.setData(bins[i], s);
+        out->setData(_bins[i], s);
+    }
+    if (fix) {  // C (sum n_k^2 Cinv_k) C
+        std::vector<double> t((size_t)n * n, 0.0), f((size_t)n * n, 0.0);
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) {
+                const double a = cov[(size_t)i * n + k];
+                for (int j = 0; j < n; ++j) t[(size_t)i * n + j] += a * icovSq[(size_t)k * n + j];
+            }
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) {
+                const double a = t[(size_t)i * n + k];
+                for (int j = 0; j < n; ++j) f[(size_t)i * n + j] += a * cov[(size_t)k * n + j];
+            }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j <= i; ++j) cov[(size_t)i * n + j] = cov[(size_t)j * n + i] = 0.5 * (f[(size_t)i * n + j] + f[(size_t)j * n + i]);
     }
     for (int i = 0; i < n; ++i)
-        for (int j = 0; j <= i; ++j) into.setCovariance(bins[i], bins[j], cov[(size_t)i * n + j]);
+        for (int j = 0; j <= i; ++j) out->setCovariance(_bins[i], _bins[j], cov[(size_t)i * n + j]);
+    if (_first->useCustomGrid()) out->copyCustomGridFrom(*_first);
+    return out;
 }
 
-void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov) {
-    std::string paramsName = dataName + ".data";
+AbsCorrelationDataPtr BinnedDataResampler::combined() const {
+    return combine(std::vector<int>(getNObservations(), 1), false);
+}
+
+static long binomial(int n, int k) {
+    if (k < 0 || k > n) return 0;
+    double c = 1;
+    for (int i = 1; i <= k; ++i) c = c * (n - k + i) / i;
+    return c > 9e18 ? (long)9e18 : (long)(c + 0.5);
+}
+
+long BinnedDataResampler::jackknifeSize(int nobs, int ndrop) {
+    if (ndrop <= 0 || ndrop >= nobs) return 0;  // at least one observation is dropped and one is left
+    return binomial(nobs, ndrop);
+}
+
+AbsCorrelationDataPtr BinnedDataResampler::jackknife(int ndrop, long seqno) const {
+    const int nobs = getNObservations();
+    if (seqno < 0 || seqno >= jackknifeSize(nobs, ndrop)) return AbsCorrelationDataPtr();
+    // seqno-th ndrop-subset of {0..nobs-1} in lexicographic order
+    std::vector<int> counts(nobs, 1);
+    long rank = seqno;
+    int next = 0;
+    for (int slot = 0; slot < ndrop; ++slot)
+        for (int c = next; c < nobs; ++c) {
+            const long with_c = binomial(nobs - c - 1, ndrop - slot - 1);  // subsets whose slot-th element is c
+            if (rank < with_c) { counts[c] = 0; next = c + 1; break; }
+            rank -= with_c;
+        }
+    return combine(counts, false);
+}
+
+std::vector<int> BinnedDataResampler::bootstrapCounts(int size, unsigned long long seed, long trial) const {
+    const int nobs = getNObservations();
+    if (size <= 0) size = nobs;
+    std::vector<int> counts(nobs, 0);
+    // splitmix64 on (seed, trial, draw): independent of how trials are distributed over ranks
+    auto mix = [](unsigned long long z) {
+        z += 0x9e3779b97f4a7c15ULL;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return z ^ (z >> 31);
+    };
+    const unsigned long long key = mix(mix(seed) ^ (unsigned long long)trial);
+    for (int q = 0; q < size; ++q) {
+        unsigned long long u = mix(key + (unsigned long long)q * 0x9e3779b97f4a7c15ULL);
+        counts[(int)((u >> 11) * (1.0 / 9007199254740992.0) * nobs)]++;
+    }
+    return counts;
+}
+
+AbsCorrelationDataPtr BinnedDataResampler::bootstrap(int size, bool fixCovariance, unsigned long long seed, long trial) const {
+    return combine(bootstrapCounts(size, seed, trial), fixCovariance);
+}
+
+AbsCorrelationDataPtr BinnedDataResampler::getObservationCopy(int index) const {
+    if (index < 0 || index >= getNObservations()) throw RuntimeError("BinnedDataResampler::getObservationCopy: bad index.");
+    std::vector<int> counts(getNObservations(), 0);
+    counts[index] = 1;
+    return combine(counts, false);
+}
+
+void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, bool icov, bool weighted, bool customGrid) {
+    std::string paramsName = dataName + (weighted ? ".wdata" : ".data");
     std::ifstream in(paramsName.c_str());
     if (!in.good()) throw RuntimeError("loadCorrelationData: Unable to open " + paramsName);
     std::string line;
@@ -312,7 +471,7 @@ void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, 
         // first two tokens only: trailing junk is accepted like the reference's phrase_parse
         if (!(ss >> index >> value))
             throw RuntimeError("loadCorrelationData: error reading line " + std::to_string(lines) + " of " + paramsName);
-        data.setData(index, value);
+        data.setData(index, value, weighted);
     }
     in.close();
     int nbins = data.getGrid().getNBinsTotal();
@@ -331,6 +490,24 @@ void loadCorrelationData(std::string const &dataName, AbsCorrelationData &data, 
             throw RuntimeError("loadCorrelationData: invalid covariance indices on line " + std::to_string(lines) + " of " + covName);
         if (icov) data.setInverseCovariance(i1, i2, value);
         else data.setCovariance(i1, i2, value);
+    }
+    if (customGrid) {  // AbsCorrelationData.cc:243-274
+        std::string gridName = dataName + ".grid";
+        std::ifstream gin(gridName.c_str());
+        if (!gin.good()) throw RuntimeError("loadCorrelationData: Unable to open " + gridName);
+        lines = 0;
+        while (std::getline(gin, line)) {
+            lines++;
+            std::istringstream ss(line);
+            int index;
+            double c1, c2, c3;
+            if (!(ss >> index >> c1 >> c2 >> c3))
+                throw RuntimeError("loadCorrelationData: error reading line " + std::to_string(lines) + " of " + gridName);
+            if (index < 0 || index >= nbins)
+                throw RuntimeError("loadCorrelationData: invalid bin index on line " + std::to_string(lines) + " of " + gridName);
+            data.setCustomBinCenters(index, c1, c2, c3);
+        }
+        data.enableCustomGrid();
     }
 }
 
@@ -402,7 +579,7 @@ void QuasarCorrelationData::transform(double ll, double sep, double dsep, double
 void QuasarCorrelationData::_setIndex(int index) const {
     if (index == _lastIndex) return;
     double c[3], w[3];
-    _grid.getBinCenters(index, c);
+    getBinCenters(index, c);
     _grid.getBinWidths(index, w);
     _zLast = c[2];
     transform(c[0], c[1], w[1], _zLast, _rLast, _muLast);
@@ -415,7 +592,7 @@ double QuasarCorrelationData::getRedshift(int index) const { _setIndex(index); r
 
 bool QuasarCorrelationData::extraCut(int index) const {
     double c[3];
-    _grid.getBinCenters(index, c);
+    getBinCenters(index, c);
     double ll(c[0]), sep(c[1]);
     return ll < _llMin || ll > _llMax || sep < _sepMin || sep > _sepMax;
 }

@@ -425,7 +425,7 @@ void CorrelationAnalyzer::dumpResiduals(std::ostream &out, likely::FunctionMinim
     for (size_t i = 0; i < kept.size(); ++i) {
         const int index = kept[i];
         double c[3];
-        _data->getGrid().getBinCenters(index, c);
+        _data->getBinCenters(index, c);  // custom centres if present, CorrelationAnalyzer.cc:630-635
         out << index << ' ' << num(c[0]) << ' ' << num(c[1]) << ' ' << num(c[2]) << ' ' << num(_data->getRadius(index)) << ' ';
         if (coord) out << num(_data->getCosAngle(index));
         else out << _data->getMultipole(index);
@@ -594,7 +594,7 @@ Options parseIni(std::string const &text) {
                                      "no-distortion", "bin-smooth", "bin-smooth-alt", "hcd-model", "hcd-model-alt",
                                      "uvfluctuation", "radiation-model", "smooth-gauss", "smooth-lorentz", "dist-matrix",
                                      "metal-model", "metal-model-interpolate", "metal-civ", "toy-metal", "combined-bias",
-                                     "combined-scale", "cross-correlation", "load-icov", "custom-grid", "parameter-scan",
+                                     "combined-scale", "cross-correlation", "load-icov", "load-wdata", "custom-grid", "parameter-scan",
                                      "verbose", "quiet"};
     Options o;
     std::stringstream ss(text);
@@ -679,10 +679,10 @@ AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDi
     return model;
 }
 
-AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir) {
+AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir, BinnedDataResamplerPtr *resamplerOut) {
     std::string fmt = opt.str("data-format");
     BinnedGrid grid = createCorrelationGrid(opt.str("axis1-bins"), opt.str("axis2-bins"), opt.str("axis3-bins"));
-    auto prototype = [&]() -> AbsCorrelationDataPtr {
+    auto bare = [opt, fmt, grid]() -> AbsCorrelationDataPtr {
         if (fmt == "comoving-cartesian") return AbsCorrelationDataPtr(new ComovingCorrelationData(grid, ComovingCorrelationData::CartesianCoordinates));
         if (fmt == "comoving-polar") return AbsCorrelationDataPtr(new ComovingCorrelationData(grid, ComovingCorrelationData::PolarCoordinates));
         if (fmt == "comoving-multipole") return AbsCorrelationDataPtr(new ComovingCorrelationData(grid, ComovingCorrelationData::MultipoleCoordinates));
@@ -695,34 +695,95 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir)
         }
         throw RuntimeError("data-format '" + fmt + "' is not supported by this build (comoving-cartesian, comoving-polar, comoving-multipole, quasar)");
     };
-    AbsCorrelationDataPtr data = prototype();
     // src/baofit.cc:510 with the defaults of :216-247
-    double rVetoWidth = opt.num("rveto-width", 0), rVetoCenter = opt.num("rveto-center", 114);
-    data->setFinalCuts(opt.num("rmin", 0), opt.num("rmax", 200), rVetoCenter - 0.5 * rVetoWidth, rVetoCenter + 0.5 * rVetoWidth,
-                       opt.num("mu-min", -1), opt.num("mu-max", 1), opt.num("rperp-min", 0), opt.num("rperp-max", 200),
-                       opt.num("rpar-min", -200), opt.num("rpar-max", 200), (int)opt.num("lmin", 0), (int)opt.num("lmax", 2),
-                       opt.num("z-min", 0), opt.num("z-max", 10));
+    auto prototype = [opt, bare]() -> AbsCorrelationDataPtr {
+        AbsCorrelationDataPtr p = bare();
+        double rVetoWidth = opt.num("rveto-width", 0), rVetoCenter = opt.num("rveto-center", 114);
+        p->setFinalCuts(opt.num("rmin", 0), opt.num("rmax", 200), rVetoCenter - 0.5 * rVetoWidth, rVetoCenter + 0.5 * rVetoWidth,
+                        opt.num("mu-min", -1), opt.num("mu-max", 1), opt.num("rperp-min", 0), opt.num("rperp-max", 200),
+                        opt.num("rpar-min", -200), opt.num("rpar-max", 200), (int)opt.num("lmin", 0), (int)opt.num("lmax", 2),
+                        opt.num("z-min", 0), opt.num("z-max", 10));
+        return p;
+    };
+    AbsCorrelationDataPtr data;
     if (!opt.str("data").empty()) {
-        loadCorrelationData(resolve(baseDir, opt.str("data")), *data, opt.flag("load-icov"));
+        data = prototype();
+        loadCorrelationData(resolve(baseDir, opt.str("data")), *data, opt.flag("load-icov"), opt.flag("load-wdata"), opt.flag("custom-grid"));
     } else {
         // individual observations named by plateroot + platelist (src/baofit.cc:531-583), combined with
         // inverse-covariance weights like likely::BinnedDataResampler::combined
         std::string root = resolve(baseDir, opt.str("plateroot")), listName = root + opt.str("platelist");
         std::ifstream list(listName.c_str());
         if (!list.good()) throw RuntimeError("Unable to open platelist file " + listName);
-        std::vector<AbsCorrelationDataPtr> plates;
+        BinnedDataResamplerPtr resampler(new BinnedDataResampler(prototype));
         std::string plateName;
         int maxPlates = (int)opt.num("max-plates", 0);
         while (list >> plateName) {
             AbsCorrelationDataPtr plate = prototype();
-            loadCorrelationData(root + plateName, *plate, opt.flag("load-icov"));
-            plates.push_back(plate);
-            if (maxPlates > 0 && (int)plates.size() == maxPlates) break;
+            loadCorrelationData(root + plateName, *plate, opt.flag("load-icov"), opt.flag("load-wdata"), opt.flag("custom-grid"));
+            resampler->addObservation(plate);
+            if (maxPlates > 0 && resampler->getNObservations() == maxPlates) break;
         }
-        combineCorrelationData(plates, *data);
+        if (resampler->getNObservations() == 0) throw RuntimeError("combineCorrelationData: no observations.");
+        data = resampler->combined();
+        if (resamplerOut) *resamplerOut = resampler;
     }
     data->finalize();
     return data;
+}
+
+// ---- resampling analyses ----------------------------------------------------------------------
+long CorrelationAnalyzer::resamplingSize(std::string const &kind, int n) const {
+    if (!_resampler || _resampler->getNObservations() <= 1) throw RuntimeError("CorrelationAnalyzer: resampling needs > 1 observation (plateroot/platelist).");
+    if (kind == "jackknife") {
+        if (n <= 0) throw RuntimeError("CorrelationAnalyzer::doJackknifeAnalysis: expected jackknifeDrop > 0.");
+        return BinnedDataResampler::jackknifeSize(_resampler->getNObservations(), n);
+    }
+    if (kind == "bootstrap") {
+        if (n <= 0) throw RuntimeError("CorrelationAnalyzer::doBootstrapAnalysis: expected bootstrapTrials > 0.");
+        return n;
+    }
+    if (kind == "each") return _resampler->getNObservations();
+    throw RuntimeError("CorrelationAnalyzer: unknown resampling kind '" + kind + "' (jackknife, bootstrap, each).");
+}
+
+AbsCorrelationDataPtr CorrelationAnalyzer::resample(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed,
+                                                    long seqno) const {
+    long total = resamplingSize(kind, n);
+    if (seqno < 0 || seqno >= total) throw RuntimeError("CorrelationAnalyzer: resampling sequence number out of range.");
+    if (size < 0) throw RuntimeError("CorrelationAnalyzer::doBootstrapAnalysis: expected bootstrapSize >= 0.");
+    AbsCorrelationDataPtr sample;
+    if (kind == "jackknife") sample = _resampler->jackknife(n, seqno);  // non-null: seqno < resamplingSize
+    else if (kind == "bootstrap") sample = _resampler->bootstrap(size, fixCovariance, seed, seqno);
+    else sample = _resampler->getObservationCopy((int)seqno);
+    sample->finalize();
+    return sample;
+}
+
+long CorrelationAnalyzer::doResampling(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long first,
+                                       long count, std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
+                                       std::vector<int> &status) const {
+    long total = resamplingSize(kind, n);
+    if (count < 0) count = total - first;
+    if (first < 0 || first + count > total) throw RuntimeError("CorrelationAnalyzer: bad resampling range.");
+    fitted.clear(); chi2.clear(); status.clear();
+    for (long q = first; q < first + count; ++q) {
+        AbsCorrelationDataPtr sample = resample(kind, n, size, fixCovariance, seed, q);
+        // a failed fit is recorded, not fatal (CorrelationAnalyzer.cc:486-489 swallows per-fit errors)
+        try {
+            likely::FunctionMinimumPtr fm = fitSample(sample);
+            std::vector<double> v;
+            for (auto const &p : fm->parameters) v.push_back(p.value);
+            fitted.push_back(v);
+            chi2.push_back(2 * fm->minValue);
+            status.push_back((int)fm->status);
+        } catch (std::runtime_error const &e) {
+            fitted.push_back(std::vector<double>(_model->getNParameters(), std::nan("")));
+            chi2.push_back(std::nan(""));
+            status.push_back((int)likely::FunctionMinimum::ERROR);
+        }
+    }
+    return count;
 }
 
 }  // namespace baofit

@@ -12,7 +12,8 @@ RESID_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_doubl
 HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
-                "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc"]
+                "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
+                "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit"]
 
 
 def lib():
@@ -46,6 +47,13 @@ def lib():
         L.bfh_lm_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, RESID_FN,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]
+        L.bfh_nobservations.argtypes = [C.c_void_p]
+        L.bfh_resampling_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long)]
+        L.bfh_bootstrap_counts.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p]
+        L.bfh_resample_data.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p,
+                                        C.c_void_p]
+        L.bfh_resample_fit.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_long, C.c_long,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
         _BOUND = True
     return L
 
@@ -172,6 +180,36 @@ class Session:
         fitted, chi2 = np.zeros((count, self.npar)), np.zeros(count)
         st = np.zeros(count, dtype=np.int32)
         _check(lib().bfh_toymc(self.h, first, count, seed, _p(fitted), _p(chi2), _p(st)))
+        return dict(fitted=fitted, chi2=chi2, status=st)
+
+
+    # ---- jackknife / bootstrap / fit-each over the observations of a plateroot/platelist session ----
+    @property
+    def nobservations(self):
+        return lib().bfh_nobservations(self.h)
+
+    def resampling_size(self, kind, n=0):
+        out = C.c_long()
+        _check(lib().bfh_resampling_size(self.h, kind.encode(), n, C.byref(out)))
+        return out.value
+
+    def bootstrap_counts(self, trial, size=0, seed=1966):
+        counts = np.zeros(self.nobservations, dtype=np.int32)
+        _check(lib().bfh_bootstrap_counts(self.h, size, seed, trial, _p(counts)))
+        return counts
+
+    def resample_data(self, kind, seqno, n=0, size=0, fix_covariance=False, seed=1966):
+        d, c = np.zeros(self.ndata), np.zeros((self.ndata, self.ndata))
+        _check(lib().bfh_resample_data(self.h, kind.encode(), n, size, int(fix_covariance), seed, seqno, _p(d), _p(c)))
+        return d, c
+
+    def resample_fit(self, kind, n=0, size=0, fix_covariance=False, seed=1966, first=0, count=-1):
+        if count < 0:
+            count = self.resampling_size(kind, n) - first
+        fitted, chi2 = np.zeros((count, self.npar)), np.zeros(count)
+        st = np.zeros(count, dtype=np.int32)
+        _check(lib().bfh_resample_fit(self.h, kind.encode(), n, size, int(fix_covariance), seed, first, count, _p(fitted), _p(chi2),
+                                      _p(st)))
         return dict(fitted=fitted, chi2=chi2, status=st)
 
 

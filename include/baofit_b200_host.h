@@ -61,6 +61,20 @@ int bfh_parameter_scan(bfh_session *s, long first, long count, double *chi2, dou
 /* CorrelationAnalyzer::doToyMCSampling for toys [first, first+count): fitted[count*npar], chi2, status */
 int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
               int *status);
+/* Resampling analyses over the individual observations of a plateroot/platelist session
+ * (CorrelationAnalyzer::doJackknifeAnalysis / doBootstrapAnalysis / fitEach, CorrelationAnalyzer.cc:301-335, through
+ * likely::BinnedDataResampler). kind = "jackknife" (n = observations dropped per sample), "bootstrap" (n = trials,
+ * size = draws per trial with replacement, 0 = number of observations; fix_covariance: account for repeated
+ * observations in the sample covariance), "each" (one sample per observation). bfh_resample_data returns the kept
+ * data vector [ndata] and covariance [ndata*ndata] of sample seqno (either may be NULL); bfh_resample_fit refits
+ * samples [first, first+count) (count < 0: to the end): fitted[count*npar], chi2 = 2*fval, status. */
+int bfh_nobservations(const bfh_session *s);
+int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size);
+int bfh_bootstrap_counts(bfh_session *s, int size, unsigned long long seed, long trial, int *counts /* [nobservations] */);
+int bfh_resample_data(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
+                      long seqno, double *data, double *cov);
+int bfh_resample_fit(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
+                     long first, long count, double *fitted, double *chi2, int *status);
 
 /* CorrelationAnalyzer::dumpResiduals (CorrelationAnalyzer.cc:607-676) at the given parameter values / errors
  * into the text file `path`; CorrelationAnalyzer::dumpModel (:678-716): multipoles[ndump*3] = mono, quad, hexa

@@ -104,3 +104,57 @@ def test_lm_driver_on_cpu_residuals():
     nwp = H.minimize(lambda p: 0.5 * (resid(p) ** 2).sum(axis=1) + 0.5 * ((p[:, 2] - 0.5) / 1e-3) ** 2, start, err, [1, 1, 1])
     assert abs(pr["fval"] - nwp["fval"]) < 1e-5 and np.allclose(pr["values"], nwp["values"], atol=1e-5)
     assert abs(pr["values"][2] - 0.5) < 0.05 and pr["fval"] > lm["fval"]
+
+
+def _qso_files(tmp_path):
+    """BOSSDR11QSOLyaF data/cov over all 512 bins, rewritten under tmp_path in the loader's optional formats."""
+    a1, a2, a3 = W.parse_binning(W.QSO_AXIS1), W.parse_binning(W.QSO_AXIS2), W.parse_binning(W.QSO_AXIS3)
+    n = len(a1) * len(a2) * len(a3)
+    val, has = W.load_data_vector(os.path.join(W.GOLDEN, "data", "BOSSDR11QSOLyaF.data"), n)
+    cov = W.load_cov(os.path.join(W.GOLDEN, "data", "BOSSDR11QSOLyaF.cov.gz"), n)
+    assert has.all()
+    icov = np.linalg.inv(cov)
+    prefix = str(tmp_path / "X")
+    idx = np.arange(n)
+    np.savetxt(prefix + ".data", np.column_stack([idx, val]), fmt="%d %.17g")
+    np.savetxt(prefix + ".wdata", np.column_stack([idx, icov @ val]), fmt="%d %.17g")
+    i, j = np.tril_indices(n)
+    np.savetxt(prefix + ".cov", np.column_stack([i, j, cov[i, j]]), fmt="%d %d %.17g")
+    np.savetxt(prefix + ".icov", np.column_stack([i, j, 0.5 * (icov + icov.T)[i, j]]), fmt="%d %d %.17g")
+    centres = np.array([[x, y, zz] for x in a1 for y in a2 for zz in a3])
+    return prefix, centres, (a1, a2, a3)
+
+
+def test_weighted_data_inverse_covariance_and_custom_grid(built, golden_tree, tmp_path):
+    """loadCorrelationData's optional inputs (baofit/AbsCorrelationData.cc:156-277): .wdata (Cinv.d), .icov with
+    bins dropped by the final cuts (pruning marginalises: sub-block of the covariance), custom bin centres."""
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF.ini")
+    prefix, centres, axes = _qso_files(tmp_path)
+    text = text.replace("data = ../data/BOSSDR11QSOLyaF", "data = " + prefix)
+    s0 = H.Session(text, base)
+    d0, c0 = s0.data_vector(), s0.covariance()
+    assert s0.ndata == 440
+    sw = H.Session(text + "\nload-wdata = yes\n", base)
+    assert np.allclose(sw.data_vector(), d0, rtol=1e-8, atol=1e-12 * np.abs(d0).max()) and np.array_equal(sw.covariance(), c0)
+    si = H.Session(text + "\nload-icov = yes\n", base)
+    assert np.allclose(si.covariance(), c0, rtol=1e-6, atol=1e-9 * np.abs(c0).max())
+    assert np.array_equal(si.data_vector(), d0)
+    swi = H.Session(text + "\nload-icov = yes\nload-wdata = yes\n", base)
+    assert np.allclose(swi.data_vector(), d0, rtol=1e-6, atol=1e-9 * np.abs(d0).max())
+    # custom centres equal to the grid's: nothing changes; halved separations: the cuts see the new radii
+    np.savetxt(prefix + ".grid", np.column_stack([np.arange(len(centres)), centres]), fmt="%d %.17g %.17g %.17g")
+    sg = H.Session(text + "\ncustom-grid = yes\n", base)
+    assert sg.ndata == 440 and all(np.array_equal(a, b) for a, b in zip(sg.kept_coordinates(), s0.kept_coordinates()))
+    half = centres * np.array([0.5, 0.5, 1.0])
+    np.savetxt(prefix + ".grid", np.column_stack([np.arange(len(centres)), half]), fmt="%d %.17g %.17g %.17g")
+    sh = H.Session(text + "\ncustom-grid = yes\n", base)
+    r = np.hypot(half[:, 0], half[:, 1])
+    mu = half[:, 0] / r
+    keep = W.final_cuts(r, mu, half[:, 2], np.ones(len(r), bool), rmin=40, rmax=180)
+    rk, muk, zk = sh.kept_coordinates()
+    assert sh.ndata == len(keep) and np.array_equal(sh.kept_indices(), keep)
+    assert np.allclose(rk, r[keep], rtol=1e-15) and np.allclose(muk, mu[keep], rtol=1e-15, atol=1e-16)
+    # every grid bin needs a centre
+    np.savetxt(prefix + ".grid", np.column_stack([np.arange(len(centres) - 1), half[:-1]]), fmt="%d %.17g %.17g %.17g")
+    with pytest.raises(H.HostError, match="number of custom bins must match"):
+        H.Session(text + "\ncustom-grid = yes\n", base)

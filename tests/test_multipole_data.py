@@ -115,3 +115,94 @@ def test_host_platelist_combination_is_inverse_covariance_weighted(built, golden
         f.write("../demo/multi_0\n../demo/multi_1\n")
     with pytest.raises(H.HostError):
         H.Session(text.replace("obs.list", "bad.list"), base)
+
+
+def _write_observations(golden_tree, nobs, seed=21):
+    m, d0 = W.demo_multi(lmax=4)
+    keep, dv, cov = d0.keep._arrays[3], d0.keep._arrays[4], d0.keep._arrays[5]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    obs, names = [], []
+    for k in range(nobs):
+        ck = cov * (1.0 + 0.3 * k)
+        dk = dv + np.linalg.cholesky(ck) @ rng.standard_normal(len(dv))
+        W.write_dataset_files(os.path.join(golden_tree, "data", "rs_%d" % k), 87, keep, dk, ck)
+        obs.append((dk, ck))
+        names.append("rs_%d" % k)
+    with open(os.path.join(golden_tree, "data", "rs.list"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    base = os.path.join(golden_tree, "config")
+    text = open(os.path.join(base, "multi_to_bao.ini")).read() + "\nplateroot = ../data/\nplatelist = rs.list\nlmax = 4\n"
+    return text, base, obs
+
+
+def _combine(obs, counts, fix):
+    icov = [np.linalg.inv(c) for _, c in obs]
+    cinv = sum(n * ic for n, ic in zip(counts, icov))
+    c = np.linalg.inv(cinv)
+    d = c @ sum(n * ic @ dk for n, ic, (dk, _) in zip(counts, icov, obs))
+    if fix and max(counts) > 1:
+        c = c @ sum(n * n * ic for n, ic in zip(counts, icov)) @ c
+    return d, c
+
+
+def test_resampler_jackknife_bootstrap_each(built, golden_tree):
+    """Stand-in for likely::BinnedDataResampler as CorrelationAnalyzer.cc:213-260 uses it: jackknife subsets,
+    bootstrap draws with the repeated-observation covariance fix, single observations."""
+    text, base, obs = _write_observations(golden_tree, 5)
+    s = H.Session(text, base)
+    assert s.nobservations == 5 and s.ndata == 87
+    close = lambda a, b: np.max(np.abs(a - b)) < 1e-10 * np.max(np.abs(b))
+    # each
+    assert s.resampling_size("each") == 5
+    for k in range(5):
+        d, c = s.resample_data("each", k)
+        assert close(d, obs[k][0]) and close(c, obs[k][1])
+    # jackknife: every 2-subset dropped exactly once, in lexicographic order
+    assert s.resampling_size("jackknife", 1) == 5 and s.resampling_size("jackknife", 2) == 10
+    pairs = [(a, b) for a in range(5) for b in range(a + 1, 5)]
+    for q, (a, b) in enumerate(pairs):
+        counts = [0 if k in (a, b) else 1 for k in range(5)]
+        d, c = s.resample_data("jackknife", q, n=2)
+        dr, cr = _combine(obs, counts, False)
+        assert close(d, dr) and close(c, cr)
+    with pytest.raises(H.HostError):
+        s.resample_data("jackknife", 10, n=2)
+    # bootstrap: draws are a function of (seed, trial) only; the covariance fix matters when an observation repeats
+    seen_repeat = False
+    for trial in range(6):
+        counts = s.bootstrap_counts(trial, seed=7)
+        assert counts.sum() == 5 and np.array_equal(counts, s.bootstrap_counts(trial, seed=7))
+        for fix in (False, True):
+            d, c = s.resample_data("bootstrap", trial, n=6, fix_covariance=fix, seed=7)
+            dr, cr = _combine(obs, list(counts), fix)
+            assert close(d, dr) and close(c, cr)
+        seen_repeat |= counts.max() > 1
+    assert seen_repeat
+    assert s.bootstrap_counts(0, size=12, seed=7).sum() == 12
+    # a single-file session has nothing to resample
+    single = H.Session(text.replace("platelist = rs.list", "").replace("plateroot = ../data/", "data = ../data/rs_0"), base)
+    assert single.nobservations == 0
+    with pytest.raises(H.HostError, match="needs > 1 observation"):
+        single.resampling_size("each")
+
+
+@pytest.mark.gpu
+def test_resampling_fits_match_direct_sessions(built, golden_tree):
+    """bfh_resample_fit: the fit of jackknife sample k equals the fit of a session built from the platelist without
+    observation k; fit-each equals single-observation sessions."""
+    text, base, obs = _write_observations(golden_tree, 4, seed=22)
+    s = H.Session(text, base)
+    jk = s.resample_fit("jackknife", n=1)
+    assert np.all(jk["status"] == 0) and len(jk["chi2"]) == 4
+    for k in range(4):
+        with open(os.path.join(golden_tree, "data", "rs_drop.list"), "w") as f:
+            f.write("\n".join("rs_%d" % q for q in range(4) if q != k) + "\n")
+        r = H.Session(text.replace("rs.list", "rs_drop.list"), base).fit()
+        assert abs(2 * r["fval"] - jk["chi2"][k]) < 1e-6 * jk["chi2"][k]
+        assert np.max(np.abs(r["values"] - jk["fitted"][k])) < 1e-5
+    each = s.resample_fit("each", first=1, count=2)
+    for q, k in enumerate((1, 2)):
+        r = H.Session(text.replace("platelist = rs.list", "").replace("plateroot = ../data/", "data = ../data/rs_%d" % k), base).fit()
+        assert abs(2 * r["fval"] - each["chi2"][q]) < 1e-6 * each["chi2"][q]
+    bs = s.resample_fit("bootstrap", n=3, fix_covariance=True, seed=5)
+    assert np.all(np.isfinite(bs["chi2"])) and bs["fitted"].shape == (3, s.npar)
