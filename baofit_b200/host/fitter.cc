@@ -503,6 +503,8 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
                                           std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
                                           std::vector<int> &status, std::string const &toymcConfig) const {
     if (!_data || !_model) throw RuntimeError("CorrelationAnalyzer::doToyMCSampling: need data and a model.");
+    const bool verbose = std::getenv("BAOFIT_VERBOSE_FITS") != nullptr;
+    double tStart = nowSeconds();
     CorrelationFitter fitter(_data, _model, _covSampleSize);
     // truth = model prediction at the (optionally reconfigured) initial parameters (:362-369)
     likely::FitParameters truthParams = _model->getFitParameters();
@@ -517,13 +519,16 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
     bf_toys *toys = nullptr;
     check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, &toys), "bf_toys_create");
     std::shared_ptr<bf_toys> guard(toys, [](bf_toys *t) { bf_toys_destroy(t); });
+    double tToys = nowSeconds();
     // every toy is refitted from the model's initial configuration; all fits in lock step
     const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
     std::vector<likely::LMFit> fits((size_t)count, likely::LMFit(_model->getFitParameters(), cs, ps));
     std::vector<int> toyOfFit(count);
     for (long t = 0; t < count; ++t) toyOfFit[t] = (int)t;
     fitter.runLockStepLM(fits, toys, &toyOfFit);
+    double tLM = nowSeconds();
     std::vector<likely::FunctionMinimumPtr> results(count);
+    size_t nRedo = 0;
     {
         // toys whose LM fit did not converge cleanly are refitted with the Newton driver
         std::vector<likely::NewtonFit> redo;
@@ -532,6 +537,7 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
             results[t] = fits[t].result();
             if (results[t]->status != likely::FunctionMinimum::OK) { redo.push_back(likely::NewtonFit(_model->getFitParameters())); redoToy.push_back((int)t); }
         }
+        nRedo = redo.size();
         std::vector<likely::Parameters> points;
         std::vector<int> toyIndex;
         std::vector<double> values;
@@ -563,6 +569,9 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
                 results[redoToy[q]] = fm;
         }
     }
+    if (verbose)
+        std::fprintf(stderr, "doToyMCSampling: %ld toys: truth + realisations %.3f s, lock-step LM %.3f s, %zu Newton refits %.3f s\n", count,
+                     tToys - tStart, tLM - tToys, nRedo, nowSeconds() - tLM);
     fitted.clear(); chi2.clear(); status.clear();
     for (long t = 0; t < count; ++t) {
         likely::FunctionMinimumPtr fm = results[t];

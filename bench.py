@@ -152,6 +152,31 @@ def run_cpu(model, data, params, nthreads):
     return time.perf_counter() - t0, chi2
 
 
+def timed_studies(fn, world, dev, warm=1, reps=3):
+    """Scans and toy studies are sub-second bursts that follow seconds of host-only set-up (files, sessions), so a
+    single cold measurement mostly sees the GPU clocks ramping: `warm` untimed full studies, then the median of
+    `reps` timed ones (each bracketed by barrier + synchronize, max over ranks). Returns (seconds, all, result)."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warm):
+        fn()
+    times, res = [], None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt)
+    return sorted(times)[len(times) // 2], times, res
+
+
 def run_scan(rank, world, dev):
     """Second half of the BASELINE metric: 2-D (alpha_perp, alpha_parallel) scan points per second.
     Workload: config/BOSSDR11QSOLyaF.ini (60 x 35 = 2100 Minuit-style refits, 18 floating
@@ -165,21 +190,12 @@ def run_scan(rank, world, dev):
     text = open(os.path.join(tree, "config", "BOSSDR11QSOLyaF.ini")).read()
     s = host_api.Session(text, os.path.join(tree, "config"))
     s.parameter_scan(0, 2)  # warm-up: device upload, kernel load
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = shard.scan_sharded(s, dev if world > 1 else None)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt, times, res = timed_studies(lambda: shard.scan_sharded(s, dev if world > 1 else None), world, dev)
     pub = np.loadtxt(os.path.join(tree, "data", "BOSSDR11QSOLyaF.scan"))
     diff = (res["chi2"] - res["best_chi2"]) - pub[:, 2]
     return {"workload": "BOSSDR11QSOLyaF.ini r-space cross-correlation, 60x35 grid, 18 floating parameters per fit",
-            "points": int(len(res["chi2"])), "seconds": dt, "points_per_s": len(res["chi2"]) / dt,
+            "points": int(len(res["chi2"])), "seconds": dt, "seconds_all": times, "timing": "median of 3 scans after 1 warm-up scan",
+            "points_per_s": len(res["chi2"]) / dt,
             "chi2_min": float(res["best_chi2"]), "max_excess_over_published": float(diff.max()),
             "frac_within_1.5e-3_of_published": float(np.mean(np.abs(diff) < 1.5e-3)),
             "reference_seconds_per_fit": 1.7, "reference_source": "config/BOSSDR11QSOLyaF_k.ini:11-12 (hardware unspecified)"}
@@ -208,21 +224,12 @@ def run_scan_k(args, rank, world, dev, ctx):
     text = open(os.path.join(tree, "config", "BOSSDR11LyaF_k.ini")).read().replace("data = ../data/BOSSDR11LyaF", "data = ../data/BOSSDR11LyaF_synthk")
     s = host_api.Session(text, os.path.join(tree, "config"))
     s.parameter_scan(0, 2)  # warm-up
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = shard.scan_sharded(s, dev if world > 1 else None)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt, times, res = timed_studies(lambda: shard.scan_sharded(s, dev if world > 1 else None), world, dev)
     ia, ip = s.names.index("BAO alpha-parallel"), s.names.index("BAO alpha-perp")
     k = int(np.argmin(res["chi2"]))
     out = {"workload": "BOSSDR11LyaF_k.ini: BaoKSpaceCorrelationModel auto-correlation, N_data=1515, 60x35 grid, %d floating parameters per grid fit; synthetic data+cov" % (int(s.floating.sum()) - 2),
-           "points": int(len(res["chi2"])), "seconds": dt, "points_per_s": len(res["chi2"]) / dt,
+           "points": int(len(res["chi2"])), "seconds": dt, "seconds_all": times, "timing": "median of 3 scans after 1 warm-up scan",
+           "points_per_s": len(res["chi2"]) / dt,
            "failed_fits": int((res["status"] == 2).sum()), "chi2_min": float(res["best_chi2"]), "ndof": int(s.ndata - s.floating.sum()),
            "grid_minimum": {"alpha_parallel": float(res["points"][k, ia]), "alpha_perp": float(res["points"][k, ip]),
                             "delta_chi2": float(res["chi2"][k] - res["best_chi2"])},
@@ -306,22 +313,11 @@ def run_fft(args, rank, world, dev, ctx):
         W.write_dataset_files(os.path.join(tree, "data", "BOSSDR11LyaF_synth"), 2500, coords[3], d.keep._arrays[4], d.keep._arrays[5])
         text = open(os.path.join(tree, "config", "BOSSDR11LyaF_fft.ini")).read().replace("data = ../data/BOSSDR11LyaF", "data = ../data/BOSSDR11LyaF_synth")
         s = host_api.Session(text, os.path.join(tree, "config"))
-        s.toymc(0, 4, seed=1)  # warm-up
         ntoys = args.toys * world
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = shard.toymc_sharded(s, ntoys, seed=1966, device=dev if world > 1 else None)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt, times, res = timed_studies(lambda: shard.toymc_sharded(s, ntoys, seed=1966, device=dev if world > 1 else None), world, dev, warm=3)
         ia, ip = s.names.index("BAO alpha-parallel"), s.names.index("BAO alpha-perp")
         good = res["status"] != 2
-        out["toymc"] = {"toys": int(ntoys), "seconds": dt, "toys_per_s": ntoys / dt, "floating_parameters": int(s.floating.sum()),
+        out["toymc"] = {"toys": int(ntoys), "seconds": dt, "seconds_all": times, "timing": "median of 3 studies after 3 warm-up studies", "toys_per_s": ntoys / dt, "floating_parameters": int(s.floating.sum()),
                         "failed_fits": int((~good).sum()), "mean_chi2": float(res["chi2"][good].mean()), "ndof": int(s.ndata - s.floating.sum()),
                         "alpha_parallel_mean_std": [float(res["fitted"][good, ia].mean()), float(res["fitted"][good, ia].std())],
                         "alpha_perp_mean_std": [float(res["fitted"][good, ip].mean()), float(res["fitted"][good, ip].std())]}
