@@ -404,7 +404,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(256, 2) metal_add_kernel(FastArgs a) {
+__global__ void __launch_bounds__(256, 3) metal_add_kernel(FastArgs a) {
     __shared__ __align__(128) double win[kMetalStages][kMetalWin * NT];
     __shared__ __align__(8) unsigned long long full_bar[kMetalStages], empty_bar[kMetalStages];
     __shared__ double red_min[8], red_max[8];
