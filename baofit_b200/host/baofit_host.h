@@ -457,6 +457,11 @@ public:
     // (< 0: z of the first kept bin), from AbsCorrelationModel::evaluate(r, multipole, z, ...).
     void dumpModel(std::ostream &out, likely::FitParameters parameters, int ndump, double zdump = -1, std::string const &script = "",
                    bool oneLine = false) const;
+    // the same multipoles for many parameter vectors in one GPU batch: [points][3 * ndump]
+    std::vector<double> modelMultipoles(std::vector<likely::Parameters> const &points, int ndump, double zdump = -1) const;
+    // SamplingOutput (CorrelationAnalyzer.cc:375-450): the file toy-MC, bootstrap, jackknife and scan analyses save
+    void writeSamples(std::string const &path, likely::FunctionMinimumPtr fmin, std::vector<std::vector<double>> const &fitted,
+                      std::vector<double> const &chi2, int nsave = 0, double zsave = -1) const;
     void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
                          std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "") const;
     // CorrelationAnalyzer.cc:301-335 (doJackknifeAnalysis, doBootstrapAnalysis, fitEach) + the loop of

@@ -190,6 +190,25 @@ extern "C" int bfh_dump_model(bfh_session *s, const double *values, int ndump, d
     BFH_CATCH
 }
 
+extern "C" int bfh_write_samples(bfh_session *s, const char *path, const double *best_values, const double *best_errors,
+                                 double best_chi2, long nsamples, const double *fitted, const double *chi2, int nsave, double zsave) {
+    BFH_TRY
+    if (!path || !best_values || (nsamples > 0 && (!fitted || !chi2))) throw RuntimeError("bfh_write_samples: null argument");
+    const int npar = s->model->getNParameters();
+    likely::FunctionMinimumPtr fm(new likely::FunctionMinimum());
+    fm->parameters = s->model->getFitParameters();
+    for (int i = 0; i < npar; ++i) {
+        fm->parameters[i].value = best_values[i];
+        if (best_errors) fm->parameters[i].error = best_errors[i];
+    }
+    fm->minValue = 0.5 * best_chi2;
+    std::vector<std::vector<double>> f((size_t)nsamples);
+    std::vector<double> c(chi2, chi2 + nsamples);
+    for (long k = 0; k < nsamples; ++k) f[k].assign(fitted + (size_t)k * npar, fitted + (size_t)(k + 1) * npar);
+    s->analyzer->writeSamples(path, fm, f, c, nsave, zsave);
+    BFH_CATCH
+}
+
 extern "C" int bfh_mcmc(bfh_session *s, int nchain, int interval, int nwalkers, unsigned long long seed, double *samples) {
     BFH_TRY
     likely::FunctionMinimumPtr fm = s->fitter->fit("mn2::vmetric", "");

@@ -442,41 +442,95 @@ void CorrelationAnalyzer::dumpResiduals(std::ostream &out, likely::FunctionMinim
     }
 }
 
-void CorrelationAnalyzer::dumpModel(std::ostream &out, likely::FitParameters parameters, int ndump, double zdump,
-                                    std::string const &script, bool oneLine) const {
+std::vector<double> CorrelationAnalyzer::modelMultipoles(std::vector<likely::Parameters> const &points, int ndump, double zdump) const {
     if (ndump <= 1) throw RuntimeError("CorrelationAnalyzer::dump: expected ndump > 1.");
     if (!_model) throw RuntimeError("CorrelationAnalyzer::dumpModel: no model.");
     if (zdump < 0) {
         if (!_data) throw RuntimeError("CorrelationAnalyzer::dumpModel: no data to take the redshift from.");
         zdump = _data->getRedshift(_data->keptIndices().at(0));
     }
-    if (!script.empty()) likely::modifyFitParameters(parameters, script);
-    likely::Parameters values;
-    for (auto const &p : parameters) values.push_back(p.value);
-    // a multipole-binned point set (r_k, ell = 0,2,4, zdump) evaluated in one batch through the C ABI
-    const int n = 3 * ndump;
+    // a multipole-binned point set (r_k, ell = 0,2,4, zdump) evaluated for all parameter vectors in one batch
+    const int n = 3 * ndump, B = (int)points.size(), npar = _model->getNParameters();
     const double dr = (_rmax - _rmin) / (ndump - 1);
-    std::vector<double> r(n), ell(n), z(n, zdump), zero(n, 0.0), eye((size_t)n * n, 0.0), pred(n);
-    std::vector<int> idx(n);
+    std::vector<double> r(n), ell(n), z(n, zdump), zero(n, 0.0), eye((size_t)n * n, 0.0), pred((size_t)n * B), flat((size_t)B * npar);
+    std::vector<int> idx(n), status(B, 0);
     for (int k = 0; k < ndump; ++k)
         for (int l = 0; l < 3; ++l) { r[3 * k + l] = _rmin + dr * k; ell[3 * k + l] = 2 * l; idx[3 * k + l] = -1; }
     for (int i = 0; i < n; ++i) eye[(size_t)i * n + i] = 1.0;
+    for (int b = 0; b < B; ++b) {
+        if ((int)points[b].size() != npar) throw RuntimeError("CorrelationAnalyzer::dumpModel: wrong number of parameters.");
+        std::copy(points[b].begin(), points[b].end(), flat.begin() + (size_t)b * npar);
+    }
     bf_data_desc dd;
     std::memset(&dd, 0, sizeof(dd));
     dd.n_data = n; dd.r = r.data(); dd.mu = ell.data(); dd.z = z.data(); dd.index = idx.data(); dd.data = zero.data();
     dd.cov = eye.data(); dd.binning_type = BF_BINNING_MULTIPOLE;
     bf_data *pts = nullptr;
     check(bf_data_create(deviceContext(), &dd, &pts), "bf_data_create");
-    int status = 0;
-    int rc = bf_eval_batch(deviceContext(), _model->deviceModel(), pts, values.data(), 1, pred.data(), 1, &status);
+    int rc = bf_eval_batch(deviceContext(), _model->deviceModel(), pts, flat.data(), B, pred.data(), B, status.data());
     bf_data_destroy(pts);
     check(rc, "bf_eval_batch");
+    std::vector<double> out((size_t)B * n);  // [sample][3 * ndump]
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < n; ++i) out[(size_t)b * n + i] = pred[(size_t)i * B + b];
+    return out;
+}
+
+void CorrelationAnalyzer::dumpModel(std::ostream &out, likely::FitParameters parameters, int ndump, double zdump,
+                                    std::string const &script, bool oneLine) const {
+    if (!script.empty()) likely::modifyFitParameters(parameters, script);
+    likely::Parameters values;
+    for (auto const &p : parameters) values.push_back(p.value);
+    std::vector<double> pred = modelMultipoles(std::vector<likely::Parameters>(1, values), ndump, zdump);
+    const double dr = (_rmax - _rmin) / (ndump - 1);
     char buf[64];
     auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.17g", v); return std::string(buf); };
     for (int k = 0; k < ndump; ++k) {
         if (!oneLine) out << num(_rmin + dr * k);
         out << ' ' << num(pred[3 * k]) << ' ' << num(pred[3 * k + 1]) << ' ' << num(pred[3 * k + 2]);
         if (!oneLine) out << std::endl;
+    }
+}
+
+// SamplingOutput, CorrelationAnalyzer.cc:375-450: header "npar nsave nfit" (nfit = 1, no refit pass), the errors of
+// the input fit, then the input fit and every sample as one line: parameter values, 2*fval, and nsave x (mono, quad,
+// hexa) of the sample's model when nsave > 0.
+void CorrelationAnalyzer::writeSamples(std::string const &path, likely::FunctionMinimumPtr fmin,
+                                       std::vector<std::vector<double>> const &fitted, std::vector<double> const &chi2, int nsave,
+                                       double zsave) const {
+    if (nsave < 0) throw RuntimeError("CorrelationAnalyzer::doSamplingAnalysis: expected nsave >= 0.");
+    if (fitted.size() != chi2.size()) throw RuntimeError("CorrelationAnalyzer::writeSamples: one chi-square per sample expected.");
+    std::ofstream out(path.c_str());
+    if (!out.good()) throw RuntimeError("CorrelationAnalyzer: unable to open " + path);
+    char buf[64];
+    auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.10g", v); return std::string(buf); };
+    const int npar = (int)fmin->parameters.size();
+    std::vector<double> dumps;
+    if (nsave > 0) {
+        std::vector<likely::Parameters> pts;
+        pts.push_back(fmin->values());
+        for (auto const &f : fitted) {
+            bool finite = true;
+            for (double v : f) finite &= std::isfinite(v);
+            pts.push_back(finite ? f : fmin->values());  // failed fits dump the input model; their chi2 says so
+        }
+        dumps = modelMultipoles(pts, nsave, zsave);
+    }
+    auto dump = [&](size_t row) {
+        for (int k = 0; k < 3 * nsave; ++k) out << ' ' << num(dumps[row * 3 * nsave + k]);
+    };
+    out << npar << ' ' << nsave << " 1" << std::endl;
+    for (int i = 0; i < npar; ++i) out << (i ? " " : "") << num(fmin->parameters[i].floating ? fmin->parameters[i].error : 0.0);
+    out << std::endl;
+    for (int i = 0; i < npar; ++i) out << num(fmin->parameters[i].value) << " ";
+    out << num(2 * fmin->minValue);
+    if (nsave > 0) dump(0);
+    out << std::endl;
+    for (size_t k = 0; k < fitted.size(); ++k) {
+        for (int i = 0; i < npar; ++i) out << num(fitted[k][i]) << " ";
+        out << num(chi2[k]);
+        if (nsave > 0) dump(k + 1);
+        out << std::endl;
     }
 }
 

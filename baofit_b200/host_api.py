@@ -13,7 +13,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_s
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
-                "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit"]
+                "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples"]
 
 
 def lib():
@@ -47,6 +47,8 @@ def lib():
         L.bfh_lm_minimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, RESID_FN,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]
+        L.bfh_write_samples.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_long, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_double]
         L.bfh_nobservations.argtypes = [C.c_void_p]
         L.bfh_resampling_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long)]
         L.bfh_bootstrap_counts.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p]
@@ -182,6 +184,14 @@ class Session:
         _check(lib().bfh_toymc(self.h, first, count, seed, _p(fitted), _p(chi2), _p(st)))
         return dict(fitted=fitted, chi2=chi2, status=st)
 
+
+    def write_samples(self, path, best_values, best_errors, best_chi2, fitted, chi2, nsave=0, zsave=-1.0):
+        """The reference's SamplingOutput file (scan.dat / toymc.dat ...): header, input fit, one line per sample."""
+        bv = np.ascontiguousarray(best_values, dtype=np.float64)
+        be = np.ascontiguousarray(best_errors, dtype=np.float64)
+        f = np.ascontiguousarray(fitted, dtype=np.float64).reshape(-1, self.npar)
+        c = np.ascontiguousarray(chi2, dtype=np.float64)
+        _check(lib().bfh_write_samples(self.h, path.encode(), _p(bv), _p(be), float(best_chi2), len(c), _p(f), _p(c), nsave, zsave))
 
     # ---- jackknife / bootstrap / fit-each over the observations of a plateroot/platelist session ----
     @property

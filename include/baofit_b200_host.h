@@ -68,6 +68,12 @@ int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, d
  * observations in the sample covariance), "each" (one sample per observation). bfh_resample_data returns the kept
  * data vector [ndata] and covariance [ndata*ndata] of sample seqno (either may be NULL); bfh_resample_fit refits
  * samples [first, first+count) (count < 0: to the end): fitted[count*npar], chi2 = 2*fval, status. */
+/* SamplingOutput (CorrelationAnalyzer.cc:375-450), the text file scans, toy-MC, bootstrap and jackknife analyses save:
+ * "npar nsave 1" / errors of the input fit / the input fit / one line per sample = npar values, chi2 (2*fval) and, if
+ * nsave > 0, nsave x (mono quad hexa) of the sample's model between the rmin and rmax options at redshift zsave. */
+int bfh_write_samples(bfh_session *s, const char *path, const double *best_values, const double *best_errors,
+                      double best_chi2, long nsamples, const double *fitted /* [nsamples*npar] */, const double *chi2,
+                      int nsave, double zsave);
 int bfh_nobservations(const bfh_session *s);
 int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size);
 int bfh_bootstrap_counts(bfh_session *s, int size, unsigned long long seed, long trial, int *counts /* [nobservations] */);

@@ -99,6 +99,23 @@ def test_toymc_is_shard_independent_and_unbiased(built, golden_tree):
     ib = s.names.index("beta")
     assert abs(a["fitted"][:, ib].mean() - 1.4) < 0.05
     assert 600 < a["chi2"].mean() < 1000  # ~ N_data - n_float
+    # SamplingOutput file (CorrelationAnalyzer.cc:375-450): "npar nsave nfit", errors, input fit, one line per toy
+    # with the sample's parameters, chi2 and nsave x (mono, quad, hexa) of its model
+    best = s.fit()
+    path = os.path.join(golden_tree, "data", "toymc_save.dat")
+    s.write_samples(path, best["values"], best["errors"], 2 * best["fval"], a["fitted"], a["chi2"], nsave=5, zsave=2.25)
+    lines = open(path).read().splitlines()
+    assert lines[0].split() == [str(s.npar), "5", "1"] and len(lines) == 3 + 12
+    assert len(lines[1].split()) == s.npar
+    rows = np.array([[float(t) for t in ln.split()] for ln in lines[2:]])
+    assert rows.shape == (13, s.npar + 1 + 15)
+    assert np.allclose(rows[0, :s.npar], best["values"], rtol=1e-9, atol=1e-12) and abs(rows[0, s.npar] - 2 * best["fval"]) < 1e-6 * rows[0, s.npar]
+    assert np.allclose(rows[1:, :s.npar], a["fitted"], rtol=1e-9, atol=1e-12) and np.allclose(rows[1:, s.npar], a["chi2"], rtol=1e-9)
+    for k in (0, 3, 11):
+        mp = s.dump_model(a["fitted"][k], 5, 2.25)
+        assert np.allclose(rows[1 + k, s.npar + 1:], mp.ravel(), rtol=1e-9, atol=1e-15)
+    s.write_samples(path, best["values"], best["errors"], 2 * best["fval"], a["fitted"][:2], a["chi2"][:2])
+    assert len(open(path).read().splitlines()) == 5 and open(path).readline().split()[1] == "0"
 
 
 def test_dump_residuals_and_model_against_oracle(built, golden_tree, tmp_path):
