@@ -461,9 +461,15 @@ public:
     std::vector<double> modelMultipoles(std::vector<likely::Parameters> const &points, int ndump, double zdump = -1) const;
     // SamplingOutput (CorrelationAnalyzer.cc:375-450): the file toy-MC, bootstrap, jackknife and scan analyses save
     void writeSamples(std::string const &path, likely::FunctionMinimumPtr fmin, std::vector<std::vector<double>> const &fitted,
-                      std::vector<double> const &chi2, int nsave = 0, double zsave = -1) const;
+                      std::vector<double> const &chi2, int nsave = 0, double zsave = -1,
+                      likely::FunctionMinimumPtr fmin2 = likely::FunctionMinimumPtr(),
+                      std::vector<std::vector<double>> const *refitted = nullptr, std::vector<double> const *rechi2 = nullptr) const;
+    // refitConfig (the reference's refit-config, CorrelationAnalyzer.cc:491-503): every sample is fitted a second time
+    // with this script applied to the initial parameters; results go to refitted / rechi2 / restatus.
     void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
-                         std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "") const;
+                         std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "",
+                         std::string const &refitConfig = "", std::vector<std::vector<double>> *refitted = nullptr,
+                         std::vector<double> *rechi2 = nullptr, std::vector<int> *restatus = nullptr) const;
     // CorrelationAnalyzer.cc:301-335 (doJackknifeAnalysis, doBootstrapAnalysis, fitEach) + the loop of
     // doSamplingAnalysis :452-532: every sample is a new data vector AND covariance, refitted from the model's
     // initial parameters. kind = "jackknife" (n = observations dropped per sample), "bootstrap" (n = trials,
@@ -474,7 +480,9 @@ public:
     long resamplingSize(std::string const &kind, int n) const;
     AbsCorrelationDataPtr resample(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long seqno) const;
     long doResampling(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long first, long count,
-                      std::vector<std::vector<double>> &fitted, std::vector<double> &chi2, std::vector<int> &status) const;
+                      std::vector<std::vector<double>> &fitted, std::vector<double> &chi2, std::vector<int> &status,
+                      std::string const &refitConfig = "", std::vector<std::vector<double>> *refitted = nullptr,
+                      std::vector<double> *rechi2 = nullptr, std::vector<int> *restatus = nullptr) const;
 
 private:
     std::string _method;

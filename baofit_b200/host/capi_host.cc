@@ -192,20 +192,42 @@ extern "C" int bfh_dump_model(bfh_session *s, const double *values, int ndump, d
 
 extern "C" int bfh_write_samples(bfh_session *s, const char *path, const double *best_values, const double *best_errors,
                                  double best_chi2, long nsamples, const double *fitted, const double *chi2, int nsave, double zsave) {
+    return bfh_write_samples_refit(s, path, best_values, best_errors, best_chi2, nsamples, fitted, chi2, nsave, zsave, nullptr, nullptr, 0,
+                                   nullptr, nullptr);
+}
+
+extern "C" int bfh_write_samples_refit(bfh_session *s, const char *path, const double *best_values, const double *best_errors,
+                                       double best_chi2, long nsamples, const double *fitted, const double *chi2, int nsave, double zsave,
+                                       const double *best2_values, const double *best2_errors, double best2_chi2, const double *refitted,
+                                       const double *rechi2) {
     BFH_TRY
     if (!path || !best_values || (nsamples > 0 && (!fitted || !chi2))) throw RuntimeError("bfh_write_samples: null argument");
     const int npar = s->model->getNParameters();
-    likely::FunctionMinimumPtr fm(new likely::FunctionMinimum());
-    fm->parameters = s->model->getFitParameters();
-    for (int i = 0; i < npar; ++i) {
-        fm->parameters[i].value = best_values[i];
-        if (best_errors) fm->parameters[i].error = best_errors[i];
-    }
-    fm->minValue = 0.5 * best_chi2;
-    std::vector<std::vector<double>> f((size_t)nsamples);
+    auto minimum = [&](const double *values, const double *errors, double c2) {
+        likely::FunctionMinimumPtr fm(new likely::FunctionMinimum());
+        fm->parameters = s->model->getFitParameters();
+        for (int i = 0; i < npar; ++i) {
+            fm->parameters[i].value = values[i];
+            if (errors) { fm->parameters[i].error = errors[i]; fm->parameters[i].floating = errors[i] > 0; }
+        }
+        fm->minValue = 0.5 * c2;
+        return fm;
+    };
+    auto rows = [&](const double *flat) {
+        std::vector<std::vector<double>> f((size_t)nsamples);
+        for (long k = 0; k < nsamples; ++k) f[k].assign(flat + (size_t)k * npar, flat + (size_t)(k + 1) * npar);
+        return f;
+    };
+    std::vector<std::vector<double>> f = rows(fitted);
     std::vector<double> c(chi2, chi2 + nsamples);
-    for (long k = 0; k < nsamples; ++k) f[k].assign(fitted + (size_t)k * npar, fitted + (size_t)(k + 1) * npar);
-    s->analyzer->writeSamples(path, fm, f, c, nsave, zsave);
+    if (best2_values) {
+        if (nsamples > 0 && (!refitted || !rechi2)) throw RuntimeError("bfh_write_samples_refit: null refit arrays");
+        std::vector<std::vector<double>> f2 = rows(refitted);
+        std::vector<double> c2(rechi2, rechi2 + nsamples);
+        s->analyzer->writeSamples(path, minimum(best_values, best_errors, best_chi2), f, c, nsave, zsave,
+                                  minimum(best2_values, best2_errors, best2_chi2), &f2, &c2);
+    } else
+        s->analyzer->writeSamples(path, minimum(best_values, best_errors, best_chi2), f, c, nsave, zsave);
     BFH_CATCH
 }
 
@@ -242,19 +264,32 @@ extern "C" int bfh_parameter_scan(bfh_session *s, long first, long count, double
     BFH_CATCH
 }
 
-extern "C" int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
-                         int *status) {
-    BFH_TRY
-    std::vector<std::vector<double>> fit;
-    std::vector<double> c;
-    std::vector<int> st;
-    s->analyzer->doToyMCSampling(first, count, seed, fit, c, st);
-    int npar = s->model->getNParameters();
+static void copyOut(int npar, long count, std::vector<std::vector<double>> const &fit, std::vector<double> const &c,
+                    std::vector<int> const &st, double *fitted, double *chi2, int *status) {
     for (long t = 0; t < count; ++t) {
         if (fitted) std::copy(fit[t].begin(), fit[t].end(), fitted + (size_t)t * npar);
         if (chi2) chi2[t] = c[t];
         if (status) status[t] = st[t];
     }
+}
+
+extern "C" int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
+                         int *status) {
+    return bfh_toymc_refit(s, first, count, seed, "", "", fitted, chi2, status, nullptr, nullptr, nullptr);
+}
+
+extern "C" int bfh_toymc_refit(bfh_session *s, long first, long count, unsigned long long seed, const char *toymc_config,
+                               const char *refit_config, double *fitted, double *chi2, int *status, double *refitted, double *rechi2,
+                               int *restatus) {
+    BFH_TRY
+    std::vector<std::vector<double>> fit, fit2;
+    std::vector<double> c, c2;
+    std::vector<int> st, st2;
+    std::string refit = refit_config ? refit_config : "";
+    s->analyzer->doToyMCSampling(first, count, seed, fit, c, st, toymc_config ? toymc_config : "", refit, &fit2, &c2, &st2);
+    int npar = s->model->getNParameters();
+    copyOut(npar, count, fit, c, st, fitted, chi2, status);
+    if (!refit.empty()) copyOut(npar, count, fit2, c2, st2, refitted, rechi2, restatus);
     BFH_CATCH
 }
 
@@ -286,17 +321,21 @@ extern "C" int bfh_resample_data(bfh_session *s, const char *kind, int n, int si
 
 extern "C" int bfh_resample_fit(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
                                 long first, long count, double *fitted, double *chi2, int *status) {
+    return bfh_resample_refit(s, kind, n, size, fix_covariance, seed, first, count, "", fitted, chi2, status, nullptr, nullptr, nullptr);
+}
+
+extern "C" int bfh_resample_refit(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
+                                  long first, long count, const char *refit_config, double *fitted, double *chi2, int *status,
+                                  double *refitted, double *rechi2, int *restatus) {
     BFH_TRY
-    std::vector<std::vector<double>> fit;
-    std::vector<double> c;
-    std::vector<int> st;
-    long done = s->analyzer->doResampling(kind, n, size, fix_covariance != 0, seed, first, count, fit, c, st);
+    std::vector<std::vector<double>> fit, fit2;
+    std::vector<double> c, c2;
+    std::vector<int> st, st2;
+    std::string refit = refit_config ? refit_config : "";
+    long done = s->analyzer->doResampling(kind, n, size, fix_covariance != 0, seed, first, count, fit, c, st, refit, &fit2, &c2, &st2);
     int npar = s->model->getNParameters();
-    for (long t = 0; t < done; ++t) {
-        if (fitted) std::copy(fit[t].begin(), fit[t].end(), fitted + (size_t)t * npar);
-        if (chi2) chi2[t] = c[t];
-        if (status) status[t] = st[t];
-    }
+    copyOut(npar, done, fit, c, st, fitted, chi2, status);
+    if (!refit.empty()) copyOut(npar, done, fit2, c2, st2, refitted, rechi2, restatus);
     BFH_CATCH
 }
 

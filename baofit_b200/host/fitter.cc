@@ -492,46 +492,67 @@ void CorrelationAnalyzer::dumpModel(std::ostream &out, likely::FitParameters par
     }
 }
 
-// SamplingOutput, CorrelationAnalyzer.cc:375-450: header "npar nsave nfit" (nfit = 1, no refit pass), the errors of
-// the input fit, then the input fit and every sample as one line: parameter values, 2*fval, and nsave x (mono, quad,
-// hexa) of the sample's model when nsave > 0.
+// SamplingOutput, CorrelationAnalyzer.cc:375-450: header "npar nsave nfit" (nfit = 2 with a refit pass), the errors of
+// the input fit(s), then the input fit(s) and every sample as one line: parameter values, 2*fval, [refit values,
+// 2*fval2,] and nsave x (mono, quad, hexa) of the sample's model(s) when nsave > 0.
 void CorrelationAnalyzer::writeSamples(std::string const &path, likely::FunctionMinimumPtr fmin,
                                        std::vector<std::vector<double>> const &fitted, std::vector<double> const &chi2, int nsave,
-                                       double zsave) const {
+                                       double zsave, likely::FunctionMinimumPtr fmin2, std::vector<std::vector<double>> const *refitted,
+                                       std::vector<double> const *rechi2) const {
     if (nsave < 0) throw RuntimeError("CorrelationAnalyzer::doSamplingAnalysis: expected nsave >= 0.");
     if (fitted.size() != chi2.size()) throw RuntimeError("CorrelationAnalyzer::writeSamples: one chi-square per sample expected.");
+    const bool refit = (bool)fmin2;
+    if (refit != (refitted && rechi2) || (refit && (refitted->size() != fitted.size() || rechi2->size() != fitted.size())))
+        throw RuntimeError("CorrelationAnalyzer::doSamplingAnalysis: inconsistent refit parameters.");
     std::ofstream out(path.c_str());
     if (!out.good()) throw RuntimeError("CorrelationAnalyzer: unable to open " + path);
     char buf[64];
     auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.10g", v); return std::string(buf); };
     const int npar = (int)fmin->parameters.size();
-    std::vector<double> dumps;
-    if (nsave > 0) {
+    // model multipoles of the input fit(s) and of every sample, all in one GPU batch; failed fits (non-finite
+    // parameters) dump the input model, their chi2 says so
+    std::vector<double> dumps, dumps2;
+    auto dumpAll = [&](likely::FunctionMinimumPtr fm, std::vector<std::vector<double>> const &f) {
         std::vector<likely::Parameters> pts;
-        pts.push_back(fmin->values());
-        for (auto const &f : fitted) {
+        pts.push_back(fm->values());
+        for (auto const &v : f) {
             bool finite = true;
-            for (double v : f) finite &= std::isfinite(v);
-            pts.push_back(finite ? f : fmin->values());  // failed fits dump the input model; their chi2 says so
+            for (double x : v) finite &= std::isfinite(x);
+            pts.push_back(finite ? v : fm->values());
         }
-        dumps = modelMultipoles(pts, nsave, zsave);
-    }
-    auto dump = [&](size_t row) {
-        for (int k = 0; k < 3 * nsave; ++k) out << ' ' << num(dumps[row * 3 * nsave + k]);
+        return modelMultipoles(pts, nsave, zsave);
     };
-    out << npar << ' ' << nsave << " 1" << std::endl;
-    for (int i = 0; i < npar; ++i) out << (i ? " " : "") << num(fmin->parameters[i].floating ? fmin->parameters[i].error : 0.0);
-    out << std::endl;
-    for (int i = 0; i < npar; ++i) out << num(fmin->parameters[i].value) << " ";
-    out << num(2 * fmin->minValue);
-    if (nsave > 0) dump(0);
-    out << std::endl;
-    for (size_t k = 0; k < fitted.size(); ++k) {
-        for (int i = 0; i < npar; ++i) out << num(fitted[k][i]) << " ";
-        out << num(chi2[k]);
-        if (nsave > 0) dump(k + 1);
-        out << std::endl;
+    if (nsave > 0) {
+        dumps = dumpAll(fmin, fitted);
+        if (refit) dumps2 = dumpAll(fmin2, *refitted);
     }
+    auto dump = [&](std::vector<double> const &d, size_t row) {
+        for (int k = 0; k < 3 * nsave; ++k) out << ' ' << num(d[row * 3 * nsave + k]);
+    };
+    auto errors = [&](likely::FunctionMinimumPtr fm, bool first) {
+        for (int i = 0; i < npar; ++i) out << (i || !first ? " " : "") << num(fm->parameters[i].floating ? fm->parameters[i].error : 0.0);
+    };
+    auto line = [&](std::vector<double> const &v, double c2, std::vector<double> const *v2, double c22, size_t row) {
+        for (int i = 0; i < npar; ++i) out << num(v[i]) << " ";
+        out << num(c2);
+        if (v2) {
+            for (int i = 0; i < npar; ++i) out << " " << num((*v2)[i]);
+            out << " " << num(c22);
+        }
+        if (nsave > 0) {
+            dump(dumps, row);
+            if (v2) dump(dumps2, row);
+        }
+        out << std::endl;
+    };
+    out << npar << ' ' << nsave << ' ' << (refit ? 2 : 1) << std::endl;
+    errors(fmin, true);
+    if (refit) errors(fmin2, false);
+    out << std::endl;
+    std::vector<double> v0 = fmin->values(), v02;
+    if (refit) v02 = fmin2->values();
+    line(v0, 2 * fmin->minValue, refit ? &v02 : nullptr, refit ? 2 * fmin2->minValue : 0.0, 0);
+    for (size_t k = 0; k < fitted.size(); ++k) line(fitted[k], chi2[k], refit ? &(*refitted)[k] : nullptr, refit ? (*rechi2)[k] : 0.0, k + 1);
 }
 
 void CorrelationAnalyzer::writeScan(std::string const &path, ScanResult const &scan) {
@@ -555,8 +576,12 @@ void CorrelationAnalyzer::writeScan(std::string const &path, ScanResult const &s
 
 void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long long seed,
                                           std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
-                                          std::vector<int> &status, std::string const &toymcConfig) const {
+                                          std::vector<int> &status, std::string const &toymcConfig, std::string const &refitConfig,
+                                          std::vector<std::vector<double>> *refitted, std::vector<double> *rechi2,
+                                          std::vector<int> *restatus) const {
     if (!_data || !_model) throw RuntimeError("CorrelationAnalyzer::doToyMCSampling: need data and a model.");
+    if (!refitConfig.empty() && !(refitted && rechi2 && restatus))
+        throw RuntimeError("CorrelationAnalyzer::doSamplingAnalysis: inconsistent refit parameters.");
     const bool verbose = std::getenv("BAOFIT_VERBOSE_FITS") != nullptr;
     double tStart = nowSeconds();
     CorrelationFitter fitter(_data, _model, _covSampleSize);
@@ -574,24 +599,27 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
     check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, &toys), "bf_toys_create");
     std::shared_ptr<bf_toys> guard(toys, [](bf_toys *t) { bf_toys_destroy(t); });
     double tToys = nowSeconds();
-    // every toy is refitted from the model's initial configuration; all fits in lock step
     const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
-    std::vector<likely::LMFit> fits((size_t)count, likely::LMFit(_model->getFitParameters(), cs, ps));
     std::vector<int> toyOfFit(count);
     for (long t = 0; t < count; ++t) toyOfFit[t] = (int)t;
-    fitter.runLockStepLM(fits, toys, &toyOfFit);
-    double tLM = nowSeconds();
-    std::vector<likely::FunctionMinimumPtr> results(count);
-    size_t nRedo = 0;
-    {
+    // every toy is (re)fitted from the model's initial configuration with `config` applied (what
+    // CorrelationFitter::fit(method, config) does, CorrelationAnalyzer.cc:480,494); all fits in lock step
+    auto fitAll = [&](std::string const &config, std::vector<std::vector<double>> &outFitted, std::vector<double> &outChi2,
+                      std::vector<int> &outStatus) {
+        likely::FitParameters start = _model->getFitParameters();
+        if (!config.empty()) likely::modifyFitParameters(start, config);
+        std::vector<likely::LMFit> fits((size_t)count, likely::LMFit(start, cs, ps));
+        double t0 = nowSeconds();
+        fitter.runLockStepLM(fits, toys, &toyOfFit);
+        double tLM = nowSeconds();
+        std::vector<likely::FunctionMinimumPtr> results(count);
         // toys whose LM fit did not converge cleanly are refitted with the Newton driver
         std::vector<likely::NewtonFit> redo;
         std::vector<int> redoToy;
         for (long t = 0; t < count; ++t) {
             results[t] = fits[t].result();
-            if (results[t]->status != likely::FunctionMinimum::OK) { redo.push_back(likely::NewtonFit(_model->getFitParameters())); redoToy.push_back((int)t); }
+            if (results[t]->status != likely::FunctionMinimum::OK) { redo.push_back(likely::NewtonFit(start)); redoToy.push_back((int)t); }
         }
-        nRedo = redo.size();
         std::vector<likely::Parameters> points;
         std::vector<int> toyIndex;
         std::vector<double> values;
@@ -622,17 +650,20 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
                 (results[redoToy[q]]->status == likely::FunctionMinimum::ERROR || fm->minValue <= results[redoToy[q]]->minValue))
                 results[redoToy[q]] = fm;
         }
-    }
-    if (verbose)
-        std::fprintf(stderr, "doToyMCSampling: %ld toys: truth + realisations %.3f s, lock-step LM %.3f s, %zu Newton refits %.3f s\n", count,
-                     tToys - tStart, tLM - tToys, nRedo, nowSeconds() - tLM);
-    fitted.clear(); chi2.clear(); status.clear();
-    for (long t = 0; t < count; ++t) {
-        likely::FunctionMinimumPtr fm = results[t];
-        fitted.push_back(fm->values());
-        chi2.push_back(2 * fm->minValue);
-        status.push_back((int)fm->status);
-    }
+        if (verbose)
+            std::fprintf(stderr, "doToyMCSampling: %ld toys%s: lock-step LM %.3f s, %zu Newton refits %.3f s\n", count,
+                         config.empty() ? "" : " (refit)", tLM - t0, redo.size(), nowSeconds() - tLM);
+        outFitted.clear(); outChi2.clear(); outStatus.clear();
+        for (long t = 0; t < count; ++t) {
+            likely::FunctionMinimumPtr fm = results[t];
+            outFitted.push_back(fm->values());
+            outChi2.push_back(2 * fm->minValue);
+            outStatus.push_back((int)fm->status);
+        }
+    };
+    if (verbose) std::fprintf(stderr, "doToyMCSampling: truth + %ld realisations %.3f s\n", count, tToys - tStart);
+    fitAll("", fitted, chi2, status);
+    if (!refitConfig.empty()) fitAll(refitConfig, *refitted, *rechi2, *restatus);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -825,26 +856,34 @@ AbsCorrelationDataPtr CorrelationAnalyzer::resample(std::string const &kind, int
 
 long CorrelationAnalyzer::doResampling(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long first,
                                        long count, std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
-                                       std::vector<int> &status) const {
+                                       std::vector<int> &status, std::string const &refitConfig,
+                                       std::vector<std::vector<double>> *refitted, std::vector<double> *rechi2,
+                                       std::vector<int> *restatus) const {
+    if (!refitConfig.empty() && !(refitted && rechi2 && restatus))
+        throw RuntimeError("CorrelationAnalyzer::doSamplingAnalysis: inconsistent refit parameters.");
     long total = resamplingSize(kind, n);
     if (count < 0) count = total - first;
     if (first < 0 || first + count > total) throw RuntimeError("CorrelationAnalyzer: bad resampling range.");
     fitted.clear(); chi2.clear(); status.clear();
+    if (refitted) { refitted->clear(); rechi2->clear(); restatus->clear(); }
+    // a failed fit is recorded, not fatal (CorrelationAnalyzer.cc:486-489 swallows per-fit errors)
+    auto fitOne = [&](AbsCorrelationDataPtr sample, std::string const &config, std::vector<std::vector<double>> &f, std::vector<double> &c,
+                      std::vector<int> &st) {
+        try {
+            likely::FunctionMinimumPtr fm = fitSample(sample, config);
+            f.push_back(fm->values());
+            c.push_back(2 * fm->minValue);
+            st.push_back((int)fm->status);
+        } catch (std::runtime_error const &e) {
+            f.push_back(std::vector<double>(_model->getNParameters(), std::nan("")));
+            c.push_back(std::nan(""));
+            st.push_back((int)likely::FunctionMinimum::ERROR);
+        }
+    };
     for (long q = first; q < first + count; ++q) {
         AbsCorrelationDataPtr sample = resample(kind, n, size, fixCovariance, seed, q);
-        // a failed fit is recorded, not fatal (CorrelationAnalyzer.cc:486-489 swallows per-fit errors)
-        try {
-            likely::FunctionMinimumPtr fm = fitSample(sample);
-            std::vector<double> v;
-            for (auto const &p : fm->parameters) v.push_back(p.value);
-            fitted.push_back(v);
-            chi2.push_back(2 * fm->minValue);
-            status.push_back((int)fm->status);
-        } catch (std::runtime_error const &e) {
-            fitted.push_back(std::vector<double>(_model->getNParameters(), std::nan("")));
-            chi2.push_back(std::nan(""));
-            status.push_back((int)likely::FunctionMinimum::ERROR);
-        }
+        fitOne(sample, "", fitted, chi2, status);
+        if (!refitConfig.empty()) fitOne(sample, refitConfig, *refitted, *rechi2, *restatus);
     }
     return count;
 }

@@ -13,7 +13,8 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_s
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
-                "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples"]
+                "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit"]
 
 
 def lib():
@@ -49,6 +50,12 @@ def lib():
                                       C.POINTER(C.c_int)]
         L.bfh_write_samples.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_long, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_double]
+        L.bfh_toymc_refit.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_ulonglong, C.c_char_p, C.c_char_p] + [C.c_void_p] * 6
+        L.bfh_resample_refit.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_long, C.c_long,
+                                         C.c_char_p] + [C.c_void_p] * 6
+        L.bfh_write_samples_refit.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_long, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                              C.c_void_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
         L.bfh_resampling_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long)]
         L.bfh_bootstrap_counts.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p]
@@ -178,20 +185,36 @@ class Session:
         _check(lib().bfh_parameter_scan(self.h, first, count, _p(chi2), _p(pts), _p(st), _p(best)))
         return dict(chi2=chi2, points=pts, status=st, best_values=best[:-1], best_chi2=best[-1])
 
-    def toymc(self, first, count, seed=1966):
+    def toymc(self, first, count, seed=1966, toymc_config="", refit_config=""):
         fitted, chi2 = np.zeros((count, self.npar)), np.zeros(count)
         st = np.zeros(count, dtype=np.int32)
-        _check(lib().bfh_toymc(self.h, first, count, seed, _p(fitted), _p(chi2), _p(st)))
-        return dict(fitted=fitted, chi2=chi2, status=st)
+        if not toymc_config and not refit_config:
+            _check(lib().bfh_toymc(self.h, first, count, seed, _p(fitted), _p(chi2), _p(st)))
+            return dict(fitted=fitted, chi2=chi2, status=st)
+        f2, c2, st2 = np.zeros((count, self.npar)), np.zeros(count), np.zeros(count, dtype=np.int32)
+        _check(lib().bfh_toymc_refit(self.h, first, count, seed, toymc_config.encode(), refit_config.encode(), _p(fitted), _p(chi2),
+                                     _p(st), _p(f2), _p(c2), _p(st2)))
+        out = dict(fitted=fitted, chi2=chi2, status=st)
+        if refit_config:
+            out.update(refitted=f2, rechi2=c2, restatus=st2)
+        return out
 
 
-    def write_samples(self, path, best_values, best_errors, best_chi2, fitted, chi2, nsave=0, zsave=-1.0):
-        """The reference's SamplingOutput file (scan.dat / toymc.dat ...): header, input fit, one line per sample."""
+    def write_samples(self, path, best_values, best_errors, best_chi2, fitted, chi2, nsave=0, zsave=-1.0, refit=None):
+        """The reference's SamplingOutput file (scan.dat / toymc.dat ...): header, input fit, one line per sample.
+        refit = (best2_values, best2_errors, best2_chi2, refitted, rechi2) adds the columns of a refit pass."""
         bv = np.ascontiguousarray(best_values, dtype=np.float64)
         be = np.ascontiguousarray(best_errors, dtype=np.float64)
         f = np.ascontiguousarray(fitted, dtype=np.float64).reshape(-1, self.npar)
         c = np.ascontiguousarray(chi2, dtype=np.float64)
-        _check(lib().bfh_write_samples(self.h, path.encode(), _p(bv), _p(be), float(best_chi2), len(c), _p(f), _p(c), nsave, zsave))
+        if refit is None:
+            _check(lib().bfh_write_samples(self.h, path.encode(), _p(bv), _p(be), float(best_chi2), len(c), _p(f), _p(c), nsave, zsave))
+            return
+        bv2, be2 = (np.ascontiguousarray(x, dtype=np.float64) for x in refit[:2])
+        f2 = np.ascontiguousarray(refit[3], dtype=np.float64).reshape(-1, self.npar)
+        c2 = np.ascontiguousarray(refit[4], dtype=np.float64)
+        _check(lib().bfh_write_samples_refit(self.h, path.encode(), _p(bv), _p(be), float(best_chi2), len(c), _p(f), _p(c), nsave, zsave,
+                                             _p(bv2), _p(be2), float(refit[2]), _p(f2), _p(c2)))
 
     # ---- jackknife / bootstrap / fit-each over the observations of a plateroot/platelist session ----
     @property
@@ -213,14 +236,18 @@ class Session:
         _check(lib().bfh_resample_data(self.h, kind.encode(), n, size, int(fix_covariance), seed, seqno, _p(d), _p(c)))
         return d, c
 
-    def resample_fit(self, kind, n=0, size=0, fix_covariance=False, seed=1966, first=0, count=-1):
+    def resample_fit(self, kind, n=0, size=0, fix_covariance=False, seed=1966, first=0, count=-1, refit_config=""):
         if count < 0:
             count = self.resampling_size(kind, n) - first
         fitted, chi2 = np.zeros((count, self.npar)), np.zeros(count)
         st = np.zeros(count, dtype=np.int32)
-        _check(lib().bfh_resample_fit(self.h, kind.encode(), n, size, int(fix_covariance), seed, first, count, _p(fitted), _p(chi2),
-                                      _p(st)))
-        return dict(fitted=fitted, chi2=chi2, status=st)
+        f2, c2, st2 = np.zeros((count, self.npar)), np.zeros(count), np.zeros(count, dtype=np.int32)
+        _check(lib().bfh_resample_refit(self.h, kind.encode(), n, size, int(fix_covariance), seed, first, count, refit_config.encode(),
+                                        _p(fitted), _p(chi2), _p(st), _p(f2), _p(c2), _p(st2)))
+        out = dict(fitted=fitted, chi2=chi2, status=st)
+        if refit_config:
+            out.update(refitted=f2, rechi2=c2, restatus=st2)
+        return out
 
 
 def minimize(fn, values, errors, floating):

@@ -74,6 +74,15 @@ int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, d
 int bfh_write_samples(bfh_session *s, const char *path, const double *best_values, const double *best_errors,
                       double best_chi2, long nsamples, const double *fitted /* [nsamples*npar] */, const double *chi2,
                       int nsave, double zsave);
+/* The same analyses with the reference's refit pass (refit-config, CorrelationAnalyzer.cc:491-503): every sample is fitted a
+ * second time with the script applied to the initial parameters. toymc_config reconfigures the truth (toymc-config). */
+int bfh_toymc_refit(bfh_session *s, long first, long count, unsigned long long seed, const char *toymc_config,
+                    const char *refit_config, double *fitted, double *chi2, int *status, double *refitted, double *rechi2,
+                    int *restatus);
+int bfh_write_samples_refit(bfh_session *s, const char *path, const double *best_values, const double *best_errors,
+                            double best_chi2, long nsamples, const double *fitted, const double *chi2, int nsave, double zsave,
+                            const double *best2_values, const double *best2_errors, double best2_chi2, const double *refitted,
+                            const double *rechi2);
 int bfh_nobservations(const bfh_session *s);
 int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size);
 int bfh_bootstrap_counts(bfh_session *s, int size, unsigned long long seed, long trial, int *counts /* [nobservations] */);
@@ -81,6 +90,9 @@ int bfh_resample_data(bfh_session *s, const char *kind, int n, int size, int fix
                       long seqno, double *data, double *cov);
 int bfh_resample_fit(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
                      long first, long count, double *fitted, double *chi2, int *status);
+int bfh_resample_refit(bfh_session *s, const char *kind, int n, int size, int fix_covariance, unsigned long long seed,
+                       long first, long count, const char *refit_config, double *fitted, double *chi2, int *status,
+                       double *refitted, double *rechi2, int *restatus);
 
 /* CorrelationAnalyzer::dumpResiduals (CorrelationAnalyzer.cc:607-676) at the given parameter values / errors
  * into the text file `path`; CorrelationAnalyzer::dumpModel (:678-716): multipoles[ndump*3] = mono, quad, hexa

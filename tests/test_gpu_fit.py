@@ -116,6 +116,20 @@ def test_toymc_is_shard_independent_and_unbiased(built, golden_tree):
         assert np.allclose(rows[1 + k, s.npar + 1:], mp.ravel(), rtol=1e-9, atol=1e-15)
     s.write_samples(path, best["values"], best["errors"], 2 * best["fval"], a["fitted"][:2], a["chi2"][:2])
     assert len(open(path).read().splitlines()) == 5 and open(path).readline().split()[1] == "0"
+    # refit pass (refit-config): every toy fitted again with beta fixed at its start value; same toys, so the first
+    # pass is unchanged and the constrained chi2 is never below the free one
+    rf = s.toymc(0, 12, seed=7, refit_config="fix[beta]=1.4")
+    assert np.array_equal(rf["fitted"], a["fitted"]) and np.all(rf["restatus"] == 0)
+    assert np.all(rf["refitted"][:, ib] == 1.4) and np.all(rf["rechi2"] >= rf["chi2"] - 1e-6)
+    best2 = s.fit("fix[beta]=1.4")
+    s.write_samples(path, best["values"], best["errors"], 2 * best["fval"], rf["fitted"], rf["chi2"], nsave=3, zsave=2.25,
+                    refit=(best2["values"], best2["errors"], 2 * best2["fval"], rf["refitted"], rf["rechi2"]))
+    lines = open(path).read().splitlines()
+    assert lines[0].split() == [str(s.npar), "3", "2"] and len(lines[1].split()) == 2 * s.npar
+    rows = np.array([[float(t) for t in ln.split()] for ln in lines[2:]])
+    assert rows.shape == (13, 2 * (s.npar + 1) + 2 * 9)
+    assert np.allclose(rows[1:, s.npar + 1:2 * s.npar + 1], rf["refitted"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(rows[1:, 2 * s.npar + 1], rf["rechi2"], rtol=1e-9)
 
 
 def test_dump_residuals_and_model_against_oracle(built, golden_tree, tmp_path):
