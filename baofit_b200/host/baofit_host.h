@@ -257,6 +257,10 @@ public:
     std::vector<double> dataVector() const;           // kept bins, iteration order
     std::vector<double> covarianceMatrix() const;     // dense kept x kept (cov or icov as loaded)
     bool isInverse() const { return _isInverse; }
+    // "save.data" / "save.icov" of src/baofit.cc:612-626: the finalized data set in the loader's own text formats
+    // ("index value", "i j Cinv_ij" for j <= i), %.17g so that reloading with load-icov reproduces the fit
+    void saveData(std::ostream &out) const;
+    void saveInverseCovariance(std::ostream &out) const;
 
 protected:
     BinnedGrid _grid;

@@ -293,6 +293,21 @@ extern "C" int bfh_toymc_refit(bfh_session *s, long first, long count, unsigned 
     BFH_CATCH
 }
 
+extern "C" int bfh_save_data(bfh_session *s, const char *data_path, const char *icov_path) {
+    BFH_TRY
+    if (data_path && *data_path) {
+        std::ofstream out(data_path);
+        if (!out.good()) throw RuntimeError(std::string("bfh_save_data: unable to open ") + data_path);
+        s->data->saveData(out);
+    }
+    if (icov_path && *icov_path) {
+        std::ofstream out(icov_path);
+        if (!out.good()) throw RuntimeError(std::string("bfh_save_data: unable to open ") + icov_path);
+        s->data->saveInverseCovariance(out);
+    }
+    BFH_CATCH
+}
+
 extern "C" int bfh_nobservations(const bfh_session *s) { return s && s->resampler ? s->resampler->getNObservations() : 0; }
 
 extern "C" int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size) {

@@ -261,6 +261,28 @@ std::vector<double> AbsCorrelationData::covarianceMatrix() const {
     return c;
 }
 
+void AbsCorrelationData::saveData(std::ostream &out) const {
+    if (!_finalized) throw RuntimeError("AbsCorrelationData::saveData: data is not finalized.");
+    char buf[64];
+    for (int idx : _kept) {
+        std::snprintf(buf, sizeof(buf), "%d %.17g", idx, _values.at(idx));
+        out << buf << std::endl;
+    }
+}
+
+void AbsCorrelationData::saveInverseCovariance(std::ostream &out) const {
+    if (!_finalized) throw RuntimeError("AbsCorrelationData::saveInverseCovariance: data is not finalized.");
+    const int n = (int)_kept.size();
+    std::vector<double> m = covarianceMatrix();
+    std::vector<double> icov = _isInverse ? m : spdInverse(n, m, "the covariance");
+    char buf[96];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+            std::snprintf(buf, sizeof(buf), "%d %d %.17g", _kept[i], _kept[j], icov[(size_t)i * n + j]);
+            out << buf << std::endl;
+        }
+}
+
 bf_data *AbsCorrelationData::deviceData(bool withGrid) {
     if (!_finalized) finalize();
     if (_device && _deviceHasGrid == withGrid) return _device;

@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_s
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data"]
 
 
 def lib():
@@ -56,6 +56,7 @@ def lib():
         L.bfh_write_samples_refit.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_long, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                               C.c_void_p]
+        L.bfh_save_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
         L.bfh_resampling_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long)]
         L.bfh_bootstrap_counts.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p]
@@ -215,6 +216,9 @@ class Session:
         c2 = np.ascontiguousarray(refit[4], dtype=np.float64)
         _check(lib().bfh_write_samples_refit(self.h, path.encode(), _p(bv), _p(be), float(best_chi2), len(c), _p(f), _p(c), nsave, zsave,
                                              _p(bv2), _p(be2), float(refit[2]), _p(f2), _p(c2)))
+
+    def save_data(self, data_path=None, icov_path=None):
+        _check(lib().bfh_save_data(self.h, data_path.encode() if data_path else None, icov_path.encode() if icov_path else None))
 
     # ---- jackknife / bootstrap / fit-each over the observations of a plateroot/platelist session ----
     @property

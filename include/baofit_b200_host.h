@@ -83,6 +83,9 @@ int bfh_write_samples_refit(bfh_session *s, const char *path, const double *best
                             double best_chi2, long nsamples, const double *fitted, const double *chi2, int nsave, double zsave,
                             const double *best2_values, const double *best2_errors, double best2_chi2, const double *refitted,
                             const double *rechi2);
+/* save-data / save-icov of src/baofit.cc:612-626: the finalized (combined, cut) data set as "<index> <value>" and
+ * "<i> <j> <Cinv_ij>" text files that bfh_session_create reads back with load-icov. Either path may be NULL. */
+int bfh_save_data(bfh_session *s, const char *data_path, const char *icov_path);
 int bfh_nobservations(const bfh_session *s);
 int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size);
 int bfh_bootstrap_counts(bfh_session *s, int size, unsigned long long seed, long trial, int *counts /* [nobservations] */);

@@ -179,6 +179,13 @@ def test_resampler_jackknife_bootstrap_each(built, golden_tree):
         seen_repeat |= counts.max() > 1
     assert seen_repeat
     assert s.bootstrap_counts(0, size=12, seed=7).sum() == 12
+    # save-data / save-icov round trip: the combined data set reloads (load-icov) to the same vector and covariance
+    prefix = os.path.join(golden_tree, "data", "rs_saved")
+    s.save_data(prefix + ".data", prefix + ".icov")
+    back = H.Session(text.replace("platelist = rs.list", "").replace("plateroot = ../data/", "data = ../data/rs_saved") + "load-icov = yes\n", base)
+    assert np.array_equal(back.data_vector(), s.data_vector())
+    cb, c0 = back.covariance(), s.covariance()  # kept = all bins with data: the inverse is handed through
+    assert np.max(np.abs(np.linalg.inv(cb) - c0)) < 1e-9 * np.max(np.abs(c0))
     # a single-file session has nothing to resample
     single = H.Session(text.replace("platelist = rs.list", "").replace("plateroot = ../data/", "data = ../data/rs_0"), base)
     assert single.nobservations == 0
