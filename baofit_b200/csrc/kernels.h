@@ -1,8 +1,26 @@
 // Kernel argument blocks and launchers (implemented in kernels_model.cu / kernels_gemm.cu).
 #pragma once
+#include <atomic>
 #include "bf_internal.h"
 
 namespace bf {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remembers, per device, how much has been
+// configured for one kernel (a process may hold contexts on several GPUs; launchers may run on several host threads).
+struct SmemOptIn {
+    static constexpr int kMaxDevices = 64;
+    std::atomic<size_t> configured[kMaxDevices];
+    SmemOptIn() { for (auto &c : configured) c.store(0); }
+    template <class F> void ensure(F func, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const bool tracked = dev >= 0 && dev < kMaxDevices;
+        if (tracked && configured[dev].load(std::memory_order_acquire) >= bytes) return;
+        cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (tracked) configured[dev].store(bytes, std::memory_order_release);
+    }
+};
+
 
 struct EvalArgs {
     DevModel m;

@@ -679,12 +679,9 @@ static void pick_grid(FastArgs &a, int sm_count, dim3 &grid) {
 
 void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part) {
     size_t smem = (size_t)2 * a.m.nr * 9 * sizeof(double2);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(kspace_fast_eval_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(kspace_fast_eval_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt_lean, opt_full;
+    opt_lean.ensure(kspace_fast_eval_kernel<true, 1>, smem);
+    opt_full.ensure(kspace_fast_eval_kernel<false, 0>, smem);
     dim3 grid;
     pick_grid(a, sm_count, grid);
     if (part == 1) kspace_fast_eval_kernel<true, 1><<<grid, 256, smem, s>>>(a);

@@ -481,11 +481,8 @@ __global__ void __launch_bounds__(PV * 3 * 32, 1) fft_plane_kernel(FftPlaneArgs 
 
 template <int NCF>
 static void launch_fft_planes_t(cudaStream_t s, const FftPlaneArgs &a, dim3 grid, int threads, size_t smem) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(fft_plane_kernel<NCF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        attr = true;
-    }
+    static SmemOptIn opt;
+    opt.ensure(fft_plane_kernel<NCF>, (size_t)226 * 1024);
     fft_plane_kernel<NCF><<<grid, threads, smem, s>>>(a);
 }
 

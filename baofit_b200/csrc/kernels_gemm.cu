@@ -377,11 +377,8 @@ void gemm_fullm_tile_A(const double *A, int M, int K, int lda, double *At) {
 
 void launch_gemm_chi2_fullm(cudaStream_t s, const GemmArgs &g, int sm_count) {
     const size_t smem = ((size_t)FSTAGES * (g.M * FLDA + FKC * FLDB) + (size_t)(g.M / 32) * FBN) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(dgemm_chi2_fullm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    opt.ensure(dgemm_chi2_fullm_kernel, smem);
     const int ntiles = (g.N + FBN - 1) / FBN;
     dgemm_chi2_fullm_kernel<<<std::min(ntiles, sm_count), g.M, smem, s>>>(g);
 }
@@ -422,11 +419,8 @@ __global__ void toy_noise_kernel(const double *__restrict__ L, int n, int n_pad,
 }
 
 void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(dgemm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        attr = true;
-    }
+    static SmemOptIn opt;
+    opt.ensure(dgemm_store_kernel, (size_t)SMEM_BYTES);
     dim3 grid((g.N + BN - 1) / BN, g.M / BM, batch);
     dgemm_store_kernel<<<grid, 128, SMEM_BYTES, s>>>(g);
 }
@@ -441,11 +435,8 @@ int gemm_chi2_split_columns(int M, int sm_count) {
 }
 
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(dgemm_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        attr = true;
-    }
+    static SmemOptIn opt;
+    opt.ensure(dgemm_chi2_kernel, (size_t)SMEM_BYTES);
     const int panels = (g.N + BN - 1) / BN, tiles = g.M / BM;
     if (g.chi2_part && g.N <= gemm_chi2_split_columns(g.M, sm_count) && g.part_ld >= panels * BN) {
         dgemm_chi2_kernel<<<dim3(panels, tiles, 1), 128, SMEM_BYTES, s>>>(g);

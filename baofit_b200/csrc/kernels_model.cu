@@ -860,21 +860,15 @@ void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a) {
 
 void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs) {
     size_t smem = (size_t)36 * m.nr * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(kspace_basis_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    opt.ensure(kspace_basis_finish_kernel, smem);
     kspace_basis_finish_kernel<<<1, 256, smem, s>>>(m, T, tabs);
 }
 
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count) {
     size_t smem = (size_t)2 * a.m.nr * 9 * sizeof(double2);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(kspace_eval_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    opt.ensure(kspace_eval_shared_kernel, smem);
     int bx = (a.B + 255) / 256;
     int want = sm_count * 6;
     int by = max(1, min(a.npts_pad, (want + bx - 1) / bx));

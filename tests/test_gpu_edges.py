@@ -72,3 +72,23 @@ def test_fft_model_rejects_bad_grids(ctx):
     m, _ = W.dr11_auto_fft(ngrid=64, spacing=-1.)
     with pytest.raises(capi.BaofitError):
         capi.Model(ctx, m)
+
+
+def test_two_devices_in_one_process(ctx):
+    """Contexts on two GPUs of one process give identical results (per-device kernel attributes such as the
+    dynamic shared-memory opt-in must be set on each device). Needs two visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.Generator(np.random.PCG64(31))
+    ctx1 = capi.Context(1)
+    for m, d in (W.qso_kspace(), W.qso_rspace()):
+        p = m.random_batch(300, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.7, 1.3)})
+        g0, d0 = capi.Model(ctx, m), capi.Data(ctx, d)
+        g1, d1 = capi.Model(ctx1, m), capi.Data(ctx1, d)
+        a, sa = capi.chi2_batch(ctx, g0, d0, p)
+        b, sb = capi.chi2_batch(ctx1, g1, d1, p)
+        assert np.array_equal(a, b) and np.array_equal(sa, sb)
+        for h in (g0, d0, g1, d1):
+            h.close()
+    ctx1.close()
