@@ -330,7 +330,11 @@ def main_reference(args, rank, world):
         return None
     model, data = build_workload()
     cores = os.cpu_count() or 1
-    S = args.cpu_sample or max(4, min(32, cores))
+    # bounded sample: one probe vector tells how long a vector takes on all host threads (the oracle parallelises
+    # the k->r transforms of a vector over radii), then S vectors per step such that the whole --steps/--warmup run
+    # stays within about 2.5 minutes
+    t_probe, _ = run_cpu(model, data, make_batches(model, 1, 1, seed=99)[0], cores)
+    S = args.cpu_sample or int(max(1, min(32, 150.0 / ((args.steps + args.warmup) * t_probe))))
     batches = make_batches(model, args.steps + args.warmup, S, seed=1234)
     for w in range(args.warmup):
         run_cpu(model, data, batches[w], cores)
@@ -344,7 +348,8 @@ def main_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_step": S},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d parameter vectors per step, oracle/oracle.c with OpenMP on all host threads" % S},
+                             "sample": "%d parameter vector(s) per step (sized from a %.2f s probe vector so that the run stays within minutes), "
+                                       "oracle/oracle.c with OpenMP on all host threads" % (S, t_probe)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     return line
