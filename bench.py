@@ -37,6 +37,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "fp64 model+chi2 evaluations per second (batched)"
 UNIT = "evals/s"
+CPU_NOTE = ("the oracle evaluates the k->r transforms by brute-force Gauss-Legendre quadrature (an independent check of the GPU's "
+            "Bessel-weight GEMM), not by the multipole transform of the reference's cosmo library, so it is much slower per "
+            "evaluation than the reference binary: the reference's own 25-39 s per k-space fit (config/BOSSDR11LyaF_k.ini header, "
+            "hardware unspecified, ~10^3 evaluations per fit) corresponds to order 10-100 evaluations/s on one core")
 WORKLOAD = ("BOSSDR11QSOLyaF_k: BaoKSpaceCorrelationModel cross-correlation, N_grid=512, N_data=440, "
             "synthetic distortion matrix (order 512) + 4 bicubic metal templates, real data+cov")
 
@@ -349,7 +353,7 @@ def main_reference(args, rank, world):
             "config": {"workload": WORKLOAD, "batch_per_step": S},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d parameter vector(s) per step (sized from a %.2f s probe vector so that the run stays within minutes), "
-                                       "oracle/oracle.c with OpenMP on all host threads" % (S, t_probe)},
+                                       "oracle/oracle.c with OpenMP on all host threads" % (S, t_probe), "note": CPU_NOTE},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     return line
@@ -502,7 +506,7 @@ def main_ours(args, rank, world, local_rank):
         got = h_chi2[:S].numpy()
         cpu = {"value": S / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d parameter vectors of the same workload, oracle/oracle.c with OpenMP on all host threads" % S,
-               "max_rel_chi2_diff_vs_gpu": float(np.max(np.abs(got - ref) / np.abs(ref)))}
+               "max_rel_chi2_diff_vs_gpu": float(np.max(np.abs(got - ref) / np.abs(ref))), "note": CPU_NOTE}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic parameter vectors, distortion matrix and metal templates; real BOSS DR11 QSOxLya data vector and covariance",
