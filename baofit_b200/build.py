@@ -19,7 +19,7 @@ BUILD = os.path.join(HERE, "_build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
-              "--expt-relaxed-constexpr"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fopenmp"]
 
 
 def _nvcc():
@@ -59,7 +59,7 @@ def build(force=False, verbose=False, ptxas_info=False):
             subprocess.check_call(cmd)
             rebuilt = True
     if rebuilt or not os.path.exists(LIB):
-        cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
+        cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread", "-lgomp"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

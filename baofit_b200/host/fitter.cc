@@ -162,8 +162,9 @@ void CorrelationFitter::gramProbes(std::vector<double> const &centres, std::vect
 
 void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys, std::vector<int> const *toyOfFit) const {
     const bool verbose = std::getenv("BAOFIT_VERBOSE_FITS") != nullptr;
-    double tGram = 0, tChi2 = 0, t0 = nowSeconds();
+    double tGram = 0, tChi2 = 0, tSolve = 0, t0 = nowSeconds();
     long nGram = 0, nChi2 = 0, rounds = 0;
+    std::vector<size_t> offsets;
     std::vector<double> flatJ, steps, flatP, gram, chi2;
     std::vector<char> bad;
     std::vector<int> jfits, pfits, jtoy, ptoy;
@@ -191,7 +192,13 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             gramProbes(flatJ, steps, (int)kv.second.size(), (G - 1) / 2, gram, bad, toys, toys ? jtoy.data() : nullptr);
             tGram += nowSeconds() - ta;
             nGram += (long)kv.second.size() * G;
-            for (size_t q = 0; q < kv.second.size(); ++q) fits[kv.second[q]].consumeJacobian(gram.data() + q * G * G, bad[q] != 0);
+            // the normal equations of the fits are independent: solved on all host threads
+            ta = nowSeconds();
+            const long nq = (long)kv.second.size();
+            std::vector<int> const &members = kv.second;
+#pragma omp parallel for schedule(static) if (nq >= 128)
+            for (long q = 0; q < nq; ++q) fits[members[q]].consumeJacobian(gram.data() + (size_t)q * G * G, bad[q] != 0);
+            tSolve += nowSeconds() - ta;
         }
         if (!pfits.empty()) {
             flatP.clear();
@@ -205,17 +212,20 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             chiSquareFlat(flatP, (int)(flatP.size() / npar), chi2, toys, toys ? ptoy.data() : nullptr);
             tChi2 += nowSeconds() - ta;
             nChi2 += (long)(flatP.size() / npar);
+            ta = nowSeconds();
+            offsets.assign(pfits.size(), 0);
             size_t off = 0;
-            for (int k : pfits) {
-                int np = fits[k].pending();
-                fits[k].consumePoints(chi2.data() + off);
-                off += np;
-            }
+            for (size_t q = 0; q < pfits.size(); ++q) { offsets[q] = off; off += fits[pfits[q]].pending(); }
+            const long np = (long)pfits.size();
+#pragma omp parallel for schedule(static) if (np >= 128)
+            for (long q = 0; q < np; ++q) fits[pfits[q]].consumePoints(chi2.data() + offsets[q]);
+            tSolve += nowSeconds() - ta;
         }
     }
     if (verbose)
-        std::fprintf(stderr, "runLockStepLM: %zu fits, %ld rounds, %.3f s total: bf_gram_batch %.3f s (%ld points), bf_chi2_batch %.3f s (%ld points)\n",
-                     fits.size(), rounds, nowSeconds() - t0, tGram, nGram, tChi2, nChi2);
+        std::fprintf(stderr, "runLockStepLM: %zu fits, %ld rounds, %.3f s total: bf_gram_batch %.3f s (%ld points), bf_chi2_batch %.3f s (%ld points), "
+                             "per-fit solves %.3f s\n",
+                     fits.size(), rounds, nowSeconds() - t0, tGram, nGram, tChi2, nChi2, tSolve);
 }
 
 void CorrelationFitter::mcmc(likely::FunctionMinimumPtr fminStart, int nchain, int interval, std::vector<double> &samples, int nwalkers,
