@@ -22,7 +22,7 @@ EXPORTS = [
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
     "bf_fft_planes_batch", "bf_model_fft_plane_dims",
-    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch", "bf_gram_probes",
+    "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch", "bf_gram_probes", "bf_normal_probes", "bf_pinned_alloc", "bf_pinned_free",
 ]
 
 
@@ -77,6 +77,10 @@ def lib():
                                          C.c_void_p, C.c_void_p]
         L.bf_gram_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+        L.bf_normal_probes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bf_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.bf_pinned_free.argtypes = [C.c_void_p]
         L.bf_gram_probes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
         L.bf_fft_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
@@ -252,6 +256,20 @@ def gram_probes(ctx, model, data, centres, steps, toys=None, toy_index=None):
     _check(lib().bf_gram_probes(ctx.h, model.h, data.h, _ptr(c), _ptr(h), nfit, nprobe, toys.h if toys is not None else None,
                                 _ptr(idx), _ptr(gram), _ptr(status)))
     return gram, status
+
+
+def normal_probes(ctx, model, data, centres, steps, toys=None, toy_index=None):
+    """bf_normal_probes: the probe groups of gram_probes reduced on the GPU to normal equations:
+    M[nfit, n+1, n+1] = [y0 a]^T [y0 a] with a_i = y(x+h_i) - y(x-h_i), t[nfit, n] = y0 . (y(x+h_i) + y(x-h_i) - 2 y0)."""
+    c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, model.npar)
+    h = np.ascontiguousarray(steps, dtype=np.float64).reshape(-1, model.npar)
+    nfit, n = c.shape[0], int(np.count_nonzero(h[0]))
+    out = np.zeros((nfit, (n + 1) * (n + 1) + n))
+    status = np.zeros(nfit, dtype=np.int32)
+    idx = None if toy_index is None else np.ascontiguousarray(toy_index, dtype=np.int32)
+    _check(lib().bf_normal_probes(ctx.h, model.h, data.h, _ptr(c), _ptr(h), nfit, n, toys.h if toys is not None else None,
+                                  _ptr(idx), _ptr(out), _ptr(status)))
+    return out[:, :(n + 1) * (n + 1)].reshape(nfit, n + 1, n + 1), out[:, (n + 1) * (n + 1):], status
 
 
 def eval_batch(ctx, model, data, params):

@@ -45,6 +45,14 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
     BF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     BF_CUDA_OK(cudaMallocHost((void **)&c->pinned_flag, 256));
+    {   // keep stream-ordered allocations (toy tables) cached in the device pool between studies
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return BF_OK;
 }
@@ -1566,15 +1574,17 @@ extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth
     bf_toys *t = new bf_toys();
     t->ctx = ctx; t->ntoy = ntoy; t->n = d->n;
     double *d_truth = nullptr;
-    cudaError_t e = cudaMalloc((void **)&t->d_table, (size_t)ntoy * d->n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_truth, (size_t)d->n * sizeof(double));
-    if (e != cudaSuccess) { if (t->d_table) cudaFree(t->d_table); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
+    // stream-ordered allocations from the device's pool (its release threshold is raised in bf_ctx_create): a toy
+    // study is a 30 ms burst, a cudaMalloc / cudaFree pair per study would be a visible part of it
+    cudaError_t e = cudaMallocAsync((void **)&t->d_table, (size_t)ntoy * d->n * sizeof(double), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_truth, (size_t)d->n * sizeof(double), ctx->stream);
+    if (e != cudaSuccess) { if (t->d_table) cudaFreeAsync(t->d_table, ctx->stream); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
     cudaMemcpyAsync(d_truth, truth, (size_t)d->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     BF_KERNEL(ctx, "toy_noise_kernel",
               launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, t->d_table));
+    cudaFreeAsync(d_truth, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_truth);
-    if (e != cudaSuccess) { cudaFree(t->d_table); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaFreeAsync(t->d_table, ctx->stream); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
     *out = t;
     return BF_OK;
 }
@@ -1582,7 +1592,7 @@ extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth
 extern "C" int bf_toys_destroy(bf_toys *t) {
     if (!t) return BF_OK;
     cudaSetDevice(t->ctx->device);
-    cudaFree(t->d_table);
+    cudaFreeAsync(t->d_table, t->ctx->stream);
     delete t;
     return BF_OK;
 }
@@ -1684,9 +1694,34 @@ extern "C" int bf_gram_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, c
     return BF_OK;
 }
 
+static int gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *centres, const double *steps, int nfit,
+                       int nprobe, const bf_toys *toys, const int *toy_index, double *gram, int *status, bool normal);
+
 extern "C" int bf_gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *centres, const double *steps,
                               int nfit, int nprobe, const bf_toys *toys, const int *toy_index, double *gram, int *status) {
+    return gram_probes(ctx, m, d, centres, steps, nfit, nprobe, toys, toy_index, gram, status, false);
+}
+
+extern "C" int bf_normal_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *centres, const double *steps,
+                                int nfit, int nprobe, const bf_toys *toys, const int *toy_index, double *normal, int *status) {
+    return gram_probes(ctx, m, d, centres, steps, nfit, nprobe, toys, toy_index, normal, status, true);
+}
+
+extern "C" int bf_pinned_alloc(size_t bytes, void **ptr) {
+    if (!ptr) BF_FAIL(BF_ERR_OPTIONS, "bf_pinned_alloc: null argument");
+    BF_CUDA_OK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return BF_OK;
+}
+
+extern "C" int bf_pinned_free(void *ptr) {
+    if (ptr) BF_CUDA_OK(cudaFreeHost(ptr));
+    return BF_OK;
+}
+
+static int gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *centres, const double *steps, int nfit,
+                       int nprobe, const bf_toys *toys, const int *toy_index, double *gram, int *status, bool normal) {
     const int G = 2 * nprobe + 1;
+    const size_t per_fit = normal ? (size_t)(nprobe + 1) * (nprobe + 1) + nprobe : (size_t)G * G;
     if (!gram || !steps || nfit <= 0 || nprobe < 0 || G > 96) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: bad argument (2 nprobe + 1 <= 96)");
     int rc = check_args(ctx, m, d, centres, nfit);
     if (rc) return rc;
@@ -1706,7 +1741,7 @@ extern "C" int bf_gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, 
     const int colcap = fits_per_pass * G, ldy = round_up(colcap, kPadN);
     size_t nb_cs = al((size_t)fits_per_pass * npar * sizeof(double)), nb_params = al((size_t)colcap * npar * sizeof(double)),
            nb_idx = al((size_t)colcap * sizeof(int)), nb_st = al((size_t)colcap * sizeof(int)), nb_sf = al((size_t)fits_per_pass * sizeof(int)),
-           nb_gram = al((size_t)fits_per_pass * G * G * sizeof(double)), nb_ov = toys ? al((size_t)colcap * n * sizeof(double)) : 0,
+           nb_gram = al((size_t)fits_per_pass * per_fit * sizeof(double)), nb_ov = toys ? al((size_t)colcap * n * sizeof(double)) : 0,
            nb_y = al((size_t)d->n_pad * ldy * sizeof(double));
     if ((rc = ensure(&ctx->io, &ctx->io_bytes, 2 * nb_cs + nb_params + nb_idx + nb_st + nb_sf + nb_gram + nb_ov + nb_y))) return rc;
     char *p = (char *)ctx->io;
@@ -1727,8 +1762,9 @@ extern "C" int bf_gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, 
             BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
         }
         if ((rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st))) return rc;
-        BF_KERNEL(ctx, "gram_kernel", launch_gram(s, d_y, ldy, n, G, nf, d_gram));
-        BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * G * G, d_gram, (size_t)nf * G * G * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (normal) BF_KERNEL(ctx, "normal_probes_kernel", launch_normal_probes(s, d_y, ldy, n, nprobe, nf, d_gram));
+        else BF_KERNEL(ctx, "gram_kernel", launch_gram(s, d_y, ldy, n, G, nf, d_gram));
+        BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * per_fit, d_gram, (size_t)nf * per_fit * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (status) {
             BF_KERNEL(ctx, "reduce_status_kernel", launch_reduce_status(s, d_st, nf, G, d_sf));
             BF_CUDA_OK(cudaMemcpyAsync(status + f0, d_sf, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -193,6 +193,8 @@ void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const do
 
 // per fit f: Gram matrix of [y0, y1-y0, ..., y_{G-1}-y0] over the columns f*G .. f*G+G-1 of Y (ld = ldy)
 void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out);
+// normal equations of central probes: out[f] = (n+1)^2 matrix [y0 a]^T [y0 a] then n values y0 . s (see the kernel)
+void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out);
 // params[(f*G + g)*npar + j] of the central-difference probe groups (bf_gram_probes); status_fit[f] = OR of status[f*G..]
 void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params);
 void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, int *status_fit);

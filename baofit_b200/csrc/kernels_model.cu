@@ -954,6 +954,63 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y,
     for (int q = 0; q < np; ++q) { o[pi[q] * G + pj[q]] = acc[q]; o[pj[q] * G + pi[q]] = acc[q]; }
 }
 
+// Normal equations of central probes. The G = 2 n + 1 columns of a fit are y0, y(x + h_1), y(x - h_1), ...; with
+// a_i = y(x + h_i) - y(x - h_i) and s_i = y(x + h_i) + y(x - h_i) - 2 y0 a minimiser needs only
+//   M = [y0 a_1 .. a_n]^T [y0 a_1 .. a_n]   ((n+1)^2, symmetric)   and   t_i = y0 . s_i   (n values),
+// a quarter of the full Gram matrix to compute and to send back: out[f] = M (row-major) followed by t.
+__global__ void __launch_bounds__(256) normal_probes_kernel(const double *__restrict__ Y, int ldy, int nrows, int n, int nfit,
+                                                            double *__restrict__ out) {
+    extern __shared__ double nsm[];  // [kGramRows][R + n]: y0, a_1..a_n, s_1..s_n
+    const int f = blockIdx.x, tid = threadIdx.x, G = 2 * n + 1, R = n + 1, W = R + n;
+    const int npairs = R * (R + 1) / 2 + n;  // pairs (i >= j) of M, then the n dot products y0 . s_i
+    double acc[6];                           // R <= 48: at most 1224 values over 256 threads
+    int pi[6], pj[6], np = 0;
+    for (int p = tid; p < npairs && np < 6; p += blockDim.x) {
+        int i, j;
+        if (p < R * (R + 1) / 2) {
+            i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > p) --i;
+            while ((i + 1) * (i + 2) / 2 <= p) ++i;
+            j = p - i * (i + 1) / 2;
+        } else {
+            i = R + (p - R * (R + 1) / 2);  // column of s
+            j = 0;
+        }
+        pi[np] = i; pj[np] = j; acc[np] = 0.0; ++np;
+    }
+    const double *base = Y + (size_t)f * G;
+    for (int r0 = 0; r0 < nrows; r0 += kGramRows) {
+        const int nr = min(kGramRows, nrows - r0);
+        __syncthreads();
+        for (int e = tid; e < nr * R; e += blockDim.x) {
+            const int r = e / R, c = e - r * R;
+            const double *row = base + (size_t)(r0 + r) * ldy;
+            if (c == 0) nsm[r * W] = row[0];
+            else {
+                const double yp = row[2 * c - 1], ym = row[2 * c];
+                nsm[r * W + c] = yp - ym;
+                nsm[r * W + R + c - 1] = (yp - row[0]) + (ym - row[0]);
+            }
+        }
+        __syncthreads();
+        for (int q = 0; q < np; ++q) {
+            double s = acc[q];
+            const int i = pi[q], j = pj[q];
+            for (int r = 0; r < nr; ++r) s = fma(nsm[r * W + i], nsm[r * W + j], s);
+            acc[q] = s;
+        }
+    }
+    double *o = out + (size_t)f * (R * R + n);
+    for (int q = 0; q < np; ++q) {
+        if (pi[q] < R) { o[pi[q] * R + pj[q]] = acc[q]; o[pj[q] * R + pi[q]] = acc[q]; }
+        else o[R * R + pi[q] - R] = acc[q];
+    }
+}
+
+void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out) {
+    normal_probes_kernel<<<nfit, 256, (size_t)kGramRows * (2 * n + 1) * sizeof(double), s>>>(Y, ldy, nrows, n, nfit, out);
+}
+
 void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out) {
     gram_kernel<<<nfit, 256, (size_t)kGramRows * G * sizeof(double), s>>>(Y, ldy, nrows, G, nfit, out);
 }

@@ -404,6 +404,10 @@ public:
     // the same with the probe columns generated on the GPU from centres / steps (bf_gram_probes)
     void gramProbes(std::vector<double> const &centres, std::vector<double> const &steps, int nfit, int nprobe, std::vector<double> &gram,
                     std::vector<char> &bad, bf_toys const *toys = nullptr, const int *toyIndexPerFit = nullptr) const;
+    // the same probes reduced on the device to the normal equations (bf_normal_probes); the returned buffer is
+    // page-locked, owned by the calling thread and valid until its next call: [(nprobe+1)^2 + nprobe] per fit
+    const double *normalProbes(std::vector<double> const &centres, std::vector<double> const &steps, int nfit, int nprobe,
+                               std::vector<char> &bad, bf_toys const *toys = nullptr, const int *toyIndexPerFit = nullptr) const;
     // Runs many LM fits in lock step (Jacobian rounds through gramFlat, trial rounds through chiSquareFlat);
     // toyOfFit (optional) gives the realisation each fit is taken against.
     void runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys = nullptr, std::vector<int> const *toyOfFit = nullptr) const;

@@ -160,8 +160,46 @@ void CorrelationFitter::gramProbes(std::vector<double> const &centres, std::vect
     for (int f = 0; f < nfit; ++f) bad[f] = status[f] != 0;
 }
 
+namespace {
+// page-locked result buffer that grows on demand (one per host thread): device-to-host copies of the normal
+// equations and chi-squares of a round run at full PCIe speed instead of through the driver's staging buffers
+struct PinnedBuffer {
+    double *p = nullptr;
+    size_t n = 0;
+    ~PinnedBuffer() { if (p) bf_pinned_free(p); }
+    double *get(size_t count) {
+        if (count > n) {
+            if (p) bf_pinned_free(p);
+            p = nullptr; n = 0;
+            void *q = nullptr;
+            check(bf_pinned_alloc((count + count / 4) * sizeof(double), &q), "bf_pinned_alloc");
+            p = (double *)q; n = count + count / 4;
+        }
+        return p;
+    }
+};
+}  // namespace
+
+const double *CorrelationFitter::normalProbes(std::vector<double> const &centres, std::vector<double> const &steps, int nfit, int nprobe,
+                                              std::vector<char> &bad, bf_toys const *toys, const int *toyIndexPerFit) const {
+    static thread_local PinnedBuffer buffer;
+    const size_t per = (size_t)(nprobe + 1) * (nprobe + 1) + nprobe;
+    bad.assign(nfit, 0);
+    if (nfit == 0) return nullptr;
+    double *out = buffer.get(per * nfit);
+    std::vector<int> status(nfit);
+    check(bf_normal_probes(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), centres.data(), steps.data(), nfit,
+                           nprobe, toys, toys ? toyIndexPerFit : nullptr, out, status.data()),
+          "bf_normal_probes");
+    for (int f = 0; f < nfit; ++f) bad[f] = status[f] != 0;
+    return out;
+}
+
 void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys const *toys, std::vector<int> const *toyOfFit) const {
     const bool verbose = std::getenv("BAOFIT_VERBOSE_FITS") != nullptr;
+    // BAOFIT_VERBOSE_FITS >= 3: per-kernel CUDA-event times of the whole run (perturbs the wall times printed below)
+    const bool kernelProfile = verbose && std::atoi(std::getenv("BAOFIT_VERBOSE_FITS")) >= 3;
+    if (kernelProfile) bf_ctx_set_profiling(deviceContext(), 1);
     double tGram = 0, tChi2 = 0, tSolve = 0, t0 = nowSeconds();
     long nGram = 0, nChi2 = 0, rounds = 0;
     std::vector<size_t> offsets;
@@ -189,7 +227,9 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
                 if (toys) jtoy.push_back((*toyOfFit)[k]);
             }
             double ta = nowSeconds();
-            gramProbes(flatJ, steps, (int)kv.second.size(), (G - 1) / 2, gram, bad, toys, toys ? jtoy.data() : nullptr);
+            const int nprobe = (G - 1) / 2;
+            const double *normal = normalProbes(flatJ, steps, (int)kv.second.size(), nprobe, bad, toys, toys ? jtoy.data() : nullptr);
+            const size_t per = (size_t)(nprobe + 1) * (nprobe + 1) + nprobe;
             tGram += nowSeconds() - ta;
             nGram += (long)kv.second.size() * G;
             // the normal equations of the fits are independent: solved on all host threads
@@ -197,7 +237,7 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             const long nq = (long)kv.second.size();
             std::vector<int> const &members = kv.second;
 #pragma omp parallel for schedule(static) if (nq >= 128)
-            for (long q = 0; q < nq; ++q) fits[members[q]].consumeJacobian(gram.data() + (size_t)q * G * G, bad[q] != 0);
+            for (long q = 0; q < nq; ++q) fits[members[q]].consumeNormal(normal + (size_t)q * per, bad[q] != 0);
             tSolve += nowSeconds() - ta;
         }
         if (!pfits.empty()) {
@@ -223,9 +263,17 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
         }
     }
     if (verbose)
-        std::fprintf(stderr, "runLockStepLM: %zu fits, %ld rounds, %.3f s total: bf_gram_batch %.3f s (%ld points), bf_chi2_batch %.3f s (%ld points), "
+        std::fprintf(stderr, "runLockStepLM: %zu fits, %ld rounds, %.3f s total: bf_normal_probes %.3f s (%ld points), bf_chi2_batch %.3f s (%ld points), "
                              "per-fit solves %.3f s\n",
                      fits.size(), rounds, nowSeconds() - t0, tGram, nGram, tChi2, nChi2, tSolve);
+    if (kernelProfile) {
+        const char *names[64];
+        double ms[64];
+        long long launches[64];
+        int n = std::min(64, bf_ctx_get_profile(deviceContext(), 64, names, ms, launches));
+        for (int k = 0; k < n; ++k) std::fprintf(stderr, "  %-48s %9.3f ms in %6lld launches\n", names[k], ms[k], launches[k]);
+        bf_ctx_set_profiling(deviceContext(), 0);
+    }
 }
 
 void CorrelationFitter::mcmc(likely::FunctionMinimumPtr fminStart, int nchain, int interval, std::vector<double> &samples, int nwalkers,

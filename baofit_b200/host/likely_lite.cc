@@ -489,31 +489,48 @@ void LMFit::solveStep() {
 }
 
 void LMFit::consumeJacobian(const double *gram, bool bad) {
-    const int G = 2 * _n + 1;
+    // reduce the full Gram matrix of [y0, d+_1, d-_1, ...] (d = y(x +- h_i) - y0) to the normal-equation form
+    const int G = 2 * _n + 1, R = _n + 1;
+    for (int k = 0; k < G * G && !bad; ++k) bad |= !std::isfinite(gram[k]);
+    std::vector<double> red((size_t)R * R + _n, 0.0);
+    if (!bad) {
+        auto gm = [&](int a, int b) { return gram[a * G + b]; };
+        red[0] = gm(0, 0);
+        for (int i = 0; i < _n; ++i) {
+            const int ip = 2 * i + 1, im = 2 * i + 2;
+            red[(i + 1) * R] = red[i + 1] = gm(ip, 0) - gm(im, 0);
+            red[(size_t)R * R + i] = gm(ip, 0) + gm(im, 0);
+            for (int j = 0; j < _n; ++j) {
+                const int jp = 2 * j + 1, jm = 2 * j + 2;
+                red[(i + 1) * R + j + 1] = gm(ip, jp) - gm(ip, jm) - gm(im, jp) + gm(im, jm);
+            }
+        }
+    } else
+        red[0] = gram[0];
+    consumeNormal(red.data(), bad);
+}
+
+void LMFit::consumeNormal(const double *normal, bool bad) {
+    const int G = 2 * _n + 1, R = _n + 1;
     _neval += G;
     const double inf = std::numeric_limits<double>::infinity();
-    for (int k = 0; k < G * G && !bad; ++k) bad |= !std::isfinite(gram[k]);
+    for (int k = 0; k < R * R + _n && !bad; ++k) bad |= !std::isfinite(normal[k]);
     if (bad) {
         // a probe (or the centre) left the valid domain: shrink the probe steps; a bad centre is fatal
-        if (!std::isfinite(gram[0]) || ++_shrinks > 8) { _failed = true; _f0 = inf; _stage = Done; return; }
+        if (!std::isfinite(normal[0]) || ++_shrinks > 8) { _failed = true; _f0 = inf; _stage = Done; return; }
         for (auto &h : _h) h *= 0.25;
         return;
     }
-    _f0 = _cs * 0.5 * gram[0] + priorValue(_x);
-    // with d+_i = y(x + h_i) - y0 (column 2i+1) and d-_i = y(x - h_i) - y0 (column 2i+2):
-    //   J_i = (d+_i - d-_i)/(2 h_i),   y0.d2y/dx_i^2 = y0.(d+_i + d-_i)/h_i^2
-    auto gm = [&](int a, int b) { return gram[a * G + b]; };
+    _f0 = _cs * 0.5 * normal[0] + priorValue(_x);
+    // with a_i = y(x + h_i) - y(x - h_i) and s_i = y(x + h_i) + y(x - h_i) - 2 y0:
+    //   J_i = a_i/(2 h_i),   y0.d2y/dx_i^2 = y0.s_i/h_i^2
     for (int i = 0; i < _n; ++i) {
-        const int ip = 2 * i + 1, im = 2 * i + 2;
         double pv, pg, ph;
         priorDerivatives(_params[_fidx[i]], _x[_fidx[i]], pv, pg, ph);
-        _g[i] = _cs * (gm(ip, 0) - gm(im, 0)) / (2 * _h[i]) + _ps * pg;
-        for (int j = 0; j < _n; ++j) {
-            const int jp = 2 * j + 1, jm = 2 * j + 2;
-            _A[i * _n + j] = _cs * (gm(ip, jp) - gm(ip, jm) - gm(im, jp) + gm(im, jm)) / (4 * _h[i] * _h[j]);
-        }
+        _g[i] = _cs * normal[(i + 1) * R] / (2 * _h[i]) + _ps * pg;
+        for (int j = 0; j < _n; ++j) _A[i * _n + j] = _cs * normal[(i + 1) * R + j + 1] / (4 * _h[i] * _h[j]);
         // diagonal of the second-order term, kept only while the curvature stays positive
-        const double second = _cs * (gm(ip, 0) + gm(im, 0)) / (_h[i] * _h[i]);
+        const double second = _cs * normal[(size_t)R * R + i] / (_h[i] * _h[i]);
         if (_A[i * _n + i] + second > 0.1 * _A[i * _n + i]) _A[i * _n + i] += second;
         _A[i * _n + i] += _ps * ph;
     }

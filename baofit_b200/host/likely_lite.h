@@ -139,6 +139,9 @@ public:
     int nFloating() const { return _n; }
     // gram[G*G] as returned by bf_gram_batch; bad = some column had a non-zero status
     void consumeJacobian(const double *gram, bool bad);
+    // the same round fed with the device-reduced normal equations of bf_normal_probes: (n+1)^2 + n values
+    void consumeNormal(const double *normal, bool bad);
+    int normalSize() const { return (_n + 1) * (_n + 1) + _n; }
     // trial round: appends pending() full-length vectors
     void requestPoints(std::vector<double> &flat);
     int pending() const { return _npending; }

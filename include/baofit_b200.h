@@ -27,6 +27,8 @@
 #ifndef BAOFIT_B200_H
 #define BAOFIT_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -326,6 +328,16 @@ int bf_gram_batch(bf_ctx *ctx, const bf_model *model, const bf_data *data, const
  * cross the bus. gram[nfit][G][G] as in bf_gram_batch; status[nfit] is the OR over the group. */
 int bf_gram_probes(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *centres, const double *steps,
                    int nfit, int nprobe, const bf_toys *toys, const int *toy_index, double *gram, int *status);
+/* The same probes reduced on the device to what a Gauss-Newton / Levenberg-Marquardt step reads (a quarter of the Gram
+ * matrix to compute and to copy back). With y0 = y(x), a_i = y(x + h_i) - y(x - h_i), s_i = y(x + h_i) + y(x - h_i) - 2 y0:
+ * normal[f] = the (nprobe+1) x (nprobe+1) matrix [y0 a_1 .. a_n]^T [y0 a_1 .. a_n] (row-major; [0][0] = chi2 at the centre,
+ * [i][0] = 2 h_i times the chi2 gradient / 2, [i][j] = 4 h_i h_j J_i . J_j) followed by the nprobe values y0 . s_i
+ * (h_i^2 times the diagonal second-order term). Replaces the same Minuit2 derivative evaluations as bf_gram_batch. */
+int bf_normal_probes(bf_ctx *ctx, const bf_model *model, const bf_data *data, const double *centres, const double *steps,
+                     int nfit, int nprobe, const bf_toys *toys, const int *toy_index, double *normal, int *status);
+/* Page-locked host memory for the buffers of the host-pointer entry points (results come back at full PCIe speed). */
+int bf_pinned_alloc(size_t bytes, void **ptr);
+int bf_pinned_free(void *ptr);
 
 #ifdef __cplusplus
 }

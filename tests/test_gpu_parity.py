@@ -288,4 +288,20 @@ def test_gram_probes_equal_explicit_probe_groups(ctx):
     a, _ = capi.gram_probes(ctx, gm, gd, centres, steps, toys, idx)
     b, _ = capi.gram_batch(ctx, gm, gd, cols, G, toys, idx)
     assert np.array_equal(a, b)
+    # bf_normal_probes: the same groups reduced on the device to [y0 a]^T [y0 a] and y0 . s. The Gram matrix holds
+    # d+ = y(x+h) - y0 and d- = y(x-h) - y0, so a = d+ - d- and s = d+ + d-.
+    n = len(fl)
+    for tt, ii in ((None, None), (toys, idx)):
+        g, _ = capi.gram_probes(ctx, gm, gd, centres, steps, tt, ii)
+        M, t, st = capi.normal_probes(ctx, gm, gd, centres, steps, tt, ii)
+        ip, im = 1 + 2 * np.arange(n), 2 + 2 * np.arange(n)
+        assert np.all(st == 0)
+        assert np.allclose(M[:, 0, 0], g[:, 0, 0], rtol=1e-13)
+        ref_a0 = g[:, ip, 0] - g[:, im, 0]
+        scale = np.sqrt(g[:, 0, 0])[:, None] * np.sqrt(np.abs(g[:, ip, ip] + g[:, im, im]))  # |y0| |d|: cancellation scale
+        assert np.max(np.abs(M[:, 1:, 0] - ref_a0) / scale) < 1e-12 and np.array_equal(M[:, 1:, 0], M[:, 0, 1:])
+        assert np.max(np.abs(t - (g[:, ip, 0] + g[:, im, 0])) / scale) < 1e-12
+        ref_aa = g[:, ip][:, :, ip] - g[:, ip][:, :, im] - g[:, im][:, :, ip] + g[:, im][:, :, im]
+        dn = np.sqrt(np.abs(g[:, ip, ip] + g[:, im, im]))
+        assert np.max(np.abs(M[:, 1:, 1:] - ref_aa) / (dn[:, :, None] * dn[:, None, :])) < 1e-12
     toys.close(), gm.close(), gd.close()
