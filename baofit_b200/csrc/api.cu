@@ -735,8 +735,11 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
         if ((rc = build_tab(d->h_r, d->h_mu, d->h_z, n, n_pad, post_slots, 2, !use_dm, p.tab_data))) return rc;
         if (use_dm && (rc = build_tab(d->h_grid_r, d->h_grid_mu, d->h_grid_z, ng, ng_pad, pre_slots, 2, true, p.tab_grid))) return rc;
     }
-    // ---- fused tail of the distortion-matrix path ----
-    if (use_dm) {
+    // ---- fused tail ----
+    // Distortion-matrix path: the post-matrix broadband and "- d" become extra K columns of [D | basis | -d] and W is
+    // folded in. Without a distortion matrix (data_mode) the same trick removes the second model pass of lean
+    // models: A = [W | W.basis | -W.d], the panel is [xi_cosmology ; coefficient rows ; 1].
+    auto build_fold = [&](bool data_mode) -> int {
         const DevBB &ba = dm.bb[BF_BB_DIST_ADD];
         bool single_class = true;
         for (int i = 1; i < n; ++i) single_class &= zc_data[i] == zc_data[0];
@@ -747,96 +750,136 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
             else if (!shift) fcase = 1;
             else if (ba.r_min == 0 && ba.r_max == 0 && ba.mu_min == 0 && ba.mu_max == 0 && ba.rp_min >= 0 && ba.rp_max <= 8) fcase = 2;
         }
-        if (fcase >= 0) {
-            auto cnt = [](int lo, int hi, int st) { return (hi - lo) / st + 1; };
-            // (the coefficient rows must fit the 64 spare rows below the xi_u panel; checked below)
-            int n_rt = ba.enabled ? cnt(ba.rt_min, ba.rt_max, ba.rt_step) : 0, n_z = ba.enabled ? cnt(ba.z_min, ba.z_max, ba.z_step) : 0;
-            int nb = 0;
-            if (fcase == 1)
-                nb = n_z * cnt(ba.mu_min, ba.mu_max, ba.mu_step) * cnt(ba.r_min, ba.r_max, ba.r_step) * cnt(ba.rp_min, ba.rp_max, ba.rp_step) * n_rt;
-            else if (fcase == 2) nb = n_z * (ba.rp_max + 1) * n_rt;
-            const int kext = round_up(nb + 1, kGemmBK), ktot = ng_pad + kext;
-            if (kext <= 64) {
-            auto legendre = [](int ell, double mu) {
-                double m2 = mu * mu;
-                switch (ell) {
-                case 0: return 1.0;
-                case 1: return mu;
-                case 2: return (-1 + 3 * m2) / 2.;
-                case 3: return mu * (-3 + 5 * m2) / 2.;
-                case 4: return (3 + m2 * (-30 + 35 * m2)) / 8.;
-                case 5: return mu * (15 + m2 * (-70 + 63 * m2)) / 8.;
-                case 6: return (-5 + m2 * (105 + m2 * (-315 + 231 * m2))) / 16.;
-                case 7: return mu * (-35 + m2 * (315 + m2 * (-693 + 429 * m2))) / 16.;
-                default: return (35 + m2 * (-1260 + m2 * (6930 + m2 * (-12012 + 6435 * m2)))) / 128.;
+        // several redshift classes among the data bins (e.g. the three z bins of BOSSDR9LyaF): the evolution factor
+        // of the broadband differs per class, so every class gets its own block of basis columns / coefficient rows
+        int ncls = 1;
+        if (fcase < 0 && data_mode && !dm.bb[BF_BB_DIST_MUL].enabled && !single_class && !shift) {
+            fcase = ba.enabled ? 1 : 0;
+            ncls = ba.enabled ? p.nz : 1;
+        }
+        if (fcase < 0) return BF_OK;
+        auto cnt = [](int lo, int hi, int st) { return (hi - lo) / st + 1; };
+        // (the coefficient rows must fit the 64 spare rows below the panel; checked below)
+        int n_rt = ba.enabled ? cnt(ba.rt_min, ba.rt_max, ba.rt_step) : 0, n_z = ba.enabled ? cnt(ba.z_min, ba.z_max, ba.z_step) : 0;
+        int nb = 0;
+        if (fcase == 1)
+            nb = n_z * cnt(ba.mu_min, ba.mu_max, ba.mu_step) * cnt(ba.r_min, ba.r_max, ba.r_step) * cnt(ba.rp_min, ba.rp_max, ba.rp_step) * n_rt;
+        else if (fcase == 2) nb = n_z * (ba.rp_max + 1) * n_rt;
+        const int nb1 = nb;  // coefficients of one class
+        nb *= ncls;
+        const int kext = round_up(nb + 1, kGemmBK), kleft = data_mode ? n_pad : ng_pad, ktot = kleft + kext;
+        if (kext > 64) return BF_OK;
+        auto legendre = [](int ell, double mu) {
+            double m2 = mu * mu;
+            switch (ell) {
+            case 0: return 1.0;
+            case 1: return mu;
+            case 2: return (-1 + 3 * m2) / 2.;
+            case 3: return mu * (-3 + 5 * m2) / 2.;
+            case 4: return (3 + m2 * (-30 + 35 * m2)) / 8.;
+            case 5: return mu * (15 + m2 * (-70 + 63 * m2)) / 8.;
+            case 6: return (-5 + m2 * (105 + m2 * (-315 + 231 * m2))) / 16.;
+            case 7: return mu * (-35 + m2 * (315 + m2 * (-693 + 429 * m2))) / 16.;
+            default: return (35 + m2 * (-1260 + m2 * (6930 + m2 * (-12012 + 6435 * m2)))) / 128.;
+            }
+        };
+        // tail columns of data bin i: the broadband basis values, then -d_i
+        auto tail_row = [&](int i, double *bs) {
+            if (ba.enabled) {
+                const double r = d->h_r[i], mu = d->h_mu[i], z = d->h_z[i];
+                const double rr = r * ba.inv_r0, rrP = r * mu * ba.inv_r0, rrT = r * std::sqrt(1 - mu * mu) * ba.inv_r0;
+                const double zz = (1 + z) / (1 + ba.z0);
+                int k = ncls > 1 ? zc_data[i] * nb1 : 0;
+                if (fcase == 1) {  // BroadbandModel.cc:204-213, one basis value per coefficient
+                    for (int zi = ba.z_min; zi <= ba.z_max; zi += ba.z_step)
+                        for (int mi = ba.mu_min; mi <= ba.mu_max; mi += ba.mu_step)
+                            for (int ri = ba.r_min; ri <= ba.r_max; ri += ba.r_step)
+                                for (int pi = ba.rp_min; pi <= ba.rp_max; pi += ba.rp_step)
+                                    for (int ti = ba.rt_min; ti <= ba.rt_max; ti += ba.rt_step)
+                                        bs[k++] = std::pow(zz, zi) * legendre(mi, mu) *
+                                                  std::pow(ri > 0 ? rr - 1 : rr, (double)ri / ba.r_denom) *
+                                                  std::pow(pi > 0 ? rrP - 1 : rrP, pi) * std::pow(ti > 0 ? rrT - 1 : rrT, ti);
+                } else {
+                    const double u = rrP - 1;
+                    for (int zi = ba.z_min; zi <= ba.z_max; zi += ba.z_step)
+                        for (int mm = 0; mm <= ba.rp_max; ++mm)
+                            for (int ti = ba.rt_min; ti <= ba.rt_max; ti += ba.rt_step)
+                                bs[k++] = std::pow(zz, zi) * std::pow(u, mm) * std::pow(ti > 0 ? rrT - 1 : rrT, ti);
                 }
-            };
+            }
+            bs[nb] = -d->h_data[i];
+        };
+        std::vector<double> wa((size_t)n_pad * ktot, 0.0);
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (!data_mode) {
             std::vector<double> aext((size_t)n_pad * ktot, 0.0);
             for (int i = 0; i < n; ++i) {
                 double *row = &aext[(size_t)i * ktot];
                 std::memcpy(row, &m->dist_matrix[(size_t)d->h_index[i] * ng], sizeof(double) * ng);
-                double *bs = row + ng_pad;
-                if (ba.enabled) {
-                    const double r = d->h_r[i], mu = d->h_mu[i], z = d->h_z[i];
-                    const double rr = r * ba.inv_r0, rrP = r * mu * ba.inv_r0, rrT = r * std::sqrt(1 - mu * mu) * ba.inv_r0;
-                    const double zz = (1 + z) / (1 + ba.z0);
-                    int k = 0;
-                    if (fcase == 1) {  // BroadbandModel.cc:204-213, one basis value per coefficient
-                        for (int zi = ba.z_min; zi <= ba.z_max; zi += ba.z_step)
-                            for (int mi = ba.mu_min; mi <= ba.mu_max; mi += ba.mu_step)
-                                for (int ri = ba.r_min; ri <= ba.r_max; ri += ba.r_step)
-                                    for (int pi = ba.rp_min; pi <= ba.rp_max; pi += ba.rp_step)
-                                        for (int ti = ba.rt_min; ti <= ba.rt_max; ti += ba.rt_step)
-                                            bs[k++] = std::pow(zz, zi) * legendre(mi, mu) *
-                                                      std::pow(ri > 0 ? rr - 1 : rr, (double)ri / ba.r_denom) *
-                                                      std::pow(pi > 0 ? rrP - 1 : rrP, pi) * std::pow(ti > 0 ? rrT - 1 : rrT, ti);
-                    } else {
-                        const double u = rrP - 1;
-                        for (int zi = ba.z_min; zi <= ba.z_max; zi += ba.z_step)
-                            for (int mm = 0; mm <= ba.rp_max; ++mm)
-                                for (int ti = ba.rt_min; ti <= ba.rt_max; ti += ba.rt_step)
-                                    bs[k++] = std::pow(zz, zi) * std::pow(u, mm) * std::pow(ti > 0 ? rrT - 1 : rrT, ti);
-                    }
-                }
-                bs[nb] = -d->h_data[i];
+                tail_row(i, row + ng_pad);
             }
             // WA = W . A_ext (W lower triangular), accumulated in long double
-            std::vector<double> wa((size_t)n_pad * ktot, 0.0);
-            {
-                unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-                std::vector<std::thread> pool;
-                for (unsigned t = 0; t < nt; ++t)
-                    pool.emplace_back([&, t] {
-                        std::vector<long double> acc(ktot);
-                        for (int i = (int)t; i < n; i += (int)nt) {
-                            std::fill(acc.begin(), acc.end(), 0.0L);
-                            for (int j = 0; j <= i; ++j) {
-                                const long double wij = d->h_W[(size_t)i * n + j];
-                                if (wij == 0) continue;
-                                const double *arow = &aext[(size_t)j * ktot];
-                                for (int k = 0; k < ktot; ++k) acc[k] += wij * arow[k];
-                            }
-                            for (int k = 0; k < ktot; ++k) wa[(size_t)i * ktot + k] = (double)acc[k];
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t)
+                pool.emplace_back([&, t] {
+                    std::vector<long double> acc(ktot);
+                    for (int i = (int)t; i < n; i += (int)nt) {
+                        std::fill(acc.begin(), acc.end(), 0.0L);
+                        for (int j = 0; j <= i; ++j) {
+                            const long double wij = d->h_W[(size_t)i * n + j];
+                            if (wij == 0) continue;
+                            const double *arow = &aext[(size_t)j * ktot];
+                            for (int k = 0; k < ktot; ++k) acc[k] += wij * arow[k];
                         }
-                    });
-                for (auto &th : pool) th.join();
-            }
+                        for (int k = 0; k < ktot; ++k) wa[(size_t)i * ktot + k] = (double)acc[k];
+                    }
+                });
+            for (auto &th : pool) th.join();
             if ((rc = upload(p.allocs, aext.data(), aext.size(), &p.d_Aext))) return rc;
-            if ((rc = upload(p.allocs, wa.data(), wa.size(), &p.d_WA))) return rc;
-            if (n_pad <= kFullmMaxM && n_pad % 32 == 0 && ktot % kFullmKC == 0) {
-                std::vector<double> wat((size_t)(ktot / kFullmKC) * n_pad * kFullmLdA);
-                gemm_fullm_tile_A(wa.data(), n_pad, ktot, ktot, wat.data());
-                if ((rc = upload(p.allocs, wat.data(), wat.size(), &p.d_WAt))) return rc;
-            }
-            p.fold_ok = true;
-            p.fold_case = fcase;
-            p.fold_nb = nb;
-            p.fold_kext = kext;
-            p.fold_pmax = ba.enabled ? ba.rp_max : 0;
-            p.fold_nrt = n_rt;
-            p.fold_nz = n_z;
-            }
+        } else {
+            // [W | W.tail]: the left block is W itself, only the kext tail columns need a product
+            std::vector<double> tails((size_t)n * kext, 0.0);
+            for (int i = 0; i < n; ++i) tail_row(i, &tails[(size_t)i * kext]);
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t)
+                pool.emplace_back([&, t] {
+                    std::vector<long double> acc(kext);
+                    for (int i = (int)t; i < n; i += (int)nt) {
+                        double *row = &wa[(size_t)i * ktot];
+                        std::fill(acc.begin(), acc.end(), 0.0L);
+                        for (int j = 0; j <= i; ++j) {
+                            const double wij = d->h_W[(size_t)i * n + j];
+                            row[j] = wij;
+                            if (wij == 0) continue;
+                            const double *trow = &tails[(size_t)j * kext];
+                            for (int k = 0; k < kext; ++k) acc[k] += (long double)wij * trow[k];
+                        }
+                        for (int k = 0; k < kext; ++k) row[n_pad + k] = (double)acc[k];
+                    }
+                });
+            for (auto &th : pool) th.join();
         }
+        if ((rc = upload(p.allocs, wa.data(), wa.size(), &p.d_WA))) return rc;
+        if (!data_mode && n_pad <= kFullmMaxM && n_pad % 32 == 0 && ktot % kFullmKC == 0) {
+            std::vector<double> wat((size_t)(ktot / kFullmKC) * n_pad * kFullmLdA);
+            gemm_fullm_tile_A(wa.data(), n_pad, ktot, ktot, wat.data());
+            if ((rc = upload(p.allocs, wat.data(), wat.size(), &p.d_WAt))) return rc;
+        }
+        p.fold_ok = true;
+        p.fold_data_mode = data_mode;
+        p.fold_case = fcase;
+        p.fold_nb = nb;
+        p.fold_ncls = ncls;
+        p.fold_kext = kext;
+        p.fold_pmax = ba.enabled ? ba.rp_max : 0;
+        p.fold_nrt = n_rt;
+        p.fold_nz = n_z;
+        return BF_OK;
+    };
+    if (use_dm) {
+        if ((rc = build_fold(false))) return rc;
+    } else if (dm.kind == BF_MODEL_KSPACE && dm.metal_kind == BF_METAL_NONE && !(dm.flags & BF_FLAG_RADIATION_MODEL) && d->h_W.size() == (size_t)n * n) {
+        if ((rc = build_fold(true))) return rc;
     }
     auto ins = d->plans.emplace(m, std::move(p));
     *out = &ins.first->second;
@@ -867,7 +910,7 @@ size_t ws_fixed_doubles(const DevModel &dm) {
 }
 
 size_t ws_doubles_per_column(const DevModel &dm, const bf_data *d, int nz) {
-    size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + 2 /*rank, sorted chi2*/ + d->n_pad /*Z*/;
+    size_t c = (size_t)dm.npar + (size_t)nz * 3 + 1 /*status*/ + 2 /*rank, sorted chi2*/ + d->n_pad + 64 /*Z + fused-tail rows*/;
     if (dm.kind == BF_MODEL_KSPACE) c += (size_t)6 * dm.nk_pad + (size_t)12 * dm.nr_pad;
     if (dm.dm_order > 0) c += (size_t)d->n_grid_pad + 64 + d->n_pad;  // xi_u panel (+ fused-tail rows) and Y
     if (dm.kind == BF_MODEL_KSPACE_FFT) c += 2 + kFftKeyMax + (size_t)dm.fft.my_pad + (size_t)2 * dm.fft.npy_pad * dm.fft.npx_pad;
@@ -899,7 +942,7 @@ void carve(void *base, const DevModel &dm, const bf_data *d, int nz, int ldb, Wo
     w.status = (int *)take(1);
     w.rank = (int *)take(1);
     w.chi2_sorted = take(1);
-    w.Z = take(d->n_pad);
+    w.Z = take((size_t)d->n_pad + 64);
     w.G = w.T = w.C2 = w.XiU = w.Y = nullptr;
     if (dm.kind == BF_MODEL_KSPACE) {
         w.G = take((size_t)6 * dm.nk_pad);
@@ -1275,6 +1318,38 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
         a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
         if (dm.kind == BF_MODEL_RSPACE) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
+        else if (shared_tables && plan->fold_ok && plan->fold_data_mode && (what == OUT_CHI2 || what == OUT_WHITENED)) {
+            // fused data tail: cosmology pass into Z, broadband coefficients and the "- d" switch as extra rows,
+            // one GEMM against [W | W.basis | -W.d] (triangular block + dense tail columns)
+            fill_tab(plan->tab_data, false, fa.pt);
+            fa.mode = 0; fa.out = w.Z; fa.ldo = ldb; fa.dsub = nullptr; fa.dov = d_override;
+            fa.sub_dov_in_part1 = d_override ? 1 : 0;
+            BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
+            FoldArgs fo;
+            std::memset(&fo, 0, sizeof(fo));
+            fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
+            fo.zc_data = plan->zc_trigger;
+            fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
+            fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz; fo.ncls = plan->fold_ncls;
+            fo.minus_d_row_value = d_override ? 0 : 1;  // with an override the data were subtracted column by column
+            fo.rows = w.Z + (size_t)d->n_pad * ldb;
+            fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
+            BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
+            GemmArgs g{};
+            g.A = plan->d_WA; g.Bm = w.Z;
+            g.M = d->n_pad; g.N = B; g.K = d->n_pad + plan->fold_kext;
+            g.lda = g.K; g.ldb = ldb;
+            g.lower_triangular = 1; g.k_tri = d->n_pad;
+            if (what == OUT_CHI2) {
+                g.C = nullptr; g.ldc = 0; g.chi2 = chi2_dst; g.status = w.status;
+                if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+                BF_KERNEL(ctx, "dgemm_chi2_kernel[fused data tail]", launch_gemm_chi2(s, g, ctx->sm_count));
+            } else {
+                g.C = d_out; g.ldc = ldo;
+                BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused data tail]", launch_gemm_store(s, g, 1));
+            }
+            finished = true;
+        }
         else if (shared_tables) {
             fill_tab(plan->tab_data, false, fa.pt);
             fa.pt.npts_pad = a.npts_pad;
@@ -1298,7 +1373,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
         BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
     }
-    if (what == OUT_WHITENED) {
+    if (what == OUT_WHITENED && !finished) {
         GemmArgs g{};
         g.A = d->d_W; g.Bm = w.Z; g.C = d_out;
         g.M = d->n_pad; g.N = B; g.K = d->n_pad;

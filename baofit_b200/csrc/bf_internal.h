@@ -220,6 +220,8 @@ struct bf_data {
         // Fused tail of the distortion-matrix path: chi2 = || WA . [xi_u ; coef(b) ; 1] ||^2 with
         // WA = W . [D_kept | broadband basis | -d]  (see DESIGN.md "fused tail")
         bool fold_ok = false;
+        int fold_ncls = 1;            // redshift classes with their own block of broadband rows (data mode)
+        bool fold_data_mode = false;  // fused tail without a distortion matrix: d_WA = [W | W.basis | -W.d]
         int fold_case = 0;            // 0: no post broadband, 1: static basis (no velocity shift), 2: binomial in dpi
         int fold_nb = 0, fold_kext = 0;  // number of basis columns; extra K rows (multiple of 16)
         int fold_pmax = 0, fold_nrt = 0, fold_nz = 0;

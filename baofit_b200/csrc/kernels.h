@@ -77,6 +77,7 @@ struct FastArgs {
     int ldo;
     const double *dsub, *dov;
     int *status;
+    int sub_dov_in_part1;  // fused data tail: the cosmology pass subtracts the per-column data override itself
 };
 
 // Coefficient rows of the fused tail + dilation-limit check of the data bins.
@@ -85,6 +86,7 @@ struct FoldArgs {
     const double *pT, *S, *vfac;
     int ldb, B, zc_data;         // single redshift class of the data bins
     int fold_case, nb, kext, pmax, nrt, nz;
+    int ncls;                    // > 1: nb = ncls blocks of nb/ncls coefficient rows, block c scaled by the bias evolution of class c
     int minus_d_row_value;       // 1: chi2 mode (row multiplies the -d column), 0: prediction mode
     double *rows;                // [kext][ldb] appended below the xi_u panel
     // data bins for the dilation check
@@ -113,6 +115,8 @@ struct GemmArgs {
     int lda, ldb, ldc;
     long long strideA, strideB, strideC;
     int lower_triangular;  // A is lower triangular: skip k tiles above the diagonal
+    int k_tri;             // with lower_triangular: only the first k_tri columns of A are triangular, columns
+                           // k_tri .. K-1 are dense for every row (0 = all K columns are triangular)
     // chi-square epilogue: chi2[n] = sum_m C[m][n]^2 (C is not stored)
     double *chi2;
     const int *status;

@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_ke
                 else if (a.dsub) val -= a.dsub[i];
             }
             if (a.mode == 0 && kPart == 1 && st_bits) val = nan("");
+            if (a.mode == 0 && kPart == 1 && a.sub_dov_in_part1) val -= a.dov[(size_t)b * pt.npts + i];
         }
         if (active) a.out[(size_t)i * a.ldo + b] = val;
     }
@@ -622,7 +623,13 @@ __global__ void __launch_bounds__(128) fold_coef_kernel(FoldArgs a) {
     const double dpi = dv * a.vfac[a.zc_data];
     double *rows = a.rows + b;
     const DevBB &s = m.bb[BF_BB_DIST_ADD];
-    if (a.fold_case == 1) {
+    if (a.fold_case == 1 && a.ncls > 1) {
+        const int nb1 = a.nb / a.ncls;
+        for (int c = 0; c < a.ncls; ++c) {
+            const double ebc = S[(size_t)(c * 3 + 0) * ldb];
+            for (int k = 0; k < nb1; ++k) rows[(size_t)(c * nb1 + k) * ldb] = ebc * pT[(size_t)(s.idx_base + k) * ldb];
+        }
+    } else if (a.fold_case == 1) {
         for (int k = 0; k < a.nb; ++k) rows[(size_t)k * ldb] = eb * pT[(size_t)(s.idx_base + k) * ldb];
     } else if (a.fold_case == 2) {
         const double v = dpi * s.inv_r0;

@@ -85,8 +85,10 @@ __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
     const double *A = g.A + (size_t)blockIdx.z * g.strideA;
     const double *Bm = g.Bm + (size_t)blockIdx.z * g.strideB;
     double *C = g.C + (size_t)blockIdx.z * g.strideC;
-    int kend = g.lower_triangular ? min(g.K, m0 + BM) : g.K;
-    const int T = kend / BK;
+    // k tiles of this row tile: the triangular part up to the diagonal, then the dense tail columns
+    const int ktri = g.lower_triangular ? (g.k_tri > 0 ? g.k_tri : g.K) : g.K;
+    const int Ttri = min(ktri, g.lower_triangular ? m0 + BM : ktri) / BK, T = Ttri + (g.K - ktri) / BK;
+    auto kofs = [&](int t) { return t < Ttri ? t * BK : ktri + (t - Ttri) * BK; };
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < T) load_stage(As + s * A_STAGE, Bs + s * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0, s * BK, tid);
+        if (s < T) load_stage(As + s * A_STAGE, Bs + s * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0, kofs(s), tid);
         cp_async_commit();
     }
     for (int t = 0; t < T; ++t) {
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
         int tn = t + STAGES - 1;
         if (tn < T)
             load_stage(As + (tn % STAGES) * A_STAGE, Bs + (tn % STAGES) * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0,
-                       tn * BK, tid);
+                       kofs(tn), tid);
         cp_async_commit();
         compute_stage(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
     }
@@ -132,12 +134,17 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
     const bool split = gridDim.y > 1;
     const int mt0 = split ? blockIdx.y : 0, mt1 = split ? blockIdx.y + 1 : g.M / BM;
     // flattened (row tile, k tile) sequence so that the cp.async pipeline never drains
-    auto ktiles = [&](int mt) { return (g.lower_triangular ? min(g.K, (mt + 1) * BM) : g.K) / BK; };
+    // k tiles of a row tile: the triangular part up to the diagonal, then the dense tail columns (GemmArgs::k_tri)
+    const int ktri = g.lower_triangular ? (g.k_tri > 0 ? g.k_tri : g.K) : g.K, tail = (g.K - ktri) / BK;
+    auto tritiles = [&](int mt) { return (g.lower_triangular ? min(ktri, (mt + 1) * BM) : ktri) / BK; };
+    auto ktiles = [&](int mt) { return tritiles(mt) + tail; };
     int total = 0;
     for (int mt = mt0; mt < mt1; ++mt) total += ktiles(mt);
     int lmt = mt0, lkt = 0;  // next tile to load
     auto issue = [&](int slot) {
-        load_stage(As + slot * A_STAGE, Bs + slot * B_STAGE, g.A, g.Bm, g.lda, g.ldb, lmt * BM, n0, lkt * BK, tid);
+        const int tt = tritiles(lmt);
+        load_stage(As + slot * A_STAGE, Bs + slot * B_STAGE, g.A, g.Bm, g.lda, g.ldb, lmt * BM, n0,
+                   lkt < tt ? lkt * BK : ktri + (lkt - tt) * BK, tid);
         if (++lkt == ktiles(lmt)) { lkt = 0; ++lmt; }
     };
     double colsum[4][2];

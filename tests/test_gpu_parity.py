@@ -305,3 +305,40 @@ def test_gram_probes_equal_explicit_probe_groups(ctx):
         dn = np.sqrt(np.abs(g[:, ip, ip] + g[:, im, im]))
         assert np.max(np.abs(M[:, 1:, 1:] - ref_aa) / (dn[:, :, None] * dn[:, None, :])) < 1e-12
     toys.close(), gm.close(), gd.close()
+
+
+def test_fused_data_tail_equals_unfused_path(ctx):
+    """k-space models without a distortion matrix run chi2 / whitened residuals as cosmology pass + broadband
+    coefficient rows + one GEMM against [W | W.basis | -W.d] (per redshift class for the three z bins of DR9).
+    The prediction output still takes the unfused two-pass path: both must agree, also with a data override and
+    through the normal-equation probes."""
+    import scipy.linalg as sl
+    rng = np.random.Generator(np.random.PCG64(41))
+    m9, d9 = W.dr9_kspace()
+    m11, (r, mu, z, keep) = W.dr11_auto_kspace()
+    n11 = len(keep)
+    xi0 = 1e-3 * (50.0 / r[keep]) ** 2
+    d11 = W.make_data(r, mu, z, keep, xi0 * (1 + 0.1 * rng.standard_normal(n11)), W.synthetic_cov(xi0))
+    for m, d in ((m9, d9), (m11, d11)):
+        gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+        B = 200
+        p = m.random_batch(B, rng, sweep={"BAO alpha-parallel": (0.9, 1.1), "BAO alpha-perp": (0.9, 1.1)})
+        jb = [j for j, nm in enumerate(m.names) if nm.startswith("dist add")]
+        p[:, jb] += 1e-4 * rng.standard_normal((B, len(jb)))  # broadband coefficients away from zero
+        dv, cov = d.keep._arrays[4], d.keep._arrays[5]
+        L = np.linalg.cholesky(cov)
+        pred, st = capi.eval_batch(ctx, gm, gd, p)
+        assert np.all(st == 0)
+        chi2, _ = capi.chi2_batch(ctx, gm, gd, p)
+        ref = np.sum(sl.solve_triangular(L, pred - dv[:, None], lower=True) ** 2, axis=0)
+        assert np.max(np.abs(chi2 - ref) / ref) < 1e-10
+        ov = dv[None, :] + (L @ rng.standard_normal((gd.n, B))).T
+        chi2o, _ = capi.chi2_batch(ctx, gm, gd, p, data_override=np.ascontiguousarray(ov))
+        refo = np.sum(sl.solve_triangular(L, pred - ov.T, lower=True) ** 2, axis=0)
+        assert np.max(np.abs(chi2o - refo) / refo) < 1e-10
+        steps = np.zeros_like(p[:8])
+        fl = np.nonzero(m.floating)[0]
+        steps[:, fl] = 0.01 * m.errors[fl]
+        M, t, stn = capi.normal_probes(ctx, gm, gd, p[:8], steps)
+        assert np.all(stn == 0) and np.max(np.abs(M[:, 0, 0] - chi2[:8]) / chi2[:8]) < 1e-10
+        gm.close(), gd.close()
