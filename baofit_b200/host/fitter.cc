@@ -419,8 +419,14 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
     for (long k = 0; k < count; ++k) {
         results[k] = fits[k].result();
         if (results[k]->status != likely::FunctionMinimum::OK) {
+            // ... from where LM stopped when that point is usable (it is usually close to the minimum, only not
+            // certified), from the initial configuration otherwise
             likely::FitParameters p = results[k]->parameters;
-            for (size_t i = 0; i < p.size(); ++i) { p[i].value = starts[k][i]; p[i].error = base[i].error; }
+            const bool usable = results[k]->status == likely::FunctionMinimum::WARNING && std::isfinite(results[k]->minValue);
+            for (size_t i = 0; i < p.size(); ++i) {
+                if (!usable) p[i].value = starts[k][i];
+                p[i].error = base[i].error;
+            }
             redo.push_back(likely::NewtonFit(p));
             redoIdx.push_back(k);
         }
