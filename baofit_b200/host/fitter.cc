@@ -386,6 +386,7 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
     // the unconstrained best fit keeps the Newton driver (its HESSE errors go into the scan header);
     // the grid fits, whose covariance nobody reads, run Levenberg-Marquardt on Gauss-Newton normal
     // equations from the GPU
+    const double tScan0 = nowSeconds();
     std::vector<likely::NewtonFit> bestFit(1, likely::NewtonFit(base));
     likely::runLockStep(bestFit, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
     const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
@@ -410,7 +411,9 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
         for (auto const &q : p) st.push_back(q.value);
         starts.push_back(st);
     }
+    const double tScan1 = nowSeconds();
     fitter.runLockStepLM(fits);
+    const double tScan2 = nowSeconds();
     // grid points where Levenberg-Marquardt did not converge cleanly (flat or saddle-like regions,
     // where the Gauss-Newton curvature is a poor model) are refitted with the Newton driver
     std::vector<likely::FunctionMinimumPtr> results(count);
@@ -428,6 +431,9 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
                 p[i].error = base[i].error;
             }
             redo.push_back(likely::NewtonFit(p));
+            // a refit that continues from LM's end point either certifies it within a few iterations or sits in a
+            // flat valley that no iteration count certifies (most of the time of a k-space scan went there)
+            if (usable) redo.back().maxIterations = 20;
             redoIdx.push_back(k);
         }
     }
@@ -437,7 +443,11 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
         std::fprintf(stderr, "parameterScan: %ld grid fits, %zu handed to the Newton driver, %ld LM evaluations\n", count, redo.size(), nev);
     }
     if (!redo.empty()) {
-        likely::runLockStep(redo, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
+        long rounds = 0, points = 0;
+        likely::runLockStep(redo, [&](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { ++rounds; points += (long)pts.size(); fitter.evaluateBatch(pts, f); });
+        if (std::getenv("BAOFIT_VERBOSE_FITS"))
+            std::fprintf(stderr, "parameterScan: unconstrained fit %.3f s, lock-step LM %.3f s, Newton refits %.3f s (%ld rounds, %ld points)\n",
+                         tScan1 - tScan0, tScan2 - tScan1, nowSeconds() - tScan2, rounds, points);
         for (size_t q = 0; q < redo.size(); ++q) {
             likely::FunctionMinimumPtr fm = redo[q].result();
             bool better = fm->status != likely::FunctionMinimum::ERROR &&
