@@ -282,6 +282,41 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         if (d->idx_rad >= 0 && !chk(d->idx_rad, 4)) { bf::set_error("bf_model_create: bad radiation block"); return fail(BF_ERR_MODEL); }
         if ((rc = make_spline_set(m, d->n_fid, d->fid_r, d->fid_xi0, d->fid_xi2, d->fid_xi4, dm.fid))) return fail(rc);
         if ((rc = make_spline_set(m, d->n_nw, d->nw_r, d->nw_xi0, d->nw_xi2, d->nw_xi4, dm.nw))) return fail(rc);
+        // Fast pass: sum_l L_l n_l xi_l(r) with the Kaiser factors n_0 = 1 + (2/3) ba + (1/5) bp, n_2 = (4/3) ba + (4/7) bp,
+        // n_4 = (8/35) bp (AbsCorrelationModel.cc:196-204) is a polynomial in c1 = 2 ba and c2 = bp, i.e. the
+        // basis-table form X_l0 + c1 X_l1 + c2 X_l2 of the k-space fast pass. Component 0 holds fiducial - nowiggles.
+        static const bool generic_only = std::getenv("BAOFIT_RSPACE_GENERIC") != nullptr;
+        const bool same_grid = dm.fid.uniform && dm.nw.uniform && d->n_fid == d->n_nw && d->fid_r[0] == d->nw_r[0] &&
+                               d->fid_r[d->n_fid - 1] == d->nw_r[d->n_nw - 1];
+        if (same_grid && !generic_only && d->metal_kind == BF_METAL_NONE && !d->dist_matrix && !(d->flags & BF_FLAG_RADIATION_MODEL) &&
+            (size_t)2 * d->n_fid * 9 * sizeof(double2) <= 200 * 1024) {
+            const int n = d->n_fid;
+            std::vector<double> cf((size_t)(n - 1) * 4);
+            std::vector<double2> tabs((size_t)2 * n * 9, make_double2(0.0, 0.0));
+            const double *fy[3] = {d->fid_xi0, d->fid_xi2, d->fid_xi4}, *ny[3] = {d->nw_xi0, d->nw_xi2, d->nw_xi4};
+            // weights of (1, c1, c2) in n_l
+            const double wgt[3][3] = {{1.0, 1.0 / 3.0, 1.0 / 5.0}, {0.0, 2.0 / 3.0, 4.0 / 7.0}, {0.0, 0.0, 8.0 / 35.0}};
+            for (int l = 0; l < 3; ++l) {
+                std::vector<double> yc[2] = {std::vector<double>(n), std::vector<double>(n)}, cc[2] = {std::vector<double>(n, 0.0), std::vector<double>(n, 0.0)};
+                for (int which = 0; which < 2; ++which) {
+                    const double *y = which == 0 ? fy[l] : ny[l];
+                    cspline_interval_coefs(n, which == 0 ? d->fid_r : d->nw_r, y, cf.data());
+                    for (int j = 0; j < n; ++j) { yc[which][j] = y[j]; cc[which][j] = j < n - 1 ? cf[(size_t)j * 4 + 2] : 0.0; }
+                }
+                for (int j = 0; j < n; ++j)
+                    for (int q = 0; q < 3; ++q) {
+                        tabs[((size_t)0 * n + j) * 9 + 3 * l + q] = make_double2(wgt[l][q] * (yc[0][j] - yc[1][j]), wgt[l][q] * (cc[0][j] - cc[1][j]));
+                        tabs[((size_t)1 * n + j) * 9 + 3 * l + q] = make_double2(wgt[l][q] * yc[1][j], wgt[l][q] * cc[1][j]);
+                    }
+            }
+            if ((rc = upload(m->allocs, tabs.data(), tabs.size(), &m->d_rs_tabs))) return fail(rc);
+            dm.nr = n;
+            dm.tr_r0 = d->fid_r[0];
+            dm.tr_dr = (d->fid_r[n - 1] - d->fid_r[0]) / (n - 1);
+            dm.tr_inv_dr = 1.0 / dm.tr_dr;
+            dm.dilmin = 0.0;     // the r-space model has no dilation limits
+            dm.dilmax = 1e300;
+        }
     } else if (d->kind == BF_MODEL_KSPACE_FFT) {
         // baofit/BaoKSpaceFftCorrelationModel.cc:36-113
         if (!chk(d->idx_nl, 2) || !chk(d->idx_cont, 2)) { bf::set_error("bf_model_create: FFT model needs SigmaNL-perp, 1+f, cont-kc, cont-pc"); return fail(BF_ERR_MODEL); }
@@ -878,7 +913,8 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
     };
     if (use_dm) {
         if ((rc = build_fold(false))) return rc;
-    } else if (dm.kind == BF_MODEL_KSPACE && dm.metal_kind == BF_METAL_NONE && !(dm.flags & BF_FLAG_RADIATION_MODEL) && d->h_W.size() == (size_t)n * n) {
+    } else if ((dm.kind == BF_MODEL_KSPACE || (dm.kind == BF_MODEL_RSPACE && m->d_rs_tabs)) && dm.metal_kind == BF_METAL_NONE &&
+               !(dm.flags & BF_FLAG_RADIATION_MODEL) && d->h_W.size() == (size_t)n * n) {
         if ((rc = build_fold(true))) return rc;
     }
     auto ins = d->plans.emplace(m, std::move(p));
@@ -1230,6 +1266,12 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     std::memset(&fa, 0, sizeof(fa));
     fa.m = dm; fa.pT = w.pT; fa.S = w.S; fa.vfac = plan->d_vfac; fa.tabs = m->d_tabs_cache; fa.ldb = ldb; fa.B = B;
     fa.nz = plan->nz; fa.zc_trigger = plan->zc_trigger; fa.status = w.status;
+    if (dm.kind == BF_MODEL_RSPACE && m->d_rs_tabs) {
+        // r-space model through the fast pass (tables are static)
+        shared_tables = true;
+        fa.tabs = m->d_rs_tabs;
+        fa.rspace = 1;
+    }
     bool finished = false;
     if (use_dm) {
         // undistorted xi on the full grid
@@ -1317,7 +1359,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.mode = 0;
         a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
         a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
-        if (dm.kind == BF_MODEL_RSPACE) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
+        if (dm.kind == BF_MODEL_RSPACE && !shared_tables) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
         else if (shared_tables && plan->fold_ok && plan->fold_data_mode && (what == OUT_CHI2 || what == OUT_WHITENED)) {
             // fused data tail: cosmology pass into Z, broadband coefficients and the "- d" switch as extra rows,
             // one GEMM against [W | W.basis | -W.d] (triangular block + dense tail columns)

@@ -175,6 +175,9 @@ struct bf_model {
     // stage layout [2 comps][ctiles][chunks][3 powers of mu^2][16][76], and the scratch
     // H[2][3][my][mx] they are built from
     mutable double *d_fft_T = nullptr, *d_fft_H = nullptr;
+    // r-space model: basis tables [2 comps][n knots][9] of (y, c) built from the tabulated multipoles when both
+    // tabulations share one uniform grid; lets the model run through the k-space fast pass (kernels_fast.cu, kRS)
+    double2 *d_rs_tabs = nullptr;
 };
 
 struct bf_data {

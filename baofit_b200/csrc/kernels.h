@@ -77,6 +77,7 @@ struct FastArgs {
     int ldo;
     const double *dsub, *dov;
     int *status;
+    int rspace;            // the r-space model through the cosmology pass (tables built at model creation)
     int sub_dov_in_part1;  // fused data tail: the cosmology pass subtracts the per-column data override itself
 };
 

@@ -226,7 +226,11 @@ __device__ __forceinline__ double metal_rows_apply(const double *__restrict__ mx
 // 2 = the rest (metals, radiation, broadband, residual) added to what part 1 stored. Splitting
 // halves the live registers of each kernel, which is what bounds the occupancy of this
 // latency-bound code.
-template <bool kLean, int kPart>
+// kRS: the r-space model (BaoCorrelationModel.cc:90-179) through the same pass. Its Kaiser normalisation factors
+// are polynomials in (beta_avg, beta_prod) = (c1/2, c2), so sum_l L_l n_l xi_l(r) has exactly the basis-table form
+// with tables built once from the tabulated multipoles (bf_model_create); what differs is the per-bin redshift
+// evolution of beta and the radiation term, which r-space models always carry.
+template <bool kLean, int kPart, bool kRS = false>
 __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_kernel(FastArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_ke
     const double *pT = a.pT + b;
     const double *S = a.S + b;
     FastVec v;
-    load_fast_vec(m, pT, ldb, S[(size_t)(a.zc_trigger * 3 + 1) * ldb], v);
+    load_fast_vec(m, pT, ldb, (kRS && a.nz != 1) ? 1.0 : S[(size_t)(a.zc_trigger * 3 + 1) * ldb], v);
     const bool aniso = m.flags & BF_FLAG_ANISOTROPIC, decoupled = m.flags & BF_FLAG_DECOUPLED;
     const bool cross_metal = m.metal_kind == BF_METAL_CROSS_BICUBIC;
     const double dmin2 = m.dilmin * m.dilmin, dmax2 = m.dilmax * m.dilmax;
@@ -269,6 +273,9 @@ __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_ke
                 if (cross_metal && c < m.metal_ncomb) cross_metal_norms(m, pT, ldb, c, eb1, ebeta, mn[3 * c], mn[3 * c + 1], mn[3 * c + 2]);
         }
     }
+    // r-space: c1, c2 follow the redshift class of the bin; v.c1, v.c2 were loaded for ebeta = 1 if there are several
+    double rad0 = 0.0;
+    if (kRS && m.idx_rad >= 0) rad0 = pT[(size_t)m.idx_rad * ldb];
     if (kPart != 2) mbar_wait(&bar, 0);
     const double2 *tab_pk = tab, *tab_nw = tab + (size_t)m.nr * 9;
     int st_bits = 0;
@@ -291,12 +298,17 @@ __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_ke
             }
         }
         if (i < pt.npts) {
-            double eb = eb1, es = es1, dpi = dpi1;
+            double eb = eb1, es = es1, dpi = dpi1, c1 = v.c1, c2 = v.c2;
             if (a.nz != 1) {
                 int zc = pt.zc[i];
                 eb = S[(size_t)(zc * 3 + 0) * ldb];
                 es = S[(size_t)(zc * 3 + 2) * ldb];
                 dpi = v.dv * a.vfac[zc];
+                if (kRS) {
+                    const double ebeta = S[(size_t)(zc * 3 + 1) * ldb];
+                    c1 *= ebeta;
+                    c2 *= ebeta * ebeta;
+                }
             }
             const double rpar = rpar0 + dpi;  // the velocity shift only moves r_parallel
             const double rp2 = rpar * rpar, rt2 = rperp * rperp, r2 = rp2 + rt2;
@@ -326,10 +338,19 @@ __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_ke
             if (!zero) {
                 double xi;
                 if (kPart != 2) {
-                    const double peak = basis_correlation(m, tab_pk, rBAO, muBAO2, v.c1, v.c2);
-                    const double smooth = decoupled ? basis_correlation(m, tab_nw, rprime, mu2, v.c1, v.c2)
-                                                    : basis_correlation(m, tab_nw, rBAO, muBAO2, v.c1, v.c2);
+                    const double peak = basis_correlation(m, tab_pk, rBAO, muBAO2, c1, c2);
+                    const double smooth = decoupled ? basis_correlation(m, tab_nw, rprime, mu2, c1, c2)
+                                                    : basis_correlation(m, tab_nw, rBAO, muBAO2, c1, c2);
                     xi = v.biasSq * eb * (v.ampl * peak + smooth);
+                    if (kRS && rad0 > 0.0 && rprime > 0.0) {  // BaoCorrelationModel.cc:165-176
+                        const double rad1 = pT[(size_t)(m.idx_rad + 1) * ldb], rad2 = pT[(size_t)(m.idx_rad + 2) * ldb];
+                        const double rad3 = pT[(size_t)(m.idx_rad + 3) * ldb];
+                        double rd = rad0 / r2;
+                        rd *= exp(-rprime / rad2);
+                        rd *= (1.0 - rad1 * (1.0 - mu2));
+                        rd *= exp(-(rprime * (1.0 - muprime) / (1.0 + pt.z[i])) / rad3);
+                        xi += rd;
+                    }
                 } else {
                     xi = a.out[(size_t)i * a.ldo + b];
                 }
@@ -687,16 +708,18 @@ static void pick_grid(FastArgs &a, int sm_count, dim3 &grid, int threads = 256) 
 
 void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part) {
     size_t smem = (size_t)2 * a.m.nr * 9 * sizeof(double2);
-    static SmemOptIn opt_lean, opt_full;
+    static SmemOptIn opt_lean, opt_full, opt_rs;
     opt_lean.ensure(kspace_fast_eval_kernel<true, 1>, smem);
     opt_full.ensure(kspace_fast_eval_kernel<false, 0>, smem);
+    opt_rs.ensure(kspace_fast_eval_kernel<true, 1, true>, smem);
     dim3 grid;
     pick_grid(a, sm_count, grid);
     if (part == 1) {
         // the cosmology pass is bound by shared-memory wavefronts and its 72 KB table allows 3 CTAs per SM at most:
         // 512 threads at 64 registers (2 CTAs, 32 warps per SM instead of 24) measured 0.344 -> 0.332 ms
         pick_grid(a, sm_count, grid, 512);
-        kspace_fast_eval_kernel<true, 1><<<grid, 512, smem, s>>>(a);
+        if (a.rspace) kspace_fast_eval_kernel<true, 1, true><<<grid, 512, smem, s>>>(a);
+        else kspace_fast_eval_kernel<true, 1><<<grid, 512, smem, s>>>(a);
     }
     else if (part == 2) {
         const int sa = a.mode == 1 ? BF_BB_DM_DIST_ADD : BF_BB_DIST_ADD, sm = a.mode == 1 ? BF_BB_DM_DIST_MUL : BF_BB_DIST_MUL;
