@@ -288,7 +288,10 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         static const bool generic_only = std::getenv("BAOFIT_RSPACE_GENERIC") != nullptr;
         const bool same_grid = dm.fid.uniform && dm.nw.uniform && d->n_fid == d->n_nw && d->fid_r[0] == d->nw_r[0] &&
                                d->fid_r[d->n_fid - 1] == d->nw_r[d->n_nw - 1];
+        // (not with a multiplicative broadband: the radiation term is added after it, BaoCorrelationModel.cc:150-176,
+        // while the fast pass adds it with the cosmological part)
         if (same_grid && !generic_only && d->metal_kind == BF_METAL_NONE && !d->dist_matrix && !(d->flags & BF_FLAG_RADIATION_MODEL) &&
+            !d->bb[BF_BB_DIST_MUL].enabled &&
             (size_t)2 * d->n_fid * 9 * sizeof(double2) <= 200 * 1024) {
             const int n = d->n_fid;
             std::vector<double> cf((size_t)(n - 1) * 4);

@@ -1,5 +1,6 @@
 """GPU parity tests proper: CUDA path (through the C ABI) versus the CPU oracle on the same
 seeded inputs. Tolerance: 1e-10 relative (north_star), see tests/util.py for the floor."""
+import os
 import numpy as np
 import pytest
 
@@ -341,4 +342,44 @@ def test_fused_data_tail_equals_unfused_path(ctx):
         steps[:, fl] = 0.01 * m.errors[fl]
         M, t, stn = capi.normal_probes(ctx, gm, gd, p[:8], steps)
         assert np.all(stn == 0) and np.max(np.abs(M[:, 0, 0] - chi2[:8]) / chi2[:8]) < 1e-10
+        gm.close(), gd.close()
+
+
+def test_rspace_fast_and_generic_kernels_against_oracle(ctx):
+    """The r-space model runs through the basis-table fast pass when both tabulations share one uniform grid and
+    through the generic per-vector kernel otherwise; both against the oracle, with the radiation term switched on
+    (Rad strength > 0 on half of the vectors), gamma-beta != 0 on three redshift classes, and a dist-mul broadband
+    (which keeps chi2 off the fused tail)."""
+    root = os.path.join(W.GOLDEN, "models")
+    fid, nw = W.load_multipoles(root, "DR9LyaMocksNLeffPk"), W.load_multipoles(root, "DR9LyaMocksSB")
+    keepk = np.ones(len(fid[0]), bool)
+    keepk[[17, 50, 51, 120]] = False  # non-uniform knots: generic kernel
+    thin = lambda t: tuple(np.ascontiguousarray(a[keepk]) for a in t)
+    rng = np.random.Generator(np.random.PCG64(52))
+    nb = 120
+    r = rng.uniform(20., 190., nb)
+    mu = rng.uniform(-1., 1., nb)
+    z = rng.choice([2.0, 2.4, 2.9], nb)
+    keep = np.arange(nb, dtype=np.int32)
+    cov = np.diag(rng.uniform(0.5, 2.0, nb) * 1e-8)
+    for tabs, kw in (((fid, nw), dict(dist_add="-2:0,0:4:2,0")), ((thin(fid), thin(nw)), dict(dist_add="-2:0,0:4:2,0")),
+                     ((fid, nw), dict(dist_add="0:1,0,0", dist_mul="0:1,0,0", cross=True))):
+        m = W.rspace_model(tabs[0], tabs[1], **kw)
+        d = W.make_data(r, mu, z, keep, 1e-4 * rng.standard_normal(nb), cov)
+        B = 64
+        p = m.random_batch(B, rng, sweep={"BAO alpha-parallel": (0.8, 1.2), "BAO alpha-perp": (0.8, 1.2)})
+        p[:, m.index("gamma-beta")] = rng.uniform(-0.5, 0.5, B)
+        p[::2, m.index("Rad strength")] = rng.uniform(0.01, 0.1, B // 2)
+        p[:, m.index("Rad anisotropy")] = rng.uniform(0.0, 0.5, B)
+        for j, nm in enumerate(m.names):
+            if nm.startswith("dist "):
+                p[:, j] = 1e-3 * rng.standard_normal(B)
+        gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+        om, od = oracle.OracleModel(m), oracle.OracleData(d)
+        pred, st = capi.eval_batch(ctx, gm, gd, p)
+        chi2, _ = capi.chi2_batch(ctx, gm, gd, p)
+        ref_chi2, ref_st, ref_pred = oracle.chi2_batch(om, od, p, nthreads=8, want_pred=True)
+        assert np.array_equal(st, ref_st)
+        assert np.max(np.abs(pred - ref_pred)) < RTOL * np.max(np.abs(ref_pred))
+        assert rel_err(chi2, ref_chi2) < RTOL
         gm.close(), gd.close()
