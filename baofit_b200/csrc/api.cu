@@ -1297,7 +1297,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         } else
             BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
         if (what == OUT_XIU) finished = true;
-        if (!finished && plan->fold_ok && !d_override && what != OUT_WHITENED) {
+        if (!finished && plan->fold_ok && !d_override) {
             // fused tail: the post-matrix broadband and "- d" are extra K rows of the panel, and for
             // chi2 the whitening W is folded into the left matrix: one GEMM, squares in the epilogue
             FoldArgs fo;
@@ -1306,7 +1306,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             fo.zc_data = plan->zc_trigger;  // single class of the data bins (= class of the first kept bin)
             fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
             fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz;
-            fo.minus_d_row_value = what == OUT_CHI2 ? 1 : 0;
+            fo.minus_d_row_value = (what == OUT_CHI2 || what == OUT_WHITENED) ? 1 : 0;
             fo.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
             fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
             BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
@@ -1327,6 +1327,10 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                     if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
                     BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g, ctx->sm_count));
                 }
+            } else if (what == OUT_WHITENED) {
+                // whitened residuals for the normal-equation probes: the same folded left matrix, store epilogue
+                g.A = plan->d_WA; g.C = d_out; g.ldc = ldo;
+                BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused tail]", launch_gemm_store(s, g, 1));
             } else {
                 g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
                 BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));

@@ -320,7 +320,7 @@ def test_fused_data_tail_equals_unfused_path(ctx):
     n11 = len(keep)
     xi0 = 1e-3 * (50.0 / r[keep]) ** 2
     d11 = W.make_data(r, mu, z, keep, xi0 * (1 + 0.1 * rng.standard_normal(n11)), W.synthetic_cov(xi0))
-    for m, d in ((m9, d9), (m11, d11)):
+    for m, d in ((m9, d9), (m11, d11), W.qso_kspace()):  # the last one: the fused tail of the distortion-matrix path
         gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
         B = 200
         p = m.random_batch(B, rng, sweep={"BAO alpha-parallel": (0.9, 1.1), "BAO alpha-perp": (0.9, 1.1)})
