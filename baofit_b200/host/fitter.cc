@@ -217,6 +217,11 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
         }
         if (byG.empty() && pfits.empty()) break;
         ++rounds;
+        if (verbose && std::atoi(std::getenv("BAOFIT_VERBOSE_FITS")) == 4) {
+            size_t nj = 0;
+            for (auto const &kv : byG) nj += kv.second.size();
+            std::fprintf(stderr, "  round %ld: %zu Jacobian fits, %zu trial fits, t = %.3f s\n", rounds, nj, pfits.size(), nowSeconds() - t0);
+        }
         for (auto const &kv : byG) {
             const int G = kv.first;
             flatJ.clear();
