@@ -224,6 +224,12 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
         }
         for (auto const &kv : byG) {
             const int G = kv.first;
+            if (G > 95) {
+                // more floating parameters than one probe group holds (bf_normal_probes: 2 n + 1 <= 96): these fits
+                // are left to the Newton driver, which every caller runs for fits that do not end OK
+                for (int k : kv.second) fits[k].abandon();
+                continue;
+            }
             flatJ.clear();
             steps.clear();
             jtoy.clear();

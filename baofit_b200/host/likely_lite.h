@@ -141,6 +141,8 @@ public:
     void consumeJacobian(const double *gram, bool bad);
     // the same round fed with the device-reduced normal equations of bf_normal_probes: (n+1)^2 + n values
     void consumeNormal(const double *normal, bool bad);
+    // gives the fit up (status ERROR) without evaluating anything: the caller's fallback driver takes over
+    void abandon() { _failed = true; _stage = Done; }
     int normalSize() const { return (_n + 1) * (_n + 1) + _n; }
     // trial round: appends pending() full-length vectors
     void requestPoints(std::vector<double> &flat);

@@ -176,3 +176,15 @@ def test_mcmc_walkers_sample_the_fit_posterior(built, golden_tree):
     assert np.all(np.abs(np.sqrt(np.diag(cov)) / sig - 1) < 0.15)
     assert np.all(chain[:, -1] >= fit["fval"] - 1e-9)
     assert np.all(chain[:, np.nonzero(~s.floating)[0]] == s.values[~s.floating])
+
+
+def test_scan_with_more_floating_parameters_than_a_probe_group(built, golden_tree):
+    """A probe group of the GPU normal equations holds 2 n + 1 <= 96 columns. Fits with more floating parameters
+    are abandoned by the lock-step LM driver and picked up by the Newton driver: the scan still completes."""
+    text, base = ini(golden_tree, "rmu_to_bao.ini")
+    text += "\ndist-add = -5:4,0:8:2,0\nmodel-config = binning[BAO alpha-perp]={0.98:1.02}*2\nmodel-config = binning[BAO alpha-parallel]={0.98:1.02}*2\n"
+    s = H.Session(text, base)
+    assert int(s.floating.sum()) - 2 > 47
+    res = s.parameter_scan()
+    assert len(res["chi2"]) == 4 and np.all(np.isfinite(res["chi2"])) and np.all(res["status"] != 2)
+    assert np.all(res["chi2"] >= res["best_chi2"] - 1e-6)
