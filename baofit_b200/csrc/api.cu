@@ -1838,7 +1838,8 @@ extern "C" int bf_pinned_alloc(size_t bytes, void **ptr) {
 }
 
 extern "C" int bf_pinned_free(void *ptr) {
-    if (ptr) BF_CUDA_OK(cudaFreeHost(ptr));
+    // may run from a thread-local destructor at process exit, after the CUDA runtime has gone: errors are ignored
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) cudaGetLastError();
     return BF_OK;
 }
 
