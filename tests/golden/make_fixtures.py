@@ -17,6 +17,9 @@ hot path at the boundary of the un-vendored likely/cosmo dependencies):
 * data/BOSSDR11QSOLyaF.{data,cov,scan}: the only published chi-square surface that can be
     reproduced without the missing cosmology dependency (config/BOSSDR11QSOLyaF.ini).
     The .cov text (2.5 MB) is stored gzip-compressed.
+* data/BOSSDR9LyaF.{data,cov,scan} (config/BOSSDR9LyaF.ini: quasar observing coordinates) and
+    data/BOSSDR9LyaFXi.{data,cov,scan} (config/BOSSDR9LyaFXi.ini: multipole-binned data,
+    data-format = comoving-multipole): the other two published surfaces whose inputs ship.
 * the .ini recipes of the hot-path configs, with their relative paths rewritten to the
     fixture tree, comments dropped.
 
@@ -38,14 +41,15 @@ DEMO = ["rmu.theory", "rmu.data", "rmu.icov", "multi.theory",
         "multi_0.data", "multi_0.cov", "multi_1.data", "multi_1.cov",
         "multi_2.data", "multi_2.cov"]
 DATA = ["BOSSDR11QSOLyaF.data", "BOSSDR11QSOLyaF.scan", "BOSSDR9LyaF.data",
-        "BOSSDR9LyaF.scan", "BOSSDR11LyaF.data"]
-DATA_GZ = ["BOSSDR11QSOLyaF.cov"]
+        "BOSSDR9LyaF.scan", "BOSSDR11LyaF.data", "BOSSDR9LyaFXi.data", "BOSSDR9LyaFXi.scan"]
+DATA_GZ = ["BOSSDR11QSOLyaF.cov", "BOSSDR9LyaF.cov", "BOSSDR9LyaFXi.cov"]
 INIS = [("config/BOSSDR9LyaF.ini", "BOSSDR9LyaF.ini"),
         ("config/BOSSDR9LyaF_k.ini", "BOSSDR9LyaF_k.ini"),
         ("config/BOSSDR11LyaF_k.ini", "BOSSDR11LyaF_k.ini"),
         ("config/BOSSDR11QSOLyaF_k.ini", "BOSSDR11QSOLyaF_k.ini"),
         ("config/BOSSDR11QSOLyaF.ini", "BOSSDR11QSOLyaF.ini"),
         ("config/BOSSDR11LyaF_fft.ini", "BOSSDR11LyaF_fft.ini"),
+        ("config/BOSSDR9LyaFXi.ini", "BOSSDR9LyaFXi.ini"),
         ("demo/rmu_to_bao.ini", "rmu_to_bao.ini"),
         ("demo/multi_to_bao.ini", "multi_to_bao.ini")]
 

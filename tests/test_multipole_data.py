@@ -213,3 +213,58 @@ def test_resampling_fits_match_direct_sessions(built, golden_tree):
         assert abs(2 * r["fval"] - each["chi2"][q]) < 1e-6 * each["chi2"][q]
     bs = s.resample_fit("bootstrap", n=3, fix_covariance=True, seed=5)
     assert np.all(np.isfinite(bs["chi2"])) and bs["fitted"].shape == (3, s.npar)
+
+
+def test_host_dr9_xi_session_layout(built, golden_tree):
+    """config/BOSSDR9LyaFXi.ini: multipole-binned data (50 radii x ell = 0, 2 at z = 2.31, r in [20, 200] -> 90
+    bins), covariance file holding both triangles, broadband with half-integer powers of r
+    (`dist-add = -2:0:-2,0:2:2,0`: negative step = denominator, baofit/BroadbandModel.cc:111-116)."""
+    base = os.path.join(golden_tree, "config")
+    s = H.Session(open(os.path.join(base, "BOSSDR9LyaFXi.ini")).read(), base)
+    assert s.ndata == 90 and s.scan_size() == 2500
+    bb = [n for n in s.names if n.startswith("dist add")]
+    assert bb[:5] == ["dist add z0 mu0 r%+d rP0 rT0" % e for e in (-4, -3, -2, -1, 0)] and len(bb) == 10
+    # floating: beta, (1+beta)*bias, both alphas, 8 of the 10 broadband terms (the two r^-3/2 terms are fixed)
+    assert int(s.floating.sum()) == 12
+    cov = s.covariance()
+    assert np.allclose(cov, cov.T) and np.all(np.linalg.eigvalsh(cov) > 0)
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_dr9_xi_scan_against_published_surface(built, golden_tree):
+    """data/BOSSDR9LyaFXi.scan: the third published chi-square surface whose inputs ship, and the only one on
+    multipole-binned data (AbsCorrelationModel.cc:43-49,65-79 projection of the r-space model onto ell = 0, 2).
+    What it can pin: with monopole and quadrupole only, beta and bias are nearly degenerate and chi-square keeps
+    falling (by ~1e-1) as beta -> infinity; the reference's Minuit stops somewhere along that valley, so most
+    published values sit ABOVE the true profile minimum by 1e-3 .. 1e-1 (a scipy profile fit of the CPU oracle
+    shows the same: 0.45 of 40 sampled points within 5e-3, differences -0.73 .. +0.14). Points where the BAO peak
+    has left the fitted range are exact, though: there chi-square does not depend on (alpha_perp, alpha_par),
+    the published value is the constant 12.4054 and ours must be one constant too, equal to it up to the common
+    offset of the two global minima. Acceptance: that plateau (>= 95 % within 2e-3 of one level, level within
+    1e-2 of 12.4054), the grid minimum at the published grid point, and one-sidedness in bulk (we may find lower
+    minima along the valley, not noticeably higher ones)."""
+    base = os.path.join(golden_tree, "config")
+    s = H.Session(open(os.path.join(base, "BOSSDR9LyaFXi.ini")).read(), base)
+    scan = s.parameter_scan()
+    pub = np.loadtxt(os.path.join(golden_tree, "data", "BOSSDR9LyaFXi.scan"))
+    assert len(scan["chi2"]) == 2500 == len(pub)
+    ia, ip = s.names.index("BAO alpha-parallel"), s.names.index("BAO alpha-perp")
+    assert np.allclose(scan["points"][:, ip], pub[:, 0], atol=5e-6) and np.allclose(scan["points"][:, ia], pub[:, 1], atol=5e-6)
+    good = scan["status"] != 2
+    dchi2 = scan["chi2"] - scan["best_chi2"]
+    diff = dchi2 - pub[:, 2]
+    plateau = (pub[:, 2] == 12.4054) & good
+    level = np.median(dchi2[plateau])
+    print("DR9 Xi scan: chi2_min %.4f, failed %d, plateau points %d level %.4f (published 12.4054), within 2e-3 of level: %.3f; "
+          "diff min %.4g max %.4g, |diff| < 5e-3: %.3f, diff < 5e-3: %.3f" %
+          (scan["best_chi2"], int((~good).sum()), int(plateau.sum()), level, np.mean(np.abs(dchi2[plateau] - level) < 2e-3),
+           diff[good].min(), diff[good].max(), np.mean(np.abs(diff[good]) < 5e-3), np.mean(diff[good] < 5e-3)))
+    assert good.mean() >= 0.99
+    assert plateau.sum() > 500
+    assert abs(level - 12.4054) < 1e-2
+    assert np.mean(np.abs(dchi2[plateau] - level) < 2e-3) >= 0.95
+    k, kp = int(np.argmin(np.where(good, dchi2, np.inf))), int(np.argmin(pub[:, 2]))
+    assert abs(pub[k, 0] - pub[kp, 0]) < 0.04 and abs(pub[k, 1] - pub[kp, 1]) < 0.02  # same or neighbouring grid point
+    assert np.mean(diff[good] < 5e-3) >= 0.80
+    s.close()
