@@ -1,6 +1,7 @@
 // C ABI of libbaofit_b200.so (include/baofit_b200.h): object lifetime, one-time setup, and the
 // per-batch kernel pipelines. No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -40,11 +41,14 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
     BF_CUDA_OK(cudaSetDevice(device));
     bf_ctx *c = new bf_ctx();
     c->device = device;
-    BF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
-    BF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaMallocHost((void **)&c->pinned_flag, 256)) != cudaSuccess) {
+        bf_ctx_destroy(c);
+        BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: ") + cudaGetErrorString(e));
+    }
     c->sm_count = prop.multiProcessorCount;
-    BF_CUDA_OK(cudaMallocHost((void **)&c->pinned_flag, 256));
     {   // keep stream-ordered allocations (toy tables) cached in the device pool between studies
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -60,13 +64,15 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
 extern "C" int bf_ctx_destroy(bf_ctx *c) {
     if (!c) return BF_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    c->prof_pending.clear();
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     if (c->mp) cudaFree(c->mp);
     if (c->chi2_part) cudaFree(c->chi2_part);
     if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BF_OK;
 }
@@ -75,12 +81,14 @@ extern "C" long long bf_ctx_launch_count(const bf_ctx *c) { return c ? c->launch
 extern "C" void *bf_ctx_stream(bf_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" int bf_ctx_synchronize(bf_ctx *c) {
     if (!c) BF_FAIL(BF_ERR_OPTIONS, "null context");
+    std::lock_guard<std::recursive_mutex> lock(c->api_mu);
     BF_CUDA_OK(cudaStreamSynchronize(c->stream));
     return BF_OK;
 }
 
 extern "C" int bf_ctx_set_profiling(bf_ctx *c, int enable) {
     if (!c) BF_FAIL(BF_ERR_OPTIONS, "null context");
+    std::lock_guard<std::recursive_mutex> lock(c->api_mu);
     BF_CUDA_OK(cudaStreamSynchronize(c->stream));
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     c->prof_pending.clear();
@@ -107,6 +115,7 @@ static int prof_drain(bf_ctx *c) {
 extern "C" int bf_ctx_get_profile(bf_ctx *c, int max_entries, const char **names, double *ms_total,
                                   long long *launches) {
     if (!c) return 0;
+    std::lock_guard<std::recursive_mutex> lock(c->api_mu);
     if (prof_drain(c)) return 0;
     int k = 0;
     for (auto &kv : c->prof_acc) {
@@ -221,7 +230,16 @@ static int make_spline_set(bf_model *m, int n, const double *x, const double *y0
 
 extern "C" int bf_model_destroy(bf_model *m) {
     if (!m) return BF_OK;
+    std::lock_guard<std::recursive_mutex> lock(m->ctx->api_mu);
     cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    // the (model, data) plans built for this model die with it
+    for (bf_data *d : m->ctx->live_data) {
+        auto it = d->plans.find(m->serial);
+        if (it == d->plans.end()) continue;
+        for (void *p : it->second.allocs) cudaFree(p);
+        d->plans.erase(it);
+    }
     for (void *p : m->allocs) cudaFree(p);
     delete m;
     return BF_OK;
@@ -261,9 +279,12 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
                 BF_FAIL(BF_ERR_MODEL, "BroadbandModel: exponents beyond +-31 are not supported");
             if (!(b.r0 > 0)) BF_FAIL(BF_ERR_MODEL, "BroadbandModel: expected r0 > 0");
         }
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     bf_model *m = new bf_model();
     m->ctx = ctx;
+    static std::atomic<unsigned long long> next_serial{1};
+    m->serial = next_serial.fetch_add(1);
     DevModel &dm = m->dev;
     std::memset(&dm, 0, sizeof(dm));
     dm.kind = d->kind; dm.flags = d->flags; dm.npar = d->npar; dm.zref = d->zref; dm.omega_matter = d->omega_matter;
@@ -388,10 +409,14 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         f.cosx = p;
         if ((rc = upload(m->allocs, cy.data(), cy.size(), &p))) return fail(rc);
         f.Cy = p;
-        BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_T, (size_t)2 * f.ctiles * nchunks * kFftStageT * sizeof(double)));
-        m->allocs.push_back(m->d_fft_T);
-        BF_CUDA_OK(cudaMalloc((void **)&m->d_fft_H, (size_t)6 * f.my * f.mx * sizeof(double)));
-        m->allocs.push_back(m->d_fft_H);
+        auto dev_alloc = [&](double **ptr, size_t count) {
+            cudaError_t e = cudaMalloc((void **)ptr, count * sizeof(double));
+            if (e != cudaSuccess) { bf::set_error(std::string("bf_model_create: cudaMalloc: ") + cudaGetErrorString(e)); return BF_ERR_ANALYSIS; }
+            m->allocs.push_back(*ptr);
+            return BF_OK;
+        };
+        if ((rc = dev_alloc(&m->d_fft_T, (size_t)2 * f.ctiles * nchunks * kFftStageT))) return fail(rc);
+        if ((rc = dev_alloc(&m->d_fft_H, (size_t)6 * f.my * f.mx))) return fail(rc);
     } else {
         if (!chk(d->idx_nl, 2)) { bf::set_error("bf_model_create: k-space model needs SigmaNL-perp, 1+f"); return fail(BF_ERR_MODEL); }
         if ((d->flags & BF_FLAG_RADIATION_MODEL) && !chk(d->idx_rad, 4)) { bf::set_error("bf_model_create: bad radiation block"); return fail(BF_ERR_MODEL); }
@@ -446,6 +471,11 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         dm.th_w = p;
         if ((rc = upload(m->allocs, thd.data(), thd.size(), &p))) return fail(rc);
         dm.th_inv_diag = p;
+        {   // shared-transform basis tables (filled on first use, kept while the key parameters are unchanged)
+            cudaError_t e = cudaMalloc((void **)&m->d_tabs_cache, (size_t)2 * dm.nr * 9 * sizeof(double2));
+            if (e != cudaSuccess) { bf::set_error(std::string("bf_model_create: cudaMalloc: ") + cudaGetErrorString(e)); return fail(BF_ERR_ANALYSIS); }
+            m->allocs.push_back(m->d_tabs_cache);
+        }
     }
     // metals
     dm.metal_kind = d->metal_kind;
@@ -523,7 +553,13 @@ extern "C" double bf_model_transform_dr(const bf_model *m) { return m ? m->dev.t
 // ------------------------------------------------------------------------------------------
 extern "C" int bf_data_destroy(bf_data *d) {
     if (!d) return BF_OK;
+    std::lock_guard<std::recursive_mutex> lock(d->ctx->api_mu);
     cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    {
+        auto &live = d->ctx->live_data;
+        live.erase(std::remove(live.begin(), live.end(), d), live.end());
+    }
     if (d->expanded) bf_data_destroy(d->expanded);
     for (void *p : d->allocs) cudaFree(p);
     for (auto &kv : d->plans)
@@ -546,6 +582,7 @@ extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out)
     if (!d->r || !d->mu || !d->z || !d->index || !d->data || !d->cov) BF_FAIL(BF_ERR_DATA, "bf_data_create: missing arrays");
     if (d->n_grid < 0 || (d->n_grid > 0 && (!d->grid_r || !d->grid_mu || !d->grid_z)))
         BF_FAIL(BF_ERR_DATA, "AbsCorrelationModel::setCoordinates: coordinate vectors not the same size.");
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     const int n = d->n_data, n_pad = round_up(n, kPadM);
     // factor the covariance once (host): W lower triangular with W^T W = C^-1
@@ -568,6 +605,7 @@ extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out)
     }
     bf_data *o = new bf_data();
     o->ctx = ctx;
+    ctx->live_data.push_back(o);
     o->n = n;
     o->n_pad = n_pad;
     o->n_grid = d->n_grid;
@@ -627,6 +665,7 @@ extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out)
         }
         bf_data *e = new bf_data();
         e->ctx = ctx;
+        ctx->live_data.push_back(e);
         e->points_only = true;
         e->trigger_mu_zero = true;
         e->n = n * nmu;
@@ -651,11 +690,16 @@ extern "C" int bf_data_create(bf_ctx *ctx, const bf_data_desc *d, bf_data **out)
 // plan = (model, data) binding: redshift classes, kept rows of the distortion matrix
 // ------------------------------------------------------------------------------------------
 static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **out) {
-    bf_data *d = const_cast<bf_data *>(dc);
-    auto it = d->plans.find(m);
+    bf_data *d = const_cast<bf_data *>(dc);  // the plan cache is the one mutable part of a data object (guarded by the context lock)
+    auto it = d->plans.find(m->serial);
     if (it != d->plans.end()) { *out = &it->second; return BF_OK; }
     const DevModel &dm = m->dev;
     bf_data::Plan p;
+    struct FreeOnFailure {  // every early return below leaves through here
+        bf_data::Plan &p;
+        bool keep = false;
+        ~FreeOnFailure() { if (!keep) for (void *q : p.allocs) cudaFree(q); }
+    } guard{p};
     std::map<double, int> cls;
     auto classify = [&](double z) {
         auto f = cls.find(z);
@@ -920,7 +964,8 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
                !(dm.flags & BF_FLAG_RADIATION_MODEL) && d->h_W.size() == (size_t)n * n) {
         if ((rc = build_fold(true))) return rc;
     }
-    auto ins = d->plans.emplace(m, std::move(p));
+    guard.keep = true;
+    auto ins = d->plans.emplace(m->serial, std::move(p));
     *out = &ins.first->second;
     return BF_OK;
 }
@@ -1063,12 +1108,10 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     carve(ctx->ws, dm, dd, nz, ldb, w);
 
     const double *d_zvals = plan ? plan->d_zvals : nullptr;
-    double *tmp_z = nullptr;
     if (!plan) {
-        // OUT_TRANSFORM without data: one class = z_trigger
-        BF_CUDA_OK(cudaMallocAsync((void **)&tmp_z, sizeof(double), s));
-        BF_CUDA_OK(cudaMemcpyAsync(tmp_z, &z_trigger_override, sizeof(double), cudaMemcpyHostToDevice, s));
-        d_zvals = tmp_z;
+        // OUT_TRANSFORM without data: one class = z_trigger, kept in a spare slot of the flag block
+        BF_CUDA_OK(cudaMemcpyAsync(w.flag + 15, &z_trigger_override, sizeof(double), cudaMemcpyHostToDevice, s));
+        d_zvals = w.flag + 15;
     }
     // coherence sort (chi2 only; outputs that are indexed by the original column stay unsorted)
     const bool sorted = what == OUT_CHI2 && !d_override && B >= 2048 && dm.kind != BF_MODEL_KSPACE_FFT;
@@ -1104,10 +1147,6 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 if (!cache_hit) { m->cached_key = key; m->cache_valid = false; }
             }
         }
-        if (shared_tables && !m->d_tabs_cache) {
-            BF_CUDA_OK(cudaMalloc((void **)&m->d_tabs_cache, (size_t)2 * dm.nr * 9 * sizeof(double2)));
-            const_cast<bf_model *>(m)->allocs.push_back(m->d_tabs_cache);
-        }
         if (shared_tables && cache_hit) {
             // basis tables of an earlier call are still valid: nothing to recompute
         } else if (shared_tables) {
@@ -1137,7 +1176,6 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                     BF_CUDA_OK(cudaMemcpy2DAsync(d_out + (size_t)t * dm.nr * ldo, (size_t)ldo * sizeof(double),
                                                  w.T + (size_t)t * dm.nr_pad * ldb, (size_t)ldb * sizeof(double),
                                                  (size_t)B * sizeof(double), dm.nr, cudaMemcpyDeviceToDevice, s));
-                if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
                 return BF_OK;
             }
             BF_KERNEL(ctx, "kspace_thomas_kernel",
@@ -1209,7 +1247,6 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             // out[((b*2 + comp)*npy + iy)*npx + ix]
             BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)f.npx * sizeof(double), w.fft_planes, (size_t)f.npx_pad * sizeof(double),
                                          (size_t)f.npx * sizeof(double), (size_t)B * 2 * f.npy_pad, cudaMemcpyDeviceToDevice, s));
-            if (tmp_z) BF_CUDA_OK(cudaFreeAsync(tmp_z, s));
             BF_CUDA_OK(cudaGetLastError());
             return BF_OK;
         }
@@ -1510,6 +1547,7 @@ static int run_device(bf_ctx *ctx, const bf_model *m, const bf_data *d, const do
                       double *d_out, int ldo, const double *d_override, int *d_status) {
     int rc = check_args(ctx, m, d, d_params, B);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     if (d->binning_type == BF_BINNING_MULTIPOLE)
         return run_device_multipole(ctx, m, d, d_params, B, what, d_out, ldo, d_override, d_status);
@@ -1547,6 +1585,7 @@ static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const doub
                     double *out, int ldo, int out_rows, const double *override_h, int *status) {
     int rc = check_args(ctx, m, d, params, B);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     const int npar = m->dev.npar;
     size_t nb_params = (size_t)B * npar * sizeof(double);
@@ -1607,6 +1646,7 @@ extern "C" int bf_transform_batch(bf_ctx *ctx, const bf_model *m, const double *
     if (!ctx || !m || !params || !out) BF_FAIL(BF_ERR_OPTIONS, "null argument");
     if (m->dev.kind != BF_MODEL_KSPACE) BF_FAIL(BF_ERR_ANALYSIS, "bf_transform_batch: not a k-space model");
     if (B <= 0 || ldb_out < B) BF_FAIL(BF_ERR_OPTIONS, "bf_transform_batch: bad batch size / leading dimension");
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     const int npar = m->dev.npar, nr = m->dev.nr;
     int cap = chunk_capacity(m, nullptr, 1);
@@ -1642,6 +1682,7 @@ extern "C" int bf_fft_planes_batch(bf_ctx *ctx, const bf_model *m, const double 
     if (!ctx || !m || !params || !out) BF_FAIL(BF_ERR_OPTIONS, "null argument");
     if (m->dev.kind != BF_MODEL_KSPACE_FFT) BF_FAIL(BF_ERR_ANALYSIS, "bf_fft_planes_batch: not an FFT model");
     if (B <= 0) BF_FAIL(BF_ERR_OPTIONS, "bf_fft_planes_batch: bad batch size");
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     const DevFft &f = m->dev.fft;
     const int npar = m->dev.npar;
@@ -1673,6 +1714,7 @@ extern "C" int bf_sample_toys(bf_ctx *ctx, const bf_data *d, const double *truth
                               long long first_toy, int ntoy, double scale, double *out) {
     if (!ctx || !d || !truth || !out || ntoy <= 0) BF_FAIL(BF_ERR_OPTIONS, "bf_sample_toys: bad argument");
     if (!d->d_L) BF_FAIL(BF_ERR_ANALYSIS, "bf_sample_toys: needs a covariance (not an inverse covariance)");
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t nb_truth = (size_t)d->n * sizeof(double), nb_out = (size_t)ntoy * d->n * sizeof(double);
@@ -1694,6 +1736,7 @@ extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth
                               long long first_toy, int ntoy, double scale, bf_toys **out) {
     if (!ctx || !d || !truth || !out || ntoy <= 0) BF_FAIL(BF_ERR_OPTIONS, "bf_toys_create: bad argument");
     if (!d->d_L) BF_FAIL(BF_ERR_ANALYSIS, "bf_toys_create: needs a covariance (not an inverse covariance)");
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     bf_toys *t = new bf_toys();
     t->ctx = ctx; t->ntoy = ntoy; t->n = d->n;
@@ -1715,6 +1758,7 @@ extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth
 
 extern "C" int bf_toys_destroy(bf_toys *t) {
     if (!t) return BF_OK;
+    std::lock_guard<std::recursive_mutex> lock(t->ctx->api_mu);
     cudaSetDevice(t->ctx->device);
     cudaFreeAsync(t->d_table, t->ctx->stream);
     delete t;
@@ -1723,6 +1767,7 @@ extern "C" int bf_toys_destroy(bf_toys *t) {
 
 extern "C" int bf_toys_download(bf_ctx *ctx, const bf_toys *t, double *out) {
     if (!ctx || !t || !out) BF_FAIL(BF_ERR_OPTIONS, "bf_toys_download: null argument");
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     BF_CUDA_OK(cudaMemcpyAsync(out, t->d_table, (size_t)t->ntoy * t->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -1734,6 +1779,7 @@ extern "C" int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *m, const bf_data 
     if (!chi2 || !toys || !toy_index) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_toys: null argument");
     int rc = check_args(ctx, m, d, params, B);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     if (toys->ctx != ctx || toys->n != d->n) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_toys: the toy table belongs to another context / data set");
     for (int b = 0; b < B; ++b)
         if (toy_index[b] < 0 || toy_index[b] >= toys->ntoy) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_toys: toy index out of range");
@@ -1774,6 +1820,7 @@ extern "C" int bf_gram_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, c
     if (!gram || nfit <= 0 || G < 1 || G > 96) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: bad argument (1 <= G <= 96)");
     int rc = check_args(ctx, m, d, params, nfit * G);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     if ((toys == nullptr) != (toy_index == nullptr)) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: toys and toy_index go together");
     if (toys) {
         if (toys->ctx != ctx || toys->n != d->n) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_batch: the toy table belongs to another context / data set");
@@ -1850,6 +1897,7 @@ static int gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const d
     if (!gram || !steps || nfit <= 0 || nprobe < 0 || G > 96) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: bad argument (2 nprobe + 1 <= 96)");
     int rc = check_args(ctx, m, d, centres, nfit);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     if ((toys == nullptr) != (toy_index == nullptr)) BF_FAIL(BF_ERR_OPTIONS, "bf_gram_probes: toys and toy_index go together");
     const int npar = m->dev.npar, n = d->n;
     for (int f = 0; f < nfit; ++f) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -133,8 +134,14 @@ struct DevModel {
 struct bf_ctx_t;
 }  // namespace bf
 
+struct bf_data;
+
 struct bf_ctx {
     int device = 0;
+    // Every compute entry point holds this lock for the duration of the call: two host threads may share one
+    // context (their calls are serialised on its stream); independent contexts never contend.
+    std::recursive_mutex api_mu;
+    std::vector<bf_data *> live_data;  // data objects of this context (bf_model_destroy purges their plans)
     cudaStream_t stream = nullptr;
     long long launches = 0;
     // growable workspaces (device)
@@ -157,6 +164,7 @@ struct bf_ctx {
 
 struct bf_model {
     bf_ctx *ctx = nullptr;
+    unsigned long long serial = 0;  // unique per created model: key of the (model, data) plans
     bf::DevModel dev;
     std::vector<void *> allocs;  // device allocations owned by the model
     // host copies needed at plan time
@@ -233,7 +241,7 @@ struct bf_data {
         double *d_WAt = nullptr;      // the same matrix in the stage layout of dgemm_chi2_fullm_kernel (n_pad <= 512)
         std::vector<void *> allocs;
     };
-    std::map<const bf_model *, Plan> plans;
+    std::map<unsigned long long, Plan> plans;  // keyed by bf_model::serial (never by address: addresses are reused)
 };
 
 struct bf_toys {

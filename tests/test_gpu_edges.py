@@ -92,3 +92,70 @@ def test_two_devices_in_one_process(ctx):
         for h in (g0, d0, g1, d1):
             h.close()
     ctx1.close()
+
+
+def test_plans_do_not_outlive_their_model(ctx):
+    """A (model, data) plan must never be found again by a *different* model that happens to reuse the address
+    of a destroyed one: create A (no distortion matrix, no metals), evaluate, destroy it, create B (distortion
+    matrix + metals) against the same Data object -- B's results must equal those of B on a fresh Data."""
+    mA, dA = W.qso_kspace(with_dist_matrix=False, with_metals=False)
+    mB, dB = W.qso_kspace()
+    rng = np.random.Generator(np.random.PCG64(77))
+    pA, pB = mA.random_batch(5, rng), mB.random_batch(5, rng)
+    gd = capi.Data(ctx, dB)  # carries the grid: usable by both models
+    fresh = capi.Data(ctx, dB)
+    for rep in range(6):  # several rounds so that the allocator does hand an old address out again
+        gA = capi.Model(ctx, mA)
+        cA, _ = capi.chi2_batch(ctx, gA, gd, pA)
+        gA.close()
+        gB = capi.Model(ctx, mB)
+        cB, _ = capi.chi2_batch(ctx, gB, gd, pB)
+        cB_fresh, _ = capi.chi2_batch(ctx, gB, fresh, pB)
+        gB.close()
+        assert np.array_equal(cB, cB_fresh)
+        if rep == 0:
+            cA0, cB0 = cA, cB
+        assert np.array_equal(cA, cA0) and np.array_equal(cB, cB0)
+    ref, _ = oracle.chi2_batch(oracle.OracleModel(mB), oracle.OracleData(dB), pB[:1], nthreads=8)
+    assert rel_err(cB0[:1], ref) < RTOL
+    gd.close(), fresh.close()
+
+
+def test_two_contexts_and_a_shared_context_from_two_threads(ctx):
+    """Runs on a one-GPU box: (1) two host threads, each with its own context / model / data on device 0,
+    evaluate concurrently; (2) two host threads share ONE context (calls are serialised by the context's lock).
+    Either way every thread gets exactly the single-threaded answer."""
+    import threading
+    m, d = W.qso_kspace()
+    rng = np.random.Generator(np.random.PCG64(3))
+    batches = [m.random_batch(700, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)}) for _ in range(2)]
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    want = [capi.chi2_batch(ctx, gm, gd, b)[0] for b in batches]
+    got, errs = [None, None], []
+
+    def own_context(k):
+        try:
+            c = capi.Context(0)
+            lm, ld = capi.Model(c, m), capi.Data(c, d)
+            for _ in range(8):
+                got[k] = capi.chi2_batch(c, lm, ld, batches[k])[0]
+            lm.close(), ld.close(), c.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    def shared_context(k):
+        try:
+            for _ in range(8):
+                got[k] = capi.chi2_batch(ctx, gm, gd, batches[k])[0]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    for target in (own_context, shared_context):
+        got[0] = got[1] = None
+        th = [threading.Thread(target=target, args=(k,)) for k in range(2)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for k in range(2):
+            assert np.array_equal(got[k], want[k], equal_nan=True), target.__name__
+    gm.close(), gd.close()

@@ -60,6 +60,33 @@ __global__ void dmma16816_kernel(double *out, int iters, double av, double bv) {
 }
 #endif
 
+// Do DMMA and DFMA overlap (separate pipes) or share one FP64 datapath? Even warps issue DMMA, odd warps DFMA;
+// if the combined rate stays at the single-pipe rate the two share the unit and a fused producer/consumer kernel
+// can only hide latency, not add throughput.
+__global__ void mixed_kernel(double *out, int iters, double a, double b) {
+    const int warp = threadIdx.x >> 5;
+    double x[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { x[i][0] = threadIdx.x * 1e-9 + i; x[i][1] = i; }
+    if (warp & 1) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { x[i][0] = fma(x[i][0], a, b); x[i][1] = fma(x[i][1], a, b); }
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dmma884(x[i][0], x[i][1], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i][0] + x[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F> static float time_ms(F f, int reps) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -86,6 +113,10 @@ int main() {
         ms = time_ms([&] { dmma884_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
         flops = 2.0 * 256 * 16 * iters * (double)wpb * blocks;
         printf(", \"dmma884_tflops_w%d\": %.3f", wpb, flops / ms * 1e-9);
+        // mixed: half the warps DMMA (2*256*16 flop per warp-iteration), half DFMA (2*128*32 flop per warp-iteration: the same pipe time if shared)
+        ms = time_ms([&] { mixed_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        flops = (2.0 * 256 * 16 + 2.0 * 128 * 32) * iters * (double)(wpb / 2) * blocks;
+        printf(", \"mixed_dmma_dfma_tflops_w%d\": %.3f", wpb, flops / ms * 1e-9);
 #ifdef HAVE_M16
         ms = time_ms([&] { dmma16816_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
         flops = 2.0 * 16 * 8 * 16 * 8 * iters * (double)wpb * blocks;
