@@ -809,6 +809,14 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
                     }
             }
             if ((rc2 = upload(p.allocs, mx.data(), mx.size(), &t.mx))) return rc2;
+            // the same rows with the periodic wrap of the Catmull-Rom stencil materialised (halo row -1 in front, rows
+            // ny and ny+1 behind): the fused kernel stages windows of consecutive rows and never wraps an index
+            const int nyh = ny + 3;
+            std::vector<double> mxh((size_t)npts * nyh * nt);
+            for (int i = 0; i < npts; ++i)
+                for (int row = 0; row < nyh; ++row)
+                    std::memcpy(&mxh[((size_t)i * nyh + row) * nt], &mx[((size_t)i * ny + wrap(row - 1, ny)) * nt], sizeof(double) * nt);
+            if ((rc2 = upload(p.allocs, mxh.data(), mxh.size(), &t.mxh))) return rc2;
         }
         return BF_OK;
     };
@@ -946,6 +954,11 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
             std::vector<double> wat((size_t)(ktot / kFullmKC) * n_pad * kFullmLdA);
             gemm_fullm_tile_A(wa.data(), n_pad, ktot, ktot, wat.data());
             if ((rc = upload(p.allocs, wat.data(), wat.size(), &p.d_WAt))) return rc;
+        }
+        if (!data_mode && ktot % 8 == 0) {
+            std::vector<double> waf((size_t)n_pad * ktot);
+            gemm_fused_tile_A(wa.data(), n_pad, ktot, ktot, waf.data());
+            if ((rc = upload(p.allocs, waf.data(), waf.size(), &p.d_WAf))) return rc;
         }
         p.fold_ok = true;
         p.fold_data_mode = data_mode;
@@ -1300,7 +1313,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         pt.zc_metal = grid ? plan->d_zc_metal_grid : plan->d_zc_metal_data;
         pt.zc_stride = grid ? d->n_grid_pad : d->n_pad;
         for (int q = 0; q < 4; ++q) { pt.bb_rt[q] = t.bb_rt[q]; pt.bb_z[q] = t.bb_z[q]; pt.n_rt[q] = t.n_rt[q]; pt.n_z[q] = t.n_z[q]; }
-        pt.mx = t.mx; pt.mx_ny = dm.metal_ny; pt.mx_nt = dm.metal_ncomb * 3;
+        pt.mx = t.mx; pt.mxh = t.mxh; pt.mx_ny = dm.metal_ny; pt.mx_nt = dm.metal_ncomb * 3;
     };
     FastArgs fa;
     std::memset(&fa, 0, sizeof(fa));
@@ -1321,7 +1334,37 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         a.mode = 1;
         a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
         if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
-        if (shared_tables) {
+        // Headline path: the model pass is the producer of the chi2 GEMM's right-hand operand (kernels_fused.cu);
+        // xi_u is never written to HBM. BAOFIT_UNFUSED=1 keeps the separate passes (A/B measurements).
+        static const bool no_fused = std::getenv("BAOFIT_UNFUSED") != nullptr;
+        if (what == OUT_CHI2 && shared_tables && !d_override && plan->fold_ok && plan->d_WAf && plan->nz == 1 && !no_fused) {
+            FusedArgs fu;
+            std::memset(&fu, 0, sizeof(fu));
+            fu.m = dm;
+            fill_tab(plan->tab_grid, true, fu.pt);
+            fu.pT = w.pT; fu.S = w.S; fu.vfac = plan->d_vfac; fu.tabs = m->d_tabs_cache; fu.ldb = ldb; fu.B = B;
+            fu.zc_trigger = plan->zc_trigger;
+            fu.At = plan->d_WAf; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
+            fu.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
+            fu.chi2 = chi2_dst; fu.status = w.status;
+            if (fused_chi2_supported(fu)) {
+                FoldArgs fo;
+                std::memset(&fo, 0, sizeof(fo));
+                fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
+                fo.zc_data = plan->zc_trigger;
+                fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
+                fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz;
+                fo.minus_d_row_value = 1;
+                fo.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
+                fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
+                BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
+                BF_KERNEL(ctx, "fused_model_chi2_kernel", launch_fused_model_chi2(s, fu, ctx->sm_count));
+                finished = true;
+            }
+        }
+        if (finished) {
+            // nothing left to do for this chunk
+        } else if (shared_tables) {
             fill_tab(plan->tab_grid, true, fa.pt);
             fa.mode = 1; fa.out = a.out; fa.ldo = a.ldo;
             if (what == OUT_XIU) fa.pt.npts_pad = fa.pt.npts;

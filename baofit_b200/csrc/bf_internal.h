@@ -226,7 +226,7 @@ struct bf_data {
             double *rpar0 = nullptr, *rperp0 = nullptr;
             double *bb_rt[4] = {nullptr, nullptr, nullptr, nullptr}, *bb_z[4] = {nullptr, nullptr, nullptr, nullptr};
             int n_rt[4] = {0, 0, 0, 0}, n_z[4] = {0, 0, 0, 0};
-            double *mx = nullptr;
+            double *mx = nullptr, *mxh = nullptr;
         } tab_data, tab_grid;
         // Fused tail of the distortion-matrix path: chi2 = || WA . [xi_u ; coef(b) ; 1] ||^2 with
         // WA = W . [D_kept | broadband basis | -d]  (see DESIGN.md "fused tail")
@@ -239,6 +239,7 @@ struct bf_data {
         double *d_Aext = nullptr;     // [n_pad][n_grid_pad + fold_kext]
         double *d_WA = nullptr;       // [n_pad][n_grid_pad + fold_kext]
         double *d_WAt = nullptr;      // the same matrix in the stage layout of dgemm_chi2_fullm_kernel (n_pad <= 512)
+        double *d_WAf = nullptr;      // the same matrix tiled [K/4][M][4] for fused_model_chi2_kernel
         std::vector<void *> allocs;
     };
     std::map<unsigned long long, Plan> plans;  // keyed by bf_model::serial (never by address: addresses are reused)

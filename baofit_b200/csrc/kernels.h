@@ -63,6 +63,7 @@ struct PointTab {
     int n_rt[4], n_z[4];
     // cross metal templates collapsed along r_perp: mx[(i*mx_ny + row)*mx_nt + t]
     const double *mx;
+    const double *mxh;                 // the same with halo rows: mxh[(i*(mx_ny+3) + row+1)*mx_nt + t], row = -1 .. mx_ny+1 (wrapped copies)
     int mx_ny, mx_nt;
 };
 
@@ -80,6 +81,25 @@ struct FastArgs {
     int rspace;            // the r-space model through the cosmology pass (tables built at model creation)
     int sub_dov_in_part1;  // fused data tail: the cosmology pass subtracts the per-column data override itself
 };
+
+// Fused model + distortion matrix + chi-square kernel (kernels_fused.cu): the model evaluation on the grid bins
+// is the producer of the right-hand operand of chi2 = || WA . [xi_u ; coefficient rows] ||^2.
+struct FusedArgs {
+    DevModel m;
+    PointTab pt;                 // grid bins
+    const double *pT, *S, *vfac;
+    const double2 *tabs;         // shared-transform basis tables
+    int ldb, B, zc_trigger;
+    const double *At;            // WA pre-tiled as [K/4][M][4] (gemm_fused_tile_A)
+    int M, K, kgrid;             // rows of WA; K = kgrid + kext; rows 0..kgrid-1 of the panel come from the model
+    const double *rows;          // [kext][ldb] coefficient rows (fold_coef_kernel)
+    double *chi2;
+    const int *status;
+    int debug;                   // timing experiments only (BAOFIT_FUSED_DEBUG): 2 = consumers skip the DMMAs (producer-bound time)
+};
+void gemm_fused_tile_A(const double *A, int M, int K, int lda, double *At /* [K/4][M][4] */);
+bool fused_chi2_supported(const FusedArgs &a);
+void launch_fused_model_chi2(cudaStream_t s, const FusedArgs &a, int sm_count);
 
 // Coefficient rows of the fused tail + dilation-limit check of the data bins.
 struct FoldArgs {

@@ -149,7 +149,7 @@ def test_kspace_shared_and_per_vector_paths_agree(ctx):
     gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
     ctx.set_profiling(True)
     shared, _ = capi.chi2_batch(ctx, gm, gd, params[1:])
-    assert any(k.startswith("kspace_fast_eval_kernel") for k in ctx.get_profile())
+    assert any(k.startswith(("kspace_fast_eval_kernel", "fused_model_chi2_kernel")) for k in ctx.get_profile())
     mixed = params.copy()
     mixed[0, m.index("SigmaNL-perp")] *= 1.1
     ctx.set_profiling(True)
@@ -383,3 +383,52 @@ def test_rspace_fast_and_generic_kernels_against_oracle(ctx):
         assert np.max(np.abs(pred - ref_pred)) < RTOL * np.max(np.abs(ref_pred))
         assert rel_err(chi2, ref_chi2) < RTOL
         gm.close(), gd.close()
+
+
+def test_fused_producer_kernel_equals_unfused_chain(built):
+    """BASELINE config 4, 20 000 vectors: fused_model_chi2_kernel (model evaluation as the producer of the chi2 GEMM's
+    right-hand operand) against the separate cosmology / metal / GEMM kernels (BAOFIT_UNFUSED=1 in a child process:
+    the switch is read once per process), and both against the oracle on a subset."""
+    import json, subprocess, sys, tempfile
+    code = r"""
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+from baofit_b200 import capi, workloads as W
+m, d = W.qso_kspace()
+rng = np.random.Generator(np.random.PCG64(91))
+p = m.random_batch(20000, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5), "delta-v": (-300, 300)})
+p[:40, m.index("delta-v")] = np.linspace(-3000, 3000, 40)   # one panel whose velocity shifts do not fit a staged window
+ctx = capi.Context(0)
+gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+ctx.set_profiling(True)
+chi2, st = capi.chi2_batch(ctx, gm, gd, p)
+names = sorted(ctx.get_profile())
+np.save(sys.argv[1], np.vstack([chi2, st]))
+print(json.dumps(names))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("fused", "unfused"):
+            env = dict(os.environ)
+            env.pop("BAOFIT_UNFUSED", None)
+            if mode == "unfused":
+                env["BAOFIT_UNFUSED"] = "1"
+            path = os.path.join(tmp, mode + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            out[mode] = (np.load(path), json.loads(r.stdout.strip().splitlines()[-1]))
+    assert "fused_model_chi2_kernel" in out["fused"][1] and "fused_model_chi2_kernel" not in out["unfused"][1]
+    (cf, sf), (cu, su) = out["fused"][0], out["unfused"][0]
+    assert np.array_equal(sf, su)
+    ok = sf == 0
+    assert ok.sum() > 15000 and np.all(np.isnan(cf[~ok]))
+    assert rel_err(cf[ok], cu[ok]) < 1e-11
+    m, d = W.qso_kspace()
+    rng = np.random.Generator(np.random.PCG64(91))
+    p = m.random_batch(20000, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5), "delta-v": (-300, 300)})
+    p[:40, m.index("delta-v")] = np.linspace(-3000, 3000, 40)
+    pick = np.r_[0:6, 19990:19996]
+    ref, rst = oracle.chi2_batch(oracle.OracleModel(m), oracle.OracleData(d), p[pick], nthreads=os.cpu_count() or 8)
+    assert np.array_equal(rst, sf[pick].astype(rst.dtype))
+    good = rst == 0
+    assert rel_err(cf[pick][good], ref[good]) < RTOL
