@@ -21,7 +21,7 @@ EXPORTS = [
     "bf_data_create", "bf_data_destroy", "bf_data_ndata", "bf_eval_batch", "bf_chi2_batch",
     "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
-    "bf_fft_planes_batch", "bf_model_fft_plane_dims",
+    "bf_fft_planes_batch", "bf_model_fft_plane_dims", "bf_kspace_transform_weights",
     "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch", "bf_gram_probes", "bf_normal_probes", "bf_pinned_alloc", "bf_pinned_free",
 ]
 
@@ -85,6 +85,7 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p]
         L.bf_fft_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.bf_model_fft_plane_dims.argtypes = [C.c_void_p, c_int_p, c_int_p]
+        L.bf_kspace_transform_weights.argtypes = [C.c_void_p, c_int_p, c_int_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -270,6 +271,15 @@ def normal_probes(ctx, model, data, centres, steps, toys=None, toy_index=None):
     _check(lib().bf_normal_probes(ctx.h, model.h, data.h, _ptr(c), _ptr(h), nfit, n, toys.h if toys is not None else None,
                                   _ptr(idx), _ptr(out), _ptr(status)))
     return out[:, :(n + 1) * (n + 1)].reshape(nfit, n + 1, n + 1), out[:, (n + 1) * (n + 1):], status
+
+
+def kspace_transform_weights(model):
+    """Host-side Bessel weights [2][3][nr][nk] of a k-space model description (no GPU involved)."""
+    nr, nk = C.c_int(0), C.c_int(0)
+    _check(lib().bf_kspace_transform_weights(C.addressof(model.desc), C.byref(nr), C.byref(nk), None))
+    w = np.zeros((2, 3, nr.value, nk.value))
+    _check(lib().bf_kspace_transform_weights(C.addressof(model.desc), C.byref(nr), C.byref(nk), _ptr(w)))
+    return w
 
 
 def eval_batch(ctx, model, data, params):

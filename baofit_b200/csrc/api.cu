@@ -471,10 +471,14 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
         dm.th_w = p;
         if ((rc = upload(m->allocs, thd.data(), thd.size(), &p))) return fail(rc);
         dm.th_inv_diag = p;
-        {   // shared-transform basis tables (filled on first use, kept while the key parameters are unchanged)
+        {   // shared-transform basis tables (filled on first use, kept while the key parameters are unchanged), the key
+            // they were built for and the two ints the device-side decision is published in
             cudaError_t e = cudaMalloc((void **)&m->d_tabs_cache, (size_t)2 * dm.nr * 9 * sizeof(double2));
+            if (e == cudaSuccess) { m->allocs.push_back(m->d_tabs_cache); e = cudaMalloc((void **)&m->d_keystate, 32 * sizeof(double)); }
+            if (e == cudaSuccess) { m->allocs.push_back(m->d_keystate); e = cudaMalloc((void **)&m->d_gate, 4 * sizeof(int)); }
+            if (e == cudaSuccess) { m->allocs.push_back(m->d_gate); e = cudaMemset(m->d_keystate, 0, 32 * sizeof(double)); }
+            if (e == cudaSuccess) e = cudaMemset(m->d_gate, 0, 4 * sizeof(int));
             if (e != cudaSuccess) { bf::set_error(std::string("bf_model_create: cudaMalloc: ") + cudaGetErrorString(e)); return fail(BF_ERR_ANALYSIS); }
-            m->allocs.push_back(m->d_tabs_cache);
         }
     }
     // metals
@@ -1100,6 +1104,10 @@ static int gemm_chi2_scratch(bf_ctx *ctx, cudaStream_t s, GemmArgs &g) {
     return BF_OK;
 }
 
+// Below this many vectors a persistent CTA per 32-column panel leaves most SMs idle (one panel is a serial chain of 66
+// stages, ~80 us): small batches keep the separate passes, whose chi2 GEMM splits its row tiles over CTAs.
+constexpr int kFusedMinBatch = 1024;
+
 enum Output { OUT_PRED, OUT_CHI2, OUT_XIU, OUT_TRANSFORM, OUT_WHITENED /* y = L^-1 (pred - d), [n_pad][ldo] */ };
 
 // Runs one chunk (B <= chunk capacity) entirely on the context's stream.
@@ -1132,67 +1140,69 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status));
     double *chi2_dst = sorted ? w.chi2_sorted : d_out;
 
-    bool shared_tables = false;
+    // ---- k-space model: which chain runs is decided on the device (no host round trip inside a call) ----
+    const Gate ungated{nullptr, 0};
+    bool can_share = false;  // shared-transform fast path possible: polynomial tracer factor (no UV / HCD terms)
+    ProjArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    // per-vector transform chain: multipoles of D(k,mu) -> Hankel GEMM -> spline second derivatives
+    auto emit_transform = [&](Gate gate) -> int {
+        pa.G = w.G;
+        pa.gate = gate;
+        BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));
+        GemmArgs g{};
+        g.gate = gate;
+        g.A = dm.hankel; g.Bm = w.G; g.C = w.T;
+        g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
+        g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
+        g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
+        BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6));
+        if (what == OUT_TRANSFORM) {
+            // out[((comp*3+l)*nr + j)*ldo + b]
+            for (int t = 0; t < 6; ++t)
+                BF_CUDA_OK(cudaMemcpy2DAsync(d_out + (size_t)t * dm.nr * ldo, (size_t)ldo * sizeof(double),
+                                             w.T + (size_t)t * dm.nr_pad * ldb, (size_t)ldb * sizeof(double),
+                                             (size_t)B * sizeof(double), dm.nr, cudaMemcpyDeviceToDevice, s));
+            return BF_OK;
+        }
+        BF_KERNEL(ctx, "kspace_thomas_kernel",
+                  launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2, gate));
+        return BF_OK;
+    };
     if (dm.kind == BF_MODEL_KSPACE) {
-        ProjArgs pa;
         pa.m = dm; pa.pT = w.pT; pa.S = w.S; pa.ldb = ldb; pa.B = B;
         pa.zc_trigger = plan ? plan->zc_trigger : 0;
         double ztrig = plan ? plan->zvals[plan->zc_trigger] : z_trigger_override;
         (void)use_ztrig_override;
         double zeff = dm.zeff > 0 ? dm.zeff : ztrig;
         nl_table(dm, zeff, pa.nl_tab, &pa.nl_pk_scale);
-        // Shared-transform fast path: possible when the tracer factor of D(k,mu) is polynomial
-        // (no UV / HCD terms) and every vector of the chunk has the same key parameters.
-        bool cache_hit = false;
-        if (what != OUT_TRANSFORM && !(dm.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT))) {
+        if (what == OUT_TRANSFORM) return emit_transform(ungated);
+        // Shared-transform fast path: possible when the tracer factor of D(k,mu) is polynomial (no UV / HCD terms) and
+        // every vector of the chunk has the same key parameters. kspace_key_check_kernel compares the vectors,
+        // kspace_key_decide_kernel compares their key with the one the cached basis tables were built for and sets
+        // gate[0] (shared) / gate[1] (rebuild the tables); everything downstream is predicated on those two ints.
+        can_share = !(dm.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT));
+        if (can_share) {
             BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
             BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
-            BF_CUDA_OK(cudaMemcpyAsync(ctx->pinned_flag, w.flag, sizeof(double) * kKeyMax, cudaMemcpyDeviceToHost, s));
-            BF_CUDA_OK(cudaStreamSynchronize(s));
-            shared_tables = (ctx->pinned_flag[0] == 0.0);
-            if (shared_tables) {
-                // key of this chunk: the key parameters of vector 0 plus everything else K(k,mu) sees
-                std::vector<double> key(ctx->pinned_flag + 1, ctx->pinned_flag + kKeyMax);
-                key.push_back(zeff);
-                key.push_back(pa.nl_pk_scale);
-                for (int q = 0; q < 5; ++q) key.push_back(pa.nl_tab[q]);
-                cache_hit = m->cache_valid && key == m->cached_key;
-                if (!cache_hit) { m->cached_key = key; m->cache_valid = false; }
-            }
-        }
-        if (shared_tables && cache_hit) {
-            // basis tables of an earlier call are still valid: nothing to recompute
-        } else if (shared_tables) {
+            KeyExtras ex;
+            ex.v[0] = zeff;
+            ex.v[1] = pa.nl_pk_scale;
+            for (int q = 0; q < 5; ++q) ex.v[2 + q] = pa.nl_tab[q];
+            BF_KERNEL(ctx, "kspace_key_decide_kernel", launch_kspace_key_decide(s, w.flag, m->d_keystate, m->d_gate, ex));
+            const Gate rebuild{m->d_gate + 1, 1};
             pa.G = w.Gb;
+            pa.gate = rebuild;
             BF_CUDA_OK(cudaMemsetAsync(w.Gb, 0, (size_t)6 * dm.nk_pad * kPadN * sizeof(double), s));
             BF_KERNEL(ctx, "kspace_basis_project_kernel", launch_kspace_basis_project(s, pa));
             GemmArgs g{};
+            g.gate = rebuild;
             g.A = dm.hankel; g.Bm = w.Gb; g.C = w.Tb;
             g.M = dm.nr_pad; g.N = 3; g.K = dm.nk_pad;
             g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
             g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
             BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
-            BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, m->d_tabs_cache));
-            m->cache_valid = true;
-        } else {
-            pa.G = w.G;
-            BF_KERNEL(ctx, "kspace_project_kernel", launch_kspace_project(s, pa, ctx->sm_count));
-            GemmArgs g{};
-            g.A = dm.hankel; g.Bm = w.G; g.C = w.T;
-            g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
-            g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
-            g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
-            BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6));
-            if (what == OUT_TRANSFORM) {
-                // out[((comp*3+l)*nr + j)*ldo + b]
-                for (int t = 0; t < 6; ++t)
-                    BF_CUDA_OK(cudaMemcpy2DAsync(d_out + (size_t)t * dm.nr * ldo, (size_t)ldo * sizeof(double),
-                                                 w.T + (size_t)t * dm.nr_pad * ldb, (size_t)ldb * sizeof(double),
-                                                 (size_t)B * sizeof(double), dm.nr, cudaMemcpyDeviceToDevice, s));
-                return BF_OK;
-            }
-            BF_KERNEL(ctx, "kspace_thomas_kernel",
-                      launch_kspace_thomas(s, B, ldb, dm.nr, dm.nr_pad, dm.tr_dr, dm.th_w, dm.th_inv_diag, w.T, w.C2));
+            BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, m->d_tabs_cache, rebuild));
         }
     }
 
@@ -1295,220 +1305,243 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         return BF_OK;
     }
 
-    EvalArgs a;
-    std::memset(&a, 0, sizeof(a));
-    a.m = dm; a.pT = w.pT; a.S = w.S; a.ldb = ldb; a.B = B;
-    a.vfac = plan->d_vfac; a.T = w.T; a.C2 = w.C2; a.status = w.status;
-    a.tabs = m->d_tabs_cache; a.zc_trigger = plan->zc_trigger;
-    const bool use_dm = dm.dm_order > 0;
-    const bool to_user = what == OUT_PRED;  // final rows go straight to the caller's buffer
+    // Everything from the model evaluation to the chi-square / prediction, for one of the two table sources.
+    auto emit = [&](bool shared_tables, Gate gate) -> int {
+        EvalArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.m = dm; a.pT = w.pT; a.S = w.S; a.ldb = ldb; a.B = B;
+        a.vfac = plan->d_vfac; a.T = w.T; a.C2 = w.C2; a.status = w.status; a.gate = gate;
+        a.tabs = m->d_tabs_cache; a.zc_trigger = plan->zc_trigger;
+        const bool use_dm = dm.dm_order > 0;
+        const bool to_user = what == OUT_PRED;  // final rows go straight to the caller's buffer
 
-    auto fill_tab = [&](const bf_data::Plan::PointTabDev &t, bool grid, PointTab &pt) {
-        pt.npts = grid ? d->n_grid : d->n;
-        pt.npts_pad = grid ? d->n_grid_pad : d->n_pad;
-        pt.rpar0 = t.rpar0; pt.rperp0 = t.rperp0;
-        pt.z = grid ? d->d_grid_z : d->d_z;
-        pt.zc = grid ? plan->d_zc_grid : plan->d_zc_data;
-        pt.gidx = grid ? nullptr : d->d_index;
-        pt.zc_metal = grid ? plan->d_zc_metal_grid : plan->d_zc_metal_data;
-        pt.zc_stride = grid ? d->n_grid_pad : d->n_pad;
-        for (int q = 0; q < 4; ++q) { pt.bb_rt[q] = t.bb_rt[q]; pt.bb_z[q] = t.bb_z[q]; pt.n_rt[q] = t.n_rt[q]; pt.n_z[q] = t.n_z[q]; }
-        pt.mx = t.mx; pt.mxh = t.mxh; pt.mx_ny = dm.metal_ny; pt.mx_nt = dm.metal_ncomb * 3;
-    };
-    FastArgs fa;
-    std::memset(&fa, 0, sizeof(fa));
-    fa.m = dm; fa.pT = w.pT; fa.S = w.S; fa.vfac = plan->d_vfac; fa.tabs = m->d_tabs_cache; fa.ldb = ldb; fa.B = B;
-    fa.nz = plan->nz; fa.zc_trigger = plan->zc_trigger; fa.status = w.status;
-    if (dm.kind == BF_MODEL_RSPACE && m->d_rs_tabs) {
-        // r-space model through the fast pass (tables are static)
-        shared_tables = true;
-        fa.tabs = m->d_rs_tabs;
-        fa.rspace = 1;
-    }
-    bool finished = false;
-    if (use_dm) {
-        // undistorted xi on the full grid
-        a.npts = d->n_grid; a.npts_pad = d->n_grid_pad;
-        a.r = d->d_grid_r; a.mu = d->d_grid_mu; a.z = d->d_grid_z; a.zc = plan->d_zc_grid; a.gidx = nullptr;
-        a.zc_metal = plan->d_zc_metal_grid; a.zc_stride = d->n_grid_pad;
-        a.mode = 1;
-        a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
-        if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
-        // Headline path: the model pass is the producer of the chi2 GEMM's right-hand operand (kernels_fused.cu);
-        // xi_u is never written to HBM. BAOFIT_UNFUSED=1 keeps the separate passes (A/B measurements).
-        static const bool no_fused = std::getenv("BAOFIT_UNFUSED") != nullptr;
-        if (what == OUT_CHI2 && shared_tables && !d_override && plan->fold_ok && plan->d_WAf && plan->nz == 1 && !no_fused) {
-            FusedArgs fu;
-            std::memset(&fu, 0, sizeof(fu));
-            fu.m = dm;
-            fill_tab(plan->tab_grid, true, fu.pt);
-            fu.pT = w.pT; fu.S = w.S; fu.vfac = plan->d_vfac; fu.tabs = m->d_tabs_cache; fu.ldb = ldb; fu.B = B;
-            fu.zc_trigger = plan->zc_trigger;
-            fu.At = plan->d_WAf; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
-            fu.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
-            fu.chi2 = chi2_dst; fu.status = w.status;
-            if (fused_chi2_supported(fu)) {
+        auto fill_tab = [&](const bf_data::Plan::PointTabDev &t, bool grid, PointTab &pt) {
+            pt.npts = grid ? d->n_grid : d->n;
+            pt.npts_pad = grid ? d->n_grid_pad : d->n_pad;
+            pt.rpar0 = t.rpar0; pt.rperp0 = t.rperp0;
+            pt.z = grid ? d->d_grid_z : d->d_z;
+            pt.zc = grid ? plan->d_zc_grid : plan->d_zc_data;
+            pt.gidx = grid ? nullptr : d->d_index;
+            pt.zc_metal = grid ? plan->d_zc_metal_grid : plan->d_zc_metal_data;
+            pt.zc_stride = grid ? d->n_grid_pad : d->n_pad;
+            for (int q = 0; q < 4; ++q) { pt.bb_rt[q] = t.bb_rt[q]; pt.bb_z[q] = t.bb_z[q]; pt.n_rt[q] = t.n_rt[q]; pt.n_z[q] = t.n_z[q]; }
+            pt.mx = t.mx; pt.mxh = t.mxh; pt.mx_ny = dm.metal_ny; pt.mx_nt = dm.metal_ncomb * 3;
+        };
+        FastArgs fa;
+        std::memset(&fa, 0, sizeof(fa));
+        fa.m = dm; fa.pT = w.pT; fa.S = w.S; fa.vfac = plan->d_vfac; fa.tabs = m->d_tabs_cache; fa.ldb = ldb; fa.B = B;
+        fa.nz = plan->nz; fa.zc_trigger = plan->zc_trigger; fa.status = w.status; fa.gate = gate;
+        if (dm.kind == BF_MODEL_RSPACE && m->d_rs_tabs) {
+            // r-space model through the fast pass (tables are static)
+            fa.tabs = m->d_rs_tabs;
+            fa.rspace = 1;
+        }
+        bool finished = false;
+        if (use_dm) {
+            // undistorted xi on the full grid
+            a.npts = d->n_grid; a.npts_pad = d->n_grid_pad;
+            a.r = d->d_grid_r; a.mu = d->d_grid_mu; a.z = d->d_grid_z; a.zc = plan->d_zc_grid; a.gidx = nullptr;
+            a.zc_metal = plan->d_zc_metal_grid; a.zc_stride = d->n_grid_pad;
+            a.mode = 1;
+            a.out = w.XiU; a.ldo = ldb; a.dsub = nullptr; a.dov = nullptr;
+            if (what == OUT_XIU) { a.out = d_out; a.ldo = ldo; a.npts_pad = a.npts; }
+            // Headline path: the model pass is the producer of the chi2 GEMM's right-hand operand (kernels_fused.cu);
+            // xi_u is never written to HBM. BAOFIT_UNFUSED=1 keeps the separate passes (A/B measurements).
+            static const bool no_fused = std::getenv("BAOFIT_UNFUSED") != nullptr;
+            if (what == OUT_CHI2 && shared_tables && !d_override && plan->fold_ok && plan->d_WAf && plan->nz == 1 && !no_fused && B >= kFusedMinBatch) {
+                FusedArgs fu;
+                std::memset(&fu, 0, sizeof(fu));
+                fu.gate = gate;
+                fu.m = dm;
+                fill_tab(plan->tab_grid, true, fu.pt);
+                fu.pT = w.pT; fu.S = w.S; fu.vfac = plan->d_vfac; fu.tabs = m->d_tabs_cache; fu.ldb = ldb; fu.B = B;
+                fu.zc_trigger = plan->zc_trigger;
+                fu.At = plan->d_WAf; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
+                fu.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
+                fu.chi2 = chi2_dst; fu.status = w.status;
+                if (fused_chi2_supported(fu)) {
+                    FoldArgs fo;
+                    std::memset(&fo, 0, sizeof(fo));
+                    fo.gate = gate;
+                    fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
+                    fo.zc_data = plan->zc_trigger;
+                    fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
+                    fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz;
+                    fo.minus_d_row_value = 1;
+                    fo.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
+                    fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
+                    BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
+                    BF_KERNEL(ctx, "fused_model_chi2_kernel", launch_fused_model_chi2(s, fu, ctx->sm_count));
+                    finished = true;
+                }
+            }
+            if (finished) {
+                // nothing left to do for this chunk
+            } else if (shared_tables) {
+                fill_tab(plan->tab_grid, true, fa.pt);
+                fa.mode = 1; fa.out = a.out; fa.ldo = a.ldo;
+                if (what == OUT_XIU) fa.pt.npts_pad = fa.pt.npts;
+                if (fast_eval_is_lean(fa)) {
+                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
+                    if (fast_eval_has_extras(fa))
+                        BF_KERNEL(ctx, "kspace_fast_eval_kernel<extras>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 2));
+                } else
+                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<all>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 0));
+            } else
+                BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
+            if (what == OUT_XIU) finished = true;
+            if (!finished && plan->fold_ok && !d_override) {
+                // fused tail: the post-matrix broadband and "- d" are extra K rows of the panel, and for
+                // chi2 the whitening W is folded into the left matrix: one GEMM, squares in the epilogue
                 FoldArgs fo;
                 std::memset(&fo, 0, sizeof(fo));
+                    fo.gate = gate;
                 fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
-                fo.zc_data = plan->zc_trigger;
+                fo.zc_data = plan->zc_trigger;  // single class of the data bins (= class of the first kept bin)
                 fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
                 fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz;
-                fo.minus_d_row_value = 1;
+                fo.minus_d_row_value = (what == OUT_CHI2 || what == OUT_WHITENED) ? 1 : 0;
                 fo.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
                 fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
                 BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
-                BF_KERNEL(ctx, "fused_model_chi2_kernel", launch_fused_model_chi2(s, fu, ctx->sm_count));
+                GemmArgs g{};
+            g.gate = gate;
+                g.Bm = w.XiU;
+                g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad + plan->fold_kext;
+                g.lda = g.K; g.ldb = ldb;
+                if (what == OUT_CHI2) {
+                    g.A = plan->d_WA; g.C = nullptr; g.ldc = 0;
+                    g.chi2 = chi2_dst; g.status = w.status;
+                    // opt-in: reads the panel from HBM exactly once, but streams the left matrix from L2 twice as
+                    // often (32-column panels) and measures slower on B200 (0.63 vs 0.56 ms)
+                    static const bool use_fullm = std::getenv("BAOFIT_FULLM_GEMM") != nullptr;
+                    if (plan->d_WAt && use_fullm) {
+                        g.A = plan->d_WAt;
+                        BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2_fullm(s, g, ctx->sm_count));
+                    } else {
+                        if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+                        BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g, ctx->sm_count));
+                    }
+                } else if (what == OUT_WHITENED) {
+                    // whitened residuals for the normal-equation probes: the same folded left matrix, store epilogue
+                    g.A = plan->d_WA; g.C = d_out; g.ldc = ldo;
+                    BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused tail]", launch_gemm_store(s, g, 1));
+                } else {
+                    g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
+                    BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));
+                    BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
+                                                 (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
+                }
                 finished = true;
             }
-        }
-        if (finished) {
-            // nothing left to do for this chunk
-        } else if (shared_tables) {
-            fill_tab(plan->tab_grid, true, fa.pt);
-            fa.mode = 1; fa.out = a.out; fa.ldo = a.ldo;
-            if (what == OUT_XIU) fa.pt.npts_pad = fa.pt.npts;
-            if (fast_eval_is_lean(fa)) {
-                BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
-                if (fast_eval_has_extras(fa))
-                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<extras>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 2));
-            } else
-                BF_KERNEL(ctx, "kspace_fast_eval_kernel<all>[grid]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 0));
-        } else
-            BF_KERNEL(ctx, "kspace_eval_kernel[grid]", launch_kspace_eval(s, a, ctx->sm_count));
-        if (what == OUT_XIU) finished = true;
-        if (!finished && plan->fold_ok && !d_override) {
-            // fused tail: the post-matrix broadband and "- d" are extra K rows of the panel, and for
-            // chi2 the whitening W is folded into the left matrix: one GEMM, squares in the epilogue
-            FoldArgs fo;
-            std::memset(&fo, 0, sizeof(fo));
-            fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
-            fo.zc_data = plan->zc_trigger;  // single class of the data bins (= class of the first kept bin)
-            fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
-            fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz;
-            fo.minus_d_row_value = (what == OUT_CHI2 || what == OUT_WHITENED) ? 1 : 0;
-            fo.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
-            fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
-            BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
-            GemmArgs g{};
-            g.Bm = w.XiU;
-            g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad + plan->fold_kext;
-            g.lda = g.K; g.ldb = ldb;
-            if (what == OUT_CHI2) {
-                g.A = plan->d_WA; g.C = nullptr; g.ldc = 0;
-                g.chi2 = chi2_dst; g.status = w.status;
-                // opt-in: reads the panel from HBM exactly once, but streams the left matrix from L2 twice as
-                // often (32-column panels) and measures slower on B200 (0.63 vs 0.56 ms)
-                static const bool use_fullm = std::getenv("BAOFIT_FULLM_GEMM") != nullptr;
-                if (plan->d_WAt && use_fullm) {
-                    g.A = plan->d_WAt;
-                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2_fullm(s, g, ctx->sm_count));
-                } else {
-                    if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
-                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused tail]", launch_gemm_chi2(s, g, ctx->sm_count));
-                }
-            } else if (what == OUT_WHITENED) {
-                // whitened residuals for the normal-equation probes: the same folded left matrix, store epilogue
-                g.A = plan->d_WA; g.C = d_out; g.ldc = ldo;
-                BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused tail]", launch_gemm_store(s, g, 1));
-            } else {
-                g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
-                BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));
-                BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
-                                             (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
+            if (!finished) {
+                GemmArgs g{};
+            g.gate = gate;
+                g.A = plan->d_Dkept; g.Bm = w.XiU; g.C = w.Y;
+                g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad;
+                g.lda = d->n_grid_pad; g.ldb = ldb; g.ldc = ldb;
+                BF_KERNEL(ctx, "dgemm_store_kernel[distortion]", launch_gemm_store(s, g, 1));
+                // tail on the data bins: post-matrix broadband, dilation check, residual.
+                // Y (ld = ldb) -> Z (ld = ldb); predictions are copied out row by row afterwards.
+                a.npts = d->n; a.npts_pad = d->n_pad;
+                a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
+                a.in = w.Y; a.out = w.Z; a.ldo = ldb;
+                a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
+                fill_tab(plan->tab_data, false, fa.pt);
+                fa.mode = 0; fa.in = w.Y; fa.out = w.Z; fa.ldo = ldb; fa.dsub = a.dsub; fa.dov = a.dov;
+                BF_KERNEL(ctx, "fast_post_kernel", launch_fast_post(s, fa, ctx->sm_count));
+                if (to_user)
+                    BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
+                                                 (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
             }
-            finished = true;
-        }
-        if (!finished) {
-            GemmArgs g{};
-            g.A = plan->d_Dkept; g.Bm = w.XiU; g.C = w.Y;
-            g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad;
-            g.lda = d->n_grid_pad; g.ldb = ldb; g.ldc = ldb;
-            BF_KERNEL(ctx, "dgemm_store_kernel[distortion]", launch_gemm_store(s, g, 1));
-            // tail on the data bins: post-matrix broadband, dilation check, residual.
-            // Y (ld = ldb) -> Z (ld = ldb); predictions are copied out row by row afterwards.
-            a.npts = d->n; a.npts_pad = d->n_pad;
+        } else {
+            if (what == OUT_XIU) BF_FAIL(BF_ERR_ANALYSIS, "bf_eval_undistorted_batch: the model has no distortion matrix");
+            a.npts = d->n; a.npts_pad = to_user ? d->n : d->n_pad;
             a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
-            a.in = w.Y; a.out = w.Z; a.ldo = ldb;
+            a.zc_metal = plan->d_zc_metal_data; a.zc_stride = d->n_pad;
+            a.mode = 0;
+            a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
             a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
-            fill_tab(plan->tab_data, false, fa.pt);
-            fa.mode = 0; fa.in = w.Y; fa.out = w.Z; fa.ldo = ldb; fa.dsub = a.dsub; fa.dov = a.dov;
-            BF_KERNEL(ctx, "fast_post_kernel", launch_fast_post(s, fa, ctx->sm_count));
-            if (to_user)
-                BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
-                                             (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
-        }
-    } else {
-        if (what == OUT_XIU) BF_FAIL(BF_ERR_ANALYSIS, "bf_eval_undistorted_batch: the model has no distortion matrix");
-        a.npts = d->n; a.npts_pad = to_user ? d->n : d->n_pad;
-        a.r = d->d_r; a.mu = d->d_mu; a.z = d->d_z; a.zc = plan->d_zc_data; a.gidx = d->d_index;
-        a.zc_metal = plan->d_zc_metal_data; a.zc_stride = d->n_pad;
-        a.mode = 0;
-        a.out = to_user ? d_out : w.Z; a.ldo = to_user ? ldo : ldb;
-        a.dsub = to_user ? nullptr : d->d_data; a.dov = to_user ? nullptr : d_override;
-        if (dm.kind == BF_MODEL_RSPACE && !shared_tables) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
-        else if (shared_tables && plan->fold_ok && plan->fold_data_mode && (what == OUT_CHI2 || what == OUT_WHITENED)) {
-            // fused data tail: cosmology pass into Z, broadband coefficients and the "- d" switch as extra rows,
-            // one GEMM against [W | W.basis | -W.d] (triangular block + dense tail columns)
-            fill_tab(plan->tab_data, false, fa.pt);
-            fa.mode = 0; fa.out = w.Z; fa.ldo = ldb; fa.dsub = nullptr; fa.dov = d_override;
-            fa.sub_dov_in_part1 = d_override ? 1 : 0;
-            BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
-            FoldArgs fo;
-            std::memset(&fo, 0, sizeof(fo));
-            fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
-            fo.zc_data = plan->zc_trigger;
-            fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
-            fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz; fo.ncls = plan->fold_ncls;
-            fo.minus_d_row_value = d_override ? 0 : 1;  // with an override the data were subtracted column by column
-            fo.rows = w.Z + (size_t)d->n_pad * ldb;
-            fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
-            BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
-            GemmArgs g{};
-            g.A = plan->d_WA; g.Bm = w.Z;
-            g.M = d->n_pad; g.N = B; g.K = d->n_pad + plan->fold_kext;
-            g.lda = g.K; g.ldb = ldb;
-            g.lower_triangular = 1; g.k_tri = d->n_pad;
-            if (what == OUT_CHI2) {
-                g.C = nullptr; g.ldc = 0; g.chi2 = chi2_dst; g.status = w.status;
-                if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
-                BF_KERNEL(ctx, "dgemm_chi2_kernel[fused data tail]", launch_gemm_chi2(s, g, ctx->sm_count));
-            } else {
-                g.C = d_out; g.ldc = ldo;
-                BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused data tail]", launch_gemm_store(s, g, 1));
-            }
-            finished = true;
-        }
-        else if (shared_tables) {
-            fill_tab(plan->tab_data, false, fa.pt);
-            fa.pt.npts_pad = a.npts_pad;
-            fa.mode = 0; fa.out = a.out; fa.ldo = a.ldo; fa.dsub = a.dsub; fa.dov = a.dov;
-            if (fast_eval_is_lean(fa)) {
+            if (dm.kind == BF_MODEL_RSPACE && !shared_tables) BF_KERNEL(ctx, "rspace_eval_kernel", launch_rspace_eval(s, a, ctx->sm_count));
+            else if (shared_tables && plan->fold_ok && plan->fold_data_mode && (what == OUT_CHI2 || what == OUT_WHITENED)) {
+                // fused data tail: cosmology pass into Z, broadband coefficients and the "- d" switch as extra rows,
+                // one GEMM against [W | W.basis | -W.d] (triangular block + dense tail columns)
+                fill_tab(plan->tab_data, false, fa.pt);
+                fa.mode = 0; fa.out = w.Z; fa.ldo = ldb; fa.dsub = nullptr; fa.dov = d_override;
+                fa.sub_dov_in_part1 = d_override ? 1 : 0;
                 BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
-                if (fast_eval_has_extras(fa))
-                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<extras>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 2));
-            } else
-                BF_KERNEL(ctx, "kspace_fast_eval_kernel<all>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 0));
+                FoldArgs fo;
+                std::memset(&fo, 0, sizeof(fo));
+                    fo.gate = gate;
+                fo.m = dm; fo.pT = w.pT; fo.S = w.S; fo.vfac = plan->d_vfac; fo.ldb = ldb; fo.B = B;
+                fo.zc_data = plan->zc_trigger;
+                fo.fold_case = plan->fold_case; fo.nb = plan->fold_nb; fo.kext = plan->fold_kext; fo.pmax = plan->fold_pmax;
+                fo.nrt = plan->fold_nrt; fo.nz = plan->fold_nz; fo.ncls = plan->fold_ncls;
+                fo.minus_d_row_value = d_override ? 0 : 1;  // with an override the data were subtracted column by column
+                fo.rows = w.Z + (size_t)d->n_pad * ldb;
+                fo.npts = d->n; fo.rpar0 = plan->tab_data.rpar0; fo.rperp0 = plan->tab_data.rperp0; fo.status = w.status;
+                BF_KERNEL(ctx, "fold_coef_kernel", launch_fold_coef(s, fo));
+                GemmArgs g{};
+            g.gate = gate;
+                g.A = plan->d_WA; g.Bm = w.Z;
+                g.M = d->n_pad; g.N = B; g.K = d->n_pad + plan->fold_kext;
+                g.lda = g.K; g.ldb = ldb;
+                g.lower_triangular = 1; g.k_tri = d->n_pad;
+                if (what == OUT_CHI2) {
+                    g.C = nullptr; g.ldc = 0; g.chi2 = chi2_dst; g.status = w.status;
+                    if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+                    BF_KERNEL(ctx, "dgemm_chi2_kernel[fused data tail]", launch_gemm_chi2(s, g, ctx->sm_count));
+                } else {
+                    g.C = d_out; g.ldc = ldo;
+                    BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused data tail]", launch_gemm_store(s, g, 1));
+                }
+                finished = true;
+            }
+            else if (shared_tables) {
+                fill_tab(plan->tab_data, false, fa.pt);
+                fa.pt.npts_pad = a.npts_pad;
+                fa.mode = 0; fa.out = a.out; fa.ldo = a.ldo; fa.dsub = a.dsub; fa.dov = a.dov;
+                if (fast_eval_is_lean(fa)) {
+                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<cosmology>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 1));
+                    if (fast_eval_has_extras(fa))
+                        BF_KERNEL(ctx, "kspace_fast_eval_kernel<extras>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 2));
+                } else
+                    BF_KERNEL(ctx, "kspace_fast_eval_kernel<all>[data]", launch_kspace_fast_eval(s, fa, ctx->sm_count, 0));
+            }
+            else BF_KERNEL(ctx, "kspace_eval_kernel[data]", launch_kspace_eval(s, a, ctx->sm_count));
         }
-        else BF_KERNEL(ctx, "kspace_eval_kernel[data]", launch_kspace_eval(s, a, ctx->sm_count));
-    }
-    if (what == OUT_CHI2 && !finished) {
-        GemmArgs g{};
-        g.A = d->d_W; g.Bm = w.Z; g.C = nullptr;
-        g.M = d->n_pad; g.N = B; g.K = d->n_pad;
-        g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
-        g.lower_triangular = 1;
-        g.chi2 = chi2_dst; g.status = w.status;
-        if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
-        BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
-    }
-    if (what == OUT_WHITENED && !finished) {
-        GemmArgs g{};
-        g.A = d->d_W; g.Bm = w.Z; g.C = d_out;
-        g.M = d->n_pad; g.N = B; g.K = d->n_pad;
-        g.lda = d->n_pad; g.ldb = ldb; g.ldc = ldo;
-        g.lower_triangular = 1;
-        BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+        if (what == OUT_CHI2 && !finished) {
+            GemmArgs g{};
+            g.gate = gate;
+            g.A = d->d_W; g.Bm = w.Z; g.C = nullptr;
+            g.M = d->n_pad; g.N = B; g.K = d->n_pad;
+            g.lda = d->n_pad; g.ldb = ldb; g.ldc = 0;
+            g.lower_triangular = 1;
+            g.chi2 = chi2_dst; g.status = w.status;
+            if (int rc = gemm_chi2_scratch(ctx, s, g)) return rc;
+            BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
+        }
+        if (what == OUT_WHITENED && !finished) {
+            GemmArgs g{};
+            g.gate = gate;
+            g.A = d->d_W; g.Bm = w.Z; g.C = d_out;
+            g.M = d->n_pad; g.N = B; g.K = d->n_pad;
+            g.lda = d->n_pad; g.ldb = ldb; g.ldc = ldo;
+            g.lower_triangular = 1;
+            BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+        }
+        return BF_OK;
+    };
+    if (dm.kind == BF_MODEL_KSPACE && can_share) {
+        // both chains are enqueued; gate[0], written by kspace_key_decide_kernel, lets exactly one of them run
+        if ((rc = emit(true, Gate{m->d_gate, 1}))) return rc;
+        if ((rc = emit_transform(Gate{m->d_gate, 0}))) return rc;
+        if ((rc = emit(false, Gate{m->d_gate, 0}))) return rc;
+    } else if (dm.kind == BF_MODEL_KSPACE) {
+        if ((rc = emit_transform(ungated))) return rc;
+        if ((rc = emit(false, ungated))) return rc;
+    } else {
+        if ((rc = emit(dm.kind == BF_MODEL_RSPACE && m->d_rs_tabs != nullptr, ungated))) return rc;
     }
     if (sorted) {
         BF_KERNEL(ctx, "unpermute_kernel", launch_unpermute(s, B, w.rank, w.chi2_sorted, w.status, d_out, d_status_out));
@@ -1710,6 +1743,19 @@ extern "C" int bf_transform_batch(bf_ctx *ctx, const bf_model *m, const double *
                                      (size_t)bc * sizeof(double), (size_t)6 * nr, cudaMemcpyDeviceToHost, ctx->stream));
         BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
+    return BF_OK;
+}
+
+extern "C" int bf_kspace_transform_weights(const bf_model_desc *d, int *nr, int *nk, double *weights) {
+    if (!d || !nr || !nk) BF_FAIL(BF_ERR_OPTIONS, "bf_kspace_transform_weights: null argument");
+    if (d->kind != BF_MODEL_KSPACE || d->n_pk < 8 || !d->pk_k || !d->pk_fid || !d->pk_nw || d->samples_per_decade < 1 ||
+        !(d->rmin > 0) || !(d->rmin < d->rmax) || !(d->dilmin > 0) || d->dilmin > d->dilmax)
+        BF_FAIL(BF_ERR_MODEL, "bf_kspace_transform_weights: not a valid k-space model description");
+    HankelSetup hs;
+    build_hankel_weights(d->n_pk, d->pk_k, d->pk_fid, d->pk_nw, d->rmin, d->rmax, d->dilmin, d->dilmax, d->samples_per_decade, kFineSub, hs);
+    *nr = hs.nr;
+    *nk = hs.nk;
+    if (weights) std::memcpy(weights, hs.weights.data(), hs.weights.size() * sizeof(double));
     return BF_OK;
 }
 

@@ -175,6 +175,8 @@ struct bf_model {
     // (the reference likewise re-transforms only when those parameters change,
     // baofit/BaoKSpaceCorrelationModel.cc:333-380)
     mutable double2 *d_tabs_cache = nullptr;
+    double *d_keystate = nullptr;  // [32] key of the cached tables + valid marker (kspace_key_decide_kernel)
+    int *d_gate = nullptr;         // [4] device-side decision of the current call: shared?, rebuild?
     mutable std::vector<double> cached_key;
     mutable bool cache_valid = false;
     double metal_dx = 0, metal_dy = 0;

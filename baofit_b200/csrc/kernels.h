@@ -22,7 +22,17 @@ struct SmemOptIn {
 };
 
 
+// Device-side predication: a kernel whose gate is set returns at once unless *flag == want. The decision which of the
+// two k-space chains runs (shared basis tables / per-vector transforms) and whether the basis tables must be rebuilt is
+// taken by kspace_key_decide_kernel on the GPU, so no entry point waits for the device in the middle of a call.
+struct Gate {
+    const int *flag;
+    int want;
+};
+#define BF_GATE(g) do { if ((g).flag && *(g).flag != (g).want) return; } while (0)
+
 struct EvalArgs {
+    Gate gate;
     DevModel m;
     const double *pT;  // transposed parameters [npar][ldb]
     const double *S;   // evolution factors [nz*3][ldb]
@@ -68,6 +78,7 @@ struct PointTab {
 };
 
 struct FastArgs {
+    Gate gate;
     DevModel m;
     PointTab pt;
     const double *pT, *S, *vfac;
@@ -85,6 +96,7 @@ struct FastArgs {
 // Fused model + distortion matrix + chi-square kernel (kernels_fused.cu): the model evaluation on the grid bins
 // is the producer of the right-hand operand of chi2 = || WA . [xi_u ; coefficient rows] ||^2.
 struct FusedArgs {
+    Gate gate;
     DevModel m;
     PointTab pt;                 // grid bins
     const double *pT, *S, *vfac;
@@ -103,6 +115,7 @@ void launch_fused_model_chi2(cudaStream_t s, const FusedArgs &a, int sm_count);
 
 // Coefficient rows of the fused tail + dilation-limit check of the data bins.
 struct FoldArgs {
+    Gate gate;
     DevModel m;
     const double *pT, *S, *vfac;
     int ldb, B, zc_data;         // single redshift class of the data bins
@@ -117,6 +130,7 @@ struct FoldArgs {
 };
 
 struct ProjArgs {
+    Gate gate;
     DevModel m;
     const double *pT, *S;
     int ldb, B, zc_trigger, k_per_block;
@@ -129,6 +143,7 @@ struct ProjArgs {
 // batched over blockIdx.z with the given strides. Operands are padded: M, K multiples of the
 // tile sizes with zero fill in A.
 struct GemmArgs {
+    Gate gate;
     const double *A;
     const double *Bm;
     double *C;
@@ -157,14 +172,18 @@ constexpr int kSortTableInts = 2048;
 void launch_rspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count);
 void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,
-                          const double *th_inv_diag, const double *T, double *C2);
+                          const double *th_inv_diag, const double *T, double *C2, Gate gate = Gate{nullptr, 0});
 void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count);
 // shared-transform fast path (all vectors of the batch share the non-polynomial part of D(k,mu))
 // keyout[0] = 1 if any vector's key differs from vector 0's, keyout[1..] = key values of vector 0
 void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, double *keyout);
 constexpr int kKeyMax = 12;
 void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a);  // a.G: [6][nk_pad][kPadN], columns 0..2
-void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs);
+void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs, Gate gate = Gate{nullptr, 0});
+// Device-side decision after kspace_key_check_kernel: gate[0] = 1 if all vectors share their key parameters, gate[1] = 1
+// if they do and the key differs from the one the cached basis tables were built for (state[32], kept in the model)
+struct KeyExtras { double v[7]; };  // z_eff, P(k) rescale, the five interpolated nlcorr coefficients
+void launch_kspace_key_decide(cudaStream_t s, const double *flag, double *state, int *gate, const KeyExtras &ex);
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count);
 void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part);  // part 0 all, 1 cosmology, 2 extras

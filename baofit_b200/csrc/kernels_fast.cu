@@ -119,6 +119,7 @@ __device__ __forceinline__ double metal_rows_apply(const double *__restrict__ mx
 // evolution of beta and the radiation term, which r-space models always carry.
 template <bool kLean, int kPart, bool kRS = false>
 __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_kernel(FastArgs a) {
+    BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
     __shared__ __align__(8) unsigned long long bar;
@@ -311,6 +312,7 @@ constexpr int kMetalWin = 8, kMetalStages = 8;
 
 template <int NT>
 __global__ void __launch_bounds__(256, 3) metal_add_kernel(FastArgs a) {
+    BF_GATE(a.gate);
     __shared__ __align__(128) double win[kMetalStages][kMetalWin * NT];
     __shared__ __align__(8) unsigned long long full_bar[kMetalStages], empty_bar[kMetalStages];
     __shared__ double red_min[8], red_max[8];
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__(256, 3) metal_add_kernel(FastArgs a) {
 // Distortion-matrix tail on the data bins: Z = Y (1 + dist mul) + dist add * evol - d and the
 // dilation-limit check of the data bin itself (BaoKSpaceCorrelationModel.cc:420-427, :529-535).
 __global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
+    BF_GATE(a.gate);
     const DevModel &m = a.m;
     const PointTab &pt = a.pt;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,6 +519,7 @@ __global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
 //   case 2 (velocity shift):    rP factors are (u_i + v_b)^p with v_b = dpi_b / r0, expanded
 //           binomially: row (z, m, t) = eb * sum_{p >= m} C(p,m) c_{z,p,t} v_b^(p-m)
 __global__ void __launch_bounds__(128) fold_coef_kernel(FoldArgs a) {
+    BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;

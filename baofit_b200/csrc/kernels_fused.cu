@@ -143,6 +143,7 @@ __device__ __forceinline__ double metal_patch(const double *__restrict__ base, c
 
 template <int M, int NT>
 __global__ void __launch_bounds__((FU_CW + FU_P) * 32, 1) fused_model_chi2_kernel(FusedArgs a) {
+    BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char fsm_raw[];
     const DevModel &m = a.m;
     constexpr int MF = M / (8 * FU_CW);  // row fragments per consumer warp

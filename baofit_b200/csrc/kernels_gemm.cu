@@ -78,6 +78,7 @@ __device__ __forceinline__ void compute_stage(const double *As, const double *Bs
 
 // ---- plain store epilogue: C = A.B --------------------------------------------------------
 __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
+    BF_GATE(g.gate);
     extern __shared__ __align__(16) double smem[];
     double *As = smem, *Bs = smem + STAGES * A_STAGE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
 // One CTA owns a 64-column panel and walks all row tiles, so the row reduction never leaves the
 // CTA: registers -> warp shuffles -> one shared-memory exchange between the two row-warps.
 __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
+    BF_GATE(g.gate);
     extern __shared__ __align__(16) double smem[];
     double *As = smem, *Bs = smem + STAGES * A_STAGE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
 
 // chi2[n] = sum over row tiles of the partial sums, in tile order (deterministic)
 __global__ void chi2_part_sum_kernel(const double *__restrict__ part, int part_ld, int tiles, int N,
-                                     const int *__restrict__ status, double *__restrict__ chi2) {
+                                     const int *__restrict__ status, double *__restrict__ chi2, Gate gate) {
+    BF_GATE(gate);
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double v = 0.0;
@@ -273,6 +276,7 @@ __device__ __forceinline__ void f_tma_g2s(void *smem_dst, const void *gsrc, unsi
 }  // namespace
 
 __global__ void __launch_bounds__(kFullmMaxM, 1) dgemm_chi2_fullm_kernel(GemmArgs g) {
+    BF_GATE(g.gate);
     extern __shared__ __align__(128) double fsm[];
     const int M = g.M, K = g.K;
     const int a_stage = M * FLDA, b_stage = FKC * FLDB;
@@ -447,7 +451,7 @@ void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count) {
     const int panels = (g.N + BN - 1) / BN, tiles = g.M / BM;
     if (g.chi2_part && g.N <= gemm_chi2_split_columns(g.M, sm_count) && g.part_ld >= panels * BN) {
         dgemm_chi2_kernel<<<dim3(panels, tiles, 1), 128, SMEM_BYTES, s>>>(g);
-        chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, tiles, g.N, g.status, g.chi2);
+        chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, tiles, g.N, g.status, g.chi2, g.gate);
         return;
     }
     dgemm_chi2_kernel<<<dim3(panels, 1, 1), 128, SMEM_BYTES, s>>>(g);

@@ -329,6 +329,7 @@ __device__ __forceinline__ void load_kpar(const DevModel &m, const ProjArgs &a, 
 
 // G[((comp*3 + l)*nk_pad + i)*ldb + b] = (2l+1) Int_0^1 L_l(mu) D_comp(k_i, mu; p_b) dmu
 __global__ void __launch_bounds__(128) kspace_project_kernel(ProjArgs a) {
+    BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -366,7 +367,8 @@ __global__ void __launch_bounds__(128) kspace_project_kernel(ProjArgs a) {
 __global__ void __launch_bounds__(128) kspace_thomas_kernel(int B, int ldb, int nr, int nr_pad, double h,
                                                             const double *__restrict__ th_w,
                                                             const double *__restrict__ th_inv_diag,
-                                                            const double *__restrict__ T, double *__restrict__ C2) {
+                                                            const double *__restrict__ T, double *__restrict__ C2, Gate gate) {
+    BF_GATE(gate);
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double *y = T + (size_t)blockIdx.y * nr_pad * ldb + b;
@@ -434,6 +436,7 @@ __device__ __forceinline__ double kspace_correlation(const EvalArgs &a, int comp
 //   mode 1: grid bins for the distortion matrix: undistorted xi_u with the range zeroing and the
 //           pre-matrix broadband (:460-521)
 __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
+    BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -526,8 +529,28 @@ __global__ void kspace_key_check_kernel(DevModel m, const double *__restrict__ p
     if (diff) keyout[0] = 1.0;
 }
 
+// The decision the host used to take after copying the flag back (and waiting for it): do all vectors share their key,
+// and if so, were the cached basis tables built for this key? state[0..17] = key of the cached tables, state[31] = 1 once
+// tables exist. Runs as one thread; the kernels that follow read gate[] (struct Gate).
+__global__ void kspace_key_decide_kernel(const double *__restrict__ flag, double *__restrict__ state, int *__restrict__ gate, KeyExtras ex) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const bool shared = flag[0] == 0.0;
+    bool same = state[31] == 1.0;
+    for (int k = 0; k < kKeyMax - 1; ++k) same &= state[k] == flag[1 + k];
+    for (int k = 0; k < 7; ++k) same &= state[kKeyMax - 1 + k] == ex.v[k];
+    const bool rebuild = shared && !same;
+    if (rebuild) {
+        for (int k = 0; k < kKeyMax - 1; ++k) state[k] = flag[1 + k];
+        for (int k = 0; k < 7; ++k) state[kKeyMax - 1 + k] = ex.v[k];
+        state[31] = 1.0;
+    }
+    gate[0] = shared ? 1 : 0;
+    gate[1] = rebuild ? 1 : 0;
+}
+
 // G[((comp*3 + l)*nk_pad + i)*kPadN + n] = (2l+1) Int_0^1 L_l(mu) mu^(2n) K_comp(k_i, mu) dmu
 __global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
+    BF_GATE(a.gate);
     const DevModel &m = a.m;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, comp = blockIdx.y;
     if (i >= m.nk_pad) return;
@@ -561,7 +584,8 @@ __global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
 // kernel: tabs[(comp*nr + j)*9 + l*3 + n] = { X_{l,n}(r_j), X''_{l,n}(r_j)/2 }.
 // One CTA; the 18 serial (1,4,1) sweeps run in shared memory instead of global memory.
 __global__ void __launch_bounds__(256) kspace_basis_finish_kernel(DevModel m, const double *__restrict__ T,
-                                                                  double2 *__restrict__ tabs) {
+                                                                  double2 *__restrict__ tabs, Gate gate) {
+    BF_GATE(gate);
     extern __shared__ double sh[];  // y[18][nr], c[18][nr]
     const int nr = m.nr;
     double *y = sh, *c = sh + 18 * nr;
@@ -669,6 +693,7 @@ __device__ __forceinline__ double shared_correlation(const DevModel &m, const do
 
 // Same contract as kspace_eval_kernel, basis tables in shared memory (TMA bulk copy + mbarrier).
 __global__ void __launch_bounds__(256, 2) kspace_eval_shared_kernel(EvalArgs a) {
+    BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
     __shared__ __align__(8) unsigned long long bar;
@@ -759,6 +784,7 @@ __global__ void __launch_bounds__(256, 2) kspace_eval_shared_kernel(EvalArgs a) 
 // dilation-limit check of the data bin itself (baofit/BaoKSpaceCorrelationModel.cc:420-427,
 // :529-535). Y = D_kept . xi_u comes from the DMMA GEMM.
 __global__ void __launch_bounds__(128, 4) dist_post_kernel(EvalArgs a) {
+    BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -838,9 +864,9 @@ void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count) {
 }
 
 void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,
-                          const double *th_inv_diag, const double *T, double *C2) {
+                          const double *th_inv_diag, const double *T, double *C2, Gate gate) {
     dim3 grid((B + 127) / 128, 6);
-    kspace_thomas_kernel<<<grid, 128, 0, s>>>(B, ldb, nr, nr_pad, h, th_w, th_inv_diag, T, C2);
+    kspace_thomas_kernel<<<grid, 128, 0, s>>>(B, ldb, nr, nr_pad, h, th_w, th_inv_diag, T, C2, gate);
 }
 
 void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
@@ -853,16 +879,20 @@ void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT
     kspace_key_check_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, pT, ldb, B, keyout);
 }
 
+void launch_kspace_key_decide(cudaStream_t s, const double *flag, double *state, int *gate, const KeyExtras &ex) {
+    kspace_key_decide_kernel<<<1, 32, 0, s>>>(flag, state, gate, ex);
+}
+
 void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a) {
     dim3 grid((a.m.nk_pad + 127) / 128, 2);
     kspace_basis_project_kernel<<<grid, 128, 0, s>>>(a);
 }
 
-void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs) {
+void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs, Gate gate) {
     size_t smem = (size_t)36 * m.nr * sizeof(double);
     static SmemOptIn opt;
     opt.ensure(kspace_basis_finish_kernel, smem);
-    kspace_basis_finish_kernel<<<1, 256, smem, s>>>(m, T, tabs);
+    kspace_basis_finish_kernel<<<1, 256, smem, s>>>(m, T, tabs, gate);
 }
 
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count) {

@@ -287,6 +287,13 @@ int bf_model_transform_nr(const bf_model *model);
 double bf_model_transform_r0(const bf_model *model);
 double bf_model_transform_dr(const bf_model *model);
 
+/* Host-side set-up of the k-space transform, no GPU involved: the Bessel weights that bf_model_create uploads,
+ * xi_ell^comp(r_j) = sum_i weights[((comp*3 + ell/2)*nr + j)*nk + i] * D_ell(k_i) with D_ell the multipoles of
+ * D(k, mu) on the coarse k grid (stand-in for the set-up inside cosmo::DistortedPowerCorrelation::initialize,
+ * call sites BaoKSpaceCorrelationModel.cc:347-353,371). weights == NULL only reports the sizes. Used by the
+ * reference-shaped CPU timing baseline of bench.py (oracle/cpu_baseline.c) and by parity tests. */
+int bf_kspace_transform_weights(const bf_model_desc *desc, int *nr, int *nk, double *weights);
+
 /* Toy-MC noise, replaces likely::CovarianceMatrix::sample (call site
  * CorrelationAnalyzer.cc:271): out[t][i] = d_i + scale * (L g_t)_i with g_t ~ N(0,1) drawn
  * from a counter-based generator keyed by (seed, first_toy + t), so that realisations do not

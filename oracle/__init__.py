@@ -22,6 +22,10 @@ def build(force=False):
     src.append(os.path.join(_HERE, "..", "include", "baofit_b200.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    so2 = os.path.join(_HERE, "libcpubaseline.so")
+    src2 = src + [os.path.join(_HERE, "cpu_baseline.c")]
+    if force or not os.path.exists(so2) or any(os.path.getmtime(s) > os.path.getmtime(so2) for s in src2):
+        subprocess.check_call(["make", "-C", _HERE, "libcpubaseline.so"], stdout=subprocess.DEVNULL)
     return so
 
 
@@ -193,3 +197,73 @@ def hankel_table(k, pk, ell, r):
     k = np.ascontiguousarray(k, dtype=np.float64)
     pk = np.ascontiguousarray(pk, dtype=np.float64)
     return lib().orc_hankel_table(len(k), _dp(k), _dp(pk), ell, float(r))
+
+
+# --------------------------------------------------------------------------------------------
+# reference-shaped CPU timing baseline (oracle/cpu_baseline.c); bench.py only
+# --------------------------------------------------------------------------------------------
+_CPUB = None
+
+
+def cpub_lib():
+    global _CPUB
+    if _CPUB is None:
+        so = os.path.join(_HERE, "libcpubaseline.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_model_create.restype = C.c_void_p
+        L.orc_model_create.argtypes = [C.c_void_p]
+        L.orc_model_destroy.argtypes = [C.c_void_p]
+        L.orc_data_create.restype = C.c_void_p
+        L.orc_data_create.argtypes = [C.c_void_p]
+        L.orc_data_destroy.argtypes = [C.c_void_p]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_transform_nr.argtypes = [C.c_void_p]
+        L.cpub_create.restype = C.c_void_p
+        L.cpub_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_double_p]
+        L.cpub_destroy.argtypes = [C.c_void_p]
+        L.cpub_chi2_batch.argtypes = [C.c_void_p, c_double_p, C.c_int, c_double_p, c_int_p, C.c_int, C.POINTER(C.c_longlong)]
+        _CPUB = L
+    return _CPUB
+
+
+class CpuBaseline:
+    """chi2 of parameter batches on host cores with the reference's control flow (per-bin loop, transform only when a
+    parameter D(k, mu) reads changed) and a transform of the reference's cost (weights from the product's host set-up,
+    passed in as [6][nr][nk]; None for r-space models)."""
+
+    def __init__(self, model, data, weights=None):
+        L = cpub_lib()
+        self.model, self.data = model, data  # keep the descriptors (and their arrays) alive
+        self.m = L.orc_model_create(C.addressof(model.desc))
+        self.d = L.orc_data_create(C.addressof(data.desc))
+        if not self.m or not self.d:
+            raise RuntimeError(L.orc_last_error().decode())
+        if weights is not None:
+            w = np.ascontiguousarray(weights, dtype=np.float64)
+            nr, nk = w.shape[-2], w.shape[-1]
+            self.h = L.cpub_create(self.m, self.d, nr, nk, _dp(w))
+        else:
+            self.h = L.cpub_create(self.m, self.d, 0, 0, None)
+        if not self.h:
+            raise RuntimeError(L.orc_last_error().decode())
+        self.npar = model.desc.npar
+
+    def chi2_batch(self, params, nthreads=1):
+        L = cpub_lib()
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, self.npar)
+        B = p.shape[0]
+        chi2, status, ntr = np.zeros(B), np.zeros(B, dtype=np.int32), C.c_longlong(0)
+        L.cpub_chi2_batch(self.h, _dp(p), B, _dp(chi2), status.ctypes.data_as(c_int_p), int(nthreads), C.byref(ntr))
+        return chi2, status, int(ntr.value)
+
+    def close(self):
+        L = cpub_lib()
+        if getattr(self, "h", None):
+            L.cpub_destroy(self.h)
+            L.orc_data_destroy(self.d)
+            L.orc_model_destroy(self.m)
+            self.h = None
+
+    __del__ = close

@@ -159,3 +159,45 @@ def test_two_contexts_and_a_shared_context_from_two_threads(ctx):
         for k in range(2):
             assert np.array_equal(got[k], want[k], equal_nan=True), target.__name__
     gm.close(), gd.close()
+
+
+def test_device_entry_points_do_not_wait_for_the_gpu(ctx):
+    """bf_chi2_batch_dev is asynchronous on the context's stream: which k-space chain runs (shared basis tables or
+    per-vector transforms) and whether the tables are rebuilt is decided on the device, so the call returns while
+    the GPU is still working -- for both kinds of batch -- and the results are those of the host-buffer call."""
+    import time
+    import torch
+    m, d = W.qso_kspace()
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    B = 37888
+    rng = np.random.Generator(np.random.PCG64(12))
+    shared = m.random_batch(B, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5)})
+    mixed = shared.copy()
+    mixed[::2, m.index("SigmaNL-perp")] *= 1.05  # two keys in one batch: per-vector transforms
+    dev = torch.device("cuda", 0)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    for name, p in (("shared", shared), ("mixed", mixed)):
+        want, want_st = capi.chi2_batch(ctx, gm, gd, p)  # also warms up workspaces (growing them may synchronise)
+        d_p = torch.from_numpy(p).to(dev)
+        d_chi2 = torch.empty(B, dtype=torch.float64, device=dev)
+        d_st = torch.empty(B, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            capi.chi2_batch_dev(ctx, gm, gd, d_p.data_ptr(), B, d_chi2.data_ptr(), d_st.data_ptr())
+        host_s = time.perf_counter() - t0
+        busy_after_return = not ext.query()
+        with torch.cuda.stream(ext):
+            e1.record()
+        torch.cuda.synchronize()
+        gpu_s = e0.elapsed_time(e1) * 1e-3
+        assert busy_after_return, name
+        assert host_s < 0.5 * gpu_s, (name, host_s, gpu_s)
+        got = d_chi2.cpu().numpy()
+        assert np.array_equal(d_st.cpu().numpy(), want_st)
+        ok = want_st == 0
+        assert np.array_equal(got[ok], want[ok]) and np.all(np.isnan(got[~ok]))
+    gm.close(), gd.close()
