@@ -43,12 +43,18 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
     c->device = device;
     cudaDeviceProp prop;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
         (e = cudaMallocHost((void **)&c->pinned_flag, 256)) != cudaSuccess) {
         bf_ctx_destroy(c);
         BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: ") + cudaGetErrorString(e));
     }
     c->sm_count = prop.multiProcessorCount;
+    for (auto &ev : c->copy_done)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
+            bf_ctx_destroy(c);
+            BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: ") + cudaGetErrorString(e));
+        }
     {   // keep stream-ordered allocations (toy tables) cached in the device pool between studies
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -72,6 +78,9 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     if (c->mp) cudaFree(c->mp);
     if (c->chi2_part) cudaFree(c->chi2_part);
     if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
+    for (auto &ev : c->copy_done)
+        if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BF_OK;
@@ -1677,10 +1686,34 @@ static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const doub
     double *d_ov = override_h ? (double *)(base + al(nb_params) + al(nb_out)) : nullptr;
     int *d_st = (int *)(base + al(nb_params) + al(nb_out) + al(nb_ov));
     cudaStream_t s = ctx->stream;
-    BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
-    if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
-    rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
-    if (rc) return rc;
+    // Large chi-square batches: the upload is cut into pieces of whole waves of 32-column panels; all pieces are queued on
+    // the copy stream at once and the evaluation of piece i waits only for its own event, so that (but for the first
+    // piece) the PCIe transfer hides behind the kernels. Every piece is an independent batch (columns are independent).
+    const int unit = 32 * ctx->sm_count;
+    int pieces = 1;
+    if (what == OUT_CHI2 && !override_h && B >= 4 * unit) pieces = std::min<int>(bf_ctx::kCopyPieces, B / (2 * unit));
+    if (pieces > 1) {
+        const int per = round_up((B + pieces - 1) / pieces, unit);
+        int np = 0;
+        for (int b0 = 0; b0 < B; b0 += per, ++np) {
+            const int bc = std::min(per, B - b0);
+            BF_CUDA_OK(cudaMemcpyAsync(d_params + (size_t)b0 * npar, params + (size_t)b0 * npar, (size_t)bc * npar * sizeof(double),
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+            BF_CUDA_OK(cudaEventRecord(ctx->copy_done[np], ctx->copy_stream));
+        }
+        np = 0;
+        for (int b0 = 0; b0 < B; b0 += per, ++np) {
+            const int bc = std::min(per, B - b0);
+            BF_CUDA_OK(cudaStreamWaitEvent(s, ctx->copy_done[np], 0));
+            rc = run_device(ctx, m, d, d_params + (size_t)b0 * npar, bc, what, d_out + b0, B, nullptr, d_st + b0);
+            if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+        }
+    } else {
+        BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
+        if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
+        rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
+        if (rc) return rc;
+    }
     if (what == OUT_CHI2)
         BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, s));
     else

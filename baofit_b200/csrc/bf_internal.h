@@ -143,6 +143,11 @@ struct bf_ctx {
     std::recursive_mutex api_mu;
     std::vector<bf_data *> live_data;  // data objects of this context (bf_model_destroy purges their plans)
     cudaStream_t stream = nullptr;
+    // host-buffer entry points: the parameter upload of a large batch is split into pieces on a second stream so that
+    // piece i+1 crosses the bus while piece i is being evaluated
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int kCopyPieces = 8;
+    cudaEvent_t copy_done[kCopyPieces] = {};
     long long launches = 0;
     // growable workspaces (device)
     void *ws = nullptr;

@@ -239,6 +239,25 @@ void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const do
 void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out);
 // normal equations of central probes: out[f] = (n+1)^2 matrix [y0 a]^T [y0 a] then n values y0 . s (see the kernel)
 void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out);
+// The same normal equations when some probed parameters enter the whitened residual LINEARLY with a bin-static basis
+// (the additive broadband coefficients of a model without velocity shift): their columns a_i = 2 h_i dy/dx_i are
+// synthesised from the static matrix WA (tail columns = W . basis, bf_data::Plan) instead of being evaluated, so a
+// fit costs 2 n_nl + 1 model evaluations instead of 2 n + 1. lin[j] = coefficient index of parameter j, or -1.
+struct NormalLinArgs {
+    const double *Y;            // whitened residuals of the centre and the 2 n_nl non-linear probes, [nrows][ldy]
+    int ldy, nrows, n, n_nl, nfit, npar;
+    const double *centres, *steps;  // [nfit][npar] (device)
+    const int *lin;                 // [npar] (device)
+    const double *WA;               // [n_pad][lda], basis columns start at kleft
+    int lda, kleft, nb1, ncls;
+    const double *zvals;            // [ncls] redshift of every class (single class: the class of the data bins)
+    int zc0;                        // first class index into zvals when ncls == 1
+    double zref;
+    int idx_gamma_bias;
+    double *out;                    // [nfit][(n+1)^2 + n]
+};
+void launch_normal_probes_lin(cudaStream_t s, const NormalLinArgs &a);
+
 // params[(f*G + g)*npar + j] of the central-difference probe groups (bf_gram_probes); status_fit[f] = OR of status[f*G..]
 void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params);
 void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, int *status_fit);

@@ -1037,6 +1037,88 @@ __global__ void __launch_bounds__(256) normal_probes_kernel(const double *__rest
     }
 }
 
+// normal_probes_kernel with the columns of linear parameters synthesised (struct NormalLinArgs)
+__global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a) {
+    extern __shared__ double lsm[];  // [kGramRows][R + n] as in normal_probes_kernel, then per-column metadata
+    const int f = blockIdx.x, tid = threadIdx.x, n = a.n, R = n + 1, W = R + n, G = 2 * a.n_nl + 1;
+    double *scale = lsm + kGramRows * W;          // [n]   2 h_i for linear columns
+    int *kind = reinterpret_cast<int *>(scale + n);  // [n]   >= 0: coefficient index (linear), -1 - q: q-th non-linear probe
+    __shared__ double eb[16];
+    const double *c = a.centres + (size_t)f * a.npar, *h = a.steps + (size_t)f * a.npar;
+    if (tid == 0) {
+        int col = 0, q = 0;
+        for (int j = 0; j < a.npar && col < n; ++j)
+            if (h[j] != 0.0) {
+                if (a.lin[j] >= 0) { kind[col] = a.lin[j]; scale[col] = 2.0 * h[j]; }
+                else { kind[col] = -1 - q; scale[col] = 0.0; ++q; }
+                ++col;
+            }
+        const double gb = c[a.idx_gamma_bias];
+        for (int k = 0; k < a.ncls; ++k) {
+            const double x = (1.0 + a.zvals[a.ncls == 1 ? a.zc0 : k]) / (1.0 + a.zref);
+            eb[k] = gb == 0.0 ? 1.0 : pow(x, gb);  // as prep_kernel (AbsCorrelationModel.cc:159-161)
+        }
+    }
+    const int npairs = R * (R + 1) / 2 + n;
+    double acc[6];
+    int pi[6], pj[6], np = 0;
+    for (int p = tid; p < npairs && np < 6; p += blockDim.x) {
+        int i, j;
+        if (p < R * (R + 1) / 2) {
+            i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > p) --i;
+            while ((i + 1) * (i + 2) / 2 <= p) ++i;
+            j = p - i * (i + 1) / 2;
+        } else {
+            i = R + (p - R * (R + 1) / 2);
+            j = 0;
+        }
+        pi[np] = i; pj[np] = j; acc[np] = 0.0; ++np;
+    }
+    const double *base = a.Y + (size_t)f * G;
+    for (int r0 = 0; r0 < a.nrows; r0 += kGramRows) {
+        const int nr = min(kGramRows, a.nrows - r0);
+        __syncthreads();
+        for (int e = tid; e < nr * R; e += blockDim.x) {
+            const int r = e / R, col = e - r * R;
+            const double *row = base + (size_t)(r0 + r) * a.ldy;
+            if (col == 0) lsm[r * W] = row[0];
+            else {
+                const int kd = kind[col - 1];
+                if (kd >= 0) {
+                    const double *wa = a.WA + (size_t)(r0 + r) * a.lda + a.kleft + kd;
+                    double v = 0.0;
+                    for (int k = 0; k < a.ncls; ++k) v = fma(eb[k], wa[k * a.nb1], v);
+                    lsm[r * W + col] = scale[col - 1] * v;
+                    lsm[r * W + R + col - 1] = 0.0;
+                } else {
+                    const int q = -1 - kd;
+                    const double yp = row[2 * q + 1], ym = row[2 * q + 2];
+                    lsm[r * W + col] = yp - ym;
+                    lsm[r * W + R + col - 1] = (yp - row[0]) + (ym - row[0]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int q = 0; q < np; ++q) {
+            double s = acc[q];
+            const int i = pi[q], j = pj[q];
+            for (int r = 0; r < nr; ++r) s = fma(lsm[r * W + i], lsm[r * W + j], s);
+            acc[q] = s;
+        }
+    }
+    double *o = a.out + (size_t)f * (R * R + n);
+    for (int q = 0; q < np; ++q) {
+        if (pi[q] < R) { o[pi[q] * R + pj[q]] = acc[q]; o[pj[q] * R + pi[q]] = acc[q]; }
+        else o[R * R + pi[q] - R] = acc[q];
+    }
+}
+
+void launch_normal_probes_lin(cudaStream_t s, const NormalLinArgs &a) {
+    const size_t smem = ((size_t)kGramRows * (2 * a.n + 1) + a.n) * sizeof(double) + (size_t)a.n * sizeof(int);
+    normal_probes_lin_kernel<<<a.nfit, 256, smem, s>>>(a);
+}
+
 void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out) {
     normal_probes_kernel<<<nfit, 256, (size_t)kGramRows * (2 * n + 1) * sizeof(double), s>>>(Y, ldy, nrows, n, nfit, out);
 }
