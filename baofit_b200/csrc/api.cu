@@ -972,6 +972,10 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
             std::vector<double> waf((size_t)n_pad * ktot);
             gemm_fused_tile_A(wa.data(), n_pad, ktot, ktot, waf.data());
             if ((rc = upload(p.allocs, waf.data(), waf.size(), &p.d_WAf))) return rc;
+            if (ktot % 16 == 0 && n_pad % 64 == 0) {
+                gemm_fused_tile_A3(wa.data(), n_pad, ktot, ktot, waf.data());
+                if ((rc = upload(p.allocs, waf.data(), waf.size(), &p.d_WAf3))) return rc;
+            }
         }
         p.fold_ok = true;
         p.fold_data_mode = data_mode;
@@ -1365,7 +1369,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 fill_tab(plan->tab_grid, true, fu.pt);
                 fu.pT = w.pT; fu.S = w.S; fu.vfac = plan->d_vfac; fu.tabs = m->d_tabs_cache; fu.ldb = ldb; fu.B = B;
                 fu.zc_trigger = plan->zc_trigger;
-                fu.At = plan->d_WAf; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
+                fu.At = plan->d_WAf; fu.At3 = plan->d_WAf3; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
                 fu.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
                 fu.chi2 = chi2_dst; fu.status = w.status;
                 if (fused_chi2_supported(fu)) {

@@ -103,6 +103,7 @@ struct FusedArgs {
     const double2 *tabs;         // shared-transform basis tables
     int ldb, B, zc_trigger;
     const double *At;            // WA pre-tiled as [K/4][M][4] (gemm_fused_tile_A)
+    const double *At3;           // WA in the streaming order of the TMEM-parking kernel (gemm_fused_tile_A3), or null
     int M, K, kgrid;             // rows of WA; K = kgrid + kext; rows 0..kgrid-1 of the panel come from the model
     const double *rows;          // [kext][ldb] coefficient rows (fold_coef_kernel)
     double *chi2;
@@ -110,6 +111,7 @@ struct FusedArgs {
     int debug;                   // timing experiments only (BAOFIT_FUSED_DEBUG): 2 = consumers skip the DMMAs (producer-bound time)
 };
 void gemm_fused_tile_A(const double *A, int M, int K, int lda, double *At /* [K/4][M][4] */);
+void gemm_fused_tile_A3(const double *A, int M, int K, int lda, double *At /* [K/16][2][4][M/2][4], K % 16 == 0, M even */);
 bool fused_chi2_supported(const FusedArgs &a);
 void launch_fused_model_chi2(cudaStream_t s, const FusedArgs &a, int sm_count);
 

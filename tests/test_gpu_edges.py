@@ -199,5 +199,8 @@ def test_device_entry_points_do_not_wait_for_the_gpu(ctx):
         got = d_chi2.cpu().numpy()
         assert np.array_equal(d_st.cpu().numpy(), want_st)
         ok = want_st == 0
-        assert np.array_equal(got[ok], want[ok]) and np.all(np.isnan(got[~ok]))
+        # the host-buffer call evaluates a large batch in pieces (upload overlapped with the kernels); a piece can fall
+        # below the batch size at which the chi2 GEMM splits its row tiles over CTAs, so sums may differ in the last bits
+        rel = float(np.max(np.abs(got[ok] - want[ok]) / np.abs(want[ok])))
+        assert rel < 1e-13 and np.all(np.isnan(got[~ok])), (name, int(np.sum(got[ok] != want[ok])), rel)
     gm.close(), gd.close()
