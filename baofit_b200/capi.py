@@ -19,7 +19,7 @@ EXPORTS = [
     "bf_last_error", "bf_version", "bf_ctx_create", "bf_ctx_destroy", "bf_ctx_launch_count",
     "bf_ctx_synchronize", "bf_ctx_stream", "bf_ctx_set_profiling", "bf_ctx_get_profile", "bf_model_create", "bf_model_destroy", "bf_model_npar",
     "bf_data_create", "bf_data_destroy", "bf_data_ndata", "bf_eval_batch", "bf_chi2_batch",
-    "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_eval_undistorted_batch", "bf_transform_batch",
+    "bf_eval_batch_dev", "bf_chi2_batch_dev", "bf_chi2_batch_submit", "bf_chi2_batch_wait", "bf_eval_undistorted_batch", "bf_transform_batch",
     "bf_model_transform_nr", "bf_model_transform_r0", "bf_model_transform_dr", "bf_sample_toys",
     "bf_fft_planes_batch", "bf_model_fft_plane_dims", "bf_kspace_transform_weights",
     "bf_toys_create", "bf_toys_destroy", "bf_toys_download", "bf_chi2_batch_toys", "bf_gram_batch", "bf_gram_probes", "bf_normal_probes", "bf_pinned_alloc", "bf_pinned_free",
@@ -60,6 +60,8 @@ def lib():
         L.bf_chi2_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bf_eval_batch_dev.argtypes = L.bf_eval_batch.argtypes
         L.bf_chi2_batch_dev.argtypes = L.bf_chi2_batch.argtypes
+        L.bf_chi2_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.bf_chi2_batch_wait.argtypes = [C.c_void_p, C.c_int]
         L.bf_eval_undistorted_batch.argtypes = L.bf_eval_batch.argtypes
         L.bf_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
         L.bf_model_transform_nr.argtypes = [C.c_void_p]
@@ -320,6 +322,18 @@ def chi2_batch_dev(ctx, model, data, d_params_ptr, B, d_chi2_ptr, d_status_ptr=N
     _check(lib().bf_chi2_batch_dev(ctx.h, model.h, data.h, C.c_void_p(d_params_ptr), B,
                                    C.c_void_p(d_override_ptr) if d_override_ptr else None,
                                    C.c_void_p(d_chi2_ptr), C.c_void_p(d_status_ptr) if d_status_ptr else None))
+
+
+def chi2_batch_submit(ctx, model, data, params_ptr, B, chi2_ptr, status_ptr=None):
+    """bf_chi2_batch_submit on raw host addresses (page-locked buffers); returns the ticket for chi2_batch_wait."""
+    ticket = C.c_int(-1)
+    _check(lib().bf_chi2_batch_submit(ctx.h, model.h, data.h, C.c_void_p(params_ptr), B, C.c_void_p(chi2_ptr),
+                                      C.c_void_p(status_ptr) if status_ptr else None, C.byref(ticket)))
+    return ticket.value
+
+
+def chi2_batch_wait(ctx, ticket):
+    _check(lib().bf_chi2_batch_wait(ctx.h, ticket))
 
 
 def chi2_batch_raw(ctx, model, data, params_ptr, B, chi2_ptr, status_ptr=None):

@@ -50,8 +50,9 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
         BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: ") + cudaGetErrorString(e));
     }
     c->sm_count = prop.multiProcessorCount;
-    for (auto &ev : c->copy_done)
-        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
+    for (auto &sl : c->async_slot)
+        if ((e = cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) {
             bf_ctx_destroy(c);
             BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: ") + cudaGetErrorString(e));
         }
@@ -78,8 +79,11 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     if (c->mp) cudaFree(c->mp);
     if (c->chi2_part) cudaFree(c->chi2_part);
     if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
-    for (auto &ev : c->copy_done)
-        if (ev) cudaEventDestroy(ev);
+    for (auto &sl : c->async_slot) {
+        if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.buf) cudaFree(sl.buf);
+    }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1156,6 +1160,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     // ---- k-space model: which chain runs is decided on the device (no host round trip inside a call) ----
     const Gate ungated{nullptr, 0};
     bool can_share = false;  // shared-transform fast path possible: polynomial tracer factor (no UV / HCD terms)
+    bool host_shared = false, host_current = false;  // KeyHint: see below
     ProjArgs pa;
     std::memset(&pa, 0, sizeof(pa));
     // per-vector transform chain: multipoles of D(k,mu) -> Hankel GEMM -> spline second derivatives
@@ -1196,26 +1201,44 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         // gate[0] (shared) / gate[1] (rebuild the tables); everything downstream is predicated on those two ints.
         can_share = !(dm.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT));
         if (can_share) {
-            BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
-            BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
             KeyExtras ex;
             ex.v[0] = zeff;
             ex.v[1] = pa.nl_pk_scale;
             for (int q = 0; q < 5; ++q) ex.v[2 + q] = pa.nl_tab[q];
-            BF_KERNEL(ctx, "kspace_key_decide_kernel", launch_kspace_key_decide(s, w.flag, m->d_keystate, m->d_gate, ex));
-            const Gate rebuild{m->d_gate + 1, 1};
-            pa.G = w.Gb;
-            pa.gate = rebuild;
-            BF_CUDA_OK(cudaMemsetAsync(w.Gb, 0, (size_t)6 * dm.nk_pad * kPadN * sizeof(double), s));
-            BF_KERNEL(ctx, "kspace_basis_project_kernel", launch_kspace_basis_project(s, pa));
-            GemmArgs g{};
-            g.gate = rebuild;
-            g.A = dm.hankel; g.Bm = w.Gb; g.C = w.Tb;
-            g.M = dm.nr_pad; g.N = 3; g.K = dm.nk_pad;
-            g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
-            g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
-            BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
-            BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, m->d_tabs_cache, rebuild));
+            // Host-buffer calls of modest size have compared the key parameters of their vectors on the host (KeyHint): then
+            // the per-vector chain is not enqueued at all, and when the key is also the one the basis tables on the device were
+            // last built for (host mirror of d_keystate, valid as long as every call since went through a hint) nothing is
+            // decided on the device: a fit's single-vector evaluations cost 6 launches instead of 25.
+            const KeyHint *hint = ctx->key_hint;
+            double hk[32] = {};
+            if (hint) {
+                for (int k = 0; k < hint->nkey; ++k) hk[k] = hint->vals[k];
+                for (int k = 0; k < 7; ++k) hk[kKeyMax - 1 + k] = ex.v[k];
+                host_shared = true;
+                host_current = m->h_key_valid;
+                for (int k = 0; k < 32 && host_current; ++k) host_current = hk[k] == m->h_key[k];
+            }
+            if (!host_current) {
+                BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
+                BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
+                BF_KERNEL(ctx, "kspace_key_decide_kernel", launch_kspace_key_decide(s, w.flag, m->d_keystate, m->d_gate, ex));
+                const Gate rebuild{m->d_gate + 1, 1};
+                pa.G = w.Gb;
+                pa.gate = rebuild;
+                BF_CUDA_OK(cudaMemsetAsync(w.Gb, 0, (size_t)6 * dm.nk_pad * kPadN * sizeof(double), s));
+                BF_KERNEL(ctx, "kspace_basis_project_kernel", launch_kspace_basis_project(s, pa));
+                GemmArgs g{};
+                g.gate = rebuild;
+                g.A = dm.hankel; g.Bm = w.Gb; g.C = w.Tb;
+                g.M = dm.nr_pad; g.N = 3; g.K = dm.nk_pad;
+                g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
+                g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
+                BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
+                BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, m->d_tabs_cache, rebuild));
+                // after a call whose vectors share a key the tables are those of that key; otherwise the host cannot know
+                m->h_key_valid = host_shared;
+                if (host_shared) std::memcpy(m->h_key, hk, sizeof(hk));
+            }
         }
     }
 
@@ -1547,9 +1570,11 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     };
     if (dm.kind == BF_MODEL_KSPACE && can_share) {
         // both chains are enqueued; gate[0], written by kspace_key_decide_kernel, lets exactly one of them run
-        if ((rc = emit(true, Gate{m->d_gate, 1}))) return rc;
-        if ((rc = emit_transform(Gate{m->d_gate, 0}))) return rc;
-        if ((rc = emit(false, Gate{m->d_gate, 0}))) return rc;
+        if ((rc = emit(true, host_current ? ungated : Gate{m->d_gate, 1}))) return rc;
+        if (!host_shared) {
+            if ((rc = emit_transform(Gate{m->d_gate, 0}))) return rc;
+            if ((rc = emit(false, Gate{m->d_gate, 0}))) return rc;
+        }
     } else if (dm.kind == BF_MODEL_KSPACE) {
         if ((rc = emit_transform(ungated))) return rc;
         if ((rc = emit(false, ungated))) return rc;
@@ -1669,6 +1694,30 @@ extern "C" int bf_chi2_batch_dev(bf_ctx *ctx, const bf_model *m, const bf_data *
     return run_device(ctx, m, d, d_params, B, OUT_CHI2, d_chi2, 0, d_override, d_status);
 }
 
+// kspace_key_check_kernel on the host, for host-buffer calls small enough that looking at the parameters costs less than
+// the launches it saves: true when every vector carries the same key parameters (same order and comparison as the kernel).
+static bool host_key_check(const DevModel &m, const double *params, int B, KeyHint *hint) {
+    constexpr int kHostKeyCheckMax = 4096;
+    if (m.kind != BF_MODEL_KSPACE || B > kHostKeyCheckMax) return false;
+    if (m.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT)) return false;
+    int idx[kKeyMax], n = 0;
+    idx[n++] = m.idx_nl; idx[n++] = m.idx_nl + 1;
+    if (m.flags & (BF_FLAG_BIN_SMOOTH | BF_FLAG_BIN_SMOOTH_ALT)) { idx[n++] = m.idx_bs; idx[n++] = m.idx_bs + 1; }
+    if (m.flags & BF_FLAG_SMOOTH_GAUSS) idx[n++] = m.idx_smgaus;
+    if (m.flags & BF_FLAG_SMOOTH_LORENTZ) idx[n++] = m.idx_smlor;
+    if (m.flags & BF_FLAG_FIT_NL_CORRECTION) { idx[n++] = m.idx_nlcorr; idx[n++] = m.idx_nlcorr + 1; }
+    hint->nkey = n;
+    for (int k = 0; k < n; ++k) hint->vals[k] = params[idx[k]];
+    for (int b = 1; b < B; ++b) {
+        const double *p = params + (size_t)b * m.npar;
+        for (int k = 0; k < n; ++k)
+            if (p[idx[k]] != hint->vals[k]) return false;
+    }
+    for (int k = 0; k < n; ++k)
+        if (hint->vals[k] != hint->vals[k]) return false;  // NaN never compares equal on the device either
+    return true;
+}
+
 // host-buffer entry points: stage through device memory owned by the context
 static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B, Output what,
                     double *out, int ldo, int out_rows, const double *override_h, int *status) {
@@ -1690,34 +1739,13 @@ static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const doub
     double *d_ov = override_h ? (double *)(base + al(nb_params) + al(nb_out)) : nullptr;
     int *d_st = (int *)(base + al(nb_params) + al(nb_out) + al(nb_ov));
     cudaStream_t s = ctx->stream;
-    // Large chi-square batches: the upload is cut into pieces of whole waves of 32-column panels; all pieces are queued on
-    // the copy stream at once and the evaluation of piece i waits only for its own event, so that (but for the first
-    // piece) the PCIe transfer hides behind the kernels. Every piece is an independent batch (columns are independent).
-    const int unit = 32 * ctx->sm_count;
-    int pieces = 1;
-    if (what == OUT_CHI2 && !override_h && B >= 4 * unit) pieces = std::min<int>(bf_ctx::kCopyPieces, B / (2 * unit));
-    if (pieces > 1) {
-        const int per = round_up((B + pieces - 1) / pieces, unit);
-        int np = 0;
-        for (int b0 = 0; b0 < B; b0 += per, ++np) {
-            const int bc = std::min(per, B - b0);
-            BF_CUDA_OK(cudaMemcpyAsync(d_params + (size_t)b0 * npar, params + (size_t)b0 * npar, (size_t)bc * npar * sizeof(double),
-                                       cudaMemcpyHostToDevice, ctx->copy_stream));
-            BF_CUDA_OK(cudaEventRecord(ctx->copy_done[np], ctx->copy_stream));
-        }
-        np = 0;
-        for (int b0 = 0; b0 < B; b0 += per, ++np) {
-            const int bc = std::min(per, B - b0);
-            BF_CUDA_OK(cudaStreamWaitEvent(s, ctx->copy_done[np], 0));
-            rc = run_device(ctx, m, d, d_params + (size_t)b0 * npar, bc, what, d_out + b0, B, nullptr, d_st + b0);
-            if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
-        }
-    } else {
-        BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
-        if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
-        rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
-        if (rc) return rc;
-    }
+    BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
+    if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
+    KeyHint hint;
+    ctx->key_hint = host_key_check(m->dev, params, B, &hint) ? &hint : nullptr;
+    rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
+    ctx->key_hint = nullptr;
+    if (rc) return rc;
     if (what == OUT_CHI2)
         BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, s));
     else
@@ -1745,6 +1773,54 @@ extern "C" int bf_chi2_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, c
                              const double *data_override, double *chi2, int *status) {
     if (!chi2) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch: null output");
     return run_host(ctx, m, d, params, B, OUT_CHI2, chi2, 0, 0, data_override, status);
+}
+
+// Asynchronous host-buffer chi-square: the upload of call n + 1 crosses the bus on the copy stream while call n is
+// being evaluated. Two staging slots; a ticket names the slot and its generation.
+extern "C" int bf_chi2_batch_submit(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B,
+                                    double *chi2, int *status, int *ticket) {
+    if (!chi2 || !ticket) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_submit: null output");
+    int rc = check_args(ctx, m, d, params, B);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
+    BF_CUDA_OK(cudaSetDevice(ctx->device));
+    const int slot = (int)(ctx->submit_serial & 1);
+    bf_ctx::AsyncSlot &sl = ctx->async_slot[slot];
+    if (sl.pending) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_submit: two calls are already in flight, wait for the older one first");
+    const int npar = m->dev.npar;
+    const size_t nb_params = (size_t)B * npar * sizeof(double), nb_out = (size_t)B * sizeof(double), nb_st = (size_t)B * sizeof(int);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    if ((rc = ensure(&sl.buf, &sl.bytes, al(nb_params) + al(nb_out) + al(nb_st)))) return rc;
+    double *d_params = (double *)sl.buf;
+    double *d_out = (double *)((char *)sl.buf + al(nb_params));
+    int *d_st = (int *)((char *)sl.buf + al(nb_params) + al(nb_out));
+    BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, ctx->copy_stream));
+    BF_CUDA_OK(cudaEventRecord(sl.uploaded, ctx->copy_stream));
+    BF_CUDA_OK(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0));
+    if ((rc = run_device(ctx, m, d, d_params, B, OUT_CHI2, d_out, B, nullptr, d_st))) return rc;
+    BF_CUDA_OK(cudaMemcpyAsync(chi2, d_out, nb_out, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) BF_CUDA_OK(cudaMemcpyAsync(status, d_st, nb_st, cudaMemcpyDeviceToHost, ctx->stream));
+    BF_CUDA_OK(cudaEventRecord(sl.done, ctx->stream));
+    sl.pending = true;
+    sl.serial = ctx->submit_serial;
+    *ticket = (int)(ctx->submit_serial & 0x7fffffff);
+    ctx->submit_serial++;
+    return BF_OK;
+}
+
+extern "C" int bf_chi2_batch_wait(bf_ctx *ctx, int ticket) {
+    if (!ctx) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_wait: null context");
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
+        bf_ctx::AsyncSlot &sl = ctx->async_slot[ticket & 1];
+        if (!sl.pending || (int)(sl.serial & 0x7fffffff) != ticket) BF_FAIL(BF_ERR_OPTIONS, "bf_chi2_batch_wait: unknown ticket");
+        ev = sl.done;
+    }
+    BF_CUDA_OK(cudaEventSynchronize(ev));  // outside the lock: another thread may submit meanwhile
+    std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
+    ctx->async_slot[ticket & 1].pending = false;
+    return BF_OK;
 }
 
 extern "C" int bf_eval_undistorted_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params,

@@ -136,6 +136,12 @@ struct bf_ctx_t;
 
 struct bf_data;
 
+// All vectors of a host-buffer call carry these key parameters (compared on the host, host_key_check in api.cu)
+struct KeyHint {
+    int nkey = 0;
+    double vals[16] = {};
+};
+
 struct bf_ctx {
     int device = 0;
     // Every compute entry point holds this lock for the duration of the call: two host threads may share one
@@ -143,11 +149,18 @@ struct bf_ctx {
     std::recursive_mutex api_mu;
     std::vector<bf_data *> live_data;  // data objects of this context (bf_model_destroy purges their plans)
     cudaStream_t stream = nullptr;
-    // host-buffer entry points: the parameter upload of a large batch is split into pieces on a second stream so that
-    // piece i+1 crosses the bus while piece i is being evaluated
+    // bf_chi2_batch_submit / _wait: uploads run on a second stream into one of two staging slots, so that the
+    // parameters of call n + 1 cross the bus while call n is being evaluated
     cudaStream_t copy_stream = nullptr;
-    static constexpr int kCopyPieces = 8;
-    cudaEvent_t copy_done[kCopyPieces] = {};
+    struct AsyncSlot {
+        void *buf = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t uploaded = nullptr, done = nullptr;
+        bool pending = false;
+        long long serial = 0;
+    } async_slot[2];
+    long long submit_serial = 0;
+    const KeyHint *key_hint = nullptr;  // set by the host-buffer entry point around its run_device call
     long long launches = 0;
     // growable workspaces (device)
     void *ws = nullptr;
@@ -182,6 +195,9 @@ struct bf_model {
     mutable double2 *d_tabs_cache = nullptr;
     double *d_keystate = nullptr;  // [32] key of the cached tables + valid marker (kspace_key_decide_kernel)
     int *d_gate = nullptr;         // [4] device-side decision of the current call: shared?, rebuild?
+    // host mirror of d_keystate, maintained by calls that carry a KeyHint (all calls of a model run under its context's lock)
+    mutable bool h_key_valid = false;
+    mutable double h_key[32] = {};
     mutable std::vector<double> cached_key;
     mutable bool cache_valid = false;
     double metal_dx = 0, metal_dy = 0;

@@ -263,6 +263,15 @@ int bf_chi2_batch_dev(bf_ctx *ctx, const bf_model *model, const bf_data *data,
                       const double *d_params, int B, const double *d_data_override,
                       double *d_chi2, int *d_status);
 
+/* bf_chi2_batch in two halves, for callers that evaluate one batch after another (the rounds of a scan or of a
+ * toy study, CorrelationAnalyzer.cc:169-190,337-373): submit returns once the work is queued, wait blocks until
+ * chi2[] / status[] of that ticket are complete. At most two tickets may be outstanding; the parameter upload of the
+ * newer one overlaps the evaluation of the older one. params, chi2 and status must stay valid until the wait
+ * returns and should be page-locked (bf_pinned_alloc), or the copies are not asynchronous. */
+int bf_chi2_batch_submit(bf_ctx *ctx, const bf_model *model, const bf_data *data,
+                         const double *params, int B, double *chi2, int *status, int *ticket);
+int bf_chi2_batch_wait(bf_ctx *ctx, int ticket);
+
 /* Undistorted correlation on the full grid (the vector DistortionMatrix::setCorrelation is
  * fed with, BaoKSpaceCorrelationModel.cc:460-521): xiu[g*ldp + b]. Host buffers. Only valid
  * for models with a distortion matrix. Exposed for parity tests of the model kernel alone. */

@@ -204,3 +204,37 @@ def test_device_entry_points_do_not_wait_for_the_gpu(ctx):
         rel = float(np.max(np.abs(got[ok] - want[ok]) / np.abs(want[ok])))
         assert rel < 1e-13 and np.all(np.isnan(got[~ok])), (name, int(np.sum(got[ok] != want[ok])), rel)
     gm.close(), gd.close()
+
+
+@pytest.mark.gpu
+def test_submit_wait_pipeline_matches_the_synchronous_call(ctx):
+    """bf_chi2_batch_submit / bf_chi2_batch_wait: two batches in flight, results identical to bf_chi2_batch; a third
+    submit without a wait and a stale ticket are refused."""
+    import torch
+    m, d = W.qso_kspace()
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+    rng = np.random.Generator(np.random.PCG64(21))
+    B = 5000
+    batches = [m.random_batch(B, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.7, 1.3)}) for _ in range(5)]
+    want = [capi.chi2_batch(ctx, gm, gd, p) for p in batches]
+    hp = [torch.from_numpy(p).pin_memory() for p in batches]
+    hc = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in batches]
+    hs = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in batches]
+    tickets = []
+    for i in range(5):
+        tickets.append(capi.chi2_batch_submit(ctx, gm, gd, hp[i].data_ptr(), B, hc[i].data_ptr(), hs[i].data_ptr()))
+        if len(tickets) == 2:
+            if i == 1:
+                with pytest.raises(capi.BaofitError):  # a third call in flight
+                    capi.chi2_batch_submit(ctx, gm, gd, hp[2].data_ptr(), B, hc[2].data_ptr(), hs[2].data_ptr())
+            capi.chi2_batch_wait(ctx, tickets.pop(0))
+    last = tickets.pop(0)
+    capi.chi2_batch_wait(ctx, last)
+    with pytest.raises(capi.BaofitError):
+        capi.chi2_batch_wait(ctx, last)  # already collected
+    for i in range(5):
+        chi2, st = want[i]
+        assert np.array_equal(hs[i].numpy(), st)
+        ok = st == 0
+        assert np.array_equal(hc[i].numpy()[ok], chi2[ok])
+    gm.close(), gd.close()
