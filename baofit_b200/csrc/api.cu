@@ -76,6 +76,7 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     c->prof_pending.clear();
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
+    if (c->aux) cudaFree(c->aux);
     if (c->mp) cudaFree(c->mp);
     if (c->chi2_part) cudaFree(c->chi2_part);
     if (c->pinned_flag) cudaFreeHost(c->pinned_flag);
@@ -1108,7 +1109,7 @@ static int gemm_chi2_scratch(bf_ctx *ctx, cudaStream_t s, GemmArgs &g) {
     g.part_ld = 0;
     if (g.N > gemm_chi2_split_columns(g.M, ctx->sm_count)) return BF_OK;
     const int ld = round_up(g.N, 64);
-    const size_t need = (size_t)(g.M / 64) * ld * sizeof(double);
+    const size_t need = (size_t)(g.M / 32) * ld * sizeof(double);  // row tiles of 32 when the batch is very small
     if (need > ctx->chi2_part_bytes) {
         BF_CUDA_OK(cudaStreamSynchronize(s));
         void *p = ctx->chi2_part;
@@ -1174,7 +1175,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         g.M = dm.nr_pad; g.N = B; g.K = dm.nk_pad;
         g.lda = dm.nk_pad; g.ldb = ldb; g.ldc = ldb;
         g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * ldb; g.strideC = (long long)dm.nr_pad * ldb;
-        BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6));
+        BF_KERNEL(ctx, "dgemm_store_kernel[hankel]", launch_gemm_store(s, g, 6, ctx->sm_count));
         if (what == OUT_TRANSFORM) {
             // out[((comp*3+l)*nr + j)*ldo + b]
             for (int t = 0; t < 6; ++t)
@@ -1233,7 +1234,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 g.M = dm.nr_pad; g.N = 3; g.K = dm.nk_pad;
                 g.lda = dm.nk_pad; g.ldb = kPadN; g.ldc = kPadN;
                 g.strideA = (long long)dm.nr_pad * dm.nk_pad; g.strideB = (long long)dm.nk_pad * kPadN; g.strideC = (long long)dm.nr_pad * kPadN;
-                BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6));
+                BF_KERNEL(ctx, "dgemm_store_kernel[hankel-basis]", launch_gemm_store(s, g, 6, ctx->sm_count));
                 BF_KERNEL(ctx, "kspace_basis_finish_kernel", launch_kspace_basis_finish(s, dm, w.Tb, m->d_tabs_cache, rebuild));
                 // after a call whose vectors share a key the tables are those of that key; otherwise the host cannot know
                 m->h_key_valid = host_shared;
@@ -1333,7 +1334,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
             } else {
                 g.C = d_out; g.ldc = ldo;
-                BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+                BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1, ctx->sm_count));
             }
         }
         if (d_status_out) BF_CUDA_OK(cudaMemcpyAsync(d_status_out, w.status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
@@ -1461,10 +1462,10 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 } else if (what == OUT_WHITENED) {
                     // whitened residuals for the normal-equation probes: the same folded left matrix, store epilogue
                     g.A = plan->d_WA; g.C = d_out; g.ldc = ldo;
-                    BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused tail]", launch_gemm_store(s, g, 1));
+                    BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused tail]", launch_gemm_store(s, g, 1, ctx->sm_count));
                 } else {
                     g.A = plan->d_Aext; g.C = w.Z; g.ldc = ldb;
-                    BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1));
+                    BF_KERNEL(ctx, "dgemm_store_kernel[distortion+broadband]", launch_gemm_store(s, g, 1, ctx->sm_count));
                     BF_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(double), w.Z, (size_t)ldb * sizeof(double),
                                                  (size_t)B * sizeof(double), d->n, cudaMemcpyDeviceToDevice, s));
                 }
@@ -1476,7 +1477,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 g.A = plan->d_Dkept; g.Bm = w.XiU; g.C = w.Y;
                 g.M = d->n_pad; g.N = B; g.K = d->n_grid_pad;
                 g.lda = d->n_grid_pad; g.ldb = ldb; g.ldc = ldb;
-                BF_KERNEL(ctx, "dgemm_store_kernel[distortion]", launch_gemm_store(s, g, 1));
+                BF_KERNEL(ctx, "dgemm_store_kernel[distortion]", launch_gemm_store(s, g, 1, ctx->sm_count));
                 // tail on the data bins: post-matrix broadband, dilation check, residual.
                 // Y (ld = ldb) -> Z (ld = ldb); predictions are copied out row by row afterwards.
                 a.npts = d->n; a.npts_pad = d->n_pad;
@@ -1529,7 +1530,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                     BF_KERNEL(ctx, "dgemm_chi2_kernel[fused data tail]", launch_gemm_chi2(s, g, ctx->sm_count));
                 } else {
                     g.C = d_out; g.ldc = ldo;
-                    BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused data tail]", launch_gemm_store(s, g, 1));
+                    BF_KERNEL(ctx, "dgemm_store_kernel[whiten, fused data tail]", launch_gemm_store(s, g, 1, ctx->sm_count));
                 }
                 finished = true;
             }
@@ -1564,7 +1565,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
             g.M = d->n_pad; g.N = B; g.K = d->n_pad;
             g.lda = d->n_pad; g.ldb = ldb; g.ldc = ldo;
             g.lower_triangular = 1;
-            BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+            BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1, ctx->sm_count));
         }
         return BF_OK;
     };
@@ -1649,7 +1650,7 @@ static int run_device_multipole(bf_ctx *ctx, const bf_model *m, const bf_data *d
                 BF_KERNEL(ctx, "dgemm_chi2_kernel", launch_gemm_chi2(s, g, ctx->sm_count));
             } else {
                 g.C = d_out + b0; g.ldc = ldo;
-                BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1));
+                BF_KERNEL(ctx, "dgemm_store_kernel[whiten]", launch_gemm_store(s, g, 1, ctx->sm_count));
             }
         }
     }
@@ -1696,7 +1697,7 @@ extern "C" int bf_chi2_batch_dev(bf_ctx *ctx, const bf_model *m, const bf_data *
 
 // kspace_key_check_kernel on the host, for host-buffer calls small enough that looking at the parameters costs less than
 // the launches it saves: true when every vector carries the same key parameters (same order and comparison as the kernel).
-static bool host_key_check(const DevModel &m, const double *params, int B, KeyHint *hint) {
+static bool host_key_check(const DevModel &m, const double *params, int B, KeyHint *hint, const double *steps) {
     constexpr int kHostKeyCheckMax = 4096;
     if (m.kind != BF_MODEL_KSPACE || B > kHostKeyCheckMax) return false;
     if (m.flags & (BF_FLAG_UVFLUCTUATION | BF_FLAG_HCD_MODEL | BF_FLAG_HCD_MODEL_ALT)) return false;
@@ -1715,8 +1716,22 @@ static bool host_key_check(const DevModel &m, const double *params, int B, KeyHi
     }
     for (int k = 0; k < n; ++k)
         if (hint->vals[k] != hint->vals[k]) return false;  // NaN never compares equal on the device either
+    if (steps)  // probe groups expanded on the device from (centre, steps): no key parameter may be probed
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < n; ++k)
+                if (steps[(size_t)b * m.npar + idx[k]] != 0.0) return false;
     return true;
 }
+
+// RAII: the hint is visible to run_chunk for the duration of one run_device call
+struct KeyHintScope {
+    bf_ctx *ctx;
+    KeyHint hint;
+    KeyHintScope(bf_ctx *c, const DevModel &m, const double *params, int B, const double *steps = nullptr) : ctx(c) {
+        ctx->key_hint = host_key_check(m, params, B, &hint, steps) ? &hint : nullptr;
+    }
+    ~KeyHintScope() { ctx->key_hint = nullptr; }
+};
 
 // host-buffer entry points: stage through device memory owned by the context
 static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const double *params, int B, Output what,
@@ -1741,10 +1756,10 @@ static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const doub
     cudaStream_t s = ctx->stream;
     BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
     if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
-    KeyHint hint;
-    ctx->key_hint = host_key_check(m->dev, params, B, &hint) ? &hint : nullptr;
-    rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
-    ctx->key_hint = nullptr;
+    {
+        KeyHintScope hs(ctx, m->dev, params, B);
+        rc = run_device(ctx, m, d, d_params, B, what, d_out, B, d_ov, d_st);
+    }
     if (rc) return rc;
     if (what == OUT_CHI2)
         BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, s));
@@ -1797,7 +1812,11 @@ extern "C" int bf_chi2_batch_submit(bf_ctx *ctx, const bf_model *m, const bf_dat
     BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, ctx->copy_stream));
     BF_CUDA_OK(cudaEventRecord(sl.uploaded, ctx->copy_stream));
     BF_CUDA_OK(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0));
-    if ((rc = run_device(ctx, m, d, d_params, B, OUT_CHI2, d_out, B, nullptr, d_st))) return rc;
+    {
+        KeyHintScope hs(ctx, m->dev, params, B);
+        rc = run_device(ctx, m, d, d_params, B, OUT_CHI2, d_out, B, nullptr, d_st);
+    }
+    if (rc) return rc;
     BF_CUDA_OK(cudaMemcpyAsync(chi2, d_out, nb_out, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) BF_CUDA_OK(cudaMemcpyAsync(status, d_st, nb_st, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA_OK(cudaEventRecord(sl.done, ctx->stream));
@@ -1923,9 +1942,11 @@ extern "C" int bf_sample_toys(bf_ctx *ctx, const bf_data *d, const double *truth
     int rc = ensure(&ctx->io, &ctx->io_bytes, al(nb_truth) + al(nb_out));
     if (rc) return rc;
     double *d_truth = (double *)ctx->io, *d_out = (double *)((char *)ctx->io + al(nb_truth));
+    if ((rc = ensure(&ctx->ws, &ctx->ws_bytes, toy_noise_work_doubles(d->n_pad, ntoy) * sizeof(double)))) return rc;
     BF_CUDA_OK(cudaMemcpyAsync(d_truth, truth, nb_truth, cudaMemcpyHostToDevice, ctx->stream));
-    BF_KERNEL(ctx, "toy_noise_kernel",
-              launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, d_out));
+    BF_KERNEL(ctx, "toy_noise[deviates + dgemm_store_kernel + transpose]",
+              launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, d_out, (double *)ctx->ws));
+    ctx->launches += 3 * ((ntoy + kToyPassCols - 1) / kToyPassCols) - 1;
     BF_CUDA_OK(cudaMemcpyAsync(out, d_out, nb_out, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return BF_OK;
@@ -1940,6 +1961,7 @@ extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth
     if (!d->d_L) BF_FAIL(BF_ERR_ANALYSIS, "bf_toys_create: needs a covariance (not an inverse covariance)");
     std::lock_guard<std::recursive_mutex> lock(ctx->api_mu);
     BF_CUDA_OK(cudaSetDevice(ctx->device));
+    if (int rc = ensure(&ctx->ws, &ctx->ws_bytes, toy_noise_work_doubles(d->n_pad, ntoy) * sizeof(double))) return rc;
     bf_toys *t = new bf_toys();
     t->ctx = ctx; t->ntoy = ntoy; t->n = d->n;
     double *d_truth = nullptr;
@@ -1949,8 +1971,9 @@ extern "C" int bf_toys_create(bf_ctx *ctx, const bf_data *d, const double *truth
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_truth, (size_t)d->n * sizeof(double), ctx->stream);
     if (e != cudaSuccess) { if (t->d_table) cudaFreeAsync(t->d_table, ctx->stream); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
     cudaMemcpyAsync(d_truth, truth, (size_t)d->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-    BF_KERNEL(ctx, "toy_noise_kernel",
-              launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, t->d_table));
+    BF_KERNEL(ctx, "toy_noise[deviates + dgemm_store_kernel + transpose]",
+              launch_toy_noise(ctx->stream, d->d_L, d->n, d->n_pad, d_truth, seed, first_toy, ntoy, scale, t->d_table, (double *)ctx->ws));
+    ctx->launches += 3 * ((ntoy + kToyPassCols - 1) / kToyPassCols) - 1;
     cudaFreeAsync(d_truth, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFreeAsync(t->d_table, ctx->stream); delete t; BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_toys_create: ") + cudaGetErrorString(e)); }
@@ -2006,7 +2029,11 @@ extern "C" int bf_chi2_batch_toys(bf_ctx *ctx, const bf_model *m, const bf_data 
         BF_CUDA_OK(cudaMemcpyAsync(d_params, params + (size_t)b0 * npar, (size_t)bc * npar * sizeof(double), cudaMemcpyHostToDevice, s));
         BF_CUDA_OK(cudaMemcpyAsync(d_idx, toy_index + b0, (size_t)bc * sizeof(int), cudaMemcpyHostToDevice, s));
         BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
-        if ((rc = run_device(ctx, m, d, d_params, bc, OUT_CHI2, d_chi2, 0, d_ov, d_st))) return rc;
+        {
+            KeyHintScope hs(ctx, m->dev, params + (size_t)b0 * npar, bc);
+            rc = run_device(ctx, m, d, d_params, bc, OUT_CHI2, d_chi2, 0, d_ov, d_st);
+        }
+        if (rc) return rc;
         BF_CUDA_OK(cudaMemcpyAsync(chi2 + b0, d_chi2, (size_t)bc * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (status) BF_CUDA_OK(cudaMemcpyAsync(status + b0, d_st, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, s));
         BF_CUDA_OK(cudaStreamSynchronize(s));
@@ -2057,7 +2084,11 @@ extern "C" int bf_gram_batch(bf_ctx *ctx, const bf_model *m, const bf_data *d, c
             BF_CUDA_OK(cudaMemcpyAsync(d_idx, colidx.data(), (size_t)bc * sizeof(int), cudaMemcpyHostToDevice, s));
             BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
         }
-        if ((rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st))) return rc;
+        {
+            KeyHintScope hs(ctx, m->dev, params + (size_t)f0 * G * npar, bc);
+            rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st);
+        }
+        if (rc) return rc;
         BF_KERNEL(ctx, "gram_kernel", launch_gram(s, d_y, ldy, n, G, nf, d_gram));
         BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * G * G, d_gram, (size_t)nf * G * G * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (status) BF_CUDA_OK(cudaMemcpyAsync(status + (size_t)f0 * G, d_st, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -2117,31 +2148,76 @@ static int gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const d
     size_t nb_cs = al((size_t)fits_per_pass * npar * sizeof(double)), nb_params = al((size_t)colcap * npar * sizeof(double)),
            nb_idx = al((size_t)colcap * sizeof(int)), nb_st = al((size_t)colcap * sizeof(int)), nb_sf = al((size_t)fits_per_pass * sizeof(int)),
            nb_gram = al((size_t)fits_per_pass * per_fit * sizeof(double)), nb_ov = toys ? al((size_t)colcap * n * sizeof(double)) : 0,
-           nb_y = al((size_t)d->n_pad * ldy * sizeof(double));
-    if ((rc = ensure(&ctx->io, &ctx->io_bytes, 2 * nb_cs + nb_params + nb_idx + nb_st + nb_sf + nb_gram + nb_ov + nb_y))) return rc;
+           nb_y = al((size_t)d->n_pad * ldy * sizeof(double)), nb_part = normal ? al(normal_probes_part_doubles(nprobe, fits_per_pass) * sizeof(double)) : 0;
+    if ((rc = ensure(&ctx->io, &ctx->io_bytes, 2 * nb_cs + nb_params + nb_idx + nb_st + nb_sf + nb_gram + nb_ov + nb_y + nb_part))) return rc;
     char *p = (char *)ctx->io;
     auto take = [&](size_t bytes) { char *q = p; p += bytes; return q; };
     double *d_c = (double *)take(nb_cs), *d_h = (double *)take(nb_cs), *d_params = (double *)take(nb_params);
     int *d_idx = (int *)take(nb_idx), *d_st = (int *)take(nb_st), *d_sf = (int *)take(nb_sf);
     double *d_gram = (double *)take(nb_gram), *d_ov = toys ? (double *)take(nb_ov) : nullptr, *d_y = (double *)take(nb_y);
+    double *d_part = normal ? (double *)take(nb_part) : nullptr;
+    // Probed parameters that enter the whitened residual linearly with a bin-static basis -- the additive broadband
+    // coefficients of a model without velocity shift, the structure the fused data tail is built on -- need no
+    // evaluations: their difference columns are synthesised from W . basis (normal_probes_lin_kernel), exactly.
+    // BOSSDR11LyaF_k.ini floats 2 non-linear and 9 such parameters per grid fit: 5 evaluations per fit instead of 23.
+    std::vector<int> lin(npar, -1);
+    int n_nl = nprobe;
+    const bf_data::Plan *plan = nullptr;
+    const bool no_lin = std::getenv("BAOFIT_NO_LINEAR_PROBES") != nullptr;  // A/B tests
+    if (normal && !no_lin && d->binning_type != BF_BINNING_MULTIPOLE && m->dev.bb[BF_BB_DIST_ADD].enabled) {
+        if ((rc = get_plan(m, d, &plan))) return rc;
+        if (plan->fold_ok && plan->fold_data_mode && plan->fold_case == 1 && plan->fold_ncls <= 16) {
+            const int nb1 = plan->fold_nb / plan->fold_ncls, base = m->dev.bb[BF_BB_DIST_ADD].idx_base;
+            for (int k = 0; k < nb1; ++k) lin[base + k] = k;
+            for (int f = 0; f < nfit; ++f) {
+                int cnt = 0;
+                for (int j = 0; j < npar; ++j) cnt += steps[(size_t)f * npar + j] != 0.0 && lin[j] < 0;
+                if (f == 0) n_nl = cnt;
+                else if (cnt != n_nl) { n_nl = nprobe; break; }  // fits probe different numbers of non-linear parameters
+            }
+        }
+    }
+    const bool use_lin = n_nl < nprobe;
+    const int Ge = use_lin ? 2 * n_nl + 1 : G;  // evaluated columns per fit
+    int *d_lin = nullptr;
+    if (use_lin) {
+        if ((rc = ensure(&ctx->aux, &ctx->aux_bytes, al((size_t)npar * sizeof(int))))) return rc;
+        d_lin = (int *)ctx->aux;
+        // (pageable source: the call returns once the bytes are in the driver's staging buffer)
+        BF_CUDA_OK(cudaMemcpyAsync(d_lin, lin.data(), (size_t)npar * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
     std::vector<int> colidx;
     for (int f0 = 0; f0 < nfit; f0 += fits_per_pass) {
-        const int nf = std::min(fits_per_pass, nfit - f0), bc = nf * G;
+        const int nf = std::min(fits_per_pass, nfit - f0), bc = nf * Ge;
         BF_CUDA_OK(cudaMemcpyAsync(d_c, centres + (size_t)f0 * npar, (size_t)nf * npar * sizeof(double), cudaMemcpyHostToDevice, s));
         BF_CUDA_OK(cudaMemcpyAsync(d_h, steps + (size_t)f0 * npar, (size_t)nf * npar * sizeof(double), cudaMemcpyHostToDevice, s));
-        BF_KERNEL(ctx, "expand_probes_kernel", launch_expand_probes(s, d_c, d_h, nf, npar, nprobe, d_params));
+        BF_KERNEL(ctx, "expand_probes_kernel", launch_expand_probes(s, d_c, d_h, nf, npar, use_lin ? n_nl : nprobe, d_params, d_lin));
         if (toys) {
             colidx.resize(bc);
-            for (int c = 0; c < bc; ++c) colidx[c] = toy_index[f0 + c / G];
+            for (int c = 0; c < bc; ++c) colidx[c] = toy_index[f0 + c / Ge];
             BF_CUDA_OK(cudaMemcpyAsync(d_idx, colidx.data(), (size_t)bc * sizeof(int), cudaMemcpyHostToDevice, s));
             BF_KERNEL(ctx, "gather_rows_kernel", launch_gather_rows(s, toys->d_table, d_idx, bc, n, d_ov));
         }
-        if ((rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st))) return rc;
-        if (normal) BF_KERNEL(ctx, "normal_probes_kernel", launch_normal_probes(s, d_y, ldy, n, nprobe, nf, d_gram));
+        {
+            KeyHintScope hs(ctx, m->dev, centres + (size_t)f0 * npar, nf, steps + (size_t)f0 * npar);
+            rc = run_device(ctx, m, d, d_params, bc, OUT_WHITENED, d_y, ldy, d_ov, d_st);
+        }
+        if (rc) return rc;
+        if (use_lin) {
+            NormalLinArgs na;
+            std::memset(&na, 0, sizeof(na));
+            na.Y = d_y; na.ldy = ldy; na.nrows = n; na.n = nprobe; na.n_nl = n_nl; na.nfit = nf; na.npar = npar;
+            na.centres = d_c; na.steps = d_h; na.lin = d_lin;
+            na.WA = plan->d_WA; na.lda = d->n_pad + plan->fold_kext; na.kleft = d->n_pad;
+            na.nb1 = plan->fold_nb / plan->fold_ncls; na.ncls = plan->fold_ncls;
+            na.zvals = plan->d_zvals; na.zc0 = plan->zc_trigger; na.zref = m->dev.zref; na.idx_gamma_bias = m->dev.idx_gamma_bias;
+            na.out = d_gram; na.part = d_part;
+            BF_KERNEL(ctx, "normal_probes_lin_kernel", launch_normal_probes_lin(s, na));
+        } else if (normal) BF_KERNEL(ctx, "normal_probes_kernel", launch_normal_probes(s, d_y, ldy, n, nprobe, nf, d_gram, d_part));
         else BF_KERNEL(ctx, "gram_kernel", launch_gram(s, d_y, ldy, n, G, nf, d_gram));
         BF_CUDA_OK(cudaMemcpyAsync(gram + (size_t)f0 * per_fit, d_gram, (size_t)nf * per_fit * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (status) {
-            BF_KERNEL(ctx, "reduce_status_kernel", launch_reduce_status(s, d_st, nf, G, d_sf));
+            BF_KERNEL(ctx, "reduce_status_kernel", launch_reduce_status(s, d_st, nf, Ge, d_sf));
             BF_CUDA_OK(cudaMemcpyAsync(status + f0, d_sf, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, s));
         }
         BF_CUDA_OK(cudaStreamSynchronize(s));

@@ -166,6 +166,8 @@ struct bf_ctx {
     void *ws = nullptr;
     size_t ws_bytes = 0;
     void *io = nullptr;  // staging for host-buffer entry points
+    void *aux = nullptr;  // small side buffers of the probe entry points (linear-parameter map, masked steps)
+    size_t aux_bytes = 0;
     size_t io_bytes = 0;
     void *mp = nullptr;  // multipole-binned data: predictions at the expanded points + residual panel
     size_t mp_bytes = 0;

@@ -240,7 +240,9 @@ void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const do
 // per fit f: Gram matrix of [y0, y1-y0, ..., y_{G-1}-y0] over the columns f*G .. f*G+G-1 of Y (ld = ldy)
 void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out);
 // normal equations of central probes: out[f] = (n+1)^2 matrix [y0 a]^T [y0 a] then n values y0 . s (see the kernel)
-void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out);
+// part: normal_probes_part_doubles(n, nfit) doubles of scratch (partial sums of the row slices)
+size_t normal_probes_part_doubles(int n, int nfit);
+void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out, double *part);
 // The same normal equations when some probed parameters enter the whitened residual LINEARLY with a bin-static basis
 // (the additive broadband coefficients of a model without velocity shift): their columns a_i = 2 h_i dy/dx_i are
 // synthesised from the static matrix WA (tail columns = W . basis, bf_data::Plan) instead of being evaluated, so a
@@ -257,11 +259,13 @@ struct NormalLinArgs {
     double zref;
     int idx_gamma_bias;
     double *out;                    // [nfit][(n+1)^2 + n]
+    double *part;                   // scratch, normal_probes_part_doubles(n, nfit)
 };
 void launch_normal_probes_lin(cudaStream_t s, const NormalLinArgs &a);
 
 // params[(f*G + g)*npar + j] of the central-difference probe groups (bf_gram_probes); status_fit[f] = OR of status[f*G..]
-void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params);
+void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params,
+                          const int *skip /* null, or [npar]: parameters with skip[j] >= 0 are not probed */);
 void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, int *status_fit);
 // override panel of the toy path: out[b][i] = table[index[b]][i]
 void launch_gather_rows(cudaStream_t s, const double *table, const int *index, int B, int n, double *out);
@@ -273,13 +277,16 @@ constexpr int kFullmKC = 8, kFullmLdA = kFullmKC + 4, kFullmBN = 32, kFullmMaxM 
 void gemm_fullm_tile_A(const double *A, int M, int K, int lda, double *At /* [K/8][M][12] */);
 void launch_gemm_chi2_fullm(cudaStream_t s, const GemmArgs &g /* g.A = At */, int sm_count);
 
-void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch);
+void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch, int sm_count = 0);  // sm_count > 0: small batches may take 32 x 32 tiles
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count = 0);
 // columns up to which launch_gemm_chi2 splits the row tiles over CTAs (scratch sizing)
 int gemm_chi2_split_columns(int M, int sm_count);
 
-// toy noise: out[t][i] = truth_i + scale * sum_j L[i][j] g_{t,j}
+// toy noise: out[t][i] = truth_i + scale * sum_j L[i][j] g_{t,j} (deviate panel, lower-triangular DMMA GEMM, transpose);
+// work: toy_noise_work_doubles(n_pad, ntoy) doubles of scratch
+constexpr int kToyPassCols = 4096;  // toys per pass
+size_t toy_noise_work_doubles(int n_pad, int ntoy);
 void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth,
-                      unsigned long long seed, long long first_toy, int ntoy, double scale, double *out);
+                      unsigned long long seed, long long first_toy, int ntoy, double scale, double *out, double *work);
 
 }  // namespace bf

@@ -21,11 +21,16 @@ namespace bf {
 namespace {
 constexpr int BM = kGemmBM, BN = kGemmBN, BK = kGemmBK;
 constexpr int STAGES = 3;
-constexpr int LDA_S = BK + 4;  // 20 doubles
-constexpr int LDB_S = BN + 4;  // 68 doubles
-constexpr int A_STAGE = BM * LDA_S;
-constexpr int B_STAGE = BK * LDB_S;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+constexpr int LDA_S = BK + 4;  // 20 doubles: conflict-free A fragments
+// Tile geometry: TB x TB output tile per CTA of 4 warps (2 x 2, each TB/2 x TB/2 = (TB/16)^2 DMMA fragments). TB = 64 is the
+// throughput shape; TB = 32 is used when a batch has so few columns that 64 x 64 tiles leave most SMs without a CTA: a
+// tile's K loop is a serial chain (64 DMMAs per warp and k-tile at TB = 64, 16 at TB = 32), and the lock-step rounds of a
+// scan spend their time in exactly these chains. The order of the sums over k does not depend on TB.
+template <int TB> struct Tile {
+    static constexpr int LDB = TB + 4, A_STAGE = TB * LDA_S, B_STAGE = BK * LDB, FR = TB / 16;
+    static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+};
+constexpr int SMEM_BYTES = Tile<BM>::SMEM;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -42,62 +47,67 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// loads one (BM x BK) tile of A and one (BK x BN) tile of B into a pipeline stage
+// loads one (TB x BK) tile of A and one (BK x TB) tile of B into a pipeline stage
+template <int TB>
 __device__ __forceinline__ void load_stage(double *As, double *Bs, const double *__restrict__ A,
                                            const double *__restrict__ Bm, int lda, int ldb, int m0, int n0, int k0,
                                            int tid) {
 #pragma unroll
-    for (int c = tid; c < BM * (BK / 2); c += 128) {
+    for (int c = tid; c < TB * (BK / 2); c += 128) {
         int row = c / (BK / 2), ch = c % (BK / 2);
         cp_async16(As + row * LDA_S + ch * 2, A + (size_t)(m0 + row) * lda + k0 + ch * 2);
     }
 #pragma unroll
-    for (int c = tid; c < BK * (BN / 2); c += 128) {
-        int row = c / (BN / 2), ch = c % (BN / 2);
-        cp_async16(Bs + row * LDB_S + ch * 2, Bm + (size_t)(k0 + row) * ldb + n0 + ch * 2);
+    for (int c = tid; c < BK * (TB / 2); c += 128) {
+        int row = c / (TB / 2), ch = c % (TB / 2);
+        cp_async16(Bs + row * Tile<TB>::LDB + ch * 2, Bm + (size_t)(k0 + row) * ldb + n0 + ch * 2);
     }
 }
 
-__device__ __forceinline__ void compute_stage(const double *As, const double *Bs, double (&acc)[4][4][2], int wm,
+template <int TB>
+__device__ __forceinline__ void compute_stage(const double *As, const double *Bs, double (&acc)[TB / 16][TB / 16][2], int wm,
                                               int wn, int lane) {
+    constexpr int FR = TB / 16, LDB = Tile<TB>::LDB;
     const int l4 = lane & 3, l8 = lane >> 2;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-        double a[4], b[4];
+        double a[FR], b[FR];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + l8) * LDA_S + kk + l4];
+        for (int mi = 0; mi < FR; ++mi) a[mi] = As[(wm * (TB / 2) + mi * 8 + l8) * LDA_S + kk + l4];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(kk + l4) * LDB_S + wn * 32 + ni * 8 + l8];
+        for (int ni = 0; ni < FR; ++ni) b[ni] = Bs[(kk + l4) * LDB + wn * (TB / 2) + ni * 8 + l8];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < FR; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = 0; ni < FR; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 }
 }  // namespace
 
 // ---- plain store epilogue: C = A.B --------------------------------------------------------
+template <int TB>
 __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
     BF_GATE(g.gate);
     extern __shared__ __align__(16) double smem[];
+    constexpr int FR = TB / 16, A_STAGE = Tile<TB>::A_STAGE, B_STAGE = Tile<TB>::B_STAGE;
     double *As = smem, *Bs = smem + STAGES * A_STAGE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int n0 = blockIdx.x * TB, m0 = blockIdx.y * TB;
     const double *A = g.A + (size_t)blockIdx.z * g.strideA;
     const double *Bm = g.Bm + (size_t)blockIdx.z * g.strideB;
     double *C = g.C + (size_t)blockIdx.z * g.strideC;
     // k tiles of this row tile: the triangular part up to the diagonal, then the dense tail columns
     const int ktri = g.lower_triangular ? (g.k_tri > 0 ? g.k_tri : g.K) : g.K;
-    const int Ttri = min(ktri, g.lower_triangular ? m0 + BM : ktri) / BK, T = Ttri + (g.K - ktri) / BK;
+    const int Ttri = min(ktri, g.lower_triangular ? m0 + TB : ktri) / BK, T = Ttri + (g.K - ktri) / BK;
     auto kofs = [&](int t) { return t < Ttri ? t * BK : ktri + (t - Ttri) * BK; };
-    double acc[4][4][2];
+    double acc[FR][FR][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < FR; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < FR; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < T) load_stage(As + s * A_STAGE, Bs + s * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0, kofs(s), tid);
+        if (s < T) load_stage<TB>(As + s * A_STAGE, Bs + s * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0, kofs(s), tid);
         cp_async_commit();
     }
     for (int t = 0; t < T; ++t) {
@@ -105,58 +115,60 @@ __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
         __syncthreads();
         int tn = t + STAGES - 1;
         if (tn < T)
-            load_stage(As + (tn % STAGES) * A_STAGE, Bs + (tn % STAGES) * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0,
-                       kofs(tn), tid);
+            load_stage<TB>(As + (tn % STAGES) * A_STAGE, Bs + (tn % STAGES) * B_STAGE, A, Bm, g.lda, g.ldb, m0, n0,
+                           kofs(tn), tid);
         cp_async_commit();
-        compute_stage(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
+        compute_stage<TB>(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
     }
     cp_async_wait<0>();
     const int l4 = lane & 3, l8 = lane >> 2;
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        int row = m0 + wm * 32 + mi * 8 + l8;
+    for (int mi = 0; mi < FR; ++mi) {
+        int row = m0 + wm * (TB / 2) + mi * 8 + l8;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            int col = n0 + wn * 32 + ni * 8 + 2 * l4;
+        for (int ni = 0; ni < FR; ++ni) {
+            int col = n0 + wn * (TB / 2) + ni * 8 + 2 * l4;
             *reinterpret_cast<double2 *>(C + (size_t)row * g.ldc + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
     }
 }
 
 // ---- chi-square epilogue: chi2[n] = sum_m (A.B)[m][n]^2 ----------------------------------------
-// One CTA owns a 64-column panel and walks all row tiles, so the row reduction never leaves the
+// One CTA owns a TB-column panel and walks all row tiles, so the row reduction never leaves the
 // CTA: registers -> warp shuffles -> one shared-memory exchange between the two row-warps.
+template <int TB>
 __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
     BF_GATE(g.gate);
     extern __shared__ __align__(16) double smem[];
+    constexpr int FR = TB / 16, A_STAGE = Tile<TB>::A_STAGE, B_STAGE = Tile<TB>::B_STAGE;
     double *As = smem, *Bs = smem + STAGES * A_STAGE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
-    const int n0 = blockIdx.x * BN;
+    const int n0 = blockIdx.x * TB;
     // gridDim.y == 1: this CTA walks all row tiles; otherwise (small batches) only row tile blockIdx.y
     const bool split = gridDim.y > 1;
-    const int mt0 = split ? blockIdx.y : 0, mt1 = split ? blockIdx.y + 1 : g.M / BM;
+    const int mt0 = split ? blockIdx.y : 0, mt1 = split ? blockIdx.y + 1 : g.M / TB;
     // flattened (row tile, k tile) sequence so that the cp.async pipeline never drains
     // k tiles of a row tile: the triangular part up to the diagonal, then the dense tail columns (GemmArgs::k_tri)
     const int ktri = g.lower_triangular ? (g.k_tri > 0 ? g.k_tri : g.K) : g.K, tail = (g.K - ktri) / BK;
-    auto tritiles = [&](int mt) { return (g.lower_triangular ? min(ktri, (mt + 1) * BM) : ktri) / BK; };
+    auto tritiles = [&](int mt) { return (g.lower_triangular ? min(ktri, (mt + 1) * TB) : ktri) / BK; };
     auto ktiles = [&](int mt) { return tritiles(mt) + tail; };
     int total = 0;
     for (int mt = mt0; mt < mt1; ++mt) total += ktiles(mt);
     int lmt = mt0, lkt = 0;  // next tile to load
     auto issue = [&](int slot) {
         const int tt = tritiles(lmt);
-        load_stage(As + slot * A_STAGE, Bs + slot * B_STAGE, g.A, g.Bm, g.lda, g.ldb, lmt * BM, n0,
-                   lkt < tt ? lkt * BK : ktri + (lkt - tt) * BK, tid);
+        load_stage<TB>(As + slot * A_STAGE, Bs + slot * B_STAGE, g.A, g.Bm, g.lda, g.ldb, lmt * TB, n0,
+                       lkt < tt ? lkt * BK : ktri + (lkt - tt) * BK, tid);
         if (++lkt == ktiles(lmt)) { lkt = 0; ++lmt; }
     };
-    double colsum[4][2];
+    double colsum[FR][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) colsum[j][0] = colsum[j][1] = 0.0;
-    double acc[4][4][2];
+    for (int j = 0; j < FR; ++j) colsum[j][0] = colsum[j][1] = 0.0;
+    double acc[FR][FR][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < FR; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < FR; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < total) issue(s);
@@ -168,13 +180,13 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
         __syncthreads();
         if (t + STAGES - 1 < total) issue((t + STAGES - 1) % STAGES);
         cp_async_commit();
-        compute_stage(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
+        compute_stage<TB>(As + (t % STAGES) * A_STAGE, Bs + (t % STAGES) * B_STAGE, acc, wm, wn, lane);
         if (++ckt == ktiles(cmt)) {
             // row tile finished: fold its squares into the column sums, restart accumulators
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < FR; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
+                for (int ni = 0; ni < FR; ++ni) {
                     colsum[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], colsum[ni][0]);
                     colsum[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], colsum[ni][1]);
                     acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
     cp_async_wait<0>();
     // reduce over the 8 row-lanes of each fragment column (lanes with equal lane%4)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni)
+    for (int ni = 0; ni < FR; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             double v = colsum[ni][e];
@@ -196,19 +208,19 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
             colsum[ni][e] = v;
         }
     __syncthreads();
-    double *red = smem;  // [2 row-warps][64 columns]
+    double *red = smem;  // [2 row-warps][TB columns]
     if (lane < 4) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            int col = wn * 32 + ni * 8 + 2 * lane;
-            red[wm * BN + col] = colsum[ni][0];
-            red[wm * BN + col + 1] = colsum[ni][1];
+        for (int ni = 0; ni < FR; ++ni) {
+            int col = wn * (TB / 2) + ni * 8 + 2 * lane;
+            red[wm * TB + col] = colsum[ni][0];
+            red[wm * TB + col + 1] = colsum[ni][1];
         }
     }
     __syncthreads();
-    if (tid < BN) {
+    if (tid < TB) {
         int n = n0 + tid;
-        double v = red[tid] + red[BN + tid];
+        double v = red[tid] + red[TB + tid];
         if (split) {
             g.chi2_part[(size_t)blockIdx.y * g.part_ld + n] = v;  // part_ld covers whole panels
         } else if (n < g.N) {
@@ -412,28 +424,46 @@ __device__ __forceinline__ double counter_normal(unsigned long long seed, unsign
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
-__global__ void toy_noise_kernel(const double *__restrict__ L, int n, int n_pad, const double *__restrict__ truth,
-                                 unsigned long long seed, long long first_toy, int ntoy, double scale,
-                                 double *__restrict__ out) {
-    extern __shared__ double gsh[];  // [n] deviates of this toy
-    int t = blockIdx.x;
-    if (t >= ntoy) return;
-    for (int j = threadIdx.x; j < n; j += blockDim.x)
-        gsh[j] = counter_normal(seed, (unsigned long long)(first_toy + t), (unsigned)j);
+// Toy realisations d = truth + scale * L g (likely::CovarianceMatrix::sample, call site baofit/CorrelationAnalyzer.cc:271)
+// as a lower-triangular DMMA GEMM over a panel of deviates: G[j][t] = deviate j of toy t (bin-major, toys contiguous),
+// Y = L . G through dgemm_store_kernel (k-tiles above the diagonal skipped), then a tiled transpose into the
+// toy-major table the refits gather from.
+__global__ void toy_deviates_kernel(int n, unsigned long long seed, long long first_toy, int ntoy, int ldg, double *__restrict__ G) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (t >= ldg) return;
+    G[(size_t)j * ldg + t] = (j < n && t < ntoy) ? counter_normal(seed, (unsigned long long)(first_toy + t), (unsigned)j) : 0.0;
+}
+
+__global__ void toy_finish_kernel(const double *__restrict__ Y, int n, int ntoy, int ldg, const double *__restrict__ truth, double scale,
+                                  double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    const int t0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, t = t0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && t < ntoy) ? Y[(size_t)i * ldg + t] : 0.0;
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double *row = L + (size_t)i * n_pad;
-        double s = 0.0;
-        for (int j = 0; j <= i; ++j) s = fma(row[j], gsh[j], s);
-        out[(size_t)t * n + i] = truth[i] + scale * s;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int t = t0 + r, i = i0 + threadIdx.x;
+        if (t < ntoy && i < n) out[(size_t)t * n + i] = fma(scale, tile[threadIdx.x][r], truth[i]);
     }
 }
 
-void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch) {
-    static SmemOptIn opt;
-    opt.ensure(dgemm_store_kernel, (size_t)SMEM_BYTES);
+// fewer 64 x 64 tiles than SMs: 32 x 32 tiles quarter the serial work of a tile's K loop
+static bool use_small_tiles(int M, int N, int batch, int sm_count) {
+    return sm_count > 0 && (long)((N + BN - 1) / BN) * (M / BM) * batch < sm_count && M % 32 == 0;
+}
+
+void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch, int sm_count) {
+    static SmemOptIn opt, opt32;
+    if (use_small_tiles(g.M, g.N, batch, sm_count)) {
+        opt32.ensure(dgemm_store_kernel<32>, (size_t)Tile<32>::SMEM);
+        dgemm_store_kernel<32><<<dim3((g.N + 31) / 32, g.M / 32, batch), 128, Tile<32>::SMEM, s>>>(g);
+        return;
+    }
+    opt.ensure(dgemm_store_kernel<BM>, (size_t)SMEM_BYTES);
     dim3 grid((g.N + BN - 1) / BN, g.M / BM, batch);
-    dgemm_store_kernel<<<grid, 128, SMEM_BYTES, s>>>(g);
+    dgemm_store_kernel<BM><<<grid, 128, SMEM_BYTES, s>>>(g);
 }
 
 // Row tiles are split over CTAs while all (panel, row tile) CTAs fit in about two waves of 4 resident CTAs
@@ -446,20 +476,44 @@ int gemm_chi2_split_columns(int M, int sm_count) {
 }
 
 void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count) {
-    static SmemOptIn opt;
-    opt.ensure(dgemm_chi2_kernel, (size_t)SMEM_BYTES);
+    static SmemOptIn opt, opt32;
     const int panels = (g.N + BN - 1) / BN, tiles = g.M / BM;
     if (g.chi2_part && g.N <= gemm_chi2_split_columns(g.M, sm_count) && g.part_ld >= panels * BN) {
-        dgemm_chi2_kernel<<<dim3(panels, tiles, 1), 128, SMEM_BYTES, s>>>(g);
+        if (use_small_tiles(g.M, g.N, 1, sm_count)) {  // scratch holds M / 32 partial rows (gemm_chi2_scratch)
+            opt32.ensure(dgemm_chi2_kernel<32>, (size_t)Tile<32>::SMEM);
+            dgemm_chi2_kernel<32><<<dim3((g.N + 31) / 32, g.M / 32, 1), 128, Tile<32>::SMEM, s>>>(g);
+            chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, g.M / 32, g.N, g.status, g.chi2, g.gate);
+            return;
+        }
+        opt.ensure(dgemm_chi2_kernel<BM>, (size_t)SMEM_BYTES);
+        dgemm_chi2_kernel<BM><<<dim3(panels, tiles, 1), 128, SMEM_BYTES, s>>>(g);
         chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, tiles, g.N, g.status, g.chi2, g.gate);
         return;
     }
-    dgemm_chi2_kernel<<<dim3(panels, 1, 1), 128, SMEM_BYTES, s>>>(g);
+    opt.ensure(dgemm_chi2_kernel<BM>, (size_t)SMEM_BYTES);
+    dgemm_chi2_kernel<BM><<<dim3(panels, 1, 1), 128, SMEM_BYTES, s>>>(g);
 }
 
-void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth,
-                      unsigned long long seed, long long first_toy, int ntoy, double scale, double *out) {
-    toy_noise_kernel<<<ntoy, 256, n * sizeof(double), s>>>(L, n, n_pad, truth, seed, first_toy, ntoy, scale, out);
+size_t toy_noise_work_doubles(int n_pad, int ntoy) {
+    const int cols = std::min(round_up(ntoy, BN), kToyPassCols);
+    return (size_t)2 * n_pad * cols;
+}
+
+void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const double *truth, unsigned long long seed, long long first_toy,
+                      int ntoy, double scale, double *out, double *work) {
+    const int cols = std::min(round_up(ntoy, BN), kToyPassCols);
+    double *G = work, *Y = work + (size_t)n_pad * cols;
+    for (int t0 = 0; t0 < ntoy; t0 += cols) {
+        const int nt = std::min(cols, ntoy - t0), ldg = round_up(nt, BN);
+        toy_deviates_kernel<<<dim3((ldg + 127) / 128, n_pad), 128, 0, s>>>(n, seed, first_toy + t0, nt, ldg, G);
+        GemmArgs g{};
+        g.A = L; g.Bm = G; g.C = Y;
+        g.M = n_pad; g.N = nt; g.K = n_pad;
+        g.lda = n_pad; g.ldb = ldg; g.ldc = ldg;
+        g.lower_triangular = 1;
+        launch_gemm_store(s, g, 1, 0);
+        toy_finish_kernel<<<dim3((nt + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, s>>>(Y, n, nt, ldg, truth, scale, out + (size_t)t0 * n);
+    }
 }
 
 }  // namespace bf

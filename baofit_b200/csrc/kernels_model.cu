@@ -948,6 +948,7 @@ void launch_gather_rows(cudaStream_t s, const double *table, const int *index, i
 // Gauss-Newton normal equations: one CTA per fit
 // ------------------------------------------------------------------------------------------
 constexpr int kGramRows = 32;  // G <= 96 (checked by the callers): at most 19 pairs per thread
+constexpr int kProbeSplit = 8;  // row slices of the normal-equation kernels
 
 __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y, int ldy, int nrows, int G, int nfit,
                                                    double *__restrict__ out) {
@@ -988,8 +989,10 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y,
 // a_i = y(x + h_i) - y(x - h_i) and s_i = y(x + h_i) + y(x - h_i) - 2 y0 a minimiser needs only
 //   M = [y0 a_1 .. a_n]^T [y0 a_1 .. a_n]   ((n+1)^2, symmetric)   and   t_i = y0 . s_i   (n values),
 // a quarter of the full Gram matrix to compute and to send back: out[f] = M (row-major) followed by t.
+// The rows are cut into kProbeSplit slices (always, so that the sums do not depend on how many fits share a call): CTA
+// (f, s) writes its partial sums to part[(f * kProbeSplit + s) * npairs + p], normal_probes_sum_kernel adds them in order.
 __global__ void __launch_bounds__(256) normal_probes_kernel(const double *__restrict__ Y, int ldy, int nrows, int n, int nfit,
-                                                            double *__restrict__ out) {
+                                                            double *__restrict__ part) {
     extern __shared__ double nsm[];  // [kGramRows][R + n]: y0, a_1..a_n, s_1..s_n
     const int f = blockIdx.x, tid = threadIdx.x, G = 2 * n + 1, R = n + 1, W = R + n;
     const int npairs = R * (R + 1) / 2 + n;  // pairs (i >= j) of M, then the n dot products y0 . s_i
@@ -1009,8 +1012,9 @@ __global__ void __launch_bounds__(256) normal_probes_kernel(const double *__rest
         pi[np] = i; pj[np] = j; acc[np] = 0.0; ++np;
     }
     const double *base = Y + (size_t)f * G;
-    for (int r0 = 0; r0 < nrows; r0 += kGramRows) {
-        const int nr = min(kGramRows, nrows - r0);
+    const int per_slice = (nrows + kProbeSplit - 1) / kProbeSplit, r_lo = min(nrows, (int)blockIdx.y * per_slice), r_hi = min(nrows, r_lo + per_slice);
+    for (int r0 = r_lo; r0 < r_hi; r0 += kGramRows) {
+        const int nr = min(kGramRows, r_hi - r0);
         __syncthreads();
         for (int e = tid; e < nr * R; e += blockDim.x) {
             const int r = e / R, c = e - r * R;
@@ -1030,10 +1034,26 @@ __global__ void __launch_bounds__(256) normal_probes_kernel(const double *__rest
             acc[q] = s;
         }
     }
+    double *o = part + ((size_t)f * kProbeSplit + blockIdx.y) * npairs;
+    for (int q = 0; q < np; ++q) o[tid + q * blockDim.x] = acc[q];
+}
+
+// out[f] = M (row-major, symmetric) followed by t, from the kProbeSplit partial sums of every pair, added in slice order
+__global__ void __launch_bounds__(256) normal_probes_sum_kernel(const double *__restrict__ part, int n, int nfit, double *__restrict__ out) {
+    const int f = blockIdx.x, R = n + 1, npairs = R * (R + 1) / 2 + n;
     double *o = out + (size_t)f * (R * R + n);
-    for (int q = 0; q < np; ++q) {
-        if (pi[q] < R) { o[pi[q] * R + pj[q]] = acc[q]; o[pj[q] * R + pi[q]] = acc[q]; }
-        else o[R * R + pi[q] - R] = acc[q];
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        double v = 0.0;
+        for (int s = 0; s < kProbeSplit; ++s) v += part[((size_t)f * kProbeSplit + s) * npairs + p];
+        if (p < R * (R + 1) / 2) {
+            int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > p) --i;
+            while ((i + 1) * (i + 2) / 2 <= p) ++i;
+            const int j = p - i * (i + 1) / 2;
+            o[i * R + j] = v;
+            o[j * R + i] = v;
+        } else
+            o[R * R + p - R * (R + 1) / 2] = v;
     }
 }
 
@@ -1076,8 +1096,10 @@ __global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a)
         pi[np] = i; pj[np] = j; acc[np] = 0.0; ++np;
     }
     const double *base = a.Y + (size_t)f * G;
-    for (int r0 = 0; r0 < a.nrows; r0 += kGramRows) {
-        const int nr = min(kGramRows, a.nrows - r0);
+    const int per_slice = (a.nrows + kProbeSplit - 1) / kProbeSplit, r_lo = min(a.nrows, (int)blockIdx.y * per_slice),
+              r_hi = min(a.nrows, r_lo + per_slice);
+    for (int r0 = r_lo; r0 < r_hi; r0 += kGramRows) {
+        const int nr = min(kGramRows, r_hi - r0);
         __syncthreads();
         for (int e = tid; e < nr * R; e += blockDim.x) {
             const int r = e / R, col = e - r * R;
@@ -1107,20 +1129,21 @@ __global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a)
             acc[q] = s;
         }
     }
-    double *o = a.out + (size_t)f * (R * R + n);
-    for (int q = 0; q < np; ++q) {
-        if (pi[q] < R) { o[pi[q] * R + pj[q]] = acc[q]; o[pj[q] * R + pi[q]] = acc[q]; }
-        else o[R * R + pi[q] - R] = acc[q];
-    }
+    double *o = a.part + ((size_t)f * kProbeSplit + blockIdx.y) * npairs;
+    for (int q = 0; q < np; ++q) o[tid + q * blockDim.x] = acc[q];
 }
+
+size_t normal_probes_part_doubles(int n, int nfit) { return (size_t)nfit * kProbeSplit * ((size_t)(n + 1) * (n + 2) / 2 + n); }
 
 void launch_normal_probes_lin(cudaStream_t s, const NormalLinArgs &a) {
     const size_t smem = ((size_t)kGramRows * (2 * a.n + 1) + a.n) * sizeof(double) + (size_t)a.n * sizeof(int);
-    normal_probes_lin_kernel<<<a.nfit, 256, smem, s>>>(a);
+    normal_probes_lin_kernel<<<dim3(a.nfit, kProbeSplit), 256, smem, s>>>(a);
+    normal_probes_sum_kernel<<<a.nfit, 256, 0, s>>>(a.part, a.n, a.nfit, a.out);
 }
 
-void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out) {
-    normal_probes_kernel<<<nfit, 256, (size_t)kGramRows * (2 * n + 1) * sizeof(double), s>>>(Y, ldy, nrows, n, nfit, out);
+void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out, double *part) {
+    normal_probes_kernel<<<dim3(nfit, kProbeSplit), 256, (size_t)kGramRows * (2 * n + 1) * sizeof(double), s>>>(Y, ldy, nrows, n, nfit, part);
+    normal_probes_sum_kernel<<<nfit, 256, 0, s>>>(part, n, nfit, out);
 }
 
 void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out) {
@@ -1128,7 +1151,7 @@ void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int
 }
 
 __global__ void expand_probes_kernel(const double *__restrict__ centres, const double *__restrict__ steps, int nfit, int npar,
-                                     int nprobe, double *__restrict__ params) {
+                                     int nprobe, double *__restrict__ params, const int *__restrict__ skip) {
     const int G = 2 * nprobe + 1;
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= nfit * G) return;
@@ -1140,7 +1163,7 @@ __global__ void expand_probes_kernel(const double *__restrict__ centres, const d
     const double sgn = (g & 1) ? 1.0 : -1.0;
     for (int j = 0; j < npar; ++j) {
         double v = c[j];
-        if (h[j] != 0.0) {
+        if (h[j] != 0.0 && !(skip && skip[j] >= 0)) {  // skip: parameters whose columns are synthesised (NormalLinArgs::lin)
             if (seen == want) v += sgn * h[j];
             ++seen;
         }
@@ -1156,9 +1179,10 @@ __global__ void reduce_status_kernel(const int *__restrict__ status, int nfit, i
     status_fit[f] = s;
 }
 
-void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params) {
+void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params,
+                          const int *skip) {
     const int total = nfit * (2 * nprobe + 1);
-    expand_probes_kernel<<<(total + 127) / 128, 128, 0, s>>>(centres, steps, nfit, npar, nprobe, params);
+    expand_probes_kernel<<<(total + 127) / 128, 128, 0, s>>>(centres, steps, nfit, npar, nprobe, params, skip);
 }
 
 void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, int *status_fit) {

@@ -222,6 +222,32 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             for (auto const &kv : byG) nj += kv.second.size();
             std::fprintf(stderr, "  round %ld: %zu Jacobian fits, %zu trial fits, t = %.3f s\n", rounds, nj, pfits.size(), nowSeconds() - t0);
         }
+        // The trial points of this round go first and asynchronously (bf_chi2_batch_submit): their evaluation is queued ahead
+        // of the probe groups below, and the host waits only once per round instead of once per call.
+        int ticket = -1, nPoints = 0;
+        double *pinnedChi2 = nullptr;
+        int *pinnedStatus = nullptr;
+        if (!pfits.empty()) {
+            flatP.clear();
+            ptoy.clear();
+            for (int k : pfits) {
+                fits[k].requestPoints(flatP);
+                if (toys) ptoy.insert(ptoy.end(), fits[k].pending(), (*toyOfFit)[k]);
+            }
+            nPoints = (int)(flatP.size() / fits[pfits[0]].nPar());
+            if (!toys && !byG.empty()) {
+                static thread_local PinnedBuffer inBuf, outBuf, stBuf;
+                double *pin = inBuf.get(flatP.size());
+                std::memcpy(pin, flatP.data(), flatP.size() * sizeof(double));
+                pinnedChi2 = outBuf.get(nPoints);
+                pinnedStatus = reinterpret_cast<int *>(stBuf.get((nPoints + 1) / 2));
+                double ta = nowSeconds();
+                check(bf_chi2_batch_submit(deviceContext(), _model->deviceModel(), _data->deviceData(needsGrid(_model)), pin, nPoints, pinnedChi2,
+                                           pinnedStatus, &ticket),
+                      "bf_chi2_batch_submit");
+                tChi2 += nowSeconds() - ta;
+            }
+        }
         for (auto const &kv : byG) {
             const int G = kv.first;
             if (G > 95) {
@@ -252,17 +278,16 @@ void CorrelationFitter::runLockStepLM(std::vector<likely::LMFit> &fits, bf_toys 
             tSolve += nowSeconds() - ta;
         }
         if (!pfits.empty()) {
-            flatP.clear();
-            ptoy.clear();
-            for (int k : pfits) {
-                fits[k].requestPoints(flatP);
-                if (toys) ptoy.insert(ptoy.end(), fits[k].pending(), (*toyOfFit)[k]);
-            }
-            const int npar = fits[pfits[0]].nPar();
             double ta = nowSeconds();
-            chiSquareFlat(flatP, (int)(flatP.size() / npar), chi2, toys, toys ? ptoy.data() : nullptr);
+            if (ticket >= 0) {
+                check(bf_chi2_batch_wait(deviceContext(), ticket), "bf_chi2_batch_wait");
+                chi2.assign(pinnedChi2, pinnedChi2 + nPoints);
+                for (int b = 0; b < nPoints; ++b)
+                    if (pinnedStatus[b]) chi2[b] = std::numeric_limits<double>::quiet_NaN();
+            } else
+                chiSquareFlat(flatP, nPoints, chi2, toys, toys ? ptoy.data() : nullptr);
             tChi2 += nowSeconds() - ta;
-            nChi2 += (long)(flatP.size() / npar);
+            nChi2 += (long)nPoints;
             ta = nowSeconds();
             offsets.assign(pfits.size(), 0);
             size_t off = 0;

@@ -345,6 +345,54 @@ def test_fused_data_tail_equals_unfused_path(ctx):
         gm.close(), gd.close()
 
 
+def test_linear_probe_columns_are_synthesised_exactly(ctx):
+    """bf_normal_probes on models whose additive broadband enters the whitened residual linearly with a bin-static
+    basis (k-space without distortion matrix, no velocity shift): the difference columns of those parameters come
+    from W . basis instead of two evaluations each. Same normal equations as the all-evaluated path
+    (BAOFIT_NO_LINEAR_PROBES), for one redshift class (DR11 auto) and three (DR9), with and without toys; and far
+    fewer evaluations."""
+    rng = np.random.Generator(np.random.PCG64(43))
+    m9, d9 = W.dr9_kspace()
+    m11, (r, mu, z, keep) = W.dr11_auto_kspace()
+    n11 = len(keep)
+    xi0 = 1e-3 * (50.0 / r[keep]) ** 2
+    d11 = W.make_data(r, mu, z, keep, xi0 * (1 + 0.1 * rng.standard_normal(n11)), W.synthetic_cov(xi0))
+    for m, d in ((m11, d11), (m9, d9)):
+        gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+        nfit = 9
+        p = m.random_batch(nfit, rng, sweep={"BAO alpha-parallel": (0.9, 1.1), "BAO alpha-perp": (0.9, 1.1)})
+        jb = [j for j, nm in enumerate(m.names) if nm.startswith("dist add")]
+        p[:, jb] += 1e-4 * rng.standard_normal((nfit, len(jb)))
+        steps = np.zeros_like(p)
+        fl = [j for j in np.nonzero(m.floating)[0] if not m.names[j].startswith("BAO alpha")]
+        assert len(set(fl) & set(jb)) >= 3
+        steps[:, fl] = 0.01 * m.errors[fl] * (1 + 0.3 * rng.random((nfit, len(fl))))
+        truth = capi.eval_batch(ctx, gm, gd, p[:1])[0][:, 0]
+        toys = capi.Toys(ctx, gd, truth, 5, 0, 4)
+        ti = rng.integers(0, 4, nfit).astype(np.int32)
+        for tt, ii in ((None, None), (toys, ti)):
+            out = {}
+            for mode in ("lin", "all"):
+                if mode == "all":
+                    os.environ["BAOFIT_NO_LINEAR_PROBES"] = "1"
+                try:
+                    ctx.set_profiling(True)
+                    out[mode] = capi.normal_probes(ctx, gm, gd, p, steps, tt, ii)
+                    prof = ctx.get_profile()
+                    ctx.set_profiling(False)
+                finally:
+                    os.environ.pop("BAOFIT_NO_LINEAR_PROBES", None)
+                assert ("normal_probes_lin_kernel" in prof) == (mode == "lin"), prof.keys()
+            (Ml, tl, sl_), (Ma, ta, sa) = out["lin"], out["all"]
+            assert np.array_equal(sl_, sa) and np.all(sa == 0)
+            dn = np.sqrt(np.abs(np.einsum("fii->fi", Ma)))
+            assert np.max(np.abs(Ml - Ma) / (dn[:, :, None] * dn[:, None, :])) < 1e-9
+            # y0 . s_i: exactly zero for a linear parameter, rounding noise of two evaluations otherwise
+            scale = dn[:, :1] * dn[:, :1]
+            assert np.max(np.abs(tl - ta) / scale) < 1e-9
+        toys.close(), gm.close(), gd.close()
+
+
 def test_rspace_fast_and_generic_kernels_against_oracle(ctx):
     """The r-space model runs through the basis-table fast pass when both tabulations share one uniform grid and
     through the generic per-vector kernel otherwise; both against the oracle, with the radiation term switched on
