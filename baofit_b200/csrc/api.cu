@@ -297,6 +297,7 @@ extern "C" int bf_model_create(bf_ctx *ctx, const bf_model_desc *d, bf_model **o
     BF_CUDA_OK(cudaSetDevice(ctx->device));
     bf_model *m = new bf_model();
     m->ctx = ctx;
+    m->dzmin = d->dzmin;
     static std::atomic<unsigned long long> next_serial{1};
     m->serial = next_serial.fetch_add(1);
     DevModel &dm = m->dev;
@@ -756,6 +757,22 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
         }
     }
     p.nz = (int)p.zvals.size();
+    // The reference re-runs its k-space transforms in the middle of a sweep over the bins when the redshift of two
+    // consecutive bins differs by more than dzmin (BaoKSpaceCorrelationModel.cc:317-319,333), with beta(z) -- and z_eff
+    // when none is set -- of the bin it happens to be at: a result that depends on the bin order. Here the transform
+    // uses the redshift of the first kept bin. The two agree unless such a jump exists AND something in D(k, mu) depends
+    // on z: gamma-beta != 0 (flagged per vector, BF_STATUS_Z_RETRIGGER) or a non-linear correction without z_eff (refused).
+    p.z_retrigger = false;
+    if (dm.kind == BF_MODEL_KSPACE) {
+        const std::vector<double> &zs = use_dm ? d->h_grid_z : d->h_z;
+        const int nzs = use_dm ? ng : n;
+        for (int i = 1; i < nzs; ++i)
+            if (std::fabs(zs[i] - zs[i - 1]) > m->dzmin) p.z_retrigger = true;
+        if (p.z_retrigger && dm.zeff <= 0 && (dm.flags & (BF_FLAG_NL_CORRECTION | BF_FLAG_NL_CORRECTION_ALT | BF_FLAG_FIT_NL_CORRECTION)))
+            BF_FAIL(BF_ERR_OPTIONS, "k-space model with a non-linear correction and no zeff on data whose consecutive bins jump by more than "
+                                    "dzmin in redshift: the reference re-transforms per bin here (BaoKSpaceCorrelationModel.cc:315-333), "
+                                    "which is not reproduced; set zeff");
+    }
     std::vector<double> vfac(p.nz);
     for (int c = 0; c < p.nz; ++c) {
         double zp1 = 1.0 + p.zvals[c];
@@ -1155,7 +1172,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     // coherence sort (chi2 only; outputs that are indexed by the original column stay unsorted)
     const bool sorted = what == OUT_CHI2 && !d_override && B >= 2048 && dm.kind != BF_MODEL_KSPACE_FFT;
     if (sorted) BF_KERNEL(ctx, "coherence_sort_kernels", launch_coherence_sort(s, dm, d_params, B, w.sort_hist, w.sort_base, w.rank));
-    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status));
+    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status, plan && plan->z_retrigger));
     double *chi2_dst = sorted ? w.chi2_sorted : d_out;
 
     // ---- k-space model: which chain runs is decided on the device (no host round trip inside a call) ----

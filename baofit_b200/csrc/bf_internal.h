@@ -185,6 +185,7 @@ struct bf_ctx {
 struct bf_model {
     bf_ctx *ctx = nullptr;
     unsigned long long serial = 0;  // unique per created model: key of the (model, data) plans
+    double dzmin = 0.5;             // bf_model_desc::dzmin (plan-time check of the reference's mid-sweep re-transform)
     bf::DevModel dev;
     std::vector<void *> allocs;  // device allocations owned by the model
     // host copies needed at plan time
@@ -245,6 +246,7 @@ struct bf_data {
         int *d_zc_metal_data = nullptr;  // [ncomb][n_pad]    class of metal zgrid[c][index_i]
         int *d_zc_metal_grid = nullptr;  // [ncomb][n_grid_pad]
         int zc_trigger = 0;          // class of the z that triggers the k-space transform
+        bool z_retrigger = false;    // consecutive bins jump by more than dzmin in z (see get_plan)
         double *d_Dkept = nullptr;   // [n_pad][n_grid_pad] rows of the distortion matrix of kept bins
         // bin-static tables of the cartesian-form kernels (kernels_fast.cu)
         struct PointTabDev {

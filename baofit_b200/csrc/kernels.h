@@ -165,7 +165,7 @@ struct GemmArgs {
 };
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
-                 const double *zvals, const int *rank, double *pT, double *S, int *status);
+                 const double *zvals, const int *rank, double *pT, double *S, int *status, bool z_retrigger = false);
 // counting sort of the vectors on their quantised dilation parameters; hist/base: 2048 ints each
 void launch_coherence_sort(cudaStream_t s, const DevModel &m, const double *params, int B, int *hist, int *base, int *rank);
 void launch_unpermute(cudaStream_t s, int B, const int *rank, const double *chi2_sorted, const int *status_sorted,

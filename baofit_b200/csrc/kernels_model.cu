@@ -14,7 +14,7 @@ namespace bf {
 // ------------------------------------------------------------------------------------------
 __global__ void prep_kernel(DevModel m, const double *__restrict__ params, int B, int ldb, int nz,
                             const double *__restrict__ zvals, const int *__restrict__ rank, double *__restrict__ pT,
-                            double *__restrict__ S, int *__restrict__ status) {
+                            double *__restrict__ S, int *__restrict__ status, int z_retrigger) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double *p = params + (size_t)b * m.npar;
@@ -28,7 +28,8 @@ __global__ void prep_kernel(DevModel m, const double *__restrict__ params, int B
         S[(size_t)(c * 3 + 1) * ldb + col] = gbeta == 0.0 ? 1.0 : pow(x, gbeta);
         S[(size_t)(c * 3 + 2) * ldb + col] = gs == 0.0 ? 1.0 : pow(x, gs);
     }
-    status[col] = 0;
+    // gamma-beta != 0 on data where the reference would re-transform in the middle of its sweep (bf_data::Plan::z_retrigger)
+    status[col] = (z_retrigger && gbeta != 0.0) ? BF_STATUS_Z_RETRIGGER : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -834,8 +835,8 @@ static int pick_pts_per_block(int npts_pad, int B, int sm_count) {
 }
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
-                 const double *zvals, const int *rank, double *pT, double *S, int *status) {
-    prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(m, params, B, ldb, nz, zvals, rank, pT, S, status);
+                 const double *zvals, const int *rank, double *pT, double *S, int *status, bool z_retrigger) {
+    prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(m, params, B, ldb, nz, zvals, rank, pT, S, status, z_retrigger ? 1 : 0);
 }
 
 void launch_coherence_sort(cudaStream_t s, const DevModel &m, const double *params, int B, int *hist, int *base, int *rank) {

@@ -25,7 +25,7 @@ FLAGS = {
 }
 BF_METAL_NONE, BF_METAL_AUTO_TABLE, BF_METAL_CROSS_BICUBIC, BF_METAL_TOY = 0, 1, 2, 3
 BF_BB_DIST_ADD, BF_BB_DIST_MUL, BF_BB_DM_DIST_ADD, BF_BB_DM_DIST_MUL = 0, 1, 2, 3
-BF_STATUS_DILATION_MIN, BF_STATUS_DILATION_MAX, BF_STATUS_FFT_RANGE = 1, 2, 4
+BF_STATUS_DILATION_MIN, BF_STATUS_DILATION_MAX, BF_STATUS_FFT_RANGE, BF_STATUS_Z_RETRIGGER = 1, 2, 4, 8
 
 
 class BroadbandSpec(C.Structure):

@@ -44,6 +44,8 @@ extern "C" {
 #define BF_STATUS_DILATION_MIN 1 /* "hit min dilation limit", BaoKSpaceCorrelationModel.cc:420 */
 #define BF_STATUS_DILATION_MAX 2 /* "hit max dilation limit", BaoKSpaceCorrelationModel.cc:424 */
 #define BF_STATUS_FFT_RANGE 4    /* FFT model: a dilated bin falls outside the tabulated (r_perp, r_par) plane (fft_rmax) */
+#define BF_STATUS_Z_RETRIGGER 8  /* k-space model, gamma-beta != 0 on data whose consecutive bins jump by more than dzmin in z:
+                                  * the reference re-transforms mid-sweep (BaoKSpaceCorrelationModel.cc:317-319), not reproduced */
 
 /* model kinds */
 #define BF_MODEL_RSPACE 0     /* baofit/BaoCorrelationModel.cc          */
@@ -141,7 +143,7 @@ typedef struct bf_model_desc {
     int ell_max;           /* 0, 2 or 4                                                     */
     double zeff;           /* <=0: take z of the triggering data bin (:315)                 */
     double sigma8;         /* NonLinearCorrectionModel.cc:62-64                             */
-    double dzmin;          /* kept for interface completeness; see DESIGN.md (quirk 3.4)    */
+    double dzmin;          /* BaoKSpaceCorrelationModel.cc:318; used to flag what is not reproduced */
 
     bf_broadband_spec bb[4]; /* BF_BB_* slots                                               */
 
