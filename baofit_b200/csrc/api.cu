@@ -76,6 +76,7 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     c->prof_pending.clear();
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
+    if (c->stage) cudaFreeHost(c->stage);
     if (c->aux) cudaFree(c->aux);
     if (c->mp) cudaFree(c->mp);
     if (c->chi2_part) cudaFree(c->chi2_part);
@@ -1771,6 +1772,29 @@ static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const doub
     double *d_ov = override_h ? (double *)(base + al(nb_params) + al(nb_out)) : nullptr;
     int *d_st = (int *)(base + al(nb_params) + al(nb_out) + al(nb_ov));
     cudaStream_t s = ctx->stream;
+    // Small chi-square calls (the rounds of a fit) go through page-locked staging owned by the context: one upload, ONE
+    // download of the adjacent chi2 | status block and one wait, instead of three pageable copies that each synchronise.
+    constexpr size_t kStageBytes = 1u << 20;
+    const size_t nb_back = al(nb_out) + nb_st;
+    const bool staged = what == OUT_CHI2 && !override_h && nb_params <= kStageBytes && nb_back <= kStageBytes;
+    if (staged && !ctx->stage) {
+        if (cudaHostAlloc((void **)&ctx->stage, 2 * kStageBytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->stage = nullptr; }
+    }
+    if (staged && ctx->stage) {
+        std::memcpy(ctx->stage, params, nb_params);
+        BF_CUDA_OK(cudaMemcpyAsync(d_params, ctx->stage, nb_params, cudaMemcpyHostToDevice, s));
+        {
+            KeyHintScope hs(ctx, m->dev, params, B);
+            rc = run_device(ctx, m, d, d_params, B, what, d_out, B, nullptr, d_st);
+        }
+        if (rc) return rc;
+        char *back = ctx->stage + kStageBytes;
+        BF_CUDA_OK(cudaMemcpyAsync(back, d_out, nb_back, cudaMemcpyDeviceToHost, s));
+        BF_CUDA_OK(cudaStreamSynchronize(s));
+        std::memcpy(out, back, nb_out);
+        if (status) std::memcpy(status, back + al(nb_out), nb_st);
+        return BF_OK;
+    }
     BF_CUDA_OK(cudaMemcpyAsync(d_params, params, nb_params, cudaMemcpyHostToDevice, s));
     if (override_h) BF_CUDA_OK(cudaMemcpyAsync(d_ov, override_h, nb_ov, cudaMemcpyHostToDevice, s));
     {

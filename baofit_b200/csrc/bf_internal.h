@@ -166,6 +166,7 @@ struct bf_ctx {
     void *ws = nullptr;
     size_t ws_bytes = 0;
     void *io = nullptr;  // staging for host-buffer entry points
+    char *stage = nullptr;  // page-locked staging of small host-buffer chi-square calls (2 x 1 MB: in, out)
     void *aux = nullptr;  // small side buffers of the probe entry points (linear-parameter map, masked steps)
     size_t aux_bytes = 0;
     size_t io_bytes = 0;

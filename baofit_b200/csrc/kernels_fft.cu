@@ -523,8 +523,10 @@ __device__ __forceinline__ double catmull(double pm1, double p0, double p1, doub
 }
 
 // bicubic (Catmull-Rom) interpolation on an even plane; false if the stencil leaves the plane
+template <bool LDG = true>
 __device__ __forceinline__ bool plane_lookup(const DevFft &f, const double *__restrict__ pl, double r, double mu,
                                              double &out) {
+    auto ld = [](const double *p) { return LDG ? __ldg(p) : *p; };
     const double x = r * sqrt(1.0 - mu * mu) * f.inv_delta, y = fabs(r * mu) * f.inv_delta;
     const int ix = (int)floor(x), iy = (int)floor(y);
     if (ix + 2 > f.npx - 1 || iy + 2 > f.npy - 1 || !(x >= 0.0)) { out = nan(""); return false; }
@@ -533,7 +535,7 @@ __device__ __forceinline__ bool plane_lookup(const DevFft &f, const double *__re
 #pragma unroll
     for (int bq = 0; bq < 4; ++bq) {
         const double *row = pl + (size_t)abs(iy - 1 + bq) * f.npx_pad;
-        col[bq] = catmull(__ldg(row + abs(ix - 1)), __ldg(row + ix), __ldg(row + ix + 1), __ldg(row + ix + 2), tx);
+        col[bq] = catmull(ld(row + abs(ix - 1)), ld(row + ix), ld(row + ix + 1), ld(row + ix + 2), tx);
     }
     out = catmull(col[0], col[1], col[2], col[3], ty);
     return true;
@@ -603,7 +605,81 @@ __global__ void __launch_bounds__(256, 4) fft_eval_kernel(FftEvalArgs a) {
     if (st && valid && bin_lane == 0) atomicOr(a.status + b, st);
 }
 
+// The same evaluation with the two planes of a parameter vector staged in shared memory: one CTA per vector, the 83 KB of
+// planes arrive by TMA bulk copies (two CTAs per SM), and the 2 x 16 stencil reads of every bin are shared-memory loads
+// instead of L2 round trips. fft_eval_kernel was bound by load latency (1.14 ms for 18 944 vectors x 1515 bins at 37 %
+// occupancy, its 8 vectors per CTA sweep 660 KB of planes through L1); here each plane byte crosses L2 once.
+__global__ void __launch_bounds__(256, 2) fft_eval_smem_kernel(FftEvalArgs a) {
+    extern __shared__ __align__(128) double esm[];
+    __shared__ __align__(8) unsigned long long bar;
+    const DevModel &m = a.m;
+    const DevFft &f = m.fft;
+    const int b = blockIdx.x, tid = threadIdx.x, ldb = a.ldb;
+    const unsigned plane_doubles = (unsigned)(f.npy_pad * f.npx_pad), bytes = 2u * plane_doubles * (unsigned)sizeof(double);
+    if (tid == 0) {
+        p_mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        p_mbar_expect_tx(&bar, bytes);
+        const char *src = reinterpret_cast<const char *>(a.planes + (size_t)b * 2 * plane_doubles);
+        for (unsigned off = 0; off < bytes; off += 32768u)
+            p_tma_g2s(reinterpret_cast<char *>(esm) + off, src + off, min(32768u, bytes - off), &bar);
+    }
+    const double *pT = a.pT + b;
+    const bool cross = m.flags & BF_FLAG_CROSS_CORRELATION;
+    const double beta = pT[(size_t)m.idx_beta * ldb];
+    const double bias = pT[(size_t)m.idx_bb * ldb] / (1.0 + beta);
+    const double biasSq = cross ? bias * pT[(size_t)m.idx_bias2 * ldb] : bias * bias;
+    const double gammaBias = pT[(size_t)m.idx_gamma_bias * ldb];
+    const double dv = cross ? pT[(size_t)m.idx_delta_v * ldb] : 0.0;
+    const double ampl = pT[(size_t)m.idx_bao * ldb], s_iso = pT[(size_t)(m.idx_bao + 1) * ldb];
+    const double s_par = pT[(size_t)(m.idx_bao + 2) * ldb], s_perp = pT[(size_t)(m.idx_bao + 3) * ldb];
+    const double gamma_scale = pT[(size_t)(m.idx_bao + 4) * ldb];
+    const double *pl_peak = esm, *pl_smooth = esm + plane_doubles;
+    __syncthreads();  // the barrier is initialised
+    p_mbar_wait(&bar, 0);
+    int st = 0;
+    for (int i = tid; i < a.npts; i += blockDim.x) {
+        double r = a.r[i], mu = a.mu[i], z = a.z[i];
+        if (cross) velocity_shift(fft_dpi(m, dv, z), r, mu);  // AbsCorrelationModel.cc:25
+        z = fft_zcorr(f, r, mu, z);
+        const double zf = (1.0 + z) / (1.0 + m.zref);
+        const double evb = gammaBias == 0.0 ? 1.0 : pow(zf, gammaBias);
+        const double evs = gamma_scale == 0.0 ? 1.0 : pow(zf, gamma_scale);
+        double rBAO, muBAO;
+        if (m.flags & BF_FLAG_ANISOTROPIC) {
+            const double apar = s_par * evs, aperp = s_perp * evs, musq = mu * mu;
+            const double scale = sqrt(apar * apar * musq + aperp * aperp * (1.0 - musq));
+            rBAO = r * scale;
+            muBAO = apar * mu / scale;
+        } else {
+            rBAO = r * (s_iso * evs);
+            muBAO = mu;
+        }
+        double peak, smooth;
+        bool ok = plane_lookup<false>(f, pl_peak, rBAO, muBAO, peak);
+        if (m.flags & BF_FLAG_DECOUPLED) ok &= plane_lookup<false>(f, pl_smooth, r, mu, smooth);
+        else ok &= plane_lookup<false>(f, pl_smooth, rBAO, muBAO, smooth);
+        if (!ok) st |= BF_STATUS_FFT_RANGE;
+        double xi = (biasSq * evb) * (ampl * peak + smooth);
+        if (m.bb[BF_BB_DIST_MUL].enabled) xi *= 1.0 + broadband_eval(m.bb[BF_BB_DIST_MUL], pT, ldb, r, mu, z);
+        if (m.bb[BF_BB_DIST_ADD].enabled) xi += broadband_eval(m.bb[BF_BB_DIST_ADD], pT, ldb, r, mu, z) * evb;
+        const double sub = a.dov ? a.dov[(size_t)b * a.npts + i] : (a.dsub ? a.dsub[i] : 0.0);
+        a.out[(size_t)i * a.ldo + b] = xi - sub;
+    }
+    st = __reduce_or_sync(0xffffffffu, st);
+    if (st && (tid & 31) == 0) atomicOr(a.status + b, st);
+}
+
 void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a) {
+    const DevFft &f = a.m.fft;
+    const size_t smem = (size_t)2 * f.npy_pad * f.npx_pad * sizeof(double);
+    static const bool no_smem = std::getenv("BAOFIT_FFT_EVAL_GLOBAL") != nullptr;  // A/B measurements
+    if (!no_smem && smem <= 110 * 1024 && smem % 16 == 0 && a.B >= 64) {
+        static SmemOptIn opt;
+        opt.ensure(fft_eval_smem_kernel, smem);
+        fft_eval_smem_kernel<<<a.B, 256, smem, s>>>(a);
+        return;
+    }
     dim3 grid((a.B + kEvalVecPerBlock - 1) / kEvalVecPerBlock, (a.npts + kEvalBinsPerBlock - 1) / kEvalBinsPerBlock);
     fft_eval_kernel<<<grid, 256, 0, s>>>(a);
 }

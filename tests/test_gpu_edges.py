@@ -245,8 +245,8 @@ def test_reference_mid_sweep_retransform_is_flagged_not_silently_different(ctx):
     """Where the reference would re-run its k-space transforms in the middle of a sweep over the bins (consecutive bins
     whose redshifts differ by more than dzmin, BaoKSpaceCorrelationModel.cc:317-319) and D(k, mu) depends on z through
     gamma-beta, the answer depends on the bin order and is not reproduced: such vectors come back with
-    BF_STATUS_Z_RETRIGGER and NaN; with gamma-beta = 0, or dzmin above the jumps (the reference's 0.5 against DR9's
-    three z bins), nothing is flagged."""
+    BF_STATUS_Z_RETRIGGER and NaN; with gamma-beta = 0 (as config/BOSSDR9LyaF_k.ini fixes it), or dzmin above the jumps
+    between DR9's three z bins, nothing is flagged."""
     from baofit_b200.desc import BF_STATUS_Z_RETRIGGER
     m, d = W.dr9_kspace()
     rng = np.random.Generator(np.random.PCG64(31))
@@ -254,11 +254,12 @@ def test_reference_mid_sweep_retransform_is_flagged_not_silently_different(ctx):
     jg = m.index("gamma-beta")
     p[:3, jg] = 0.0
     p[3:, jg] = 0.7
-    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)  # dzmin = 0.5: no consecutive jump is larger
+    m.desc.dzmin = 2.0  # no jump between consecutive bins is larger
+    gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
     chi2, st = capi.chi2_batch(ctx, gm, gd, p)
     assert np.all(st == 0) and np.all(np.isfinite(chi2))
     gm.close(), gd.close()
-    m.desc.dzmin = 0.2
+    m.desc.dzmin = 0.5  # the reference's default: the sweep over DR9's bins crosses from one z bin to another
     gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
     chi2b, stb = capi.chi2_batch(ctx, gm, gd, p)
     assert np.all(stb[:3] == 0) and np.array_equal(chi2b[:3], chi2[:3])
