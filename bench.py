@@ -82,6 +82,16 @@ def load_traffic(kernel, B):
         return None
 
 
+def ncu_pipes(kernel):
+    """DMMA and FP64 pipe utilisation of `kernel` from the committed ncu --set full capture (percent of peak), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
+            k = json.load(f)["kernels"][kernel]
+        return {"dmma": k["dmma_inst_pct_of_peak"], "fp64": k["fp64_pipe_pct_of_peak"]}
+    except Exception:
+        return None
+
+
 def load_dmma_issue_peak():
     """Issue-bound DMMA rate of tools/fp64_peak (own measurement; MEASURED_PEAKS.json has no fp64 figure)."""
     for name in ("fp64_peaks_r02.json", "fp64_peaks_r01.json"):
@@ -601,6 +611,16 @@ def main_ours(args, rank, world, local_rank):
                           "frac_executed": fl.get(top, f_eval_survey) * B / step_s * 1e-12 / fp64,
                           "tflops_survey_8d": f_eval_survey * B / step_s * 1e-12, "frac_survey_8d": f_eval_survey * B / step_s * 1e-12 / fp64}
     roof["traffic"] = load_traffic(top, B)
+    if top == "fused_model_chi2_kernel":
+        # the fused kernel also runs the model's own FP64 work on the same datapath as the DMMAs (about 218 FP64 instructions per
+        # grid bin and vector, cuobjdump count of the producer loop): tensor + model flops, and what ncu measured for the two pipes
+        model_flops = 2.0 * 218.0 * gd.n_grid
+        roof["fp64_datapath"] = {"flops_per_eval_tensor_plus_model": fl[top] + model_flops,
+                                 "achieved_tflops": (fl[top] + model_flops) * B / (kernels[top]["ms_per_launch"] * 1e-3) * 1e-12,
+                                 "frac_of_fp64_peak": (fl[top] + model_flops) * B / (kernels[top]["ms_per_launch"] * 1e-3) * 1e-12 / fp64,
+                                 "ncu_pipe_busy_pct": ncu_pipes(top),
+                                 "note": "DFMA and DMMA share one FP64 datapath per SM sub-partition (tools/fp64_mix.cu, profiles/fp64_mix_r02.json); "
+                                         "`frac` above counts the executed tensor flops only"}
     roof["traffic_unit"] = "bytes of DRAM read+write per launch (ncu --set full, profiles/ncu_traffic_r02.json)"
     roof["algorithmic_bytes_per_launch"] = (8.0 * npar + 8.0 + 4.0) * B  # parameters in, chi2 + status out: the panel never reaches HBM
 
