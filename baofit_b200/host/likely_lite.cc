@@ -486,6 +486,15 @@ void LMFit::solveStep() {
     _capped = worst > _radius;
     if (_capped)
         for (int i = 0; i < _n; ++i) _step[i] *= _radius / worst;
+    // projection onto the box priors: a step that would cross a wall ends on it (see the active set in consumeNormal)
+    for (int i = 0; i < _n; ++i) {
+        FitParameter const &fp = _params[_fidx[i]];
+        if (fp.priorType != FitParameter::BoxPrior) continue;
+        const double x = _x[_fidx[i]];
+        if (!_active.empty() && _active[i]) _step[i] = 0;
+        else if (x <= fp.priorMax && x + _step[i] > fp.priorMax) _step[i] = fp.priorMax - x;
+        else if (x >= fp.priorMin && x + _step[i] < fp.priorMin) _step[i] = fp.priorMin - x;
+    }
 }
 
 void LMFit::consumeJacobian(const double *gram, bool bad) {
@@ -533,6 +542,23 @@ void LMFit::consumeNormal(const double *normal, bool bad) {
         const double second = _cs * normal[(size_t)R * R + i] / (_h[i] * _h[i]);
         if (_A[i * _n + i] + second > 0.1 * _A[i * _n + i]) _A[i * _n + i] += second;
         _A[i * _n + i] += _ps * ph;
+    }
+    // Active set for box priors: a parameter that sits on a wall of its box while chi-square still falls towards the
+    // outside stays on the wall (its row and column leave the normal equations; it is released as soon as the gradient
+    // turns inward). Without this a valley that runs into a wall -- beta -> 100 with (1+beta)*bias fixed by the data in
+    // BOSSDR11LyaF_k.ini -- is followed across the kink of the penalty in dozens of ever smaller damped steps; these few
+    // fits set the number of lock-step rounds of a whole scan.
+    _active.assign(_n, 0);
+    for (int i = 0; i < _n; ++i) {
+        FitParameter const &fp = _params[_fidx[i]];
+        if (fp.priorType != FitParameter::BoxPrior) continue;
+        const double x = _x[_fidx[i]], gchi = _cs * normal[(i + 1) * R] / (2 * _h[i]), eps = 1e-9 * (fp.priorMax - fp.priorMin);
+        if ((x >= fp.priorMax - eps && gchi < 0) || (x <= fp.priorMin + eps && gchi > 0)) {
+            _active[i] = 1;
+            _g[i] = 0;
+            for (int j = 0; j < _n; ++j) _A[i * _n + j] = _A[j * _n + i] = 0;
+            _A[i * _n + i] = 1;
+        }
     }
     if (_n == 0) { _converged = true; _stage = Done; return; }
     // estimated distance to the minimum with the undamped Gauss-Newton step

@@ -165,6 +165,7 @@ private:
     bool _failed = false, _converged = false;
     Parameters _x;
     std::vector<double> _h, _g, _A, _step, _alphas, _scale;  // _scale: natural size of each floating parameter (its error estimate)
+    std::vector<char> _active;  // floating parameters held on a wall of their box prior in this iteration
     double priorValue(Parameters const &x) const;
     void solveStep();
 };
