@@ -476,6 +476,18 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
     if (std::getenv("BAOFIT_VERBOSE_FITS")) {
         long nev = 0;
         for (auto const &r : results) nev += r->nEvaluations;
+        // the slowest grid fits set the number of lock-step rounds: who are they
+        std::vector<long> order(count);
+        for (long k = 0; k < count; ++k) order[k] = k;
+        std::sort(order.begin(), order.end(), [&](long a, long b) { return results[a]->nIterations > results[b]->nIterations; });
+        for (long q = 0; q < std::min<long>(4, count); ++q) {
+            likely::FunctionMinimumPtr r = results[order[q]];
+            std::fprintf(stderr, "parameterScan: slow fit %ld: %d iterations, status %d, f %.6f edm %.3e, x", first + order[q], r->nIterations, (int)r->status,
+                         r->minValue, r->edm);
+            for (auto const &fp : r->parameters)
+                if (fp.floating) std::fprintf(stderr, " %s=%.6g", fp.name.c_str(), fp.value);
+            std::fprintf(stderr, "\n");
+        }
         std::fprintf(stderr, "parameterScan: %ld grid fits, %zu handed to the Newton driver, %ld LM evaluations\n", count, redo.size(), nev);
     }
     if (!redo.empty()) {

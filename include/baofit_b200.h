@@ -258,7 +258,9 @@ int bf_chi2_batch(bf_ctx *ctx, const bf_model *model, const bf_data *data,
                   double *chi2, int *status);
 
 /* Same two operations on buffers that already live in device memory of the context's GPU
- * (device addresses passed as plain pointers); asynchronous on the context's stream. */
+ * (device addresses passed as plain pointers); asynchronous on the context's stream for the r-space and
+ * k-space models (which k-space chain runs is decided on the device). The FFT model still reads the key flag of a
+ * batch back on the host before it builds its per-key tables, i.e. its _dev calls wait for the GPU once. */
 int bf_eval_batch_dev(bf_ctx *ctx, const bf_model *model, const bf_data *data,
                       const double *d_params, int B, double *d_pred, int ldp, int *d_status);
 int bf_chi2_batch_dev(bf_ctx *ctx, const bf_model *model, const bf_data *data,
