@@ -425,13 +425,19 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
     const double tScan0 = nowSeconds();
     std::vector<likely::NewtonFit> bestFit(1, likely::NewtonFit(base));
     likely::runLockStep(bestFit, [&fitter](std::vector<likely::Parameters> const &pts, std::vector<double> &f) { fitter.evaluateBatch(pts, f); });
+    const double tScan1a = nowSeconds();
     const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
-    std::vector<likely::LMFit> fits;
-    std::vector<likely::Parameters> starts;
-    fits.reserve(count);
-    for (long g = first; g < first + count; ++g) {
-        likely::FitParameters p = base;
-        long rem = g;
+    // (built on all host threads: a FitParameters copy is 37 heap-allocated names and two binning vectors, 2100 of them
+    // were 5 ms of a 40 ms scan)
+    std::vector<likely::LMFit> fits((size_t)count);
+    std::vector<likely::Parameters> starts((size_t)count);
+    likely::FitParameters lean = base;
+    for (auto &q : lean) q.binning.clear();  // a grid fit has no use for the axes
+    const bool traceFirst = std::getenv("BAOFIT_VERBOSE_FITS") && std::atoi(std::getenv("BAOFIT_VERBOSE_FITS")) > 1;
+#pragma omp parallel for schedule(static) if (count >= 256)
+    for (long k = 0; k < count; ++k) {
+        likely::FitParameters p = lean;
+        long rem = first + k;
         for (int a = (int)axes.size() - 1; a >= 0; --a) {
             int nb = (int)base[axes[a]].binning.size();
             int ib = (int)(rem % nb);
@@ -441,11 +447,11 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
         }
         // each grid fit starts from the model's initial configuration, not from the best fit
         // (CorrelationAnalyzer.cc:591)
-        fits.push_back(likely::LMFit(p, cs, ps));
-        if (g == first && std::getenv("BAOFIT_VERBOSE_FITS") && std::atoi(std::getenv("BAOFIT_VERBOSE_FITS")) > 1) fits.back().debug = true;
+        fits[k] = likely::LMFit(p, cs, ps);
+        if (k == 0 && traceFirst) fits[k].debug = true;
         likely::Parameters st;
         for (auto const &q : p) st.push_back(q.value);
-        starts.push_back(st);
+        starts[k] = st;
     }
     const double tScan1 = nowSeconds();
     fitter.runLockStepLM(fits);
@@ -455,8 +461,9 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
     std::vector<likely::FunctionMinimumPtr> results(count);
     std::vector<likely::NewtonFit> redo;
     std::vector<long> redoIdx;
+#pragma omp parallel for schedule(static) if (count >= 256)
+    for (long k = 0; k < count; ++k) results[k] = fits[k].result();
     for (long k = 0; k < count; ++k) {
-        results[k] = fits[k].result();
         if (results[k]->status != likely::FunctionMinimum::OK) {
             // ... from where LM stopped when that point is usable (it is usually close to the minimum, only not
             // certified), from the initial configuration otherwise
@@ -488,7 +495,8 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
                 if (fp.floating) std::fprintf(stderr, " %s=%.6g", fp.name.c_str(), fp.value);
             std::fprintf(stderr, "\n");
         }
-        std::fprintf(stderr, "parameterScan: %ld grid fits, %zu handed to the Newton driver, %ld LM evaluations\n", count, redo.size(), nev);
+        std::fprintf(stderr, "parameterScan: %ld grid fits, %zu handed to the Newton driver, %ld LM evaluations; unconstrained fit %.4f s, "
+                             "fit set-up %.4f s, lock-step LM %.4f s\n", count, redo.size(), nev, tScan1a - tScan0, tScan1 - tScan1a, tScan2 - tScan1);
     }
     if (!redo.empty()) {
         long rounds = 0, points = 0;
@@ -730,7 +738,12 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
                       std::vector<int> &outStatus) {
         likely::FitParameters start = _model->getFitParameters();
         if (!config.empty()) likely::modifyFitParameters(start, config);
-        std::vector<likely::LMFit> fits((size_t)count, likely::LMFit(start, cs, ps));
+        std::vector<likely::LMFit> fits((size_t)count);
+        {
+            const likely::LMFit proto(start, cs, ps);
+#pragma omp parallel for schedule(static) if (count >= 256)
+            for (long t = 0; t < count; ++t) fits[t] = proto;
+        }
         double t0 = nowSeconds();
         fitter.runLockStepLM(fits, toys, &toyOfFit);
         double tLM = nowSeconds();
@@ -738,10 +751,10 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
         // toys whose LM fit did not converge cleanly are refitted with the Newton driver
         std::vector<likely::NewtonFit> redo;
         std::vector<int> redoToy;
-        for (long t = 0; t < count; ++t) {
-            results[t] = fits[t].result();
+#pragma omp parallel for schedule(static) if (count >= 256)
+        for (long t = 0; t < count; ++t) results[t] = fits[t].result();
+        for (long t = 0; t < count; ++t)
             if (results[t]->status != likely::FunctionMinimum::OK) { redo.push_back(likely::NewtonFit(start)); redoToy.push_back((int)t); }
-        }
         std::vector<likely::Parameters> points;
         std::vector<int> toyIndex;
         std::vector<double> values;

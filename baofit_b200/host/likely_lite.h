@@ -127,6 +127,7 @@ void priorDerivatives(FitParameter const &p, double x, double &value, double &gr
 class LMFit {
 public:
     LMFit(FitParameters const &params, double chi2Scale = 1.0, double priorScale = 1.0);
+    LMFit() : _stage(Done), _n(0), _cs(1.0), _ps(1.0) {}  // placeholder to be assigned (fits of a scan are built on all host threads)
     bool done() const { return _stage == Done; }
     bool wantsJacobian() const { return _stage == Jacobian; }
     int groupSize() const { return 2 * _n + 1; }
