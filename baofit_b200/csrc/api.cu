@@ -50,6 +50,7 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
         BF_FAIL(BF_ERR_ANALYSIS, std::string("bf_ctx_create: ") + cudaGetErrorString(e));
     }
     c->sm_count = prop.multiProcessorCount;
+    c->no_graphs = std::getenv("BAOFIT_NO_GRAPHS") != nullptr;
     for (auto &sl : c->async_slot)
         if ((e = cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) {
@@ -68,6 +69,8 @@ extern "C" int bf_ctx_create(int device, bf_ctx **out) {
     return BF_OK;
 }
 
+static void purge_graphs(bf_ctx *ctx, unsigned long long model_serial, const void *data);
+
 extern "C" int bf_ctx_destroy(bf_ctx *c) {
     if (!c) return BF_OK;
     cudaSetDevice(c->device);
@@ -75,6 +78,7 @@ extern "C" int bf_ctx_destroy(bf_ctx *c) {
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     c->prof_pending.clear();
     if (c->ws) cudaFree(c->ws);
+    purge_graphs(c, 0, nullptr);
     if (c->io) cudaFree(c->io);
     if (c->stage) cudaFreeHost(c->stage);
     if (c->aux) cudaFree(c->aux);
@@ -248,6 +252,7 @@ extern "C" int bf_model_destroy(bf_model *m) {
     std::lock_guard<std::recursive_mutex> lock(m->ctx->api_mu);
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
+    purge_graphs(m->ctx, m->serial, nullptr);
     // the (model, data) plans built for this model die with it
     for (bf_data *d : m->ctx->live_data) {
         auto it = d->plans.find(m->serial);
@@ -580,6 +585,7 @@ extern "C" int bf_data_destroy(bf_data *d) {
         auto &live = d->ctx->live_data;
         live.erase(std::remove(live.begin(), live.end(), d), live.end());
     }
+    purge_graphs(d->ctx, 0, d);
     if (d->expanded) bf_data_destroy(d->expanded);
     for (void *p : d->allocs) cudaFree(p);
     for (auto &kv : d->plans)
@@ -1236,6 +1242,8 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 host_shared = true;
                 host_current = m->h_key_valid;
                 for (int k = 0; k < 32 && host_current; ++k) host_current = hk[k] == m->h_key[k];
+                std::memcpy(ctx->last_hk, hk, sizeof(hk));
+                ctx->last_host_current = host_current;
             }
             if (!host_current) {
                 BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
@@ -1713,6 +1721,19 @@ extern "C" int bf_chi2_batch_dev(bf_ctx *ctx, const bf_model *m, const bf_data *
     return run_device(ctx, m, d, d_params, B, OUT_CHI2, d_chi2, 0, d_override, d_status);
 }
 
+// graphs of small-call kernel chains hold device pointers of a model and a data set: dropped with either
+// (model_serial = 0 and data = null: drop all)
+static void purge_graphs(bf_ctx *ctx, unsigned long long model_serial, const void *data) {
+    for (auto it = ctx->graphs.begin(); it != ctx->graphs.end();) {
+        const bool hit = (!model_serial && !data) || (model_serial && it->first.model_serial == model_serial) || (data && it->first.data == data);
+        if (hit) {
+            if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+            it = ctx->graphs.erase(it);
+        } else
+            ++it;
+    }
+}
+
 // kspace_key_check_kernel on the host, for host-buffer calls small enough that looking at the parameters costs less than
 // the launches it saves: true when every vector carries the same key parameters (same order and comparison as the kernel).
 static bool host_key_check(const DevModel &m, const double *params, int B, KeyHint *hint, const double *steps) {
@@ -1783,11 +1804,71 @@ static int run_host(bf_ctx *ctx, const bf_model *m, const bf_data *d, const doub
     if (staged && ctx->stage) {
         std::memcpy(ctx->stage, params, nb_params);
         BF_CUDA_OK(cudaMemcpyAsync(d_params, ctx->stage, nb_params, cudaMemcpyHostToDevice, s));
-        {
-            KeyHintScope hs(ctx, m->dev, params, B);
-            rc = run_device(ctx, m, d, d_params, B, what, d_out, B, nullptr, d_st);
+        // The kernel chain of a small call is a fixed function of (model, data, B, buffers) once the host has established that
+        // the vectors share their key and that the device tables are current for it (KeyHint): such a call is seen once, then
+        // captured into a CUDA graph on its second occurrence and replayed from the third on -- one launch instead of six.
+        // (Repeated small calls are what a Minuit-style fit makes: B = 1, 2 n + 1, a handful of line-search points.)
+        KeyHint hint;
+        const bool hinted = host_key_check(m->dev, params, B, &hint, nullptr);
+        const bool graphable = B <= bf_ctx::kGraphMaxB && !ctx->profiling && !ctx->no_graphs && m->dev.kind != BF_MODEL_KSPACE_FFT &&
+                               d->binning_type != BF_BINNING_MULTIPOLE && (m->dev.kind != BF_MODEL_KSPACE || hinted);
+        bf_ctx::GraphEntry *ge = nullptr;
+        const bf_ctx::GraphKey key{m->serial, (const void *)d, B, ctx->io, ctx->ws, ctx->ws_bytes, ctx->chi2_part};
+        if (graphable) {
+            if (ctx->graphs.size() >= 64 && !ctx->graphs.count(key)) purge_graphs(ctx, 0, nullptr);  // bounded cache
+            ge = &ctx->graphs[key];
+            bool current = true;  // k-space: the tables on the device must be those the chain was captured for
+            if (m->dev.kind == BF_MODEL_KSPACE) {
+                current = m->h_key_valid && ge->nkey == hint.nkey;
+                for (int k = 0; k < hint.nkey && current; ++k) current = hint.vals[k] == ge->hk[k];
+                for (int k = 0; k < 32 && current; ++k) current = ge->hk[k] == m->h_key[k];
+            }
+            if (ge->exec && current) {
+                BF_CUDA_OK(cudaGraphLaunch(ge->exec, s));
+                ctx->launches += ge->launches;
+                goto staged_download;
+            }
+            if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; ge->seen = 0; }
         }
-        if (rc) return rc;
+        {
+            // capture only what will run as the fixed chain: for the k-space model the host mirror must already hold this key
+            bool mirror_ok = m->dev.kind != BF_MODEL_KSPACE || m->h_key_valid;
+            for (int k = 0; k < hint.nkey && mirror_ok && m->dev.kind == BF_MODEL_KSPACE; ++k) mirror_ok = hint.vals[k] == m->h_key[k];
+            bool capturing = ge && ge->seen >= 1 && mirror_ok;
+            const long long l0 = ctx->launches;
+            if (capturing && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); capturing = false; ge->seen = -1000000; }
+            {
+                KeyHintScope hs(ctx, m->dev, params, B);
+                rc = run_device(ctx, m, d, d_params, B, what, d_out, B, nullptr, d_st);
+            }
+            if (capturing) {
+                cudaGraph_t graph = nullptr;
+                const cudaError_t e = cudaStreamEndCapture(s, &graph);
+                const bool same_buffers = ctx->io == key.io && ctx->ws == key.ws && ctx->ws_bytes == key.ws_bytes && ctx->chi2_part == key.chi2_part;
+                if (rc == BF_OK && e == cudaSuccess && graph && same_buffers && (m->dev.kind != BF_MODEL_KSPACE || ctx->last_host_current) &&
+                    cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {
+                    ge->launches = ctx->launches - l0;
+                    ge->nkey = hint.nkey;
+                    std::memcpy(ge->hk, ctx->last_hk, sizeof(ge->hk));
+                } else {
+                    cudaGetLastError();
+                    ge->exec = nullptr;
+                    ge->seen = -1000000;  // do not try again for this key
+                }
+                if (graph) cudaGraphDestroy(graph);
+                if (rc) return rc;
+                if (ge->exec) BF_CUDA_OK(cudaGraphLaunch(ge->exec, s));
+                else {  // nothing ran during the capture: run the chain the ordinary way
+                    m->h_key_valid = false;  // the host mirror may have been advanced by the pass that did not execute
+                    KeyHintScope hs(ctx, m->dev, params, B);
+                    if ((rc = run_device(ctx, m, d, d_params, B, what, d_out, B, nullptr, d_st))) return rc;
+                }
+            } else {
+                if (rc) return rc;
+                if (ge) ge->seen++;
+            }
+        }
+    staged_download:
         char *back = ctx->stage + kStageBytes;
         BF_CUDA_OK(cudaMemcpyAsync(back, d_out, nb_back, cudaMemcpyDeviceToHost, s));
         BF_CUDA_OK(cudaStreamSynchronize(s));

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/baofit_b200.h"
@@ -161,6 +162,31 @@ struct bf_ctx {
     } async_slot[2];
     long long submit_serial = 0;
     const KeyHint *key_hint = nullptr;  // set by the host-buffer entry point around its run_device call
+    // what run_chunk made of the last hinted k-space call (read by the graph cache of the host-buffer entry point)
+    double last_hk[32] = {};
+    bool last_host_current = false;
+    // CUDA graphs of the kernel chains of small host-buffer chi-square calls (run_host)
+    static constexpr int kGraphMaxB = 256;
+    struct GraphKey {
+        unsigned long long model_serial;
+        const void *data;
+        int B;
+        const void *io, *ws;
+        size_t ws_bytes;
+        const void *chi2_part;
+        bool operator<(const GraphKey &o) const {
+            return std::tie(model_serial, data, B, io, ws, ws_bytes, chi2_part) < std::tie(o.model_serial, o.data, o.B, o.io, o.ws, o.ws_bytes, o.chi2_part);
+        }
+    };
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int seen = 0;
+        long long launches = 0;
+        int nkey = 0;
+        double hk[32] = {};
+    };
+    std::map<GraphKey, GraphEntry> graphs;
+    bool no_graphs = false;  // BAOFIT_NO_GRAPHS
     long long launches = 0;
     // growable workspaces (device)
     void *ws = nullptr;

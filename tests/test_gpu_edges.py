@@ -1,5 +1,7 @@
 """Edge cases of the C ABI on the GPU: ragged batch sizes, single vectors, out-of-range bins,
 argument errors. Every call goes through libbaofit_b200.so."""
+import os
+
 import numpy as np
 import pytest
 
@@ -266,3 +268,39 @@ def test_reference_mid_sweep_retransform_is_flagged_not_silently_different(ctx):
     assert np.all(stb[3:] == BF_STATUS_Z_RETRIGGER) and np.all(np.isnan(chi2b[3:]))
     gm.close(), gd.close()
     m.desc.dzmin = 0.5
+
+
+@pytest.mark.gpu
+def test_small_call_graphs_replay_the_same_answers(ctx):
+    """Small host-buffer chi2 calls (B <= 256) are captured into a CUDA graph on their second occurrence and replayed from
+    the third on, as long as the key parameters stay those the device tables were built for. Same answers as a context
+    that never uses graphs (BAOFIT_NO_GRAPHS), across a change of the key and back, for the k-space and r-space models."""
+    os.environ["BAOFIT_NO_GRAPHS"] = "1"
+    try:
+        plain = capi.Context(0)
+    finally:
+        os.environ.pop("BAOFIT_NO_GRAPHS", None)
+    rng = np.random.Generator(np.random.PCG64(77))
+    for m, d in (W.qso_kspace(), W.qso_rspace()):
+        gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
+        pm, pd_ = capi.Model(plain, m), capi.Data(plain, d)
+        kspace = "SigmaNL-perp" in m.names
+        for B in (1, 7):
+            batches = [m.random_batch(B, rng, sweep={"BAO alpha-parallel": (0.9, 1.1), "BAO alpha-perp": (0.9, 1.1)}) for _ in range(9)]
+            if kspace:
+                for q in (4, 5):  # another key for two calls, then back
+                    batches[q][:, m.index("SigmaNL-perp")] *= 1.07
+            l0 = ctx.launches
+            per_call = []
+            for p in batches:
+                before = ctx.launches
+                got, st = capi.chi2_batch(ctx, gm, gd, p)
+                per_call.append(ctx.launches - before)
+                want, wst = capi.chi2_batch(plain, pm, pd_, p)
+                assert np.array_equal(st, wst)
+                ok = wst == 0
+                assert np.max(np.abs(got[ok] - want[ok]) / np.abs(want[ok])) < 1e-13, (B, per_call)
+            # the launch counter keeps counting the kernels a replayed graph runs
+            assert per_call[-1] == per_call[2] and per_call[-1] > 0, per_call
+        gm.close(), gd.close(), pm.close(), pd_.close()
+    plain.close()

@@ -27,6 +27,15 @@ for name in ("qso_kspace", "qso_rspace"):
         for _ in range(reps):
             capi.chi2_batch(ctx, gm, gd, p)
         dt = (time.perf_counter() - t0) / reps
-        rows.append({"B": B, "us_per_call": dt * 1e6, "evals_per_s": B / dt})
+        # the same call on preallocated buffers through raw addresses (what a C caller pays: no numpy allocation / conversion per call)
+        pc = np.ascontiguousarray(p)
+        chi2, st = np.empty(B), np.empty(B, dtype=np.int32)
+        for _ in range(5):
+            capi.chi2_batch_raw(ctx, gm, gd, pc.ctypes.data, B, chi2.ctypes.data, st.ctypes.data)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            capi.chi2_batch_raw(ctx, gm, gd, pc.ctypes.data, B, chi2.ctypes.data, st.ctypes.data)
+        dt_raw = (time.perf_counter() - t0) / reps
+        rows.append({"B": B, "us_per_call": dt * 1e6, "us_per_call_raw_buffers": dt_raw * 1e6, "evals_per_s": B / dt})
     out[name] = rows
 print(json.dumps(out, indent=1))
