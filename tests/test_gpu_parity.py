@@ -451,7 +451,9 @@ gm, gd = capi.Model(ctx, m), capi.Data(ctx, d)
 ctx.set_profiling(True)
 chi2, st = capi.chi2_batch(ctx, gm, gd, p)
 names = sorted(ctx.get_profile())
-np.save(sys.argv[1], np.vstack([chi2, st]))
+# ragged batches: a last panel with fewer than 32 vectors, fewer panels than SMs, one panel more than SMs
+extra = [capi.chi2_batch(ctx, gm, gd, p[:n]) for n in (1031, 4737, 4801)]
+np.save(sys.argv[1], np.vstack([np.concatenate([chi2] + [e[0] for e in extra]), np.concatenate([st] + [e[1] for e in extra])]))
 print(json.dumps(names))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
@@ -467,10 +469,18 @@ print(json.dumps(names))
             out[mode] = (np.load(path), json.loads(r.stdout.strip().splitlines()[-1]))
     assert "fused_model_chi2_kernel" in out["fused"][1] and "fused_model_chi2_kernel" not in out["unfused"][1]
     (cf, sf), (cu, su) = out["fused"][0], out["unfused"][0]
+    assert cf.shape == (20000 + 1031 + 4737 + 4801,)
     assert np.array_equal(sf, su)
     ok = sf == 0
     assert ok.sum() > 15000 and np.all(np.isnan(cf[~ok]))
     assert rel_err(cf[ok], cu[ok]) < 1e-11
+    # a vector's chi2 does not depend on the batch it is evaluated in
+    at = 20000
+    for n in (1031, 4737, 4801):
+        sub = cf[at:at + n]
+        good = ok[:n]
+        assert np.array_equal(sub[good], cf[:n][good]), n
+        at += n
     m, d = W.qso_kspace()
     rng = np.random.Generator(np.random.PCG64(91))
     p = m.random_batch(20000, rng, sweep={"BAO alpha-parallel": (0.8, 1.3), "BAO alpha-perp": (0.6, 1.5), "delta-v": (-300, 300)})

@@ -27,6 +27,19 @@ def run(name, m, d, B, G=3):
 run("rspace", *W.qso_rspace(), 70)
 run("rspace-large-sorted", *W.qso_rspace(), 2100)
 run("kspace+dm+metals", *W.qso_kspace(), 70)
+run("kspace+dm+metals, fused kernel (TMEM-parked accumulators)", *W.qso_kspace(), 1100)
+# repeated small calls: graph capture + replay; probes with synthesised linear columns
+m9, d9 = W.dr9_kspace()
+gm, gd = capi.Model(ctx, m9), capi.Data(ctx, d9)
+p = m9.random_batch(3, rng)
+for _ in range(4):
+    capi.chi2_batch(ctx, gm, gd, p)
+steps = np.zeros_like(p)
+fl = [j for j in np.nonzero(m9.floating)[0] if not m9.names[j].startswith("BAO alpha")]
+steps[:, fl] = 0.01 * m9.errors[fl]
+capi.normal_probes(ctx, gm, gd, p, steps)
+print("graphs + linear probes ok")
+gm.close(), gd.close()
 m, d = W.qso_kspace(with_dist_matrix=False, with_metals=False)
 run("kspace plain", m, d, 9)
 fm, fc = W.dr11_auto_fft(ngrid=64, spacing=8., nbins=20)
