@@ -2288,9 +2288,15 @@ static int gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const d
     const bool no_lin = std::getenv("BAOFIT_NO_LINEAR_PROBES") != nullptr;  // A/B tests
     if (normal && !no_lin && d->binning_type != BF_BINNING_MULTIPOLE && m->dev.bb[BF_BB_DIST_ADD].enabled) {
         if ((rc = get_plan(m, d, &plan))) return rc;
-        if (plan->fold_ok && plan->fold_data_mode && plan->fold_case == 1 && plan->fold_ncls <= 16) {
-            const int nb1 = plan->fold_nb / plan->fold_ncls, base = m->dev.bb[BF_BB_DIST_ADD].idx_base;
-            for (int k = 0; k < nb1; ++k) lin[base + k] = k;
+        const DevBB &ba = m->dev.bb[BF_BB_DIST_ADD];
+        const int n_rp = (ba.rp_max - ba.rp_min) / ba.rp_step + 1;
+        if (plan->fold_ok && plan->fold_data_mode && plan->fold_ncls <= 16 &&
+            (plan->fold_case == 1 || (plan->fold_case == 2 && plan->fold_ncls == 1 && plan->fold_pmax < 16))) {
+            // case 1: one static column per coefficient (and redshift class); case 2 (velocity shift): the coefficient
+            // (z, p, t) is a combination of the static columns (z, m <= p, t) with weights C(p, m) v^(p - m) of the fit
+            const int ncoef = plan->fold_case == 1 ? plan->fold_nb / plan->fold_ncls : plan->fold_nz * n_rp * plan->fold_nrt;
+            const int base = ba.idx_base;
+            for (int k = 0; k < ncoef; ++k) lin[base + k] = k;
             for (int f = 0; f < nfit; ++f) {
                 int cnt = 0;
                 for (int j = 0; j < npar; ++j) cnt += steps[(size_t)f * npar + j] != 0.0 && lin[j] < 0;
@@ -2332,6 +2338,12 @@ static int gram_probes(bf_ctx *ctx, const bf_model *m, const bf_data *d, const d
             na.centres = d_c; na.steps = d_h; na.lin = d_lin;
             na.WA = plan->d_WA; na.lda = d->n_pad + plan->fold_kext; na.kleft = d->n_pad;
             na.nb1 = plan->fold_nb / plan->fold_ncls; na.ncls = plan->fold_ncls;
+            {
+                const DevBB &ba = m->dev.bb[BF_BB_DIST_ADD];
+                na.fold_case = plan->fold_case; na.pmax = plan->fold_pmax; na.nrt = plan->fold_nrt;
+                na.n_rp = (ba.rp_max - ba.rp_min) / ba.rp_step + 1; na.rp_min = ba.rp_min; na.rp_step = ba.rp_step;
+                na.idx_delta_v = m->dev.idx_delta_v; na.inv_r0 = ba.inv_r0; na.vfac = plan->d_vfac;
+            }
             na.zvals = plan->d_zvals; na.zc0 = plan->zc_trigger; na.zref = m->dev.zref; na.idx_gamma_bias = m->dev.idx_gamma_bias;
             na.out = d_gram; na.part = d_part;
             BF_KERNEL(ctx, "normal_probes_lin_kernel", launch_normal_probes_lin(s, na));

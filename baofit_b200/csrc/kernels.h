@@ -254,6 +254,11 @@ struct NormalLinArgs {
     const int *lin;                 // [npar] (device)
     const double *WA;               // [n_pad][lda], basis columns start at kleft
     int lda, kleft, nb1, ncls;
+    // fold_case 2 (velocity shift, fold_coef_kernel): coefficient (z, p, t) feeds the rows (z, m <= p, t) with C(p, m) v^(p-m),
+    // v = delta-v . vfac[zc0] / r0 of the fit's centre
+    int fold_case, pmax, nrt, n_rp, rp_min, rp_step, idx_delta_v;
+    double inv_r0;
+    const double *vfac;
     const double *zvals;            // [ncls] redshift of every class (single class: the class of the data bins)
     int zc0;                        // first class index into zvals when ncls == 1
     double zref;

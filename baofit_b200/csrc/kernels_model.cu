@@ -1059,26 +1059,53 @@ __global__ void __launch_bounds__(256) normal_probes_sum_kernel(const double *__
 }
 
 // normal_probes_kernel with the columns of linear parameters synthesised (struct NormalLinArgs)
+constexpr int kLinMaxTerms = 16;  // static columns one synthesised column is a combination of (redshift classes, or powers of v)
+
 __global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a) {
     extern __shared__ double lsm[];  // [kGramRows][R + n] as in normal_probes_kernel, then per-column metadata
     const int f = blockIdx.x, tid = threadIdx.x, n = a.n, R = n + 1, W = R + n, G = 2 * a.n_nl + 1;
-    double *scale = lsm + kGramRows * W;          // [n]   2 h_i for linear columns
-    int *kind = reinterpret_cast<int *>(scale + n);  // [n]   >= 0: coefficient index (linear), -1 - q: q-th non-linear probe
-    __shared__ double eb[16];
+    // column i of a linear parameter: scale_i * sum_q cw[i][q] * WA[row][kleft + cbase_i + q * cstride]
+    double *scale = lsm + kGramRows * W;                       // [n]   2 h_i for linear columns
+    double *cw = scale + n;                                    // [n][kLinMaxTerms]
+    int *kind = reinterpret_cast<int *>(cw + n * kLinMaxTerms);  // [n]   >= 0: linear, -1 - q: q-th non-linear probe
+    int *cbase = kind + n, *cnum = cbase + n;                  // [n] each
     const double *c = a.centres + (size_t)f * a.npar, *h = a.steps + (size_t)f * a.npar;
+    const int cstride = a.fold_case == 2 ? a.nrt : a.nb1;
     if (tid == 0) {
-        int col = 0, q = 0;
-        for (int j = 0; j < a.npar && col < n; ++j)
-            if (h[j] != 0.0) {
-                if (a.lin[j] >= 0) { kind[col] = a.lin[j]; scale[col] = 2.0 * h[j]; }
-                else { kind[col] = -1 - q; scale[col] = 0.0; ++q; }
-                ++col;
-            }
         const double gb = c[a.idx_gamma_bias];
+        double eb[kLinMaxTerms];
         for (int k = 0; k < a.ncls; ++k) {
             const double x = (1.0 + a.zvals[a.ncls == 1 ? a.zc0 : k]) / (1.0 + a.zref);
             eb[k] = gb == 0.0 ? 1.0 : pow(x, gb);  // as prep_kernel (AbsCorrelationModel.cc:159-161)
         }
+        // velocity shift of this fit's centre in units of r0 (fold_coef_kernel, case 2)
+        const double v = a.fold_case == 2 ? c[a.idx_delta_v] * a.vfac[a.zc0] * a.inv_r0 : 0.0;
+        int col = 0, q = 0;
+        for (int j = 0; j < a.npar && col < n; ++j)
+            if (h[j] != 0.0) {
+                const int k = a.lin[j];
+                if (k >= 0) {
+                    kind[col] = k;
+                    scale[col] = 2.0 * h[j];
+                    if (a.fold_case == 2) {
+                        // coefficient (zi, ip, t) feeds the rows (zi, m <= p, t) with C(p, m) v^(p - m)
+                        const int t = k % a.nrt, ip = (k / a.nrt) % a.n_rp, zi = k / (a.nrt * a.n_rp), p = a.rp_min + ip * a.rp_step;
+                        cbase[col] = zi * (a.pmax + 1) * a.nrt + t;
+                        cnum[col] = p + 1;
+                        for (int mm = 0; mm <= p; ++mm) {
+                            double binom = 1.0, vp = 1.0;
+                            for (int u = 0; u < mm; ++u) binom = binom * (p - u) / (u + 1);
+                            for (int u = 0; u < p - mm; ++u) vp *= v;
+                            cw[col * kLinMaxTerms + mm] = eb[0] * binom * vp;
+                        }
+                    } else {
+                        cbase[col] = k;
+                        cnum[col] = a.ncls;
+                        for (int u = 0; u < a.ncls; ++u) cw[col * kLinMaxTerms + u] = eb[u];
+                    }
+                } else { kind[col] = -1 - q; scale[col] = 0.0; cnum[col] = 0; cbase[col] = 0; ++q; }
+                ++col;
+            }
     }
     const int npairs = R * (R + 1) / 2 + n;
     double acc[6];
@@ -1109,9 +1136,10 @@ __global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a)
             else {
                 const int kd = kind[col - 1];
                 if (kd >= 0) {
-                    const double *wa = a.WA + (size_t)(r0 + r) * a.lda + a.kleft + kd;
+                    const double *wa = a.WA + (size_t)(r0 + r) * a.lda + a.kleft + cbase[col - 1];
+                    const double *w = cw + (col - 1) * kLinMaxTerms;
                     double v = 0.0;
-                    for (int k = 0; k < a.ncls; ++k) v = fma(eb[k], wa[k * a.nb1], v);
+                    for (int u = 0; u < cnum[col - 1]; ++u) v = fma(w[u], wa[u * cstride], v);
                     lsm[r * W + col] = scale[col - 1] * v;
                     lsm[r * W + R + col - 1] = 0.0;
                 } else {
@@ -1137,7 +1165,9 @@ __global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a)
 size_t normal_probes_part_doubles(int n, int nfit) { return (size_t)nfit * kProbeSplit * ((size_t)(n + 1) * (n + 2) / 2 + n); }
 
 void launch_normal_probes_lin(cudaStream_t s, const NormalLinArgs &a) {
-    const size_t smem = ((size_t)kGramRows * (2 * a.n + 1) + a.n) * sizeof(double) + (size_t)a.n * sizeof(int);
+    const size_t smem = ((size_t)kGramRows * (2 * a.n + 1) + a.n + (size_t)a.n * kLinMaxTerms) * sizeof(double) + (size_t)3 * a.n * sizeof(int);
+    static SmemOptIn opt;
+    opt.ensure(normal_probes_lin_kernel, smem);
     normal_probes_lin_kernel<<<dim3(a.nfit, kProbeSplit), 256, smem, s>>>(a);
     normal_probes_sum_kernel<<<a.nfit, 256, 0, s>>>(a.part, a.n, a.nfit, a.out);
 }
