@@ -6,6 +6,8 @@
 #include <string>
 
 #include "../../include/baofit_b200_host.h"
+#include <omp.h>
+
 #include "baofit_host.h"
 
 using namespace baofit;
@@ -35,6 +37,11 @@ extern "C" int bfh_set_device(int device) {
     BFH_TRY
     setDevice(device);
     BFH_CATCH
+}
+
+extern "C" int bfh_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
 }
 
 extern "C" int bfh_session_create(const char *ini_text, const char *base_dir, const char *extra_config, bfh_session **out) {

@@ -9,7 +9,7 @@ _BOUND = False
 BATCH_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)
 RESID_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)
 
-HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
+HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_session_create", "bfh_session_destroy", "bfh_npar", "bfh_ndata",
                 "bfh_param_name", "bfh_param_info", "bfh_kept_indices", "bfh_kept_coordinates", "bfh_data_vector", "bfh_set_distortion_matrix", "bfh_evaluate_batch",
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
@@ -85,6 +85,19 @@ def _p(a):
 
 def set_device(device):
     _check(lib().bfh_set_device(device))
+
+
+def set_num_threads(n=0):
+    """Host threads of the per-fit linear algebra (OpenMP); n <= 0 only queries. Returns the number in use."""
+    return int(lib().bfh_set_num_threads(int(n)))
+
+
+def share_host_cores():
+    """One process per GPU on one host: give this process its share of the cores. Launchers such as torchrun export
+    OMP_NUM_THREADS=1 for every rank, which leaves the per-fit solves of a scan on a single thread."""
+    import os
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return set_num_threads(max(1, (os.cpu_count() or 1) // max(1, local)))
 
 
 class Session:

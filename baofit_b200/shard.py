@@ -38,11 +38,24 @@ def gather_blocks(local, total, device=None):
     return np.concatenate(parts, axis=0)
 
 
+_cores_shared = False
+
+
+def _share_cores_once():
+    """Every rank takes cores / ranks-on-this-host OpenMP threads for its per-fit host work (see host_api.share_host_cores)."""
+    global _cores_shared
+    if not _cores_shared and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        from baofit_b200 import host_api
+        host_api.share_host_cores()
+    _cores_shared = True
+
+
 def scan_sharded(session, device=None):
     """CorrelationAnalyzer::parameterScan with the grid split over the ranks of the default
     process group; every rank returns the full surface (chi2[total], points[total, npar])."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    _share_cores_once()
     total = session.scan_size()
     first, count = shard_range(total, rank, world)
     part = session.parameter_scan(first, count)
@@ -57,6 +70,7 @@ def toymc_sharded(session, ntoys, seed=1966, device=None):
     generator keyed by the global toy index, so results do not depend on the number of ranks."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    _share_cores_once()
     first, count = shard_range(ntoys, rank, world)
     part = session.toymc(first, count, seed)
     packed = np.concatenate([part["chi2"][:, None], part["fitted"], part["status"][:, None].astype(np.float64)], axis=1)

@@ -20,6 +20,9 @@ typedef struct bfh_session bfh_session;
 const char *bfh_last_error(void);
 /* selects the GPU of this process (one process per GPU); call before the first session */
 int bfh_set_device(int device);
+/* Host threads of the per-fit linear algebra and of the fit set-up (OpenMP); n <= 0 only queries. Returns the number in use.
+ * One process per GPU on a shared host should take cores / processes (launchers such as torchrun export OMP_NUM_THREADS=1). */
+int bfh_set_num_threads(int n);
 
 /* Builds model + data + fitter from INI text (same keys as the reference's .ini files,
  * src/baofit.cc:46-300); relative paths are resolved against base_dir. extra_config is appended
