@@ -476,7 +476,7 @@ ScanResult CorrelationAnalyzer::parameterScan(AbsCorrelationDataPtr sample, long
             redo.push_back(likely::NewtonFit(p));
             // a refit that continues from LM's end point either certifies it within a few iterations or sits in a
             // flat valley that no iteration count certifies (most of the time of a k-space scan went there)
-            if (usable) redo.back().maxIterations = 20;
+            if (usable) redo.back().maxIterations = 10;
             redoIdx.push_back(k);
         }
     }
