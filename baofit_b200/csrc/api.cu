@@ -1001,8 +1001,51 @@ static int get_plan(const bf_model *m, const bf_data *dc, const bf_data::Plan **
             std::vector<double> waf((size_t)n_pad * ktot);
             gemm_fused_tile_A(wa.data(), n_pad, ktot, ktot, waf.data());
             if ((rc = upload(p.allocs, waf.data(), waf.size(), &p.d_WAf))) return rc;
-            if (ktot % 16 == 0 && n_pad % 64 == 0) {
-                gemm_fused_tile_A3(wa.data(), n_pad, ktot, ktot, waf.data());
+            if (ktot % 16 == 0 && n_pad == 448) {
+                // chi2 = || WA x ||^2 = || R x ||^2 with WA = Q R (Householder, Q orthonormal): R is upper trapezoidal, row i
+                // starts at column i, so the fused kernel can skip every DMMA fragment whose rows have not started yet at
+                // the K chunk it is working on -- 43 % of the tensor work of a 440 x 528 matrix. The row order of R is free
+                // (a permutation does not change the norm): fragment f (rows 8f .. 8f+7) goes to consumer warp f % 4, half
+                // (f / 4) % 2, slot f / 8, so that all warps and both halves fill up at the same pace.
+                static const bool no_tri = std::getenv("BAOFIT_FUSED_DENSE") != nullptr;  // A/B measurements
+                if (!no_tri && n <= ktot) {
+                    std::vector<double> R(wa.begin(), wa.begin() + (size_t)n * ktot), wrow(ktot), v(n);
+                    for (int j = 0; j < n; ++j) {
+                        double nrm = 0;
+                        for (int i = j; i < n; ++i) nrm += R[(size_t)i * ktot + j] * R[(size_t)i * ktot + j];
+                        nrm = std::sqrt(nrm);
+                        if (nrm == 0) continue;
+                        const double alpha = R[(size_t)j * ktot + j] > 0 ? -nrm : nrm;
+                        double vn2 = 0;
+                        for (int i = j; i < n; ++i) { v[i] = R[(size_t)i * ktot + j] - (i == j ? alpha : 0.0); vn2 += v[i] * v[i]; }
+                        if (vn2 == 0) continue;
+                        std::fill(wrow.begin() + j, wrow.end(), 0.0);
+                        for (int i = j; i < n; ++i) {
+                            const double vi = v[i];
+                            const double *row = &R[(size_t)i * ktot];
+                            for (int cidx = j; cidx < ktot; ++cidx) wrow[cidx] += vi * row[cidx];
+                        }
+                        const double s2 = 2.0 / vn2;
+                        for (int i = j; i < n; ++i) {
+                            const double f = s2 * v[i];
+                            double *row = &R[(size_t)i * ktot];
+                            for (int cidx = j; cidx < ktot; ++cidx) row[cidx] -= f * wrow[cidx];
+                        }
+                        R[(size_t)j * ktot + j] = alpha;
+                        for (int i = j + 1; i < n; ++i) R[(size_t)i * ktot + j] = 0.0;
+                    }
+                    std::vector<double> perm((size_t)n_pad * ktot, 0.0);
+                    for (int f = 0; f < n_pad / 8; ++f) {
+                        const int w_ = f % 4, h_ = (f / 4) % 2, mi = f / 8;
+                        for (int jr = 0; jr < 8; ++jr) {
+                            const int src = 8 * f + jr, dst = h_ * (n_pad / 2) + w_ * (n_pad / 8) + mi * 8 + jr;
+                            if (src < n) std::memcpy(&perm[(size_t)dst * ktot], &R[(size_t)src * ktot], sizeof(double) * ktot);
+                        }
+                    }
+                    gemm_fused_tile_A3(perm.data(), n_pad, ktot, ktot, waf.data());
+                    p.fused_tri = true;
+                } else
+                    gemm_fused_tile_A3(wa.data(), n_pad, ktot, ktot, waf.data());
                 if ((rc = upload(p.allocs, waf.data(), waf.size(), &p.d_WAf3))) return rc;
             }
         }
@@ -1419,7 +1462,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 fill_tab(plan->tab_grid, true, fu.pt);
                 fu.pT = w.pT; fu.S = w.S; fu.vfac = plan->d_vfac; fu.tabs = m->d_tabs_cache; fu.ldb = ldb; fu.B = B;
                 fu.zc_trigger = plan->zc_trigger;
-                fu.At = plan->d_WAf; fu.At3 = plan->d_WAf3; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
+                fu.At = plan->d_WAf; fu.At3 = plan->d_WAf3; fu.tri = plan->fused_tri ? 1 : 0; fu.M = d->n_pad; fu.kgrid = d->n_grid_pad; fu.K = d->n_grid_pad + plan->fold_kext;
                 fu.rows = w.XiU + (size_t)d->n_grid_pad * ldb;
                 fu.chi2 = chi2_dst; fu.status = w.status;
                 if (fused_chi2_supported(fu)) {

@@ -295,6 +295,7 @@ struct bf_data {
         double *d_WAt = nullptr;      // the same matrix in the stage layout of dgemm_chi2_fullm_kernel (n_pad <= 512)
         double *d_WAf = nullptr;      // the same matrix tiled [K/4][M][4] for fused_model_chi2_kernel
         double *d_WAf3 = nullptr;     // ... and in the streaming order of fused3_model_chi2_kernel (gemm_fused_tile_A3)
+        bool fused_tri = false;       // d_WAf3 holds the trapezoidal R factor of WA in interleaved fragment order (get_plan)
         std::vector<void *> allocs;
     };
     std::map<unsigned long long, Plan> plans;  // keyed by bf_model::serial (never by address: addresses are reused)

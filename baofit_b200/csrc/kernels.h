@@ -104,6 +104,8 @@ struct FusedArgs {
     int ldb, B, zc_trigger;
     const double *At;            // WA pre-tiled as [K/4][M][4] (gemm_fused_tile_A)
     const double *At3;           // WA in the streaming order of the TMEM-parking kernel (gemm_fused_tile_A3), or null
+    int tri;                     // At3 is the upper-trapezoidal R factor of WA, fragment f at (warp f % 4, half (f / 4) % 2, slot f / 8):
+                                 // fragments whose first row 8 f lies beyond the current K columns are skipped
     int M, K, kgrid;             // rows of WA; K = kgrid + kext; rows 0..kgrid-1 of the panel come from the model
     const double *rows;          // [kext][ldb] coefficient rows (fold_coef_kernel)
     double *chi2;

@@ -622,6 +622,26 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *gsrc, unsigne
                  : "memory");
 }
 
+// One visit of a consumer warp: 16 K-rows against the first NA row fragments of its half (NA x 4 column fragments per k-step).
+template <int NA, int MH>
+__device__ __forceinline__ void f3_visit(double (&acc)[56], const double *__restrict__ as, const double *__restrict__ bs) {
+    double bf_ = bs[0];
+#pragma unroll
+    for (int ks = 0; ks < F3_CH / 4; ++ks) {
+        double af[NA];
+#pragma unroll
+        for (int mi = 0; mi < NA; ++mi) af[mi] = as[(ks * MH + mi * 8) * 4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const double bcur = bf_;
+            const int nx = ks * 4 + ni + 1;  // next (k-step, column fragment), fetched before this group's DMMAs
+            if (nx < F3_CH) bf_ = bs[(nx >> 2) * 4 * F3_LDB + (nx & 3) * 8];
+#pragma unroll
+            for (int mi = 0; mi < NA; ++mi) dmma_f(acc[(mi * 4 + ni) * 2], acc[(mi * 4 + ni) * 2 + 1], af[mi], bcur);
+        }
+    }
+}
+
 template <int M, int NT>
 __global__ void __launch_bounds__((F3_CW + F3_P) * 32, 1) fused3_model_chi2_kernel(FusedArgs a) {
     BF_GATE(a.gate);
@@ -856,20 +876,20 @@ __global__ void __launch_bounds__((F3_CW + F3_P) * 32, 1) fused3_model_chi2_kern
                     mb_wait(full_a + 8 * sa, (g / F3_NSA) & 1);
                     const double *as = as0 + sa * (F3_CH * MH);
                     if (a.debug != 2) {
-                        double bf_ = bs[0];
-#pragma unroll
-                        for (int ks = 0; ks < F3_CH / 4; ++ks) {
-                            double af[MF];
-#pragma unroll
-                            for (int mi = 0; mi < MF; ++mi) af[mi] = as[(ks * MH + mi * 8) * 4];
-#pragma unroll
-                            for (int ni = 0; ni < 4; ++ni) {
-                                const double bcur = bf_;
-                                const int nx = ks * 4 + ni + 1;  // next (k-step, column fragment), fetched before this group's DMMAs
-                                if (nx < F3_CH) bf_ = bs[(nx >> 2) * 4 * F3_LDB + (nx & 3) * 8];
-#pragma unroll
-                                for (int mi = 0; mi < MF; ++mi) dmma_f(acc[(mi * 4 + ni) * 2], acc[(mi * 4 + ni) * 2 + 1], af[mi], bcur);
-                            }
+                        // trapezoidal left matrix: slot mi of this warp and half holds fragment f = 8 mi + 4 half + warp, whose rows
+                        // start at column 8 f: the visit runs the variant with as many slots as have started by its last column
+                        // (one jump per visit; predicated-off DMMAs would still cost their 16 issue cycles each)
+                        const int half_now = (c + visit) & 1, frag0 = 32 * half_now + 8 * cw, kend = c * F3_CH + F3_CH - 1;
+                        const int nact = a.tri ? min(MF, kend >= frag0 ? (kend - frag0) / 64 + 1 : 0) : MF;
+                        switch (nact) {
+                        case 7: f3_visit<7, MH>(acc, as, bs); break;
+                        case 6: f3_visit<6, MH>(acc, as, bs); break;
+                        case 5: f3_visit<5, MH>(acc, as, bs); break;
+                        case 4: f3_visit<4, MH>(acc, as, bs); break;
+                        case 3: f3_visit<3, MH>(acc, as, bs); break;
+                        case 2: f3_visit<2, MH>(acc, as, bs); break;
+                        case 1: f3_visit<1, MH>(acc, as, bs); break;
+                        default: break;
                         }
                     }
                     __syncwarp();
