@@ -192,8 +192,22 @@ def flops_per_eval(nd, ng, nr, nk):
             # work is one N_d x (N_g + 16) product plus the squares (fewer flops than the two-GEMM
             # form 2 N_d N_g + N_d^2 the survey counts; we report what is executed, unpadded)
             "dgemm_chi2_kernel[fused tail]": 2.0 * nd * (ng + 16) + 2.0 * nd,
-            # the same product inside the fused model + chi2 kernel (the model's own FP64 work is not counted)
-            "fused_model_chi2_kernel": 2.0 * nd * (ng + 16) + 2.0 * nd}
+            # the fused model + chi2 kernel multiplies by the upper-trapezoidal R factor of that matrix and skips the row fragments
+            # that have not started yet: executed DMMA flops per evaluation, counted as the kernel schedules them (visits of 16 K
+            # columns, fragment f = 8 slot + 4 half + warp starts at column 8 f; the model's own FP64 work is not counted)
+            "fused_model_chi2_kernel": fused_tensor_flops(ng + 16) + 2.0 * nd}
+
+
+def fused_tensor_flops(K):
+    total = 0
+    for c in range(K // 16):
+        kend = 16 * c + 15
+        for half in range(2):
+            for warp in range(4):
+                frag0 = 32 * half + 8 * warp
+                nact = min(7, (kend - frag0) // 64 + 1) if kend >= frag0 else 0
+                total += nact * 8 * 16 * 2  # rows x K columns x (multiply + add), per batch column
+    return float(total)
 
 
 def make_cpu_baseline(model, data):

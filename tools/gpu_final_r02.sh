@@ -14,3 +14,5 @@ CMD="python bench.py --steps 3 --warmup 3 --no-scan --no-cpu-baseline --no-fft"
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fused3_model_chi2_kernel' -s 4 -c 1 -f -o $OUT/prof_fused3_$TAG $CMD > $OUT/ncu_fused3_$TAG.log 2>&1
+echo "ncu fused3 exit $?"
