@@ -14,6 +14,10 @@
 namespace bf {
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
+bool pdl_enabled() {
+    static const bool on = std::getenv("BAOFIT_NO_PDL") == nullptr;
+    return on;
+}
 }  // namespace bf
 
 using namespace bf;
@@ -1222,7 +1226,7 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
     // coherence sort (chi2 only; outputs that are indexed by the original column stay unsorted)
     const bool sorted = what == OUT_CHI2 && !d_override && B >= 2048 && dm.kind != BF_MODEL_KSPACE_FFT;
     if (sorted) BF_KERNEL(ctx, "coherence_sort_kernels", launch_coherence_sort(s, dm, d_params, B, w.sort_hist, w.sort_base, w.rank));
-    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status, plan && plan->z_retrigger));
+    BF_KERNEL(ctx, "prep_kernel", launch_prep(s, dm, d_params, B, ldb, nz, d_zvals, sorted ? w.rank : nullptr, w.pT, w.S, w.status, plan && plan->z_retrigger, w.flag));
     double *chi2_dst = sorted ? w.chi2_sorted : d_out;
 
     // ---- k-space model: which chain runs is decided on the device (no host round trip inside a call) ----
@@ -1289,13 +1293,11 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
                 ctx->last_host_current = host_current;
             }
             if (!host_current) {
-                BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
                 BF_KERNEL(ctx, "kspace_key_check_kernel", launch_kspace_key_check(s, dm, w.pT, ldb, B, w.flag));
                 BF_KERNEL(ctx, "kspace_key_decide_kernel", launch_kspace_key_decide(s, w.flag, m->d_keystate, m->d_gate, ex));
                 const Gate rebuild{m->d_gate + 1, 1};
                 pa.G = w.Gb;
                 pa.gate = rebuild;
-                BF_CUDA_OK(cudaMemsetAsync(w.Gb, 0, (size_t)6 * dm.nk_pad * kPadN * sizeof(double), s));
                 BF_KERNEL(ctx, "kspace_basis_project_kernel", launch_kspace_basis_project(s, pa));
                 GemmArgs g{};
                 g.gate = rebuild;
@@ -1321,7 +1323,6 @@ int run_chunk(bf_ctx *ctx, const bf_model *m, const bf_data *d, const bf_data::P
         va.use_ztrig = d ? 0 : 1;
         va.ztrig = z_trigger_override;
         va.keyflag = w.flag; va.keys = w.fft_keys; va.c12 = w.fft_c12; va.cont = w.fft_cont; va.status = w.status;
-        BF_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(double), s));
         BF_KERNEL(ctx, "fft_vec_kernel", launch_fft_vec(s, va));
         BF_CUDA_OK(cudaMemcpyAsync(ctx->pinned_flag, w.flag, sizeof(double) * kFftKeyMax, cudaMemcpyDeviceToHost, s));
         BF_CUDA_OK(cudaStreamSynchronize(s));

@@ -1,6 +1,7 @@
 // Kernel argument blocks and launchers (implemented in kernels_model.cu / kernels_gemm.cu).
 #pragma once
 #include <atomic>
+#include <utility>
 #include "bf_internal.h"
 
 namespace bf {
@@ -21,6 +22,39 @@ struct SmemOptIn {
     }
 };
 
+
+// Programmatic dependent launch. A call is a chain of ~20 small dependent kernels on one stream, and a plain launch
+// boundary costs 3-4 us on a B200; with the stream-serialization attribute the next grid is set up while its predecessor
+// drains: 1.7 us per boundary (tools/pdl_probe.cu, profiles/pdl_probe_r02.json). EVERY kernel of the library starts with
+// pdl_sync() = griddepcontrol.wait: nothing of a kernel runs before all the work before it in the stream is complete and
+// visible, so the order of memory effects is that of plain launches. No kernel triggers its successor early
+// (griddepcontrol.launch_dependents): the probe shows no gain over the implicit trigger at grid completion, and parked
+// CTAs of a successor next to a running multi-wave grid cost the FFT model and the lock-step scans 25 % when it was tried.
+// BAOFIT_NO_PDL=1 switches the attribute off (A/B measurements).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+bool pdl_enabled();  // api.cu
+
+struct Launch {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    Launch(dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    }
+    template <class... K, class... A> void operator()(void (*kernel)(K...), A &&...args) {
+        cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+    }
+};
 
 // Device-side predication: a kernel whose gate is set returns at once unless *flag == want. The decision which of the
 // two k-space chains runs (shared basis tables / per-vector transforms) and whether the basis tables must be rebuilt is
@@ -167,7 +201,8 @@ struct GemmArgs {
 };
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
-                 const double *zvals, const int *rank, double *pT, double *S, int *status, bool z_retrigger = false);
+                 const double *zvals, const int *rank, double *pT, double *S, int *status, bool z_retrigger,
+                 double *key_flag /* key_flag[0] = 0: the key checks that follow raise it */);
 // counting sort of the vectors on their quantised dilation parameters; hist/base: 2048 ints each
 void launch_coherence_sort(cudaStream_t s, const DevModel &m, const double *params, int B, int *hist, int *base, int *rank);
 void launch_unpermute(cudaStream_t s, int B, const int *rank, const double *chi2_sorted, const int *status_sorted,

@@ -119,6 +119,7 @@ __device__ __forceinline__ double metal_rows_apply(const double *__restrict__ mx
 // evolution of beta and the radiation term, which r-space models always carry.
 template <bool kLean, int kPart, bool kRS = false>
 __global__ void __launch_bounds__(kPart == 1 ? 512 : 256, 2) kspace_fast_eval_kernel(FastArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
@@ -312,6 +313,7 @@ constexpr int kMetalWin = 8, kMetalStages = 8;
 
 template <int NT>
 __global__ void __launch_bounds__(256, 3) metal_add_kernel(FastArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     __shared__ __align__(128) double win[kMetalStages][kMetalWin * NT];
     __shared__ __align__(8) unsigned long long full_bar[kMetalStages], empty_bar[kMetalStages];
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(256, 3) metal_add_kernel(FastArgs a) {
 // Distortion-matrix tail on the data bins: Z = Y (1 + dist mul) + dist add * evol - d and the
 // dilation-limit check of the data bin itself (BaoKSpaceCorrelationModel.cc:420-427, :529-535).
 __global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     const DevModel &m = a.m;
     const PointTab &pt = a.pt;
@@ -519,6 +522,7 @@ __global__ void __launch_bounds__(256, 2) fast_post_kernel(FastArgs a) {
 //   case 2 (velocity shift):    rP factors are (u_i + v_b)^p with v_b = dpi_b / r0, expanded
 //           binomially: row (z, m, t) = eb * sum_{p >= m} C(p,m) c_{z,p,t} v_b^(p-m)
 __global__ void __launch_bounds__(128) fold_coef_kernel(FoldArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(128) fold_coef_kernel(FoldArgs a) {
     if (st) atomicOr(a.status + b, st);
 }
 
-void launch_fold_coef(cudaStream_t s, const FoldArgs &a) { fold_coef_kernel<<<(a.B + 127) / 128, 128, 0, s>>>(a); }
+void launch_fold_coef(cudaStream_t s, const FoldArgs &a) { Launch((a.B + 127) / 128, 128, 0, s)(fold_coef_kernel, a); }
 
 static void pick_grid(FastArgs &a, int sm_count, dim3 &grid, int threads = 256) {
     int bx = (a.B + threads - 1) / threads;
@@ -605,25 +609,25 @@ void launch_kspace_fast_eval(cudaStream_t s, FastArgs &a, int sm_count, int part
         // the cosmology pass is bound by shared-memory wavefronts and its 72 KB table allows 3 CTAs per SM at most:
         // 512 threads at 64 registers (2 CTAs, 32 warps per SM instead of 24) measured 0.344 -> 0.332 ms
         pick_grid(a, sm_count, grid, 512);
-        if (a.rspace) kspace_fast_eval_kernel<true, 1, true><<<grid, 512, smem, s>>>(a);
-        else kspace_fast_eval_kernel<true, 1><<<grid, 512, smem, s>>>(a);
+        if (a.rspace) Launch(grid, 512, smem, s)(kspace_fast_eval_kernel<true, 1, true>, a);
+        else Launch(grid, 512, smem, s)(kspace_fast_eval_kernel<true, 1>, a);
     }
     else if (part == 2) {
         const int sa = a.mode == 1 ? BF_BB_DM_DIST_ADD : BF_BB_DIST_ADD, sm = a.mode == 1 ? BF_BB_DM_DIST_MUL : BF_BB_DIST_MUL;
         const bool metals_only = a.m.metal_kind == BF_METAL_CROSS_BICUBIC && a.nz == 1 && !a.m.bb[sa].enabled &&
                                  !a.m.bb[sm].enabled && !(a.mode == 0 && (a.dsub || a.dov)) &&
                                  (a.pt.mx_nt == 12 || a.pt.mx_nt == 15);
-        if (metals_only && a.pt.mx_nt == 12) metal_add_kernel<12><<<grid, 256, 0, s>>>(a);
-        else if (metals_only) metal_add_kernel<15><<<grid, 256, 0, s>>>(a);
-        else kspace_fast_eval_kernel<true, 2><<<grid, 256, 0, s>>>(a);
+        if (metals_only && a.pt.mx_nt == 12) Launch(grid, 256, 0, s)(metal_add_kernel<12>, a);
+        else if (metals_only) Launch(grid, 256, 0, s)(metal_add_kernel<15>, a);
+        else Launch(grid, 256, 0, s)(kspace_fast_eval_kernel<true, 2>, a);
     }
-    else kspace_fast_eval_kernel<false, 0><<<grid, 256, smem, s>>>(a);
+    else Launch(grid, 256, smem, s)(kspace_fast_eval_kernel<false, 0>, a);
 }
 
 void launch_fast_post(cudaStream_t s, FastArgs &a, int sm_count) {
     dim3 grid;
     pick_grid(a, sm_count, grid);
-    fast_post_kernel<<<grid, 256, 0, s>>>(a);
+    Launch(grid, 256, 0, s)(fast_post_kernel, a);
 }
 
 }  // namespace bf

@@ -74,6 +74,7 @@ __device__ __forceinline__ double fft_nl_correction(unsigned flags, const FftKey
 // per key: H[comp][j][my][mx] = sum_mz w_mz K(k,mu) P_comp(k) mu^2j
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) fft_hsum_kernel(DevModel m, FftKeyState ks, double *__restrict__ H) {
+    pdl_sync();
     const DevFft &f = m.fft;
     const int mx = blockIdx.x * blockDim.x + threadIdx.x, my = blockIdx.y, comp = blockIdx.z;
     if (mx >= f.mx) return;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(128) fft_hsum_kernel(DevModel m, FftKeyState k
 // T[comp*3+j][my][ix] = norm w_my sum_mx w_mx cos(2 pi mx ix / nx) H[comp*3+j][my][mx], stored in the stage
 // layout of fft_plane_kernel: [comp][ctile][chunk][j][kr][kFftLdT]; rows my >= My and columns >= npx are zero
 __global__ void __launch_bounds__(128) fft_xtrans_kernel(DevModel m, const double *__restrict__ H, double *__restrict__ T) {
+    pdl_sync();
     const DevFft &f = m.fft;
     const int ixl = threadIdx.x, ctile = blockIdx.x, my = blockIdx.y, t = blockIdx.z;
     if (ixl >= kFftLdT) return;
@@ -130,8 +132,8 @@ __global__ void __launch_bounds__(128) fft_xtrans_kernel(DevModel m, const doubl
 
 void launch_fft_tables(cudaStream_t s, const DevModel &m, const FftKeyState &k, double *H, double *T) {
     const DevFft &f = m.fft;
-    fft_hsum_kernel<<<dim3((f.mx + 127) / 128, f.my, 2), 128, 0, s>>>(m, k, H);
-    fft_xtrans_kernel<<<dim3(f.ctiles, f.my_pad, 6), 128, 0, s>>>(m, H, T);
+    Launch(dim3((f.mx + 127) / 128, f.my, 2), 128, 0, s)(fft_hsum_kernel, m, k, H);
+    Launch(dim3(f.ctiles, f.my_pad, 6), 128, 0, s)(fft_xtrans_kernel, m, H, T);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -162,6 +164,7 @@ __device__ __forceinline__ double fft_trigger_z(const FftVecArgs &a, const doubl
 constexpr int kFftVecRows = 16;  // k_par rows per thread of fft_vec_kernel
 
 __global__ void __launch_bounds__(128) fft_vec_kernel(FftVecArgs a) {
+    pdl_sync();
     const DevModel &m = a.m;
     const DevFft &f = m.fft;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(128) fft_vec_kernel(FftVecArgs a) {
 
 void launch_fft_vec(cudaStream_t s, const FftVecArgs &a) {
     dim3 grid((a.B + 127) / 128, (a.m.fft.my_pad + kFftVecRows - 1) / kFftVecRows);
-    fft_vec_kernel<<<grid, 128, 0, s>>>(a);
+    Launch(grid, 128, 0, s)(fft_vec_kernel, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -306,6 +309,7 @@ struct FftPlaneArgs {
 // NCF (column fragments per tile) is a template parameter: all tile index arithmetic is constant.
 template <int NCF>
 __global__ void __launch_bounds__(PV * 3 * 32, 1) fft_plane_kernel(FftPlaneArgs a) {
+    pdl_sync();
     extern __shared__ __align__(128) double psm[];
     const DevFft &f = a.f;
     constexpr int NCOLS = NCF * 8, NRF = 9;
@@ -483,7 +487,7 @@ template <int NCF>
 static void launch_fft_planes_t(cudaStream_t s, const FftPlaneArgs &a, dim3 grid, int threads, size_t smem) {
     static SmemOptIn opt;
     opt.ensure(fft_plane_kernel<NCF>, (size_t)226 * 1024);
-    fft_plane_kernel<NCF><<<grid, threads, smem, s>>>(a);
+    Launch(grid, threads, smem, s)(fft_plane_kernel<NCF>, a);
 }
 
 void launch_fft_planes(cudaStream_t s, const DevModel &m, const double *T, const double *c12, const double *cont,
@@ -545,6 +549,7 @@ constexpr int kEvalVecPerBlock = 8;    // one warp per parameter vector
 }  // namespace
 
 __global__ void __launch_bounds__(256, 4) fft_eval_kernel(FftEvalArgs a) {
+    pdl_sync();
     const DevModel &m = a.m;
     const DevFft &f = m.fft;
     // One warp per parameter vector, lanes = 32 consecutive bins: consecutive bins are neighbours in r_perp, so the
@@ -610,6 +615,7 @@ __global__ void __launch_bounds__(256, 4) fft_eval_kernel(FftEvalArgs a) {
 // instead of L2 round trips. fft_eval_kernel was bound by load latency (1.14 ms for 18 944 vectors x 1515 bins at 37 %
 // occupancy, its 8 vectors per CTA sweep 660 KB of planes through L1); here each plane byte crosses L2 once.
 __global__ void __launch_bounds__(256, 2) fft_eval_smem_kernel(FftEvalArgs a) {
+    pdl_sync();
     extern __shared__ __align__(128) double esm[];
     __shared__ __align__(8) unsigned long long bar;
     const DevModel &m = a.m;
@@ -680,11 +686,11 @@ void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a) {
     if (!no_smem && smem <= 110 * 1024 && smem % 16 == 0 && a.B >= 64) {
         static SmemOptIn opt;
         opt.ensure(fft_eval_smem_kernel, smem);
-        fft_eval_smem_kernel<<<a.B, 256, smem, s>>>(a);
+        Launch(a.B, 256, smem, s)(fft_eval_smem_kernel, a);
         return;
     }
     dim3 grid((a.B + kEvalVecPerBlock - 1) / kEvalVecPerBlock, (a.npts + kEvalBinsPerBlock - 1) / kEvalBinsPerBlock);
-    fft_eval_kernel<<<grid, 256, 0, s>>>(a);
+    Launch(grid, 256, 0, s)(fft_eval_kernel, a);
 }
 
 }  // namespace bf

@@ -143,6 +143,7 @@ __device__ __forceinline__ double metal_patch(const double *__restrict__ base, c
 
 template <int M, int NT>
 __global__ void __launch_bounds__((FU_CW + FU_P) * 32, 1) fused_model_chi2_kernel(FusedArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char fsm_raw[];
     const DevModel &m = a.m;
@@ -644,6 +645,7 @@ __device__ __forceinline__ void f3_visit(double (&acc)[56], const double *__rest
 
 template <int M, int NT>
 __global__ void __launch_bounds__((F3_CW + F3_P) * 32, 1) fused3_model_chi2_kernel(FusedArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char fsm_raw[];
     const DevModel &m = a.m;
@@ -998,10 +1000,10 @@ void launch_fused_model_chi2(cudaStream_t s, const FusedArgs &a_in, int sm_count
         static SmemOptIn o0, o12;
         if (a.m.metal_kind == BF_METAL_CROSS_BICUBIC) {
             o12.ensure(fused3_model_chi2_kernel<M, 12>, smem);
-            fused3_model_chi2_kernel<M, 12><<<grid, threads, smem, s>>>(a);
+            Launch(grid, threads, smem, s)(fused3_model_chi2_kernel<M, 12>, a);
         } else {
             o0.ensure(fused3_model_chi2_kernel<M, 0>, smem);
-            fused3_model_chi2_kernel<M, 0><<<grid, threads, smem, s>>>(a);
+            Launch(grid, threads, smem, s)(fused3_model_chi2_kernel<M, 0>, a);
         }
         return;
     }
@@ -1011,10 +1013,10 @@ void launch_fused_model_chi2(cudaStream_t s, const FusedArgs &a_in, int sm_count
     static SmemOptIn opt0, opt12;
     if (a.m.metal_kind == BF_METAL_CROSS_BICUBIC) {
         opt12.ensure(fused_model_chi2_kernel<M, 12>, smem);
-        fused_model_chi2_kernel<M, 12><<<grid, threads, smem, s>>>(a);
+        Launch(grid, threads, smem, s)(fused_model_chi2_kernel<M, 12>, a);
     } else {
         opt0.ensure(fused_model_chi2_kernel<M, 0>, smem);
-        fused_model_chi2_kernel<M, 0><<<grid, threads, smem, s>>>(a);
+        Launch(grid, threads, smem, s)(fused_model_chi2_kernel<M, 0>, a);
     }
 }
 

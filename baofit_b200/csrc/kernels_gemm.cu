@@ -87,6 +87,7 @@ __device__ __forceinline__ void compute_stage(const double *As, const double *Bs
 // ---- plain store epilogue: C = A.B --------------------------------------------------------
 template <int TB>
 __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
+    pdl_sync();
     BF_GATE(g.gate);
     extern __shared__ __align__(16) double smem[];
     constexpr int FR = TB / 16, A_STAGE = Tile<TB>::A_STAGE, B_STAGE = Tile<TB>::B_STAGE;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(128) dgemm_store_kernel(GemmArgs g) {
 // CTA: registers -> warp shuffles -> one shared-memory exchange between the two row-warps.
 template <int TB>
 __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
+    pdl_sync();
     BF_GATE(g.gate);
     extern __shared__ __align__(16) double smem[];
     constexpr int FR = TB / 16, A_STAGE = Tile<TB>::A_STAGE, B_STAGE = Tile<TB>::B_STAGE;
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(128) dgemm_chi2_kernel(GemmArgs g) {
 // chi2[n] = sum over row tiles of the partial sums, in tile order (deterministic)
 __global__ void chi2_part_sum_kernel(const double *__restrict__ part, int part_ld, int tiles, int N,
                                      const int *__restrict__ status, double *__restrict__ chi2, Gate gate) {
+    pdl_sync();
     BF_GATE(gate);
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -288,6 +291,7 @@ __device__ __forceinline__ void f_tma_g2s(void *smem_dst, const void *gsrc, unsi
 }  // namespace
 
 __global__ void __launch_bounds__(kFullmMaxM, 1) dgemm_chi2_fullm_kernel(GemmArgs g) {
+    pdl_sync();
     BF_GATE(g.gate);
     extern __shared__ __align__(128) double fsm[];
     const int M = g.M, K = g.K;
@@ -403,7 +407,7 @@ void launch_gemm_chi2_fullm(cudaStream_t s, const GemmArgs &g, int sm_count) {
     static SmemOptIn opt;
     opt.ensure(dgemm_chi2_fullm_kernel, smem);
     const int ntiles = (g.N + FBN - 1) / FBN;
-    dgemm_chi2_fullm_kernel<<<std::min(ntiles, sm_count), g.M, smem, s>>>(g);
+    Launch(std::min(ntiles, sm_count), g.M, smem, s)(dgemm_chi2_fullm_kernel, g);
 }
 
 // ---- toy-MC noise ------------------------------------------------------------------------------
@@ -429,6 +433,7 @@ __device__ __forceinline__ double counter_normal(unsigned long long seed, unsign
 // Y = L . G through dgemm_store_kernel (k-tiles above the diagonal skipped), then a tiled transpose into the
 // toy-major table the refits gather from.
 __global__ void toy_deviates_kernel(int n, unsigned long long seed, long long first_toy, int ntoy, int ldg, double *__restrict__ G) {
+    pdl_sync();
     const int t = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (t >= ldg) return;
     G[(size_t)j * ldg + t] = (j < n && t < ntoy) ? counter_normal(seed, (unsigned long long)(first_toy + t), (unsigned)j) : 0.0;
@@ -436,6 +441,7 @@ __global__ void toy_deviates_kernel(int n, unsigned long long seed, long long fi
 
 __global__ void toy_finish_kernel(const double *__restrict__ Y, int n, int ntoy, int ldg, const double *__restrict__ truth, double scale,
                                   double *__restrict__ out) {
+    pdl_sync();
     __shared__ double tile[32][33];
     const int t0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -458,12 +464,12 @@ void launch_gemm_store(cudaStream_t s, const GemmArgs &g, int batch, int sm_coun
     static SmemOptIn opt, opt32;
     if (use_small_tiles(g.M, g.N, batch, sm_count)) {
         opt32.ensure(dgemm_store_kernel<32>, (size_t)Tile<32>::SMEM);
-        dgemm_store_kernel<32><<<dim3((g.N + 31) / 32, g.M / 32, batch), 128, Tile<32>::SMEM, s>>>(g);
+        Launch(dim3((g.N + 31) / 32, g.M / 32, batch), 128, Tile<32>::SMEM, s)(dgemm_store_kernel<32>, g);
         return;
     }
     opt.ensure(dgemm_store_kernel<BM>, (size_t)SMEM_BYTES);
     dim3 grid((g.N + BN - 1) / BN, g.M / BM, batch);
-    dgemm_store_kernel<BM><<<grid, 128, SMEM_BYTES, s>>>(g);
+    Launch(grid, 128, SMEM_BYTES, s)(dgemm_store_kernel<BM>, g);
 }
 
 // Row tiles are split over CTAs while all (panel, row tile) CTAs fit in about two waves of 4 resident CTAs
@@ -481,17 +487,17 @@ void launch_gemm_chi2(cudaStream_t s, const GemmArgs &g, int sm_count) {
     if (g.chi2_part && g.N <= gemm_chi2_split_columns(g.M, sm_count) && g.part_ld >= panels * BN) {
         if (use_small_tiles(g.M, g.N, 1, sm_count)) {  // scratch holds M / 32 partial rows (gemm_chi2_scratch)
             opt32.ensure(dgemm_chi2_kernel<32>, (size_t)Tile<32>::SMEM);
-            dgemm_chi2_kernel<32><<<dim3((g.N + 31) / 32, g.M / 32, 1), 128, Tile<32>::SMEM, s>>>(g);
-            chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, g.M / 32, g.N, g.status, g.chi2, g.gate);
+            Launch(dim3((g.N + 31) / 32, g.M / 32, 1), 128, Tile<32>::SMEM, s)(dgemm_chi2_kernel<32>, g);
+            Launch((g.N + 127) / 128, 128, 0, s)(chi2_part_sum_kernel, g.chi2_part, g.part_ld, g.M / 32, g.N, g.status, g.chi2, g.gate);
             return;
         }
         opt.ensure(dgemm_chi2_kernel<BM>, (size_t)SMEM_BYTES);
-        dgemm_chi2_kernel<BM><<<dim3(panels, tiles, 1), 128, SMEM_BYTES, s>>>(g);
-        chi2_part_sum_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(g.chi2_part, g.part_ld, tiles, g.N, g.status, g.chi2, g.gate);
+        Launch(dim3(panels, tiles, 1), 128, SMEM_BYTES, s)(dgemm_chi2_kernel<BM>, g);
+        Launch((g.N + 127) / 128, 128, 0, s)(chi2_part_sum_kernel, g.chi2_part, g.part_ld, tiles, g.N, g.status, g.chi2, g.gate);
         return;
     }
     opt.ensure(dgemm_chi2_kernel<BM>, (size_t)SMEM_BYTES);
-    dgemm_chi2_kernel<BM><<<dim3(panels, 1, 1), 128, SMEM_BYTES, s>>>(g);
+    Launch(dim3(panels, 1, 1), 128, SMEM_BYTES, s)(dgemm_chi2_kernel<BM>, g);
 }
 
 size_t toy_noise_work_doubles(int n_pad, int ntoy) {
@@ -505,14 +511,14 @@ void launch_toy_noise(cudaStream_t s, const double *L, int n, int n_pad, const d
     double *G = work, *Y = work + (size_t)n_pad * cols;
     for (int t0 = 0; t0 < ntoy; t0 += cols) {
         const int nt = std::min(cols, ntoy - t0), ldg = round_up(nt, BN);
-        toy_deviates_kernel<<<dim3((ldg + 127) / 128, n_pad), 128, 0, s>>>(n, seed, first_toy + t0, nt, ldg, G);
+        Launch(dim3((ldg + 127) / 128, n_pad), 128, 0, s)(toy_deviates_kernel, n, seed, first_toy + t0, nt, ldg, G);
         GemmArgs g{};
         g.A = L; g.Bm = G; g.C = Y;
         g.M = n_pad; g.N = nt; g.K = n_pad;
         g.lda = n_pad; g.ldb = ldg; g.ldc = ldg;
         g.lower_triangular = 1;
         launch_gemm_store(s, g, 1, 0);
-        toy_finish_kernel<<<dim3((nt + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, s>>>(Y, n, nt, ldg, truth, scale, out + (size_t)t0 * n);
+        Launch(dim3((nt + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, s)(toy_finish_kernel, Y, n, nt, ldg, truth, scale, out + (size_t)t0 * n);
     }
 }
 

@@ -14,8 +14,10 @@ namespace bf {
 // ------------------------------------------------------------------------------------------
 __global__ void prep_kernel(DevModel m, const double *__restrict__ params, int B, int ldb, int nz,
                             const double *__restrict__ zvals, const int *__restrict__ rank, double *__restrict__ pT,
-                            double *__restrict__ S, int *__restrict__ status, int z_retrigger) {
+                            double *__restrict__ S, int *__restrict__ status, int z_retrigger, double *__restrict__ key_flag) {
+    pdl_sync();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) key_flag[0] = 0.0;  // kspace_key_check_kernel, which follows, raises it (a memset node here would end the dependent-launch chain)
     if (b >= B) return;
     const double *p = params + (size_t)b * m.npar;
     const int col = rank ? rank[b] : b;  // column of this vector in the (possibly sorted) panels
@@ -54,12 +56,14 @@ __device__ __forceinline__ int sort_bucket(const DevModel &m, const double *__re
 }
 
 __global__ void sort_hist_kernel(DevModel m, const double *__restrict__ params, int B, int *__restrict__ hist) {
+    pdl_sync();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     atomicAdd(hist + sort_bucket(m, params + (size_t)b * m.npar), 1);
 }
 
 __global__ void sort_scan_kernel(int *__restrict__ hist, int *__restrict__ base) {
+    pdl_sync();
     // exclusive prefix sum over kSortBuckets (= 2 per thread of a 1024-thread block)
     __shared__ int sh[kSortBuckets];
     int t = threadIdx.x;
@@ -82,6 +86,7 @@ __global__ void sort_scan_kernel(int *__restrict__ hist, int *__restrict__ base)
 
 __global__ void sort_rank_kernel(DevModel m, const double *__restrict__ params, int B, const int *__restrict__ base,
                                  int *__restrict__ cursor, int *__restrict__ rank) {
+    pdl_sync();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int k = sort_bucket(m, params + (size_t)b * m.npar);
@@ -90,6 +95,7 @@ __global__ void sort_rank_kernel(DevModel m, const double *__restrict__ params, 
 
 __global__ void unpermute_kernel(int B, const int *__restrict__ rank, const double *__restrict__ chi2_sorted,
                                  const int *__restrict__ status_sorted, double *__restrict__ chi2, int *__restrict__ status) {
+    pdl_sync();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int c = rank[b];
@@ -159,6 +165,7 @@ __device__ __forceinline__ double post_broadband(const DevModel &m, const double
 // what this latency-bound loop needs: 1.00 -> 0.83 ms for 37 888 vectors x 440 bins (80 / 96 registers were slower).
 template <bool METALS>
 __global__ void __launch_bounds__(128, METALS ? 4 : 8) rspace_eval_kernel(EvalArgs a) {
+    pdl_sync();
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -330,6 +337,7 @@ __device__ __forceinline__ void load_kpar(const DevModel &m, const ProjArgs &a, 
 
 // G[((comp*3 + l)*nk_pad + i)*ldb + b] = (2l+1) Int_0^1 L_l(mu) D_comp(k_i, mu; p_b) dmu
 __global__ void __launch_bounds__(128) kspace_project_kernel(ProjArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(128) kspace_thomas_kernel(int B, int ldb, int 
                                                             const double *__restrict__ th_w,
                                                             const double *__restrict__ th_inv_diag,
                                                             const double *__restrict__ T, double *__restrict__ C2, Gate gate) {
+    pdl_sync();
     BF_GATE(gate);
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -437,6 +446,7 @@ __device__ __forceinline__ double kspace_correlation(const EvalArgs &a, int comp
 //   mode 1: grid bins for the distortion matrix: undistorted xi_u with the range zeroing and the
 //           pre-matrix broadband (:460-521)
 __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,6 +519,7 @@ __global__ void __launch_bounds__(128) kspace_eval_kernel(EvalArgs a) {
 // tables become small and static: they are staged in shared memory with one TMA bulk copy.
 // ------------------------------------------------------------------------------------------
 __global__ void kspace_key_check_kernel(DevModel m, const double *__restrict__ pT, int ldb, int B, double *keyout) {
+    pdl_sync();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     bool diff = false;
@@ -534,6 +545,7 @@ __global__ void kspace_key_check_kernel(DevModel m, const double *__restrict__ p
 // and if so, were the cached basis tables built for this key? state[0..17] = key of the cached tables, state[31] = 1 once
 // tables exist. Runs as one thread; the kernels that follow read gate[] (struct Gate).
 __global__ void kspace_key_decide_kernel(const double *__restrict__ flag, double *__restrict__ state, int *__restrict__ gate, KeyExtras ex) {
+    pdl_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const bool shared = flag[0] == 0.0;
     bool same = state[31] == 1.0;
@@ -551,6 +563,7 @@ __global__ void kspace_key_decide_kernel(const double *__restrict__ flag, double
 
 // G[((comp*3 + l)*nk_pad + i)*kPadN + n] = (2l+1) Int_0^1 L_l(mu) mu^(2n) K_comp(k_i, mu) dmu
 __global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     const DevModel &m = a.m;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, comp = blockIdx.y;
@@ -579,6 +592,9 @@ __global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
 #pragma unroll
         for (int n = 0; n < 3; ++n)
             a.G[((size_t)(comp * 3 + l) * m.nk_pad + i) * kPadN + n] = l <= lmax ? (2 * l * 2 + 1) * s[l][n] : 0.0;
+    // the padding columns the Hankel GEMM's tiles read (written here rather than by a memset node before the kernel)
+    for (int l = 0; l < 3; ++l)
+        for (int n = 3; n < kPadN; ++n) a.G[((size_t)(comp * 3 + l) * m.nk_pad + i) * kPadN + n] = 0.0;
 }
 
 // Natural-spline second derivatives of the 18 basis tables and packing for the evaluation
@@ -586,6 +602,7 @@ __global__ void __launch_bounds__(128) kspace_basis_project_kernel(ProjArgs a) {
 // One CTA; the 18 serial (1,4,1) sweeps run in shared memory instead of global memory.
 __global__ void __launch_bounds__(256) kspace_basis_finish_kernel(DevModel m, const double *__restrict__ T,
                                                                   double2 *__restrict__ tabs, Gate gate) {
+    pdl_sync();
     BF_GATE(gate);
     extern __shared__ double sh[];  // y[18][nr], c[18][nr]
     const int nr = m.nr;
@@ -694,6 +711,7 @@ __device__ __forceinline__ double shared_correlation(const DevModel &m, const do
 
 // Same contract as kspace_eval_kernel, basis tables in shared memory (TMA bulk copy + mbarrier).
 __global__ void __launch_bounds__(256, 2) kspace_eval_shared_kernel(EvalArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tab = reinterpret_cast<double2 *>(smem_raw);
@@ -785,6 +803,7 @@ __global__ void __launch_bounds__(256, 2) kspace_eval_shared_kernel(EvalArgs a) 
 // dilation-limit check of the data bin itself (baofit/BaoKSpaceCorrelationModel.cc:420-427,
 // :529-535). Y = D_kept . xi_u comes from the DMMA GEMM.
 __global__ void __launch_bounds__(128, 4) dist_post_kernel(EvalArgs a) {
+    pdl_sync();
     BF_GATE(a.gate);
     const DevModel &m = a.m;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -835,65 +854,65 @@ static int pick_pts_per_block(int npts_pad, int B, int sm_count) {
 }
 
 void launch_prep(cudaStream_t s, const DevModel &m, const double *params, int B, int ldb, int nz,
-                 const double *zvals, const int *rank, double *pT, double *S, int *status, bool z_retrigger) {
-    prep_kernel<<<(B + 127) / 128, 128, 0, s>>>(m, params, B, ldb, nz, zvals, rank, pT, S, status, z_retrigger ? 1 : 0);
+                 const double *zvals, const int *rank, double *pT, double *S, int *status, bool z_retrigger, double *key_flag) {
+    Launch((B + 127) / 128, 128, 0, s)(prep_kernel, m, params, B, ldb, nz, zvals, rank, pT, S, status, z_retrigger ? 1 : 0, key_flag);
 }
 
 void launch_coherence_sort(cudaStream_t s, const DevModel &m, const double *params, int B, int *hist, int *base, int *rank) {
     cudaMemsetAsync(hist, 0, sizeof(int) * kSortBuckets, s);
-    sort_hist_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, params, B, hist);
-    sort_scan_kernel<<<1, kSortBuckets / 2, 0, s>>>(hist, base);
-    sort_rank_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, params, B, base, hist, rank);
+    Launch((B + 255) / 256, 256, 0, s)(sort_hist_kernel, m, params, B, hist);
+    Launch(1, kSortBuckets / 2, 0, s)(sort_scan_kernel, hist, base);
+    Launch((B + 255) / 256, 256, 0, s)(sort_rank_kernel, m, params, B, base, hist, rank);
 }
 
 void launch_unpermute(cudaStream_t s, int B, const int *rank, const double *chi2_sorted, const int *status_sorted,
                       double *chi2, int *status) {
-    unpermute_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, rank, chi2_sorted, status_sorted, chi2, status);
+    Launch((B + 255) / 256, 256, 0, s)(unpermute_kernel, B, rank, chi2_sorted, status_sorted, chi2, status);
 }
 
 void launch_rspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
     a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
     dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
-    if (a.m.metal_kind != BF_METAL_NONE) rspace_eval_kernel<true><<<grid, 128, 0, s>>>(a);
-    else rspace_eval_kernel<false><<<grid, 128, 0, s>>>(a);
+    if (a.m.metal_kind != BF_METAL_NONE) Launch(grid, 128, 0, s)(rspace_eval_kernel<true>, a);
+    else Launch(grid, 128, 0, s)(rspace_eval_kernel<false>, a);
 }
 
 void launch_kspace_project(cudaStream_t s, ProjArgs &a, int sm_count) {
     a.k_per_block = pick_pts_per_block(a.m.nk_pad, a.B, sm_count);
     dim3 grid((a.B + 127) / 128, (a.m.nk_pad + a.k_per_block - 1) / a.k_per_block, 2);
-    kspace_project_kernel<<<grid, 128, 0, s>>>(a);
+    Launch(grid, 128, 0, s)(kspace_project_kernel, a);
 }
 
 void launch_kspace_thomas(cudaStream_t s, int B, int ldb, int nr, int nr_pad, double h, const double *th_w,
                           const double *th_inv_diag, const double *T, double *C2, Gate gate) {
     dim3 grid((B + 127) / 128, 6);
-    kspace_thomas_kernel<<<grid, 128, 0, s>>>(B, ldb, nr, nr_pad, h, th_w, th_inv_diag, T, C2, gate);
+    Launch(grid, 128, 0, s)(kspace_thomas_kernel, B, ldb, nr, nr_pad, h, th_w, th_inv_diag, T, C2, gate);
 }
 
 void launch_kspace_eval(cudaStream_t s, EvalArgs &a, int sm_count) {
     a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
     dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
-    kspace_eval_kernel<<<grid, 128, 0, s>>>(a);
+    Launch(grid, 128, 0, s)(kspace_eval_kernel, a);
 }
 
 void launch_kspace_key_check(cudaStream_t s, const DevModel &m, const double *pT, int ldb, int B, double *keyout) {
-    kspace_key_check_kernel<<<(B + 255) / 256, 256, 0, s>>>(m, pT, ldb, B, keyout);
+    Launch((B + 255) / 256, 256, 0, s)(kspace_key_check_kernel, m, pT, ldb, B, keyout);
 }
 
 void launch_kspace_key_decide(cudaStream_t s, const double *flag, double *state, int *gate, const KeyExtras &ex) {
-    kspace_key_decide_kernel<<<1, 32, 0, s>>>(flag, state, gate, ex);
+    Launch(1, 32, 0, s)(kspace_key_decide_kernel, flag, state, gate, ex);
 }
 
 void launch_kspace_basis_project(cudaStream_t s, ProjArgs &a) {
     dim3 grid((a.m.nk_pad + 127) / 128, 2);
-    kspace_basis_project_kernel<<<grid, 128, 0, s>>>(a);
+    Launch(grid, 128, 0, s)(kspace_basis_project_kernel, a);
 }
 
 void launch_kspace_basis_finish(cudaStream_t s, const DevModel &m, const double *T, double2 *tabs, Gate gate) {
     size_t smem = (size_t)36 * m.nr * sizeof(double);
     static SmemOptIn opt;
     opt.ensure(kspace_basis_finish_kernel, smem);
-    kspace_basis_finish_kernel<<<1, 256, smem, s>>>(m, T, tabs, gate);
+    Launch(1, 256, smem, s)(kspace_basis_finish_kernel, m, T, tabs, gate);
 }
 
 void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count) {
@@ -905,13 +924,13 @@ void launch_kspace_eval_shared(cudaStream_t s, EvalArgs &a, int sm_count) {
     int by = max(1, min(a.npts_pad, (want + bx - 1) / bx));
     a.pts_per_block = (a.npts_pad + by - 1) / by;
     dim3 grid(bx, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
-    kspace_eval_shared_kernel<<<grid, 256, smem, s>>>(a);
+    Launch(grid, 256, smem, s)(kspace_eval_shared_kernel, a);
 }
 
 void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count) {
     a.pts_per_block = pick_pts_per_block(a.npts_pad, a.B, sm_count);
     dim3 grid((a.B + 127) / 128, (a.npts_pad + a.pts_per_block - 1) / a.pts_per_block);
-    dist_post_kernel<<<grid, 128, 0, s>>>(a);
+    Launch(grid, 128, 0, s)(dist_post_kernel, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -921,6 +940,7 @@ void launch_dist_post(cudaStream_t s, EvalArgs &a, int sm_count) {
 __global__ void multipole_project_kernel(const double *__restrict__ X, int ldx, const double *__restrict__ proj, int n, int nmu,
                                          int B, double *__restrict__ out, int ldo, const double *__restrict__ dsub,
                                          const double *__restrict__ dov) {
+    pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (b >= B) return;
     double s = 0.0;
@@ -931,18 +951,19 @@ __global__ void multipole_project_kernel(const double *__restrict__ X, int ldx, 
 
 void launch_multipole_project(cudaStream_t s, const double *X, int ldx, const double *proj, int n, int nmu, int B,
                               double *out, int ldo, const double *dsub, const double *dov) {
-    multipole_project_kernel<<<dim3((B + 127) / 128, n), 128, 0, s>>>(X, ldx, proj, n, nmu, B, out, ldo, dsub, dov);
+    Launch(dim3((B + 127) / 128, n), 128, 0, s)(multipole_project_kernel, X, ldx, proj, n, nmu, B, out, ldo, dsub, dov);
 }
 
 __global__ void gather_rows_kernel(const double *__restrict__ table, const int *__restrict__ index, int B, int n,
                                    double *__restrict__ out) {
+    pdl_sync();
     const int b = blockIdx.y;
     const double *src = table + (size_t)index[b] * n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[(size_t)b * n + i] = src[i];
 }
 
 void launch_gather_rows(cudaStream_t s, const double *table, const int *index, int B, int n, double *out) {
-    gather_rows_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(table, index, B, n, out);
+    Launch(dim3((n + 255) / 256, B), 256, 0, s)(gather_rows_kernel, table, index, B, n, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -953,6 +974,7 @@ constexpr int kProbeSplit = 8;  // row slices of the normal-equation kernels
 
 __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y, int ldy, int nrows, int G, int nfit,
                                                    double *__restrict__ out) {
+    pdl_sync();
     extern __shared__ double gsm[];  // [kGramRows][G]
     const int f = blockIdx.x, tid = threadIdx.x;
     const int npairs = G * (G + 1) / 2;
@@ -994,6 +1016,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ Y,
 // (f, s) writes its partial sums to part[(f * kProbeSplit + s) * npairs + p], normal_probes_sum_kernel adds them in order.
 __global__ void __launch_bounds__(256) normal_probes_kernel(const double *__restrict__ Y, int ldy, int nrows, int n, int nfit,
                                                             double *__restrict__ part) {
+    pdl_sync();
     extern __shared__ double nsm[];  // [kGramRows][R + n]: y0, a_1..a_n, s_1..s_n
     const int f = blockIdx.x, tid = threadIdx.x, G = 2 * n + 1, R = n + 1, W = R + n;
     const int npairs = R * (R + 1) / 2 + n;  // pairs (i >= j) of M, then the n dot products y0 . s_i
@@ -1041,6 +1064,7 @@ __global__ void __launch_bounds__(256) normal_probes_kernel(const double *__rest
 
 // out[f] = M (row-major, symmetric) followed by t, from the kProbeSplit partial sums of every pair, added in slice order
 __global__ void __launch_bounds__(256) normal_probes_sum_kernel(const double *__restrict__ part, int n, int nfit, double *__restrict__ out) {
+    pdl_sync();
     const int f = blockIdx.x, R = n + 1, npairs = R * (R + 1) / 2 + n;
     double *o = out + (size_t)f * (R * R + n);
     for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
@@ -1062,6 +1086,7 @@ __global__ void __launch_bounds__(256) normal_probes_sum_kernel(const double *__
 constexpr int kLinMaxTerms = 16;  // static columns one synthesised column is a combination of (redshift classes, or powers of v)
 
 __global__ void __launch_bounds__(256) normal_probes_lin_kernel(NormalLinArgs a) {
+    pdl_sync();
     extern __shared__ double lsm[];  // [kGramRows][R + n] as in normal_probes_kernel, then per-column metadata
     const int f = blockIdx.x, tid = threadIdx.x, n = a.n, R = n + 1, W = R + n, G = 2 * a.n_nl + 1;
     // column i of a linear parameter: scale_i * sum_q cw[i][q] * WA[row][kleft + cbase_i + q * cstride]
@@ -1168,21 +1193,22 @@ void launch_normal_probes_lin(cudaStream_t s, const NormalLinArgs &a) {
     const size_t smem = ((size_t)kGramRows * (2 * a.n + 1) + a.n + (size_t)a.n * kLinMaxTerms) * sizeof(double) + (size_t)3 * a.n * sizeof(int);
     static SmemOptIn opt;
     opt.ensure(normal_probes_lin_kernel, smem);
-    normal_probes_lin_kernel<<<dim3(a.nfit, kProbeSplit), 256, smem, s>>>(a);
-    normal_probes_sum_kernel<<<a.nfit, 256, 0, s>>>(a.part, a.n, a.nfit, a.out);
+    Launch(dim3(a.nfit, kProbeSplit), 256, smem, s)(normal_probes_lin_kernel, a);
+    Launch(a.nfit, 256, 0, s)(normal_probes_sum_kernel, a.part, a.n, a.nfit, a.out);
 }
 
 void launch_normal_probes(cudaStream_t s, const double *Y, int ldy, int nrows, int n, int nfit, double *out, double *part) {
-    normal_probes_kernel<<<dim3(nfit, kProbeSplit), 256, (size_t)kGramRows * (2 * n + 1) * sizeof(double), s>>>(Y, ldy, nrows, n, nfit, part);
-    normal_probes_sum_kernel<<<nfit, 256, 0, s>>>(part, n, nfit, out);
+    Launch(dim3(nfit, kProbeSplit), 256, (size_t)kGramRows * (2 * n + 1) * sizeof(double), s)(normal_probes_kernel, Y, ldy, nrows, n, nfit, part);
+    Launch(nfit, 256, 0, s)(normal_probes_sum_kernel, part, n, nfit, out);
 }
 
 void launch_gram(cudaStream_t s, const double *Y, int ldy, int nrows, int G, int nfit, double *out) {
-    gram_kernel<<<nfit, 256, (size_t)kGramRows * G * sizeof(double), s>>>(Y, ldy, nrows, G, nfit, out);
+    Launch(nfit, 256, (size_t)kGramRows * G * sizeof(double), s)(gram_kernel, Y, ldy, nrows, G, nfit, out);
 }
 
 __global__ void expand_probes_kernel(const double *__restrict__ centres, const double *__restrict__ steps, int nfit, int npar,
                                      int nprobe, double *__restrict__ params, const int *__restrict__ skip) {
+    pdl_sync();
     const int G = 2 * nprobe + 1;
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= nfit * G) return;
@@ -1203,6 +1229,7 @@ __global__ void expand_probes_kernel(const double *__restrict__ centres, const d
 }
 
 __global__ void reduce_status_kernel(const int *__restrict__ status, int nfit, int G, int *__restrict__ status_fit) {
+    pdl_sync();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nfit) return;
     int s = 0;
@@ -1213,11 +1240,11 @@ __global__ void reduce_status_kernel(const int *__restrict__ status, int nfit, i
 void launch_expand_probes(cudaStream_t s, const double *centres, const double *steps, int nfit, int npar, int nprobe, double *params,
                           const int *skip) {
     const int total = nfit * (2 * nprobe + 1);
-    expand_probes_kernel<<<(total + 127) / 128, 128, 0, s>>>(centres, steps, nfit, npar, nprobe, params, skip);
+    Launch((total + 127) / 128, 128, 0, s)(expand_probes_kernel, centres, steps, nfit, npar, nprobe, params, skip);
 }
 
 void launch_reduce_status(cudaStream_t s, const int *status, int nfit, int G, int *status_fit) {
-    reduce_status_kernel<<<(nfit + 127) / 128, 128, 0, s>>>(status, nfit, G, status_fit);
+    Launch((nfit + 127) / 128, 128, 0, s)(reduce_status_kernel, status, nfit, G, status_fit);
 }
 
 }  // namespace bf

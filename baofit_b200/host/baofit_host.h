@@ -205,6 +205,8 @@ public:
 private:
     std::vector<double> _axis[3], _width[3];
 };
+// eigenmodes of a dense symmetric matrix: values ascending, vectors[k*n + i] = component i of mode k
+void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &values, std::vector<double> &vectors);
 BinnedGrid createCorrelationGrid(std::string const &axis1Bins, std::string const &axis2Bins,
                                  std::string const &axis3Bins);  // AbsCorrelationData.cc:96-150
 
@@ -246,6 +248,9 @@ public:
     // applies the final cuts (AbsCorrelationData.cc:67-94), prunes, and freezes the data set
     virtual void finalize();
     bool isFinalized() const { return _finalized; }
+    // "project-modes-keep" (src/baofit.cc:194,597-603): before finalize(), replaces the data vector by its projection onto the
+    // nkeep largest- (nkeep > 0) or smallest-variance (nkeep < 0) eigenmodes of the covariance over the bins with data
+    void projectOntoModes(int nkeep);
     // coordinates of every grid bin, for AbsCorrelationModel::setCoordinates
     void gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const;
     // device-resident data (kept bins, d, Cholesky factors); gridFor: model whose distortion

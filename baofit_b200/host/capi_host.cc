@@ -315,6 +315,16 @@ extern "C" int bfh_save_data(bfh_session *s, const char *data_path, const char *
     BFH_CATCH
 }
 
+extern "C" int bfh_symmetric_eigenmodes(int n, const double *matrix, double *values, double *vectors) {
+    BFH_TRY
+    if (n <= 0 || !matrix || !values || !vectors) throw RuntimeError("bfh_symmetric_eigenmodes: bad arguments");
+    std::vector<double> vals, vecs;
+    symmetricEigenModes(n, std::vector<double>(matrix, matrix + (size_t)n * n), vals, vecs);
+    std::copy(vals.begin(), vals.end(), values);
+    std::copy(vecs.begin(), vecs.end(), vectors);
+    BFH_CATCH
+}
+
 extern "C" int bfh_nobservations(const bfh_session *s) { return s && s->resampler ? s->resampler->getNObservations() : 0; }
 
 extern "C" int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size) {

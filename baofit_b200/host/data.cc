@@ -216,6 +216,146 @@ void AbsCorrelationData::finalize() {
     _finalized = true;
 }
 
+// Eigenmodes of a dense symmetric matrix (likely::CovarianceMatrix::getEigenModes calls LAPACK there; the dependency is
+// not in the tree): Householder reflections bring the matrix to tridiagonal form, implicit-shift QL sweeps diagonalise it.
+// values ascending; vectors[k*n + i] = component i of mode k, unit norm (the layout BinnedData::projectOntoModes reads).
+void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &values, std::vector<double> &vectors) {
+    if (n <= 0 || a.size() != (size_t)n * n) throw RuntimeError("symmetricEigenModes: bad dimensions");
+    std::vector<double> d(n), e(n, 0.0), beta(n, 0.0), v(n), pv(n);
+    auto A = [&](int i, int j) -> double & { return a[(size_t)i * n + j]; };
+    // reflection k zeroes column k below the sub-diagonal; its vector stays in that column (rows k+1..)
+    for (int k = 0; k + 2 < n; ++k) {
+        double tail = 0;
+        for (int i = k + 2; i < n; ++i) tail += A(i, k) * A(i, k);
+        const double x0 = A(k + 1, k);
+        if (tail == 0.0) { e[k] = x0; continue; }
+        const double alpha = x0 > 0 ? -std::sqrt(x0 * x0 + tail) : std::sqrt(x0 * x0 + tail);
+        for (int i = k + 1; i < n; ++i) v[i] = A(i, k);
+        v[k + 1] -= alpha;
+        double vv = 0;
+        for (int i = k + 1; i < n; ++i) vv += v[i] * v[i];
+        const double b = 2.0 / vv;
+        // p = b A22 v, w = p - (b/2)(v.p) v, A22 -= v w^T + w v^T (both triangles are kept: rows stay contiguous)
+        double vp = 0;
+        for (int i = k + 1; i < n; ++i) {
+            const double *row = &a[(size_t)i * n];
+            double sum = 0;
+            for (int j = k + 1; j < n; ++j) sum += row[j] * v[j];
+            pv[i] = b * sum;
+            vp += v[i] * pv[i];
+        }
+        const double half = 0.5 * b * vp;
+        for (int i = k + 1; i < n; ++i) pv[i] -= half * v[i];
+        for (int i = k + 1; i < n; ++i) {
+            double *row = &a[(size_t)i * n];
+            const double vi = v[i], wi = pv[i];
+            for (int j = k + 1; j < n; ++j) row[j] -= vi * pv[j] + wi * v[j];
+        }
+        e[k] = alpha;
+        beta[k] = b;
+        for (int i = k + 1; i < n; ++i) A(i, k) = v[i];
+    }
+    if (n >= 2) e[n - 2] = A(n - 1, n - 2);
+    for (int i = 0; i < n; ++i) d[i] = A(i, i);
+    // Z = Q^T with Q = H_0 H_1 ...: rows of Z are the (future) modes, so a QL rotation mixes two contiguous rows
+    std::vector<double> z((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) z[(size_t)i * n + i] = 1.0;
+    for (int k = n - 3; k >= 0; --k) {
+        if (beta[k] == 0.0) continue;
+        // Q <- H_k Q on rows k+1.. of Q, i.e. on columns k+1.. of Z: Z[r][:] -= beta (Z[r][:].v) v for every row r > k
+        for (int r = k + 1; r < n; ++r) {
+            double *row = &z[(size_t)r * n];
+            double dot = 0;
+            for (int i = k + 1; i < n; ++i) dot += row[i] * A(i, k);
+            dot *= beta[k];
+            for (int i = k + 1; i < n; ++i) row[i] -= dot * A(i, k);
+        }
+    }
+    // implicit-shift QL on (d, e)
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; ++l) {
+        for (int iter = 0;; ++iter) {
+            int m = l;
+            for (; m + 1 < n; ++m)
+                if (std::fabs(e[m]) <= eps * (std::fabs(d[m]) + std::fabs(d[m + 1]))) break;
+            if (m == l) break;
+            if (iter == 80) throw RuntimeError("symmetricEigenModes: QL iteration did not converge");
+            double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+            double r = std::hypot(g, 1.0);
+            g = d[m] - d[l] + e[l] / (g + (g >= 0 ? r : -r));
+            double sn = 1.0, cs = 1.0, p = 0.0;
+            int i = m - 1;
+            for (; i >= l; --i) {
+                double f = sn * e[i], bb = cs * e[i];
+                r = std::hypot(f, g);
+                e[i + 1] = r;
+                if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                sn = f / r;
+                cs = g / r;
+                g = d[i + 1] - p;
+                r = (d[i] - g) * sn + 2.0 * cs * bb;
+                p = sn * r;
+                d[i + 1] = g + p;
+                g = cs * r - bb;
+                double *zi = &z[(size_t)i * n], *zi1 = &z[(size_t)(i + 1) * n];
+                for (int q = 0; q < n; ++q) {
+                    const double t = zi1[q];
+                    zi1[q] = sn * zi[q] + cs * t;
+                    zi[q] = cs * zi[q] - sn * t;
+                }
+            }
+            if (r == 0.0 && i >= l) continue;
+            d[l] -= p;
+            e[l] = g;
+            e[m] = 0.0;
+        }
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d[x] < d[y]; });
+    values.resize(n);
+    vectors.resize((size_t)n * n);
+    for (int k = 0; k < n; ++k) {
+        values[k] = d[order[k]];
+        std::copy(z.begin() + (size_t)order[k] * n, z.begin() + (size_t)(order[k] + 1) * n, vectors.begin() + (size_t)k * n);
+    }
+}
+
+// likely::BinnedData::projectOntoModes as src/baofit.cc:597-603 uses it (before the final cuts): the data vector is replaced by
+// its projection onto the nkeep eigenmodes of the covariance with the largest (nkeep > 0) or smallest (nkeep < 0) variance;
+// the covariance stays as it is. UNVERIFIED (dep): restated from the option's documentation (src/baofit.cc:194-195).
+void AbsCorrelationData::projectOntoModes(int nkeep) {
+    if (_finalized) throw RuntimeError("AbsCorrelationData::projectOntoModes: data set is already finalized.");
+    if (!_haveCov) throw RuntimeError("BinnedData::projectOntoModes: no covariance available.");
+    std::vector<int> bins = binsWithData();
+    const int n = (int)bins.size();
+    if (nkeep == 0 || nkeep > n || -nkeep > n) throw RuntimeError("BinnedData::projectOntoModes: invalid nkeep.");
+    std::vector<double> m = denseOverBinsWithData();
+    std::vector<double> cov = _isInverse ? spdInverse(n, m, "the inverse covariance") : m;
+    std::vector<double> data(n);
+    for (int i = 0; i < n; ++i) data[i] = _values.at(bins[i]);
+    if (_weighted) {  // stored values are elements of Cinv.d
+        std::vector<double> w = data;
+        for (int i = 0; i < n; ++i) {
+            double sum = 0;
+            for (int j = 0; j < n; ++j) sum += cov[(size_t)i * n + j] * w[j];
+            data[i] = sum;
+        }
+        _weighted = false;
+    }
+    std::vector<double> values, modes;
+    symmetricEigenModes(n, cov, values, modes);
+    const int first = nkeep > 0 ? n - nkeep : 0, last = nkeep > 0 ? n : -nkeep;
+    std::vector<double> projected(n, 0.0);
+    for (int k = first; k < last; ++k) {
+        const double *mode = &modes[(size_t)k * n];
+        double dot = 0;
+        for (int i = 0; i < n; ++i) dot += mode[i] * data[i];
+        for (int i = 0; i < n; ++i) projected[i] += dot * mode[i];
+    }
+    for (int i = 0; i < n; ++i) _values[bins[i]] = projected[i];
+}
+
 void AbsCorrelationData::gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const {
     int n = _grid.getNBinsTotal();
     r.resize(n); mu.resize(n); z.resize(n);

@@ -957,6 +957,9 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir,
         data = resampler->combined();
         if (resamplerOut) *resamplerOut = resampler;
     }
+    // src/baofit.cc:597-603: the combined data before final cuts are projected onto eigenmodes, then finalized
+    const int projectModesNKeep = (int)opt.num("project-modes-keep", 0);
+    if (projectModesNKeep != 0) data->projectOntoModes(projectModesNKeep);
     data->finalize();
     return data;
 }

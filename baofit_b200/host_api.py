@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes"]
 
 
 def lib():
@@ -57,6 +57,7 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                               C.c_void_p]
         L.bfh_save_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.bfh_symmetric_eigenmodes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
         L.bfh_resampling_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long)]
         L.bfh_bootstrap_counts.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p]
@@ -90,6 +91,15 @@ def set_device(device):
 def set_num_threads(n=0):
     """Host threads of the per-fit linear algebra (OpenMP); n <= 0 only queries. Returns the number in use."""
     return int(lib().bfh_set_num_threads(int(n)))
+
+
+def symmetric_eigenmodes(matrix):
+    """Eigenmodes of a dense symmetric matrix as project-modes-keep uses them: (values ascending, modes as rows)."""
+    a = np.ascontiguousarray(matrix, dtype=np.float64)
+    n = a.shape[0]
+    values, vectors = np.empty(n), np.empty((n, n))
+    _check(lib().bfh_symmetric_eigenmodes(n, a.ctypes.data, values.ctypes.data, vectors.ctypes.data))
+    return values, vectors
 
 
 def share_host_cores():

@@ -89,6 +89,9 @@ int bfh_write_samples_refit(bfh_session *s, const char *path, const double *best
 /* save-data / save-icov of src/baofit.cc:612-626: the finalized (combined, cut) data set as "<index> <value>" and
  * "<i> <j> <Cinv_ij>" text files that bfh_session_create reads back with load-icov. Either path may be NULL. */
 int bfh_save_data(bfh_session *s, const char *data_path, const char *icov_path);
+/* Eigenmodes of a dense symmetric n x n matrix, the decomposition behind project-modes-keep (src/baofit.cc:194,597-603;
+ * likely::CovarianceMatrix::getEigenModes in the reference): values ascending, vectors[k*n + i] = component i of mode k. Host only. */
+int bfh_symmetric_eigenmodes(int n, const double *matrix, double *values /* [n] */, double *vectors /* [n*n] */);
 int bfh_nobservations(const bfh_session *s);
 int bfh_resampling_size(bfh_session *s, const char *kind, int n, long *size);
 int bfh_bootstrap_counts(bfh_session *s, int size, unsigned long long seed, long trial, int *counts /* [nobservations] */);
