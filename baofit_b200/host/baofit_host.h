@@ -251,6 +251,9 @@ public:
     // "project-modes-keep" (src/baofit.cc:194,597-603): before finalize(), replaces the data vector by its projection onto the
     // nkeep largest- (nkeep > 0) or smallest-variance (nkeep < 0) eigenmodes of the covariance over the bins with data
     void projectOntoModes(int nkeep);
+    // "fix-mode-scales" (src/baofit.cc:192,570-572): multiplies the eigenvalues of the covariance over the bins with data by
+    // modeScales (ascending eigenvalue order, all > 0); before finalize()
+    void rescaleEigenvalues(std::vector<double> const &modeScales);
     // coordinates of every grid bin, for AbsCorrelationModel::setCoordinates
     void gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const;
     // device-resident data (kept bins, d, Cholesky factors); gridFor: model whose distortion

@@ -356,6 +356,46 @@ void AbsCorrelationData::projectOntoModes(int nkeep) {
     for (int i = 0; i < n; ++i) _values[bins[i]] = projected[i];
 }
 
+// "fix-mode-scales" (src/baofit.cc:192,514-524,570-572): every loaded data set has the eigenvalues of its covariance multiplied
+// by the scales read from a file, smallest-variance mode first (likely::CovarianceMatrix::rescaleEigenvalues; UNVERIFIED (dep)).
+// The data vector does not change; a matrix that was loaded as an inverse is kept as a covariance from here on.
+void AbsCorrelationData::rescaleEigenvalues(std::vector<double> const &modeScales) {
+    if (_finalized) throw RuntimeError("AbsCorrelationData::rescaleEigenvalues: data set is already finalized.");
+    if (!_haveCov) throw RuntimeError("BinnedData::rescaleEigenvalues: no covariance available.");
+    std::vector<int> bins = binsWithData();
+    const int n = (int)bins.size();
+    if ((int)modeScales.size() != n) throw RuntimeError("CovarianceMatrix::rescaleEigenvalues: unexpected number of mode scales.");
+    for (double scale : modeScales)
+        if (!(scale > 0)) throw RuntimeError("CovarianceMatrix::rescaleEigenvalues: expected all mode scales > 0.");
+    std::vector<double> m = denseOverBinsWithData();
+    std::vector<double> cov = _isInverse ? spdInverse(n, m, "the inverse covariance") : m;
+    if (_weighted) {  // stored values are elements of Cinv.d with the covariance as loaded
+        std::vector<double> w(n);
+        for (int i = 0; i < n; ++i) w[i] = _values.at(bins[i]);
+        for (int i = 0; i < n; ++i) {
+            double sum = 0;
+            for (int j = 0; j < n; ++j) sum += cov[(size_t)i * n + j] * w[j];
+            _values[bins[i]] = sum;
+        }
+        _weighted = false;
+    }
+    std::vector<double> values, modes;
+    symmetricEigenModes(n, cov, values, modes);
+    std::fill(cov.begin(), cov.end(), 0.0);
+    for (int k = 0; k < n; ++k) {
+        const double *mode = &modes[(size_t)k * n];
+        const double lambda = values[k] * modeScales[k];
+        for (int i = 0; i < n; ++i) {
+            const double a = lambda * mode[i];
+            for (int j = 0; j <= i; ++j) cov[(size_t)i * n + j] += a * mode[j];
+        }
+    }
+    _cov.clear();
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) _cov[std::make_pair(std::min(bins[i], bins[j]), std::max(bins[i], bins[j]))] = cov[(size_t)i * n + j];
+    _isInverse = false;
+}
+
 void AbsCorrelationData::gridCoordinates(std::vector<double> &r, std::vector<double> &mu, std::vector<double> &z) const {
     int n = _grid.getNBinsTotal();
     r.resize(n); mu.resize(n); z.resize(n);

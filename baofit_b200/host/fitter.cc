@@ -934,10 +934,21 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir,
                         opt.num("z-min", 0), opt.num("z-max", 10));
         return p;
     };
+    // src/baofit.cc:514-524: one mode scale per line; applied to every data set right after it has been loaded (:570-572)
+    std::vector<double> modeScales;
+    if (!opt.str("fix-mode-scales").empty()) {
+        std::string scalesName = resolve(baseDir, opt.str("fix-mode-scales"));
+        std::ifstream in(scalesName.c_str());
+        if (!in.good()) throw RuntimeError("Unable to open mode scales file " + scalesName);
+        double scale;
+        while (in >> scale) modeScales.push_back(scale);
+        if (modeScales.empty()) throw RuntimeError("No mode scales found in " + scalesName);
+    }
     AbsCorrelationDataPtr data;
     if (!opt.str("data").empty()) {
         data = prototype();
         loadCorrelationData(resolve(baseDir, opt.str("data")), *data, opt.flag("load-icov"), opt.flag("load-wdata"), opt.flag("custom-grid"));
+        if (!modeScales.empty()) data->rescaleEigenvalues(modeScales);
     } else {
         // individual observations named by plateroot + platelist (src/baofit.cc:531-583), combined with
         // inverse-covariance weights like likely::BinnedDataResampler::combined
@@ -950,6 +961,7 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir,
         while (list >> plateName) {
             AbsCorrelationDataPtr plate = prototype();
             loadCorrelationData(root + plateName, *plate, opt.flag("load-icov"), opt.flag("load-wdata"), opt.flag("custom-grid"));
+            if (!modeScales.empty()) plate->rescaleEigenvalues(modeScales);
             resampler->addObservation(plate);
             if (maxPlates > 0 && resampler->getNObservations() == maxPlates) break;
         }

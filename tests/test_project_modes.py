@@ -65,3 +65,26 @@ def test_project_modes_keep_rejects_bad_nkeep(built, golden_tree):
     text, base, _, _ = _qso(golden_tree)
     with pytest.raises(H.HostError):
         H.Session(text + "\nproject-modes-keep = 513\n", base)
+
+
+def test_fix_mode_scales_option(built, golden_tree, tmp_path):
+    """fix-mode-scales (src/baofit.cc:192,514-524,570-572): eigenvalues of the loaded covariance times the scales of a file,
+    smallest-variance mode first; the data vector is untouched; the cuts then take the kept block."""
+    text, base, data, cov = _qso(golden_tree)
+    n = len(data)
+    rng = np.random.Generator(np.random.PCG64(3))
+    scales = np.exp(0.3 * rng.standard_normal(n))
+    np.savetxt(tmp_path / "scales.dat", scales, fmt="%.17g")
+    plain = H.Session(text, base)
+    fixed = H.Session(text + "\nfix-mode-scales = %s\n" % (tmp_path / "scales.dat"), base)
+    kept = plain.kept_indices()
+    assert np.array_equal(fixed.data_vector(), plain.data_vector())
+    w, v = np.linalg.eigh(cov)
+    expected = (v * (w * scales)) @ v.T
+    got = fixed.covariance()
+    assert np.max(np.abs(got - expected[np.ix_(kept, kept)])) < 1e-10 * np.max(np.abs(cov))
+    assert np.max(np.abs(got - plain.covariance())) > 1e-3 * np.max(np.abs(cov))
+    np.savetxt(tmp_path / "bad.dat", scales[:-1], fmt="%.17g")
+    with pytest.raises(H.HostError):
+        H.Session(text + "\nfix-mode-scales = %s\n" % (tmp_path / "bad.dat"), base)
+    plain.close(), fixed.close()
