@@ -614,7 +614,8 @@ __global__ void __launch_bounds__(256, 4) fft_eval_kernel(FftEvalArgs a) {
 // planes arrive by TMA bulk copies (two CTAs per SM), and the 2 x 16 stencil reads of every bin are shared-memory loads
 // instead of L2 round trips. fft_eval_kernel was bound by load latency (1.14 ms for 18 944 vectors x 1515 bins at 37 %
 // occupancy, its 8 vectors per CTA sweep 660 KB of planes through L1); here each plane byte crosses L2 once.
-__global__ void __launch_bounds__(256, 2) fft_eval_smem_kernel(FftEvalArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) fft_eval_smem_kernel(FftEvalArgs a) {
     pdl_sync();
     extern __shared__ __align__(128) double esm[];
     __shared__ __align__(8) unsigned long long bar;
@@ -684,9 +685,18 @@ void launch_fft_eval(cudaStream_t s, const FftEvalArgs &a) {
     const size_t smem = (size_t)2 * f.npy_pad * f.npx_pad * sizeof(double);
     static const bool no_smem = std::getenv("BAOFIT_FFT_EVAL_GLOBAL") != nullptr;  // A/B measurements
     if (!no_smem && smem <= 110 * 1024 && smem % 16 == 0 && a.B >= 64) {
-        static SmemOptIn opt;
-        opt.ensure(fft_eval_smem_kernel, smem);
-        Launch(a.B, 256, smem, s)(fft_eval_smem_kernel, a);
+        // 384 threads per CTA (two CTAs per SM by shared memory: 24 resident warps at <= 85 registers, a few spilled words)
+        // against 256 at 128 registers: 1.03 -> 0.94 ms for 18 944 x 1515; 320 / 448 / 512 threads measured 0.98 / 0.94 / 0.95.
+        // The loop is bound by dependency latency, not by issue slots. BAOFIT_FFT_EVAL_THREADS=256 keeps the old shape (A/B).
+        static const bool t256 = std::getenv("BAOFIT_FFT_EVAL_THREADS") && std::atoi(std::getenv("BAOFIT_FFT_EVAL_THREADS")) == 256;
+        static SmemOptIn opt256, opt384;
+        if (t256) {
+            opt256.ensure(fft_eval_smem_kernel<256>, smem);
+            Launch(a.B, 256, smem, s)(fft_eval_smem_kernel<256>, a);
+        } else {
+            opt384.ensure(fft_eval_smem_kernel<384>, smem);
+            Launch(a.B, 384, smem, s)(fft_eval_smem_kernel<384>, a);
+        }
         return;
     }
     dim3 grid((a.B + kEvalVecPerBlock - 1) / kEvalVecPerBlock, (a.npts + kEvalBinsPerBlock - 1) / kEvalBinsPerBlock);
