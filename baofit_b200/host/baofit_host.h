@@ -522,6 +522,8 @@ struct Options {
 };
 // Parses an INI text (key = value, '#' comments; "yes/true/1" switches; model-config composes).
 Options parseIni(std::string const &text);
+// keys outside the reference's option list, and options that select what this build does not have, throw (called by parseIni)
+void checkOptions(Options const &options);
 // src/baofit.cc:415-464: builds the model the options describe (r-space or --kspace).
 AbsCorrelationModelPtr createModel(Options const &opt, std::string const &baseDir);
 // src/baofit.cc:475-628 (comoving formats): builds, loads, cuts and finalizes the data set.

@@ -853,7 +853,41 @@ Options parseIni(std::string const &text) {
             o.values[key] = val;
         }
     }
+    checkOptions(o);
     return o;
+}
+
+// Every key must be an option src/baofit.cc:46-300 declares (boost::program_options rejects anything else the same way); options
+// that would select a model or a data treatment this build does not have are refused here instead of being ignored.
+void checkOptions(Options const &o) {
+    static const std::set<std::string> declared = {
+        "abserr", "abserr-hybrid", "alt-config", "anisotropic", "axis1-bins", "axis2-bins", "axis3-bins", "bin-smooth", "bin-smooth-alt",
+        "bootstrap-cov-trials", "bootstrap-size", "bootstrap-trials", "calculate-gradients", "check-posdef", "combined-bias", "combined-scale",
+        "compare-each", "compare-each-final", "constrained-multipoles", "cov-sample-size", "cross-correlation", "cspline", "custom-grid", "data",
+        "data-format", "decorrelated", "decoupled", "dilmax", "dilmin", "dist-add", "dist-matrix", "dist-matrix-dist-add", "dist-matrix-dist-mul",
+        "dist-matrix-name", "dist-matrix-order", "dist-mul", "dist-r0", "distortion-alt", "dll", "dll2", "dsep", "dz", "dzmin", "ell-max", "fiducial",
+        "fit-each", "fit-nl-correction", "fix-aln-cov", "fix-mode-scales", "gridscaling", "gridspacing", "hcd-model", "hcd-model-alt", "help",
+        "hubble-constant", "ini-file", "jackknife-drop", "khi-spline", "klo-spline", "kspace", "kspace-fft", "kspace-hybrid", "kxmax", "ll-max",
+        "ll-min", "lmax", "lmin", "load-icov", "load-wdata", "max-plates", "maxll", "mcmc-interval", "mcmc-save", "metal-civ", "metal-model",
+        "metal-model-interpolate", "metal-model-name", "min-method", "minll", "minsep", "minz", "model-config", "modelroot", "mu-max", "mu-min",
+        "n-spline", "naive-covariance", "ndump", "ngridx", "ngridy", "ngridz", "nl-broadband", "nl-correction", "nl-correction-alt",
+        "no-distortion", "no-initial-fit", "nowiggles", "nsep", "nz", "omega-matter", "order-spline", "output-prefix", "parameter-scan",
+        "platelist", "plateroot", "project-modes-keep", "quiet", "radiation-model", "random-seed", "refit-config", "relerr", "relerr-hybrid",
+        "reuse-cov", "rmax", "rmin", "rpar-max", "rpar-min", "rperp-max", "rperp-min", "rveto-center", "rveto-width", "samples-per-decade",
+        "save-data", "save-icov", "save-icov-scale", "scalar-weights", "sep-max", "sep-min", "sigma8", "smooth-gauss", "smooth-lorentz",
+        "toy-metal", "toymc-config", "toymc-samples", "toymc-save", "toymc-scale", "uvfluctuation", "xi-method", "xi-points", "z-max", "z-min",
+        "zcorr0", "zcorr1", "zcorr2", "zdump", "zeff", "zref",
+        // not reference options: the radiation density of the quasar-coordinate cosmology, and the counterpart of "quiet"
+        "omega-radiation", "verbose"};
+    for (auto const &kv : o.values)
+        if (!declared.count(kv.first)) throw RuntimeError("unrecognised option '" + kv.first + "'");
+    for (auto const &f : o.flags)
+        if (!declared.count(f)) throw RuntimeError("unrecognised option '" + f + "'");
+    // src/baofit.cc:415-423,504,406: models and data treatments outside the accelerated path
+    if (o.num("n-spline", 0) > 0) throw RuntimeError("n-spline > 0 selects PkCorrelationModel, which is not part of this build");
+    if (!o.str("xi-points").empty()) throw RuntimeError("xi-points selects XiCorrelationModel, which is not part of this build");
+    if (o.has("fix-aln-cov")) throw RuntimeError("fix-aln-cov (QuasarCorrelationData::fixCovariance) is not part of this build");
+    if (o.has("scalar-weights")) throw RuntimeError("scalar-weights (BinnedDataResampler with scalar weights) is not part of this build");
 }
 
 static std::string resolve(std::string const &baseDir, std::string const &path) {

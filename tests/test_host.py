@@ -158,3 +158,21 @@ def test_weighted_data_inverse_covariance_and_custom_grid(built, golden_tree, tm
     np.savetxt(prefix + ".grid", np.column_stack([np.arange(len(centres) - 1), half[:-1]]), fmt="%d %.17g %.17g %.17g")
     with pytest.raises(H.HostError, match="number of custom bins must match"):
         H.Session(text + "\ncustom-grid = yes\n", base)
+
+
+def test_options_outside_the_reference_list_are_rejected(built, golden_tree):
+    """boost::program_options rejects undeclared keys (src/baofit.cc:46-300, 313-340); options that would select a model or a
+    data treatment this build does not have are refused instead of being ignored."""
+    text, base = ini(golden_tree, "BOSSDR11QSOLyaF.ini")
+    with pytest.raises(H.HostError) as e:
+        H.Session(text + "\nrmaxx = 180\n", base)
+    assert e.value.code == -1 and "unrecognised option 'rmaxx'" in str(e.value)
+    for extra, what in (("xi-points = 50,100,150", "XiCorrelationModel"), ("n-spline = 10", "PkCorrelationModel"),
+                        ("fix-aln-cov = yes", "fix-aln-cov"), ("scalar-weights = yes", "scalar-weights")):
+        with pytest.raises(H.HostError) as e:
+            H.Session(text + "\n" + extra + "\n", base)
+        assert e.value.code == -1 and what in str(e.value)
+    # analysis-control options of the reference are accepted: they are arguments of the entry points here
+    s = H.Session(text + "\nbootstrap-trials = 10\noutput-prefix = x_\nrandom-seed = 7\ncheck-posdef = yes\nndump = 0\n", base)
+    assert s.ndata == 440
+    s.close()
