@@ -207,6 +207,12 @@ private:
 };
 // eigenmodes of a dense symmetric matrix: values ascending, vectors[k*n + i] = component i of mode k
 void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &values, std::vector<double> &vectors);
+// regularised upper incomplete gamma function Q(a, x) = 1 - P(a, x) (boost::math::gamma_p in the reference, CorrelationAnalyzer.cc:117)
+double gammaQ(double a, double x);
+class AbsCorrelationData;
+// data vector and covariance (never the inverse) over the bins with data (finalized = false) or over the kept bins of a
+// finalized data set
+void dataAndCovariance(AbsCorrelationData const &data, bool finalized, std::vector<double> &d, std::vector<double> &cov);
 BinnedGrid createCorrelationGrid(std::string const &axis1Bins, std::string const &axis2Bins,
                                  std::string const &axis3Bins);  // AbsCorrelationData.cc:96-150
 
@@ -493,6 +499,13 @@ public:
     // [first, first+count) of the sequence, count < 0: to its end. Returns the number of samples fitted.
     void setResampler(BinnedDataResamplerPtr resampler) { _resampler = resampler; }
     BinnedDataResamplerPtr resampler() const { return _resampler; }
+    // CorrelationAnalyzer::compareEach (CorrelationAnalyzer.cc:77-125; "compare-each" / "compare-each-final" of src/baofit.cc:636-645):
+    // every observation against the combined data, before (finalized = false) or after the final cuts. Per observation:
+    // log|C_k| / n, chi2 = sum over the eigenmodes of C_k - C_ref of (v_m . (d_k - d_ref))^2 / lambda_m, and its chi-square
+    // probability for n degrees of freedom; the per-mode contributions go to the file (empty name: no file),
+    // "<k> <log|C|/n> <chi2> <mode 0> ... <mode n-1>" with modes in ascending eigenvalue order.
+    void compareEach(std::string const &saveName, bool finalized, std::vector<double> &prob, std::vector<double> &chi2,
+                     std::vector<double> &logDet) const;
     long resamplingSize(std::string const &kind, int n) const;
     AbsCorrelationDataPtr resample(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long seqno) const;
     long doResampling(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long first, long count,

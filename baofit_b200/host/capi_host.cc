@@ -315,6 +315,21 @@ extern "C" int bfh_save_data(bfh_session *s, const char *data_path, const char *
     BFH_CATCH
 }
 
+extern "C" double bfh_gamma_q(double a, double x) {
+    try { return gammaQ(a, x); } catch (std::exception const &e) { g_herr = e.what(); return -1.0; }
+}
+
+extern "C" int bfh_compare_each(bfh_session *s, const char *path, int finalized, double *prob, double *chi2, double *logdet) {
+    BFH_TRY
+    if (!s) throw RuntimeError("bfh_compare_each: null session");
+    std::vector<double> p, c, l;
+    s->analyzer->compareEach(path ? path : "", finalized != 0, p, c, l);
+    if (prob) std::copy(p.begin(), p.end(), prob);
+    if (chi2) std::copy(c.begin(), c.end(), chi2);
+    if (logdet) std::copy(l.begin(), l.end(), logdet);
+    BFH_CATCH
+}
+
 extern "C" int bfh_symmetric_eigenmodes(int n, const double *matrix, double *values, double *vectors) {
     BFH_TRY
     if (n <= 0 || !matrix || !values || !vectors) throw RuntimeError("bfh_symmetric_eigenmodes: bad arguments");

@@ -321,6 +321,53 @@ void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &valu
     }
 }
 
+// Q(a, x): series for x < a + 1, Lentz continued fraction otherwise (the two standard expansions of the incomplete gamma function)
+double gammaQ(double a, double x) {
+    if (!(a > 0) || x < 0) throw RuntimeError("gammaQ: invalid arguments");
+    if (x == 0) return 1.0;
+    const double lg = std::lgamma(a);
+    if (x < a + 1.0) {
+        double term = 1.0 / a, sum = term, ap = a;
+        for (int it = 0; it < 100000; ++it) {
+            ap += 1.0;
+            term *= x / ap;
+            sum += term;
+            if (std::fabs(term) < std::fabs(sum) * 1e-16) break;
+        }
+        return 1.0 - sum * std::exp(-x + a * std::log(x) - lg);
+    }
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, dd = 1.0 / b, h = dd;
+    for (int it = 1; it < 100000; ++it) {
+        const double an = -it * (it - a);
+        b += 2.0;
+        dd = an * dd + b;
+        if (std::fabs(dd) < tiny) dd = tiny;
+        c = b + an / c;
+        if (std::fabs(c) < tiny) c = tiny;
+        dd = 1.0 / dd;
+        const double delta = dd * c;
+        h *= delta;
+        if (std::fabs(delta - 1.0) < 1e-16) break;
+    }
+    return std::exp(-x + a * std::log(x) - lg) * h;
+}
+
+void dataAndCovariance(AbsCorrelationData const &data, bool finalized, std::vector<double> &d, std::vector<double> &cov) {
+    if (finalized) {
+        if (!data.isFinalized()) throw RuntimeError("dataAndCovariance: data set is not finalized.");
+        d = data.dataVector();
+        cov = data.covarianceMatrix();
+    } else {
+        std::vector<int> bins = data.binsWithData();
+        d.resize(bins.size());
+        for (size_t i = 0; i < bins.size(); ++i) d[i] = data.getData(bins[i]);
+        cov = data.denseOverBinsWithData();
+    }
+    if (data.isWeighted()) throw RuntimeError("dataAndCovariance: weighted data (Cinv.d) must be finalized first.");
+    if (data.isInverse()) cov = spdInverse((int)d.size(), cov, "the inverse covariance");
+}
+
 // likely::BinnedData::projectOntoModes as src/baofit.cc:597-603 uses it (before the final cuts): the data vector is replaced by
 // its projection onto the nkeep eigenmodes of the covariance with the largest (nkeep > 0) or smallest (nkeep < 0) variance;
 // the covariance stays as it is. UNVERIFIED (dep): restated from the option's documentation (src/baofit.cc:194-195).

@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "baofit_host.h"
+#include "../csrc/host_setup.h"
 
 namespace baofit {
 
@@ -1008,6 +1009,62 @@ AbsCorrelationDataPtr createData(Options const &opt, std::string const &baseDir,
     if (projectModesNKeep != 0) data->projectOntoModes(projectModesNKeep);
     data->finalize();
     return data;
+}
+
+void CorrelationAnalyzer::compareEach(std::string const &saveName, bool finalized, std::vector<double> &prob, std::vector<double> &chi2,
+                                      std::vector<double> &logDet) const {
+    if (!_resampler || _resampler->getNObservations() <= 1) throw RuntimeError("CorrelationAnalyzer::compareEach: needs > 1 observation (plateroot/platelist).");
+    std::ofstream out;
+    if (!saveName.empty()) {
+        out.open(saveName.c_str());
+        if (!out.good()) throw RuntimeError("CorrelationAnalyzer::compareEach: unable to open " + saveName);
+    }
+    // the combined data as the reference (CorrelationAnalyzer.cc:84-87)
+    AbsCorrelationDataPtr refData = _resampler->combined();
+    if (finalized) refData->finalize();
+    std::vector<double> dref, cref;
+    dataAndCovariance(*refData, finalized, dref, cref);
+    const int n = (int)dref.size(), nobs = _resampler->getNObservations();
+    prob.assign(nobs, 0.0);
+    chi2.assign(nobs, 0.0);
+    logDet.assign(nobs, 0.0);
+    char buf[64];
+    for (int k = 0; k < nobs; ++k) {
+        AbsCorrelationDataPtr observation = _resampler->getObservationCopy(k);
+        if (finalized) observation->finalize();
+        std::vector<double> dk, ck;
+        dataAndCovariance(*observation, finalized, dk, ck);
+        if ((int)dk.size() != n) throw RuntimeError("CorrelationAnalyzer::compareEach: observation is not congruent with the combined data.");
+        // log|C_k| / n from the Cholesky factor
+        std::vector<double> L = ck;
+        if (!bf::cholesky_lower(n, L.data())) throw RuntimeError("CorrelationAnalyzer::compareEach: observation covariance is not positive definite.");
+        double ld = 0;
+        for (int i = 0; i < n; ++i) ld += 2.0 * std::log(L[(size_t)i * n + i]);
+        logDet[k] = ld / n;
+        // chi-square of (d_k - d_ref) with covariance C_k - C_ref, mode by mode (:102-115)
+        for (size_t q = 0; q < ck.size(); ++q) ck[q] -= cref[q];
+        std::vector<double> values, modes;
+        symmetricEigenModes(n, ck, values, modes);
+        std::vector<double> chi2modes(n);
+        double sum = 0;
+        for (int mI = 0; mI < n; ++mI) {
+            const double *mode = &modes[(size_t)mI * n];
+            double dot = 0;
+            for (int i = 0; i < n; ++i) dot += mode[i] * (dk[i] - dref[i]);
+            chi2modes[mI] = dot * dot / values[mI];
+            sum += chi2modes[mI];
+        }
+        chi2[k] = sum;
+        prob[k] = sum > 0 ? gammaQ(0.5 * n, 0.5 * sum) : 1.0;  // 1 - gamma_p(n/2, chi2/2), :117
+        if (out.is_open()) {
+            out << k << ' ' << logDet[k] << ' ' << chi2[k];
+            for (int mI = 0; mI < n; ++mI) {
+                std::snprintf(buf, sizeof(buf), " %.4lg", chi2modes[mI]);
+                out << buf;
+            }
+            out << std::endl;
+        }
+    }
 }
 
 // ---- resampling analyses ----------------------------------------------------------------------

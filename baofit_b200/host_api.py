@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q"]
 
 
 def lib():
@@ -57,6 +57,7 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                               C.c_void_p]
         L.bfh_save_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.bfh_compare_each.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_symmetric_eigenmodes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
         L.bfh_resampling_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long)]
@@ -242,6 +243,13 @@ class Session:
 
     def save_data(self, data_path=None, icov_path=None):
         _check(lib().bfh_save_data(self.h, data_path.encode() if data_path else None, icov_path.encode() if icov_path else None))
+
+    def compare_each(self, path=None, finalized=False):
+        """CorrelationAnalyzer::compareEach: every observation against the combined data; returns prob, chi2, log|C|/n."""
+        n = self.nobservations
+        prob, chi2, logdet = np.zeros(n), np.zeros(n), np.zeros(n)
+        _check(lib().bfh_compare_each(self.h, path.encode() if path else None, 1 if finalized else 0, _p(prob), _p(chi2), _p(logdet)))
+        return prob, chi2, logdet
 
     # ---- jackknife / bootstrap / fit-each over the observations of a plateroot/platelist session ----
     @property

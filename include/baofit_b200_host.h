@@ -89,6 +89,13 @@ int bfh_write_samples_refit(bfh_session *s, const char *path, const double *best
 /* save-data / save-icov of src/baofit.cc:612-626: the finalized (combined, cut) data set as "<index> <value>" and
  * "<i> <j> <Cinv_ij>" text files that bfh_session_create reads back with load-icov. Either path may be NULL. */
 int bfh_save_data(bfh_session *s, const char *data_path, const char *icov_path);
+/* CorrelationAnalyzer::compareEach (baofit/CorrelationAnalyzer.cc:77-125; compare-each / compare-each-final, src/baofit.cc:636-645):
+ * every observation of a plateroot/platelist session against the combined data before (finalized = 0) or after the final cuts.
+ * Per observation: chi-square probability, chi2 over the eigenmodes of C_k - C_combined, log|C_k| / n; the per-mode contributions go
+ * to the text file `path` ("<k> <log|C|/n> <chi2> <modes...>", may be NULL). Outputs are [nobservations] each and may be NULL. Host only. */
+int bfh_compare_each(bfh_session *s, const char *path, int finalized, double *prob, double *chi2, double *logdet);
+/* regularised upper incomplete gamma function Q(a, x) used for that probability (boost::math::gamma_p in the reference); -1 on bad arguments */
+double bfh_gamma_q(double a, double x);
 /* Eigenmodes of a dense symmetric n x n matrix, the decomposition behind project-modes-keep (src/baofit.cc:194,597-603;
  * likely::CovarianceMatrix::getEigenModes in the reference): values ascending, vectors[k*n + i] = component i of mode k. Host only. */
 int bfh_symmetric_eigenmodes(int n, const double *matrix, double *values /* [n] */, double *vectors /* [n*n] */);

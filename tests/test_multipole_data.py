@@ -193,6 +193,47 @@ def test_resampler_jackknife_bootstrap_each(built, golden_tree):
         single.resampling_size("each")
 
 
+def test_compare_each_against_numpy(built, golden_tree, tmp_path):
+    """CorrelationAnalyzer::compareEach (CorrelationAnalyzer.cc:77-125): chi-square of every observation against the combined
+    data over the eigenmodes of C_k - C_combined, its probability, log|C_k| / n; before and after the final cuts."""
+    from scipy.special import gammaincc
+    text, base, obs = _write_observations(golden_tree, 4, seed=23)
+    s = H.Session(text, base)
+    dref, cref = _combine(obs, [1, 1, 1, 1], False)
+    for finalized in (False, True):  # every bin with data survives the cuts of this recipe: same numbers both ways
+        path = str(tmp_path / ("compare_%d.dat" % finalized))
+        prob, chi2, logdet = s.compare_each(path, finalized=finalized)
+        rows = [l.split() for l in open(path)]
+        assert len(rows) == 4
+        for k, (dk, ck) in enumerate(obs):
+            n = len(dk)
+            w, v = np.linalg.eigh(ck - cref)
+            modes = (v.T @ (dk - dref)) ** 2 / w
+            assert abs(chi2[k] - modes.sum()) < 1e-8 * modes.sum()
+            assert abs(logdet[k] - np.linalg.slogdet(ck)[1] / n) < 1e-10
+            assert abs(prob[k] - gammaincc(0.5 * n, 0.5 * chi2[k])) < 1e-10
+            assert int(rows[k][0]) == k and len(rows[k]) == 3 + n
+            assert abs(float(rows[k][2]) - chi2[k]) < 1e-4 * chi2[k]
+            got = np.array([float(x) for x in rows[k][3:]])
+            assert np.allclose(got, modes, rtol=2e-3, atol=1e-3 * modes.max())   # " %.4lg" per mode, ascending eigenvalue order
+    single = H.Session(text.replace("platelist = rs.list", "").replace("plateroot = ../data/", "data = ../data/rs_0"), base)
+    with pytest.raises(H.HostError, match="needs > 1 observation"):
+        single.compare_each()
+
+
+def test_incomplete_gamma_matches_scipy(built):
+    """gammaQ behind compareEach's probability, through a two-observation comparison is indirect: check the tails directly."""
+    from scipy.special import gammaincc
+    import ctypes as C
+    L = H.lib()
+    L.bfh_gamma_q.restype = C.c_double
+    L.bfh_gamma_q.argtypes = [C.c_double, C.c_double]
+    for a in (0.5, 1.0, 7.5, 43.5, 220.0, 757.5):
+        for x in (1e-3, 0.3 * a, a, a + 1.0, 1.7 * a, 4.0 * a):
+            ref = gammaincc(a, x)
+            assert abs(L.bfh_gamma_q(a, x) - ref) < 1e-12 + 1e-10 * ref, (a, x)
+
+
 @pytest.mark.gpu
 def test_resampling_fits_match_direct_sessions(built, golden_tree):
     """bfh_resample_fit: the fit of jackknife sample k equals the fit of a session built from the platelist without
