@@ -19,6 +19,7 @@ struct bfh_session {
     BinnedDataResamplerPtr resampler;  // platelist sessions only
     std::shared_ptr<CorrelationFitter> fitter;
     std::shared_ptr<CorrelationAnalyzer> analyzer;
+    likely::FunctionMinimumPtr lastFit;  // of the latest bfh_fit without a config script (the "initial fit" of src/baofit.cc:646-660)
 };
 
 static thread_local std::string g_herr;
@@ -160,6 +161,7 @@ extern "C" int bfh_fit(bfh_session *s, const char *config, double *values, doubl
                        int *nevaluations, double *covariance) {
     BFH_TRY
     likely::FunctionMinimumPtr fm = s->fitter->fit("mn2::vmetric", config ? config : "");
+    if (!config || !*config) s->lastFit = fm;
     for (size_t i = 0; i < fm->parameters.size(); ++i) {
         if (values) values[i] = fm->parameters[i].value;
         if (errors) errors[i] = fm->parameters[i].floating ? fm->parameters[i].error : 0.0;
@@ -168,6 +170,65 @@ extern "C" int bfh_fit(bfh_session *s, const char *config, double *values, doubl
     if (status) *status = (int)fm->status;
     if (nevaluations) *nevaluations = fm->nEvaluations;
     if (covariance) std::copy(fm->covariance.begin(), fm->covariance.end(), covariance);
+    BFH_CATCH
+}
+
+// The result files src/baofit.cc:661-687 writes after the fit of the combined sample, with its file names.
+extern "C" int bfh_write_fit_outputs(bfh_session *s, const char *prefix) {
+    BFH_TRY
+    if (!s || !s->lastFit) throw RuntimeError("bfh_write_fit_outputs: call bfh_fit (without a config script) first");
+    likely::FunctionMinimum const &fm = *s->lastFit;
+    const std::string pre = prefix ? prefix : "";
+    auto open = [&](std::string const &name, std::ofstream &out) {
+        out.open((pre + name).c_str());
+        if (!out.good()) throw RuntimeError("bfh_write_fit_outputs: unable to open " + pre + name);
+    };
+    char buf[256];
+    int nfloat = 0;
+    for (auto const &p : fm.parameters) nfloat += p.floating ? 1 : 0;
+    {   // CorrelationAnalyzer::dumpChisquare, CorrelationAnalyzer.cc:192-206: "chisq nbins npar prob" (prob = -1 if undefined)
+        std::ofstream out;
+        open("fit.chisq", out);
+        const double chisq = 2 * fm.minValue;
+        const int nbins = (int)s->data->keptIndices().size();
+        if (chisq > 0 && nbins > nfloat) {
+            std::snprintf(buf, sizeof(buf), "%.17g %d %d %.17g", chisq, nbins, nfloat, gammaQ(0.5 * (nbins - nfloat), 0.5 * chisq));
+        } else
+            std::snprintf(buf, sizeof(buf), "%.17g %d %d -1", chisq, nbins, nfloat);
+        out << buf << std::endl;
+    }
+    {   // likely::fitParametersToScript: the fitted parameters as a model-config script (dependency absent: our own statements,
+        // which configureFitParameters reads back)
+        std::ofstream out;
+        open("fit.config", out);
+        for (auto const &p : fm.parameters) {
+            if (p.floating) std::snprintf(buf, sizeof(buf), "value[%s]=%.17g; error[%s]=%.17g;", p.name.c_str(), p.value, p.name.c_str(), p.error);
+            else std::snprintf(buf, sizeof(buf), "fix[%s]=%.17g;", p.name.c_str(), p.value);
+            out << buf << std::endl;
+        }
+    }
+    {   // FunctionMinimum::saveParameters: "<index> <value> <error>", error 0 for fixed parameters (layout ours, dependency absent)
+        std::ofstream out;
+        open("save.pars", out);
+        for (size_t i = 0; i < fm.parameters.size(); ++i) {
+            std::snprintf(buf, sizeof(buf), "%d %.17g %.17g", (int)i, fm.parameters[i].value, fm.parameters[i].floating ? fm.parameters[i].error : 0.0);
+            out << buf << std::endl;
+        }
+    }
+    if ((int)fm.covariance.size() == nfloat * nfloat && nfloat > 0) {
+        // FunctionMinimum::saveFloatingParameterCovariance: "<i> <j> <cov_ij>" over the floating parameters, j <= i, indexed in the
+        // full parameter list (layout ours, dependency absent)
+        std::ofstream out;
+        open("save.pcov", out);
+        std::vector<int> index;
+        for (size_t i = 0; i < fm.parameters.size(); ++i)
+            if (fm.parameters[i].floating) index.push_back((int)i);
+        for (int a = 0; a < nfloat; ++a)
+            for (int b = 0; b <= a; ++b) {
+                std::snprintf(buf, sizeof(buf), "%d %d %.17g", index[a], index[b], fm.covariance[(size_t)a * nfloat + b]);
+                out << buf << std::endl;
+            }
+    }
     BFH_CATCH
 }
 

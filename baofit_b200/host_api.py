@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs"]
 
 
 def lib():
@@ -57,6 +57,7 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                               C.c_void_p]
         L.bfh_save_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.bfh_write_fit_outputs.argtypes = [C.c_void_p, C.c_char_p]
         L.bfh_compare_each.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_symmetric_eigenmodes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
@@ -196,6 +197,10 @@ class Session:
         _check(lib().bfh_fit(self.h, config.encode(), _p(v), _p(e), C.byref(fval), C.byref(status), C.byref(nev), _p(cov)))
         return dict(values=v, errors=e, fval=fval.value, status=status.value, nevaluations=nev.value,
                     covariance=cov.ravel()[:nf * nf].reshape(nf, nf) if config == "" else None)
+
+    def write_fit_outputs(self, prefix):
+        """fit.chisq, fit.config, save.pars, save.pcov of the latest fit() without a config (src/baofit.cc:661-687)."""
+        _check(lib().bfh_write_fit_outputs(self.h, prefix.encode()))
 
     def scan_size(self):
         n = C.c_long()

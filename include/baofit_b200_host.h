@@ -55,6 +55,11 @@ int bfh_predict_batch(bfh_session *s, const double *params, int B, double *pred)
  * covariance of the floating parameters [nfloat*nfloat] (may be NULL) */
 int bfh_fit(bfh_session *s, const char *config, double *values, double *errors, double *fval, int *status,
             int *nevaluations, double *covariance);
+/* The result files of src/baofit.cc:661-687 for the latest bfh_fit without a config script: <prefix>fit.chisq ("chisq nbins npar prob",
+ * CorrelationAnalyzer::dumpChisquare, baofit/CorrelationAnalyzer.cc:192-206), <prefix>fit.config (the fitted parameters as a model-config
+ * script that bfh_session_create's extra_config reads back), <prefix>save.pars ("index value error"), <prefix>save.pcov ("i j cov_ij" over
+ * the floating parameters, j <= i; only if the fit has a covariance). */
+int bfh_write_fit_outputs(bfh_session *s, const char *prefix);
 /* CorrelationAnalyzer::parameterScan over grid points [first, first+count) (count<0: all):
  * chi2[count] = 2*fval, points[count*npar], status[count]; best[npar+1] = unconstrained best fit
  * values followed by its 2*fval. Returns the total grid size through *total. */

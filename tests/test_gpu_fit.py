@@ -188,3 +188,33 @@ def test_scan_with_more_floating_parameters_than_a_probe_group(built, golden_tre
     res = s.parameter_scan()
     assert len(res["chi2"]) == 4 and np.all(np.isfinite(res["chi2"])) and np.all(res["status"] != 2)
     assert np.all(res["chi2"] >= res["best_chi2"] - 1e-6)
+
+
+def test_fit_output_files(built, golden_tree, tmp_path):
+    """fit.chisq / fit.config / save.pars / save.pcov of src/baofit.cc:661-687 after the fit of the combined sample."""
+    from scipy.special import gammaincc
+    text = open(os.path.join(golden_tree, "config", "rmu_to_bao.ini")).read()
+    base = os.path.join(golden_tree, "config")
+    s = H.Session(text, base)
+    with pytest.raises(H.HostError, match="bfh_fit"):
+        s.write_fit_outputs(str(tmp_path / "early_"))
+    r = s.fit()
+    prefix = str(tmp_path / "rmu_")
+    s.write_fit_outputs(prefix)
+    nf = int(s.floating.sum())
+    chisq, nbins, npar, prob = open(prefix + "fit.chisq").read().split()
+    assert float(chisq) == 2 * r["fval"] and int(nbins) == s.ndata and int(npar) == nf
+    assert abs(float(prob) - gammaincc(0.5 * (s.ndata - nf), r["fval"])) < 1e-10
+    pars = np.loadtxt(prefix + "save.pars")
+    assert np.array_equal(pars[:, 0], np.arange(s.npar)) and np.array_equal(pars[:, 1], r["values"]) and np.array_equal(pars[:, 2], r["errors"])
+    pcov = np.loadtxt(prefix + "save.pcov")
+    idx = np.nonzero(s.floating)[0]
+    assert len(pcov) == nf * (nf + 1) // 2
+    for i, j, c in pcov:
+        assert c == r["covariance"][list(idx).index(int(i)), list(idx).index(int(j))]
+    # the script reproduces the fitted state in a new session
+    script = " ".join(l.strip() for l in open(prefix + "fit.config"))
+    again = H.Session(text, base, extra_config=script)
+    assert np.array_equal(again.values, r["values"]) and np.array_equal(again.floating, s.floating)
+    assert np.allclose(again.errors[s.floating], r["errors"][s.floating], rtol=1e-15)
+    s.close(), again.close()
