@@ -506,6 +506,12 @@ public:
     // "<k> <log|C|/n> <chi2> <mode 0> ... <mode n-1>" with modes in ascending eigenvalue order.
     void compareEach(std::string const &saveName, bool finalized, std::vector<double> &prob, std::vector<double> &chi2,
                      std::vector<double> &logDet) const;
+    // CorrelationAnalyzer::estimateCombinedCovariance (CorrelationAnalyzer.cc:733-746; "bootstrap-cov-trials", src/baofit.cc:736-756):
+    // sample covariance, over nSamples bootstrap draws of the observations, of the combined (unfinalized) data vector; dense over
+    // the bins with data (returned in bins). With icovName, its inverse is written in the loader's "i j value" format when the
+    // estimate is positive definite ("bs.icov"). Returns whether it is. Draws: bootstrapCounts(0, seed, trial).
+    bool estimateCombinedCovariance(int nSamples, unsigned long long seed, std::string const &icovName, std::vector<int> &bins,
+                                    std::vector<double> &cov) const;
     long resamplingSize(std::string const &kind, int n) const;
     AbsCorrelationDataPtr resample(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long seqno) const;
     long doResampling(std::string const &kind, int n, int size, bool fixCovariance, unsigned long long seed, long first, long count,

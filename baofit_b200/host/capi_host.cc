@@ -376,6 +376,21 @@ extern "C" int bfh_save_data(bfh_session *s, const char *data_path, const char *
     BFH_CATCH
 }
 
+extern "C" int bfh_bootstrap_covariance(bfh_session *s, int trials, unsigned long long seed, const char *icov_path, double *cov, int cov_order,
+                                        int *bins, int *posdef) {
+    BFH_TRY
+    if (!s) throw RuntimeError("bfh_bootstrap_covariance: null session");
+    std::vector<int> b;
+    std::vector<double> c;
+    const bool ok = s->analyzer->estimateCombinedCovariance(trials, seed, icov_path ? icov_path : "", b, c);
+    if ((cov || bins) && cov_order != (int)b.size())
+        throw RuntimeError("bfh_bootstrap_covariance: the combined data have " + std::to_string(b.size()) + " bins with data");
+    if (cov) std::copy(c.begin(), c.end(), cov);
+    if (bins) std::copy(b.begin(), b.end(), bins);
+    if (posdef) *posdef = ok ? 1 : 0;
+    BFH_CATCH
+}
+
 extern "C" double bfh_gamma_q(double a, double x) {
     try { return gammaQ(a, x); } catch (std::exception const &e) { g_herr = e.what(); return -1.0; }
 }

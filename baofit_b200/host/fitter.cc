@@ -1067,6 +1067,52 @@ void CorrelationAnalyzer::compareEach(std::string const &saveName, bool finalize
     }
 }
 
+bool CorrelationAnalyzer::estimateCombinedCovariance(int nSamples, unsigned long long seed, std::string const &icovName, std::vector<int> &bins,
+                                                     std::vector<double> &cov) const {
+    if (!_resampler || _resampler->getNObservations() <= 1) throw RuntimeError("CorrelationAnalyzer::estimateCombinedCovariance: needs > 1 observation (plateroot/platelist).");
+    if (nSamples < 2) throw RuntimeError("CorrelationAnalyzer::estimateCombinedCovariance: expected at least 2 samples.");
+    // Welford accumulation of the combined data vector over the draws (likely::CovarianceAccumulator in the reference; the
+    // unbiased 1/(N-1) normalisation is ours, the dependency is absent)
+    std::vector<double> mean, m2, d, c;
+    int n = 0;
+    for (long trial = 0; trial < nSamples; ++trial) {
+        AbsCorrelationDataPtr sample = _resampler->bootstrap(0, false, seed, trial);
+        dataAndCovariance(*sample, false, d, c);
+        if (trial == 0) {
+            bins = sample->binsWithData();
+            n = (int)d.size();
+            mean.assign(n, 0.0);
+            m2.assign((size_t)n * n, 0.0);
+        }
+        std::vector<double> delta(n);
+        for (int i = 0; i < n; ++i) { delta[i] = d[i] - mean[i]; mean[i] += delta[i] / (trial + 1); }
+        for (int i = 0; i < n; ++i) {
+            const double di = delta[i];
+            for (int j = 0; j <= i; ++j) m2[(size_t)i * n + j] += di * (d[j] - mean[j]);
+        }
+    }
+    cov.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) cov[(size_t)i * n + j] = cov[(size_t)j * n + i] = m2[(size_t)i * n + j] / (nSamples - 1);
+    std::vector<double> L = cov;
+    const bool posdef = bf::cholesky_lower(n, L.data());
+    if (posdef && !icovName.empty()) {
+        std::vector<double> li((size_t)n * n, 0.0);
+        bf::invert_lower(n, L.data(), li.data());
+        std::ofstream out(icovName.c_str());
+        if (!out.good()) throw RuntimeError("CorrelationAnalyzer::estimateCombinedCovariance: unable to open " + icovName);
+        char buf[96];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double sum = 0;
+                for (int k = i; k < n; ++k) sum += li[(size_t)k * n + i] * li[(size_t)k * n + j];  // (L^-T L^-1)_ij
+                std::snprintf(buf, sizeof(buf), "%d %d %.17g", bins[i], bins[j], sum);
+                out << buf << std::endl;
+            }
+    }
+    return posdef;
+}
+
 // ---- resampling analyses ----------------------------------------------------------------------
 long CorrelationAnalyzer::resamplingSize(std::string const &kind, int n) const {
     if (!_resampler || _resampler->getNObservations() <= 1) throw RuntimeError("CorrelationAnalyzer: resampling needs > 1 observation (plateroot/platelist).");

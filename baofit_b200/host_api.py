@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs", "bfh_bootstrap_covariance"]
 
 
 def lib():
@@ -58,6 +58,7 @@ def lib():
                                               C.c_void_p]
         L.bfh_save_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.bfh_write_fit_outputs.argtypes = [C.c_void_p, C.c_char_p]
+        L.bfh_bootstrap_covariance.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.bfh_compare_each.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_symmetric_eigenmodes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
@@ -248,6 +249,13 @@ class Session:
 
     def save_data(self, data_path=None, icov_path=None):
         _check(lib().bfh_save_data(self.h, data_path.encode() if data_path else None, icov_path.encode() if icov_path else None))
+
+    def bootstrap_covariance(self, trials, nbins, seed=1966, icov_path=None):
+        """CorrelationAnalyzer::estimateCombinedCovariance: (bins, covariance over them, positive definite?)."""
+        cov, bins, ok = np.zeros((nbins, nbins)), np.zeros(nbins, dtype=np.int32), C.c_int()
+        _check(lib().bfh_bootstrap_covariance(self.h, trials, seed, icov_path.encode() if icov_path else None, _p(cov), nbins, _p(bins),
+                                              C.byref(ok)))
+        return bins, cov, bool(ok.value)
 
     def compare_each(self, path=None, finalized=False):
         """CorrelationAnalyzer::compareEach: every observation against the combined data; returns prob, chi2, log|C|/n."""

@@ -99,6 +99,12 @@ int bfh_save_data(bfh_session *s, const char *data_path, const char *icov_path);
  * Per observation: chi-square probability, chi2 over the eigenmodes of C_k - C_combined, log|C_k| / n; the per-mode contributions go
  * to the text file `path` ("<k> <log|C|/n> <chi2> <modes...>", may be NULL). Outputs are [nobservations] each and may be NULL. Host only. */
 int bfh_compare_each(bfh_session *s, const char *path, int finalized, double *prob, double *chi2, double *logdet);
+/* CorrelationAnalyzer::estimateCombinedCovariance (baofit/CorrelationAnalyzer.cc:733-746; bootstrap-cov-trials, src/baofit.cc:736-756):
+ * sample covariance of the combined, unfinalized data vector over `trials` bootstrap draws of the observations (the draws of
+ * bfh_bootstrap_counts with size 0). cov [cov_order^2] and bins [cov_order] may be NULL; cov_order = number of bins with data.
+ * With icov_path the inverse is written in the loader's format when the estimate is positive definite (*posdef). Host only. */
+int bfh_bootstrap_covariance(bfh_session *s, int trials, unsigned long long seed, const char *icov_path, double *cov, int cov_order,
+                             int *bins, int *posdef);
 /* regularised upper incomplete gamma function Q(a, x) used for that probability (boost::math::gamma_p in the reference); -1 on bad arguments */
 double bfh_gamma_q(double a, double x);
 /* Eigenmodes of a dense symmetric n x n matrix, the decomposition behind project-modes-keep (src/baofit.cc:194,597-603;

@@ -221,6 +221,34 @@ def test_compare_each_against_numpy(built, golden_tree, tmp_path):
         single.compare_each()
 
 
+def test_bootstrap_estimate_of_the_combined_covariance(built, golden_tree, tmp_path):
+    """CorrelationAnalyzer::estimateCombinedCovariance (bootstrap-cov-trials): sample covariance of the combined data vector over
+    bootstrap draws, its inverse saved in the loader's format when it is positive definite."""
+    text, base, obs = _write_observations(golden_tree, 6, seed=24)
+    s = H.Session(text, base)
+    n, trials = len(obs[0][0]), 40
+    path = str(tmp_path / "bs.icov")
+    bins, cov, ok = s.bootstrap_covariance(trials, n, seed=5, icov_path=path)
+    samples = np.array([_combine(obs, list(s.bootstrap_counts(t, seed=5)), False)[0] for t in range(trials)])
+    ref = np.cov(samples.T, ddof=1)
+    assert np.max(np.abs(cov - ref)) < 1e-9 * np.max(np.abs(ref))
+    assert np.array_equal(bins, s.kept_indices())            # this recipe cuts nothing
+    assert not ok and not os.path.exists(path)                # 40 draws of 87 bins: rank deficient, nothing is written
+    with pytest.raises(H.HostError, match="87 bins"):
+        s.bootstrap_covariance(trials, n - 1, seed=5)
+    # more observations than bins and enough draws: the estimate is positive definite and the file holds its inverse
+    text, base, obs = _write_observations(golden_tree, 100, seed=25)
+    s = H.Session(text, base)
+    bins, cov, ok = s.bootstrap_covariance(300, n, seed=6, icov_path=path)
+    assert ok
+    rows = np.loadtxt(path)
+    icov = np.zeros((n, n))
+    pos = {int(b): k for k, b in enumerate(bins)}
+    for i, j, v in rows:
+        icov[pos[int(i)], pos[int(j)]] = icov[pos[int(j)], pos[int(i)]] = v
+    assert np.max(np.abs(icov @ cov - np.eye(n))) < 1e-6
+
+
 def test_incomplete_gamma_matches_scipy(built):
     """gammaQ behind compareEach's probability, through a two-observation comparison is indirect: check the tails directly."""
     from scipy.special import gammaincc
