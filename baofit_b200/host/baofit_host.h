@@ -438,6 +438,8 @@ public:
     AbsCorrelationModelPtr model() const { return _model; }
     AbsCorrelationDataPtr data() const { return _data; }
     double icovScale() const { return _icovScale; }
+    // the covariance of the data times `factor` (toy studies with toymc-scale): chi2 terms are weighted by icovScale / factor
+    void scaleCovariance(double factor) { _icovScale /= factor; }
 
 private:
     AbsCorrelationDataPtr _data;
@@ -488,6 +490,9 @@ public:
                       std::vector<std::vector<double>> const *refitted = nullptr, std::vector<double> const *rechi2 = nullptr) const;
     // refitConfig (the reference's refit-config, CorrelationAnalyzer.cc:491-503): every sample is fitted a second time
     // with this script applied to the initial parameters; results go to refitted / rechi2 / restatus.
+    // "toymc-scale" (src/baofit.cc:294, CorrelationAnalyzer.cc:349-357): the covariance of the toy prototype times this factor, for the
+    // noise and, as the reference's code has it, for the fits of the toys (their chi2 is 1/scale of the unscaled one)
+    void setToyMCScale(double varianceScale);
     void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
                          std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "",
                          std::string const &refitConfig = "", std::vector<std::vector<double>> *refitted = nullptr,
@@ -523,6 +528,7 @@ private:
     std::string _method;
     double _rmin, _rmax;
     int _covSampleSize;
+    double _toyScale = 1.0;
     bool _verbose;
     AbsCorrelationDataPtr _data;
     AbsCorrelationModelPtr _model;

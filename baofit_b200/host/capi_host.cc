@@ -71,6 +71,7 @@ extern "C" int bfh_session_create(const char *ini_text, const char *base_dir, co
         s->analyzer->addData(s->data);
         s->analyzer->setModel(s->model);
         s->analyzer->setResampler(s->resampler);
+        s->analyzer->setToyMCScale(s->options.num("toymc-scale", 1));
     } catch (std::exception const &e) { g_herr = e.what(); delete s; return -4; }
     *out = s;
     return 0;

@@ -705,6 +705,11 @@ void CorrelationAnalyzer::writeScan(std::string const &path, ScanResult const &s
     }
 }
 
+void CorrelationAnalyzer::setToyMCScale(double varianceScale) {
+    if (!(varianceScale > 0)) throw RuntimeError("CorrelationAnalyzer::doMCSampling: expected varianceScale > 0.");
+    _toyScale = varianceScale;
+}
+
 void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long long seed,
                                           std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
                                           std::vector<int> &status, std::string const &toymcConfig, std::string const &refitConfig,
@@ -727,9 +732,10 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
     // the realisations are drawn on the GPU and stay there; every evaluation point carries the
     // index of the toy it belongs to
     bf_toys *toys = nullptr;
-    check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, 1.0, &toys), "bf_toys_create");
+    check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, std::sqrt(_toyScale), &toys), "bf_toys_create");
     std::shared_ptr<bf_toys> guard(toys, [](bf_toys *t) { bf_toys_destroy(t); });
     double tToys = nowSeconds();
+    if (_toyScale != 1) fitter.scaleCovariance(_toyScale);  // after the truth prediction; applies to the LM and Newton drivers alike
     const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();
     std::vector<int> toyOfFit(count);
     for (long t = 0; t < count; ++t) toyOfFit[t] = (int)t;

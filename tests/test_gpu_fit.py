@@ -218,3 +218,28 @@ def test_fit_output_files(built, golden_tree, tmp_path):
     assert np.array_equal(again.values, r["values"]) and np.array_equal(again.floating, s.floating)
     assert np.allclose(again.errors[s.floating], r["errors"][s.floating], rtol=1e-15)
     s.close(), again.close()
+
+
+def test_toymc_scale_scales_noise_and_chi2(built, golden_tree):
+    """toymc-scale (src/baofit.cc:294, CorrelationAnalyzer.cc:349-357): the toy prototype's covariance times the factor. The same
+    deviates give sqrt(scale) times the noise, so with no priors the fitted offsets from the truth scale by sqrt(scale) to first
+    order and the chi2 values (against the scaled covariance) keep their distribution."""
+    text, base = ini(golden_tree, "rmu_to_bao.ini")
+    tmp = os.path.join(golden_tree, "data", "rmu_cov2")
+    with open(tmp + ".data", "w") as f:
+        f.write(open(os.path.join(golden_tree, "demo", "rmu.data")).read())
+    with open(tmp + ".cov", "w") as f:
+        for i in range(800):
+            f.write("%d %d 1e-11\n" % (i, i))
+    text = text.replace("load-icov = yes", "").replace("data = ../demo/rmu", "data = ../data/rmu_cov2")
+    a = H.Session(text, base).toymc(0, 8, seed=3)
+    b = H.Session(text + "\ntoymc-scale = 4\n", base).toymc(0, 8, seed=3)
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    assert np.allclose(b["chi2"], a["chi2"], rtol=2e-2)          # same deviates, covariance and noise scaled together
+    s = H.Session(text, base)
+    fl = s.floating
+    da, db = a["fitted"][:, fl] - s.values[fl], b["fitted"][:, fl] - s.values[fl]
+    assert np.allclose(db, 2 * da, rtol=0.25, atol=0.1 * np.abs(da).max())  # first order only: the model is not linear
+    assert abs(np.median(db[np.abs(da) > 1e-3] / da[np.abs(da) > 1e-3]) - 2) < 0.15
+    with pytest.raises(H.HostError, match="varianceScale > 0"):
+        H.Session(text + "\ntoymc-scale = 0\n", base)
