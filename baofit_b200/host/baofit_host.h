@@ -496,7 +496,11 @@ public:
     void doToyMCSampling(long first, long count, unsigned long long seed, std::vector<std::vector<double>> &fitted,
                          std::vector<double> &chi2, std::vector<int> &status, std::string const &toymcConfig = "",
                          std::string const &refitConfig = "", std::vector<std::vector<double>> *refitted = nullptr,
-                         std::vector<double> *rechi2 = nullptr, std::vector<int> *restatus = nullptr) const;
+                         std::vector<double> *rechi2 = nullptr, std::vector<int> *restatus = nullptr,
+                         likely::FitParameters const *truthBase = nullptr, std::string const &saveFirstName = "") const;
+    // truthBase: the parameters the truth vector is predicted from before toymcConfig is applied -- the reference takes those of the
+    // fit of the combined sample (fmin, CorrelationAnalyzer.cc:361-369); null: the model's initial parameters (what fmin is with
+    // no-initial-fit). saveFirstName ("toymc-save", :281-286): the first realisation of the study (toy 0) in saveData's format.
     // CorrelationAnalyzer.cc:301-335 (doJackknifeAnalysis, doBootstrapAnalysis, fitEach) + the loop of
     // doSamplingAnalysis :452-532: every sample is a new data vector AND covariance, refitted from the model's
     // initial parameters. kind = "jackknife" (n = observations dropped per sample), "bootstrap" (n = trials,

@@ -20,6 +20,7 @@ struct bfh_session {
     std::shared_ptr<CorrelationFitter> fitter;
     std::shared_ptr<CorrelationAnalyzer> analyzer;
     likely::FunctionMinimumPtr lastFit;  // of the latest bfh_fit without a config script (the "initial fit" of src/baofit.cc:646-660)
+    std::string toymcSaveName;           // bfh_set_toymc_save
 };
 
 static thread_local std::string g_herr;
@@ -355,10 +356,19 @@ extern "C" int bfh_toymc_refit(bfh_session *s, long first, long count, unsigned 
     std::vector<double> c, c2;
     std::vector<int> st, st2;
     std::string refit = refit_config ? refit_config : "";
-    s->analyzer->doToyMCSampling(first, count, seed, fit, c, st, toymc_config ? toymc_config : "", refit, &fit2, &c2, &st2);
+    // the truth vector starts from the fit of the combined sample when the session has made one (src/baofit.cc:646-660,788-794)
+    s->analyzer->doToyMCSampling(first, count, seed, fit, c, st, toymc_config ? toymc_config : "", refit, &fit2, &c2, &st2,
+                                 s->lastFit ? &s->lastFit->parameters : nullptr, s->toymcSaveName);
     int npar = s->model->getNParameters();
     copyOut(npar, count, fit, c, st, fitted, chi2, status);
     if (!refit.empty()) copyOut(npar, count, fit2, c2, st2, refitted, rechi2, restatus);
+    BFH_CATCH
+}
+
+extern "C" int bfh_set_toymc_save(bfh_session *s, const char *path) {
+    BFH_TRY
+    if (!s) throw RuntimeError("bfh_set_toymc_save: null session");
+    s->toymcSaveName = path ? path : "";
     BFH_CATCH
 }
 

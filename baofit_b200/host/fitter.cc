@@ -714,15 +714,16 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
                                           std::vector<std::vector<double>> &fitted, std::vector<double> &chi2,
                                           std::vector<int> &status, std::string const &toymcConfig, std::string const &refitConfig,
                                           std::vector<std::vector<double>> *refitted, std::vector<double> *rechi2,
-                                          std::vector<int> *restatus) const {
+                                          std::vector<int> *restatus, likely::FitParameters const *truthBase,
+                                          std::string const &saveFirstName) const {
     if (!_data || !_model) throw RuntimeError("CorrelationAnalyzer::doToyMCSampling: need data and a model.");
     if (!refitConfig.empty() && !(refitted && rechi2 && restatus))
         throw RuntimeError("CorrelationAnalyzer::doSamplingAnalysis: inconsistent refit parameters.");
     const bool verbose = std::getenv("BAOFIT_VERBOSE_FITS") != nullptr;
     double tStart = nowSeconds();
     CorrelationFitter fitter(_data, _model, _covSampleSize);
-    // truth = model prediction at the (optionally reconfigured) initial parameters (:362-369)
-    likely::FitParameters truthParams = _model->getFitParameters();
+    // truth = model prediction at the (optionally reconfigured) parameters of the fit of the combined sample (:361-369)
+    likely::FitParameters truthParams = truthBase ? *truthBase : _model->getFitParameters();
     if (!toymcConfig.empty()) likely::modifyFitParameters(truthParams, toymcConfig);
     likely::Parameters tp;
     for (auto const &p : truthParams) tp.push_back(p.value);
@@ -734,6 +735,19 @@ void CorrelationAnalyzer::doToyMCSampling(long first, long count, unsigned long 
     bf_toys *toys = nullptr;
     check(bf_toys_create(deviceContext(), _data->deviceData(grid), truth.data(), seed, first, (int)count, std::sqrt(_toyScale), &toys), "bf_toys_create");
     std::shared_ptr<bf_toys> guard(toys, [](bf_toys *t) { bf_toys_destroy(t); });
+    if (!saveFirstName.empty() && first == 0 && count > 0) {
+        // the first realisation of the study in saveData's format ("<index> <value>" over the kept bins)
+        const int n = (int)_data->keptIndices().size();
+        std::vector<double> table((size_t)count * n);
+        check(bf_toys_download(deviceContext(), toys, table.data()), "bf_toys_download");
+        std::ofstream out(saveFirstName.c_str());
+        if (!out.good()) throw RuntimeError("CorrelationAnalyzer::doToyMCSampling: unable to open " + saveFirstName);
+        char buf[64];
+        for (int i = 0; i < n; ++i) {
+            std::snprintf(buf, sizeof(buf), "%d %.17g", _data->keptIndices()[i], table[i]);
+            out << buf << std::endl;
+        }
+    }
     double tToys = nowSeconds();
     if (_toyScale != 1) fitter.scaleCovariance(_toyScale);  // after the truth prediction; applies to the LM and Newton drivers alike
     const double cs = fitter.icovScale() / fitter.errorScale(), ps = 1.0 / fitter.errorScale();

@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs", "bfh_bootstrap_covariance"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs", "bfh_bootstrap_covariance", "bfh_set_toymc_save"]
 
 
 def lib():
@@ -59,6 +59,7 @@ def lib():
         L.bfh_save_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.bfh_write_fit_outputs.argtypes = [C.c_void_p, C.c_char_p]
         L.bfh_bootstrap_covariance.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.bfh_set_toymc_save.argtypes = [C.c_void_p, C.c_char_p]
         L.bfh_compare_each.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_symmetric_eigenmodes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bfh_nobservations.argtypes = [C.c_void_p]
@@ -215,6 +216,10 @@ class Session:
         st, best = np.zeros(n, dtype=np.int32), np.zeros(self.npar + 1)
         _check(lib().bfh_parameter_scan(self.h, first, count, _p(chi2), _p(pts), _p(st), _p(best)))
         return dict(chi2=chi2, points=pts, status=st, best_values=best[:-1], best_chi2=best[-1])
+
+    def set_toymc_save(self, path):
+        """toymc-save: the first realisation of the next study that starts at toy 0 goes to `path` (save-data's format)."""
+        _check(lib().bfh_set_toymc_save(self.h, path.encode() if path else None))
 
     def toymc(self, first, count, seed=1966, toymc_config="", refit_config=""):
         fitted, chi2 = np.zeros((count, self.npar)), np.zeros(count)

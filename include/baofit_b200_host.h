@@ -66,9 +66,15 @@ int bfh_write_fit_outputs(bfh_session *s, const char *prefix);
 int bfh_scan_size(const bfh_session *s, long *total);
 int bfh_parameter_scan(bfh_session *s, long first, long count, double *chi2, double *points, int *status,
                        double *best);
-/* CorrelationAnalyzer::doToyMCSampling for toys [first, first+count): fitted[count*npar], chi2, status */
+/* CorrelationAnalyzer::doToyMCSampling for toys [first, first+count): fitted[count*npar], chi2, status. As in the reference
+ * (baofit/CorrelationAnalyzer.cc:361-369) the truth vector is predicted from the parameters of the fit of the combined sample when the
+ * session has made one (bfh_fit without a config script), otherwise from the model's initial parameters (no-initial-fit); toymc-config
+ * is applied on top. The ini option toymc-scale scales the covariance of the toy prototype. */
 int bfh_toymc(bfh_session *s, long first, long count, unsigned long long seed, double *fitted, double *chi2,
               int *status);
+/* toymc-save (baofit/CorrelationAnalyzer.cc:281-286): the first realisation of the next toy study that starts at toy 0 is written to
+ * `path` in save-data's format; NULL or "" switches it off. */
+int bfh_set_toymc_save(bfh_session *s, const char *path);
 /* Resampling analyses over the individual observations of a plateroot/platelist session
  * (CorrelationAnalyzer::doJackknifeAnalysis / doBootstrapAnalysis / fitEach, CorrelationAnalyzer.cc:301-335, through
  * likely::BinnedDataResampler). kind = "jackknife" (n = observations dropped per sample), "bootstrap" (n = trials,

@@ -118,8 +118,10 @@ def test_toymc_is_shard_independent_and_unbiased(built, golden_tree):
     assert len(open(path).read().splitlines()) == 5 and open(path).readline().split()[1] == "0"
     # refit pass (refit-config): every toy fitted again with beta fixed at its start value; same toys, so the first
     # pass is unchanged and the constrained chi2 is never below the free one
+    # (the session has fitted the combined sample by now, so the truth vector is the best-fit prediction from here on)
+    a2 = s.toymc(0, 12, seed=7)
     rf = s.toymc(0, 12, seed=7, refit_config="fix[beta]=1.4")
-    assert np.array_equal(rf["fitted"], a["fitted"]) and np.all(rf["restatus"] == 0)
+    assert np.array_equal(rf["fitted"], a2["fitted"]) and np.all(rf["restatus"] == 0)
     assert np.all(rf["refitted"][:, ib] == 1.4) and np.all(rf["rechi2"] >= rf["chi2"] - 1e-6)
     best2 = s.fit("fix[beta]=1.4")
     s.write_samples(path, best["values"], best["errors"], 2 * best["fval"], rf["fitted"], rf["chi2"], nsave=3, zsave=2.25,
@@ -243,3 +245,36 @@ def test_toymc_scale_scales_noise_and_chi2(built, golden_tree):
     assert abs(np.median(db[np.abs(da) > 1e-3] / da[np.abs(da) > 1e-3]) - 2) < 0.15
     with pytest.raises(H.HostError, match="varianceScale > 0"):
         H.Session(text + "\ntoymc-scale = 0\n", base)
+
+
+def test_toymc_truth_follows_the_combined_fit_and_first_toy_is_saved(built, golden_tree, tmp_path):
+    """The truth vector of a toy study is the prediction at the parameters of the fit of the combined sample
+    (CorrelationAnalyzer.cc:361-369), or at the initial parameters when no fit has been made (no-initial-fit); toymc-save
+    writes the first realisation."""
+    text, base = ini(golden_tree, "rmu_to_bao.ini")
+    tmp = os.path.join(golden_tree, "data", "rmu_cov3")
+    rng = np.random.Generator(np.random.PCG64(12))
+    rows = [l.split() for l in open(os.path.join(golden_tree, "demo", "rmu.data"))]
+    with open(tmp + ".data", "w") as f:   # data moved away from the truth of the recipe so that the fit differs from the start values
+        for i, v in rows:
+            f.write("%s %.17g\n" % (i, 1.05 * float(v)))
+    with open(tmp + ".cov", "w") as f:
+        for i in range(800):
+            f.write("%d %d 1e-11\n" % (i, i))
+    text = text.replace("load-icov = yes", "").replace("data = ../demo/rmu", "data = ../data/rmu_cov3")
+    s = H.Session(text, base)
+    path = str(tmp_path / "toymcsave.data")
+    s.set_toymc_save(path)
+    before = s.toymc(0, 6, seed=4)
+    saved0 = np.loadtxt(path)
+    assert np.array_equal(saved0[:, 0].astype(int), s.kept_indices())
+    pred0 = s.predict(s.values[None, :])[:, 0]
+    assert np.max(np.abs(saved0[:, 1] - pred0)) < 8 * np.sqrt(1e-11)          # truth at the start values + noise of sigma 1e-5.5
+    best = s.fit()
+    assert np.max(np.abs(best["values"] - s.values)) > 1e-3
+    after = s.toymc(0, 6, seed=4)
+    saved1 = np.loadtxt(path)
+    pred1 = s.predict(best["values"][None, :])[:, 0]
+    assert np.max(np.abs((saved1[:, 1] - pred1) - (saved0[:, 1] - pred0))) < 1e-12   # same deviates on the new truth
+    fl = s.floating
+    assert np.max(np.abs(after["fitted"][:, fl].mean(axis=0) - best["values"][fl])) < np.max(np.abs(before["fitted"][:, fl].mean(axis=0) - best["values"][fl]))
