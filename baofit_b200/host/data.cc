@@ -1,6 +1,7 @@
 // Host-side binned data: grid, loaders, final cuts (bit-exact restatement of the reference's
 // comparisons), device upload.
 #include <cmath>
+#include <omp.h>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -236,16 +237,19 @@ void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &valu
         for (int i = k + 1; i < n; ++i) vv += v[i] * v[i];
         const double b = 2.0 / vv;
         // p = b A22 v, w = p - (b/2)(v.p) v, A22 -= v w^T + w v^T (both triangles are kept: rows stay contiguous)
-        double vp = 0;
+        const bool par = n - k >= 640;  // rows are independent in both passes; the sums keep their order within a row
+#pragma omp parallel for schedule(static) if (par)
         for (int i = k + 1; i < n; ++i) {
             const double *row = &a[(size_t)i * n];
             double sum = 0;
             for (int j = k + 1; j < n; ++j) sum += row[j] * v[j];
             pv[i] = b * sum;
-            vp += v[i] * pv[i];
         }
+        double vp = 0;
+        for (int i = k + 1; i < n; ++i) vp += v[i] * pv[i];
         const double half = 0.5 * b * vp;
         for (int i = k + 1; i < n; ++i) pv[i] -= half * v[i];
+#pragma omp parallel for schedule(static) if (par)
         for (int i = k + 1; i < n; ++i) {
             double *row = &a[(size_t)i * n];
             const double vi = v[i], wi = pv[i];
@@ -263,16 +267,21 @@ void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &valu
     for (int k = n - 3; k >= 0; --k) {
         if (beta[k] == 0.0) continue;
         // Q <- H_k Q on rows k+1.. of Q, i.e. on columns k+1.. of Z: Z[r][:] -= beta (Z[r][:].v) v for every row r > k
+        for (int i = k + 1; i < n; ++i) v[i] = A(i, k);  // contiguous copy of the reflection vector
+#pragma omp parallel for schedule(static) if (n - k >= 640)
         for (int r = k + 1; r < n; ++r) {
             double *row = &z[(size_t)r * n];
             double dot = 0;
-            for (int i = k + 1; i < n; ++i) dot += row[i] * A(i, k);
+            for (int i = k + 1; i < n; ++i) dot += row[i] * v[i];
             dot *= beta[k];
-            for (int i = k + 1; i < n; ++i) row[i] -= dot * A(i, k);
+            for (int i = k + 1; i < n; ++i) row[i] -= dot * v[i];
         }
     }
     // implicit-shift QL on (d, e)
     const double eps = 2.220446049250313e-16;
+    struct Rotation { int i; double c, s; };
+    std::vector<Rotation> rot;
+    rot.reserve(n);
     for (int l = 0; l < n; ++l) {
         for (int iter = 0;; ++iter) {
             int m = l;
@@ -285,6 +294,7 @@ void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &valu
             g = d[m] - d[l] + e[l] / (g + (g >= 0 ? r : -r));
             double sn = 1.0, cs = 1.0, p = 0.0;
             int i = m - 1;
+            rot.clear();
             for (; i >= l; --i) {
                 double f = sn * e[i], bb = cs * e[i];
                 r = std::hypot(f, g);
@@ -297,11 +307,24 @@ void symmetricEigenModes(int n, std::vector<double> a, std::vector<double> &valu
                 p = sn * r;
                 d[i + 1] = g + p;
                 g = cs * r - bb;
-                double *zi = &z[(size_t)i * n], *zi1 = &z[(size_t)(i + 1) * n];
-                for (int q = 0; q < n; ++q) {
-                    const double t = zi1[q];
-                    zi1[q] = sn * zi[q] + cs * t;
-                    zi[q] = cs * zi[q] - sn * t;
+                rot.push_back({i, cs, sn});
+            }
+            // the rotations of this sweep mix rows (i, i+1) of Z in sequence; column slices are independent of each other
+            {
+                const int nrot = (int)rot.size();
+                const int slices = (n >= 768 && nrot >= 16) ? std::max(1, std::min(omp_get_max_threads(), n / 64)) : 1;
+#pragma omp parallel for schedule(static) num_threads(slices) if (slices > 1)
+                for (int sl = 0; sl < slices; ++sl) {
+                    const int q0 = (int)((long long)n * sl / slices), q1 = (int)((long long)n * (sl + 1) / slices);
+                    for (int k = 0; k < nrot; ++k) {
+                        double *zi = &z[(size_t)rot[k].i * n], *zi1 = zi + n;
+                        const double c = rot[k].c, sgn = rot[k].s;
+                        for (int q = q0; q < q1; ++q) {
+                            const double t = zi1[q];
+                            zi1[q] = sgn * zi[q] + c * t;
+                            zi[q] = c * zi[q] - sgn * t;
+                        }
+                    }
                 }
             }
             if (r == 0.0 && i >= l) continue;
