@@ -402,6 +402,26 @@ extern "C" int bfh_bootstrap_covariance(bfh_session *s, int trials, unsigned lon
     BFH_CATCH
 }
 
+// CorrelationAnalyzer::printScaleZEff (CorrelationAnalyzer.cc:127-167): for a fit that floats a BAO scale and gamma-scale, the
+// redshift at which scale(z) = scale ((1+z)/(1+zref))^gamma is best determined, the scale there and its error.
+extern "C" int bfh_scale_zeff(double scale, double dscale, double gamma, double dgamma, double cov_scale_gamma, double zref,
+                              double *zeff, double *scale_eff, double *dscale_eff) {
+    BFH_TRY
+    if (!(dscale > 0) || !(dgamma > 0) || scale == 0 || gamma == 0) throw RuntimeError("bfh_scale_zeff: scale and gamma-scale must both float (non-zero values, positive errors)");
+    const double rho = cov_scale_gamma / (dscale * dgamma);
+    const double a = dscale / (scale * dgamma), b = 1 / (2 * gamma);
+    const double disc = b * b - a * a * (1 - rho * rho);
+    if (disc < 0) throw RuntimeError("bfh_scale_zeff: no real solution for zeff");
+    const double logz = -b - a * rho + std::sqrt(disc);
+    const double zEff = std::exp(logz) * (1 + zref) - 1;
+    const double ratio = (1 + zEff) / (1 + zref), evol = std::pow(ratio, gamma), logRatio = std::log(ratio);
+    const double tmp = scale * dgamma * logRatio;
+    if (zeff) *zeff = zEff;
+    if (scale_eff) *scale_eff = scale * evol;
+    if (dscale_eff) *dscale_eff = evol * std::sqrt(dscale * dscale + 2 * rho * scale * dscale * dgamma * logRatio + tmp * tmp);
+    BFH_CATCH
+}
+
 extern "C" double bfh_gamma_q(double a, double x) {
     try { return gammaQ(a, x); } catch (std::exception const &e) { g_herr = e.what(); return -1.0; }
 }

@@ -14,7 +14,7 @@ HOST_EXPORTS = ["bfh_last_error", "bfh_set_device", "bfh_set_num_threads", "bfh_
                 "bfh_predict_batch", "bfh_fit", "bfh_scan_size", "bfh_parameter_scan", "bfh_toymc", "bfh_minimize",
                 "bfh_lm_minimize", "bfh_dump_residuals", "bfh_dump_model", "bfh_mcmc", "bfh_nobservations",
                 "bfh_resampling_size", "bfh_bootstrap_counts", "bfh_resample_data", "bfh_resample_fit", "bfh_write_samples",
-                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs", "bfh_bootstrap_covariance", "bfh_set_toymc_save"]
+                "bfh_toymc_refit", "bfh_resample_refit", "bfh_write_samples_refit", "bfh_save_data", "bfh_symmetric_eigenmodes", "bfh_compare_each", "bfh_gamma_q", "bfh_write_fit_outputs", "bfh_bootstrap_covariance", "bfh_set_toymc_save", "bfh_scale_zeff"]
 
 
 def lib():
@@ -95,6 +95,15 @@ def set_device(device):
 def set_num_threads(n=0):
     """Host threads of the per-fit linear algebra (OpenMP); n <= 0 only queries. Returns the number in use."""
     return int(lib().bfh_set_num_threads(int(n)))
+
+
+def scale_zeff(scale, dscale, gamma, dgamma, cov_scale_gamma, zref):
+    """CorrelationAnalyzer::printScaleZEff: (zeff, scale at zeff, its error) from the fit results of a BAO scale and gamma-scale."""
+    L = lib()
+    L.bfh_scale_zeff.argtypes = [C.c_double] * 6 + [C.POINTER(C.c_double)] * 3
+    z, s, ds = C.c_double(), C.c_double(), C.c_double()
+    _check(L.bfh_scale_zeff(scale, dscale, gamma, dgamma, cov_scale_gamma, zref, C.byref(z), C.byref(s), C.byref(ds)))
+    return z.value, s.value, ds.value
 
 
 def symmetric_eigenmodes(matrix):

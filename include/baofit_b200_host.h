@@ -111,6 +111,10 @@ int bfh_compare_each(bfh_session *s, const char *path, int finalized, double *pr
  * With icov_path the inverse is written in the loader's format when the estimate is positive definite (*posdef). Host only. */
 int bfh_bootstrap_covariance(bfh_session *s, int trials, unsigned long long seed, const char *icov_path, double *cov, int cov_order,
                              int *bins, int *posdef);
+/* CorrelationAnalyzer::printScaleZEff (baofit/CorrelationAnalyzer.cc:127-167) as a function of the fit results of a BAO scale parameter
+ * and of gamma-scale (values, errors, their covariance): zeff, the scale evolved to zeff and its error. */
+int bfh_scale_zeff(double scale, double dscale, double gamma, double dgamma, double cov_scale_gamma, double zref,
+                   double *zeff, double *scale_eff, double *dscale_eff);
 /* regularised upper incomplete gamma function Q(a, x) used for that probability (boost::math::gamma_p in the reference); -1 on bad arguments */
 double bfh_gamma_q(double a, double x);
 /* Eigenmodes of a dense symmetric n x n matrix, the decomposition behind project-modes-keep (src/baofit.cc:194,597-603;

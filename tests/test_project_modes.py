@@ -88,3 +88,27 @@ def test_fix_mode_scales_option(built, golden_tree, tmp_path):
     with pytest.raises(H.HostError):
         H.Session(text + "\nfix-mode-scales = %s\n" % (tmp_path / "bad.dat"), base)
     plain.close(), fixed.close()
+
+
+def test_scale_zeff_is_where_the_evolved_scale_is_best_determined(built):
+    """printScaleZEff (CorrelationAnalyzer.cc:127-167): scale(z) = scale ((1+z)/(1+zref))^gamma has, by error propagation with the
+    (scale, gamma) covariance, an error that is stationary at zeff; the returned scale and error are the propagated ones."""
+    zref = 2.25
+    for scale, ds, gamma, dg, rho in ((1.01, 0.02, 0.6, 0.5, -0.4), (0.98, 0.03, -1.2, 0.8, 0.3), (1.0, 0.015, 2.0, 1.5, 0.0)):
+        zeff, se, dse = H.scale_zeff(scale, ds, gamma, dg, rho * ds * dg, zref)
+
+        def propagated(z):
+            lr = np.log((1 + z) / (1 + zref))
+            ev = ((1 + z) / (1 + zref)) ** gamma
+            return scale * ev, ev * np.sqrt(ds ** 2 + 2 * rho * scale * ds * dg * lr + (scale * dg * lr) ** 2)
+        s0, e0 = propagated(zeff)
+        assert abs(se - s0) < 1e-14 and abs(dse - e0) < 1e-14
+        # zeff solves V' + 2 gamma V = 0 for V = (error / evolution)^2 as a function of x = log((1+z)/(1+zref)): the ABSOLUTE error of the
+        # evolved scale is stationary there
+        err = lambda z: propagated(z)[1]
+        h = 1e-4
+        slope = (err(zeff + h) - err(zeff - h)) / (2 * h)
+        typical = abs(err(zeff + 0.3) - err(zeff)) / 0.3
+        assert abs(slope) < 1e-6 * max(typical, 1e-6) + 1e-10, (slope, typical)
+    with pytest.raises(H.HostError):
+        H.scale_zeff(1.0, 0.0, 0.5, 0.5, 0.0, zref)
